@@ -1,0 +1,163 @@
+// K3 (first version): softmax(Q K^T * scale) V with an online (flash-style) softmax, bf16 in / bf16 out, fp32 math.
+// One thread owns one query row; the K/V rows of the (batch, head) are staged through shared memory in chunks and
+// read by all threads as broadcasts.  With the reference's head_dim = 8 (64 heads at C = 512,
+// src/nn/blocks/legacy_unet.py:32) the op is exp-bound, not MMA-bound, so this CUDA-core
+// formulation is the baseline; a tensor-core variant is future work.
+// Replaces F.scaled_dot_product_attention (src/nn/blocks/attention.py:41-44).
+#include "common.cuh"
+
+namespace fm {
+
+constexpr int kAttThreads = 128;
+
+template <int HD>
+__global__ void __launch_bounds__(kAttThreads) attention_kernel(const __nv_bfloat16* __restrict__ q,
+                                                               const __nv_bfloat16* __restrict__ k,
+                                                               const __nv_bfloat16* __restrict__ v,
+                                                               __nv_bfloat16* __restrict__ out, int Tq, int Tk,
+                                                               int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
+                                                               int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh,
+                                                               int64_t o_st, float scale_log2e, int kchunk) {
+  extern __shared__ uint4 smem_u4[];
+  constexpr int V8 = HD / 8;                  // 16-byte vectors per row
+  uint4* sk = smem_u4;                        // [kchunk][V8]
+  uint4* sv = smem_u4 + (size_t)kchunk * V8;  // [kchunk][V8]
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int t = blockIdx.x * kAttThreads + threadIdx.x;
+  const bool active = t < Tq;
+
+  float qr[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) { qr[d] = 0.f; acc[d] = 0.f; }
+  if (active) {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + b * q_sb + h * q_sh + (int64_t)t * q_st);
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+      const uint4 u = qp[i];
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      qr[i * 8 + 0] = f0.x * scale_log2e; qr[i * 8 + 1] = f0.y * scale_log2e;
+      qr[i * 8 + 2] = f1.x * scale_log2e; qr[i * 8 + 3] = f1.y * scale_log2e;
+      qr[i * 8 + 4] = f2.x * scale_log2e; qr[i * 8 + 5] = f2.y * scale_log2e;
+      qr[i * 8 + 6] = f3.x * scale_log2e; qr[i * 8 + 7] = f3.y * scale_log2e;
+    }
+  }
+  float m = -INFINITY, l = 0.f;
+  const __nv_bfloat16* kb = k + b * kv_sb + h * kv_sh;
+  const __nv_bfloat16* vb = v + b * kv_sb + h * kv_sh;
+
+  for (int j0 = 0; j0 < Tk; j0 += kchunk) {
+    const int nj = min(kchunk, Tk - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nj * V8; i += kAttThreads) {
+      const int j = i / V8, c = i - j * V8;
+      sk[i] = reinterpret_cast<const uint4*>(kb + (int64_t)(j0 + j) * kv_st)[c];
+      sv[i] = reinterpret_cast<const uint4*>(vb + (int64_t)(j0 + j) * kv_st)[c];
+    }
+    __syncthreads();
+    for (int j = 0; j < nj; j += 4) {
+      float s[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float sacc = 0.f;
+        if (j + u < nj) {
+#pragma unroll
+          for (int i = 0; i < V8; ++i) {
+            const uint4 kk = sk[(j + u) * V8 + i];
+            const float2 f0 = unpack_bf16x2(kk.x), f1 = unpack_bf16x2(kk.y), f2 = unpack_bf16x2(kk.z),
+                         f3 = unpack_bf16x2(kk.w);
+            sacc = fmaf(qr[i * 8 + 0], f0.x, sacc); sacc = fmaf(qr[i * 8 + 1], f0.y, sacc);
+            sacc = fmaf(qr[i * 8 + 2], f1.x, sacc); sacc = fmaf(qr[i * 8 + 3], f1.y, sacc);
+            sacc = fmaf(qr[i * 8 + 4], f2.x, sacc); sacc = fmaf(qr[i * 8 + 5], f2.y, sacc);
+            sacc = fmaf(qr[i * 8 + 6], f3.x, sacc); sacc = fmaf(qr[i * 8 + 7], f3.y, sacc);
+          }
+        } else {
+          sacc = -INFINITY;
+        }
+        s[u] = sacc;
+      }
+      const float mx = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), m);
+      const float corr = exp2f(m - mx);
+      float pr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pr[u] = exp2f(s[u] - mx);
+      l = l * corr + (pr[0] + pr[1]) + (pr[2] + pr[3]);
+      m = mx;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j + u < nj) {
+#pragma unroll
+          for (int i = 0; i < V8; ++i) {
+            const uint4 vv = sv[(j + u) * V8 + i];
+            const float2 f0 = unpack_bf16x2(vv.x), f1 = unpack_bf16x2(vv.y), f2 = unpack_bf16x2(vv.z),
+                         f3 = unpack_bf16x2(vv.w);
+            acc[i * 8 + 0] = fmaf(pr[u], f0.x, acc[i * 8 + 0]); acc[i * 8 + 1] = fmaf(pr[u], f0.y, acc[i * 8 + 1]);
+            acc[i * 8 + 2] = fmaf(pr[u], f1.x, acc[i * 8 + 2]); acc[i * 8 + 3] = fmaf(pr[u], f1.y, acc[i * 8 + 3]);
+            acc[i * 8 + 4] = fmaf(pr[u], f2.x, acc[i * 8 + 4]); acc[i * 8 + 5] = fmaf(pr[u], f2.y, acc[i * 8 + 5]);
+            acc[i * 8 + 6] = fmaf(pr[u], f3.x, acc[i * 8 + 6]); acc[i * 8 + 7] = fmaf(pr[u], f3.y, acc[i * 8 + 7]);
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    const float inv = 1.0f / l;
+    uint4* op = reinterpret_cast<uint4*>(out + b * o_sb + h * o_sh + (int64_t)t * o_st);
+#pragma unroll
+    for (int i = 0; i < V8; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[i * 8 + 0] * inv, acc[i * 8 + 1] * inv);
+      o.y = pack_bf16x2(acc[i * 8 + 2] * inv, acc[i * 8 + 3] * inv);
+      o.z = pack_bf16x2(acc[i * 8 + 4] * inv, acc[i * 8 + 5] * inv);
+      o.w = pack_bf16x2(acc[i * 8 + 6] * inv, acc[i * 8 + 7] * inv);
+      op[i] = o;
+    }
+  }
+}
+
+template <int HD>
+static int launch_attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk,
+                            int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb, int64_t kv_sh, int64_t kv_st,
+                            int64_t o_sb, int64_t o_sh, int64_t o_st, float scale, cudaStream_t st) {
+  int kchunk = 8192 / HD;  // 32 KB of K+V per chunk
+  if (kchunk > Tk) kchunk = (Tk + 3) / 4 * 4;
+  const size_t smem = (size_t)kchunk * (HD / 8) * 16 * 2;
+  dim3 grid((Tq + kAttThreads - 1) / kAttThreads, heads, B);
+  attention_kernel<HD><<<grid, kAttThreads, smem, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+      reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Tq, Tk, q_sb, q_sh, q_st,
+      kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale * 1.4426950408889634f, kchunk);
+  FM_LAUNCH_CHECK("attention_kernel");
+  return 0;
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t heads,
+                                 int32_t Tq, int32_t Tk, int32_t head_dim, int64_t q_sb, int64_t q_sh, int64_t q_st,
+                                 int64_t kv_sb, int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st,
+                                 float scale, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(q && k && v && out, "attention: null pointer");
+  FM_REQUIRE(B > 0 && heads > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
+  FM_REQUIRE(heads <= 65535 && B <= 65535, "attention: grid too large");
+  FM_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0,
+             "attention: pointers must be 16B aligned");
+  FM_REQUIRE(((q_sb | q_sh | q_st | kv_sb | kv_sh | kv_st | o_sb | o_sh | o_st) & 7) == 0,
+             "attention: strides must be multiples of 8 elements");
+  cudaStream_t st = (cudaStream_t)stream;
+#define FM_ATT_ARGS q, k, v, out, B, heads, Tq, Tk, q_sb, q_sh, q_st, kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale, st
+  switch (head_dim) {
+    case 8: return launch_attention<8>(FM_ATT_ARGS);
+    case 16: return launch_attention<16>(FM_ATT_ARGS);
+    case 32: return launch_attention<32>(FM_ATT_ARGS);
+    case 64: return launch_attention<64>(FM_ATT_ARGS);
+    default:
+      set_error("attention: head_dim=%d unsupported (8, 16, 32, 64)", head_dim);
+      return FM_ERR_UNSUPPORTED;
+  }
+#undef FM_ATT_ARGS
+}

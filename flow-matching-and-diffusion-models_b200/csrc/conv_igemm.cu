@@ -1,0 +1,442 @@
+// K1: conv2d (3x3 s1/s2, 1x1) as an implicit GEMM on tcgen05 tensor cores.
+//
+//   M = B*Ho*Wo output pixels, N = Cout, K = sum over segments of taps*C.
+//   A (activations, NHWC bf16) is never im2col'ed in memory: for every (tap, 64-channel block) one TMA tiled load
+//   of the box (64 ch, Wt, Ht, Nt) shifted by (kw-pad, kh-pad) lands a 128x64 K-major, 128B-swizzled operand tile
+//   in shared memory; TMA's out-of-bounds zero fill implements the conv padding, the ragged image edge and the
+//   channel tail.  Stride-2 convs use the tensor map's element strides.  The skip-connection torch.cat
+//   (legacy_unet.py:150) is a second K segment (another tensor map), never a copy.
+//   B (weights) is a pre-packed [Cout][Ktot] K-major bf16 matrix, TMA-loaded as (64, BLOCK_N) boxes.
+//   D accumulates in TMEM (fp32, 128 lanes x BLOCK_N columns); one elected thread issues tcgen05.mma.
+//   Epilogue warps read TMEM with tcgen05.ld, add bias / per-sample time-embedding vector / residual, optionally
+//   accumulate GroupNorm partial sums for the consumer norm, convert to bf16, stage the tile in 128B-swizzled
+//   shared memory and write it with one TMA store per 64-channel slab (the store clips ragged tiles).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (warp w owns TMEM lanes 32*(w%4)..+31).  Reference op replaced: nn.Conv2d via ConvND.forward
+// (src/nn/ops/convolution.py:53-54) and the adds around it in ResBlockND.forward (src/nn/blocks/residual.py:97-120).
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fm {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                      // 64 bf16 = 128 B = one swizzle row
+constexpr int kABytes = kTileM * kBlockK * 2;    // 16 KB
+constexpr int kConvThreads = 192;
+
+struct alignas(64) ConvKernelParams {
+  CUtensorMap src[FM_CONV_MAX_SEG];
+  CUtensorMap wgt;
+  CUtensorMap out;
+  int nseg;
+  int seg_c[FM_CONV_MAX_SEG];       // channels per segment
+  int seg_taps[FM_CONV_MAX_SEG];    // 1 or 9
+  int seg_koff[FM_CONV_MAX_SEG];    // K offset of the segment in the packed weight
+  int Wt, Ht, Nt;                   // M-tile box, Wt*Ht*Nt == 128
+  int tiles_w, tiles_h;             // tiles per image row / column
+  int stride;
+  int B, Ho, Wo, Cout;
+  const float* bias;
+  const float* addvec;
+  int addvec_stride;
+  const __nv_bfloat16* residual;
+  float* gn_stats;
+  int gn_groups;
+  int num_k_blocks;
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kOutBytes = kTileM * BLOCK_N * 2;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + (kPipeBytes > kOutBytes ? kPipeBytes : kOutBytes) + 256;
+  static_assert(kOutBytes <= kPipeBytes, "output staging reuses the pipeline buffers");
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + Cfg::kStages * kABytes;
+  const uint32_t bar_base = smem_base + Cfg::kPipeBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full; then the TMEM base address word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 1);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kPipeBytes + 8 * (2 * Cfg::kStages + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates ----
+  const int tiles_per_img_group = p.tiles_w * p.tiles_h;
+  const int m_tile = blockIdx.x;
+  const int tn = m_tile / tiles_per_img_group;
+  const int rem = m_tile - tn * tiles_per_img_group;
+  const int th = rem / p.tiles_w;
+  const int tw = rem - th * p.tiles_w;
+  const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt;
+  const int ncol0 = blockIdx.y * BLOCK_N;
+  const int nk = p.num_k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.src[s]);
+    tma_prefetch_desc(&p.wgt);
+    tma_prefetch_desc(&p.out);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<BLOCK_N>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int taps = p.seg_taps[s];
+        const int C = p.seg_c[s];
+        const int cblocks = (C + kBlockK - 1) / kBlockK;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dh = (taps == 9) ? (tap / 3 - 1) : 0;
+          const int dw = (taps == 9) ? (tap % 3 - 1) : 0;
+          for (int cb = 0; cb < cblocks; ++cb, ++it) {
+            const int stage = it % Cfg::kStages;
+            const uint32_t phase = (it / Cfg::kStages) & 1;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_4d(&p.src[s], full_bar(stage), smem_a0 + stage * kABytes, cb * kBlockK,
+                        w0 * p.stride + dw, h0 * p.stride + dh, n0);
+            tma_load_2d(&p.wgt, full_bar(stage), smem_b0 + stage * Cfg::kBBytes,
+                        p.seg_koff[s] + tap * C + cb * kBlockK, ncol0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, BLOCK_N);
+    for (int it = 0; it < nk; ++it) {
+      const int stage = it % Cfg::kStages;
+      const uint32_t phase = (it / Cfg::kStages) & 1;
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_a0 + stage * kABytes;
+        const uint32_t b_addr = smem_b0 + stage * Cfg::kBBytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t da = make_sw128_kmajor_desc(a_addr + k * 32);
+          const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
+          umma_bf16_ss(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));                 // frees the smem stage once these MMAs retire
+        if (it == nk - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;    // row of the 128-row tile == TMEM lane
+    // pixel of this row
+    const int rw = row % p.Wt;
+    const int rh = (row / p.Wt) % p.Ht;
+    const int rn = row / (p.Wt * p.Ht);
+    const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
+    const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
+    const size_t pix = ((size_t)on * p.Ho + oh) * p.Wo + ow;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+    const int cg = (p.gn_stats != nullptr) ? (p.Cout / p.gn_groups) : 0;  // channels per GN group
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const int col0 = ncol0 + c0;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (col0 < p.Cout) {  // Cout % 8 == 0, handle in groups of 8 columns
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int col = col0 + j8 * 8;
+          if (col < p.Cout) {
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
+              v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
+            }
+            if (p.addvec != nullptr && valid) {
+              const float* av = p.addvec + (size_t)on * p.addvec_stride + col;
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(av));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(av + 4));
+              v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
+              v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
+            }
+            if (p.residual != nullptr && valid) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + col);
+              const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
+              const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
+              v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
+              v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
+            }
+          }
+        }
+      }
+      // pack to bf16 and stage (128B-swizzled rows of 64 channels, one 16 KB slab per 64 output channels)
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+
+      if (p.gn_stats != nullptr) {
+        // GroupNorm partial sums of the *rounded* bf16 outputs (what the consumer norm will read).
+        // Rows of one warp may span images only when Nt > 1; handle by per-row accumulation + shuffles
+        // keyed on the (uniform within 32/(Wt*Ht) rows) image index.
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int col = col0 + j8 * 8;
+          // 8 columns -> cg in {4, 8, 16, ...}: if cg==4 two groups, else the 8 columns sit in one group
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(pk[j8 * 4 + j]);
+            const float a = valid ? f.x : 0.f, b = valid ? f.y : 0.f;
+            if (j < 2) { s0 += a + b; q0 += a * a + b * b; } else { s1 += a + b; q1 += a * a + b * b; }
+          }
+          if (col < p.Cout) {
+            if (p.Wt * p.Ht >= 32) {
+              // all 32 rows of this warp belong to one image: reduce across the warp first
+              s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
+              if (lane == 0 && on < p.B) {
+                float* st = p.gn_stats + ((size_t)on * p.gn_groups) * 2;
+                if (cg == 4) {
+                  atomicAdd(st + (col / 4) * 2, s0); atomicAdd(st + (col / 4) * 2 + 1, q0);
+                  atomicAdd(st + (col / 4 + 1) * 2, s1); atomicAdd(st + (col / 4 + 1) * 2 + 1, q1);
+                } else {
+                  atomicAdd(st + (col / cg) * 2, s0 + s1); atomicAdd(st + (col / cg) * 2 + 1, q0 + q1);
+                }
+              }
+            } else if (valid) {
+              float* st = p.gn_stats + ((size_t)on * p.gn_groups) * 2;
+              if (cg == 4) {
+                atomicAdd(st + (col / 4) * 2, s0); atomicAdd(st + (col / 4) * 2 + 1, q0);
+                atomicAdd(st + (col / 4 + 1) * 2, s1); atomicAdd(st + (col / 4 + 1) * 2 + 1, q1);
+              } else {
+                atomicAdd(st + (col / cg) * 2, s0 + s1); atomicAdd(st + (col / cg) * 2 + 1, q0 + q1);
+              }
+            }
+          }
+        }
+      }
+
+      const int slab = c0 >> 6;                 // which 64-channel slab
+      const int chunk0 = (c0 & 63) >> 3;        // first 16-byte chunk within the 128-byte row (0 or 4)
+      uint8_t* rowp = smem_gen + slab * (kTileM * 128) + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int chunk = (chunk0 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+            make_uint4(pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+    }
+    // make the generic-proxy smem writes visible to the async proxy, then one thread issues the TMA stores
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) {
+#pragma unroll
+      for (int slab = 0; slab < BLOCK_N / 64; ++slab) {
+        if (ncol0 + slab * 64 < p.Cout)
+          tma_store_4d(&p.out, smem_base + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
+      }
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BLOCK_N>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || sym == nullptr)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  return fn;
+}
+
+// 4D NHWC activation map: dims (C, W, H, N), box (64, bw, bh, bn), element strides (1, s, s, 1).
+static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bn,
+                          int estride) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return FM_ERR_NO_DEVICE; }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d N=%d box=%d,%d,%d stride=%d) failed: %d", C, W, H, N, bw, bh,
+              bn, estride, (int)r);
+    return (int)r;
+  }
+  return 0;
+}
+
+static int encode_wgt_map(CUtensorMap* m, const void* ptr, int Ktot, int Cout, int block_n) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return FM_ERR_NO_DEVICE; }
+  cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t gstr[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weight K=%d Cout=%d) failed: %d", Ktot, Cout, (int)r);
+    return (int)r;
+  }
+  return 0;
+}
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cudaStream_t st) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_igemm)");
+    attr_set = true;
+  }
+  conv_igemm_kernel<BLOCK_N><<<dim3(m_tiles, n_tiles), kConvThreads, Cfg::kSmemBytes, st>>>(kp);
+  FM_LAUNCH_CHECK("conv_igemm_kernel");
+  return 0;
+}
+
+}  // namespace fm
+
+extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream) {
+  using namespace fm;
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(p != nullptr, "conv: null params");
+  FM_REQUIRE(p->nseg >= 1 && p->nseg <= FM_CONV_MAX_SEG, "conv: nseg=%d out of range", p->nseg);
+  FM_REQUIRE(p->stride == 1 || p->stride == 2, "conv: stride must be 1 or 2 (got %d)", p->stride);
+  FM_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0, "conv: empty input %dx%dx%d", p->B, p->H, p->W);
+  FM_REQUIRE(p->Cout > 0 && p->Cout % 8 == 0, "conv: Cout=%d must be a positive multiple of 8", p->Cout);
+  FM_REQUIRE(p->weight && p->out, "conv: null weight/out");
+  FM_REQUIRE(((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->out & 15) == 0, "conv: weight/out not 16B aligned");
+  const int Ho = (p->H + p->stride - 1) / p->stride, Wo = (p->W + p->stride - 1) / p->stride;
+
+  ConvKernelParams kp;
+  memset(&kp, 0, sizeof(kp));
+  // tile box
+  kp.Wt = pow2_ceil(Wo) < kTileM ? pow2_ceil(Wo) : kTileM;
+  int rest = kTileM / kp.Wt;
+  kp.Ht = pow2_ceil(Ho) < rest ? pow2_ceil(Ho) : rest;
+  kp.Nt = rest / kp.Ht;
+  kp.tiles_w = (Wo + kp.Wt - 1) / kp.Wt;
+  kp.tiles_h = (Ho + kp.Ht - 1) / kp.Ht;
+  const int tiles_n = (p->B + kp.Nt - 1) / kp.Nt;
+  kp.stride = p->stride;
+  kp.B = p->B; kp.Ho = Ho; kp.Wo = Wo; kp.Cout = p->Cout;
+  kp.nseg = p->nseg;
+  int ktot = 0, nk = 0;
+  for (int s = 0; s < p->nseg; ++s) {
+    const fm_conv_seg& sg = p->seg[s];
+    FM_REQUIRE(sg.src != nullptr && ((uintptr_t)sg.src & 15) == 0, "conv: segment %d source null/unaligned", s);
+    FM_REQUIRE(sg.C > 0 && sg.C % 8 == 0, "conv: segment %d channels=%d must be a positive multiple of 8", s, sg.C);
+    FM_REQUIRE(sg.ksize == 1 || sg.ksize == 3, "conv: segment %d ksize=%d unsupported", s, sg.ksize);
+    FM_REQUIRE(!(sg.ksize == 1 && p->stride != 1 && p->nseg > 1), "conv: fused 1x1 segment needs stride 1");
+    if (sg.upsample) { set_error("conv: upsample-fused segments are not implemented yet"); return FM_ERR_UNSUPPORTED; }
+    kp.seg_c[s] = sg.C;
+    kp.seg_taps[s] = sg.ksize * sg.ksize;
+    kp.seg_koff[s] = ktot;
+    ktot += kp.seg_taps[s] * sg.C;
+    nk += kp.seg_taps[s] * ((sg.C + kBlockK - 1) / kBlockK);
+    if (int e = encode_act_map(&kp.src[s], sg.src, sg.C, p->W, p->H, p->B, kp.Wt, kp.Ht, kp.Nt, p->stride)) return e;
+  }
+  kp.num_k_blocks = nk;
+  const int block_n = (p->Cout > 128) ? 256 : (p->Cout > 64 ? 128 : 64);
+  if (int e = encode_wgt_map(&kp.wgt, p->weight, ktot, p->Cout, block_n)) return e;
+  if (int e = encode_act_map(&kp.out, p->out, p->Cout, Wo, Ho, p->B, kp.Wt, kp.Ht, kp.Nt, 1)) return e;
+  kp.bias = p->bias;
+  kp.addvec = p->addvec;
+  kp.addvec_stride = p->addvec_stride;
+  FM_REQUIRE(p->addvec == nullptr || (p->addvec_stride % 4 == 0 && ((uintptr_t)p->addvec & 15) == 0),
+             "conv: addvec must be 16B aligned with stride %% 4 == 0");
+  FM_REQUIRE(p->bias == nullptr || ((uintptr_t)p->bias & 15) == 0, "conv: bias must be 16B aligned");
+  kp.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
+  FM_REQUIRE(p->residual == nullptr || ((uintptr_t)p->residual & 15) == 0, "conv: residual must be 16B aligned");
+  kp.gn_stats = p->gn_stats;
+  kp.gn_groups = p->gn_groups;
+  if (p->gn_stats) {
+    FM_REQUIRE(p->gn_groups > 0 && p->Cout % p->gn_groups == 0, "conv: gn_groups=%d must divide Cout=%d",
+               p->gn_groups, p->Cout);
+    const int cg = p->Cout / p->gn_groups;
+    FM_REQUIRE(cg == 4 || cg % 8 == 0, "conv: fused GN statistics need channels/group in {4, 8k} (got %d)", cg);
+  }
+  const int m_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
+  const int n_tiles = (p->Cout + block_n - 1) / block_n;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (block_n) {
+    case 64: return launch_conv<64>(kp, m_tiles, n_tiles, st);
+    case 128: return launch_conv<128>(kp, m_tiles, n_tiles, st);
+    default: return launch_conv<256>(kp, m_tiles, n_tiles, st);
+  }
+}

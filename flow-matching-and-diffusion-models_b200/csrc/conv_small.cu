@@ -1,0 +1,176 @@
+// The two degenerate convolutions of the UNet: the stem (Cin = 1..8, K = 9*Cin too small for a tensor-core tile)
+// and the head (Cout = 1..4, N too small).  Both touch the largest tensors of the network and are treated as
+// bandwidth kernels on CUDA cores.  The stem also absorbs the torch.cat([x, cond], 1) of the sampling loop
+// (src/pipelines/utils.py:204-205), the optional 2x-1 centering (unet_diffusers_nd.py:155-157), the fp32->bf16
+// cast and the NCHW->NHWC layout change; the head emits the fp32 NCHW prediction the scheduler step consumes.
+#include "common.cuh"
+
+namespace fm {
+
+constexpr int kStemMaxCin = 8;
+
+// one thread = one output pixel x 8 output channels; weights live in smem as [ci][tap][co]
+__global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ x0, int C0,
+                                                       const float* __restrict__ x1, int C1, float in_scale,
+                                                       float in_shift, const float* __restrict__ w_oihw,
+                                                       const float* __restrict__ bias, uint4* __restrict__ out, int B,
+                                                       int H, int W, int Cout) {
+  extern __shared__ float sw[];  // [Cin*9][Cout] + bias[Cout]
+  const int Cin = C0 + C1;
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;  // k = ci*9 + tap matches OIHW inner order
+    sw[i] = w_oihw[(size_t)co * K + k];
+  }
+  float* sbias = sw + K * Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sbias[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+
+  const int c8n = Cout / 8;
+  const int64_t total = (int64_t)B * H * W * c8n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int c8 = (int)(idx % c8n);
+    int64_t pix = idx / c8n;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((int64_t)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sbias[c8 * 8 + j];
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float* src = (ci < C0) ? x0 + ((size_t)n * C0 + ci) * H * W : x1 + ((size_t)n * C1 + (ci - C0)) * H * W;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = w + kw - 1;
+          if (iw < 0 || iw >= W) continue;
+          const float xv = fmaf(__ldg(src + (size_t)ih * W + iw), in_scale, in_shift);
+          const float* wp = sw + (size_t)(ci * 9 + kh * 3 + kw) * Cout + c8 * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    out[idx] = o;
+  }
+}
+
+// Head: one thread = one output pixel (all Cout <= 4 channels); weights in smem as [tap][ci][co] fp32.
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_head_kernel(const uint4* __restrict__ x, const float* __restrict__ w_oihw,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                       int H, int W, int Cin) {
+  extern __shared__ float sw[];  // [9][Cin][COUT]
+  for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) {
+    const int co = i % COUT;
+    const int ci = (i / COUT) % Cin;
+    const int tap = i / (COUT * Cin);
+    sw[i] = w_oihw[((size_t)co * Cin + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int c8n = Cin / 8;
+  // 2D tiling: a block covers 32 x 4 pixels so neighbouring threads share input rows through L1
+  const int w = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int h = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  if (w >= W || h >= H) return;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = bias ? bias[c] : 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = h + kh - 1;
+    if (ih < 0 || ih >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = w + kw - 1;
+      if (iw < 0 || iw >= W) continue;
+      const uint4* px = x + (((size_t)n * H + ih) * W + iw) * c8n;
+      const float* wt = sw + (size_t)(kh * 3 + kw) * Cin * COUT;
+#pragma unroll 4
+      for (int c8 = 0; c8 < c8n; ++c8) {
+        const uint4 u = __ldg(px + c8);
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                     f3 = unpack_bf16x2(u.w);
+        const float v[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v[j], wt[(c8 * 8 + j) * COUT + c], acc[c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) out[(((size_t)n * COUT + c) * H + h) * W + w] = acc[c];
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale,
+                                     float in_shift, const float* weight_oihw, const float* bias, void* out, int32_t B,
+                                     int32_t H, int32_t W, int32_t Cout, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x0 && C0 > 0 && (x1 != nullptr) == (C1 > 0), "conv_stem: inconsistent sources");
+  FM_REQUIRE(C0 + C1 <= kStemMaxCin, "conv_stem: Cin=%d exceeds %d", C0 + C1, kStemMaxCin);
+  FM_REQUIRE(Cout > 0 && Cout % 8 == 0 && Cout <= 512, "conv_stem: Cout=%d must be a multiple of 8 (<=512)", Cout);
+  FM_REQUIRE(weight_oihw && out && B > 0 && H > 0 && W > 0, "conv_stem: bad argument");
+  const size_t smem = ((size_t)(C0 + C1) * 9 * Cout + Cout) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_stem)");
+    attr = smem;
+  }
+  const int64_t total = (int64_t)B * H * W * (Cout / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  conv_stem_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x0, C0, x1, C1, in_scale, in_shift, weight_oihw,
+                                                                      bias, reinterpret_cast<uint4*>(out), B, H, W,
+                                                                      Cout);
+  FM_LAUNCH_CHECK("conv_stem_kernel");
+  return 0;
+}
+
+extern "C" int fm_conv_head_bf16_f32(const void* x, const float* weight_oihw, const float* bias, float* out, int32_t B,
+                                     int32_t H, int32_t W, int32_t Cin, int32_t Cout, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && weight_oihw && out && B > 0 && H > 0 && W > 0, "conv_head: bad argument");
+  FM_REQUIRE(Cin > 0 && Cin % 8 == 0, "conv_head: Cin=%d must be a multiple of 8", Cin);
+  FM_REQUIRE(Cout >= 1 && Cout <= 4, "conv_head: Cout=%d must be in 1..4", Cout);
+  const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+  FM_REQUIRE(smem <= 200 * 1024, "conv_head: weights do not fit shared memory");
+  dim3 grid((W + 31) / 32, (H + 3) / 4, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+#define FM_HEAD_CASE(N)                                                                                              \
+  case N: {                                                                                                          \
+    if (smem > 48 * 1024) {                                                                                          \
+      cudaError_t e = cudaFuncSetAttribute(conv_head_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                           (int)smem);                                                               \
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_head)");                                 \
+    }                                                                                                                \
+    conv_head_kernel<N><<<grid, 128, smem, st>>>(xp, weight_oihw, bias, out, B, H, W, Cin);                          \
+    break;                                                                                                           \
+  }
+  switch (Cout) {
+    FM_HEAD_CASE(1)
+    FM_HEAD_CASE(2)
+    FM_HEAD_CASE(3)
+    FM_HEAD_CASE(4)
+  }
+#undef FM_HEAD_CASE
+  FM_LAUNCH_CHECK("conv_head_kernel");
+  return 0;
+}

@@ -1,0 +1,384 @@
+// K4 scheduler-step kernels and the small HBM-bound helpers (time embedding, tiny fp32 Linear, weight pre-pack,
+// nearest upsample, transpose, clamp).  All fp32 scheduler arithmetic uses explicit round-to-nearest intrinsics in
+// the same operation order as diffusers' eager PyTorch code so results are bit-identical to the oracle
+// (oracle/schedulers.py), i.e. no FMA contraction.
+#include "common.cuh"
+
+namespace fm {
+
+__device__ __forceinline__ int pick_step(const int32_t* step_dev, int step_host) {
+  return step_dev != nullptr ? *step_dev : step_host;
+}
+
+// x_out = x + dt * v                                   (FlowMatchEulerDiscreteScheduler.step)
+__global__ void __launch_bounds__(256) sched_flowmatch_kernel(float* __restrict__ xo, const float* __restrict__ x,
+                                                             const float* __restrict__ v,
+                                                             const float* __restrict__ coef,
+                                                             const int32_t* __restrict__ step_dev, int step_host,
+                                                             int64_t n) {
+  const float dt = coef[pick_step(step_dev, step_host) * FM_FLOWMATCH_NCOEF];
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(v) + i);
+    float4 o;
+    o.x = __fadd_rn(a.x, __fmul_rn(dt, b.x));
+    o.y = __fadd_rn(a.y, __fmul_rn(dt, b.y));
+    o.z = __fadd_rn(a.z, __fmul_rn(dt, b.z));
+    o.w = __fadd_rn(a.w, __fmul_rn(dt, b.w));
+    reinterpret_cast<float4*>(xo)[i] = o;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    xo[i] = __fadd_rn(x[i], __fmul_rn(dt, v[i]));
+}
+
+// DDIM (eta = 0, epsilon prediction):  x0 = (x - sqrt(1-a_t) e) / sqrt(a_t); clamp; x = sqrt(a_p) x0 + dir * e
+__device__ __forceinline__ float ddim_one(float x, float e, float sb, float sa, float sp, float dc, int clip,
+                                          float cr) {
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(sb, e)), sa);
+  if (clip) x0 = fminf(fmaxf(x0, -cr), cr);
+  return __fadd_rn(__fmul_rn(sp, x0), __fmul_rn(dc, e));
+}
+__global__ void __launch_bounds__(256) sched_ddim_kernel(float* __restrict__ xo, const float* __restrict__ x,
+                                                        const float* __restrict__ eps,
+                                                        const float* __restrict__ coef,
+                                                        const int32_t* __restrict__ step_dev, int step_host,
+                                                        int clip, float cr, int64_t n) {
+  const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_DDIM_NCOEF;
+  const float sb = c[0], sa = c[1], sp = c[2], dc = c[3];
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(eps) + i);
+    float4 o;
+    o.x = ddim_one(a.x, b.x, sb, sa, sp, dc, clip, cr);
+    o.y = ddim_one(a.y, b.y, sb, sa, sp, dc, clip, cr);
+    o.z = ddim_one(a.z, b.z, sb, sa, sp, dc, clip, cr);
+    o.w = ddim_one(a.w, b.w, sb, sa, sp, dc, clip, cr);
+    reinterpret_cast<float4*>(xo)[i] = o;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    xo[i] = ddim_one(x[i], eps[i], sb, sa, sp, dc, clip, cr);
+}
+
+// DPM-Solver++(2M), midpoint, data prediction.  m = (x - sigma_s e)/alpha_s;
+//   first order : x = c1 x - c2 m ;  second order: x = c1 x - c2 m - c3 * (inv_r0 * (m - m_prev))
+__device__ __forceinline__ float dpmpp_one(float x, float e, float mp, float ss, float as, float c1, float c2,
+                                           float c3, float ir, bool second, float* m_out) {
+  const float m = __fdiv_rn(__fsub_rn(x, __fmul_rn(ss, e)), as);
+  *m_out = m;
+  float r = __fsub_rn(__fmul_rn(c1, x), __fmul_rn(c2, m));
+  if (second) r = __fsub_rn(r, __fmul_rn(c3, __fmul_rn(ir, __fsub_rn(m, mp))));
+  return r;
+}
+__global__ void __launch_bounds__(256) sched_dpmpp_kernel(float* __restrict__ xo, float* __restrict__ m_cur,
+                                                         const float* __restrict__ x,
+                                                         const float* __restrict__ eps,
+                                                         const float* __restrict__ m_prev,
+                                                         const float* __restrict__ coef,
+                                                         const int32_t* __restrict__ step_dev, int step_host,
+                                                         int64_t n) {
+  const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_DPMPP_NCOEF;
+  const float ss = c[0], as = c[1], c1 = c[2], c2 = c[3], c3 = c[4], ir = c[5];
+  const bool second = c[6] != 0.0f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(eps) + i);
+    float4 mp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (second) mp = reinterpret_cast<const float4*>(m_prev)[i];
+    float4 o, m;
+    o.x = dpmpp_one(a.x, b.x, mp.x, ss, as, c1, c2, c3, ir, second, &m.x);
+    o.y = dpmpp_one(a.y, b.y, mp.y, ss, as, c1, c2, c3, ir, second, &m.y);
+    o.z = dpmpp_one(a.z, b.z, mp.z, ss, as, c1, c2, c3, ir, second, &m.z);
+    o.w = dpmpp_one(a.w, b.w, mp.w, ss, as, c1, c2, c3, ir, second, &m.w);
+    reinterpret_cast<float4*>(xo)[i] = o;
+    reinterpret_cast<float4*>(m_cur)[i] = m;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float m;
+    xo[i] = dpmpp_one(x[i], eps[i], second ? m_prev[i] : 0.f, ss, as, c1, c2, c3, ir, second, &m);
+    m_cur[i] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) add_noise_kernel(float* __restrict__ xo, const float* __restrict__ x0,
+                                                       const float* __restrict__ noise,
+                                                       const float* __restrict__ a, const float* __restrict__ b,
+                                                       int64_t per_sample, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int s = (int)(i / per_sample);
+    xo[i] = __fadd_rn(__fmul_rn(a[s], x0[i]), __fmul_rn(b[s], noise[i]));
+  }
+}
+
+__global__ void counter_add_kernel(int32_t* ctr, int32_t delta) { *ctr += delta; }
+
+__global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ y, const float* __restrict__ x, float lo,
+                                                   float hi, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = fminf(fmaxf(x[i], lo), hi);
+}
+
+// ---- sinusoidal timestep embedding (src/nn/ops/time_embedding.py:23-31), accurate sin/cos ---------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ t_table,
+                                          const int32_t* __restrict__ step_dev, float* __restrict__ out, int B,
+                                          int dim, float neg_log_period, int flip, float denom) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * dim) return;
+  const int b = idx / dim, j = idx - b * dim;
+  const float tv = (t_table != nullptr) ? t_table[*step_dev] : t[b];
+  if (j >= 2 * half) { out[idx] = 0.f; return; }
+  // reference layout [sin | cos]; flip_sin_to_cos swaps the halves
+  const bool second_half = j >= half;
+  const int i = second_half ? j - half : j;
+  const bool want_cos = flip ? !second_half : second_half;
+  const float e = __fdiv_rn(__fmul_rn(neg_log_period, (float)i), denom);
+  const float arg = __fmul_rn(tv, expf(e));
+  out[idx] = want_cos ? cosf(arg) : sinf(arg);
+}
+
+// ---- tiny fp32 Linear: one warp per output feature, batch rows in chunks of 8 ---------------------------------
+__global__ void __launch_bounds__(128) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                        const float* __restrict__ bias,
+                                                        const float* __restrict__ bias2, float* __restrict__ y,
+                                                        int B, int I, int O, int silu_in, int silu_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 4 + warp;
+  if (o >= O) return;
+  const float* w = W + (size_t)o * I;
+  float bsum = 0.f;
+  if (bias) bsum += bias[o];
+  if (bias2) bsum += bias2[o];
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int i = lane; i < I; i += 32) {
+      const float wv = w[i];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (b0 + r < B) {
+          float xv = x[(size_t)(b0 + r) * I + i];
+          if (silu_in) xv = xv / (1.0f + expf(-xv));
+          acc[r] = fmaf(xv, wv, acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float s = warp_sum(acc[r]);
+      if (lane == 0 && b0 + r < B) {
+        s += bsum;
+        if (silu_out) s = s / (1.0f + expf(-s));
+        y[(size_t)(b0 + r) * O + o] = s;
+      }
+    }
+  }
+}
+
+// ---- weight pre-pack: OIHW fp32 -> [Cout][K] bf16, K = (tap, channel) ------------------------------------------
+__global__ void weight_prepack_kernel(__nv_bfloat16* __restrict__ dst, int64_t dst_row_stride, int64_t koff,
+                                      const float* __restrict__ src, int Cout, int Cin_total, int c_begin, int Cseg,
+                                      int ks) {
+  const int taps = ks * ks;
+  const int64_t total = (int64_t)Cout * taps * Cseg;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % Cseg);
+  const int tap = (int)((i / Cseg) % taps);
+  const int co = (int)(i / ((int64_t)Cseg * taps));
+  const float v = src[((int64_t)co * Cin_total + c_begin + c) * taps + tap];
+  dst[(int64_t)co * dst_row_stride + koff + (int64_t)tap * Cseg + c] = __float2bfloat16_rn(v);
+}
+
+// ---- nearest 2x upsample, NHWC bf16, 16 B per thread -----------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B,
+                                                        int H, int W, int C8) {
+  const int64_t total = (int64_t)B * (2 * H) * (2 * W) * C8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C8);
+    int64_t r = i / C8;
+    const int ow = (int)(r % (2 * W)); r /= (2 * W);
+    const int oh = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    out[i] = x[(((int64_t)n * H + (oh >> 1)) * W + (ow >> 1)) * C8 + c];
+  }
+}
+
+// ---- [B][R][C] -> [B][C][R] bf16 ------------------------------------------------------------------------------
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int R,
+                                      int C) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const __nv_bfloat16* xb = x + (size_t)b * R * C;
+  __nv_bfloat16* ob = out + (size_t)b * R * C;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = xb[(size_t)r * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) ob[(size_t)c * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+static inline int ew_blocks(int64_t work_items) {
+  int64_t b = (work_items + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" int fm_sched_flowmatch_f32(float* x_out, const float* x, const float* v, const float* coef,
+                                      const int32_t* step_dev, int32_t step_host, int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x_out && x && v && coef && n >= 0, "flowmatch: null pointer or negative n");
+  FM_REQUIRE((((uintptr_t)x_out | (uintptr_t)x | (uintptr_t)v) & 15) == 0, "flowmatch: pointers must be 16B aligned");
+  FM_REQUIRE(step_dev != nullptr || step_host >= 0, "flowmatch: negative step");
+  if (n == 0) return 0;
+  sched_flowmatch_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, x, v, coef, step_dev,
+                                                                                 step_host, n);
+  FM_LAUNCH_CHECK("sched_flowmatch_kernel");
+  return 0;
+}
+
+extern "C" int fm_sched_ddim_f32(float* x_out, const float* x, const float* eps, const float* coef,
+                                 const int32_t* step_dev, int32_t step_host, int32_t clip, float clip_range,
+                                 int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x_out && x && eps && coef && n >= 0, "ddim: null pointer or negative n");
+  FM_REQUIRE((((uintptr_t)x_out | (uintptr_t)x | (uintptr_t)eps) & 15) == 0, "ddim: pointers must be 16B aligned");
+  FM_REQUIRE(step_dev != nullptr || step_host >= 0, "ddim: negative step");
+  if (n == 0) return 0;
+  sched_ddim_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, x, eps, coef, step_dev, step_host,
+                                                                            clip, clip_range, n);
+  FM_LAUNCH_CHECK("sched_ddim_kernel");
+  return 0;
+}
+
+extern "C" int fm_sched_dpmpp2m_f32(float* x_out, float* m_cur, const float* x, const float* eps,
+                                    const float* m_prev, const float* coef, const int32_t* step_dev,
+                                    int32_t step_host, int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x_out && m_cur && x && eps && m_prev && coef && n >= 0, "dpmpp2m: null pointer or negative n");
+  FM_REQUIRE((((uintptr_t)x_out | (uintptr_t)x | (uintptr_t)eps | (uintptr_t)m_cur | (uintptr_t)m_prev) & 15) == 0,
+             "dpmpp2m: pointers must be 16B aligned");
+  FM_REQUIRE(step_dev != nullptr || step_host >= 0, "dpmpp2m: negative step");
+  if (n == 0) return 0;
+  sched_dpmpp_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, m_cur, x, eps, m_prev, coef,
+                                                                             step_dev, step_host, n);
+  FM_LAUNCH_CHECK("sched_dpmpp_kernel");
+  return 0;
+}
+
+extern "C" int fm_sched_add_noise_f32(float* x_out, const float* x0, const float* noise, const float* a,
+                                      const float* b, int32_t B, int64_t per_sample, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x_out && x0 && noise && a && b && B >= 0 && per_sample >= 0, "add_noise: bad argument");
+  const int64_t n = (int64_t)B * per_sample;
+  if (n == 0) return 0;
+  add_noise_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x_out, x0, noise, a, b, per_sample, n);
+  FM_LAUNCH_CHECK("add_noise_kernel");
+  return 0;
+}
+
+extern "C" int fm_counter_add(int32_t* ctr, int32_t delta, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(ctr != nullptr, "counter_add: null counter");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, delta);
+  FM_LAUNCH_CHECK("counter_add_kernel");
+  return 0;
+}
+
+extern "C" int fm_clamp_f32(float* y, const float* x, float lo, float hi, int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(y && x && n >= 0, "clamp: bad argument");
+  if (n == 0) return 0;
+  clamp_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(y, x, lo, hi, n);
+  FM_LAUNCH_CHECK("clamp_kernel");
+  return 0;
+}
+
+extern "C" int fm_timestep_embedding_f32(const float* t, const float* t_table, const int32_t* step_dev, float* out,
+                                         int32_t B, int32_t dim, float max_period, int32_t flip_sin_to_cos,
+                                         float freq_shift, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(out && B > 0 && dim > 0, "timestep_embedding: bad shape B=%d dim=%d", B, dim);
+  FM_REQUIRE((t != nullptr) != (t_table != nullptr), "timestep_embedding: exactly one of t / t_table must be given");
+  FM_REQUIRE(t_table == nullptr || step_dev != nullptr, "timestep_embedding: t_table needs step_dev");
+  const int half = dim / 2;
+  float denom = (float)half - freq_shift;
+  if (denom < 1.0f) denom = 1.0f;
+  const float nlp = (float)(-log((double)max_period));
+  const int total = B * dim;
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, t_table, step_dev, out, B, dim,
+                                                                                   nlp, flip_sin_to_cos, denom);
+  FM_LAUNCH_CHECK("timestep_embedding_kernel");
+  return 0;
+}
+
+extern "C" int fm_linear_f32(const float* x, const float* W, const float* bias, const float* bias2, float* y,
+                             int32_t B, int32_t I, int32_t O, int32_t silu_in, int32_t silu_out,
+                             fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && W && y && B > 0 && I > 0 && O > 0, "linear: bad argument B=%d I=%d O=%d", B, I, O);
+  linear_f32_kernel<<<(O + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, W, bias, bias2, y, B, I, O, silu_in, silu_out);
+  FM_LAUNCH_CHECK("linear_f32_kernel");
+  return 0;
+}
+
+extern "C" int fm_weight_prepack_bf16(void* dst, int64_t dst_row_stride, int64_t koff, const float* src_oihw,
+                                      int32_t Cout, int32_t Cin_total, int32_t c_begin, int32_t Cseg, int32_t ksize,
+                                      fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(dst && src_oihw && Cout > 0 && Cseg > 0 && c_begin >= 0 && c_begin + Cseg <= Cin_total,
+             "weight_prepack: bad channel range");
+  FM_REQUIRE(ksize == 1 || ksize == 3, "weight_prepack: ksize must be 1 or 3");
+  const int64_t total = (int64_t)Cout * ksize * ksize * Cseg;
+  weight_prepack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(dst), dst_row_stride, koff, src_oihw, Cout, Cin_total, c_begin, Cseg, ksize);
+  FM_LAUNCH_CHECK("weight_prepack_kernel");
+  return 0;
+}
+
+extern "C" int fm_upsample_nearest2x_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                                          fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample: bad shape (C %% 8 != 0?)");
+  const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                        reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  FM_LAUNCH_CHECK("upsample2x_kernel");
+  return 0;
+}
+
+extern "C" int fm_transpose_bf16(const void* x, void* out, int32_t B, int32_t R, int32_t C, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && out && B > 0 && R > 0 && C > 0, "transpose: bad shape");
+  dim3 grid((C + 31) / 32, (R + 31) / 32, B), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                 reinterpret_cast<__nv_bfloat16*>(out), R, C);
+  FM_LAUNCH_CHECK("transpose_bf16_kernel");
+  return 0;
+}
+
+extern "C" int fm_memset_f32(float* p, int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(p != nullptr && n >= 0, "memset: bad argument");
+  return check_cuda(cudaMemsetAsync(p, 0, (size_t)n * sizeof(float), (cudaStream_t)stream), "cudaMemsetAsync");
+}

@@ -1,0 +1,190 @@
+// K2: GroupNorm (+SiLU, +scale-shift) over NHWC bf16 activations with fp32 statistics.  HBM-bound: every thread
+// moves 16 B (8 channels) per access, fully coalesced along the channel-contiguous NHWC rows; per-channel partial
+// sums are reduced through shared memory and land in global memory with one atomicAdd per (block, group).
+// Two sources are read as a virtual channel concat (the up-path torch.cat of legacy_unet.py:150 never exists in
+// memory); the apply kernel writes the concatenated, normalised, activated tensor the consumer conv reads.
+// Reference ops replaced: nn.GroupNorm + nn.SiLU (src/nn/blocks/residual.py:95-96,113-116).
+#include "common.cuh"
+
+namespace fm {
+
+constexpr int kGnThreads = 256;
+
+__device__ __forceinline__ uint4 ld_chunk(const uint4* __restrict__ x0, int c80, const uint4* __restrict__ x1,
+                                          int c81, int64_t pix, int chunk) {
+  return (chunk < c80) ? x0[pix * c80 + chunk] : x1[pix * c81 + (chunk - c80)];
+}
+
+// stats[n][g] += (sum, sumsq) over this block's pixel slab
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __restrict__ x0, int c80,
+                                                             const uint4* __restrict__ x1, int c81, int64_t HW,
+                                                             int groups, float* __restrict__ stats,
+                                                             int64_t pix_per_block) {
+  extern __shared__ float sm[];  // [ppi][C][2]
+  const int tpp = c80 + c81;     // 8-channel chunks per pixel
+  const int C = tpp * 8;
+  const int ppi = kGnThreads / tpp;
+  const int n = blockIdx.y;
+  const int chunk = threadIdx.x % tpp;
+  const int prow = threadIdx.x / tpp;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  int64_t p_end = p_begin + pix_per_block;
+  if (p_end > HW) p_end = HW;
+
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (prow < ppi) {
+    const int64_t base = (int64_t)n * HW;
+    for (int64_t p = p_begin + prow; p < p_end; p += ppi) {
+      const uint4 u = ld_chunk(x0, c80, x1, c81, base + p, chunk);
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      const float v[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[((size_t)prow * C + chunk * 8 + j) * 2 + 0] = s[j];
+      sm[((size_t)prow * C + chunk * 8 + j) * 2 + 1] = q[j];
+    }
+  }
+  __syncthreads();
+  // one thread per group: fold pixel rows and the group's channels
+  const int cg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+    float ts = 0.f, tq = 0.f;
+    for (int r = 0; r < ppi; ++r)
+      for (int c = g * cg; c < (g + 1) * cg; ++c) {
+        ts += sm[((size_t)r * C + c) * 2 + 0];
+        tq += sm[((size_t)r * C + c) * 2 + 1];
+      }
+    atomicAdd(&stats[((size_t)n * groups + g) * 2 + 0], ts);
+    atomicAdd(&stats[((size_t)n * groups + g) * 2 + 1], tq);
+  }
+}
+
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __restrict__ x0, int c80,
+                                                             const uint4* __restrict__ x1, int c81, int64_t HW,
+                                                             int groups, float eps, const float* __restrict__ stats,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ scale_shift, int silu,
+                                                             uint4* __restrict__ out, int64_t pix_per_block) {
+  extern __shared__ float sm[];  // a[C], b[C]
+  const int tpp = c80 + c81;
+  const int C = tpp * 8;
+  const int n = blockIdx.y;
+  float* sa = sm;
+  float* sb = sm + C;
+  const int cg = C / groups;
+  const float inv_cnt = 1.0f / ((float)HW * (float)cg);
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    const int g = c / cg;
+    const float sum = stats[((size_t)n * groups + g) * 2 + 0];
+    const float sq = stats[((size_t)n * groups + g) * 2 + 1];
+    const float mean = sum * inv_cnt;
+    float var = sq * inv_cnt - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    const float rstd = rsqrtf(var + eps);
+    float a = rstd * gamma[c];
+    float b = beta[c] - mean * a;
+    if (scale_shift != nullptr) {
+      const float sc = 1.0f + scale_shift[(size_t)n * 2 * C + c];
+      const float sh = scale_shift[(size_t)n * 2 * C + C + c];
+      a *= sc;
+      b = b * sc + sh;
+    }
+    sa[c] = a;
+    sb[c] = b;
+  }
+  __syncthreads();
+
+  const int ppi = kGnThreads / tpp;
+  const int chunk = threadIdx.x % tpp;
+  const int prow = threadIdx.x / tpp;
+  if (prow >= ppi) return;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = sa[chunk * 8 + j]; b[j] = sb[chunk * 8 + j]; }
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  int64_t p_end = p_begin + pix_per_block;
+  if (p_end > HW) p_end = HW;
+  const int64_t base = (int64_t)n * HW;
+  for (int64_t p = p_begin + prow; p < p_end; p += ppi) {
+    const uint4 u = ld_chunk(x0, c80, x1, c81, base + p, chunk);
+    const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    float v[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(v[j], a[j], b[j]);
+      if (silu) v[j] = silu_f(v[j]);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    out[(base + p) * tpp + chunk] = o;
+  }
+}
+
+static int gn_grid(int B, int64_t HW, int tpp, int64_t* pix_per_block) {
+  const int ppi = kGnThreads / tpp;
+  int64_t target_blocks = ((int64_t)sm_count() * 8 + B - 1) / B;  // ~8 CTAs per SM across the batch
+  if (target_blocks < 1) target_blocks = 1;
+  int64_t ppb = (HW + target_blocks - 1) / target_blocks;
+  const int64_t min_ppb = (int64_t)ppi * 4;
+  if (ppb < min_ppb) ppb = min_ppb;
+  ppb = (ppb + ppi - 1) / ppi * ppi;
+  *pix_per_block = ppb;
+  return (int)((HW + ppb - 1) / ppb);
+}
+
+static int gn_check(const void* x0, int C0, const void* x1, int C1, int B, int64_t HW, int groups) {
+  FM_REQUIRE(x0 != nullptr && C0 > 0 && C0 % 8 == 0, "groupnorm: source 0 needs C %% 8 == 0 (C0=%d)", C0);
+  FM_REQUIRE((x1 == nullptr) == (C1 == 0) && C1 % 8 == 0, "groupnorm: source 1 inconsistent (C1=%d)", C1);
+  FM_REQUIRE(((uintptr_t)x0 & 15) == 0 && ((uintptr_t)x1 & 15) == 0, "groupnorm: sources must be 16B aligned");
+  const int C = C0 + C1;
+  FM_REQUIRE(C / 8 <= kGnThreads, "groupnorm: C=%d too large (max %d)", C, kGnThreads * 8);
+  FM_REQUIRE(groups > 0 && C % groups == 0, "groupnorm: groups=%d must divide C=%d", groups, C);
+  FM_REQUIRE(B > 0 && HW > 0, "groupnorm: empty input");
+  return 0;
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
+                                       int32_t groups, float* stats, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  if (int e = gn_check(x0, C0, x1, C1, B, HW, groups)) return e;
+  FM_REQUIRE(stats != nullptr, "groupnorm_stats: null stats");
+  const int tpp = (C0 + C1) / 8;
+  int64_t ppb;
+  const int gx = gn_grid(B, HW, tpp, &ppb);
+  const int ppi = kGnThreads / tpp;
+  const size_t smem = (size_t)ppi * (C0 + C1) * 2 * sizeof(float);
+  gn_stats_kernel<<<dim3(gx, B), kGnThreads, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, stats, ppb);
+  FM_LAUNCH_CHECK("gn_stats_kernel");
+  return 0;
+}
+
+extern "C" int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
+                                       int32_t groups, float eps, const float* stats, const float* gamma,
+                                       const float* beta, const float* scale_shift, int32_t silu, void* out,
+                                       fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  if (int e = gn_check(x0, C0, x1, C1, B, HW, groups)) return e;
+  FM_REQUIRE(stats && gamma && beta && out, "groupnorm_apply: null pointer");
+  FM_REQUIRE(((uintptr_t)out & 15) == 0, "groupnorm_apply: out must be 16B aligned");
+  const int tpp = (C0 + C1) / 8;
+  int64_t ppb;
+  const int gx = gn_grid(B, HW, tpp, &ppb);
+  const size_t smem = (size_t)(C0 + C1) * 2 * sizeof(float);
+  gn_apply_kernel<<<dim3(gx, B), kGnThreads, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, eps, stats,
+      gamma, beta, scale_shift, silu, reinterpret_cast<uint4*>(out), ppb);
+  FM_LAUNCH_CHECK("gn_apply_kernel");
+  return 0;
+}

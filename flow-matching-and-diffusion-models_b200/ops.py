@@ -1,0 +1,396 @@
+"""Thin tensor-level wrappers over the C-ABI kernels.
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the current stream; every function below
+launches exactly the hand-written sm_100a kernels through ctypes.  Activations are logical NCHW tensors stored
+channels_last in bf16 ("NHWC bf16"); the sampler state and model prediction are fp32 NCHW.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"fmdm_b200.{what}: tensor is on {t.device}; the B200 hot path has no CPU implementation "
+            "(use the oracle/ package or the reference for CPU runs)."
+        )
+
+
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor -> bf16 channels_last storage (no copy if already so)."""
+    require_cuda(x, "to_nhwc_bf16")
+    if x.dtype == BF16 and x.dim() == 4 and is_nhwc(x):
+        return x
+    return x.to(dtype=BF16).contiguous(memory_format=torch.channels_last)
+
+
+def is_nhwc(x: torch.Tensor) -> bool:
+    if x.dim() != 4:
+        return False
+    b, c, h, w = x.shape
+    return x.stride() == (h * w * c, 1, w * c, c) or x.permute(0, 2, 3, 1).is_contiguous()
+
+
+def empty_nhwc(b: int, c: int, h: int, w: int, device) -> torch.Tensor:
+    return torch.empty((b, h, w, c), dtype=BF16, device=device).permute(0, 3, 1, 2)
+
+
+def _check_act(x: torch.Tensor, what: str) -> None:
+    require_cuda(x, what)
+    if x.dtype != BF16 or not is_nhwc(x):
+        raise RuntimeError(f"fmdm_b200.{what}: expected a bf16 channels_last activation, got {x.dtype} {x.stride()}")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# conv2d implicit GEMM
+# --------------------------------------------------------------------------------------------------------------
+class PackedConvWeight:
+    """K-major bf16 weight matrix [Cout][Ktot] for fm_conv2d_igemm_bf16, K = (segment, tap, channel)."""
+
+    def __init__(self, mat: torch.Tensor, seg_channels: Sequence[int], seg_ksize: Sequence[int], cout: int):
+        self.mat = mat
+        self.seg_channels = tuple(int(c) for c in seg_channels)
+        self.seg_ksize = tuple(int(k) for k in seg_ksize)
+        self.cout = int(cout)
+
+
+def pack_conv_weight(parts: Sequence[tuple]) -> PackedConvWeight:
+    """parts: [(weight_oihw_fp32 [Cout][Cin][k][k] (or [Cout][Cin] for linear), c_begin, c_count), ...]
+
+    Each part becomes one K segment reading `c_count` input channels starting at `c_begin` of that weight.
+    """
+    lib = _lib.lib()
+    cout = parts[0][0].shape[0]
+    seg_c, seg_k = [], []
+    ktot = 0
+    for w, c_begin, c_count in parts:
+        ks = 1 if w.dim() == 2 else int(w.shape[-1])
+        if w.shape[0] != cout:
+            raise ValueError("all parts must share Cout")
+        seg_c.append(int(c_count))
+        seg_k.append(ks)
+        ktot += ks * ks * int(c_count)
+    dev = parts[0][0].device
+    require_cuda(parts[0][0], "pack_conv_weight")
+    mat = torch.empty((cout, ktot), dtype=BF16, device=dev)
+    koff = 0
+    keep = []
+    for (w, c_begin, c_count), ks in zip(parts, seg_k):
+        w32 = w.detach().to(dtype=torch.float32).contiguous()
+        keep.append(w32)
+        cin_total = w32.shape[1]
+        _lib.check(
+            lib.fm_weight_prepack_bf16(
+                mat.data_ptr(), ktot, koff, w32.data_ptr(), cout, cin_total, int(c_begin), int(c_count), ks, _stream()
+            ),
+            "weight_prepack",
+        )
+        koff += ks * ks * int(c_count)
+    return PackedConvWeight(mat, seg_c, seg_k, cout)
+
+
+def conv2d(
+    srcs: Sequence[torch.Tensor],
+    weight: PackedConvWeight,
+    *,
+    stride: int = 1,
+    bias: Optional[torch.Tensor] = None,
+    addvec: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Implicit-GEMM conv over the virtual channel concat of `srcs` (one K segment per source)."""
+    lib = _lib.lib()
+    if len(srcs) != len(weight.seg_channels) or len(srcs) > _lib.FM_CONV_MAX_SEG:
+        raise ValueError(f"conv2d: {len(srcs)} sources for {len(weight.seg_channels)} weight segments")
+    b, _, h, w = srcs[0].shape
+    p = _lib.ConvParams()
+    for i, (s, c, ks) in enumerate(zip(srcs, weight.seg_channels, weight.seg_ksize)):
+        _check_act(s, "conv2d")
+        if s.shape != (b, c, h, w):
+            raise ValueError(f"conv2d: segment {i} has shape {tuple(s.shape)}, expected {(b, c, h, w)}")
+        p.seg[i].src = s.data_ptr()
+        p.seg[i].C = c
+        p.seg[i].ksize = ks
+        p.seg[i].upsample = 0
+    p.nseg = len(srcs)
+    p.B, p.H, p.W = b, h, w
+    p.stride = stride
+    p.Cout = weight.cout
+    ho, wo = (h + stride - 1) // stride, (w + stride - 1) // stride
+    if out is None:
+        out = empty_nhwc(b, weight.cout, ho, wo, srcs[0].device)
+    else:
+        _check_act(out, "conv2d(out)")
+    p.weight = weight.mat.data_ptr()
+    p.bias = _ptr(bias)
+    if addvec is not None:
+        if addvec.dtype != torch.float32 or addvec.dim() != 2 or addvec.shape[0] != b or addvec.stride(1) != 1:
+            raise ValueError("conv2d: addvec must be fp32 [B][>=Cout] with unit inner stride")
+        p.addvec = addvec.data_ptr()
+        p.addvec_stride = addvec.stride(0)
+    if residual is not None:
+        _check_act(residual, "conv2d(residual)")
+        if residual.shape != out.shape:
+            raise ValueError("conv2d: residual shape mismatch")
+        p.residual = residual.data_ptr()
+    p.out = out.data_ptr()
+    p.gn_stats = None
+    p.gn_groups = 0
+    _lib.check(lib.fm_conv2d_igemm_bf16(C.byref(p), _stream()), "conv2d_igemm_bf16")
+    return out
+
+
+def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0) -> torch.Tensor:
+    """fp32 NCHW (x0 [, x1]) -> bf16 NHWC, 3x3 s1 p1; fuses the conditioning concat and the 2x-1 centering."""
+    lib = _lib.lib()
+    require_cuda(x0, "conv_stem")
+    x0 = x0.to(torch.float32).contiguous()
+    b, c0, h, w = x0.shape
+    c1 = 0
+    if x1 is not None:
+        x1 = x1.to(torch.float32).contiguous()
+        c1 = x1.shape[1]
+    cout = weight_oihw.shape[0]
+    out = empty_nhwc(b, cout, h, w, x0.device)
+    _lib.check(
+        lib.fm_conv_stem_f32_bf16(
+            x0.data_ptr(), c0, _ptr(x1), c1, float(in_scale), float(in_shift), weight_oihw.data_ptr(), _ptr(bias),
+            out.data_ptr(), b, h, w, cout, _stream(),
+        ),
+        "conv_stem",
+    )
+    return out
+
+
+def conv_head(x: torch.Tensor, weight_oihw, bias) -> torch.Tensor:
+    """bf16 NHWC -> fp32 NCHW, 3x3 s1 p1, Cout <= 4."""
+    lib = _lib.lib()
+    _check_act(x, "conv_head")
+    b, cin, h, w = x.shape
+    cout = weight_oihw.shape[0]
+    out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(
+        lib.fm_conv_head_bf16_f32(x.data_ptr(), weight_oihw.data_ptr(), _ptr(bias), out.data_ptr(), b, h, w, cin, cout,
+                                  _stream()),
+        "conv_head",
+    )
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU, +scale/shift)
+# --------------------------------------------------------------------------------------------------------------
+def group_norm(
+    srcs: Sequence[torch.Tensor],
+    groups: int,
+    eps: float,
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    *,
+    silu: bool,
+    scale_shift: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """GroupNorm over the virtual concat of one or two NHWC bf16 sources; returns the concatenated result."""
+    lib = _lib.lib()
+    if not 1 <= len(srcs) <= 2:
+        raise ValueError("group_norm: one or two sources")
+    for s in srcs:
+        _check_act(s, "group_norm")
+    x0 = srcs[0]
+    x1 = srcs[1] if len(srcs) == 2 else None
+    b, c0, h, w = x0.shape
+    c1 = x1.shape[1] if x1 is not None else 0
+    ctot = c0 + c1
+    stats = torch.zeros((b, groups, 2), dtype=torch.float32, device=x0.device)
+    st = _stream()
+    _lib.check(
+        lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, stats.data_ptr(), st),
+        "groupnorm_stats",
+    )
+    out = empty_nhwc(b, ctot, h, w, x0.device)
+    if scale_shift is not None and (scale_shift.dtype != torch.float32 or scale_shift.shape != (b, 2 * ctot)
+                                    or not scale_shift.is_contiguous()):
+        raise ValueError("group_norm: scale_shift must be contiguous fp32 [B][2C]")
+    _lib.check(
+        lib.fm_groupnorm_apply_bf16(
+            x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps), stats.data_ptr(), gamma.data_ptr(),
+            beta.data_ptr(), _ptr(scale_shift), int(silu), out.data_ptr(), st,
+        ),
+        "groupnorm_apply",
+    )
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.lib()
+    _check_act(x, "upsample_nearest2x")
+    b, c, h, w = x.shape
+    out = empty_nhwc(b, c, 2 * h, 2 * w, x.device)
+    _lib.check(lib.fm_upsample_nearest2x_bf16(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "upsample")
+    return out
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[B][R][C] contiguous bf16 -> [B][C][R]."""
+    lib = _lib.lib()
+    require_cuda(x, "transpose")
+    assert x.dtype == BF16 and x.dim() == 3 and x.is_contiguous()
+    b, r, c = x.shape
+    out = torch.empty((b, c, r), dtype=BF16, device=x.device)
+    _lib.check(lib.fm_transpose_bf16(x.data_ptr(), out.data_ptr(), b, r, c, _stream()), "transpose")
+    return out
+
+
+def attention(q, k, v, out, *, batch, heads, tq, tk, head_dim, q_strides, kv_strides, o_strides, scale=None):
+    """Strided softmax(QK^T)V; q/k/v/out are bf16 tensors (views give the base pointers), strides in elements."""
+    lib = _lib.lib()
+    for t in (q, k, v, out):
+        require_cuda(t, "attention")
+        assert t.dtype == BF16
+    if scale is None:
+        scale = 1.0 / math.sqrt(head_dim)
+    _lib.check(
+        lib.fm_attention_bf16(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, tq, tk, head_dim,
+            *[int(s) for s in q_strides], *[int(s) for s in kv_strides], *[int(s) for s in o_strides], float(scale),
+            _stream(),
+        ),
+        "attention",
+    )
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# time embedding path
+# --------------------------------------------------------------------------------------------------------------
+def timestep_embedding(t: Optional[torch.Tensor], dim: int, max_period: float = 10000.0, *, flip_sin_to_cos=True,
+                       freq_shift: float = 0.0, batch: Optional[int] = None, t_table=None, step_dev=None):
+    lib = _lib.lib()
+    if t is not None:
+        require_cuda(t, "timestep_embedding")
+        t = t.to(torch.float32).contiguous()
+        batch = t.shape[0]
+        dev = t.device
+    else:
+        dev = t_table.device
+    out = torch.empty((batch, dim), dtype=torch.float32, device=dev)
+    _lib.check(
+        lib.fm_timestep_embedding_f32(_ptr(t), _ptr(t_table), _ptr(step_dev), out.data_ptr(), batch, dim,
+                                      float(max_period), int(bool(flip_sin_to_cos)), float(freq_shift), _stream()),
+        "timestep_embedding",
+    )
+    return out
+
+
+def linear_f32(x, weight, bias=None, bias2=None, *, silu_in=False, silu_out=False) -> torch.Tensor:
+    lib = _lib.lib()
+    require_cuda(x, "linear_f32")
+    x = x.to(torch.float32).contiguous()
+    b, i = x.shape
+    o = weight.shape[0]
+    assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.shape[1] == i
+    y = torch.empty((b, o), dtype=torch.float32, device=x.device)
+    _lib.check(
+        lib.fm_linear_f32(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(bias2), y.data_ptr(), b, i, o,
+                          int(silu_in), int(silu_out), _stream()),
+        "linear_f32",
+    )
+    return y
+
+
+# --------------------------------------------------------------------------------------------------------------
+# scheduler steps
+# --------------------------------------------------------------------------------------------------------------
+def sched_flowmatch(x, v, coef, step, x_out=None, step_dev=None):
+    lib = _lib.lib()
+    require_cuda(x, "sched_flowmatch")
+    assert x.dtype == torch.float32 and v.dtype == torch.float32 and x.is_contiguous() and v.is_contiguous()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    _lib.check(
+        lib.fm_sched_flowmatch_f32(x_out.data_ptr(), x.data_ptr(), v.data_ptr(), coef.data_ptr(), _ptr(step_dev),
+                                   int(step), x.numel(), _stream()),
+        "sched_flowmatch",
+    )
+    return x_out
+
+
+def sched_ddim(x, eps, coef, step, clip, clip_range, x_out=None, step_dev=None):
+    lib = _lib.lib()
+    require_cuda(x, "sched_ddim")
+    assert x.dtype == torch.float32 and eps.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    _lib.check(
+        lib.fm_sched_ddim_f32(x_out.data_ptr(), x.data_ptr(), eps.data_ptr(), coef.data_ptr(), _ptr(step_dev),
+                              int(step), int(bool(clip)), float(clip_range), x.numel(), _stream()),
+        "sched_ddim",
+    )
+    return x_out
+
+
+def sched_dpmpp2m(x, eps, m_prev, coef, step, x_out=None, m_cur=None, step_dev=None):
+    lib = _lib.lib()
+    require_cuda(x, "sched_dpmpp2m")
+    for t in (x, eps, m_prev):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    if m_cur is None:
+        m_cur = torch.empty_like(x)
+    _lib.check(
+        lib.fm_sched_dpmpp2m_f32(x_out.data_ptr(), m_cur.data_ptr(), x.data_ptr(), eps.data_ptr(), m_prev.data_ptr(),
+                                 coef.data_ptr(), _ptr(step_dev), int(step), x.numel(), _stream()),
+        "sched_dpmpp2m",
+    )
+    return x_out, m_cur
+
+
+def sched_add_noise(x0, noise, a, b):
+    lib = _lib.lib()
+    require_cuda(x0, "sched_add_noise")
+    x0 = x0.to(torch.float32).contiguous()
+    noise = noise.to(torch.float32).contiguous()
+    out = torch.empty_like(x0)
+    bsz = x0.shape[0]
+    _lib.check(
+        lib.fm_sched_add_noise_f32(out.data_ptr(), x0.data_ptr(), noise.data_ptr(), a.data_ptr(), b.data_ptr(), bsz,
+                                   x0.numel() // max(bsz, 1), _stream()),
+        "sched_add_noise",
+    )
+    return out
+
+
+def counter_add(ctr: torch.Tensor, delta: int) -> None:
+    _lib.check(_lib.lib().fm_counter_add(ctr.data_ptr(), int(delta), _stream()), "counter_add")
+
+
+def clamp_f32(x: torch.Tensor, lo: float, hi: float) -> torch.Tensor:
+    require_cuda(x, "clamp")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().fm_clamp_f32(y.data_ptr(), x.data_ptr(), float(lo), float(hi), x.numel(), _stream()),
+               "clamp")
+    return y
+
+
+def launch_count() -> int:
+    return int(_lib.lib().fm_launch_count())

@@ -1,0 +1,170 @@
+/*
+ * fmdm_b200 — C-ABI of the B200-native sampling hot path.
+ *
+ * The reference (tomn681/Flow-Matching-and-Diffusion-Models) has no FFI: its "plugin API" for this path is
+ * Python nn.Module classes calling ATen ops, plus the diffusers scheduler duck-type.  Every entry point below
+ * replaces the ATen/diffusers call(s) made at the cited reference line(s).  The host side
+ * (`flow-matching-and-diffusion-models_b200/`) mirrors the reference modules and calls these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - activations are NHWC bf16 ("channels_last" storage of a logical NCHW tensor); the sampler state x and the
+ *     model prediction are fp32 NCHW;
+ *   - the caller owns every buffer (PyTorch's caching allocator); the library never allocates device memory,
+ *     keeps no pointer after the call returns and is safe under CUDA-graph capture;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 ok, <0 bad argument (see fm_last_error()), >0 a cudaError_t / CUresult.
+ *   - there is no CPU path: on a machine without an sm_100 device every compute entry point returns an error.
+ */
+#ifndef FMDM_B200_H
+#define FMDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fm_stream_t;
+
+#define FM_OK 0
+#define FM_ERR_BAD_ARG (-1)
+#define FM_ERR_UNSUPPORTED (-2)
+#define FM_ERR_NO_DEVICE (-3)
+
+/* library identity / diagnostics */
+int fm_version(void);
+const char* fm_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+long long fm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K1: conv2d as implicit GEMM on tcgen05/TMEM, TMA-fed, bf16 in / fp32 accumulate / bf16 out.
+ * Replaces nn.Conv2d reached through ConvND.forward (src/nn/ops/convolution.py:53-54), the 1x1 skip
+ * (src/nn/blocks/residual.py:82,120), DownsampleND.op (src/nn/ops/upsampling.py:49-56), the q/k/v/out nn.Linear
+ * of DiffusersAttentionND (src/nn/blocks/attention.py:216-229) seen as 1x1 convs on NHWC, the skip torch.cat
+ * (src/nn/blocks/legacy_unet.py:150) as a multi-segment K loop, the temb broadcast add
+ * (src/nn/blocks/residual.py:111-112) and the residual add (residual.py:120) as epilogues.
+ *
+ * out[n,ho,wo,co] = sum_seg sum_tap sum_c  src_seg[n, ho*stride+kh-pad, wo*stride+kw-pad, c] * W[co, k(seg,tap,c)]
+ *                   + bias[co] + addvec[n,co] + residual[n,ho,wo,co]
+ * W is the pre-packed K-major weight matrix [Cout][Ktot] bf16, K ordered (segment, tap=kh*3+kw, channel).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define FM_CONV_MAX_SEG 4
+
+typedef struct fm_conv_seg {
+  const void* src;   /* bf16 NHWC [B][H][W][C]                                        */
+  int32_t C;         /* channels of this segment (multiple of 8)                      */
+  int32_t ksize;     /* 1 or 3 (3 => pad 1, 1 => pad 0)                               */
+  int32_t upsample;  /* 1: the segment is read through a nearest-2x upsample (src is [B][H/2][W/2][C]) */
+  int32_t _pad;
+} fm_conv_seg;
+
+typedef struct fm_conv_params {
+  fm_conv_seg seg[FM_CONV_MAX_SEG];
+  int32_t nseg;
+  int32_t B, H, W;         /* input spatial size (after the optional upsample)          */
+  int32_t stride;          /* 1 or 2; output is ceil(H/stride) x ceil(W/stride)          */
+  int32_t Cout;            /* multiple of 8                                              */
+  int32_t _pad0;
+  const void* weight;      /* bf16 [Cout][Ktot], Ktot = sum_seg ksize^2 * C               */
+  const float* bias;       /* fp32 [Cout] or NULL                                        */
+  const float* addvec;     /* fp32 [B][addvec_stride] per-sample channel add, or NULL    */
+  int32_t addvec_stride;
+  int32_t _pad1;
+  const void* residual;    /* bf16 NHWC [B][Ho][Wo][Cout] or NULL                        */
+  void* out;               /* bf16 NHWC [B][Ho][Wo][Cout]                                */
+  float* gn_stats;         /* fp32 [B][gn_groups][2] (sum, sumsq) accumulated over `out`, or NULL; must be zeroed by caller */
+  int32_t gn_groups;
+  int32_t _pad2;
+} fm_conv_params;
+
+int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream);
+
+/* Re-order an OIHW fp32 conv weight (or [O][I] linear weight with ksize=1) into the K-major bf16 matrix the
+ * conv kernel reads: dst[co][koff + tap*Cseg + c] = src[co][c_begin + c][kh][kw]. */
+int fm_weight_prepack_bf16(void* dst, int64_t dst_row_stride, int64_t koff, const float* src_oihw, int32_t Cout,
+                           int32_t Cin_total, int32_t c_begin, int32_t Cseg, int32_t ksize, fm_stream_t stream);
+
+/* Stem conv (tiny Cin): fp32 NCHW inputs (x and optional concatenated conditioning, src/pipelines/utils.py:204-205,
+ * unet_diffusers_nd.py:148-158,173) -> bf16 NHWC.  3x3, stride 1, pad 1.  weight fp32 OIHW, bias fp32. */
+int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale, float in_shift,
+                          const float* weight_oihw, const float* bias, void* out_nhwc_bf16, int32_t B, int32_t H,
+                          int32_t W, int32_t Cout, fm_stream_t stream);
+
+/* Head conv (tiny Cout): bf16 NHWC -> fp32 NCHW (unet_diffusers_nd.py:190, unet.py:288-292). 3x3 s1 p1. */
+int fm_conv_head_bf16_f32(const void* x_nhwc_bf16, const float* weight_oihw, const float* bias, float* out_nchw,
+                          int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K2: GroupNorm (+SiLU, +scale-shift) on NHWC bf16, fp32 statistics.
+ * Replaces nn.GroupNorm + nn.SiLU (src/nn/ops/normalization.py:11-19; residual.py:95-96,113-116;
+ * unet_diffusers_nd.py:188-189; attention.py:235-236).  Up to two sources are read as a virtual channel concat.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* stats[n][g] = (sum, sumsq) over the group; `stats` must be zeroed by the caller (or by fm_memset_f32). */
+int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
+                            int32_t groups, float* stats, fm_stream_t stream);
+/* y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), act = SiLU if silu!=0.
+ * scale_shift: fp32 [B][2*C] (scale first, then shift; residual.py:109,115) or NULL. */
+int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
+                            int32_t groups, float eps, const float* stats, const float* gamma, const float* beta,
+                            const float* scale_shift, int32_t silu, void* out, fm_stream_t stream);
+int fm_memset_f32(float* p, int64_t n, fm_stream_t stream);
+
+/* nearest-neighbour 2x upsample on NHWC bf16 (F.interpolate, src/nn/ops/upsampling.py:27) */
+int fm_upsample_nearest2x_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                               fm_stream_t stream);
+/* [B][R][C] -> [B][C][R] bf16 transpose (SpatialSelfAttention raw-reshape support, attention.py:111-115) */
+int fm_transpose_bf16(const void* x, void* out, int32_t B, int32_t R, int32_t C, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K3: softmax(QK^T/sqrt(d))V, bf16 in/out, fp32 softmax.  Replaces F.scaled_dot_product_attention
+ * (src/nn/blocks/attention.py:41-44).  Generic strides (in elements) so both the DiffusersAttentionND layout
+ * ([B][T][3C], head-major channels) and SpatialSelfAttention's raw reshape ([b][heads][T][3*dh]) are served.
+ * head_dim in {8,16,32,64}.
+ * ---------------------------------------------------------------------------------------------------------- */
+int fm_attention_bf16(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t heads, int32_t Tq,
+                      int32_t Tk, int32_t head_dim, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
+                      int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float scale,
+                      fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Time embedding path (fp32).  timestep_embedding (src/nn/ops/time_embedding.py:4-32) and the small Linear layers
+ * (models/unet/utils.py:9-24, residual.py:99-108).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* t: fp32 [B] (or, if t_table != NULL, every row uses t_table[*step_dev]); out fp32 [B][dim] */
+int fm_timestep_embedding_f32(const float* t, const float* t_table, const int32_t* step_dev, float* out, int32_t B,
+                              int32_t dim, float max_period, int32_t flip_sin_to_cos, float freq_shift,
+                              fm_stream_t stream);
+/* y[b][o] = bias[o] + bias2[o] + sum_i f(x[b][i]) * W[o][i]; f = SiLU if silu_in; y = SiLU(y) if silu_out */
+int fm_linear_f32(const float* x, const float* W, const float* bias, const float* bias2, float* y, int32_t B,
+                  int32_t I, int32_t O, int32_t silu_in, int32_t silu_out, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K4: one fused elementwise kernel per sampler step (fp32 state, round-to-nearest mul/add, no FMA contraction).
+ * Replaces diffusers' Scheduler.step called at src/pipelines/utils.py:218.  Coefficients are precomputed on the
+ * host exactly as diffusers computes its 0-dim fp32 scalars and live in a device table [nsteps][ncoef];
+ * the row is `step_host`, or `*step_dev` when step_dev != NULL (CUDA-graph replay).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define FM_FLOWMATCH_NCOEF 1 /* {dt = sigma[i+1]-sigma[i]} */
+int fm_sched_flowmatch_f32(float* x_out, const float* x, const float* v, const float* coef, const int32_t* step_dev,
+                           int32_t step_host, int64_t n, fm_stream_t stream);
+#define FM_DDIM_NCOEF 4 /* {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-std^2)} */
+int fm_sched_ddim_f32(float* x_out, const float* x, const float* eps, const float* coef, const int32_t* step_dev,
+                      int32_t step_host, int32_t clip, float clip_range, int64_t n, fm_stream_t stream);
+#define FM_DPMPP_NCOEF 8 /* {sigma_s, alpha_s, c1, c2, c3, inv_r0, second_order, unused} */
+int fm_sched_dpmpp2m_f32(float* x_out, float* m_cur, const float* x, const float* eps, const float* m_prev,
+                         const float* coef, const int32_t* step_dev, int32_t step_host, int64_t n,
+                         fm_stream_t stream);
+/* x_out = a[n]*x0 + b[n]*noise (scheduler.add_noise, src/utils/model_utils/diffusion_utils.py:222) */
+int fm_sched_add_noise_f32(float* x_out, const float* x0, const float* noise, const float* a, const float* b,
+                           int32_t B, int64_t per_sample, fm_stream_t stream);
+/* *ctr += delta (device-side step counter for graph replay) */
+int fm_counter_add(int32_t* ctr, int32_t delta, fm_stream_t stream);
+/* y = clamp(x, lo, hi) fp32 (samplers/diffusion_like.py:135) */
+int fm_clamp_f32(float* y, const float* x, float lo, float hi, int64_t n, fm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMDM_B200_H */

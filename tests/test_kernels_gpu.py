@@ -1,0 +1,182 @@
+"""Per-kernel parity on the B200: every C-ABI kernel against a plain PyTorch fp32 reference of the same op
+(the floating-point kernels) or against the oracle bit-for-bit (the scheduler steps)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from fmdm_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _nhwc(t):
+    return t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def _rel_l2(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _conv_case(B, H, W, cins, cout, ks_list, stride=1, bias=True, addvec=False, residual=False, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xs = [_bf16r(torch.randn(B, c, H, W, generator=g)).to(DEV) for c in cins]
+    ws = [_bf16r(torch.randn(cout, c, k, k, generator=g) / math.sqrt(c * k * k)).to(DEV) for c, k in zip(cins, ks_list)]
+    bvec = torch.randn(cout, generator=g).to(DEV) if bias else None
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    av = torch.randn(B, cout, generator=g).to(DEV) if addvec else None
+    res = _bf16r(torch.randn(B, cout, Ho, Wo, generator=g)).to(DEV) if residual else None
+    ref = torch.zeros(B, cout, Ho, Wo, device=DEV)
+    for x, w, k in zip(xs, ws, ks_list):
+        ref = ref + F.conv2d(x, w, None, stride=stride, padding=k // 2)
+    if bias:
+        ref = ref + bvec.view(1, -1, 1, 1)
+    if addvec:
+        ref = ref + av.view(B, cout, 1, 1)
+    if residual:
+        ref = ref + res
+    packed = ops.pack_conv_weight([(w, 0, c) for w, c in zip(ws, cins)])
+    out = ops.conv2d([_nhwc(x) for x in xs], packed, stride=stride, bias=bvec, addvec=av,
+                     residual=_nhwc(res) if residual else None)
+    torch.cuda.synchronize()
+    return out.float(), ref
+
+
+CONV_CASES = [
+    # B, H, W, cins, cout, ks, stride, bias, addvec, residual
+    (1, 16, 16, [64], 64, [1], 1, False, False, False),
+    (1, 16, 16, [128], 128, [1], 1, True, False, False),
+    (1, 16, 16, [64], 128, [3], 1, True, False, False),
+    (2, 32, 32, [128], 256, [3], 1, True, True, True),
+    (2, 32, 32, [128], 128, [3], 2, True, False, False),
+    (2, 16, 16, [64, 128], 128, [3, 3], 1, True, True, False),
+    (2, 16, 16, [128, 64, 128], 128, [3, 1, 1], 1, True, True, False),
+    (3, 28, 28, [64], 64, [3], 1, True, False, True),
+    (3, 14, 14, [128], 128, [3], 1, True, True, True),
+    (3, 7, 7, [128], 128, [3], 1, True, True, True),
+    (3, 28, 28, [64], 64, [3], 2, True, False, False),
+    (3, 14, 14, [128], 128, [3], 2, True, False, False),
+    (2, 16, 16, [1024], 512, [3], 1, True, True, True),
+    (1, 16, 16, [32], 72, [3], 1, True, False, False),
+    (1, 64, 256, [128], 128, [3], 1, True, True, True),
+    (2, 33, 35, [64], 64, [3], 2, True, False, False),
+    (1, 1024, 1, [512], 1536, [1], 1, True, False, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "B{}_{}x{}_cin{}_cout{}_k{}_s{}".format(
+    c[0], c[1], c[2], "+".join(map(str, c[3])), c[4], "".join(map(str, c[5])), c[6]))
+def test_conv2d_igemm(case):
+    out, ref = _conv_case(*case)
+    err = _rel_l2(out, ref)
+    assert err < 6e-3, f"rel L2 {err}"
+    assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 0.05
+
+
+def test_group_norm_silu():
+    g = torch.Generator().manual_seed(1)
+    for (B, C, H, W, groups) in [(2, 128, 32, 32, 32), (3, 64, 7, 7, 32), (2, 512, 16, 16, 32), (1, 256, 64, 64, 32)]:
+        x = _bf16r(torch.randn(B, C, H, W, generator=g) * 2 + 0.5).to(DEV)
+        gamma = torch.randn(C, generator=g).to(DEV)
+        beta = torch.randn(C, generator=g).to(DEV)
+        for silu in (True, False):
+            ref = F.group_norm(x, groups, gamma, beta, 1e-5)
+            if silu:
+                ref = F.silu(ref)
+            out = ops.group_norm([_nhwc(x)], groups, 1e-5, gamma, beta, silu=silu).float()
+            assert _rel_l2(out, ref) < 5e-3
+
+
+def test_group_norm_concat_and_scale_shift():
+    g = torch.Generator().manual_seed(2)
+    B, C0, C1, H, W = 2, 256, 128, 16, 16
+    x0 = _bf16r(torch.randn(B, C0, H, W, generator=g)).to(DEV)
+    x1 = _bf16r(torch.randn(B, C1, H, W, generator=g) * 3 - 1).to(DEV)
+    gamma = torch.randn(C0 + C1, generator=g).to(DEV)
+    beta = torch.randn(C0 + C1, generator=g).to(DEV)
+    ref = F.silu(F.group_norm(torch.cat([x0, x1], 1), 32, gamma, beta, 1e-5))
+    out = ops.group_norm([_nhwc(x0), _nhwc(x1)], 32, 1e-5, gamma, beta, silu=True).float()
+    assert _rel_l2(out, ref) < 5e-3
+    ss = torch.randn(B, 2 * C0, generator=g).to(DEV) * 0.5
+    gam0, bet0 = gamma[:C0].contiguous(), beta[:C0].contiguous()
+    ref = F.group_norm(x0, 32, gam0, bet0, 1e-5) * (1 + ss[:, :C0, None, None]) + ss[:, C0:, None, None]
+    ref = F.silu(ref)
+    out = ops.group_norm([_nhwc(x0)], 32, 1e-5, gam0, bet0, silu=True, scale_shift=ss).float()
+    assert _rel_l2(out, ref) < 5e-3
+
+
+def test_stem_and_head():
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 40, 36
+    x0 = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    x1 = torch.rand(B, 1, H, W, generator=g).to(DEV)
+    w = (torch.randn(128, 2, 3, 3, generator=g) / 4).to(DEV)
+    b = torch.randn(128, generator=g).to(DEV)
+    ref = F.conv2d(torch.cat([x0, x1], 1), w, b, padding=1)
+    out = ops.conv_stem(x0, x1, w, b).float()
+    assert _rel_l2(out, ref) < 4e-3
+    ref = F.conv2d(2 * x0 - 1, w[:, :1].contiguous(), b, padding=1)
+    out = ops.conv_stem(x0, None, w[:, :1].contiguous(), b, in_scale=2.0, in_shift=-1.0).float()
+    assert _rel_l2(out, ref) < 4e-3
+    for cout in (1, 4):
+        xh = _bf16r(torch.randn(B, 128, H, W, generator=g)).to(DEV)
+        wh = (torch.randn(cout, 128, 3, 3, generator=g) / 30).to(DEV)
+        bh = torch.randn(cout, generator=g).to(DEV)
+        ref = F.conv2d(xh, wh, bh, padding=1)
+        out = ops.conv_head(_nhwc(xh), wh, bh)
+        assert out.dtype == torch.float32 and out.is_contiguous()
+        assert _rel_l2(out, ref) < 1e-4
+
+
+def test_upsample_transpose():
+    g = torch.Generator().manual_seed(4)
+    x = _bf16r(torch.randn(2, 64, 9, 7, generator=g)).to(DEV)
+    out = ops.upsample_nearest2x(_nhwc(x)).float()
+    assert torch.equal(out, F.interpolate(x, scale_factor=2, mode="nearest"))
+    t = torch.randn(3, 50, 72, generator=g).to(DEV).to(torch.bfloat16)
+    assert torch.equal(ops.transpose_bf16(t), t.transpose(1, 2).contiguous())
+
+
+@pytest.mark.parametrize("hd,heads,T", [(8, 64, 1024), (8, 16, 256), (64, 4, 256), (16, 8, 100), (32, 2, 77)])
+def test_attention(hd, heads, T):
+    g = torch.Generator().manual_seed(5)
+    B = 2
+    C = hd * heads
+    qkv = _bf16r(torch.randn(B, T, 3 * C, generator=g)).to(DEV)
+    q, k, v = [t.reshape(B, T, heads, hd).transpose(1, 2) for t in qkv.split(C, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, C)
+    qkv16 = qkv.to(torch.bfloat16).contiguous()
+    out = torch.empty(B, T, C, dtype=torch.bfloat16, device=DEV)
+    ops.attention(qkv16, qkv16[:, :, C:], qkv16[:, :, 2 * C:], out, batch=B, heads=heads, tq=T, tk=T, head_dim=hd,
+                  q_strides=(T * 3 * C, hd, 3 * C), kv_strides=(T * 3 * C, hd, 3 * C), o_strides=(T * C, hd, C))
+    assert _rel_l2(out.float(), ref) < 6e-3
+
+
+def test_timestep_embedding_and_linear():
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle.denoiser import timestep_embedding as ref_temb
+
+    t = torch.tensor([1000.0, 979.6122, 500.5, 21.3877, 1.0, 0.0], device=DEV)
+    for dim, flip, shift in [(128, True, 0), (64, False, 0), (128, True, 1), (33, False, 0)]:
+        out = ops.timestep_embedding(t, dim, flip_sin_to_cos=flip, freq_shift=shift)
+        ref = ref_temb(t.cpu(), dim, flip_sin_to_cos=flip, freq_shift=shift).to(DEV)
+        assert float((out - ref).abs().max()) < 2e-4
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(16, 512, generator=g).to(DEV)
+    w = (torch.randn(384, 512, generator=g) / 22).to(DEV)
+    b = torch.randn(384, generator=g).to(DEV)
+    b2 = torch.randn(384, generator=g).to(DEV)
+    ref = F.linear(F.silu(x), w, b) + b2
+    out = ops.linear_f32(x, w, b, b2, silu_in=True)
+    assert float((out - ref).abs().max()) < 1e-4
+    ref = F.silu(F.linear(x, w, b))
+    out = ops.linear_f32(x, w, b, silu_out=True)
+    assert float((out - ref).abs().max()) < 1e-4
