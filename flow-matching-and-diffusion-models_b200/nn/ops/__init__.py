@@ -1,0 +1,7 @@
+from .convolution import ConvND, ConvTransposeND
+from .normalization import RMSNormND, fused_group_norm, make_group_norm
+from .time_embedding import timestep_embedding
+from .upsampling import DownsampleND, UpsampleND
+
+__all__ = ["ConvND", "ConvTransposeND", "RMSNormND", "make_group_norm", "fused_group_norm", "timestep_embedding",
+           "UpsampleND", "DownsampleND"]

@@ -1,0 +1,51 @@
+"""GroupNorm construction (`src/nn/ops/normalization.py:11-19`) plus the fused GroupNorm(+SiLU) entry point."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..._runtime import f32, out_of_scope
+
+
+def make_group_norm(channels: int, groups: int = 32, eps: float = 1e-5) -> nn.GroupNorm:
+    """GroupNorm whose group count falls back to the largest divisor of `channels` not above `groups`."""
+    g = max(1, min(groups, channels))
+    while g > 1 and channels % g:
+        g -= 1
+    return nn.GroupNorm(g, channels, eps=eps)
+
+
+def fused_group_norm(norm: nn.GroupNorm, srcs: Sequence[torch.Tensor], *, silu: bool,
+                     scale_shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Run `norm` (+SiLU, + (1+scale)*y+shift) over the virtual concat of `srcs` with the K2 kernel."""
+    srcs = [ops.to_nhwc_bf16(s) for s in srcs]
+    if len(srcs) > 2:
+        srcs = [ops.to_nhwc_bf16(torch.cat(srcs, 1))]
+    if any(s.shape[1] % 8 for s in srcs):
+        out_of_scope(f"GroupNorm over {[s.shape[1] for s in srcs]} channels (needs multiples of 8)")
+        x = torch.cat([s.float() for s in srcs], 1)
+        y = torch.nn.functional.group_norm(x, norm.num_groups, norm.weight.float(), norm.bias.float(), norm.eps)
+        if scale_shift is not None:
+            c = y.shape[1]
+            y = y * (1 + scale_shift[:, :c, None, None]) + scale_shift[:, c:, None, None]
+        return torch.nn.functional.silu(y) if silu else y
+    return ops.group_norm(srcs, norm.num_groups, norm.eps, f32(norm.weight), f32(norm.bias), silu=silu,
+                          scale_shift=scale_shift)
+
+
+class RMSNormND(nn.Module):
+    """API-parity shell for `src/nn/ops/normalization.py:22-34` (not on any BASELINE path; out of scope)."""
+
+    def __init__(self, channels: int, eps: float = 1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(channels))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        out_of_scope("RMSNormND")
+        x = x.float()
+        rms = torch.sqrt(torch.mean(x.pow(2), dim=tuple(range(1, x.ndim)), keepdim=True) + self.eps)
+        return self.weight.view(1, -1, *([1] * (x.ndim - 2))) * x / rms

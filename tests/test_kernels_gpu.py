@@ -11,6 +11,9 @@ pytestmark = pytest.mark.gpu
 from fmdm_b200 import ops  # noqa: E402
 
 DEV = "cuda"
+# the fp32 references must be true fp32 (cuDNN/cuBLAS default to TF32 for convs)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def _bf16r(t):

@@ -1,0 +1,54 @@
+"""Micro-benchmark of the conv implicit-GEMM kernel on the LDCT-512 shapes (SURVEY.md §8d shape list)."""
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fmdm_b200 import ops  # noqa: E402
+
+SHAPES = [  # (Cin segments, Cout, k, stride, H(in), count per forward)
+    ([128], 128, 3, 1, 512, 8), ([128, 128], 128, 3, 1, 512, 3), ([128], 128, 3, 1, 256, 7),
+    ([256], 256, 3, 1, 128, 7), ([256, 256], 256, 3, 1, 128, 2), ([256], 256, 3, 1, 256, 1),
+    ([128, 128], 128, 3, 1, 256, 2), ([256, 128], 128, 3, 1, 256, 1), ([128, 128], 128, 1, 1, 512, 3),
+    ([256], 256, 3, 1, 64, 7), ([512], 512, 3, 1, 32, 7), ([512], 512, 3, 1, 16, 11), ([512, 512], 512, 3, 1, 32, 2),
+    ([128], 128, 3, 2, 512, 1), ([512], 1536, 1, 1, 32, 5),
+]
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    dev = "cuda"
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    rows = []
+    tot_t = tot_f = 0.0
+    for cins, cout, k, s, H, cnt in SHAPES:
+        xs = [torch.randn(B, H, H, c, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2) for c in cins]
+        ws = [torch.randn(cout, c, k, k, device=dev) * 0.05 for c in cins]
+        pw = ops.pack_conv_weight([(w, 0, c) for w, c in zip(ws, cins)])
+        bias = torch.randn(cout, device=dev)
+        Ho = (H + s - 1) // s
+        out = ops.empty_nhwc(B, cout, Ho, Ho, dev)
+        for _ in range(3):
+            ops.conv2d(xs, pw, stride=s, bias=bias, out=out)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.conv2d(xs, pw, stride=s, bias=bias, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2]
+        flops = 2.0 * B * Ho * Ho * cout * sum(cins) * k * k
+        rows.append(dict(cin=cins, cout=cout, k=k, stride=s, H=H, ms=round(t, 4), tflops=round(flops / t / 1e9, 1)))
+        tot_t += t * cnt
+        tot_f += flops * cnt
+        print(rows[-1], flush=True)
+    print(json.dumps(dict(B=B, weighted_ms=tot_t, weighted_tflops=tot_f / tot_t / 1e9)))
+
+
+if __name__ == "__main__":
+    main()
