@@ -1,0 +1,47 @@
+"""BaseUNetND — the forward contract of the denoisers (`src/models/unet/base.py:10-53`)."""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+
+class BaseUNetND(nn.Module, ABC):
+    """forward(x, t, context=None, context_ca=None) -> prediction with the shape/dtype of the reference (fp32 NCHW)."""
+
+    def _normalize_timesteps(self, t, x: torch.Tensor) -> torch.Tensor:
+        if not torch.is_tensor(t):
+            t = torch.tensor([t], device=x.device, dtype=torch.long)  # python scalars become int64, as upstream
+        if t.ndim == 0:
+            t = t[None].to(x.device)
+        return t.expand(x.shape[0]).to(x.device)
+
+    def _prepare_input(self, x, context, context_ca):
+        return x
+
+    @abstractmethod
+    def _build_time_embedding(self, t: Optional[torch.Tensor], x: torch.Tensor, *, t_table=None,
+                              step_dev=None) -> torch.Tensor:
+        raise NotImplementedError
+
+    @abstractmethod
+    def _run_network(self, x, emb: torch.Tensor, context_ca: Optional[torch.Tensor]) -> torch.Tensor:
+        raise NotImplementedError
+
+    def _postprocess_output(self, y: torch.Tensor) -> torch.Tensor:
+        return y
+
+    def forward(self, x: torch.Tensor, t, context: Optional[torch.Tensor] = None,
+                context_ca: Optional[torch.Tensor] = None, *, t_table: Optional[torch.Tensor] = None,
+                step_dev: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        """`t_table`/`step_dev` (fp32 device table + int32 device cursor) replace `t` under CUDA-graph replay:
+        every sample of the batch then uses the timestep `t_table[*step_dev]`."""
+        if t_table is not None:
+            emb = self._build_time_embedding(None, x, t_table=t_table, step_dev=step_dev)
+        else:
+            t = self._normalize_timesteps(t, x)
+            emb = self._build_time_embedding(t, x)
+        y = self._run_network(self._prepare_input(x, context, context_ca), emb, context_ca)
+        return self._postprocess_output(y)

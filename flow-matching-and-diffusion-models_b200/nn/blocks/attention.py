@@ -1,0 +1,247 @@
+"""Attention blocks — drop-ins for `src/nn/blocks/attention.py` on the B200 kernels.
+
+In scope: `DiffusersAttentionND` self-attention (GN -> fused QKV 1x1 GEMM on tcgen05 ->
+K3 softmax(QK^T)V -> out-proj GEMM with the residual in its epilogue) and `SpatialSelfAttention` including the
+reference's raw-memory head split.  Cross-attention variants and linear attention keep the API but are out of scope.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from ..._runtime import ParamCache, f32, out_of_scope
+from .common import zero_module
+
+
+class QKVAttention(nn.Module):
+    """softmax(q k^T / sqrt(d)) v over (N, heads, T, d) tensors (`attention.py:10-50`)."""
+
+    def __init__(self, efficient_attn: bool = True, dropout: float = 0.0):
+        super().__init__()
+        self.dropout = dropout
+        self.efficient_attn = bool(efficient_attn)
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+        if q.dim() != 4 or (self.training and self.dropout > 0) or q.shape[-1] not in (8, 16, 32, 64) \
+                or v.shape[-1] != q.shape[-1]:
+            out_of_scope(f"QKVAttention on {tuple(q.shape)} (dropout={self.dropout})")
+            return F.scaled_dot_product_attention(q, k, v, dropout_p=self.dropout if self.training else 0.0)
+        ops.require_cuda(q, "QKVAttention")
+        b, h, tq, d = q.shape
+        tk = k.shape[2]
+        q, k, v = [t.to(torch.bfloat16).contiguous() for t in (q, k, v)]
+        out = torch.empty((b, h, tq, d), dtype=torch.bfloat16, device=q.device)
+        ops.attention(q, k, v, out, batch=b, heads=h, tq=tq, tk=tk, head_dim=d, q_strides=(h * tq * d, tq * d, d),
+                      kv_strides=(h * tk * d, tk * d, d), o_strides=(h * tq * d, tq * d, d))
+        return out
+
+
+class LinearQKVAttention(nn.Module):
+    """Softmax-factorised linear attention (`attention.py:53-70`); not on any BASELINE path (out of scope)."""
+
+    def __init__(self, dropout: float = 0.0, eps: float = 1e-6):
+        super().__init__()
+        self.dropout = dropout
+        self.eps = eps
+
+    def forward(self, q, k, v):
+        out_of_scope("LinearQKVAttention")
+        ks, qs = F.softmax(k.float(), dim=-2), F.softmax(q.float(), dim=-1)
+        ctx = torch.einsum("...nd,...ne->...de", ks, v.float())
+        ctx = ctx / (ks.sum(dim=-2).unsqueeze(-1) + self.eps)
+        return F.dropout(torch.einsum("...nd,...de->...ne", qs, ctx), p=self.dropout, training=self.training)
+
+
+class ContextBlock(nn.Module):
+    """Base class of layers consuming an external context tensor."""
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:  # pragma: no cover
+        raise NotImplementedError
+
+
+class SpatialSelfAttention(nn.Module):
+    """CompVis-style MHSA block (`attention.py:82-117`): GN -> Conv1d qkv -> *raw reshape* head split -> SDPA ->
+    raw reshape back -> zero-init Conv1d -> + x.  The raw reshape re-reads the channel-major (b, 3*inner, T) buffer
+    as (b, heads, T, 3*dh); we reproduce it exactly by transposing the NHWC GEMM output to channel-major once and
+    handing K3 the matching strides."""
+
+    def __init__(self, dim: int, heads: int = 4, dim_head: int = 64, use_linear: bool = False,
+                 use_efficient_attn: bool = True):
+        super().__init__()
+        self.dim, self.heads, self.dim_head = dim, heads, dim_head
+        self.inner_dim = dim_head * heads
+        self.use_linear = use_linear
+        self.norm = nn.GroupNorm(max(1, math.gcd(dim, 32)), dim)
+        self.qkv = nn.Conv1d(dim, self.inner_dim * 3, 1)
+        self.attention = LinearQKVAttention() if use_linear else QKVAttention(efficient_attn=use_efficient_attn)
+        self.proj_out = zero_module(nn.Conv1d(self.inner_dim, self.dim, 1))
+        self._cache = ParamCache()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        b, c, *spatial = x.shape
+        if self.use_linear or len(spatial) != 2 or c % 8 or self.dim_head not in (8, 16, 32, 64):
+            out_of_scope(f"SpatialSelfAttention(use_linear={self.use_linear}, spatial={spatial}, dim_head={self.dim_head})")
+            return self._eager(x.float())
+        x = ops.to_nhwc_bf16(x)
+        hh, ww = spatial
+        t = hh * ww
+        inner, dh, nh = self.inner_dim, self.dim_head, self.heads
+        n = ops.group_norm([x], self.norm.num_groups, self.norm.eps, f32(self.norm.weight), f32(self.norm.bias),
+                           silu=False)
+        wq = self._cache.get("qkv", [self.qkv.weight],
+                             lambda: ops.pack_conv_weight([(self.qkv.weight.squeeze(-1), 0, c)]))
+        wo = self._cache.get("out", [self.proj_out.weight],
+                             lambda: ops.pack_conv_weight([(self.proj_out.weight.squeeze(-1), 0, inner)]))
+        qkv = ops.conv2d([n], wq, bias=f32(self.qkv.bias))                      # NHWC == [b][T][3*inner]
+        qkv_cm = ops.transpose_bf16(qkv.permute(0, 2, 3, 1).reshape(b, t, 3 * inner))  # [b][3*inner][T]
+        att = torch.empty((b, nh, t, dh), dtype=torch.bfloat16, device=x.device)
+        flat = qkv_cm.view(-1)
+        ops.attention(flat, flat[dh:], flat[2 * dh:], att, batch=b, heads=nh, tq=t, tk=t, head_dim=dh,
+                      q_strides=(3 * inner * t, t * 3 * dh, 3 * dh), kv_strides=(3 * inner * t, t * 3 * dh, 3 * dh),
+                      o_strides=(nh * t * dh, t * dh, dh))
+        # raw reshape (b, heads, T, dh) -> (b, inner, T), then back to NHWC for the projection GEMM
+        h_tc = ops.transpose_bf16(att.view(b, inner, t))                          # [b][T][inner]
+        h_nhwc = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
+        return ops.conv2d([h_nhwc], wo, bias=f32(self.proj_out.bias), residual=x)
+
+    def _eager(self, x):
+        b, c, *spatial = x.shape
+        t = x.reshape(b, c, -1)
+        qkv = self.qkv(self.norm(t))
+        qkv = qkv.reshape(b, self.heads, qkv.shape[-1], -1)
+        q, k, v = qkv.chunk(3, dim=-1)
+        h = self.attention(q, k, v).float().reshape(b, self.inner_dim, -1)
+        return (t + self.proj_out(h)).reshape(b, c, *spatial)
+
+
+class SpatialCrossAttention(ContextBlock):
+    """API-parity shell of `attention.py:120-189` (conditioning:"attention" configs; out of scope)."""
+
+    def __init__(self, dim: int, context_dim: int, heads: int = 4, dim_head: int = 64, use_linear: bool = False,
+                 use_efficient_attn: bool = True):
+        super().__init__()
+        self.dim, self.context_dim, self.heads, self.dim_head = dim, context_dim, heads, dim_head
+        self.inner_dim = dim_head * heads
+        self.norm = nn.GroupNorm(max(1, math.gcd(dim, 32)), dim)
+        self.context_norm = nn.GroupNorm(max(1, math.gcd(context_dim, 32)), context_dim)
+        self.q_proj = nn.Conv1d(dim, self.inner_dim, 1)
+        self.kv_proj = nn.Conv1d(context_dim, self.inner_dim * 2, 1)
+        self.attention = LinearQKVAttention() if use_linear else QKVAttention(efficient_attn=use_efficient_attn)
+        self.proj_out = zero_module(nn.Conv1d(self.inner_dim, self.dim, 1))
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        if context is None:
+            raise ValueError("SpatialCrossAttention requires a non-empty context tensor.")
+        out_of_scope("SpatialCrossAttention")
+        x = x.float()
+        context = context.float()
+        b, c, *spatial = x.shape
+        xf = x.reshape(b, c, -1)
+        if context.dim() == 3:
+            if context.shape[1] == self.context_dim:
+                cf = context
+            elif context.shape[-1] == self.context_dim:
+                cf = context.transpose(1, 2)
+            else:
+                raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {context.shape}.")
+        else:
+            if context.shape[1] != self.context_dim:
+                raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {context.shape}.")
+            cf = context.reshape(context.shape[0], context.shape[1], -1)
+        q = self.q_proj(self.norm(xf))
+        kv = self.kv_proj(self.context_norm(cf))
+        q = q.reshape(b, self.heads, q.shape[-1], -1)
+        kv = kv.reshape(b, self.heads, kv.shape[-1], -1)
+        k, v = kv.chunk(2, dim=-1)
+        h = F.scaled_dot_product_attention(q, k, v).reshape(b, self.inner_dim, -1)
+        return (xf + self.proj_out(h)).reshape(b, c, *spatial)
+
+
+class DiffusersAttentionND(nn.Module):
+    """Diffusers-style attention over flattened spatial tokens (`attention.py:192-274`), self-attention on the
+    B200 kernels: q/k/v Linear layers run as ONE 1x1 implicit GEMM (N = 3C), to_out as another with the residual
+    add in its epilogue.  Children / state_dict keys: group_norm, to_q, to_k, to_v, to_out.0."""
+
+    def __init__(self, channels: int, heads: int = 1, context_dim: int | None = None, norm_num_groups: int = 32,
+                 eps: float = 1e-5, dropout: float = 0.0, use_efficient_attn: bool = True):
+        super().__init__()
+        self.channels = channels
+        self.heads = max(1, heads)
+        self.head_dim = channels // self.heads
+        self.context_dim = int(context_dim) if context_dim is not None else None
+        self.group_norm = nn.GroupNorm(max(1, math.gcd(channels, norm_num_groups)), channels, eps=eps)
+        self.to_q = nn.Linear(channels, channels)
+        kv_in = channels if self.context_dim is None else self.context_dim
+        self.context_norm = None if self.context_dim is None else nn.GroupNorm(
+            max(1, math.gcd(self.context_dim, norm_num_groups)), self.context_dim, eps=eps)
+        self.to_k = nn.Linear(kv_in, channels)
+        self.to_v = nn.Linear(kv_in, channels)
+        self.to_out = nn.ModuleList([nn.Linear(channels, channels), nn.Dropout(dropout)])
+        self.attention = QKVAttention(efficient_attn=use_efficient_attn, dropout=dropout)
+        self.dropout = dropout
+        self._cache = ParamCache()
+
+    def forward(self, hidden_states: torch.Tensor, context: torch.Tensor | None = None) -> torch.Tensor:
+        b, c = hidden_states.shape[:2]
+        spatial = hidden_states.shape[2:]
+        if self.context_dim is not None:
+            if context is None:
+                raise ValueError("DiffusersAttentionND cross-attention requires a non-empty context tensor.")
+            out_of_scope("DiffusersAttentionND cross-attention")
+            return self._eager(hidden_states.float(), context.float())
+        if len(spatial) != 2 or c % 8 or self.head_dim not in (8, 16, 32, 64) or (self.training and self.dropout > 0):
+            out_of_scope(f"DiffusersAttentionND(spatial={tuple(spatial)}, head_dim={self.head_dim})")
+            return self._eager(hidden_states.float(), None)
+        x = ops.to_nhwc_bf16(hidden_states)
+        hh, ww = spatial
+        t = hh * ww
+        gn = self.group_norm
+        n = ops.group_norm([x], gn.num_groups, gn.eps, f32(gn.weight), f32(gn.bias), silu=False)
+
+        def build_qkv():
+            w = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0).detach()
+            bias = torch.cat([self.to_q.bias, self.to_k.bias, self.to_v.bias], 0).detach().float().contiguous()
+            return ops.pack_conv_weight([(w, 0, c)]), bias
+
+        wqkv, bqkv = self._cache.get("qkv", [self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias,
+                                             self.to_k.bias, self.to_v.bias], build_qkv)
+        wout = self._cache.get("out", [self.to_out[0].weight],
+                               lambda: ops.pack_conv_weight([(self.to_out[0].weight, 0, c)]))
+        qkv = ops.conv2d([n], wqkv, bias=bqkv)                                   # NHWC == [b][T][3C]
+        flat = qkv.permute(0, 2, 3, 1).reshape(-1)
+        att = ops.empty_nhwc(b, c, hh, ww, x.device)                             # [b][T][C]
+        hd = self.head_dim
+        ops.attention(flat, flat[c:], flat[2 * c:], att.permute(0, 2, 3, 1).reshape(-1), batch=b, heads=self.heads,
+                      tq=t, tk=t, head_dim=hd, q_strides=(t * 3 * c, hd, 3 * c), kv_strides=(t * 3 * c, hd, 3 * c),
+                      o_strides=(t * c, hd, c))
+        return ops.conv2d([att], wout, bias=f32(self.to_out[0].bias), residual=x)
+
+    def _eager(self, hidden_states, context):
+        b, c = hidden_states.shape[:2]
+        spatial = hidden_states.shape[2:]
+        x = self.group_norm(hidden_states.reshape(b, c, -1)).transpose(1, 2)
+        q = self.to_q(x)
+        src = x
+        if self.context_dim is not None:
+            if context.dim() == 3:
+                if context.shape[1] == self.context_dim:
+                    ctx = context
+                elif context.shape[-1] == self.context_dim:
+                    ctx = context.transpose(1, 2)
+                else:
+                    raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {tuple(context.shape)}.")
+            else:
+                if context.shape[1] != self.context_dim:
+                    raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {tuple(context.shape)}.")
+                ctx = context.reshape(context.shape[0], context.shape[1], -1)
+            src = self.context_norm(ctx).transpose(1, 2)
+        k, v = self.to_k(src), self.to_v(src)
+        q, k, v = [z.view(b, -1, self.heads, self.head_dim).transpose(1, 2) for z in (q, k, v)]
+        out = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, -1, c)
+        out = self.to_out[1](self.to_out[0](out))
+        return out.transpose(1, 2).reshape(b, c, *spatial) + hidden_states

@@ -171,7 +171,7 @@ class DPMSolverPPOracle:
         N = int(num_inference_steps)
         last_timestep = T  # lambda_min_clipped = -inf => nothing clipped
         ts = np.linspace(0, last_timestep - 1, N + 1).round()[::-1][:-1].copy().astype(np.int64)
-        sig_all = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig_all = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig_all)), sig_all)
         sig = np.concatenate([sig, [0.0]]).astype(np.float32)  # final_sigmas_type == "zero"
         self.sigmas = torch.from_numpy(sig)

@@ -1,0 +1,138 @@
+"""Pins the oracle's scheduler restatement with analytic known-answer tests (the reference holds no golden vector
+for any scheduler and diffusers is not installable here: SURVEY.md §8c, "parity unpinned")."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.sampling import make_scheduler, sample_loop, select_timesteps
+from oracle.schedulers import DDIMOracle, DPMSolverPPOracle, FlowMatchEulerOracle
+
+
+def test_flowmatch_schedule_values():
+    s = FlowMatchEulerOracle(1000)
+    assert s.sigma_min == pytest.approx(0.0010000000474974513, abs=0) and s.sigma_max == 1.0
+    s.set_timesteps(50)
+    ts = s.timesteps
+    assert ts.dtype == torch.float32 and ts.shape == (50,)
+    assert float(ts[0]) == 1000.0 and float(ts[-1]) == 1.0
+    assert float(ts[1]) == pytest.approx(979.6122, abs=1e-3) and float(ts[-2]) == pytest.approx(21.3877, abs=1e-3)
+    assert s.sigmas.shape == (51,) and float(s.sigmas[-1]) == 0.0
+    dts = s.sigmas[1:] - s.sigmas[:-1]
+    assert float(dts.double().sum()) == pytest.approx(-1.0, abs=1e-6)
+
+
+def test_flowmatch_point_mass_recovery():
+    # data distribution = point mass at x0: the exact velocity field is v(x, t) = (x - x0) / sigma_t ... with the
+    # reference's training target (noise - x0) the ODE x_t = (1-s) x0 + s*noise has dx/ds = noise - x0 = (x - x0)/s
+    x0 = torch.tensor([[[[0.25, -0.5], [0.75, 1.0]]]])
+    s = FlowMatchEulerOracle(1000)
+    g = torch.Generator().manual_seed(0)
+    noise = torch.randn(x0.shape, generator=g)
+    state = {}
+
+    def model(x, t):
+        sigma = (t / 1000.0).view(-1, 1, 1, 1)
+        return (x - x0) / sigma
+
+    out = sample_loop(model, s, 50, noise)
+    assert float((out - x0).abs().max()) < 1e-6
+
+
+def test_flowmatch_rejects_integer_timesteps():
+    s = FlowMatchEulerOracle(1000)
+    s.set_timesteps(10)
+    with pytest.raises(ValueError):
+        s.step(torch.zeros(1), 5, torch.zeros(1))
+
+
+def test_ddim_schedule_and_point_mass():
+    s = DDIMOracle(1000, 1e-4, 0.02)
+    s.set_timesteps(50)
+    assert s.timesteps.dtype == torch.int64
+    assert s.timesteps[:3].tolist() == [980, 960, 940] and int(s.timesteps[-1]) == 0
+    # alphas_cumprod closed form check in float64
+    betas = np.linspace(1e-4, 0.02, 1000)
+    ac = np.cumprod(1 - betas)
+    assert np.allclose(s.alphas_cumprod.numpy(), ac, rtol=2e-5)
+    x0 = torch.tensor([[[[0.25, -0.5], [0.75, 0.9]]]])
+    g = torch.Generator().manual_seed(1)
+    a = s.alphas_cumprod[980]
+    xT = a.sqrt() * x0 + (1 - a).sqrt() * torch.randn(x0.shape, generator=g)
+
+    def model(x, t):  # exact epsilon for a point mass
+        at = s.alphas_cumprod[t.long()].view(-1, 1, 1, 1)
+        return (x - at.sqrt() * x0) / (1 - at).sqrt()
+
+    out = sample_loop(model, s, 50, xT)
+    assert float((out - x0).abs().max()) < 2e-5
+    # clipping: a point mass outside [-1, 1] is clamped
+    x0b = torch.full((1, 1, 2, 2), 1.7)
+    xT = a.sqrt() * x0b + (1 - a).sqrt() * torch.randn(x0b.shape, generator=g)
+
+    def model_b(x, t):
+        at = s.alphas_cumprod[t.long()].view(-1, 1, 1, 1)
+        return (x - at.sqrt() * x0b) / (1 - at).sqrt()
+
+    s.set_timesteps(50)
+    outb = sample_loop(model_b, s, 50, xT)
+    assert float(outb.max()) < 1.7 - 0.1
+
+
+def test_ddim_add_noise():
+    s = DDIMOracle(1000)
+    x0 = torch.ones(2, 1, 2, 2)
+    n = torch.full((2, 1, 2, 2), 2.0)
+    t = torch.tensor([0, 999])
+    out = s.add_noise(x0, n, t)
+    for b in range(2):
+        a = s.alphas_cumprod[t[b]]
+        assert torch.allclose(out[b], a.sqrt() + 2 * (1 - a).sqrt())
+
+
+def test_dpmpp_schedule_and_point_mass():
+    s = DPMSolverPPOracle(1000, 1e-4, 0.02)
+    s.set_timesteps(20)
+    assert s.timesteps.tolist()[:3] == [999, 949, 899] and int(s.timesteps[-1]) == 50
+    assert s.sigmas.shape == (21,) and float(s.sigmas[-1]) == 0.0 and s.sigmas.dtype == torch.float32
+    x0 = torch.tensor([[[[0.25, -0.5], [0.75, 0.9]]]])
+    g = torch.Generator().manual_seed(2)
+    sig0 = s.sigmas[0]
+    al0 = 1 / (sig0 ** 2 + 1).sqrt()
+    xT = al0 * x0 + sig0 * al0 * torch.randn(x0.shape, generator=g)
+    sig_of_t = {int(t): s.sigmas[i] for i, t in enumerate(s.timesteps)}
+
+    def model(x, t):
+        sg = sig_of_t[int(t[0])]
+        al = 1 / (sg ** 2 + 1).sqrt()
+        return (x - al * x0) / (sg * al)
+
+    out = sample_loop(model, s, 20, xT)
+    assert float((out - x0).abs().max()) < 1e-5
+    assert s.lower_order_nums == 2
+
+
+def test_dpmpp_orders():
+    s = DPMSolverPPOracle(1000)
+    s.set_timesteps(5)
+    x = torch.zeros(1, 1, 1, 1)
+    calls = []
+    first, second = s._first_order, s._second_order
+    s._first_order = lambda m0, sample: (calls.append(1), first(m0, sample))[1]
+    s._second_order = lambda sample: (calls.append(2), second(sample))[1]
+    for t in s.timesteps:
+        x = s.step(torch.ones_like(x), t, x).prev_sample
+    assert calls == [1, 2, 2, 2, 1]
+
+
+def test_select_timesteps():
+    s = make_scheduler("ddim")
+    s.set_timesteps(50)
+    sel = select_timesteps(s.timesteps, start_step=700)
+    assert int(sel[0]) == 700 and int(sel[-1]) == 0
+    assert select_timesteps(s.timesteps, last_n_steps=3).tolist() == [40, 20, 0]
+    with pytest.raises(ValueError):
+        select_timesteps(s.timesteps, start_step=-1)
+    with pytest.raises(ValueError):
+        select_timesteps(s.timesteps[s.timesteps < 0])
