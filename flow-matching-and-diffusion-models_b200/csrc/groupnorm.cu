@@ -15,10 +15,11 @@ __device__ __forceinline__ uint4 ld_chunk(const uint4* __restrict__ x0, int c80,
   return (chunk < c80) ? x0[pix * c80 + chunk] : x1[pix * c81 + (chunk - c80)];
 }
 
-// stats[n][g] += (sum, sumsq) over this block's pixel slab
+// partial[n][blk][g] = (sum, sumsq) over this block's pixel slab (no atomics: the reduction order is fixed, so the
+// whole network is bit-reproducible run to run)
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __restrict__ x0, int c80,
                                                              const uint4* __restrict__ x1, int c81, int64_t HW,
-                                                             int groups, float* __restrict__ stats,
+                                                             int groups, float* __restrict__ partial,
                                                              int64_t pix_per_block) {
   extern __shared__ float sm[];  // [ppi][C][2]
   const int tpp = c80 + c81;     // 8-channel chunks per pixel
@@ -59,14 +60,34 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __res
         ts += sm[((size_t)r * C + c) * 2 + 0];
         tq += sm[((size_t)r * C + c) * 2 + 1];
       }
-    atomicAdd(&stats[((size_t)n * groups + g) * 2 + 0], ts);
-    atomicAdd(&stats[((size_t)n * groups + g) * 2 + 1], tq);
+    float* dst = partial + (((size_t)n * gridDim.x + blockIdx.x) * groups + g) * 2;
+    dst[0] = ts;
+    dst[1] = tq;
+  }
+}
+
+// stats[n][g] = (mean, rstd) from the per-block partial sums, accumulated in fp64 in a fixed order
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, int groups, double inv_cnt, float eps,
+                                   float* __restrict__ stats) {
+  const int n = blockIdx.x;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+      const float* src = partial + (((size_t)n * nblk + b) * groups + g) * 2;
+      s += (double)src[0];
+      q += (double)src[1];
+    }
+    const double mean = s * inv_cnt;
+    double var = q * inv_cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)n * groups + g) * 2 + 0] = (float)mean;
+    stats[((size_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
 
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __restrict__ x0, int c80,
                                                              const uint4* __restrict__ x1, int c81, int64_t HW,
-                                                             int groups, float eps, const float* __restrict__ stats,
+                                                             int groups, const float* __restrict__ stats,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
                                                              const float* __restrict__ scale_shift, int silu,
@@ -78,15 +99,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
   float* sa = sm;
   float* sb = sm + C;
   const int cg = C / groups;
-  const float inv_cnt = 1.0f / ((float)HW * (float)cg);
   for (int c = threadIdx.x; c < C; c += kGnThreads) {
     const int g = c / cg;
-    const float sum = stats[((size_t)n * groups + g) * 2 + 0];
-    const float sq = stats[((size_t)n * groups + g) * 2 + 1];
-    const float mean = sum * inv_cnt;
-    float var = sq * inv_cnt - mean * mean;
-    var = var > 0.f ? var : 0.f;
-    const float rstd = rsqrtf(var + eps);
+    const float mean = stats[((size_t)n * groups + g) * 2 + 0];
+    const float rstd = stats[((size_t)n * groups + g) * 2 + 1];
     float a = rstd * gamma[c];
     float b = beta[c] - mean * a;
     if (scale_shift != nullptr) {
@@ -154,24 +170,36 @@ static int gn_check(const void* x0, int C0, const void* x1, int C1, int B, int64
 
 using namespace fm;
 
+extern "C" int64_t fm_groupnorm_workspace_elems(int32_t B, int64_t HW, int32_t C, int32_t groups) {
+  if (B <= 0 || HW <= 0 || C <= 0 || C % 8 || groups <= 0 || C / 8 > kGnThreads) return 0;
+  int64_t ppb;
+  const int gx = gn_grid(B, HW, C / 8, &ppb);
+  return (int64_t)B * gx * groups * 2;
+}
+
 extern "C" int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
-                                       int32_t groups, float* stats, fm_stream_t stream) {
+                                       int32_t groups, float eps, float* workspace, float* stats,
+                                       fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   if (int e = gn_check(x0, C0, x1, C1, B, HW, groups)) return e;
-  FM_REQUIRE(stats != nullptr, "groupnorm_stats: null stats");
+  FM_REQUIRE(stats != nullptr && workspace != nullptr, "groupnorm_stats: null stats/workspace");
   const int tpp = (C0 + C1) / 8;
   int64_t ppb;
   const int gx = gn_grid(B, HW, tpp, &ppb);
   const int ppi = kGnThreads / tpp;
   const size_t smem = (size_t)ppi * (C0 + C1) * 2 * sizeof(float);
   gn_stats_kernel<<<dim3(gx, B), kGnThreads, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, stats, ppb);
+      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, workspace,
+      ppb);
   FM_LAUNCH_CHECK("gn_stats_kernel");
+  const double inv_cnt = 1.0 / ((double)HW * (double)((C0 + C1) / groups));
+  gn_finalize_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(workspace, gx, groups, inv_cnt, eps, stats);
+  FM_LAUNCH_CHECK("gn_finalize_kernel");
   return 0;
 }
 
 extern "C" int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
-                                       int32_t groups, float eps, const float* stats, const float* gamma,
+                                       int32_t groups, const float* stats, const float* gamma,
                                        const float* beta, const float* scale_shift, int32_t silu, void* out,
                                        fm_stream_t stream) {
   if (int e = ensure_device()) return e;
@@ -183,7 +211,7 @@ extern "C" int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x
   const int gx = gn_grid(B, HW, tpp, &ppb);
   const size_t smem = (size_t)(C0 + C1) * 2 * sizeof(float);
   gn_apply_kernel<<<dim3(gx, B), kGnThreads, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, eps, stats,
+      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, stats,
       gamma, beta, scale_shift, silu, reinterpret_cast<uint4*>(out), ppb);
   FM_LAUNCH_CHECK("gn_apply_kernel");
   return 0;

@@ -219,10 +219,15 @@ def group_norm(
     b, c0, h, w = x0.shape
     c1 = x1.shape[1] if x1 is not None else 0
     ctot = c0 + c1
-    stats = torch.zeros((b, groups, 2), dtype=torch.float32, device=x0.device)
+    stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x0.device)
+    ws_elems = int(lib.fm_groupnorm_workspace_elems(b, h * w, ctot, groups))
+    if ws_elems <= 0:
+        raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={ctot} groups={groups}")
+    ws = torch.empty((ws_elems,), dtype=torch.float32, device=x0.device)
     st = _stream()
     _lib.check(
-        lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, stats.data_ptr(), st),
+        lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps), ws.data_ptr(),
+                                    stats.data_ptr(), st),
         "groupnorm_stats",
     )
     out = empty_nhwc(b, ctot, h, w, x0.device)
@@ -231,7 +236,7 @@ def group_norm(
         raise ValueError("group_norm: scale_shift must be contiguous fp32 [B][2C]")
     _lib.check(
         lib.fm_groupnorm_apply_bf16(
-            x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps), stats.data_ptr(), gamma.data_ptr(),
+            x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, stats.data_ptr(), gamma.data_ptr(),
             beta.data_ptr(), _ptr(scale_shift), int(silu), out.data_ptr(), st,
         ),
         "groupnorm_apply",

@@ -101,13 +101,16 @@ int fm_conv_head_bf16_f32(const void* x_nhwc_bf16, const float* weight_oihw, con
  * Replaces nn.GroupNorm + nn.SiLU (src/nn/ops/normalization.py:11-19; residual.py:95-96,113-116;
  * unet_diffusers_nd.py:188-189; attention.py:235-236).  Up to two sources are read as a virtual channel concat.
  * ---------------------------------------------------------------------------------------------------------- */
-/* stats[n][g] = (sum, sumsq) over the group; `stats` must be zeroed by the caller (or by fm_memset_f32). */
+/* stats[n][g] = (mean, rstd) of the group.  Deterministic two-stage reduction (no atomics): per-block partial sums go
+ * to `workspace` (fm_groupnorm_workspace_elems(B, HW, C0+C1, groups) floats), a second tiny kernel folds them in
+ * fp64 in a fixed order. */
+int64_t fm_groupnorm_workspace_elems(int32_t B, int64_t HW, int32_t C, int32_t groups);
 int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
-                            int32_t groups, float* stats, fm_stream_t stream);
+                            int32_t groups, float eps, float* workspace, float* stats, fm_stream_t stream);
 /* y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), act = SiLU if silu!=0.
  * scale_shift: fp32 [B][2*C] (scale first, then shift; residual.py:109,115) or NULL. */
 int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
-                            int32_t groups, float eps, const float* stats, const float* gamma, const float* beta,
+                            int32_t groups, const float* stats, const float* gamma, const float* beta,
                             const float* scale_shift, int32_t silu, void* out, fm_stream_t stream);
 int fm_memset_f32(float* p, int64_t n, fm_stream_t stream);
 
