@@ -21,6 +21,44 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- optional per-kernel timing (bench.py's live roofline measurement; CUDA events on the launching stream) ----
+_PROFILE = None
+
+
+class profile:
+    """with ops.profile() as rec: ...  -> rec.rows = [(tag, work, milliseconds)] after exit (synchronises)."""
+
+    def __enter__(self):
+        global _PROFILE
+        self._events = []
+        _PROFILE = self._events
+        self.rows = []
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+        torch.cuda.synchronize()
+        self.rows = [(tag, work, e0.elapsed_time(e1)) for tag, work, e0, e1 in self._events]
+        return False
+
+
+def _prof_begin():
+    if _PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(tag: str, work: float, e0) -> None:
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    _PROFILE.append((tag, work, e0, e1))
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -154,7 +192,9 @@ def conv2d(
     p.out = out.data_ptr()
     p.gn_stats = None
     p.gn_groups = 0
+    e0 = _prof_begin()
     _lib.check(lib.fm_conv2d_igemm_bf16(C.byref(p), _stream()), "conv2d_igemm_bf16")
+    _prof_end("conv_igemm", 2.0 * b * ho * wo * weight.cout * weight.mat.shape[1], e0)
     return out
 
 
@@ -170,6 +210,7 @@ def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0) -> torch
         c1 = x1.shape[1]
     cout = weight_oihw.shape[0]
     out = empty_nhwc(b, cout, h, w, x0.device)
+    e0 = _prof_begin()
     _lib.check(
         lib.fm_conv_stem_f32_bf16(
             x0.data_ptr(), c0, _ptr(x1), c1, float(in_scale), float(in_shift), weight_oihw.data_ptr(), _ptr(bias),
@@ -177,6 +218,7 @@ def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0) -> torch
         ),
         "conv_stem",
     )
+    _prof_end("conv_stem", 2.0 * b * h * w * (c0 + c1) * 9 * cout, e0)
     return out
 
 
@@ -187,11 +229,13 @@ def conv_head(x: torch.Tensor, weight_oihw, bias) -> torch.Tensor:
     b, cin, h, w = x.shape
     cout = weight_oihw.shape[0]
     out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device)
+    e0 = _prof_begin()
     _lib.check(
         lib.fm_conv_head_bf16_f32(x.data_ptr(), weight_oihw.data_ptr(), _ptr(bias), out.data_ptr(), b, h, w, cin, cout,
                                   _stream()),
         "conv_head",
     )
+    _prof_end("conv_head", 2.0 * b * h * w * cin * 9 * cout, e0)
     return out
 
 
@@ -225,6 +269,7 @@ def group_norm(
         raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={ctot} groups={groups}")
     ws = torch.empty((ws_elems,), dtype=torch.float32, device=x0.device)
     st = _stream()
+    e0 = _prof_begin()
     _lib.check(
         lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps), ws.data_ptr(),
                                     stats.data_ptr(), st),
@@ -241,6 +286,7 @@ def group_norm(
         ),
         "groupnorm_apply",
     )
+    _prof_end("groupnorm", 4.0 * b * ctot * h * w, e0)  # algorithmic bytes: read once + write once, bf16
     return out
 
 
@@ -249,7 +295,9 @@ def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
     _check_act(x, "upsample_nearest2x")
     b, c, h, w = x.shape
     out = empty_nhwc(b, c, 2 * h, 2 * w, x.device)
+    e0 = _prof_begin()
     _lib.check(lib.fm_upsample_nearest2x_bf16(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "upsample")
+    _prof_end("upsample", 2.0 * b * c * h * w * 5, e0)
     return out
 
 
@@ -272,6 +320,7 @@ def attention(q, k, v, out, *, batch, heads, tq, tk, head_dim, q_strides, kv_str
         assert t.dtype == BF16
     if scale is None:
         scale = 1.0 / math.sqrt(head_dim)
+    e0 = _prof_begin()
     _lib.check(
         lib.fm_attention_bf16(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, tq, tk, head_dim,
@@ -280,6 +329,7 @@ def attention(q, k, v, out, *, batch, heads, tq, tk, head_dim, q_strides, kv_str
         ),
         "attention",
     )
+    _prof_end("attention", 4.0 * batch * heads * tq * tk * head_dim, e0)
     return out
 
 
