@@ -1,7 +1,8 @@
 from .convolution import ConvND, ConvTransposeND
 from .normalization import RMSNormND, fused_group_norm, make_group_norm
+from .pooling import AvgPoolND, MaxPoolND, PoolND, UnPoolND
 from .time_embedding import timestep_embedding
 from .upsampling import DownsampleND, UpsampleND
 
-__all__ = ["ConvND", "ConvTransposeND", "RMSNormND", "make_group_norm", "fused_group_norm", "timestep_embedding",
-           "UpsampleND", "DownsampleND"]
+__all__ = ["ConvND", "ConvTransposeND", "PoolND", "AvgPoolND", "MaxPoolND", "UnPoolND", "RMSNormND",
+           "make_group_norm", "fused_group_norm", "timestep_embedding", "UpsampleND", "DownsampleND"]
