@@ -116,6 +116,123 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(const __nv_bfloa
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// head_dim == 8 (the reference's default: 64 heads at C = 512): tensor-core version on legacy mma.sync m16n8k8
+// (bf16 in, fp32 accumulate).  tcgen05 is the wrong tool here: K = 8 is half of one UMMA K step and the op is
+// exp-bound (64*T^2 exponentials per sample per layer), so the win is in removing the 16 FMAs per score from the
+// CUDA cores, not in MMA peak.  One warp owns 16 query rows; S = Q K^T comes from one m16n8k8 per 8 keys, the
+// accumulator fragment is re-used in place as the A operand of P V (same lane layout), V is staged transposed.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kAtt8Warps = 8;
+constexpr int kAtt8Threads = kAtt8Warps * 32;
+constexpr int kAtt8KeyChunk = 1024;            // keys staged per pass
+constexpr int kAtt8VtStride = kAtt8KeyChunk + 8;  // +8 bf16 (16 B) padding: conflict-free transposed reads
+
+__device__ __forceinline__ void mma_m16n8k8_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+
+__global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+    __nv_bfloat16* __restrict__ out, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
+    int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float scale_log2e) {
+  __shared__ __align__(16) __nv_bfloat16 sK[kAtt8KeyChunk * 8];      // [key][8]
+  __shared__ __align__(16) __nv_bfloat16 sVt[8 * kAtt8VtStride];     // [dim][key]
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * (kAtt8Warps * 16) + warp * 16;
+  const __nv_bfloat16* qb = q + b * q_sb + h * q_sh;
+  const __nv_bfloat16* kb = k + b * kv_sb + h * kv_sh;
+  const __nv_bfloat16* vb = v + b * kv_sb + h * kv_sh;
+
+  // Q fragment: a0 = Q[q0+g][2t,2t+1], a1 = Q[q0+g+8][2t,2t+1]  (rows clamped; stores are masked)
+  const int r0 = min(q0 + g, Tq - 1), r1 = min(q0 + g + 8, Tq - 1);
+  const uint32_t qa0 = *reinterpret_cast<const uint32_t*>(qb + (int64_t)r0 * q_st + 2 * t);
+  const uint32_t qa1 = *reinterpret_cast<const uint32_t*>(qb + (int64_t)r1 * q_st + 2 * t);
+
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max (log2 domain) / partial sums per row
+
+  for (int c0 = 0; c0 < Tk; c0 += kAtt8KeyChunk) {
+    const int nk = min(kAtt8KeyChunk, Tk - c0);
+    const int nk_pad = (nk + 63) & ~63;
+    __syncthreads();
+    for (int j = threadIdx.x; j < nk_pad; j += kAtt8Threads) {
+      uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (j < nk) {
+        kk = *reinterpret_cast<const uint4*>(kb + (int64_t)(c0 + j) * kv_st);
+        vv = *reinterpret_cast<const uint4*>(vb + (int64_t)(c0 + j) * kv_st);
+      }
+      *reinterpret_cast<uint4*>(sK + j * 8) = kk;
+      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) sVt[d * kAtt8VtStride + j] = ve[d];
+    }
+    __syncthreads();
+
+    for (int kb0 = 0; kb0 < nk_pad; kb0 += 64) {
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const uint32_t bk = *reinterpret_cast<const uint32_t*>(sK + (kb0 + j * 8 + g) * 8 + 2 * t);
+        mma_m16n8k8_bf16(s[j], qa0, qa1, bk);
+      }
+      if (kb0 + 64 > nk) {  // mask the padded keys of the last block
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int key = kb0 + j * 8 + 2 * t;
+          if (key >= nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+          if (key + 1 >= nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        }
+      }
+      float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0 * scale_log2e), mn1 = fmaxf(m1, mx1 * scale_log2e);
+      const float corr0 = exp2f(m0 - mn0), corr1 = exp2f(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      l0 *= corr0; l1 *= corr1;
+      o[0] *= corr0; o[1] *= corr0; o[2] *= corr1; o[3] *= corr1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -mn0));
+        const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -mn0));
+        const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -mn1));
+        const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -mn1));
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        const uint32_t pa0 = pack_bf16x2(p0, p1), pa1 = pack_bf16x2(p2, p3);
+        // B fragment of P*V: (k = keys 2t,2t+1 ; n = dim g) from the transposed V tile
+        const uint32_t bv = *reinterpret_cast<const uint32_t*>(sVt + g * kAtt8VtStride + kb0 + j * 8 + 2 * t);
+        mma_m16n8k8_bf16(o, pa0, pa1, bv);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  __nv_bfloat16* ob = out + b * o_sb + h * o_sh;
+  if (q0 + g < Tq)
+    *reinterpret_cast<uint32_t*>(ob + (int64_t)(q0 + g) * o_st + 2 * t) = pack_bf16x2(o[0] * i0, o[1] * i0);
+  if (q0 + g + 8 < Tq)
+    *reinterpret_cast<uint32_t*>(ob + (int64_t)(q0 + g + 8) * o_st + 2 * t) = pack_bf16x2(o[2] * i1, o[3] * i1);
+}
+
 template <int HD>
 static int launch_attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk,
                             int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb, int64_t kv_sh, int64_t kv_st,
@@ -151,7 +268,15 @@ extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, vo
   cudaStream_t st = (cudaStream_t)stream;
 #define FM_ATT_ARGS q, k, v, out, B, heads, Tq, Tk, q_sb, q_sh, q_st, kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale, st
   switch (head_dim) {
-    case 8: return launch_attention<8>(FM_ATT_ARGS);
+    case 8: {
+      dim3 grid((Tq + kAtt8Warps * 16 - 1) / (kAtt8Warps * 16), heads, B);
+      attention_hd8_mma_kernel<<<grid, kAtt8Threads, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+          reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Tq, Tk, q_sb, q_sh, q_st,
+          kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale * 1.4426950408889634f);
+      FM_LAUNCH_CHECK("attention_hd8_mma_kernel");
+      return 0;
+    }
     case 16: return launch_attention<16>(FM_ATT_ARGS);
     case 32: return launch_attention<32>(FM_ATT_ARGS);
     case 64: return launch_attention<64>(FM_ATT_ARGS);

@@ -8,13 +8,16 @@
 namespace fm {
 
 constexpr int kStemMaxCin = 8;
+constexpr int kStemThreads = 256;
 
-// one thread = one output pixel x 8 output channels; weights live in smem as [ci][tap][co]
-__global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ x0, int C0,
-                                                       const float* __restrict__ x1, int C1, float in_scale,
-                                                       float in_shift, const float* __restrict__ w_oihw,
-                                                       const float* __restrict__ bias, uint4* __restrict__ out, int B,
-                                                       int H, int W, int Cout) {
+// one thread = one output pixel x 8 output channels; weights live in smem as [ci*9+tap][co]; 32-bit index math.
+__global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __restrict__ x0, int C0,
+                                                                const float* __restrict__ x1, int C1,
+                                                                float in_scale, float in_shift,
+                                                                const float* __restrict__ w_oihw,
+                                                                const float* __restrict__ bias,
+                                                                uint4* __restrict__ out, int B, int H, int W,
+                                                                int Cout) {
   extern __shared__ float sw[];  // [Cin*9][Cout] + bias[Cout]
   const int Cin = C0 + C1;
   const int K = Cin * 9;
@@ -26,91 +29,125 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sbias[i] = bias ? bias[i] : 0.f;
   __syncthreads();
 
-  const int c8n = Cout / 8;
-  const int64_t total = (int64_t)B * H * W * c8n;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int c8 = (int)(idx % c8n);
-    int64_t pix = idx / c8n;
-    const int w = (int)(pix % W);
-    const int h = (int)((pix / W) % H);
-    const int n = (int)(pix / ((int64_t)W * H));
+  const int chunks = Cout >> 3;
+  const int ppb = kStemThreads / chunks;  // pixels per block iteration
+  const int c8 = threadIdx.x % chunks;
+  const int pl = threadIdx.x / chunks;
+  if (pl >= ppb) return;
+  const int HW = H * W;
+  const int total = B * HW;
+  float bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bi[j] = sbias[c8 * 8 + j];
+  for (int pix = blockIdx.x * ppb + pl; pix < total; pix += gridDim.x * ppb) {
+    const int n = pix / HW;
+    const int rem = pix - n * HW;
+    const int h = rem / W;
+    const int w = rem - h * W;
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sbias[c8 * 8 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = bi[j];
     for (int ci = 0; ci < Cin; ++ci) {
-      const float* src = (ci < C0) ? x0 + ((size_t)n * C0 + ci) * H * W : x1 + ((size_t)n * C1 + (ci - C0)) * H * W;
+      const float* src = (ci < C0) ? x0 + ((size_t)n * C0 + ci) * HW : x1 + ((size_t)n * C1 + (ci - C0)) * HW;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int ih = h + kh - 1;
-        if (ih < 0 || ih >= H) continue;
+        const bool hok = (unsigned)ih < (unsigned)H;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const int iw = w + kw - 1;
-          if (iw < 0 || iw >= W) continue;
-          const float xv = fmaf(__ldg(src + (size_t)ih * W + iw), in_scale, in_shift);
-          const float* wp = sw + (size_t)(ci * 9 + kh * 3 + kw) * Cout + c8 * 8;
-          const float4 w0 = *reinterpret_cast<const float4*>(wp);
-          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
-          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+          if (hok && (unsigned)iw < (unsigned)W) {
+            const float xv = fmaf(__ldg(src + ih * W + iw), in_scale, in_shift);
+            const float* wp = sw + (ci * 9 + kh * 3 + kw) * Cout + c8 * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+            acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+            acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+            acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+          }
         }
       }
     }
     uint4 o;
     o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
     o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    out[idx] = o;
+    out[(size_t)pix * chunks + c8] = o;
   }
 }
 
-// Head: one thread = one output pixel (all Cout <= 4 channels); weights in smem as [tap][ci][co] fp32.
+// Head: a block computes a 32 x 4 tile of output pixels from a (34 x 6)-pixel halo tile staged in shared memory
+// (row pitch Cin*2+16 bytes => conflict-free 16-byte reads with one thread per pixel); weights fp32 in smem as
+// [tap][ci][co].  Global reads are fully coalesced (NHWC rows are contiguous), every input byte is read once per tile.
+constexpr int kHeadTW = 32, kHeadTH = 4, kHeadThreads = kHeadTW * kHeadTH;
+
 template <int COUT>
-__global__ void __launch_bounds__(128) conv_head_kernel(const uint4* __restrict__ x, const float* __restrict__ w_oihw,
-                                                       const float* __restrict__ bias, float* __restrict__ out, int B,
-                                                       int H, int W, int Cin) {
-  extern __shared__ float sw[];  // [9][Cin][COUT]
-  for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) {
+__global__ void __launch_bounds__(kHeadThreads) conv_head_kernel(const uint4* __restrict__ x,
+                                                                const float* __restrict__ w_oihw,
+                                                                const float* __restrict__ bias,
+                                                                float* __restrict__ out, int B, int H, int W,
+                                                                int Cin) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int c8n = Cin >> 3;
+  const int pitch = Cin * 2 + 16;                                   // bytes per staged pixel
+  float* sw = reinterpret_cast<float*>(smem);                       // [9][Cin][COUT]
+  uint8_t* st = smem + ((9 * Cin * COUT * 4 + 15) & ~15);           // [(TH+2)*(TW+2)][pitch]
+  for (int i = threadIdx.x; i < 9 * Cin * COUT; i += kHeadThreads) {
     const int co = i % COUT;
     const int ci = (i / COUT) % Cin;
     const int tap = i / (COUT * Cin);
     sw[i] = w_oihw[((size_t)co * Cin + ci) * 9 + tap];
   }
+  const int w0 = blockIdx.x * kHeadTW, h0 = blockIdx.y * kHeadTH, n = blockIdx.z;
+  constexpr int HP = kHeadTH + 2, WP = kHeadTW + 2;
+  for (int i = threadIdx.x; i < HP * WP * c8n; i += kHeadThreads) {
+    const int c = i % c8n;
+    const int p = i / c8n;
+    const int pw = p % WP, ph = p / WP;
+    const int ih = h0 + ph - 1, iw = w0 + pw - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+      v = __ldg(x + (((size_t)n * H + ih) * W + iw) * c8n + c);
+    *reinterpret_cast<uint4*>(st + p * pitch + c * 16) = v;
+  }
   __syncthreads();
-  const int c8n = Cin / 8;
-  // 2D tiling: a block covers 32 x 4 pixels so neighbouring threads share input rows through L1
-  const int w = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int h = blockIdx.y * 4 + (threadIdx.x >> 5);
-  const int n = blockIdx.z;
-  if (w >= W || h >= H) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ow = w0 + tx, oh = h0 + ty;
   float acc[COUT];
 #pragma unroll
   for (int c = 0; c < COUT; ++c) acc[c] = bias ? bias[c] : 0.f;
+#pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
-    const int ih = h + kh - 1;
-    if (ih < 0 || ih >= H) continue;
+#pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
-      const int iw = w + kw - 1;
-      if (iw < 0 || iw >= W) continue;
-      const uint4* px = x + (((size_t)n * H + ih) * W + iw) * c8n;
-      const float* wt = sw + (size_t)(kh * 3 + kw) * Cin * COUT;
-#pragma unroll 4
+      const uint8_t* px = st + ((ty + kh) * WP + tx + kw) * pitch;
+      const float* wt = sw + (kh * 3 + kw) * Cin * COUT;
+#pragma unroll 2
       for (int c8 = 0; c8 < c8n; ++c8) {
-        const uint4 u = __ldg(px + c8);
+        const uint4 u = *reinterpret_cast<const uint4*>(px + c8 * 16);
         const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
                      f3 = unpack_bf16x2(u.w);
         const float v[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+        if (COUT == 1) {
+          const float4 wa = *reinterpret_cast<const float4*>(wt + c8 * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(wt + c8 * 8 + 4);
+          // four independent partial sums keep the FMA pipe busy (the chain is 1152 FMAs long otherwise)
+          const float p0 = fmaf(v[1], wa.y, v[0] * wa.x), p1 = fmaf(v[3], wa.w, v[2] * wa.z);
+          const float p2 = fmaf(v[5], wb.y, v[4] * wb.x), p3 = fmaf(v[7], wb.w, v[6] * wb.z);
+          acc[0] += (p0 + p1) + (p2 + p3);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < 8; ++j)
 #pragma unroll
-          for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v[j], wt[(c8 * 8 + j) * COUT + c], acc[c]);
+            for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v[j], wt[(c8 * 8 + j) * COUT + c], acc[c]);
+        }
       }
     }
   }
+  if (ow < W && oh < H) {
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) out[(((size_t)n * COUT + c) * H + h) * W + w] = acc[c];
+    for (int c = 0; c < COUT; ++c) out[(((size_t)n * COUT + c) * H + oh) * W + ow] = acc[c];
+  }
 }
 
 }  // namespace fm
@@ -125,6 +162,7 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
   FM_REQUIRE(C0 + C1 <= kStemMaxCin, "conv_stem: Cin=%d exceeds %d", C0 + C1, kStemMaxCin);
   FM_REQUIRE(Cout > 0 && Cout % 8 == 0 && Cout <= 512, "conv_stem: Cout=%d must be a multiple of 8 (<=512)", Cout);
   FM_REQUIRE(weight_oihw && out && B > 0 && H > 0 && W > 0, "conv_stem: bad argument");
+  FM_REQUIRE((int64_t)B * H * W < (1ll << 31), "conv_stem: too many pixels for 32-bit indexing");
   const size_t smem = ((size_t)(C0 + C1) * 9 * Cout + Cout) * sizeof(float);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
@@ -132,13 +170,12 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_stem)");
     attr = smem;
   }
-  const int64_t total = (int64_t)B * H * W * (Cout / 8);
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int ppb = kStemThreads / (Cout / 8);
+  int64_t blocks = ((int64_t)B * H * W + ppb - 1) / ppb;
+  const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  conv_stem_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x0, C0, x1, C1, in_scale, in_shift, weight_oihw,
-                                                                      bias, reinterpret_cast<uint4*>(out), B, H, W,
-                                                                      Cout);
+  conv_stem_kernel<<<(int)blocks, kStemThreads, smem, (cudaStream_t)stream>>>(
+      x0, C0, x1, C1, in_scale, in_shift, weight_oihw, bias, reinterpret_cast<uint4*>(out), B, H, W, Cout);
   FM_LAUNCH_CHECK("conv_stem_kernel");
   return 0;
 }
@@ -149,9 +186,11 @@ extern "C" int fm_conv_head_bf16_f32(const void* x, const float* weight_oihw, co
   FM_REQUIRE(x && weight_oihw && out && B > 0 && H > 0 && W > 0, "conv_head: bad argument");
   FM_REQUIRE(Cin > 0 && Cin % 8 == 0, "conv_head: Cin=%d must be a multiple of 8", Cin);
   FM_REQUIRE(Cout >= 1 && Cout <= 4, "conv_head: Cout=%d must be in 1..4", Cout);
-  const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
-  FM_REQUIRE(smem <= 200 * 1024, "conv_head: weights do not fit shared memory");
-  dim3 grid((W + 31) / 32, (H + 3) / 4, B);
+  FM_REQUIRE(B <= 65535, "conv_head: batch too large for the grid");
+  const size_t wbytes = ((size_t)9 * Cin * Cout * sizeof(float) + 15) & ~(size_t)15;
+  const size_t smem = wbytes + (size_t)(kHeadTH + 2) * (kHeadTW + 2) * (Cin * 2 + 16);
+  FM_REQUIRE(smem <= 200 * 1024, "conv_head: Cin=%d does not fit shared memory", Cin);
+  dim3 grid((W + kHeadTW - 1) / kHeadTW, (H + kHeadTH - 1) / kHeadTH, B);
   cudaStream_t st = (cudaStream_t)stream;
   const uint4* xp = reinterpret_cast<const uint4*>(x);
 #define FM_HEAD_CASE(N)                                                                                              \
@@ -161,7 +200,7 @@ extern "C" int fm_conv_head_bf16_f32(const void* x, const float* weight_oihw, co
                                            (int)smem);                                                               \
       if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_head)");                                 \
     }                                                                                                                \
-    conv_head_kernel<N><<<grid, 128, smem, st>>>(xp, weight_oihw, bias, out, B, H, W, Cin);                          \
+    conv_head_kernel<N><<<grid, kHeadThreads, smem, st>>>(xp, weight_oihw, bias, out, B, H, W, Cin);                 \
     break;                                                                                                           \
   }
   switch (Cout) {

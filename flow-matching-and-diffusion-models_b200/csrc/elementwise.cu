@@ -144,40 +144,49 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, const flo
   out[idx] = want_cos ? cosf(arg) : sinf(arg);
 }
 
-// ---- tiny fp32 Linear: one warp per output feature, batch rows in chunks of 8 ---------------------------------
+// ---- tiny fp32 Linear: one warp per output feature; the (activated) input rows are staged once in smem ---------
+constexpr int kLinRows = 16;
 __global__ void __launch_bounds__(128) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                         const float* __restrict__ bias,
                                                         const float* __restrict__ bias2, float* __restrict__ y,
-                                                        int B, int I, int O, int silu_in, int silu_out) {
+                                                        int B, int I, int O, int silu_in, int silu_out, int rows) {
+  extern __shared__ float sx[];  // [rows][I]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * 4 + warp;
-  if (o >= O) return;
-  const float* w = W + (size_t)o * I;
+  const float* w = W + (size_t)(o < O ? o : 0) * I;
   float bsum = 0.f;
-  if (bias) bsum += bias[o];
-  if (bias2) bsum += bias2[o];
-  for (int b0 = 0; b0 < B; b0 += 8) {
-    float acc[8];
+  if (o < O) {
+    if (bias) bsum += bias[o];
+    if (bias2) bsum += bias2[o];
+  }
+  for (int b0 = 0; b0 < B; b0 += rows) {
+    const int nb = min(rows, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * I; i += blockDim.x) {
+      float xv = x[(size_t)b0 * I + i];
+      if (silu_in) xv = xv / (1.0f + expf(-xv));
+      sx[i] = xv;
+    }
+    __syncthreads();
+    if (o >= O) continue;
+    float acc[kLinRows];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
     for (int i = lane; i < I; i += 32) {
-      const float wv = w[i];
+      const float wv = __ldg(w + i);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (b0 + r < B) {
-          float xv = x[(size_t)(b0 + r) * I + i];
-          if (silu_in) xv = xv / (1.0f + expf(-xv));
-          acc[r] = fmaf(xv, wv, acc[r]);
-        }
-      }
+      for (int r = 0; r < kLinRows; ++r)
+        if (r < nb) acc[r] = fmaf(sx[r * I + i], wv, acc[r]);
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float s = warp_sum(acc[r]);
-      if (lane == 0 && b0 + r < B) {
-        s += bsum;
-        if (silu_out) s = s / (1.0f + expf(-s));
-        y[(size_t)(b0 + r) * O + o] = s;
+    for (int r = 0; r < kLinRows; ++r) {
+      if (r < nb) {
+        float s = warp_sum(acc[r]);
+        if (lane == 0) {
+          s += bsum;
+          if (silu_out) s = s / (1.0f + expf(-s));
+          y[(size_t)(b0 + r) * O + o] = s;
+        }
       }
     }
   }
@@ -337,7 +346,12 @@ extern "C" int fm_linear_f32(const float* x, const float* W, const float* bias, 
                              fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x && W && y && B > 0 && I > 0 && O > 0, "linear: bad argument B=%d I=%d O=%d", B, I, O);
-  linear_f32_kernel<<<(O + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, W, bias, bias2, y, B, I, O, silu_in, silu_out);
+  int rows = (48 * 1024) / (I * (int)sizeof(float));
+  if (rows > kLinRows) rows = kLinRows;
+  FM_REQUIRE(rows >= 1, "linear: in_features=%d too large", I);
+  const size_t smem = (size_t)rows * I * sizeof(float);
+  linear_f32_kernel<<<(O + 3) / 4, 128, smem, (cudaStream_t)stream>>>(x, W, bias, bias2, y, B, I, O, silu_in,
+                                                                      silu_out, rows);
   FM_LAUNCH_CHECK("linear_f32_kernel");
   return 0;
 }

@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
                                                              int groups, const float* __restrict__ stats,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
-                                                             const float* __restrict__ scale_shift, int silu,
-                                                             uint4* __restrict__ out, int64_t pix_per_block) {
+                                                             const float* __restrict__ scale_shift,
+                                                             int64_t ss_stride, int silu, uint4* __restrict__ out,
+                                                             int64_t pix_per_block) {
   extern __shared__ float sm[];  // a[C], b[C]
   const int tpp = c80 + c81;
   const int C = tpp * 8;
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
     float a = rstd * gamma[c];
     float b = beta[c] - mean * a;
     if (scale_shift != nullptr) {
-      const float sc = 1.0f + scale_shift[(size_t)n * 2 * C + c];
-      const float sh = scale_shift[(size_t)n * 2 * C + C + c];
+      const float sc = 1.0f + scale_shift[(size_t)n * ss_stride + c];
+      const float sh = scale_shift[(size_t)n * ss_stride + C + c];
       a *= sc;
       b = b * sc + sh;
     }
@@ -200,8 +201,8 @@ extern "C" int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x
 
 extern "C" int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
                                        int32_t groups, const float* stats, const float* gamma,
-                                       const float* beta, const float* scale_shift, int32_t silu, void* out,
-                                       fm_stream_t stream) {
+                                       const float* beta, const float* scale_shift, int64_t ss_stride, int32_t silu,
+                                       void* out, fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   if (int e = gn_check(x0, C0, x1, C1, B, HW, groups)) return e;
   FM_REQUIRE(stats && gamma && beta && out, "groupnorm_apply: null pointer");
@@ -212,7 +213,7 @@ extern "C" int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x
   const size_t smem = (size_t)(C0 + C1) * 2 * sizeof(float);
   gn_apply_kernel<<<dim3(gx, B), kGnThreads, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, stats,
-      gamma, beta, scale_shift, silu, reinterpret_cast<uint4*>(out), ppb);
+      gamma, beta, scale_shift, ss_stride, silu, reinterpret_cast<uint4*>(out), ppb);
   FM_LAUNCH_CHECK("gn_apply_kernel");
   return 0;
 }

@@ -21,6 +21,25 @@ class BaseUNetND(nn.Module, ABC):
     def _prepare_input(self, x, context, context_ca):
         return x
 
+    def _pack_temb(self, emb: torch.Tensor):
+        """Project `emb` for every ResBlock of the model with one batched fp32 kernel (see nn.blocks.TembPack)."""
+        from ... import ops
+        from ..._runtime import ParamCache
+        from ...nn.blocks.residual import ResBlockND, TembPack
+
+        if not hasattr(self, "_temb_blocks"):
+            self._temb_blocks = [m for m in self.modules() if isinstance(m, ResBlockND) and m.uses_embedding]
+            self._temb_params = [p for m in self._temb_blocks
+                                 for p in (m.emb_layers.weight, m.emb_layers.bias, m.conv1.conv.bias)]
+            self._temb_cache = ParamCache()
+        if not self._temb_blocks:
+            return emb
+        plan = self._temb_cache.get("plan", self._temb_params, lambda: TembPack.plan(self._temb_blocks))
+        if plan is None:
+            return emb
+        weight, bias, offsets, silu = plan
+        return TembPack(emb, ops.linear_f32(emb, weight, bias, silu_in=silu), offsets)
+
     @abstractmethod
     def _build_time_embedding(self, t: Optional[torch.Tensor], x: torch.Tensor, *, t_table=None,
                               step_dev=None) -> torch.Tensor:

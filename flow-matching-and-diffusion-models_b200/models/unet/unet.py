@@ -132,6 +132,7 @@ class EfficientUNetND(BaseUNetND):
     def _run_network(self, x, emb: torch.Tensor, context_ca) -> torch.Tensor:
         x, context = x
         ops.require_cuda(x, "EfficientUNetND.forward")
+        emb = self._pack_temb(emb)
         if self.spatial_dims != 2:
             out_of_scope("EfficientUNetND with spatial_dims != 2")
         stem = self.input_blocks[0][0].conv

@@ -131,6 +131,7 @@ class UNetDiffusersND(BaseUNetND):
 
     def _run_network(self, x, emb: torch.Tensor, context_ca) -> torch.Tensor:
         x, context = x
+        emb = self._pack_temb(emb)
         sample = self._stem(x, context)
         skips = [sample]
         for block in self.down_blocks:

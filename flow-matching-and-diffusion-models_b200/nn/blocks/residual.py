@@ -24,6 +24,54 @@ from .common import zero_module
 from .timestep import TimestepBlock
 
 
+class TembPack:
+    """All time-embedding projections of a model in ONE launch.
+
+    The reference projects `temb` separately inside each of its ~35 ResBlocks (`residual.py:99-108`); the input is
+    the same for all of them, so the denoiser concatenates every block's `emb_layers` weight into one
+    [sum(out), emb] matrix (conv1's bias folded in for the add-to-hidden variant) and runs one small fp32 kernel
+    per step.  Blocks receive this object in place of `emb` and take their row slice."""
+
+    def __init__(self, raw: torch.Tensor, proj: torch.Tensor, offsets: dict):
+        self.raw, self.proj, self.offsets = raw, proj, offsets
+
+    def has(self, block) -> bool:
+        return id(block) in self.offsets
+
+    def slice(self, block) -> torch.Tensor:
+        lo, n = self.offsets[id(block)]
+        return self.proj[:, lo:lo + n]
+
+    @staticmethod
+    def plan(blocks):
+        """(weight [sumO][I], bias [sumO], offsets) for the blocks that can use the batched projection."""
+        ws, bs, offsets, lo = [], [], {}, 0
+        silu = None
+        for blk in blocks:
+            if not (blk.uses_embedding and (blk.use_scale_shift_norm or blk.add_embedding_to_hidden)):
+                continue
+            if silu is None:
+                silu = blk.emb_activation_before_proj
+            if blk.emb_activation_before_proj != silu:
+                continue
+            w = blk.emb_layers.weight.detach().float()
+            b = blk.emb_layers.bias.detach().float()
+            if not blk.use_scale_shift_norm and blk.conv1.conv.bias is not None:
+                b = b + blk.conv1.conv.bias.detach().float()
+            n = w.shape[0]
+            pad = (-n) % 4  # keep every slice 16-byte aligned
+            ws.append(w)
+            bs.append(b)
+            if pad:
+                ws.append(torch.zeros((pad, w.shape[1]), dtype=w.dtype, device=w.device))
+                bs.append(torch.zeros((pad,), dtype=b.dtype, device=b.device))
+            offsets[id(blk)] = (lo, n)
+            lo += n + pad
+        if not ws:
+            return None
+        return torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous(), offsets, bool(silu)
+
+
 class ResBlockND(TimestepBlock):
     def __init__(self, channels: int, emb_channels: Optional[int], dropout: float, out_channels: int = None,
                  use_conv: bool = False, use_scale_shift_norm: bool = False, spatial_dims: int = 2,
@@ -114,7 +162,15 @@ class ResBlockND(TimestepBlock):
         h = fused_group_norm(self.norm1, srcs, silu=True)
 
         addvec, scale_shift, bias1 = None, None, f32(self.conv1.conv.bias)
-        if self.uses_embedding:
+        if self.uses_embedding and isinstance(emb, TembPack) and emb.has(self):
+            # projection already computed for every block of the model in one batched launch
+            if self.use_scale_shift_norm:
+                scale_shift = emb.slice(self)
+            elif self.add_embedding_to_hidden:
+                addvec, bias1 = emb.slice(self), None  # conv1's bias is folded into the packed bias
+        elif self.uses_embedding:
+            if isinstance(emb, TembPack):
+                emb = emb.raw
             if emb is None:
                 raise ValueError("ResBlockND expects `emb` when emb_channels is set.")
             if self.use_scale_shift_norm:

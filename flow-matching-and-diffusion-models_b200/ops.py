@@ -277,12 +277,13 @@ def group_norm(
     )
     out = empty_nhwc(b, ctot, h, w, x0.device)
     if scale_shift is not None and (scale_shift.dtype != torch.float32 or scale_shift.shape != (b, 2 * ctot)
-                                    or not scale_shift.is_contiguous()):
-        raise ValueError("group_norm: scale_shift must be contiguous fp32 [B][2C]")
+                                    or scale_shift.stride(1) != 1):
+        raise ValueError("group_norm: scale_shift must be fp32 [B][2C] with unit inner stride")
     _lib.check(
         lib.fm_groupnorm_apply_bf16(
             x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, stats.data_ptr(), gamma.data_ptr(),
-            beta.data_ptr(), _ptr(scale_shift), int(silu), out.data_ptr(), st,
+            beta.data_ptr(), _ptr(scale_shift), 0 if scale_shift is None else scale_shift.stride(0), int(silu),
+            out.data_ptr(), st,
         ),
         "groupnorm_apply",
     )

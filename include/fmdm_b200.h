@@ -108,10 +108,11 @@ int64_t fm_groupnorm_workspace_elems(int32_t B, int64_t HW, int32_t C, int32_t g
 int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
                             int32_t groups, float eps, float* workspace, float* stats, fm_stream_t stream);
 /* y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), act = SiLU if silu!=0.
- * scale_shift: fp32 [B][2*C] (scale first, then shift; residual.py:109,115) or NULL. */
+ * scale_shift: fp32 rows of 2*C (scale first, then shift; residual.py:109,115), row n at scale_shift + n*ss_stride,
+ * or NULL. */
 int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
                             int32_t groups, const float* stats, const float* gamma, const float* beta,
-                            const float* scale_shift, int32_t silu, void* out, fm_stream_t stream);
+                            const float* scale_shift, int64_t ss_stride, int32_t silu, void* out, fm_stream_t stream);
 int fm_memset_f32(float* p, int64_t n, fm_stream_t stream);
 
 /* nearest-neighbour 2x upsample on NHWC bf16 (F.interpolate, src/nn/ops/upsampling.py:27) */
