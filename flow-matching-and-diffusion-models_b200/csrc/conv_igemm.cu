@@ -43,8 +43,8 @@ struct alignas(64) ConvKernelParams {
   const float* addvec;
   int addvec_stride;
   const __nv_bfloat16* residual;
-  float* gn_stats;
-  int gn_groups;
+  float* gn_partial;                // [m_tiles*4][Cout/4][2] quad statistics, or null
+  int log_wt, log_ht;               // Wt, Ht are powers of two
   int num_k_blocks;
 };
 
@@ -169,12 +169,42 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
     const int rn = row / (p.Wt * p.Ht);
     const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
     const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
-    const size_t pix = ((size_t)on * p.Ho + oh) * p.Wo + ow;
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 
-    const int cg = (p.gn_stats != nullptr) ? (p.Cout / p.gn_groups) : 0;  // channels per GN group
+    // ---- residual tile: coalesced global reads (each lane 16 B, a warp covers whole 2*BLOCK_N-byte rows) staged
+    //      into this warp's 32 rows of the swizzled output tile; the pipeline buffers are free once tmem_full fired
+    constexpr int kChunksPerRow = BLOCK_N / 8;
+    if (p.residual != nullptr) {
+      constexpr int kLoads = kChunksPerRow;  // (32 rows * kChunksPerRow) / 32 lanes
+#pragma unroll 1
+      for (int i0 = 0; i0 < kLoads; i0 += 8) {
+        uint4 buf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = (i0 + u) * 32 + lane;
+          const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+          const int rr = quad * 32 + rl;
+          const int pw = w0 + (rr & (p.Wt - 1));
+          const int ph = h0 + ((rr >> p.log_wt) & (p.Ht - 1));
+          const int pn = n0 + (rr >> (p.log_wt + p.log_ht));
+          const int col = ncol0 + ch * 8;
+          buf[u] = make_uint4(0, 0, 0, 0);
+          if (pw < p.Wo && ph < p.Ho && pn < p.B && col < p.Cout)
+            buf[u] = *reinterpret_cast<const uint4*>(p.residual + (((size_t)pn * p.Ho + ph) * p.Wo + pw) * p.Cout + col);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = (i0 + u) * 32 + lane;
+          const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+          const int rr = quad * 32 + rl;
+          uint8_t* dst = smem_gen + (ch >> 3) * (kTileM * 128) + rr * 128 + (((ch & 7) ^ (rr & 7)) * 16);
+          *reinterpret_cast<uint4*>(dst) = buf[u];
+        }
+      }
+      __syncwarp();
+    }
 
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -185,6 +215,9 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const int slab = c0 >> 6;                 // which 64-channel slab
+      const int chunk0 = (c0 & 63) >> 3;        // first 16-byte chunk within the 128-byte row (0 or 4)
+      uint8_t* rowp = smem_gen + slab * (kTileM * 128) + row * 128;
       if (col0 < p.Cout) {  // Cout % 8 == 0, handle in groups of 8 columns
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
@@ -203,8 +236,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
               v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
               v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
             }
-            if (p.residual != nullptr && valid) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + col);
+            if (p.residual != nullptr) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
               const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
               const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
               v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
@@ -213,55 +246,40 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           }
         }
       }
+
+      if (p.gn_partial != nullptr) {
+        // GroupNorm statistics for the consumer norm: per channel quad (4 channels) sum and sum of squares over this
+        // warp's 32 rows, reduced with a recursive-halving butterfly (16 values -> 16 shuffles), written without
+        // atomics to partial[(m_tile*4 + quad)][Cout/4][2] (deterministic; folded by fm_groupnorm_finalize_partials).
+        float red[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a0 = valid ? v[4 * j + 0] : 0.f, a1 = valid ? v[4 * j + 1] : 0.f;
+          const float a2 = valid ? v[4 * j + 2] : 0.f, a3 = valid ? v[4 * j + 3] : 0.f;
+          red[j] = (a0 + a1) + (a2 + a3);
+          red[8 + j] = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
+        }
+#pragma unroll
+        for (int width = 8, mask = 16; width >= 1; width >>= 1, mask >>= 1) {
+          const bool upper = (lane & mask) != 0;
+#pragma unroll
+          for (int i = 0; i < width; ++i) {
+            const float keep = upper ? red[i + width] : red[i];
+            const float give = upper ? red[i] : red[i + width];
+            red[i] = keep + __shfl_xor_sync(0xffffffffu, give, mask);
+          }
+        }
+        red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
+        const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        const int qcol = col0 + (vidx & 7) * 4;
+        if ((lane & 1) == 0 && qcol < p.Cout)
+          p.gn_partial[(((size_t)m_tile * 4 + quad) * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = red[0];
+      }
+
       // pack to bf16 and stage (128B-swizzled rows of 64 channels, one 16 KB slab per 64 output channels)
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-
-      if (p.gn_stats != nullptr) {
-        // GroupNorm partial sums of the *rounded* bf16 outputs (what the consumer norm will read).
-        // Rows of one warp may span images only when Nt > 1; handle by per-row accumulation + shuffles
-        // keyed on the (uniform within 32/(Wt*Ht) rows) image index.
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const int col = col0 + j8 * 8;
-          // 8 columns -> cg in {4, 8, 16, ...}: if cg==4 two groups, else the 8 columns sit in one group
-          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack_bf16x2(pk[j8 * 4 + j]);
-            const float a = valid ? f.x : 0.f, b = valid ? f.y : 0.f;
-            if (j < 2) { s0 += a + b; q0 += a * a + b * b; } else { s1 += a + b; q1 += a * a + b * b; }
-          }
-          if (col < p.Cout) {
-            if (p.Wt * p.Ht >= 32) {
-              // all 32 rows of this warp belong to one image: reduce across the warp first
-              s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
-              if (lane == 0 && on < p.B) {
-                float* st = p.gn_stats + ((size_t)on * p.gn_groups) * 2;
-                if (cg == 4) {
-                  atomicAdd(st + (col / 4) * 2, s0); atomicAdd(st + (col / 4) * 2 + 1, q0);
-                  atomicAdd(st + (col / 4 + 1) * 2, s1); atomicAdd(st + (col / 4 + 1) * 2 + 1, q1);
-                } else {
-                  atomicAdd(st + (col / cg) * 2, s0 + s1); atomicAdd(st + (col / cg) * 2 + 1, q0 + q1);
-                }
-              }
-            } else if (valid) {
-              float* st = p.gn_stats + ((size_t)on * p.gn_groups) * 2;
-              if (cg == 4) {
-                atomicAdd(st + (col / 4) * 2, s0); atomicAdd(st + (col / 4) * 2 + 1, q0);
-                atomicAdd(st + (col / 4 + 1) * 2, s1); atomicAdd(st + (col / 4 + 1) * 2 + 1, q1);
-              } else {
-                atomicAdd(st + (col / cg) * 2, s0 + s1); atomicAdd(st + (col / cg) * 2 + 1, q0 + q1);
-              }
-            }
-          }
-        }
-      }
-
-      const int slab = c0 >> 6;                 // which 64-channel slab
-      const int chunk0 = (c0 & 63) >> 3;        // first 16-byte chunk within the 128-byte row (0 or 4)
-      uint8_t* rowp = smem_gen + slab * (kTileM * 128) + row * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int chunk = (chunk0 + j) ^ (row & 7);
@@ -371,6 +389,21 @@ static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cud
 
 }  // namespace fm
 
+extern "C" int fm_conv_stats_layout(int32_t B, int32_t H, int32_t W, int32_t stride, int32_t* rows_per_image,
+                                    int32_t* total_rows) {
+  using namespace fm;
+  if (B <= 0 || H <= 0 || W <= 0 || (stride != 1 && stride != 2) || !rows_per_image || !total_rows) return FM_ERR_BAD_ARG;
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const int Wt = pow2_ceil(Wo) < kTileM ? pow2_ceil(Wo) : kTileM;
+  const int rest = kTileM / Wt;
+  const int Ht = pow2_ceil(Ho) < rest ? pow2_ceil(Ho) : rest;
+  if (rest / Ht != 1) return FM_ERR_UNSUPPORTED;  // several images per tile: no fused statistics
+  const int tiles = ((Wo + Wt - 1) / Wt) * ((Ho + Ht - 1) / Ht);
+  *rows_per_image = tiles * 4;
+  *total_rows = tiles * 4 * B;
+  return 0;
+}
+
 extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream) {
   using namespace fm;
   if (int e = ensure_device()) return e;
@@ -423,13 +456,13 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   FM_REQUIRE(p->bias == nullptr || ((uintptr_t)p->bias & 15) == 0, "conv: bias must be 16B aligned");
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
   FM_REQUIRE(p->residual == nullptr || ((uintptr_t)p->residual & 15) == 0, "conv: residual must be 16B aligned");
-  kp.gn_stats = p->gn_stats;
-  kp.gn_groups = p->gn_groups;
+  kp.gn_partial = p->gn_stats;
+  kp.log_wt = 0; while ((1 << kp.log_wt) < kp.Wt) ++kp.log_wt;
+  kp.log_ht = 0; while ((1 << kp.log_ht) < kp.Ht) ++kp.log_ht;
   if (p->gn_stats) {
-    FM_REQUIRE(p->gn_groups > 0 && p->Cout % p->gn_groups == 0, "conv: gn_groups=%d must divide Cout=%d",
-               p->gn_groups, p->Cout);
-    const int cg = p->Cout / p->gn_groups;
-    FM_REQUIRE(cg == 4 || cg % 8 == 0, "conv: fused GN statistics need channels/group in {4, 8k} (got %d)", cg);
+    FM_REQUIRE(kp.Nt == 1, "conv: fused GroupNorm statistics need >= 128 pixels per image (use "
+                           "fm_groupnorm_stats_bf16 for tiny images)");
+    FM_REQUIRE(p->Cout % 4 == 0, "conv: fused GroupNorm statistics need Cout %% 4 == 0");
   }
   const int m_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
   const int n_tiles = (p->Cout + block_n - 1) / block_n;

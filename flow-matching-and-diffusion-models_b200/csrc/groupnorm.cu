@@ -85,6 +85,45 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
   }
 }
 
+// stats[n][g] = (mean, rstd) from the channel-quad partial sums the conv epilogues wrote
+// (partial_s[(n*rows_s + r)][C_s/4][2]); the two sources form the virtual concat.  fp64, fixed order.
+__global__ void __launch_bounds__(128) gn_finalize_partials_kernel(const float* __restrict__ p0, int rows0, int nq0,
+                                                                  const float* __restrict__ p1, int rows1, int nq1,
+                                                                  int groups, double inv_cnt, float eps,
+                                                                  float* __restrict__ stats) {
+  __shared__ double ss[128], sq[128];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int qpg = (nq0 + nq1) / groups;  // quads per group
+  const int q_begin = g * qpg;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < qpg; ++k) {
+    const int qi = q_begin + k;
+    const float* base;
+    int rows, nq, ql;
+    if (qi < nq0) { base = p0; rows = rows0; nq = nq0; ql = qi; } else { base = p1; rows = rows1; nq = nq1; ql = qi - nq0; }
+    const float* src = base + ((size_t)n * rows * nq + ql) * 2;
+    for (int r = threadIdx.x; r < rows; r += 128) {
+      const float2 v = *reinterpret_cast<const float2*>(src + (size_t)r * nq * 2);
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+  }
+  ss[threadIdx.x] = s;
+  sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sq[threadIdx.x] += sq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = ss[0] * inv_cnt;
+    double var = sq[0] * inv_cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)n * groups + g) * 2 + 0] = (float)mean;
+    stats[((size_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __restrict__ x0, int c80,
                                                              const uint4* __restrict__ x1, int c81, int64_t HW,
                                                              int groups, const float* __restrict__ stats,
@@ -196,6 +235,24 @@ extern "C" int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x
   const double inv_cnt = 1.0 / ((double)HW * (double)((C0 + C1) / groups));
   gn_finalize_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(workspace, gx, groups, inv_cnt, eps, stats);
   FM_LAUNCH_CHECK("gn_finalize_kernel");
+  return 0;
+}
+
+extern "C" int fm_groupnorm_finalize_partials(const float* p0, int32_t rows0, int32_t C0, const float* p1,
+                                              int32_t rows1, int32_t C1, int32_t B, int64_t HW, int32_t groups,
+                                              float eps, float* stats, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(p0 != nullptr && rows0 > 0 && C0 > 0 && C0 % 4 == 0, "gn_finalize_partials: bad source 0");
+  FM_REQUIRE((p1 == nullptr) == (C1 == 0) && C1 % 4 == 0 && (p1 == nullptr || rows1 > 0),
+             "gn_finalize_partials: bad source 1");
+  const int C = C0 + C1;
+  FM_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 4 == 0,
+             "gn_finalize_partials: channels per group (%d/%d) must be a multiple of 4", C, groups);
+  FM_REQUIRE(B > 0 && B <= 65535 && HW > 0 && stats != nullptr, "gn_finalize_partials: bad argument");
+  const double inv_cnt = 1.0 / ((double)HW * (double)(C / groups));
+  gn_finalize_partials_kernel<<<dim3(groups, B), 128, 0, (cudaStream_t)stream>>>(p0, rows0, C0 / 4, p1, rows1, C1 / 4,
+                                                                                 groups, inv_cnt, eps, stats);
+  FM_LAUNCH_CHECK("gn_finalize_partials_kernel");
   return 0;
 }
 

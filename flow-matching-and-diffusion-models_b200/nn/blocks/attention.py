@@ -107,7 +107,7 @@ class SpatialSelfAttention(nn.Module):
         # raw reshape (b, heads, T, dh) -> (b, inner, T), then back to NHWC for the projection GEMM
         h_tc = ops.transpose_bf16(att.view(b, inner, t))                          # [b][T][inner]
         h_nhwc = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
-        return ops.conv2d([h_nhwc], wo, bias=f32(self.proj_out.bias), residual=x)
+        return ops.conv2d([h_nhwc], wo, bias=f32(self.proj_out.bias), residual=x, want_stats=True)
 
     def _eager(self, x):
         b, c, *spatial = x.shape
@@ -219,7 +219,7 @@ class DiffusersAttentionND(nn.Module):
         ops.attention(flat, flat[c:], flat[2 * c:], att.permute(0, 2, 3, 1).reshape(-1), batch=b, heads=self.heads,
                       tq=t, tk=t, head_dim=hd, q_strides=(t * 3 * c, hd, 3 * c), kv_strides=(t * 3 * c, hd, 3 * c),
                       o_strides=(t * c, hd, c))
-        return ops.conv2d([att], wout, bias=f32(self.to_out[0].bias), residual=x)
+        return ops.conv2d([att], wout, bias=f32(self.to_out[0].bias), residual=x, want_stats=True)
 
     def _eager(self, hidden_states, context):
         b, c = hidden_states.shape[:2]

@@ -180,17 +180,17 @@ class ResBlockND(TimestepBlock):
                 addvec = ops.linear_f32(emb, f32(self.emb_layers.weight), f32(self.emb_layers.bias), bias1,
                                         silu_in=self.emb_activation_before_proj)
                 bias1 = None
-        h = ops.conv2d([h], self.conv1.packed([self.channels]), bias=bias1, addvec=addvec)
+        h = ops.conv2d([h], self.conv1.packed([self.channels]), bias=bias1, addvec=addvec, want_stats=True)
         h = fused_group_norm(self.norm2, [h], silu=True, scale_shift=scale_shift)
 
         if isinstance(self.skip_connection, nn.Identity):
             if len(srcs) != 1:
                 srcs = [ops.to_nhwc_bf16(torch.cat(srcs, 1))]
             return ops.conv2d([h], self.conv2.packed([self.out_channels]), bias=f32(self.conv2.conv.bias),
-                              residual=srcs[0])
+                              residual=srcs[0], want_stats=True)
         split = [s.shape[1] for s in srcs]
         pw, bias = self._fused_tail_weight(split)
-        return ops.conv2d([h] + srcs, pw, bias=bias)
+        return ops.conv2d([h] + srcs, pw, bias=bias, want_stats=True)
 
     # eager PyTorch restatement used only for out-of-scope variants (FMDM_B200_ALLOW_EAGER=1)
     def _eager(self, x: torch.Tensor, emb):

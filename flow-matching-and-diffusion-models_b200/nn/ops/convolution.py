@@ -59,7 +59,7 @@ class ConvND(nn.Module):
 
         return self._cache.get("w:" + ",".join(map(str, split)), [w], build)
 
-    def forward(self, x, *, addvec=None, residual=None) -> torch.Tensor:
+    def forward(self, x, *, addvec=None, residual=None, want_stats: bool = False) -> torch.Tensor:
         srcs = list(x) if isinstance(x, (tuple, list)) else [x]
         if not self.fast_path_ok():
             c = self.conv
@@ -82,7 +82,7 @@ class ConvND(nn.Module):
         srcs = [ops.to_nhwc_bf16(s) for s in srcs]
         pw = self.packed([s.shape[1] for s in srcs])
         return ops.conv2d(srcs, pw, stride=_as_int(self.conv.stride), bias=f32(self.conv.bias), addvec=addvec,
-                          residual=None if residual is None else ops.to_nhwc_bf16(residual))
+                          residual=None if residual is None else ops.to_nhwc_bf16(residual), want_stats=want_stats)
 
 
 class ConvTransposeND(nn.Module):

@@ -28,7 +28,7 @@ class UpsampleND(nn.Module):
             y = F.interpolate(x.float(), scale_factor=2, mode="nearest")
             return self.conv(y) if self.use_conv else y
         y = ops.upsample_nearest2x(ops.to_nhwc_bf16(x))
-        return self.conv(y) if self.use_conv else y
+        return self.conv(y, want_stats=True) if self.use_conv else y
 
 
 class DownsampleND(nn.Module):
@@ -50,4 +50,4 @@ class DownsampleND(nn.Module):
         if not self.use_conv:
             out_of_scope("DownsampleND(use_conv=False)")
             return self.op(x.float())
-        return self.op(x)
+        return self.op(x, want_stats=True)

@@ -153,8 +153,12 @@ def conv2d(
     addvec: Optional[torch.Tensor] = None,
     residual: Optional[torch.Tensor] = None,
     out: Optional[torch.Tensor] = None,
+    want_stats: bool = False,
 ) -> torch.Tensor:
-    """Implicit-GEMM conv over the virtual channel concat of `srcs` (one K segment per source)."""
+    """Implicit-GEMM conv over the virtual channel concat of `srcs` (one K segment per source).
+
+    want_stats: also emit, from the epilogue, the GroupNorm partial statistics of the output; they ride on the
+    returned tensor (`out._fm_stats`) and let the consumer `group_norm` skip its statistics pass."""
     lib = _lib.lib()
     if len(srcs) != len(weight.seg_channels) or len(srcs) > _lib.FM_CONV_MAX_SEG:
         raise ValueError(f"conv2d: {len(srcs)} sources for {len(weight.seg_channels)} weight segments")
@@ -192,9 +196,17 @@ def conv2d(
     p.out = out.data_ptr()
     p.gn_stats = None
     p.gn_groups = 0
+    stats_ws = None
+    if want_stats and weight.cout % 4 == 0:
+        rpi, tot = C.c_int32(0), C.c_int32(0)
+        if lib.fm_conv_stats_layout(b, h, w, stride, C.byref(rpi), C.byref(tot)) == 0:
+            stats_ws = torch.empty((tot.value, weight.cout // 4, 2), dtype=torch.float32, device=srcs[0].device)
+            p.gn_stats = stats_ws.data_ptr()
     e0 = _prof_begin()
     _lib.check(lib.fm_conv2d_igemm_bf16(C.byref(p), _stream()), "conv2d_igemm_bf16")
     _prof_end("conv_igemm", 2.0 * b * ho * wo * weight.cout * weight.mat.shape[1], e0)
+    if stats_ws is not None:
+        out._fm_stats = (stats_ws, rpi.value)
     return out
 
 
@@ -264,17 +276,27 @@ def group_norm(
     c1 = x1.shape[1] if x1 is not None else 0
     ctot = c0 + c1
     stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x0.device)
-    ws_elems = int(lib.fm_groupnorm_workspace_elems(b, h * w, ctot, groups))
-    if ws_elems <= 0:
-        raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={ctot} groups={groups}")
-    ws = torch.empty((ws_elems,), dtype=torch.float32, device=x0.device)
     st = _stream()
     e0 = _prof_begin()
-    _lib.check(
-        lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps), ws.data_ptr(),
-                                    stats.data_ptr(), st),
-        "groupnorm_stats",
-    )
+    fused = [getattr(s, "_fm_stats", None) for s in srcs]
+    if all(f is not None for f in fused) and (ctot // groups) % 4 == 0:
+        # statistics were produced by the convs that wrote the sources: fold their partial sums, no extra read pass
+        p1 = fused[1] if len(fused) == 2 else (None, 0)
+        _lib.check(
+            lib.fm_groupnorm_finalize_partials(fused[0][0].data_ptr(), fused[0][1], c0, _ptr(p1[0]), p1[1], c1, b,
+                                               h * w, groups, float(eps), stats.data_ptr(), st),
+            "groupnorm_finalize_partials",
+        )
+    else:
+        ws_elems = int(lib.fm_groupnorm_workspace_elems(b, h * w, ctot, groups))
+        if ws_elems <= 0:
+            raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={ctot} groups={groups}")
+        ws = torch.empty((ws_elems,), dtype=torch.float32, device=x0.device)
+        _lib.check(
+            lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps),
+                                        ws.data_ptr(), stats.data_ptr(), st),
+            "groupnorm_stats",
+        )
     out = empty_nhwc(b, ctot, h, w, x0.device)
     if scale_shift is not None and (scale_shift.dtype != torch.float32 or scale_shift.shape != (b, 2 * ctot)
                                     or scale_shift.stride(1) != 1):

@@ -74,12 +74,18 @@ typedef struct fm_conv_params {
   int32_t _pad1;
   const void* residual;    /* bf16 NHWC [B][Ho][Wo][Cout] or NULL                        */
   void* out;               /* bf16 NHWC [B][Ho][Wo][Cout]                                */
-  float* gn_stats;         /* fp32 [B][gn_groups][2] (sum, sumsq) accumulated over `out`, or NULL; must be zeroed by caller */
-  int32_t gn_groups;
+  float* gn_stats;         /* fp32 [total_rows][Cout/4][2] workspace (fm_conv_stats_layout) receiving, per 32-row
+                              group of every M tile, the channel-quad (sum, sumsq) of `out` for the consumer
+                              GroupNorm (no atomics; folded by fm_groupnorm_finalize_partials), or NULL */
+  int32_t gn_groups;       /* unused (kept for layout stability) */
   int32_t _pad2;
 } fm_conv_params;
 
 int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream);
+/* Row-group layout of the fused GroupNorm statistics for a conv with this input size/stride: 4 rows per M tile.
+ * Returns FM_ERR_UNSUPPORTED when an M tile would span several images (fewer than 128 output pixels per image). */
+int fm_conv_stats_layout(int32_t B, int32_t H, int32_t W, int32_t stride, int32_t* rows_per_image,
+                         int32_t* total_rows);
 
 /* Re-order an OIHW fp32 conv weight (or [O][I] linear weight with ksize=1) into the K-major bf16 matrix the
  * conv kernel reads: dst[co][koff + tap*Cseg + c] = src[co][c_begin + c][kh][kw]. */
@@ -107,6 +113,11 @@ int fm_conv_head_bf16_f32(const void* x_nhwc_bf16, const float* weight_oihw, con
 int64_t fm_groupnorm_workspace_elems(int32_t B, int64_t HW, int32_t C, int32_t groups);
 int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
                             int32_t groups, float eps, float* workspace, float* stats, fm_stream_t stream);
+/* Same statistics from the channel-quad partial sums written by the producing convs' epilogues (virtual concat of
+ * two producers): p_s is [B*rows_s][C_s/4][2]. */
+int fm_groupnorm_finalize_partials(const float* p0, int32_t rows0, int32_t C0, const float* p1, int32_t rows1,
+                                   int32_t C1, int32_t B, int64_t HW, int32_t groups, float eps, float* stats,
+                                   fm_stream_t stream);
 /* y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), act = SiLU if silu!=0.
  * scale_shift: fp32 rows of 2*C (scale first, then shift; residual.py:109,115), row n at scale_shift + n*ss_stride,
  * or NULL. */

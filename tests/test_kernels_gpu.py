@@ -183,3 +183,37 @@ def test_timestep_embedding_and_linear():
     ref = F.silu(F.linear(x, w, b))
     out = ops.linear_f32(x, w, b, silu_out=True)
     assert float((out - ref).abs().max()) < 1e-4
+
+
+def test_conv_fused_groupnorm_statistics():
+    """GroupNorm fed by the conv epilogue's channel-quad partial sums == GroupNorm with its own statistics pass."""
+    g = torch.Generator().manual_seed(11)
+    for (B, H, W, cin, cout, stride) in [(2, 32, 32, 64, 128, 1), (3, 28, 28, 64, 64, 1), (2, 32, 32, 128, 256, 2),
+                                         (1, 16, 48, 64, 512, 1)]:
+        x = _bf16r(torch.randn(B, cin, H, W, generator=g)).to(DEV)
+        w = _bf16r(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(DEV)
+        bias = torch.randn(cout, generator=g).to(DEV)
+        res = None
+        if stride == 1:
+            res = _bf16r(torch.randn(B, cout, H, W, generator=g)).to(DEV)
+        pw = ops.pack_conv_weight([(w, 0, cin)])
+        y = ops.conv2d([_nhwc(x)], pw, stride=stride, bias=bias, residual=None if res is None else _nhwc(res),
+                       want_stats=True)
+        assert hasattr(y, "_fm_stats")
+        gamma = torch.randn(cout, generator=g).to(DEV)
+        beta = torch.randn(cout, generator=g).to(DEV)
+        fused = ops.group_norm([y], 32, 1e-5, gamma, beta, silu=True).float()
+        plain = ops.group_norm([y.clone(memory_format=torch.preserve_format)], 32, 1e-5, gamma, beta, silu=True).float()
+        ref = F.silu(F.group_norm(y.float(), 32, gamma, beta, 1e-5))
+        assert _rel_l2(fused, ref) < 5e-3 and _rel_l2(fused, plain) < 2e-3
+    # virtual concat of two producers with a group size that straddles neither source evenly (384 ch -> 12/group)
+    xa = _bf16r(torch.randn(2, 64, 16, 16, generator=g)).to(DEV)
+    wa = _bf16r(torch.randn(256, 64, 3, 3, generator=g) / 24).to(DEV)
+    wb = _bf16r(torch.randn(128, 64, 3, 3, generator=g) / 24).to(DEV)
+    ya = ops.conv2d([_nhwc(xa)], ops.pack_conv_weight([(wa, 0, 64)]), want_stats=True)
+    yb = ops.conv2d([_nhwc(xa)], ops.pack_conv_weight([(wb, 0, 64)]), want_stats=True)
+    gamma = torch.randn(384, generator=g).to(DEV)
+    beta = torch.randn(384, generator=g).to(DEV)
+    fused = ops.group_norm([ya, yb], 32, 1e-5, gamma, beta, silu=False).float()
+    ref = F.group_norm(torch.cat([ya.float(), yb.float()], 1), 32, gamma, beta, 1e-5)
+    assert _rel_l2(fused, ref) < 5e-3
