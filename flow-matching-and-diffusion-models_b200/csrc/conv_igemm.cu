@@ -16,6 +16,7 @@
 // (warp w owns TMEM lanes 32*(w%4)..+31).  Reference op replaced: nn.Conv2d via ConvND.forward
 // (src/nn/ops/convolution.py:53-54) and the adds around it in ResBlockND.forward (src/nn/blocks/residual.py:97-120).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -45,37 +46,54 @@ struct alignas(64) ConvKernelParams {
   const __nv_bfloat16* residual;
   float* gn_partial;                // [m_tiles*4][Cout/4][2] quad statistics, or null
   int log_wt, log_ht;               // Wt, Ht are powers of two
+  int desc_base_offset;             // row mode: encode the swizzle phase of row-shifted A views in the descriptor
   int num_k_blocks;
 };
 
-template <int BLOCK_N>
+// MODE 0: one A tile per (tap, 64-channel block)  - any tile box, stride 1/2.
+// MODE 1: "row" mode for stride-1 convs whose M tile is 128 consecutive pixels of one image row (Wt == 128):
+//         ONE TMA load of the 130-pixel halo row per (kh, channel block) serves the three kw taps - the UMMA A
+//         descriptor simply starts kw rows (kw*128 B) into the slot; the 128B swizzle is a function of the absolute
+//         shared-memory address, so a row-shifted view of a TMA-written tile is still a valid SW128 K-major operand.
+//         A traffic from L2 drops 3x (the per-tap form re-reads every input pixel nine times).
+constexpr int kARowBytes = 128;
+constexpr int kARowSlot = 17 * 1024;  // 130 rows * 128 B = 16640 B, rounded up to keep every slot 1024 B aligned
+constexpr int kARowTx = 130 * 128;
+
+template <int BLOCK_N, int MODE>
 struct ConvCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 3 : 4);
-  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kASlot = (MODE == 1) ? kARowSlot : kABytes;
+  static constexpr int kATx = (MODE == 1) ? kARowTx : kABytes;
+  static constexpr int kAStages = (MODE == 1) ? ((BLOCK_N == 256) ? 3 : 2) : ((BLOCK_N == 128) ? 3 : 4);
+  static constexpr int kBStages = (MODE == 1) ? ((BLOCK_N == 256) ? 5 : 4) : kAStages;
+  static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
   static constexpr int kOutBytes = kTileM * BLOCK_N * 2;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + (kPipeBytes > kOutBytes ? kPipeBytes : kOutBytes) + 256;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 1;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kPipeBytes + 256;
   static_assert(kOutBytes <= kPipeBytes, "output staging reuses the pipeline buffers");
+  static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a0 = smem_base;
-  const uint32_t smem_b0 = smem_base + Cfg::kStages * kABytes;
+  const uint32_t smem_b0 = smem_base + Cfg::kAStages * Cfg::kASlot;
   const uint32_t bar_base = smem_base + Cfg::kPipeBytes;
-  // barriers: full[kStages], empty[kStages], tmem_full; then the TMEM base address word
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 1);
+  // barriers: a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full; then the TMEM base address word
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (Cfg::kNumBars - 1);
+  const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kPipeBytes + 8 * (2 * Cfg::kStages + 1));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kPipeBytes + 8 * Cfg::kNumBars);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,7 +107,6 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   const int tw = rem - th * p.tiles_w;
   const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt;
   const int ncol0 = blockIdx.y * BLOCK_N;
-  const int nk = p.num_k_blocks;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.src[s]);
@@ -98,11 +115,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < Cfg::kStages; ++s) {
-        mbar_init(full_bar(s), 1);
-        mbar_init(empty_bar(s), 1);
-      }
-      mbar_init(tmem_full_bar, 1);
+      for (int s = 0; s < Cfg::kNumBars; ++s) mbar_init(bar_base + 8u * s, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -113,26 +126,36 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
+  // K loop shape shared by the producer and the MMA issuer.  Per segment: `asteps` A loads per channel block
+  // (MODE 0: one per tap; MODE 1: one per kh), each feeding `bsteps` weight tiles (MODE 0: 1; MODE 1: the kw taps).
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      int it = 0;
+      int ia = 0, ib = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const int taps = p.seg_taps[s];
         const int C = p.seg_c[s];
         const int cblocks = (C + kBlockK - 1) / kBlockK;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int dh = (taps == 9) ? (tap / 3 - 1) : 0;
-          const int dw = (taps == 9) ? (tap % 3 - 1) : 0;
-          for (int cb = 0; cb < cblocks; ++cb, ++it) {
-            const int stage = it % Cfg::kStages;
-            const uint32_t phase = (it / Cfg::kStages) & 1;
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_4d(&p.src[s], full_bar(stage), smem_a0 + stage * kABytes, cb * kBlockK,
-                        w0 * p.stride + dw, h0 * p.stride + dh, n0);
-            tma_load_2d(&p.wgt, full_bar(stage), smem_b0 + stage * Cfg::kBBytes,
-                        p.seg_koff[s] + tap * C + cb * kBlockK, ncol0);
+        const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
+        const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
+        for (int as = 0; as < asteps; ++as) {
+          int dh, dw;
+          if (MODE == 1) { dh = (taps == 9) ? as - 1 : 0; dw = -1; }
+          else { dh = (taps == 9) ? (as / 3 - 1) : 0; dw = (taps == 9) ? (as % 3 - 1) : 0; }
+          for (int cb = 0; cb < cblocks; ++cb, ++ia) {
+            const int sa = ia % Cfg::kAStages;
+            mbar_wait(a_empty(sa), ((ia / Cfg::kAStages) & 1) ^ 1u);
+            mbar_expect_tx(a_full(sa), Cfg::kATx);
+            tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot, cb * kBlockK, w0 * p.stride + dw,
+                        h0 * p.stride + dh, n0);
+            for (int bs = 0; bs < bsteps; ++bs, ++ib) {
+              const int tap = (MODE == 1) ? (taps == 9 ? as * 3 + bs : 0) : as;
+              const int sb = ib % Cfg::kBStages;
+              mbar_wait(b_empty(sb), ((ib / Cfg::kBStages) & 1) ^ 1u);
+              mbar_expect_tx(b_full(sb), Cfg::kBBytes);
+              tma_load_2d(&p.wgt, b_full(sb), smem_b0 + sb * Cfg::kBBytes, p.seg_koff[s] + tap * C + cb * kBlockK,
+                          ncol0);
+            }
           }
         }
       }
@@ -140,25 +163,47 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, BLOCK_N);
-    for (int it = 0; it < nk; ++it) {
-      const int stage = it % Cfg::kStages;
-      const uint32_t phase = (it / Cfg::kStages) & 1;
-      mbar_wait(full_bar(stage), phase);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_a0 + stage * kABytes;
-        const uint32_t b_addr = smem_b0 + stage * Cfg::kBBytes;
+    int ia = 0, ib = 0;
+    uint32_t accumulate = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      const int taps = p.seg_taps[s];
+      const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
+      const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
+      const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
+      for (int as = 0; as < asteps; ++as) {
+        for (int cb = 0; cb < cblocks; ++cb, ++ia) {
+          const int sa = ia % Cfg::kAStages;
+          mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
+          for (int bs = 0; bs < bsteps; ++bs, ++ib) {
+            const int sb = ib % Cfg::kBStages;
+            mbar_wait(b_full(sb), (ib / Cfg::kBStages) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              // MODE 1: tap kw reads the halo row starting kw pixels in (a 1x1 segment reads the centre, kw = 1)
+              const int a_row = (MODE == 1) ? (taps == 9 ? bs : 1) : 0;
+              const uint32_t a_addr = smem_a0 + sa * Cfg::kASlot + a_row * kARowBytes;
+              const uint32_t b_addr = smem_b0 + sb * Cfg::kBBytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = make_sw128_kmajor_desc(a_addr + k * 32);
-          const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
-          umma_bf16_ss(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                uint64_t da = make_sw128_kmajor_desc(a_addr + k * 32);
+                // a start address that is not 1024 B aligned needs the swizzle phase ("matrix base offset",
+                // descriptor bits [49,52)) = (address >> 7) & 7, per the PTX matrix-descriptor rules
+                if (MODE == 1 && p.desc_base_offset) da |= (uint64_t)((a_addr >> 7) & 7) << 49;
+                const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
+                umma_bf16_ss(tmem_base, da, db, idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(b_empty(sb));  // frees the weight slot once these MMAs retire
+            }
+            __syncwarp();
+          }
+          if (lane == 0) umma_commit(a_empty(sa));
+          __syncwarp();
         }
-        umma_commit(empty_bar(stage));                 // frees the smem stage once these MMAs retire
-        if (it == nk - 1) umma_commit(tmem_full_bar);  // accumulator complete
       }
-      __syncwarp();
     }
+    if (lane == 0) umma_commit(tmem_full_bar);  // accumulator complete
+    __syncwarp();
   } else {
     // ================= epilogue (warps 2..5) =================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
@@ -372,17 +417,17 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cudaStream_t st) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_igemm)");
     attr_set = true;
   }
-  conv_igemm_kernel<BLOCK_N><<<dim3(m_tiles, n_tiles), kConvThreads, Cfg::kSmemBytes, st>>>(kp);
+  conv_igemm_kernel<BLOCK_N, MODE><<<dim3(m_tiles, n_tiles), kConvThreads, Cfg::kSmemBytes, st>>>(kp);
   FM_LAUNCH_CHECK("conv_igemm_kernel");
   return 0;
 }
@@ -429,6 +474,13 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   kp.stride = p->stride;
   kp.B = p->B; kp.Ho = Ho; kp.Wo = Wo; kp.Cout = p->Cout;
   kp.nseg = p->nseg;
+  // row mode (kw tap reuse): stride 1, M tile = 128 consecutive pixels of one row, at least one 3x3 segment
+  bool row_mode = (p->stride == 1 && kp.Wt == kTileM && getenv("FMDM_CONV_NO_ROW_MODE") == nullptr);
+  {
+    bool any3 = false;
+    for (int s = 0; s < p->nseg; ++s) any3 |= (p->seg[s].ksize == 3);
+    row_mode = row_mode && any3;
+  }
   int ktot = 0, nk = 0;
   for (int s = 0; s < p->nseg; ++s) {
     const fm_conv_seg& sg = p->seg[s];
@@ -442,7 +494,9 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
     kp.seg_koff[s] = ktot;
     ktot += kp.seg_taps[s] * sg.C;
     nk += kp.seg_taps[s] * ((sg.C + kBlockK - 1) / kBlockK);
-    if (int e = encode_act_map(&kp.src[s], sg.src, sg.C, p->W, p->H, p->B, kp.Wt, kp.Ht, kp.Nt, p->stride)) return e;
+    if (int e = encode_act_map(&kp.src[s], sg.src, sg.C, p->W, p->H, p->B, row_mode ? kTileM + 2 : kp.Wt, kp.Ht, kp.Nt,
+                               p->stride))
+      return e;
   }
   kp.num_k_blocks = nk;
   const int block_n = (p->Cout > 128) ? 256 : (p->Cout > 64 ? 128 : 64);
@@ -456,6 +510,10 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   FM_REQUIRE(p->bias == nullptr || ((uintptr_t)p->bias & 15) == 0, "conv: bias must be 16B aligned");
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
   FM_REQUIRE(p->residual == nullptr || ((uintptr_t)p->residual & 15) == 0, "conv: residual must be 16B aligned");
+  {
+    const char* bo = getenv("FMDM_CONV_DESC_BASE_OFFSET");
+    kp.desc_base_offset = bo ? atoi(bo) : 0;  // measured on B200: the swizzle is address-based, phase bits must stay 0
+  }
   kp.gn_partial = p->gn_stats;
   kp.log_wt = 0; while ((1 << kp.log_wt) < kp.Wt) ++kp.log_wt;
   kp.log_ht = 0; while ((1 << kp.log_ht) < kp.Ht) ++kp.log_ht;
@@ -467,9 +525,16 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   const int m_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
   const int n_tiles = (p->Cout + block_n - 1) / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (row_mode) {
+    switch (block_n) {
+      case 64: return launch_conv<64, 1>(kp, m_tiles, n_tiles, st);
+      case 128: return launch_conv<128, 1>(kp, m_tiles, n_tiles, st);
+      default: return launch_conv<256, 1>(kp, m_tiles, n_tiles, st);
+    }
+  }
   switch (block_n) {
-    case 64: return launch_conv<64>(kp, m_tiles, n_tiles, st);
-    case 128: return launch_conv<128>(kp, m_tiles, n_tiles, st);
-    default: return launch_conv<256>(kp, m_tiles, n_tiles, st);
+    case 64: return launch_conv<64, 0>(kp, m_tiles, n_tiles, st);
+    case 128: return launch_conv<128, 0>(kp, m_tiles, n_tiles, st);
+    default: return launch_conv<256, 0>(kp, m_tiles, n_tiles, st);
   }
 }

@@ -9,6 +9,7 @@ namespace fm {
 
 constexpr int kStemMaxCin = 8;
 constexpr int kStemThreads = 256;
+constexpr int kStemPix = 4;
 
 // one thread = one output pixel x 8 output channels; weights live in smem as [ci*9+tap][co]; 32-bit index math.
 __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __restrict__ x0, int C0,
@@ -29,50 +30,69 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sbias[i] = bias ? bias[i] : 0.f;
   __syncthreads();
 
+  // one thread = 8 output channels x kStemPix consecutive pixels of a row: every weight vector fetched from shared
+  // memory feeds kStemPix*8 FMAs (with one pixel per thread the kernel is shared-memory-bandwidth bound)
   const int chunks = Cout >> 3;
-  const int ppb = kStemThreads / chunks;  // pixels per block iteration
+  const int gpb = kStemThreads / chunks;  // pixel groups per block iteration
   const int c8 = threadIdx.x % chunks;
-  const int pl = threadIdx.x / chunks;
-  if (pl >= ppb) return;
+  const int gl = threadIdx.x / chunks;
+  if (gl >= gpb) return;
   const int HW = H * W;
-  const int total = B * HW;
+  const int WG = (W + kStemPix - 1) / kStemPix;
+  const int groups_per_img = H * WG;
+  const int total = B * groups_per_img;
   float bi[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bi[j] = sbias[c8 * 8 + j];
-  for (int pix = blockIdx.x * ppb + pl; pix < total; pix += gridDim.x * ppb) {
-    const int n = pix / HW;
-    const int rem = pix - n * HW;
-    const int h = rem / W;
-    const int w = rem - h * W;
-    float acc[8];
+  for (int grp = blockIdx.x * gpb + gl; grp < total; grp += gridDim.x * gpb) {
+    const int n = grp / groups_per_img;
+    const int rem = grp - n * groups_per_img;
+    const int h = rem / WG;
+    const int wbase = (rem - h * WG) * kStemPix;
+    float acc[kStemPix][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bi[j];
+    for (int p = 0; p < kStemPix; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = bi[j];
     for (int ci = 0; ci < Cin; ++ci) {
       const float* src = (ci < C0) ? x0 + ((size_t)n * C0 + ci) * HW : x1 + ((size_t)n * C1 + (ci - C0)) * HW;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int ih = h + kh - 1;
-        const bool hok = (unsigned)ih < (unsigned)H;
+        if ((unsigned)ih >= (unsigned)H) continue;
+        float xin[kStemPix + 2];
+#pragma unroll
+        for (int q = 0; q < kStemPix + 2; ++q) {
+          const int iw = wbase + q - 1;
+          // zero padding applies AFTER the optional 2x-1 centering (the reference centres, then convolves)
+          xin[q] = ((unsigned)iw < (unsigned)W) ? fmaf(__ldg(src + ih * W + iw), in_scale, in_shift) : 0.f;
+        }
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int iw = w + kw - 1;
-          if (hok && (unsigned)iw < (unsigned)W) {
-            const float xv = fmaf(__ldg(src + ih * W + iw), in_scale, in_shift);
-            const float* wp = sw + (ci * 9 + kh * 3 + kw) * Cout + c8 * 8;
-            const float4 w0 = *reinterpret_cast<const float4*>(wp);
-            const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
-            acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-            acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-            acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+          const float* wp = sw + (ci * 9 + kh * 3 + kw) * Cout + c8 * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+          for (int p = 0; p < kStemPix; ++p) {
+            const float xv = xin[p + kw];
+            acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]);
+            acc[p][2] = fmaf(xv, w0.z, acc[p][2]); acc[p][3] = fmaf(xv, w0.w, acc[p][3]);
+            acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
+            acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
           }
         }
       }
     }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    out[(size_t)pix * chunks + c8] = o;
+    const size_t pix0 = ((size_t)n * H + h) * W + wbase;
+#pragma unroll
+    for (int p = 0; p < kStemPix; ++p) {
+      if (wbase + p < W) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[p][0], acc[p][1]); o.y = pack_bf16x2(acc[p][2], acc[p][3]);
+        o.z = pack_bf16x2(acc[p][4], acc[p][5]); o.w = pack_bf16x2(acc[p][6], acc[p][7]);
+        out[(pix0 + p) * chunks + c8] = o;
+      }
+    }
   }
 }
 
@@ -170,8 +190,8 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_stem)");
     attr = smem;
   }
-  const int ppb = kStemThreads / (Cout / 8);
-  int64_t blocks = ((int64_t)B * H * W + ppb - 1) / ppb;
+  const int gpb = kStemThreads / (Cout / 8);
+  int64_t blocks = ((int64_t)B * H * ((W + kStemPix - 1) / kStemPix) + gpb - 1) / gpb;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   conv_stem_kernel<<<(int)blocks, kStemThreads, smem, (cudaStream_t)stream>>>(

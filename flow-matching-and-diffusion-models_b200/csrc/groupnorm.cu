@@ -167,19 +167,32 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
   int64_t p_end = p_begin + pix_per_block;
   if (p_end > HW) p_end = HW;
   const int64_t base = (int64_t)n * HW;
-  for (int64_t p = p_begin + prow; p < p_end; p += ppi) {
-    const uint4 u = ld_chunk(x0, c80, x1, c81, base + p, chunk);
-    const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-    float v[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+  constexpr int kUnroll = 4;  // independent 16-byte loads in flight per thread
+  for (int64_t p = p_begin + prow; p < p_end; p += (int64_t)ppi * kUnroll) {
+    uint4 u[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = fmaf(v[j], a[j], b[j]);
-      if (silu) v[j] = silu_f(v[j]);
+    for (int k = 0; k < kUnroll; ++k) {
+      const int64_t pk = p + (int64_t)k * ppi;
+      u[k] = make_uint4(0, 0, 0, 0);
+      if (pk < p_end) u[k] = ld_chunk(x0, c80, x1, c81, base + pk, chunk);
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    out[(base + p) * tpp + chunk] = o;
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int64_t pk = p + (int64_t)k * ppi;
+      if (pk >= p_end) break;
+      const float2 f0 = unpack_bf16x2(u[k].x), f1 = unpack_bf16x2(u[k].y), f2 = unpack_bf16x2(u[k].z),
+                   f3 = unpack_bf16x2(u[k].w);
+      float v[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = fmaf(v[j], a[j], b[j]);
+        if (silu) v[j] = silu_f(v[j]);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      out[(base + pk) * tpp + chunk] = o;
+    }
   }
 }
 

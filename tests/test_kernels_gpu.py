@@ -71,6 +71,13 @@ CONV_CASES = [
     (1, 64, 256, [128], 128, [3], 1, True, True, True),
     (2, 33, 35, [64], 64, [3], 2, True, False, False),
     (1, 1024, 1, [512], 1536, [1], 1, True, False, False),
+    # row mode (Wt == 128): kw taps served from one 130-pixel halo row
+    (1, 8, 128, [64], 64, [3], 1, True, False, False),
+    (2, 5, 256, [128], 128, [3], 1, True, True, True),
+    (1, 6, 200, [64, 128], 256, [3, 3], 1, True, True, False),
+    (2, 4, 130, [128, 64, 64], 128, [3, 1, 1], 1, True, False, False),
+    (1, 3, 512, [256], 512, [3], 1, True, False, True),
+    (1, 7, 100, [32], 72, [3], 1, True, False, False),
 ]
 
 
