@@ -60,13 +60,20 @@ constexpr int kARowBytes = 128;
 constexpr int kARowSlot = 17 * 1024;  // 130 rows * 128 B = 16640 B, rounded up to keep every slot 1024 B aligned
 constexpr int kARowTx = 130 * 128;
 
-template <int BLOCK_N, int MODE>
+// CG = 2: a CTA pair (cluster of two) computes a 256-row tile with tcgen05.mma.cta_group::2; each CTA stages its own
+//         128 (130) A rows and HALF of the weight tile, so weight traffic from L2 per CTA halves and one MMA
+//         instruction covers twice the work (the single issuing thread of the leader CTA is no longer the pacer).
+template <int BLOCK_N, int MODE, int CG>
 struct ConvCfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
   static constexpr int kASlot = (MODE == 1) ? kARowSlot : kABytes;
   static constexpr int kATx = (MODE == 1) ? kARowTx : kABytes;
-  static constexpr int kAStages = (MODE == 1) ? ((BLOCK_N == 256) ? 3 : 2) : ((BLOCK_N == 128) ? 3 : 4);
-  static constexpr int kBStages = (MODE == 1) ? ((BLOCK_N == 256) ? 5 : 4) : kAStages;
+  static constexpr int kAStages =
+      (CG == 2) ? ((MODE == 1) ? ((BLOCK_N == 256) ? 4 : 3) : ((BLOCK_N == 256) ? 6 : 4))
+                : ((MODE == 1) ? ((BLOCK_N == 256) ? 3 : 2) : ((BLOCK_N == 128) ? 3 : 4));
+  static constexpr int kBStages =
+      (CG == 2) ? ((MODE == 1) ? ((BLOCK_N == 256) ? 8 : 6) : kAStages)
+                : ((MODE == 1) ? ((BLOCK_N == 256) ? 5 : 4) : kAStages);
   static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
   static constexpr int kOutBytes = kTileM * BLOCK_N * 2;
   static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 1;
@@ -75,10 +82,12 @@ struct ConvCfg {
   static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
 };
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N, MODE>;
+  using Cfg = ConvCfg<BLOCK_N, MODE, CG>;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -119,10 +128,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<BLOCK_N>(tmem_slot);
+    if (CG == 2) tmem_alloc_pair<BLOCK_N>(tmem_slot); else tmem_alloc<BLOCK_N>(tmem_slot);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // pair: the peer's barriers must exist before remote arrivals
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -145,24 +154,37 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
           for (int cb = 0; cb < cblocks; ++cb, ++ia) {
             const int sa = ia % Cfg::kAStages;
             mbar_wait(a_empty(sa), ((ia / Cfg::kAStages) & 1) ^ 1u);
-            mbar_expect_tx(a_full(sa), Cfg::kATx);
-            tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot, cb * kBlockK, w0 * p.stride + dw,
-                        h0 * p.stride + dh, n0);
+            if (CG == 2) {
+              // both CTAs' bytes land on the LEADER's full barrier; only the leader arms it (with the pair's total)
+              if (is_leader) mbar_expect_tx(a_full(sa), 2 * Cfg::kATx);
+              tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot, cb * kBlockK,
+                               w0 * p.stride + dw, h0 * p.stride + dh, n0);
+            } else {
+              mbar_expect_tx(a_full(sa), Cfg::kATx);
+              tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot, cb * kBlockK, w0 * p.stride + dw,
+                          h0 * p.stride + dh, n0);
+            }
             for (int bs = 0; bs < bsteps; ++bs, ++ib) {
               const int tap = (MODE == 1) ? (taps == 9 ? as * 3 + bs : 0) : as;
               const int sb = ib % Cfg::kBStages;
               mbar_wait(b_empty(sb), ((ib / Cfg::kBStages) & 1) ^ 1u);
-              mbar_expect_tx(b_full(sb), Cfg::kBBytes);
-              tma_load_2d(&p.wgt, b_full(sb), smem_b0 + sb * Cfg::kBBytes, p.seg_koff[s] + tap * C + cb * kBlockK,
-                          ncol0);
+              if (CG == 2) {
+                if (is_leader) mbar_expect_tx(b_full(sb), 2 * Cfg::kBBytes);
+                tma_load_2d_pair(&p.wgt, mapa_shared(b_full(sb), 0), smem_b0 + sb * Cfg::kBBytes,
+                                 p.seg_koff[s] + tap * C + cb * kBlockK, ncol0 + (int)cta_rank * (BLOCK_N / 2));
+              } else {
+                mbar_expect_tx(b_full(sb), Cfg::kBBytes);
+                tma_load_2d(&p.wgt, b_full(sb), smem_b0 + sb * Cfg::kBBytes, p.seg_koff[s] + tap * C + cb * kBlockK,
+                            ncol0);
+              }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, BLOCK_N);
+  } else if (warp == 1 && is_leader) {
+    // ================= MMA issuer (pair: leader CTA only) =================
+    constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM * CG, BLOCK_N);
     int ia = 0, ib = 0;
     uint32_t accumulate = 0;
     for (int s = 0; s < p.nseg; ++s) {
@@ -190,21 +212,25 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 // descriptor bits [49,52)) = (address >> 7) & 7, per the PTX matrix-descriptor rules
                 if (MODE == 1 && p.desc_base_offset) da |= (uint64_t)((a_addr >> 7) & 7) << 49;
                 const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
-                umma_bf16_ss(tmem_base, da, db, idesc, accumulate);
+                if (CG == 2) umma_bf16_ss_pair(tmem_base, da, db, idesc, accumulate);
+                else umma_bf16_ss(tmem_base, da, db, idesc, accumulate);
                 accumulate = 1;
               }
-              umma_commit(b_empty(sb));  // frees the weight slot once these MMAs retire
+              // frees the weight slot (in both CTAs of a pair) once these MMAs retire
+              if (CG == 2) umma_commit_pair(b_empty(sb)); else umma_commit(b_empty(sb));
             }
             __syncwarp();
           }
-          if (lane == 0) umma_commit(a_empty(sa));
+          if (lane == 0) { if (CG == 2) umma_commit_pair(a_empty(sa)); else umma_commit(a_empty(sa)); }
           __syncwarp();
         }
       }
     }
-    if (lane == 0) umma_commit(tmem_full_bar);  // accumulator complete
+    if (lane == 0) { if (CG == 2) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar); }
     __syncwarp();
-  } else {
+  } else if (warp == 1) {
+    // peer CTA of a pair: its tensor core is driven by the leader's instructions
+  } else if (warp >= 2) {
     // ================= epilogue (warps 2..5) =================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;    // row of the 128-row tile == TMEM lane
@@ -317,7 +343,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
         red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
         const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
         const int qcol = col0 + (vidx & 7) * 4;
-        if ((lane & 1) == 0 && qcol < p.Cout)
+        if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
           p.gn_partial[(((size_t)m_tile * 4 + quad) * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = red[0];
       }
 
@@ -348,10 +374,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // pair: both CTAs' smem/TMEM/barriers stay alive until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BLOCK_N>(tmem_base);
+    if (CG == 2) tmem_dealloc_pair<BLOCK_N>(tmem_base); else tmem_dealloc<BLOCK_N>(tmem_base);
   }
 }
 
@@ -417,17 +443,36 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int CG>
 static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cudaStream_t st) {
-  using Cfg = ConvCfg<BLOCK_N, MODE>;
+  using Cfg = ConvCfg<BLOCK_N, MODE, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, MODE>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, MODE, CG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_igemm)");
     attr_set = true;
   }
-  conv_igemm_kernel<BLOCK_N, MODE><<<dim3(m_tiles, n_tiles), kConvThreads, Cfg::kSmemBytes, st>>>(kp);
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((m_tiles + 1) & ~1, n_tiles);  // pairs of M tiles; a padded tile is fully out of bounds
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, MODE, CG>, kp);
+    count_launch();
+    if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_igemm pair)");
+    return 0;
+  }
+  conv_igemm_kernel<BLOCK_N, MODE, CG><<<dim3(m_tiles, n_tiles), kConvThreads, Cfg::kSmemBytes, st>>>(kp);
   FM_LAUNCH_CHECK("conv_igemm_kernel");
   return 0;
 }
@@ -500,7 +545,14 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   }
   kp.num_k_blocks = nk;
   const int block_n = (p->Cout > 128) ? 256 : (p->Cout > 64 ? 128 : 64);
-  if (int e = encode_wgt_map(&kp.wgt, p->weight, ktot, p->Cout, block_n)) return e;
+  // CTA pairs (cta_group::2): enabled for the 128/256-wide tiles when there are at least two M tiles
+  const int m_tiles_total = kp.tiles_w * kp.tiles_h * tiles_n;
+  bool pair = (block_n >= 128) && (m_tiles_total >= 2);
+  {
+    const char* pe = getenv("FMDM_CONV_PAIR");  // 0 disables, 1 (default) enables
+    if (pe && atoi(pe) == 0) pair = false;
+  }
+  if (int e = encode_wgt_map(&kp.wgt, p->weight, ktot, p->Cout, pair ? block_n / 2 : block_n)) return e;
   if (int e = encode_act_map(&kp.out, p->out, p->Cout, Wo, Ho, p->B, kp.Wt, kp.Ht, kp.Nt, 1)) return e;
   kp.bias = p->bias;
   kp.addvec = p->addvec;
@@ -525,16 +577,22 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   const int m_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
   const int n_tiles = (p->Cout + block_n - 1) / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pair) {
+    if (row_mode) return block_n == 128 ? launch_conv<128, 1, 2>(kp, m_tiles, n_tiles, st)
+                                        : launch_conv<256, 1, 2>(kp, m_tiles, n_tiles, st);
+    return block_n == 128 ? launch_conv<128, 0, 2>(kp, m_tiles, n_tiles, st)
+                          : launch_conv<256, 0, 2>(kp, m_tiles, n_tiles, st);
+  }
   if (row_mode) {
     switch (block_n) {
-      case 64: return launch_conv<64, 1>(kp, m_tiles, n_tiles, st);
-      case 128: return launch_conv<128, 1>(kp, m_tiles, n_tiles, st);
-      default: return launch_conv<256, 1>(kp, m_tiles, n_tiles, st);
+      case 64: return launch_conv<64, 1, 1>(kp, m_tiles, n_tiles, st);
+      case 128: return launch_conv<128, 1, 1>(kp, m_tiles, n_tiles, st);
+      default: return launch_conv<256, 1, 1>(kp, m_tiles, n_tiles, st);
     }
   }
   switch (block_n) {
-    case 64: return launch_conv<64, 0>(kp, m_tiles, n_tiles, st);
-    case 128: return launch_conv<128, 0>(kp, m_tiles, n_tiles, st);
-    default: return launch_conv<256, 0>(kp, m_tiles, n_tiles, st);
+    case 64: return launch_conv<64, 0, 1>(kp, m_tiles, n_tiles, st);
+    case 128: return launch_conv<128, 0, 1>(kp, m_tiles, n_tiles, st);
+    default: return launch_conv<256, 0, 1>(kp, m_tiles, n_tiles, st);
   }
 }
