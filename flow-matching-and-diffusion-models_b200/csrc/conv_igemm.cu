@@ -48,6 +48,7 @@ struct alignas(64) ConvKernelParams {
   int log_wt, log_ht;               // Wt, Ht are powers of two
   int desc_base_offset;             // row mode: encode the swizzle phase of row-shifted A views in the descriptor
   int num_k_blocks;
+  int m_tiles, n_tiles;             // persistent kernel: real tile counts (M tiles padded to even for CTA pairs)
 };
 
 // MODE 0: one A tile per (tap, 64-channel block)  - any tile box, stride 1/2.
@@ -381,6 +382,368 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   }
 }
 
+
+// =================================================================================================================
+// Persistent variant.  One CTA (or CTA pair) per SM walks a static round-robin list of output tiles; the TMA/MMA
+// pipeline never drains between tiles and the accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the
+// epilogue of tile i (TMEM -> registers -> bias/temb/residual/GroupNorm statistics -> bf16 -> TMA store) overlaps
+// the main loop of tile i+1.  Measured on the one-tile-per-CTA kernel above, the per-tile prologue + pipeline fill +
+// epilogue + teardown cost 31 % (single CTA) / 58 % (CTA pair) of the run time of a K = 1152 conv; this removes it.
+// =================================================================================================================
+constexpr int kStageCols = 128;  // output columns staged (and TMA-stored) at a time
+
+template <int BLOCK_N, int MODE, int CG>
+struct PConvCfg {
+  static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
+  static constexpr int kASlot = (MODE == 1) ? kARowSlot : kABytes;
+  static constexpr int kATx = (MODE == 1) ? kARowTx : kABytes;
+  static constexpr int kHalfCols = (BLOCK_N < kStageCols) ? BLOCK_N : kStageCols;
+  static constexpr int kOutBytes = kTileM * kHalfCols * 2;
+  static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kOutBytes;
+  static constexpr int kAStages = (MODE == 1) ? ((kBudget >= 3 * kASlot + 8 * kBBytes) ? 3 : 2)
+                                              : ((kBudget / (kASlot + kBBytes)) > 8 ? 8 : (kBudget / (kASlot + kBBytes)));
+  static constexpr int kBStagesRaw = (MODE == 1) ? (kBudget - kAStages * kASlot) / kBBytes : kAStages;
+  static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
+  static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
+  static constexpr int kSmemBytes = 1024 + kPipeBytes + kOutBytes + 512;
+  static_assert(kAStages >= 2 && kBStages >= 3, "pipeline too shallow");
+  static_assert(kNumBars * 8 + 8 <= 512, "barrier area");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int BLOCK_N, int MODE, int CG>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = PConvCfg<BLOCK_N, MODE, CG>;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + Cfg::kAStages * Cfg::kASlot;
+  const uint32_t smem_out = smem_base + Cfg::kPipeBytes;          // dedicated output staging (1024 B aligned)
+  uint8_t* out_gen = smem_gen + Cfg::kPipeBytes;
+  const uint32_t bar_base = smem_out + Cfg::kOutBytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
+  auto t_full = [&](int b) { return bar_base + 8u * (2 * Cfg::kAStages + 2 * Cfg::kBStages + b); };
+  auto t_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::kAStages + 2 * Cfg::kBStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(out_gen + Cfg::kOutBytes + 8 * Cfg::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (<= 512)
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.src[s]);
+    tma_prefetch_desc(&p.wgt);
+    tma_prefetch_desc(&p.out);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 2 * Cfg::kAStages + 2 * Cfg::kBStages + 2; ++s) mbar_init(bar_base + 8u * s, 1);
+      // accumulator-drained barriers: one arrival per epilogue warp of every CTA writing into this MMA's TMEM
+      mbar_init(t_empty(0), 4 * CG);
+      mbar_init(t_empty(1), 4 * CG);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    if (CG == 2) tmem_alloc_pair<kTmemCols>(tmem_slot); else tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // ---- static tile schedule: work unit = (M tile [pair], N tile), N fastest so neighbours share the A rows in L2
+  const int units_m = p.m_tiles / CG;
+  const int total_units = units_m * p.n_tiles;
+  const int first_unit = (int)blockIdx.x / CG;
+  const int unit_stride = (int)gridDim.x / CG;
+  const int tiles_per_img_group = p.tiles_w * p.tiles_h;
+
+  auto tile_coords = [&](int unit, int& m_tile, int& w0, int& h0, int& n0, int& ncol0) {
+    const int um = unit / p.n_tiles;
+    ncol0 = (unit - um * p.n_tiles) * BLOCK_N;
+    m_tile = um * CG + (int)cta_rank;
+    const int tn = m_tile / tiles_per_img_group;
+    const int rem = m_tile - tn * tiles_per_img_group;
+    const int th = rem / p.tiles_w;
+    w0 = (rem - th * p.tiles_w) * p.Wt;
+    h0 = th * p.Ht;
+    n0 = tn * p.Nt;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (runs ahead across tiles) =================
+    if (lane == 0) {
+      int ia = 0, ib = 0;
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+        int m_tile, w0, h0, n0, ncol0;
+        tile_coords(unit, m_tile, w0, h0, n0, ncol0);
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          const int C = p.seg_c[s];
+          const int cblocks = (C + kBlockK - 1) / kBlockK;
+          const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
+          const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
+          for (int as = 0; as < asteps; ++as) {
+            int dh, dw;
+            if (MODE == 1) { dh = (taps == 9) ? as - 1 : 0; dw = -1; }
+            else { dh = (taps == 9) ? (as / 3 - 1) : 0; dw = (taps == 9) ? (as % 3 - 1) : 0; }
+            for (int cb = 0; cb < cblocks; ++cb, ++ia) {
+              const int sa = ia % Cfg::kAStages;
+              mbar_wait(a_empty(sa), ((ia / Cfg::kAStages) & 1) ^ 1u);
+              if (CG == 2) {
+                if (is_leader) mbar_expect_tx(a_full(sa), 2 * Cfg::kATx);
+                tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot, cb * kBlockK,
+                                 w0 * p.stride + dw, h0 * p.stride + dh, n0);
+              } else {
+                mbar_expect_tx(a_full(sa), Cfg::kATx);
+                tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot, cb * kBlockK, w0 * p.stride + dw,
+                            h0 * p.stride + dh, n0);
+              }
+              for (int bs = 0; bs < bsteps; ++bs, ++ib) {
+                const int tap = (MODE == 1) ? (taps == 9 ? as * 3 + bs : 0) : as;
+                const int sb = ib % Cfg::kBStages;
+                mbar_wait(b_empty(sb), ((ib / Cfg::kBStages) & 1) ^ 1u);
+                if (CG == 2) {
+                  if (is_leader) mbar_expect_tx(b_full(sb), 2 * Cfg::kBBytes);
+                  tma_load_2d_pair(&p.wgt, mapa_shared(b_full(sb), 0), smem_b0 + sb * Cfg::kBBytes,
+                                   p.seg_koff[s] + tap * C + cb * kBlockK, ncol0 + (int)cta_rank * (BLOCK_N / 2));
+                } else {
+                  mbar_expect_tx(b_full(sb), Cfg::kBBytes);
+                  tma_load_2d(&p.wgt, b_full(sb), smem_b0 + sb * Cfg::kBBytes,
+                              p.seg_koff[s] + tap * C + cb * kBlockK, ncol0);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && is_leader) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM * CG, BLOCK_N);
+    int ia = 0, ib = 0, it = 0;
+    for (int unit = first_unit; unit < total_units; unit += unit_stride, ++it) {
+      const int buf = it & 1;
+      mbar_wait(t_empty(buf), ((it >> 1) & 1) ^ 1u);  // epilogue(s) drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int taps = p.seg_taps[s];
+        const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
+        const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
+        const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
+        for (int as = 0; as < asteps; ++as) {
+          for (int cb = 0; cb < cblocks; ++cb, ++ia) {
+            const int sa = ia % Cfg::kAStages;
+            mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
+            for (int bs = 0; bs < bsteps; ++bs, ++ib) {
+              const int sb = ib % Cfg::kBStages;
+              mbar_wait(b_full(sb), (ib / Cfg::kBStages) & 1);
+              tc_fence_after();
+              if (lane == 0) {
+                const int a_row = (MODE == 1) ? (taps == 9 ? bs : 1) : 0;
+                const uint32_t a_addr = smem_a0 + sa * Cfg::kASlot + a_row * kARowBytes;
+                const uint32_t b_addr = smem_b0 + sb * Cfg::kBBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t da = make_sw128_kmajor_desc(a_addr + k * 32);
+                  const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
+                  if (CG == 2) umma_bf16_ss_pair(tmem_d, da, db, idesc, accumulate);
+                  else umma_bf16_ss(tmem_d, da, db, idesc, accumulate);
+                  accumulate = 1;
+                }
+                if (CG == 2) umma_commit_pair(b_empty(sb)); else umma_commit(b_empty(sb));
+              }
+              __syncwarp();
+            }
+            if (lane == 0) { if (CG == 2) umma_commit_pair(a_empty(sa)); else umma_commit(a_empty(sa)); }
+            __syncwarp();
+          }
+        }
+      }
+      if (lane == 0) { if (CG == 2) umma_commit_pair(t_full(buf)); else umma_commit(t_full(buf)); }
+      __syncwarp();
+    }
+  } else if (warp >= 2) {
+    // ================= epilogue (warps 2..5) =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool store_issuer = (warp == 2 && lane == 0);
+    const uint32_t t_empty_leader0 = (CG == 2) ? mapa_shared(t_empty(0), 0) : t_empty(0);
+    const uint32_t t_empty_leader1 = (CG == 2) ? mapa_shared(t_empty(1), 0) : t_empty(1);
+    constexpr int kHalves = BLOCK_N / Cfg::kHalfCols;
+    constexpr int kChunksPerRow = Cfg::kHalfCols / 8;
+    int it = 0;
+    for (int unit = first_unit; unit < total_units; unit += unit_stride, ++it) {
+      int m_tile, w0, h0, n0, ncol_tile;
+      tile_coords(unit, m_tile, w0, h0, n0, ncol_tile);
+      const int buf = it & 1;
+      const int rw = row & (p.Wt - 1);
+      const int rh = (row >> p.log_wt) & (p.Ht - 1);
+      const int rn = row >> (p.log_wt + p.log_ht);
+      const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
+      const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
+
+      mbar_wait(t_full(buf), (it >> 1) & 1);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int half = 0; half < kHalves; ++half) {
+        const int ncol0 = ncol_tile + half * Cfg::kHalfCols;
+        // the previous TMA store must have finished reading the staging tile before anyone overwrites it
+        if (store_issuer) tma_store_wait_read0();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+
+        if (p.residual != nullptr) {
+#pragma unroll 1
+          for (int i0 = 0; i0 < kChunksPerRow; i0 += 8) {
+            uint4 buf4[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int idx = (i0 + u) * 32 + lane;
+              const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+              const int rr = quad * 32 + rl;
+              const int pw = w0 + (rr & (p.Wt - 1));
+              const int ph = h0 + ((rr >> p.log_wt) & (p.Ht - 1));
+              const int pn = n0 + (rr >> (p.log_wt + p.log_ht));
+              const int col = ncol0 + ch * 8;
+              buf4[u] = make_uint4(0, 0, 0, 0);
+              if (pw < p.Wo && ph < p.Ho && pn < p.B && col < p.Cout)
+                buf4[u] = *reinterpret_cast<const uint4*>(p.residual +
+                                                          (((size_t)pn * p.Ho + ph) * p.Wo + pw) * p.Cout + col);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int idx = (i0 + u) * 32 + lane;
+              const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+              const int rr = quad * 32 + rl;
+              uint8_t* dst = out_gen + (ch >> 3) * (kTileM * 128) + rr * 128 + (((ch & 7) ^ (rr & 7)) * 16);
+              *reinterpret_cast<uint4*>(dst) = buf4[u];
+            }
+          }
+          __syncwarp();
+        }
+
+#pragma unroll 1
+        for (int c0 = 0; c0 < Cfg::kHalfCols; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                 (uint32_t)(buf * BLOCK_N + half * Cfg::kHalfCols + c0), r);
+          tmem_ld_wait();
+          const int col0 = ncol0 + c0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int slab = c0 >> 6;
+          const int chunk0 = (c0 & 63) >> 3;
+          uint8_t* rowp = out_gen + slab * (kTileM * 128) + row * 128;
+          if (col0 < p.Cout) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const int col = col0 + j8 * 8;
+              if (col < p.Cout) {
+                if (p.bias != nullptr) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                  v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
+                  v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
+                }
+                if (p.addvec != nullptr && valid) {
+                  const float* av = p.addvec + (size_t)on * p.addvec_stride + col;
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(av));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(av + 4));
+                  v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
+                  v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
+                }
+                if (p.residual != nullptr) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
+                  const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
+                  const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
+                  v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
+                  v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
+                }
+              }
+            }
+          }
+          if (p.gn_partial != nullptr) {
+            float red[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = valid ? v[4 * j + 0] : 0.f, a1 = valid ? v[4 * j + 1] : 0.f;
+              const float a2 = valid ? v[4 * j + 2] : 0.f, a3 = valid ? v[4 * j + 3] : 0.f;
+              red[j] = (a0 + a1) + (a2 + a3);
+              red[8 + j] = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
+            }
+#pragma unroll
+            for (int width = 8, mask = 16; width >= 1; width >>= 1, mask >>= 1) {
+              const bool upper = (lane & mask) != 0;
+#pragma unroll
+              for (int i = 0; i < width; ++i) {
+                const float keep = upper ? red[i + width] : red[i];
+                const float give = upper ? red[i] : red[i + width];
+                red[i] = keep + __shfl_xor_sync(0xffffffffu, give, mask);
+              }
+            }
+            red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
+            const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const int qcol = col0 + (vidx & 7) * 4;
+            if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
+              p.gn_partial[(((size_t)m_tile * 4 + quad) * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = red[0];
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (chunk0 + j) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+                make_uint4(pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+        if (half == kHalves - 1) {
+          // all TMEM reads of this accumulator buffer are done: hand it back to the MMA issuer (leader CTA)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t bar = buf ? t_empty_leader1 : t_empty_leader0;
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (store_issuer) {
+#pragma unroll
+          for (int slab = 0; slab < Cfg::kHalfCols / 64; ++slab) {
+            if (ncol0 + slab * 64 < p.Cout)
+              tma_store_4d(&p.out, smem_out + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (store_issuer) tma_store_wait_read0();
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (CG == 2) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -474,6 +837,38 @@ static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cud
   }
   conv_igemm_kernel<BLOCK_N, MODE, CG><<<dim3(m_tiles, n_tiles), kConvThreads, Cfg::kSmemBytes, st>>>(kp);
   FM_LAUNCH_CHECK("conv_igemm_kernel");
+  return 0;
+}
+
+template <int BLOCK_N, int MODE, int CG>
+static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
+  using Cfg = PConvCfg<BLOCK_N, MODE, CG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<BLOCK_N, MODE, CG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_igemm_persistent)");
+    attr_set = true;
+  }
+  const int units = (kp.m_tiles / CG) * kp.n_tiles;
+  int ctas = (sm_count() / CG) * CG;  // one CTA (pair) per SM (pair)
+  if (ctas > units * CG) ctas = units * CG;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<BLOCK_N, MODE, CG>, kp);
+  count_launch();
+  if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_igemm_persistent)");
   return 0;
 }
 
@@ -577,6 +972,24 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   const int m_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
   const int n_tiles = (p->Cout + block_n - 1) / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  kp.n_tiles = n_tiles;
+  kp.m_tiles = pair ? ((m_tiles + 1) & ~1) : m_tiles;
+  {
+    const char* pe = getenv("FMDM_CONV_PERSISTENT");  // 0 selects the one-tile-per-CTA kernel
+    const bool persistent = !(pe && atoi(pe) == 0);
+    if (persistent) {
+#define FM_PC(N, M, G) return launch_conv_persistent<N, M, G>(kp, st)
+      if (pair) {
+        if (row_mode) { if (block_n == 128) FM_PC(128, 1, 2); else FM_PC(256, 1, 2); }
+        else { if (block_n == 128) FM_PC(128, 0, 2); else FM_PC(256, 0, 2); }
+      } else if (row_mode) {
+        if (block_n == 64) FM_PC(64, 1, 1); else if (block_n == 128) FM_PC(128, 1, 1); else FM_PC(256, 1, 1);
+      } else {
+        if (block_n == 64) FM_PC(64, 0, 1); else if (block_n == 128) FM_PC(128, 0, 1); else FM_PC(256, 0, 1);
+      }
+#undef FM_PC
+    }
+  }
   if (pair) {
     if (row_mode) return block_n == 128 ? launch_conv<128, 1, 2>(kp, m_tiles, n_tiles, st)
                                         : launch_conv<256, 1, 2>(kp, m_tiles, n_tiles, st);
