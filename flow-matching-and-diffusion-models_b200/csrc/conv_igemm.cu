@@ -398,22 +398,28 @@ struct PConvCfg {
   static constexpr int kASlot = (MODE == 1) ? kARowSlot : kABytes;
   static constexpr int kATx = (MODE == 1) ? kARowTx : kABytes;
   static constexpr int kHalfCols = (BLOCK_N < kStageCols) ? BLOCK_N : kStageCols;
-  static constexpr int kOutBytes = kTileM * kHalfCols * 2;
-  static constexpr int kBudget = 227 * 1024 - 1024 - 512 - kOutBytes;
+  static constexpr int kOutBytes = kTileM * kHalfCols * 2;       // one staging buffer
+  static constexpr int kOutBufs = 2;                              // store of half i overlaps the math of half i+1
+  static constexpr int kTailBytes = 512 + BLOCK_N * 4;            // barriers + TMEM slot + per-tile bias vector
+  static constexpr int kBudget = 227 * 1024 - 1024 - kTailBytes - kOutBufs * kOutBytes;
   static constexpr int kAStages = (MODE == 1) ? ((kBudget >= 3 * kASlot + 8 * kBBytes) ? 3 : 2)
                                               : ((kBudget / (kASlot + kBBytes)) > 8 ? 8 : (kBudget / (kASlot + kBBytes)));
   static constexpr int kBStagesRaw = (MODE == 1) ? (kBudget - kAStages * kASlot) / kBBytes : kAStages;
   static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
   static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
   static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
-  static constexpr int kSmemBytes = 1024 + kPipeBytes + kOutBytes + 512;
+  static constexpr int kSmemBytes = 1024 + kPipeBytes + kOutBufs * kOutBytes + kTailBytes;
   static_assert(kAStages >= 2 && kBStages >= 3, "pipeline too shallow");
   static_assert(kNumBars * 8 + 8 <= 512, "barrier area");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
+constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quadrant, each owning half the columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kPConvThreads = 64 + kEpiThreads;     // + TMA producer warp + MMA warp
+
 template <int BLOCK_N, int MODE, int CG>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kPConvThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = PConvCfg<BLOCK_N, MODE, CG>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -425,7 +431,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t smem_b0 = smem_base + Cfg::kAStages * Cfg::kASlot;
   const uint32_t smem_out = smem_base + Cfg::kPipeBytes;          // dedicated output staging (1024 B aligned)
   uint8_t* out_gen = smem_gen + Cfg::kPipeBytes;
-  const uint32_t bar_base = smem_out + Cfg::kOutBytes;
+  const uint32_t bar_base = smem_out + Cfg::kOutBufs * Cfg::kOutBytes;
+  float* sbias = reinterpret_cast<float*>(out_gen + Cfg::kOutBufs * Cfg::kOutBytes + 512);  // [BLOCK_N]
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
@@ -434,7 +441,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   auto t_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::kAStages + 2 * Cfg::kBStages + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(out_gen + Cfg::kOutBytes + 8 * Cfg::kNumBars);
+      reinterpret_cast<volatile uint32_t*>(out_gen + Cfg::kOutBufs * Cfg::kOutBytes + 8 * Cfg::kNumBars);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -449,8 +456,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
     if (lane == 0) {
       for (int s = 0; s < 2 * Cfg::kAStages + 2 * Cfg::kBStages + 2; ++s) mbar_init(bar_base + 8u * s, 1);
       // accumulator-drained barriers: one arrival per epilogue warp of every CTA writing into this MMA's TMEM
-      mbar_init(t_empty(0), 4 * CG);
-      mbar_init(t_empty(1), 4 * CG);
+      mbar_init(t_empty(0), kEpiWarps * CG);
+      mbar_init(t_empty(1), kEpiWarps * CG);
       fence_barrier_init();
     }
     __syncwarp();
@@ -576,15 +583,19 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
       __syncwarp();
     }
   } else if (warp >= 2) {
-    // ================= epilogue (warps 2..5) =================
-    const int quad = warp & 3;
+    // ================= epilogue (warps 2..9) =================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int cgrp = (warp - 2) >> 2;          // which half of the staged columns this warp owns
     const int row = quad * 32 + lane;
+    const int etid = threadIdx.x - 64;         // 0..255
     const bool store_issuer = (warp == 2 && lane == 0);
     const uint32_t t_empty_leader0 = (CG == 2) ? mapa_shared(t_empty(0), 0) : t_empty(0);
     const uint32_t t_empty_leader1 = (CG == 2) ? mapa_shared(t_empty(1), 0) : t_empty(1);
     constexpr int kHalves = BLOCK_N / Cfg::kHalfCols;
-    constexpr int kChunksPerRow = Cfg::kHalfCols / 8;
-    int it = 0;
+    constexpr int kWarpCols = Cfg::kHalfCols / 2;          // columns per warp per half (64, or 32 for BLOCK_N = 64)
+    constexpr int kWarpChunks = kWarpCols / 8;             // 16-byte chunks per row per warp
+    const bool vec_per_tile = (p.Nt == 1);                 // all rows of a tile belong to one image
+    int it = 0, stage_use = 0;
     for (int unit = first_unit; unit < total_units; unit += unit_stride, ++it) {
       int m_tile, w0, h0, n0, ncol_tile;
       tile_coords(unit, m_tile, w0, h0, n0, ncol_tile);
@@ -595,24 +606,39 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
       const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
       const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
 
+      // per-tile bias (+ per-image time-embedding vector) -> shared memory; the previous tile's readers are past
+      // their last read (they all crossed the pre-store barrier of its last half)
+      if (etid < BLOCK_N) {
+        const int col = ncol_tile + etid;
+        float bv = 0.f;
+        if (col < p.Cout) {
+          if (p.bias != nullptr) bv = __ldg(p.bias + col);
+          if (p.addvec != nullptr && vec_per_tile && n0 < p.B) bv += __ldg(p.addvec + (size_t)n0 * p.addvec_stride + col);
+        }
+        sbias[etid] = bv;
+      }
+
       mbar_wait(t_full(buf), (it >> 1) & 1);
       tc_fence_after();
 
 #pragma unroll 1
-      for (int half = 0; half < kHalves; ++half) {
+      for (int half = 0; half < kHalves; ++half, ++stage_use) {
         const int ncol0 = ncol_tile + half * Cfg::kHalfCols;
-        // the previous TMA store must have finished reading the staging tile before anyone overwrites it
-        if (store_issuer) tma_store_wait_read0();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t* stg = out_gen + (stage_use & 1) * Cfg::kOutBytes;
+        const uint32_t stg_u32 = smem_out + (stage_use & 1) * Cfg::kOutBytes;
+        // the TMA store that last read THIS staging buffer (two halves ago) must be done reading it
+        if (store_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
 
         if (p.residual != nullptr) {
-#pragma unroll 1
-          for (int i0 = 0; i0 < kChunksPerRow; i0 += 8) {
+          // coalesced 16-byte reads of this warp's 32 rows x kWarpCols columns, staged into the swizzled tile
+#pragma unroll
+          for (int i0 = 0; i0 < kWarpChunks; i0 += 8) {
             uint4 buf4[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int idx = (i0 + u) * 32 + lane;
-              const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+              const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
               const int rr = quad * 32 + rl;
               const int pw = w0 + (rr & (p.Wt - 1));
               const int ph = h0 + ((rr >> p.log_wt) & (p.Ht - 1));
@@ -626,9 +652,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int idx = (i0 + u) * 32 + lane;
-              const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
+              const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
               const int rr = quad * 32 + rl;
-              uint8_t* dst = out_gen + (ch >> 3) * (kTileM * 128) + rr * 128 + (((ch & 7) ^ (rr & 7)) * 16);
+              uint8_t* dst = stg + (ch >> 3) * (kTileM * 128) + rr * 128 + (((ch & 7) ^ (rr & 7)) * 16);
               *reinterpret_cast<uint4*>(dst) = buf4[u];
             }
           }
@@ -636,7 +662,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
         }
 
 #pragma unroll 1
-        for (int c0 = 0; c0 < Cfg::kHalfCols; c0 += 32) {
+        for (int c0 = cgrp * kWarpCols; c0 < (cgrp + 1) * kWarpCols; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) +
                                  (uint32_t)(buf * BLOCK_N + half * Cfg::kHalfCols + c0), r);
@@ -647,33 +673,30 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           const int slab = c0 >> 6;
           const int chunk0 = (c0 & 63) >> 3;
-          uint8_t* rowp = out_gen + slab * (kTileM * 128) + row * 128;
-          if (col0 < p.Cout) {
+          uint8_t* rowp = stg + slab * (kTileM * 128) + row * 128;
+          const float* sb = sbias + half * Cfg::kHalfCols + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb + j4 * 4);
+            v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+          }
+          if (p.addvec != nullptr && !vec_per_tile && valid) {  // tiny images: several images per tile
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (col0 + j4 * 4 < p.Cout) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.addvec + (size_t)on * p.addvec_stride + col0 + j4 * 4));
+                v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+              }
+            }
+          }
+          if (p.residual != nullptr) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
-              const int col = col0 + j8 * 8;
-              if (col < p.Cout) {
-                if (p.bias != nullptr) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                  v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
-                  v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
-                }
-                if (p.addvec != nullptr && valid) {
-                  const float* av = p.addvec + (size_t)on * p.addvec_stride + col;
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(av));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(av + 4));
-                  v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
-                  v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
-                }
-                if (p.residual != nullptr) {
-                  const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
-                  const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
-                  const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
-                  v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
-                  v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
-                }
-              }
+              const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
+              const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
+              const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
+              v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
+              v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
             }
           }
           if (p.gn_partial != nullptr) {
@@ -721,12 +744,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           }
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (store_issuer) {
 #pragma unroll
           for (int slab = 0; slab < Cfg::kHalfCols / 64; ++slab) {
             if (ncol0 + slab * 64 < p.Cout)
-              tma_store_4d(&p.out, smem_out + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
+              tma_store_4d(&p.out, stg_u32 + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
           }
           tma_store_commit();
         }
@@ -856,7 +879,7 @@ static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas);
-  cfg.blockDim = dim3(kConvThreads);
+  cfg.blockDim = dim3(kPConvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
