@@ -57,6 +57,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (converged) warp.  Unlike `lane == 0`, the compiler knows a region guarded by elect.sync runs in
+// exactly one thread, so single-thread instructions (TMA, tcgen05.mma/commit) are emitted directly on the uniform
+// datapath instead of inside per-instruction ELECT/branch loops (measured: the TMA producer was issue-bound).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier / TMA / tcgen05 PTX wrappers (sm_100a) --------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -140,7 +140,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
   // (MODE 0: one per tap; MODE 1: one per kh), each feeding `bsteps` weight tiles (MODE 0: 1; MODE 1: the kw taps).
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int ia = 0, ib = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const int taps = p.seg_taps[s];
@@ -489,7 +489,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
 
   if (warp == 0) {
     // ================= TMA producer (runs ahead across tiles) =================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int ia = 0, ib = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
         int m_tile, w0, h0, n0, ncol0;
@@ -538,27 +538,27 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   } else if (warp == 1 && is_leader) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM * CG, BLOCK_N);
-    int ia = 0, ib = 0, it = 0;
-    for (int unit = first_unit; unit < total_units; unit += unit_stride, ++it) {
-      const int buf = it & 1;
-      mbar_wait(t_empty(buf), ((it >> 1) & 1) ^ 1u);  // epilogue(s) drained this accumulator buffer
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
-      uint32_t accumulate = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int taps = p.seg_taps[s];
-        const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
-        const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
-        const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
-        for (int as = 0; as < asteps; ++as) {
-          for (int cb = 0; cb < cblocks; ++cb, ++ia) {
-            const int sa = ia % Cfg::kAStages;
-            mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
-            for (int bs = 0; bs < bsteps; ++bs, ++ib) {
-              const int sb = ib % Cfg::kBStages;
-              mbar_wait(b_full(sb), (ib / Cfg::kBStages) & 1);
-              tc_fence_after();
-              if (lane == 0) {
+    if (elect_one_sync()) {
+      int ia = 0, ib = 0, it = 0;
+      for (int unit = first_unit; unit < total_units; unit += unit_stride, ++it) {
+        const int buf = it & 1;
+        mbar_wait(t_empty(buf), ((it >> 1) & 1) ^ 1u);  // epilogue(s) drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
+          const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
+          const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
+          for (int as = 0; as < asteps; ++as) {
+            for (int cb = 0; cb < cblocks; ++cb, ++ia) {
+              const int sa = ia % Cfg::kAStages;
+              mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
+              for (int bs = 0; bs < bsteps; ++bs, ++ib) {
+                const int sb = ib % Cfg::kBStages;
+                mbar_wait(b_full(sb), (ib / Cfg::kBStages) & 1);
+                tc_fence_after();
                 const int a_row = (MODE == 1) ? (taps == 9 ? bs : 1) : 0;
                 const uint32_t a_addr = smem_a0 + sa * Cfg::kASlot + a_row * kARowBytes;
                 const uint32_t b_addr = smem_b0 + sb * Cfg::kBBytes;
@@ -572,15 +572,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
                 }
                 if (CG == 2) umma_commit_pair(b_empty(sb)); else umma_commit(b_empty(sb));
               }
-              __syncwarp();
+              if (CG == 2) umma_commit_pair(a_empty(sa)); else umma_commit(a_empty(sa));
             }
-            if (lane == 0) { if (CG == 2) umma_commit_pair(a_empty(sa)); else umma_commit(a_empty(sa)); }
-            __syncwarp();
           }
         }
+        if (CG == 2) umma_commit_pair(t_full(buf)); else umma_commit(t_full(buf));
       }
-      if (lane == 0) { if (CG == 2) umma_commit_pair(t_full(buf)); else umma_commit(t_full(buf)); }
-      __syncwarp();
     }
   } else if (warp >= 2) {
     // ================= epilogue (warps 2..9) =================
@@ -588,7 +585,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
     const int cgrp = (warp - 2) >> 2;          // which half of the staged columns this warp owns
     const int row = quad * 32 + lane;
     const int etid = threadIdx.x - 64;         // 0..255
-    const bool store_issuer = (warp == 2 && lane == 0);
+    const bool store_issuer = (warp == 2) && elect_one_sync();
     const uint32_t t_empty_leader0 = (CG == 2) ? mapa_shared(t_empty(0), 0) : t_empty(0);
     const uint32_t t_empty_leader1 = (CG == 2) ? mapa_shared(t_empty(1), 0) : t_empty(1);
     constexpr int kHalves = BLOCK_N / Cfg::kHalfCols;

@@ -23,7 +23,9 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     rows = []
     tot_t = tot_f = 0.0
-    for cins, cout, k, s, H, cnt in SHAPES:
+    sel = os.environ.get("SHAPES")
+    shapes = SHAPES if not sel else [SHAPES[int(i)] for i in sel.split(",")]
+    for cins, cout, k, s, H, cnt in shapes:
         xs = [torch.randn(B, H, H, c, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2) for c in cins]
         ws = [torch.randn(cout, c, k, k, device=dev) * 0.05 for c in cins]
         pw = ops.pack_conv_weight([(w, 0, c) for w, c in zip(ws, cins)])
