@@ -392,17 +392,22 @@ conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
 // =================================================================================================================
 constexpr int kStageCols = 128;  // output columns staged (and TMA-stored) at a time
 
-template <int BLOCK_N, int MODE, int CG>
+// MT = 2 (only with BLOCK_N = 128): every weight tile is used for TWO M tiles per CTA (accumulators side by side in
+// TMEM, like one 256-column tile), halving the weight traffic per FLOP for the Cout = 128 layers, which are otherwise
+// bound by L2->SM bandwidth (13.5 KB per 64-deep k-block per CTA against a 256-cycle MMA budget).
+template <int BLOCK_N, int MODE, int CG, int MT>
 struct PConvCfg {
   static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
-  static constexpr int kASlot = (MODE == 1) ? kARowSlot : kABytes;
-  static constexpr int kATx = (MODE == 1) ? kARowTx : kABytes;
+  static constexpr int kASub = (MODE == 1) ? kARowSlot : kABytes;  // one M tile's A operand
+  static constexpr int kASlot = kASub * MT;
+  static constexpr int kATx = ((MODE == 1) ? kARowTx : kABytes) * MT;
+  static constexpr int kAccCols = BLOCK_N * MT;                    // accumulator columns per buffer
   static constexpr int kHalfCols = (BLOCK_N < kStageCols) ? BLOCK_N : kStageCols;
   static constexpr int kOutBytes = kTileM * kHalfCols * 2;       // one staging buffer
   static constexpr int kOutBufs = 2;                              // store of half i overlaps the math of half i+1
   static constexpr int kTailBytes = 512 + BLOCK_N * 4;            // barriers + TMEM slot + per-tile bias vector
   static constexpr int kBudget = 227 * 1024 - 1024 - kTailBytes - kOutBufs * kOutBytes;
-  static constexpr int kAStages = (MODE == 1) ? ((kBudget >= 3 * kASlot + 8 * kBBytes) ? 3 : 2)
+  static constexpr int kAStages = (MODE == 1) ? ((kBudget >= 3 * kASlot + 6 * kBBytes) ? 3 : 2)
                                               : ((kBudget / (kASlot + kBBytes)) > 8 ? 8 : (kBudget / (kASlot + kBBytes)));
   static constexpr int kBStagesRaw = (MODE == 1) ? (kBudget - kAStages * kASlot) / kBBytes : kAStages;
   static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
@@ -418,10 +423,11 @@ constexpr int kEpiWarps = 8;                        // two warps per TMEM lane q
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kPConvThreads = 64 + kEpiThreads;     // + TMA producer warp + MMA warp
 
-template <int BLOCK_N, int MODE, int CG>
+template <int BLOCK_N, int MODE, int CG, int MT>
 __global__ void __launch_bounds__(kPConvThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = PConvCfg<BLOCK_N, MODE, CG>;
+  using Cfg = PConvCfg<BLOCK_N, MODE, CG, MT>;
+  static_assert(MT == 1 || BLOCK_N == 128, "two M tiles per CTA only for 128-wide N tiles");
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = (cta_rank == 0);
   extern __shared__ uint8_t smem_raw[];
@@ -445,7 +451,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (<= 512)
+  constexpr int kTmemCols = 2 * Cfg::kAccCols;  // double-buffered accumulator (<= 512)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.src[s]);
@@ -469,16 +475,16 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   const uint32_t tmem_base = *tmem_slot_gen;
 
   // ---- static tile schedule: work unit = (M tile [pair], N tile), N fastest so neighbours share the A rows in L2
-  const int units_m = p.m_tiles / CG;
+  const int units_m = p.m_tiles / (CG * MT);
   const int total_units = units_m * p.n_tiles;
   const int first_unit = (int)blockIdx.x / CG;
   const int unit_stride = (int)gridDim.x / CG;
   const int tiles_per_img_group = p.tiles_w * p.tiles_h;
 
-  auto tile_coords = [&](int unit, int& m_tile, int& w0, int& h0, int& n0, int& ncol0) {
+  auto tile_coords = [&](int unit, int sub, int& m_tile, int& w0, int& h0, int& n0, int& ncol0) {
     const int um = unit / p.n_tiles;
     ncol0 = (unit - um * p.n_tiles) * BLOCK_N;
-    m_tile = um * CG + (int)cta_rank;
+    m_tile = (um * CG + (int)cta_rank) * MT + sub;
     const int tn = m_tile / tiles_per_img_group;
     const int rem = m_tile - tn * tiles_per_img_group;
     const int th = rem / p.tiles_w;
@@ -492,8 +498,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
     if (elect_one_sync()) {
       int ia = 0, ib = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
-        int m_tile, w0, h0, n0, ncol0;
-        tile_coords(unit, m_tile, w0, h0, n0, ncol0);
+        int m_tile, w0, h0, n0, ncol0, w1 = 0, h1 = 0, n1 = 0;
+        tile_coords(unit, 0, m_tile, w0, h0, n0, ncol0);
+        if (MT == 2) tile_coords(unit, 1, m_tile, w1, h1, n1, ncol0);
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
           const int C = p.seg_c[s];
@@ -511,10 +518,16 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
                 if (is_leader) mbar_expect_tx(a_full(sa), 2 * Cfg::kATx);
                 tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot, cb * kBlockK,
                                  w0 * p.stride + dw, h0 * p.stride + dh, n0);
+                if (MT == 2)
+                  tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot + Cfg::kASub,
+                                   cb * kBlockK, w1 * p.stride + dw, h1 * p.stride + dh, n1);
               } else {
                 mbar_expect_tx(a_full(sa), Cfg::kATx);
                 tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot, cb * kBlockK, w0 * p.stride + dw,
                             h0 * p.stride + dh, n0);
+                if (MT == 2)
+                  tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot + Cfg::kASub, cb * kBlockK,
+                              w1 * p.stride + dw, h1 * p.stride + dh, n1);
               }
               for (int bs = 0; bs < bsteps; ++bs, ++ib) {
                 const int tap = (MODE == 1) ? (taps == 9 ? as * 3 + bs : 0) : as;
@@ -544,7 +557,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
         const int buf = it & 1;
         mbar_wait(t_empty(buf), ((it >> 1) & 1) ^ 1u);  // epilogue(s) drained this accumulator buffer
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * Cfg::kAccCols);
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
@@ -563,13 +576,17 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
                 const uint32_t a_addr = smem_a0 + sa * Cfg::kASlot + a_row * kARowBytes;
                 const uint32_t b_addr = smem_b0 + sb * Cfg::kBBytes;
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  const uint64_t da = make_sw128_kmajor_desc(a_addr + k * 32);
-                  const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
-                  if (CG == 2) umma_bf16_ss_pair(tmem_d, da, db, idesc, accumulate);
-                  else umma_bf16_ss(tmem_d, da, db, idesc, accumulate);
-                  accumulate = 1;
+                for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t da = make_sw128_kmajor_desc(a_addr + sub * Cfg::kASub + k * 32);
+                    const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
+                    const uint32_t acc = accumulate | (uint32_t)(k > 0);  // first k-step of a unit overwrites
+                    if (CG == 2) umma_bf16_ss_pair(tmem_d + sub * BLOCK_N, da, db, idesc, acc);
+                    else umma_bf16_ss(tmem_d + sub * BLOCK_N, da, db, idesc, acc);
+                  }
                 }
+                accumulate = 1;
                 if (CG == 2) umma_commit_pair(b_empty(sb)); else umma_commit(b_empty(sb));
               }
               if (CG == 2) umma_commit_pair(a_empty(sa)); else umma_commit(a_empty(sa));
@@ -594,9 +611,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
     const bool vec_per_tile = (p.Nt == 1);                 // all rows of a tile belong to one image
     int it = 0, stage_use = 0;
     for (int unit = first_unit; unit < total_units; unit += unit_stride, ++it) {
+     const int buf = it & 1;
+#pragma unroll 1
+     for (int sub = 0; sub < MT; ++sub) {
       int m_tile, w0, h0, n0, ncol_tile;
-      tile_coords(unit, m_tile, w0, h0, n0, ncol_tile);
-      const int buf = it & 1;
+      tile_coords(unit, sub, m_tile, w0, h0, n0, ncol_tile);
       const int rw = row & (p.Wt - 1);
       const int rh = (row >> p.log_wt) & (p.Ht - 1);
       const int rn = row >> (p.log_wt + p.log_ht);
@@ -662,7 +681,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
         for (int c0 = cgrp * kWarpCols; c0 < (cgrp + 1) * kWarpCols; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                 (uint32_t)(buf * BLOCK_N + half * Cfg::kHalfCols + c0), r);
+                                 (uint32_t)(buf * Cfg::kAccCols + sub * BLOCK_N + half * Cfg::kHalfCols + c0), r);
           tmem_ld_wait();
           const int col0 = ncol0 + c0;
           float v[32];
@@ -731,7 +750,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
                 make_uint4(pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
         }
-        if (half == kHalves - 1) {
+        if (half == kHalves - 1 && sub == MT - 1) {
           // all TMEM reads of this accumulator buffer are done: hand it back to the MMA issuer (leader CTA)
           tc_fence_before();
           __syncwarp();
@@ -751,6 +770,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           tma_store_commit();
         }
       }
+     }
     }
     if (store_issuer) tma_store_wait_read0();
   }
@@ -860,17 +880,17 @@ static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cud
   return 0;
 }
 
-template <int BLOCK_N, int MODE, int CG>
+template <int BLOCK_N, int MODE, int CG, int MT>
 static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
-  using Cfg = PConvCfg<BLOCK_N, MODE, CG>;
+  using Cfg = PConvCfg<BLOCK_N, MODE, CG, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<BLOCK_N, MODE, CG>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<BLOCK_N, MODE, CG, MT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_igemm_persistent)");
     attr_set = true;
   }
-  const int units = (kp.m_tiles / CG) * kp.n_tiles;
+  const int units = (kp.m_tiles / (CG * MT)) * kp.n_tiles;
   int ctas = (sm_count() / CG) * CG;  // one CTA (pair) per SM (pair)
   if (ctas > units * CG) ctas = units * CG;
   cudaLaunchConfig_t cfg;
@@ -886,7 +906,7 @@ static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<BLOCK_N, MODE, CG>, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<BLOCK_N, MODE, CG, MT>, kp);
   count_launch();
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_igemm_persistent)");
   return 0;
@@ -993,13 +1013,24 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   const int n_tiles = (p->Cout + block_n - 1) / block_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   kp.n_tiles = n_tiles;
-  kp.m_tiles = pair ? ((m_tiles + 1) & ~1) : m_tiles;
+  // two M tiles per CTA (MT = 2) for 128-wide N tiles when every SM pair still gets several work units
+  int mt = (pair && block_n == 128 && m_tiles >= 8 * sm_count()) ? 2 : 1;
+  {
+    const char* me = getenv("FMDM_CONV_MT");  // 1 forces one M tile per CTA, 2 forces two wherever the variant exists
+    if (me && atoi(me) == 1) mt = 1;
+    if (me && atoi(me) == 2 && pair && block_n == 128) mt = 2;
+  }
+  const int m_round = (pair ? 2 : 1) * mt;
+  kp.m_tiles = (m_tiles + m_round - 1) / m_round * m_round;
   {
     const char* pe = getenv("FMDM_CONV_PERSISTENT");  // 0 selects the one-tile-per-CTA kernel
     const bool persistent = !(pe && atoi(pe) == 0);
     if (persistent) {
-#define FM_PC(N, M, G) return launch_conv_persistent<N, M, G>(kp, st)
-      if (pair) {
+#define FM_PC(N, M, G) return launch_conv_persistent<N, M, G, 1>(kp, st)
+      if (pair && mt == 2) {
+        if (row_mode) return launch_conv_persistent<128, 1, 2, 2>(kp, st);
+        return launch_conv_persistent<128, 0, 2, 2>(kp, st);
+      } else if (pair) {
         if (row_mode) { if (block_n == 128) FM_PC(128, 1, 2); else FM_PC(256, 1, 2); }
         else { if (block_n == 128) FM_PC(128, 0, 2); else FM_PC(256, 0, 2); }
       } else if (row_mode) {

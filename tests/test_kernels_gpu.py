@@ -90,6 +90,22 @@ def test_conv2d_igemm(case):
     assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 0.05
 
 
+@pytest.mark.parametrize("case", [
+    (2, 5, 256, [128], 128, [3], 1, True, True, True),          # row mode, ragged unit count (10 tiles -> 3 units)
+    (3, 28, 28, [64], 128, [3], 1, True, True, True),           # box mode, tiles straddle nothing, odd tile count
+    (2, 4, 130, [128, 64, 64], 128, [3, 1, 1], 1, True, False, False),
+    (3, 33, 35, [64], 96, [3], 2, True, False, False),
+    (2, 512, 512, [128], 128, [3], 1, True, True, True),        # the LDCT level-0 shape (picked without the override)
+], ids=["row", "box", "row_3seg", "box_s2", "ldct_level0"])
+def test_conv2d_igemm_two_m_tiles_per_cta(case, monkeypatch):
+    """The MT = 2 variant (two M tiles per CTA share every weight tile) against the same fp32 reference."""
+    monkeypatch.setenv("FMDM_CONV_MT", "2")
+    out, ref = _conv_case(*case)
+    err = _rel_l2(out, ref)
+    assert err < 6e-3, f"rel L2 {err}"
+    assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 0.05
+
+
 def test_group_norm_silu():
     g = torch.Generator().manual_seed(1)
     for (B, C, H, W, groups) in [(2, 128, 32, 32, 32), (3, 64, 7, 7, 32), (2, 512, 16, 16, 32), (1, 256, 64, 64, 32)]:
@@ -213,6 +229,20 @@ def test_conv_fused_groupnorm_statistics():
         plain = ops.group_norm([y.clone(memory_format=torch.preserve_format)], 32, 1e-5, gamma, beta, silu=True).float()
         ref = F.silu(F.group_norm(y.float(), 32, gamma, beta, 1e-5))
         assert _rel_l2(fused, ref) < 5e-3 and _rel_l2(fused, plain) < 2e-3
+    # the two-M-tiles-per-CTA variant writes the same partial-sum layout (B=2, 256x256 -> 1024 tiles; forced)
+    import os
+    os.environ["FMDM_CONV_MT"] = "2"
+    try:
+        x = _bf16r(torch.randn(2, 64, 64, 256, generator=g)).to(DEV)
+        w = _bf16r(torch.randn(128, 64, 3, 3, generator=g) / 24).to(DEV)
+        y = ops.conv2d([_nhwc(x)], ops.pack_conv_weight([(w, 0, 64)]), want_stats=True)
+        gamma = torch.randn(128, generator=g).to(DEV)
+        beta = torch.randn(128, generator=g).to(DEV)
+        fused = ops.group_norm([y], 32, 1e-5, gamma, beta, silu=True).float()
+        ref = F.silu(F.group_norm(y.float(), 32, gamma, beta, 1e-5))
+        assert _rel_l2(fused, ref) < 5e-3
+    finally:
+        del os.environ["FMDM_CONV_MT"]
     # virtual concat of two producers with a group size that straddles neither source evenly (384 ch -> 12/group)
     xa = _bf16r(torch.randn(2, 64, 16, 16, generator=g)).to(DEV)
     wa = _bf16r(torch.randn(256, 64, 3, 3, generator=g) / 24).to(DEV)
