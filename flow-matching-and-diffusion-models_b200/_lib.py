@@ -22,6 +22,10 @@ class ConvSeg(C.Structure):
         ("C", C.c_int32),
         ("ksize", C.c_int32),
         ("upsample", C.c_int32),
+        ("norm_act", C.c_int32),
+        ("norm_a", C.c_void_p),
+        ("norm_b", C.c_void_p),
+        ("norm_stride", C.c_int32),
         ("_pad", C.c_int32),
     ]
 
@@ -57,11 +61,17 @@ SIGNATURES = {
     "fm_last_error": (C.c_char_p, []),
     "fm_launch_count": (C.c_longlong, []),
     "fm_conv2d_igemm_bf16": (C.c_int, [C.POINTER(ConvParams), _vp]),
+    "fm_conv_operand_norm_supported": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "fm_groupnorm_affine_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "fm_groupnorm_finalize_partials_affine": (
+        C.c_int,
+        [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    ),
     "fm_conv_stats_layout": (C.c_int, [_i32, _i32, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fm_groupnorm_finalize_partials": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i64, _i32, _f32, _vp, _vp]),
     "fm_weight_prepack_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_conv_stem_f32_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "fm_conv_head_bf16_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "fm_conv_head_bf16_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "fm_groupnorm_workspace_elems": (C.c_int64, [_i32, _i64, _i32, _i32]),
     "fm_groupnorm_stats_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp]),
     "fm_groupnorm_apply_bf16": (

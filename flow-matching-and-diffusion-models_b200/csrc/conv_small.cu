@@ -106,12 +106,14 @@ __global__ void __launch_bounds__(kHeadThreads) conv_head_kernel(const uint4* __
                                                                 const float* __restrict__ w_oihw,
                                                                 const float* __restrict__ bias,
                                                                 float* __restrict__ out, int B, int H, int W,
-                                                                int Cin) {
+                                                                int Cin, const float* __restrict__ norm_ab,
+                                                                int norm_act) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int c8n = Cin >> 3;
   const int pitch = Cin * 2 + 16;                                   // bytes per staged pixel
   float* sw = reinterpret_cast<float*>(smem);                       // [9][Cin][COUT]
-  uint8_t* st = smem + ((9 * Cin * COUT * 4 + 15) & ~15);           // [(TH+2)*(TW+2)][pitch]
+  float* sab = reinterpret_cast<float*>(smem + ((9 * Cin * COUT * 4 + 15) & ~15));  // [2][Cin] a, b (halved for SiLU)
+  uint8_t* st = reinterpret_cast<uint8_t*>(sab + 2 * Cin);          // [(TH+2)*(TW+2)][pitch]
   for (int i = threadIdx.x; i < 9 * Cin * COUT; i += kHeadThreads) {
     const int co = i % COUT;
     const int ci = (i / COUT) % Cin;
@@ -120,14 +122,33 @@ __global__ void __launch_bounds__(kHeadThreads) conv_head_kernel(const uint4* __
   }
   const int w0 = blockIdx.x * kHeadTW, h0 = blockIdx.y * kHeadTH, n = blockIdx.z;
   constexpr int HP = kHeadTH + 2, WP = kHeadTW + 2;
+  if (norm_ab != nullptr) {
+    const float k = norm_act ? 0.5f : 1.0f;
+    for (int i = threadIdx.x; i < 2 * Cin; i += kHeadThreads) sab[i] = k * norm_ab[(size_t)n * 2 * Cin + i];
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < HP * WP * c8n; i += kHeadThreads) {
     const int c = i % c8n;
     const int p = i / c8n;
     const int pw = p % WP, ph = p / WP;
     const int ih = h0 + ph - 1, iw = w0 + pw - 1;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+    if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
       v = __ldg(x + (((size_t)n * H + ih) * W + iw) * c8n + c);
+      if (norm_ab != nullptr) {  // conv_norm_out + SiLU folded into the load; padding stays zero
+        const float4 a0 = *reinterpret_cast<const float4*>(sab + c * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(sab + c * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sab + Cin + c * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(sab + Cin + c * 8 + 4);
+        if (norm_act) {
+          v.x = xf_word<true>(v.x, a0.x, b0.x, a0.y, b0.y); v.y = xf_word<true>(v.y, a0.z, b0.z, a0.w, b0.w);
+          v.z = xf_word<true>(v.z, a1.x, b1.x, a1.y, b1.y); v.w = xf_word<true>(v.w, a1.z, b1.z, a1.w, b1.w);
+        } else {
+          v.x = xf_word<false>(v.x, a0.x, b0.x, a0.y, b0.y); v.y = xf_word<false>(v.y, a0.z, b0.z, a0.w, b0.w);
+          v.z = xf_word<false>(v.z, a1.x, b1.x, a1.y, b1.y); v.w = xf_word<false>(v.w, a1.z, b1.z, a1.w, b1.w);
+        }
+      }
+    }
     *reinterpret_cast<uint4*>(st + p * pitch + c * 16) = v;
   }
   __syncthreads();
@@ -201,14 +222,17 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
 }
 
 extern "C" int fm_conv_head_bf16_f32(const void* x, const float* weight_oihw, const float* bias, float* out, int32_t B,
-                                     int32_t H, int32_t W, int32_t Cin, int32_t Cout, fm_stream_t stream) {
+                                     int32_t H, int32_t W, int32_t Cin, int32_t Cout, const float* norm_ab,
+                                     int32_t norm_act, fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x && weight_oihw && out && B > 0 && H > 0 && W > 0, "conv_head: bad argument");
   FM_REQUIRE(Cin > 0 && Cin % 8 == 0, "conv_head: Cin=%d must be a multiple of 8", Cin);
   FM_REQUIRE(Cout >= 1 && Cout <= 4, "conv_head: Cout=%d must be in 1..4", Cout);
   FM_REQUIRE(B <= 65535, "conv_head: batch too large for the grid");
   const size_t wbytes = ((size_t)9 * Cin * Cout * sizeof(float) + 15) & ~(size_t)15;
-  const size_t smem = wbytes + (size_t)(kHeadTH + 2) * (kHeadTW + 2) * (Cin * 2 + 16);
+  const size_t smem =
+      wbytes + (size_t)2 * Cin * sizeof(float) + (size_t)(kHeadTH + 2) * (kHeadTW + 2) * (Cin * 2 + 16);
+  FM_REQUIRE(norm_ab == nullptr || ((uintptr_t)norm_ab & 15) == 0, "conv_head: norm_ab must be 16B aligned");
   FM_REQUIRE(smem <= 200 * 1024, "conv_head: Cin=%d does not fit shared memory", Cin);
   dim3 grid((W + kHeadTW - 1) / kHeadTW, (H + kHeadTH - 1) / kHeadTH, B);
   cudaStream_t st = (cudaStream_t)stream;
@@ -220,7 +244,8 @@ extern "C" int fm_conv_head_bf16_f32(const void* x, const float* weight_oihw, co
                                            (int)smem);                                                               \
       if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_head)");                                 \
     }                                                                                                                \
-    conv_head_kernel<N><<<grid, kHeadThreads, smem, st>>>(xp, weight_oihw, bias, out, B, H, W, Cin);                 \
+    conv_head_kernel<N><<<grid, kHeadThreads, smem, st>>>(xp, weight_oihw, bias, out, B, H, W, Cin, norm_ab,        \
+                                                          norm_act);                                               \
     break;                                                                                                           \
   }
   switch (Cout) {

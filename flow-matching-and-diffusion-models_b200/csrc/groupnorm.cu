@@ -90,8 +90,13 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
 __global__ void __launch_bounds__(128) gn_finalize_partials_kernel(const float* __restrict__ p0, int rows0, int nq0,
                                                                   const float* __restrict__ p1, int rows1, int nq1,
                                                                   int groups, double inv_cnt, float eps,
-                                                                  float* __restrict__ stats) {
+                                                                  float* __restrict__ stats,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta,
+                                                                  const float* __restrict__ scale_shift,
+                                                                  int64_t ss_stride, float* __restrict__ ab) {
   __shared__ double ss[128], sq[128];
+  __shared__ float s_mean, s_rstd;
   const int g = blockIdx.x, n = blockIdx.y;
   const int qpg = (nq0 + nq1) / groups;  // quads per group
   const int q_begin = g * qpg;
@@ -119,8 +124,53 @@ __global__ void __launch_bounds__(128) gn_finalize_partials_kernel(const float* 
     const double mean = ss[0] * inv_cnt;
     double var = sq[0] * inv_cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    stats[((size_t)n * groups + g) * 2 + 0] = (float)mean;
-    stats[((size_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (stats != nullptr) {
+      stats[((size_t)n * groups + g) * 2 + 0] = (float)mean;
+      stats[((size_t)n * groups + g) * 2 + 1] = rstd;
+    }
+    s_mean = (float)mean;
+    s_rstd = rstd;
+  }
+  if (ab == nullptr) return;
+  __syncthreads();
+  // the group's channels in the affine form consumed by the conv operand transform (same arithmetic as gn_apply)
+  const int C = (nq0 + nq1) * 4, cg = qpg * 4;
+  for (int c = g * cg + threadIdx.x; c < (g + 1) * cg; c += 128) {
+    float a = s_rstd * gamma[c];
+    float b = beta[c] - s_mean * a;
+    if (scale_shift != nullptr) {
+      const float sc = 1.0f + scale_shift[(size_t)n * ss_stride + c];
+      const float sh = scale_shift[(size_t)n * ss_stride + C + c];
+      a *= sc;
+      b = b * sc + sh;
+    }
+    ab[((size_t)n * 2 + 0) * C + c] = a;
+    ab[((size_t)n * 2 + 1) * C + c] = b;
+  }
+}
+
+// ab[n][0][c], ab[n][1][c] from finished (mean, rstd) statistics
+__global__ void __launch_bounds__(256) gn_affine_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta,
+                                                       const float* __restrict__ scale_shift, int64_t ss_stride,
+                                                       int C, int groups, float* __restrict__ ab) {
+  const int n = blockIdx.x;
+  const int cg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cg;
+    const float mean = stats[((size_t)n * groups + g) * 2 + 0];
+    const float rstd = stats[((size_t)n * groups + g) * 2 + 1];
+    float a = rstd * gamma[c];
+    float b = beta[c] - mean * a;
+    if (scale_shift != nullptr) {
+      const float sc = 1.0f + scale_shift[(size_t)n * ss_stride + c];
+      const float sh = scale_shift[(size_t)n * ss_stride + C + c];
+      a *= sc;
+      b = b * sc + sh;
+    }
+    ab[((size_t)n * 2 + 0) * C + c] = a;
+    ab[((size_t)n * 2 + 1) * C + c] = b;
   }
 }
 
@@ -263,9 +313,41 @@ extern "C" int fm_groupnorm_finalize_partials(const float* p0, int32_t rows0, in
              "gn_finalize_partials: channels per group (%d/%d) must be a multiple of 4", C, groups);
   FM_REQUIRE(B > 0 && B <= 65535 && HW > 0 && stats != nullptr, "gn_finalize_partials: bad argument");
   const double inv_cnt = 1.0 / ((double)HW * (double)(C / groups));
-  gn_finalize_partials_kernel<<<dim3(groups, B), 128, 0, (cudaStream_t)stream>>>(p0, rows0, C0 / 4, p1, rows1, C1 / 4,
-                                                                                 groups, inv_cnt, eps, stats);
+  gn_finalize_partials_kernel<<<dim3(groups, B), 128, 0, (cudaStream_t)stream>>>(
+      p0, rows0, C0 / 4, p1, rows1, C1 / 4, groups, inv_cnt, eps, stats, nullptr, nullptr, nullptr, 0, nullptr);
   FM_LAUNCH_CHECK("gn_finalize_partials_kernel");
+  return 0;
+}
+
+extern "C" int fm_groupnorm_finalize_partials_affine(const float* p0, int32_t rows0, int32_t C0, const float* p1,
+                                                     int32_t rows1, int32_t C1, int32_t B, int64_t HW, int32_t groups,
+                                                     float eps, const float* gamma, const float* beta,
+                                                     const float* scale_shift, int64_t ss_stride, float* stats,
+                                                     float* ab, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(p0 != nullptr && rows0 > 0 && C0 > 0 && C0 % 4 == 0, "gn_finalize_partials_affine: bad source 0");
+  FM_REQUIRE((p1 == nullptr) == (C1 == 0) && C1 % 4 == 0 && (p1 == nullptr || rows1 > 0),
+             "gn_finalize_partials_affine: bad source 1");
+  const int C = C0 + C1;
+  FM_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 4 == 0,
+             "gn_finalize_partials_affine: channels per group (%d/%d) must be a multiple of 4", C, groups);
+  FM_REQUIRE(B > 0 && B <= 65535 && HW > 0 && gamma && beta && ab, "gn_finalize_partials_affine: bad argument");
+  const double inv_cnt = 1.0 / ((double)HW * (double)(C / groups));
+  gn_finalize_partials_kernel<<<dim3(groups, B), 128, 0, (cudaStream_t)stream>>>(
+      p0, rows0, C0 / 4, p1, rows1, C1 / 4, groups, inv_cnt, eps, stats, gamma, beta, scale_shift, ss_stride, ab);
+  FM_LAUNCH_CHECK("gn_finalize_partials_kernel");
+  return 0;
+}
+
+extern "C" int fm_groupnorm_affine_f32(const float* stats, const float* gamma, const float* beta,
+                                       const float* scale_shift, int64_t ss_stride, int32_t B, int32_t C,
+                                       int32_t groups, float* ab, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(stats && gamma && beta && ab, "groupnorm_affine: null pointer");
+  FM_REQUIRE(B > 0 && C > 0 && groups > 0 && C % groups == 0, "groupnorm_affine: bad shape B=%d C=%d groups=%d", B, C,
+             groups);
+  gn_affine_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(stats, gamma, beta, scale_shift, ss_stride, C, groups, ab);
+  FM_LAUNCH_CHECK("gn_affine_kernel");
   return 0;
 }
 

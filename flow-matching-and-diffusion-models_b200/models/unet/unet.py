@@ -16,7 +16,7 @@ from ...nn.blocks.attention import ContextBlock, SpatialCrossAttention, SpatialS
 from ...nn.blocks.residual import ResBlockND, zero_module
 from ...nn.blocks.timestep import TimestepBlock
 from ...nn.ops.convolution import ConvND
-from ...nn.ops.normalization import fused_group_norm, make_group_norm
+from ...nn.ops.normalization import fused_group_norm, fused_group_norm_table, make_group_norm
 from ...nn.ops.upsampling import DownsampleND, UpsampleND
 from .base import BaseUNetND
 from .utils import build_timestep_features, time_mlp
@@ -150,8 +150,12 @@ class EfficientUNetND(BaseUNetND):
         h = self.middle_block(h, emb, context_ca)
         for block in self.output_blocks:
             h = block((h, hs.pop()), emb, context_ca)
-        h = fused_group_norm(self.out[0], [h], silu=True)
         head = self.out[2].conv
+        if head.out_channels <= 4:
+            tab = fused_group_norm_table(self.out[0], [h], silu=True)
+            if tab is not None:
+                return ops.conv_head(h, f32(head.weight), f32(head.bias), norm=tab)
+        h = fused_group_norm(self.out[0], [h], silu=True)
         if head.out_channels <= 4:
             return ops.conv_head(h, f32(head.weight), f32(head.bias))
         return self.out[2](h).float().contiguous()

@@ -15,7 +15,7 @@ from ... import ops
 from ..._runtime import f32, out_of_scope
 from ...nn.blocks import DownBlock2DCompat, UNetMidBlock2DCompat, UpBlock2DCompat
 from ...nn.ops.convolution import ConvND
-from ...nn.ops.normalization import fused_group_norm, make_group_norm
+from ...nn.ops.normalization import fused_group_norm, fused_group_norm_table, make_group_norm
 from .base import BaseUNetND
 from .utils import TimestepEmbedding, build_timestep_features
 
@@ -143,6 +143,11 @@ class UNetDiffusersND(BaseUNetND):
             n = len(block.resnets)
             res, skips = skips[-n:], skips[:-n]
             sample = block(sample, tuple(res), emb, context=context_ca)
+        if self.conv_out.out_channels <= 4:
+            # conv_norm_out + SiLU ride in the head kernel's load path (no normalised tensor in HBM)
+            tab = fused_group_norm_table(self.conv_norm_out, [sample], silu=True)
+            if tab is not None:
+                return ops.conv_head(sample, f32(self.conv_out.weight), f32(self.conv_out.bias), norm=tab)
         sample = fused_group_norm(self.conv_norm_out, [sample], silu=True)
         return self._head(sample)
 

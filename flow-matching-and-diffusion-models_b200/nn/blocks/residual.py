@@ -19,7 +19,7 @@ import torch.nn as nn
 from ... import ops
 from ..._runtime import ParamCache, f32, out_of_scope
 from ..ops.convolution import ConvND
-from ..ops.normalization import RMSNormND, fused_group_norm, make_group_norm
+from ..ops.normalization import RMSNormND, fused_group_norm, fused_group_norm_table, make_group_norm
 from .common import zero_module
 from .timestep import TimestepBlock
 
@@ -159,7 +159,15 @@ class ResBlockND(TimestepBlock):
         if len(srcs) > 2:
             srcs = [ops.to_nhwc_bf16(torch.cat(srcs, 1))]
 
-        h = fused_group_norm(self.norm1, srcs, silu=True)
+        # GroupNorm apply + SiLU fold into the consumer conv's operand path wherever the conv runs in row mode
+        # (image rows of >= 65 pixels): the normalised tensor is never written.  Elsewhere: the standalone K2 kernel.
+        _, _, hh, ww = srcs[0].shape
+        split = [s.shape[1] for s in srcs]
+        tab1 = None
+        if ops.conv_operand_norm_ok(hh, ww, 1, [3] * len(srcs), split):
+            tab1 = fused_group_norm_table(self.norm1, srcs, silu=True)
+        if tab1 is None:
+            h = fused_group_norm(self.norm1, srcs, silu=True)
 
         addvec, scale_shift, bias1 = None, None, f32(self.conv1.conv.bias)
         if self.uses_embedding and isinstance(emb, TembPack) and emb.has(self):
@@ -180,17 +188,27 @@ class ResBlockND(TimestepBlock):
                 addvec = ops.linear_f32(emb, f32(self.emb_layers.weight), f32(self.emb_layers.bias), bias1,
                                         silu_in=self.emb_activation_before_proj)
                 bias1 = None
-        h = ops.conv2d([h], self.conv1.packed([self.channels]), bias=bias1, addvec=addvec, want_stats=True)
-        h = fused_group_norm(self.norm2, [h], silu=True, scale_shift=scale_shift)
+        if tab1 is not None:
+            offs = [sum(split[:i]) for i in range(len(split))]
+            h = ops.conv2d(srcs, self.conv1.packed(split), bias=bias1, addvec=addvec, want_stats=True,
+                           norm=[(tab1, o) for o in offs])
+        else:
+            h = ops.conv2d([h], self.conv1.packed([self.channels]), bias=bias1, addvec=addvec, want_stats=True)
+        tab2 = None
+        if ops.conv_operand_norm_ok(hh, ww, 1, [3], [self.out_channels]):
+            tab2 = fused_group_norm_table(self.norm2, [h], silu=True, scale_shift=scale_shift)
+        if tab2 is None:
+            h = fused_group_norm(self.norm2, [h], silu=True, scale_shift=scale_shift)
+        n2 = None if tab2 is None else [(tab2, 0)]
 
         if isinstance(self.skip_connection, nn.Identity):
             if len(srcs) != 1:
                 srcs = [ops.to_nhwc_bf16(torch.cat(srcs, 1))]
             return ops.conv2d([h], self.conv2.packed([self.out_channels]), bias=f32(self.conv2.conv.bias),
-                              residual=srcs[0], want_stats=True)
-        split = [s.shape[1] for s in srcs]
+                              residual=srcs[0], want_stats=True, norm=n2)
         pw, bias = self._fused_tail_weight(split)
-        return ops.conv2d([h] + srcs, pw, bias=bias, want_stats=True)
+        return ops.conv2d([h] + srcs, pw, bias=bias, want_stats=True,
+                          norm=None if n2 is None else n2 + [None] * len(srcs))
 
     # eager PyTorch restatement used only for out-of-scope variants (FMDM_B200_ALLOW_EAGER=1)
     def _eager(self, x: torch.Tensor, emb):

@@ -1,5 +1,5 @@
 from .convolution import ConvND, ConvTransposeND
-from .normalization import RMSNormND, fused_group_norm, make_group_norm
+from .normalization import RMSNormND, fused_group_norm, fused_group_norm_table, make_group_norm
 from .pooling import AvgPoolND, MaxPoolND, PoolND, UnPoolND
 from .time_embedding import timestep_embedding
 from .upsampling import DownsampleND, UpsampleND

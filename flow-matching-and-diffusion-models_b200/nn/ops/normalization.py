@@ -36,6 +36,16 @@ def fused_group_norm(norm: nn.GroupNorm, srcs: Sequence[torch.Tensor], *, silu: 
                           scale_shift=scale_shift)
 
 
+def fused_group_norm_table(norm: nn.GroupNorm, srcs: Sequence[torch.Tensor], *, silu: bool,
+                           scale_shift: Optional[torch.Tensor] = None):
+    """`norm` (+SiLU, + scale-shift) as the per-(sample, channel) affine table a consumer conv applies inside its
+    operand path (`ops.conv2d(..., norm=...)`), or None when the sources do not qualify."""
+    if not 1 <= len(srcs) <= 2 or any(s.shape[1] % 8 for s in srcs):
+        return None
+    return ops.group_norm_table(list(srcs), norm.num_groups, norm.eps, f32(norm.weight), f32(norm.bias), silu=silu,
+                                scale_shift=scale_shift)
+
+
 class RMSNormND(nn.Module):
     """API-parity shell for `src/nn/ops/normalization.py:22-34` (not on any BASELINE path; out of scope)."""
 

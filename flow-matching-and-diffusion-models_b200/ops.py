@@ -154,8 +154,12 @@ def conv2d(
     residual: Optional[torch.Tensor] = None,
     out: Optional[torch.Tensor] = None,
     want_stats: bool = False,
+    norm: Optional[Sequence] = None,
 ) -> torch.Tensor:
     """Implicit-GEMM conv over the virtual channel concat of `srcs` (one K segment per source).
+
+    norm: per source, None or a `NormTable` slice `(table, channel_offset)` — that source is read through the fused
+    operand transform act(a*x+b) (GroupNorm apply + SiLU folded into the conv; see `conv_operand_norm_ok`).
 
     want_stats: also emit, from the epilogue, the GroupNorm partial statistics of the output; they ride on the
     returned tensor (`out._fm_stats`) and let the consumer `group_norm` skip its statistics pass."""
@@ -172,6 +176,15 @@ def conv2d(
         p.seg[i].C = c
         p.seg[i].ksize = ks
         p.seg[i].upsample = 0
+        nt = None if norm is None else norm[i]
+        if nt is not None:
+            table, c_off = nt
+            if table.ab.shape[0] != b or c_off + c > table.ab.shape[2]:
+                raise ValueError("conv2d: norm table does not cover this segment")
+            p.seg[i].norm_a = table.ab.data_ptr() + 4 * c_off
+            p.seg[i].norm_b = table.ab.data_ptr() + 4 * (table.ab.shape[2] + c_off)
+            p.seg[i].norm_stride = 2 * table.ab.shape[2]
+            p.seg[i].norm_act = 1 if table.silu else 0
     p.nseg = len(srcs)
     p.B, p.H, p.W = b, h, w
     p.stride = stride
@@ -234,17 +247,20 @@ def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0) -> torch
     return out
 
 
-def conv_head(x: torch.Tensor, weight_oihw, bias) -> torch.Tensor:
-    """bf16 NHWC -> fp32 NCHW, 3x3 s1 p1, Cout <= 4."""
+def conv_head(x: torch.Tensor, weight_oihw, bias, norm: Optional["NormTable"] = None) -> torch.Tensor:
+    """bf16 NHWC -> fp32 NCHW, 3x3 s1 p1, Cout <= 4; `norm` folds the output GroupNorm (+SiLU) into the load."""
     lib = _lib.lib()
     _check_act(x, "conv_head")
     b, cin, h, w = x.shape
     cout = weight_oihw.shape[0]
     out = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device)
+    if norm is not None and tuple(norm.ab.shape) != (b, 2, cin):
+        raise ValueError("conv_head: norm table shape mismatch")
     e0 = _prof_begin()
     _lib.check(
         lib.fm_conv_head_bf16_f32(x.data_ptr(), weight_oihw.data_ptr(), _ptr(bias), out.data_ptr(), b, h, w, cin, cout,
-                                  _stream()),
+                                  None if norm is None else norm.ab.data_ptr(),
+                                  0 if norm is None else int(norm.silu), _stream()),
         "conv_head",
     )
     _prof_end("conv_head", 2.0 * b * h * w * cin * 9 * cout, e0)
@@ -254,6 +270,79 @@ def conv_head(x: torch.Tensor, weight_oihw, bias) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------------------
 # GroupNorm (+SiLU, +scale/shift)
 # --------------------------------------------------------------------------------------------------------------
+class NormTable:
+    """Per-(sample, channel) affine form of a GroupNorm: ab[n][0][c]*x + ab[n][1][c], then SiLU if `silu`."""
+
+    def __init__(self, ab: torch.Tensor, silu: bool):
+        self.ab, self.silu = ab, bool(silu)
+
+
+def conv_operand_norm_ok(h: int, w: int, stride: int, ksizes: Sequence[int], channels: Sequence[int]) -> bool:
+    """Can a conv over these sources fold the GroupNorm apply into its operand path?"""
+    if any(c % 64 for c in channels):
+        return False
+    return bool(_lib.lib().fm_conv_operand_norm_supported(h, w, stride, int(any(k == 3 for k in ksizes))))
+
+
+def group_norm_table(
+    srcs: Sequence[torch.Tensor],
+    groups: int,
+    eps: float,
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    *,
+    silu: bool,
+    scale_shift: Optional[torch.Tensor] = None,
+) -> NormTable:
+    """GroupNorm statistics of the virtual concat of `srcs` -> the a*x+b table a consumer conv applies on the fly
+    (nothing the size of the activation is written)."""
+    lib = _lib.lib()
+    if not 1 <= len(srcs) <= 2:
+        raise ValueError("group_norm_table: one or two sources")
+    for s in srcs:
+        _check_act(s, "group_norm_table")
+    x0 = srcs[0]
+    x1 = srcs[1] if len(srcs) == 2 else None
+    b, c0, h, w = x0.shape
+    c1 = x1.shape[1] if x1 is not None else 0
+    ctot = c0 + c1
+    if scale_shift is not None and (scale_shift.dtype != torch.float32 or scale_shift.shape != (b, 2 * ctot)
+                                    or scale_shift.stride(1) != 1):
+        raise ValueError("group_norm_table: scale_shift must be fp32 [B][2C] with unit inner stride")
+    ss_stride = 0 if scale_shift is None else scale_shift.stride(0)
+    ab = torch.empty((b, 2, ctot), dtype=torch.float32, device=x0.device)
+    st = _stream()
+    e0 = _prof_begin()
+    fused = [getattr(s, "_fm_stats", None) for s in srcs]
+    if all(f is not None for f in fused) and (ctot // groups) % 4 == 0:
+        p1 = fused[1] if len(fused) == 2 else (None, 0)
+        _lib.check(
+            lib.fm_groupnorm_finalize_partials_affine(
+                fused[0][0].data_ptr(), fused[0][1], c0, _ptr(p1[0]), p1[1], c1, b, h * w, groups, float(eps),
+                gamma.data_ptr(), beta.data_ptr(), _ptr(scale_shift), ss_stride, None, ab.data_ptr(), st),
+            "groupnorm_finalize_partials_affine",
+        )
+        _prof_end("groupnorm_table", 0.0, e0)
+    else:
+        ws_elems = int(lib.fm_groupnorm_workspace_elems(b, h * w, ctot, groups))
+        if ws_elems <= 0:
+            raise RuntimeError(f"fmdm_b200.group_norm_table: unsupported shape B={b} HW={h * w} C={ctot} groups={groups}")
+        ws = torch.empty((ws_elems,), dtype=torch.float32, device=x0.device)
+        stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x0.device)
+        _lib.check(
+            lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps),
+                                        ws.data_ptr(), stats.data_ptr(), st),
+            "groupnorm_stats",
+        )
+        _lib.check(
+            lib.fm_groupnorm_affine_f32(stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(scale_shift),
+                                        ss_stride, b, ctot, groups, ab.data_ptr(), st),
+            "groupnorm_affine",
+        )
+        _prof_end("groupnorm_stats", 2.0 * b * ctot * h * w, e0)  # one read pass, bf16
+    return NormTable(ab, silu)
+
+
 def group_norm(
     srcs: Sequence[torch.Tensor],
     groups: int,

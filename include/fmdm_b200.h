@@ -57,6 +57,15 @@ typedef struct fm_conv_seg {
   int32_t C;         /* channels of this segment (multiple of 8)                      */
   int32_t ksize;     /* 1 or 3 (3 => pad 1, 1 => pad 0)                               */
   int32_t upsample;  /* 1: the segment is read through a nearest-2x upsample (src is [B][H/2][W/2][C]) */
+  int32_t norm_act;  /* activation of the fused operand transform: 0 none, 1 SiLU                */
+  /* Fused operand transform (GroupNorm apply + activation folded into the conv's A-operand path, so the normalised
+   * tensor of residual.py:95-96,113-116 is never written): when norm_a != NULL the conv reads
+   *   act(norm_a[n*norm_stride + c] * src[n,h,w,c] + norm_b[n*norm_stride + c])   (zero padding applies AFTER it)
+   * instead of src.  The per-(sample, channel) table comes from fm_groupnorm_affine_f32 /
+   * fm_groupnorm_finalize_partials_affine.  Only for launches fm_conv_operand_norm_supported() accepts; C % 64 == 0. */
+  const float* norm_a;
+  const float* norm_b;
+  int32_t norm_stride; /* floats between consecutive samples' rows of norm_a / norm_b */
   int32_t _pad;
 } fm_conv_seg;
 
@@ -87,6 +96,10 @@ int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream);
 int fm_conv_stats_layout(int32_t B, int32_t H, int32_t W, int32_t stride, int32_t* rows_per_image,
                          int32_t* total_rows);
 
+/* 1 if a conv with this input size / stride / kernel mix can take fused operand transforms (fm_conv_seg.norm_a):
+ * stride 1, rows of >= 65 pixels (the M tile is 128 consecutive pixels of one image row) and a 3x3 segment. */
+int fm_conv_operand_norm_supported(int32_t H, int32_t W, int32_t stride, int32_t has_3x3);
+
 /* Re-order an OIHW fp32 conv weight (or [O][I] linear weight with ksize=1) into the K-major bf16 matrix the
  * conv kernel reads: dst[co][koff + tap*Cseg + c] = src[co][c_begin + c][kh][kw]. */
 int fm_weight_prepack_bf16(void* dst, int64_t dst_row_stride, int64_t koff, const float* src_oihw, int32_t Cout,
@@ -98,9 +111,12 @@ int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t 
                           const float* weight_oihw, const float* bias, void* out_nhwc_bf16, int32_t B, int32_t H,
                           int32_t W, int32_t Cout, fm_stream_t stream);
 
-/* Head conv (tiny Cout): bf16 NHWC -> fp32 NCHW (unet_diffusers_nd.py:190, unet.py:288-292). 3x3 s1 p1. */
+/* Head conv (tiny Cout): bf16 NHWC -> fp32 NCHW (unet_diffusers_nd.py:190, unet.py:288-292). 3x3 s1 p1.
+ * norm_ab != NULL ([B][2][Cin], fm_groupnorm_affine_f32): the input is read as SiLU(a*x+b) (norm_act=1) or a*x+b,
+ * i.e. conv_norm_out + SiLU (unet_diffusers_nd.py:188-189) folded into the load. */
 int fm_conv_head_bf16_f32(const void* x_nhwc_bf16, const float* weight_oihw, const float* bias, float* out_nchw,
-                          int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, fm_stream_t stream);
+                          int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout, const float* norm_ab,
+                          int32_t norm_act, fm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K2: GroupNorm (+SiLU, +scale-shift) on NHWC bf16, fp32 statistics.
@@ -118,6 +134,16 @@ int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x1, int32_t 
 int fm_groupnorm_finalize_partials(const float* p0, int32_t rows0, int32_t C0, const float* p1, int32_t rows1,
                                    int32_t C1, int32_t B, int64_t HW, int32_t groups, float eps, float* stats,
                                    fm_stream_t stream);
+/* Per-(sample, channel) affine form of the normalisation, ab[n][0][c] = a, ab[n][1][c] = b with
+ *   a*x + b == ((x-mean)*rstd*gamma[c]+beta[c]) * (1+scale[n,c]) + shift[n,c]
+ * (fp32 [B][2][C]); consumed by the conv operand transform (fm_conv_seg.norm_a/norm_b) and by fm_conv_head_bf16_f32. */
+int fm_groupnorm_affine_f32(const float* stats, const float* gamma, const float* beta, const float* scale_shift,
+                            int64_t ss_stride, int32_t B, int32_t C, int32_t groups, float* ab, fm_stream_t stream);
+/* fm_groupnorm_finalize_partials + fm_groupnorm_affine_f32 in one launch (stats may be NULL). */
+int fm_groupnorm_finalize_partials_affine(const float* p0, int32_t rows0, int32_t C0, const float* p1, int32_t rows1,
+                                          int32_t C1, int32_t B, int64_t HW, int32_t groups, float eps,
+                                          const float* gamma, const float* beta, const float* scale_shift,
+                                          int64_t ss_stride, float* stats, float* ab, fm_stream_t stream);
 /* y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), act = SiLU if silu!=0.
  * scale_shift: fp32 rows of 2*C (scale first, then shift; residual.py:109,115), row n at scale_shift + n*ss_stride,
  * or NULL. */

@@ -29,13 +29,31 @@ def test_library_exports_every_declared_symbol():
     assert handle.fm_version() >= 100
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof/offsetof of the parameter structs as gcc sees the header == the ctypes mirror."""
+    import subprocess
+    from pathlib import Path
+
     from fmdm_b200 import _lib
 
-    assert ctypes.sizeof(_lib.ConvSeg) == 24
-    # 4 segs (96) + 7 int32 (28, padded to 32) ... pointers 8-aligned
-    assert ctypes.sizeof(_lib.ConvParams) == 96 + 32 + 8 * 3 + 8 + 8 * 3 + 8
-    assert _lib.ConvParams.weight.offset == 128 and _lib.ConvParams.out.offset == 168
+    root = Path(__file__).resolve().parent.parent
+    fields = {"fm_conv_seg": [f[0] for f in _lib.ConvSeg._fields_], "fm_conv_params": [f[0] for f in _lib.ConvParams._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "fmdm_b200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for n in names:
+            src.append(f'  printf("{st}.{n} %zu\\n", offsetof({st}, {n}));')
+    src += ['  return 0;', '}']
+    cfile = tmp_path / "layout.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(root / "include"), str(cfile), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    mirror = {"fm_conv_seg": _lib.ConvSeg, "fm_conv_params": _lib.ConvParams}
+    for st, cls in mirror.items():
+        assert int(got[st]) == ctypes.sizeof(cls), st
+        for n in fields[st]:
+            assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, f"{st}.{n}"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

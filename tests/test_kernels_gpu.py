@@ -254,3 +254,96 @@ def test_conv_fused_groupnorm_statistics():
     fused = ops.group_norm([ya, yb], 32, 1e-5, gamma, beta, silu=False).float()
     ref = F.group_norm(torch.cat([ya.float(), yb.float()], 1), 32, gamma, beta, 1e-5)
     assert _rel_l2(fused, ref) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GroupNorm apply + SiLU folded into the conv operand path (XF kernels) and into the head conv's load
+# ---------------------------------------------------------------------------------------------------------------
+def _norm_conv_case(B, H, W, cins, normed, cout, ks_list, silu=True, residual=False, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xs = [_bf16r(torch.randn(B, c, H, W, generator=g) * 1.5 + 0.3).to(DEV) for c in cins]
+    ws = [_bf16r(torch.randn(cout, c, k, k, generator=g) / math.sqrt(c * k * k)).to(DEV) for c, k in zip(cins, ks_list)]
+    bvec = torch.randn(cout, generator=g).to(DEV)
+    ctot = sum(c for c, n in zip(cins, normed) if n)
+    ab = torch.empty(B, 2, ctot)
+    ab[:, 0] = torch.rand(B, ctot, generator=g) + 0.5
+    ab[:, 1] = torch.randn(B, ctot, generator=g) * 0.5
+    ab = ab.to(DEV)
+    table = ops.NormTable(ab, silu)
+    res = _bf16r(torch.randn(B, cout, H, W, generator=g)).to(DEV) if residual else None
+    ref = torch.zeros(B, cout, H, W, device=DEV)
+    norm, off = [], 0
+    for x, w, k, c, n in zip(xs, ws, ks_list, cins, normed):
+        if n:
+            y = x * ab[:, 0, off:off + c, None, None] + ab[:, 1, off:off + c, None, None]
+            y = _bf16r(F.silu(y) if silu else y)  # the operand reaches the tensor core in bf16
+            norm.append((table, off))
+            off += c
+        else:
+            y = x
+            norm.append(None)
+        ref = ref + F.conv2d(y, w, None, padding=k // 2)
+    ref = ref + bvec.view(1, -1, 1, 1)
+    if residual:
+        ref = ref + res
+    packed = ops.pack_conv_weight([(w, 0, c) for w, c in zip(ws, cins)])
+    out = ops.conv2d([_nhwc(x) for x in xs], packed, bias=bvec, residual=_nhwc(res) if residual else None, norm=norm)
+    torch.cuda.synchronize()
+    return out.float(), ref
+
+
+NORM_CONV_CASES = [
+    # B, H, W, cins, normed, cout, ks, silu, residual
+    (2, 5, 256, [128], [True], 128, [3], True, True),
+    (1, 6, 200, [64, 128], [True, True], 256, [3, 3], True, False),        # concat GN1 of an up block, ragged W
+    (2, 4, 130, [128, 64, 64], [True, False, False], 128, [3, 1, 1], True, False),  # conv2 + fused 1x1 skip (raw)
+    (1, 3, 512, [256], [True], 512, [3], True, True),
+    (1, 8, 128, [64], [True], 64, [3], False, False),                      # no activation
+    (3, 9, 128, [64], [True], 64, [3], True, False),                       # odd tile count
+    (2, 64, 128, [128], [True], 128, [3], True, True),
+]
+
+
+@pytest.mark.parametrize("mt,pair", [("1", "1"), ("2", "1"), ("1", "0")], ids=["pair", "pair_mt2", "single"])
+@pytest.mark.parametrize("case", NORM_CONV_CASES, ids=lambda c: "B{}_{}x{}_cin{}_cout{}".format(
+    c[0], c[1], c[2], "+".join(map(str, c[3])), c[5]))
+def test_conv2d_operand_norm(case, mt, pair, monkeypatch):
+    """conv(act(a*x+b)) with the transform running inside the conv kernel == the same conv on a pre-activated input."""
+    monkeypatch.setenv("FMDM_CONV_MT", mt)
+    monkeypatch.setenv("FMDM_CONV_PAIR", pair)
+    out, ref = _norm_conv_case(*case)
+    err = _rel_l2(out, ref)
+    assert err < 6e-3, f"rel L2 {err}"
+    assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 0.05
+
+
+def test_conv2d_operand_norm_level0_shape():
+    out, ref = _norm_conv_case(2, 512, 512, [128, 128], [True, True], 128, [3, 3], True, False, seed=3)
+    assert _rel_l2(out, ref) < 6e-3
+
+
+def test_group_norm_table_and_head():
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 128, 24, 40
+    x = _bf16r(torch.randn(B, C, H, W, generator=g) * 2 + 0.5).to(DEV)
+    gamma = torch.randn(C, generator=g).to(DEV)
+    beta = torch.randn(C, generator=g).to(DEV)
+    ss = torch.randn(B, 2 * C, generator=g).to(DEV) * 0.3
+    tab = ops.group_norm_table([_nhwc(x)], 32, 1e-5, gamma, beta, silu=True, scale_shift=ss)
+    y = x * tab.ab[:, 0, :, None, None] + tab.ab[:, 1, :, None, None]
+    ref = F.group_norm(x, 32, gamma, beta, 1e-5) * (1 + ss[:, :C, None, None]) + ss[:, C:, None, None]
+    assert float((y - ref).abs().max()) < 2e-3
+    # table from conv-epilogue partial statistics == table from the statistics pass
+    w = _bf16r(torch.randn(C, 64, 3, 3, generator=g) / 24).to(DEV)
+    xin = _bf16r(torch.randn(B, 64, H, W, generator=g)).to(DEV)
+    yc = ops.conv2d([_nhwc(xin)], ops.pack_conv_weight([(w, 0, 64)]), want_stats=True)
+    t_fused = ops.group_norm_table([yc], 32, 1e-5, gamma, beta, silu=True)
+    t_plain = ops.group_norm_table([yc.clone(memory_format=torch.preserve_format)], 32, 1e-5, gamma, beta, silu=True)
+    assert float((t_fused.ab - t_plain.ab).abs().max()) < 2e-3
+    # head conv with the output norm folded into its load
+    wh = torch.randn(1, C, 3, 3, generator=g).to(DEV) / 30
+    bh = torch.randn(1, generator=g).to(DEV)
+    tab = ops.group_norm_table([_nhwc(x)], 32, 1e-5, gamma, beta, silu=True)
+    out = ops.conv_head(_nhwc(x), wh, bh, norm=tab)
+    ref = F.conv2d(F.silu(F.group_norm(x, 32, gamma, beta, 1e-5)), wh, bh, padding=1)
+    assert _rel_l2(out, ref) < 5e-3
