@@ -400,14 +400,7 @@ constexpr int kStageCols = 128;  // output columns staged (and TMA-stored) at a 
 // MT = 2 (only with BLOCK_N = 128): every weight tile is used for TWO M tiles per CTA (accumulators side by side in
 // TMEM, like one 256-column tile), halving the weight traffic per FLOP for the Cout = 128 layers, which are otherwise
 // bound by L2->SM bandwidth (13.5 KB per 64-deep k-block per CTA against a 256-cycle MMA budget).
-// XF = 1 (row mode only): four extra "transform" warps rewrite every landed A slot in place with
-// act(a[n,c]*x + b[n,c]) (GroupNorm apply + SiLU of the producer-side statistics) before the MMA issuer may read it, so
-// the normalised activation tensor is never written to or re-read from HBM.  Halo rows/pixels that TMA zero-filled
-// stay zero (the reference pads AFTER the activation).
-constexpr int kXfWarps = 4;
-constexpr int kXfThreads = kXfWarps * 32;
-
-template <int BLOCK_N, int MODE, int CG, int MT, int XF = 0>
+template <int BLOCK_N, int MODE, int CG, int MT>
 struct PConvCfg {
   static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
   static constexpr int kASub = (MODE == 1) ? kARowSlot : kABytes;  // one M tile's A operand
@@ -424,9 +417,8 @@ struct PConvCfg {
   static constexpr int kBStagesRaw = (MODE == 1) ? (kBudget - kAStages * kASlot) / kBBytes : kAStages;
   static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
   static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
-  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4 + XF * kAStages;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
   static constexpr int kSmemBytes = 1024 + kPipeBytes + kOutBufs * kOutBytes + kTailBytes;
-  static_assert(XF == 0 || MODE == 1, "operand transform only in row mode");
   static_assert(kAStages >= 2 && kBStages >= 3, "pipeline too shallow");
   static_assert(kNumBars * 8 + 8 <= 512, "barrier area");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -436,10 +428,10 @@ constexpr int kEpiWarps = 8;                        // two warps per TMEM lane q
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kPConvThreads = 64 + kEpiThreads;     // + TMA producer warp + MMA warp
 
-template <int BLOCK_N, int MODE, int CG, int MT, int XF>
-__global__ void __launch_bounds__(kPConvThreads + XF * kXfThreads, 1)
+template <int BLOCK_N, int MODE, int CG, int MT>
+__global__ void __launch_bounds__(kPConvThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = PConvCfg<BLOCK_N, MODE, CG, MT, XF>;
+  using Cfg = PConvCfg<BLOCK_N, MODE, CG, MT>;
   static_assert(MT == 1 || BLOCK_N == 128, "two M tiles per CTA only for 128-wide N tiles");
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = (cta_rank == 0);
@@ -458,7 +450,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
   auto t_full = [&](int b) { return bar_base + 8u * (2 * Cfg::kAStages + 2 * Cfg::kBStages + b); };
   auto t_empty = [&](int b) { return bar_base + 8u * (2 * Cfg::kAStages + 2 * Cfg::kBStages + 2 + b); };
-  auto a_ready = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + 2 * Cfg::kBStages + 4 + s); };  // XF only
   const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(out_gen + Cfg::kOutBufs * Cfg::kOutBytes + 8 * Cfg::kNumBars);
@@ -478,8 +469,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
       // accumulator-drained barriers: one arrival per epilogue warp of every CTA writing into this MMA's TMEM
       mbar_init(t_empty(0), kEpiWarps * CG);
       mbar_init(t_empty(1), kEpiWarps * CG);
-      // operand-transformed barriers: one arrival per transform warp of every CTA feeding this MMA
-      if (XF) for (int s = 0; s < Cfg::kAStages; ++s) mbar_init(a_ready(s), kXfWarps * CG);
       fence_barrier_init();
     }
     __syncwarp();
@@ -530,7 +519,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
             for (int cb = 0; cb < cblocks; ++cb, ++ia) {
               const int sa = ia % Cfg::kAStages;
               mbar_wait(a_empty(sa), ((ia / Cfg::kAStages) & 1) ^ 1u);
-              if (CG == 2 && !XF) {
+              if (CG == 2) {
                 if (is_leader) mbar_expect_tx(a_full(sa), 2 * Cfg::kATx);
                 tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot, cb * kBlockK,
                                  w0 * p.stride + dw, h0 * p.stride + dh, n0);
@@ -583,7 +572,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           for (int as = 0; as < asteps; ++as) {
             for (int cb = 0; cb < cblocks; ++cb, ++ia) {
               const int sa = ia % Cfg::kAStages;
-              mbar_wait(XF ? a_ready(sa) : a_full(sa), (ia / Cfg::kAStages) & 1);
+              mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
               for (int bs = 0; bs < bsteps; ++bs, ++ib) {
                 const int sb = ib % Cfg::kBStages;
                 mbar_wait(b_full(sb), (ib / Cfg::kBStages) & 1);
@@ -610,77 +599,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           }
         }
         if (CG == 2) umma_commit_pair(t_full(buf)); else umma_commit(t_full(buf));
-      }
-    }
-  } else if (XF && warp >= 2 + kEpiWarps) {
-    // ================= operand transform (warps 10..13, XF kernels) =================
-    // thread -> fixed 8-channel chunk (lc) of the 64-channel block, rows r0, r0+16, ...: the a/b coefficients of a
-    // slot live in 16 registers; 8 consecutive lanes cover one 128-byte row (conflict-free in the 128B swizzle).
-    const int tt = (int)threadIdx.x - (64 + kEpiThreads);
-    const int lc = tt & 7;
-    const int r0 = tt >> 3;
-    const uint32_t ready_bar0 = (CG == 2) ? mapa_shared(a_ready(0), 0) : a_ready(0);  // the leader CTA's barriers
-    int ia = 0;
-    for (int unit = first_unit; unit < total_units; unit += unit_stride) {
-      int m_tile, ncol0, tw[2], th[2], tn[2];
-      tile_coords(unit, 0, m_tile, tw[0], th[0], tn[0], ncol0);
-      tw[1] = th[1] = tn[1] = 0;
-      if (MT == 2) tile_coords(unit, 1, m_tile, tw[1], th[1], tn[1], ncol0);
-      for (int s = 0; s < p.nseg; ++s) {
-        const int taps = p.seg_taps[s];
-        const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
-        const int asteps = (taps == 9) ? 3 : 1;
-        const float* na = p.seg_na[s];
-        const float* nb = p.seg_nb[s];
-        const bool silu = p.seg_nact[s] != 0;
-        for (int as = 0; as < asteps; ++as) {
-          const int dh = (taps == 9) ? as - 1 : 0;
-          for (int cb = 0; cb < cblocks; ++cb, ++ia) {
-            const int sa = ia % Cfg::kAStages;
-            mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
-            if (na != nullptr) {
-#pragma unroll
-              for (int sub = 0; sub < MT; ++sub) {
-                const int h = th[sub] + dh, n = tn[sub];
-                if ((unsigned)h >= (unsigned)p.Ho || n >= p.B) continue;  // whole halo row out of bounds: stays zero
-                const size_t co = (size_t)n * p.seg_nstride[s] + cb * kBlockK + lc * 8;
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(na + co));
-                const float4 a1 = __ldg(reinterpret_cast<const float4*>(na + co + 4));
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(nb + co));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(nb + co + 4));
-                const float k = silu ? 0.5f : 1.0f;
-                const float a[8] = {a0.x * k, a0.y * k, a0.z * k, a0.w * k, a1.x * k, a1.y * k, a1.z * k, a1.w * k};
-                const float b[8] = {b0.x * k, b0.y * k, b0.z * k, b0.w * k, b1.x * k, b1.y * k, b1.z * k, b1.w * k};
-                uint8_t* slot = smem_gen + sa * Cfg::kASlot + sub * Cfg::kASub;
-                const int wbase = tw[sub] - 1;  // input pixel of slot row 0
-#pragma unroll 3
-                for (int i = 0; i < 9; ++i) {
-                  const int r = r0 + 16 * i;
-                  if (r < kTileM + 2 && (unsigned)(wbase + r) < (unsigned)p.Wo) {
-                    uint4* ptr = reinterpret_cast<uint4*>(slot + r * 128 + ((lc ^ (r & 7)) << 4));
-                    uint4 u = *ptr;
-                    if (silu) {
-                      u.x = xf_word<true>(u.x, a[0], b[0], a[1], b[1]);
-                      u.y = xf_word<true>(u.y, a[2], b[2], a[3], b[3]);
-                      u.z = xf_word<true>(u.z, a[4], b[4], a[5], b[5]);
-                      u.w = xf_word<true>(u.w, a[6], b[6], a[7], b[7]);
-                    } else {
-                      u.x = xf_word<false>(u.x, a[0], b[0], a[1], b[1]);
-                      u.y = xf_word<false>(u.y, a[2], b[2], a[3], b[3]);
-                      u.z = xf_word<false>(u.z, a[4], b[4], a[5], b[5]);
-                      u.w = xf_word<false>(u.w, a[6], b[6], a[7], b[7]);
-                    }
-                    *ptr = u;
-                  }
-                }
-              }
-              fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            }
-            __syncwarp();
-            if (lane == 0)
-              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ready_bar0 + 8u * sa) : "memory");
-          }
-        }
       }
     }
   } else if (warp >= 2) {
@@ -843,7 +761,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           __syncwarp();
           if (lane == 0) {
             const uint32_t bar = buf ? t_empty_leader1 : t_empty_leader0;
-            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
           }
         }
         fence_proxy_async_smem();
@@ -967,12 +885,12 @@ static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cud
   return 0;
 }
 
-template <int BLOCK_N, int MODE, int CG, int MT, int XF = 0>
+template <int BLOCK_N, int MODE, int CG, int MT>
 static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
-  using Cfg = PConvCfg<BLOCK_N, MODE, CG, MT, XF>;
+  using Cfg = PConvCfg<BLOCK_N, MODE, CG, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<BLOCK_N, MODE, CG, MT, XF>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_persistent_kernel<BLOCK_N, MODE, CG, MT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_igemm_persistent)");
     attr_set = true;
@@ -983,7 +901,7 @@ static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas);
-  cfg.blockDim = dim3(kPConvThreads + XF * kXfThreads);
+  cfg.blockDim = dim3(kPConvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -993,13 +911,15 @@ static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<BLOCK_N, MODE, CG, MT, XF>, kp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<BLOCK_N, MODE, CG, MT>, kp);
   count_launch();
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_igemm_persistent)");
   return 0;
 }
 
 }  // namespace fm
+
+#include "conv_rolling.cuh"
 
 extern "C" int fm_conv_stats_layout(int32_t B, int32_t H, int32_t W, int32_t stride, int32_t* rows_per_image,
                                     int32_t* total_rows) {
@@ -1086,10 +1006,21 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
       return e;
   }
   kp.num_k_blocks = nk;
-  const int block_n = (p->Cout > 128) ? 256 : (p->Cout > 64 ? 128 : 64);
+  int block_n = (p->Cout > 128) ? 256 : (p->Cout > 64 ? 128 : 64);
+  // rolling-row kernel: stride-1 row-mode convs led by a 3x3 segment, >= 2 strips; N tiles of at most 128 columns
+  bool rolling = row_mode && p->seg[0].ksize == 3 && (kp.tiles_w * p->B >= 2 || Ho >= 8);
+  {
+    const char* re = getenv("FMDM_CONV_ROLLING");  // 0 disables, 1 = only where the operand transform is requested
+    const int rv = re ? atoi(re) : 2;
+    if ((rv == 0 || rv == 1) && !xf) rolling = false;
+    if (p->Cout > 128 && !xf && rv != 3) rolling = false;  // wide layers: the 256-column pair kernel unless fused (3 forces)
+  }
+  FM_REQUIRE(!xf || rolling, "conv: fused operand transform needs a leading 3x3 segment at stride 1 on image rows of "
+                             ">= 65 pixels (fm_conv_operand_norm_supported)");
+  if (rolling && block_n == 256) block_n = 128;
   // CTA pairs (cta_group::2): enabled for the 128/256-wide tiles when there are at least two M tiles
   const int m_tiles_total = kp.tiles_w * kp.tiles_h * tiles_n;
-  bool pair = (block_n >= 128) && (m_tiles_total >= 2);
+  bool pair = ((block_n >= 128) && (m_tiles_total >= 2)) || rolling;
   {
     const char* pe = getenv("FMDM_CONV_PAIR");  // 0 disables, 1 (default) enables
     if (pe && atoi(pe) == 0) pair = false;
@@ -1131,14 +1062,11 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   kp.m_tiles = (m_tiles + m_round - 1) / m_round * m_round;
   {
     const char* pe = getenv("FMDM_CONV_PERSISTENT");  // 0 selects the one-tile-per-CTA kernel
-    const bool persistent = !(pe && atoi(pe) == 0) || xf;
-    if (persistent && xf) {
-      if (pair && mt == 2) return launch_conv_persistent<128, 1, 2, 2, 1>(kp, st);
-      if (pair) return block_n == 128 ? launch_conv_persistent<128, 1, 2, 1, 1>(kp, st)
-                                      : launch_conv_persistent<256, 1, 2, 1, 1>(kp, st);
-      if (block_n == 64) return launch_conv_persistent<64, 1, 1, 1, 1>(kp, st);
-      if (block_n == 128) return launch_conv_persistent<128, 1, 1, 1, 1>(kp, st);
-      return launch_conv_persistent<256, 1, 1, 1, 1>(kp, st);
+    const bool persistent = !(pe && atoi(pe) == 0);
+    if (rolling) {
+      const RollSched sch = roll_schedule(p->B, Ho, kp.tiles_w, n_tiles, sm_count() / 2);
+      if (xf) return block_n == 64 ? launch_conv_rolling<64, 1>(kp, sch, st) : launch_conv_rolling<128, 1>(kp, sch, st);
+      return block_n == 64 ? launch_conv_rolling<64, 0>(kp, sch, st) : launch_conv_rolling<128, 0>(kp, sch, st);
     }
     if (persistent) {
 #define FM_PC(N, M, G) return launch_conv_persistent<N, M, G, 1>(kp, st)

@@ -1,0 +1,548 @@
+// K1, "rolling row" variant for stride-1 3x3 convs on images whose rows hold >= 65 pixels (the level-0/1/2 layers of
+// the LDCT UNet: > 90 % of its FLOPs).  Included by conv_igemm.cu (shares ConvKernelParams and the host encoders).
+//
+// A CTA pair walks STRIPS: 128 consecutive pixels of `R` consecutive output rows (one strip per CTA, two per pair,
+// tcgen05 cta_group::2, M = 256).  Input rows are streamed ONCE per strip: the 130-pixel halo row (kh-independent) of a
+// 64-channel block lands in shared memory with one TMA load and feeds all nine taps - the three kw taps as row-shifted
+// views of the slot (as in row mode) and the three kh taps by accumulating into the accumulators of three DIFFERENT
+// output rows (o = r+1, r, r-1).  Four accumulators (4 x BLOCK_N TMEM columns) form a ring: three are live, the fourth
+// is drained by the epilogue while the next input row streams.  Against the per-tile row mode this cuts the A operand
+// traffic from L2 and - the point - the number of times an input element passes the operand transform by 3x, so the
+// fused GroupNorm-apply + SiLU (XF) needs one pass per element and its four transform warps keep up with the MMAs.
+//
+// Warp roles: 0 TMA producer, 1 MMA issuer (leader CTA), 2..9 epilogue, 10..13 operand transform (XF only).
+#pragma once
+
+namespace fm {
+
+constexpr int kRollAccBufs = 4;
+// XF = 1: four extra "transform" warps rewrite every landed A slot in place with act(a[n,c]*x + b[n,c]) (GroupNorm apply
+// + SiLU from the producer-side statistics) before the MMA issuer may read it, so the normalised activation tensor is
+// never written to or re-read from HBM.  Halo rows/pixels that TMA zero-filled stay zero (the reference pads AFTER the
+// activation).
+constexpr int kXfWarps = 4;
+constexpr int kXfThreads = kXfWarps * 32;
+
+// 8 bf16 channels (one 16-byte chunk) through act(a*x+b); a, b pre-halved when kSilu (SiLU(2h) = h + h*tanh(h)).
+template <bool kSilu>
+__device__ __forceinline__ uint4 xf_chunk(uint4 u, const float (&a)[8], const float (&b)[8]) {
+  uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float h0 = fmaf(__uint_as_float(w[j] << 16), a[2 * j], b[2 * j]);
+    float h1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), a[2 * j + 1], b[2 * j + 1]);
+    if (kSilu) {
+      float t0, t1;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+      h0 = fmaf(h0, t0, h0);
+      h1 = fmaf(h1, t1, h1);
+    }
+    w[j] = pack_bf16x2(h0, h1);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int BLOCK_N, int XF>
+struct RConvCfg {
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128, "four accumulators must fit the 512 TMEM columns");
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;  // per CTA (each CTA of the pair stages half of N)
+  static constexpr int kASlot = kARowSlot;
+  static constexpr int kATx = kARowTx;
+  static constexpr int kOutBytes = kTileM * BLOCK_N * 2;
+  static constexpr int kOutBufs = 2;
+  static constexpr int kTailBytes = 512 + BLOCK_N * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024 - kTailBytes - kOutBufs * kOutBytes;
+  static constexpr int kAStages = 4;
+  static constexpr int kBStagesRaw = (kBudget - kAStages * kASlot) / kBBytes;
+  static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
+  static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 2 * kRollAccBufs + XF * kAStages;
+  static constexpr int kSmemBytes = 1024 + kPipeBytes + kOutBufs * kOutBytes + kTailBytes;
+  static constexpr int kTmemCols = kRollAccBufs * BLOCK_N;
+  static_assert(kBStages >= 6, "weight pipeline too shallow");
+  static_assert(kNumBars * 8 + 8 <= 512, "barrier area");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+struct RollSched {
+  int R;        // output rows per strip
+  int chunks;   // row chunks per image
+  int combos;   // (image, w-tile) combinations, padded to even so the two strips of a pair share their row chunk
+  int pairs;    // strip pairs = chunks * combos / 2
+};
+
+template <int BLOCK_N, int XF>
+__global__ void __launch_bounds__(kPConvThreads + XF * kXfThreads, 1)
+conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched sch) {
+  using Cfg = RConvCfg<BLOCK_N, XF>;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = (cta_rank == 0);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + Cfg::kAStages * Cfg::kASlot;
+  const uint32_t smem_out = smem_base + Cfg::kPipeBytes;
+  uint8_t* out_gen = smem_gen + Cfg::kPipeBytes;
+  const uint32_t bar_base = smem_out + Cfg::kOutBufs * Cfg::kOutBytes;
+  float* sbias = reinterpret_cast<float*>(out_gen + Cfg::kOutBufs * Cfg::kOutBytes + 512);  // [BLOCK_N]
+  constexpr int kBarT = 2 * Cfg::kAStages + 2 * Cfg::kBStages;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
+  auto t_full = [&](int b) { return bar_base + 8u * (kBarT + b); };
+  auto t_empty = [&](int b) { return bar_base + 8u * (kBarT + kRollAccBufs + b); };
+  auto a_ready = [&](int s) { return bar_base + 8u * (kBarT + 2 * kRollAccBufs + s); };  // XF only
+  const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(out_gen + Cfg::kOutBufs * Cfg::kOutBytes + 8 * Cfg::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.src[s]);
+    tma_prefetch_desc(&p.wgt);
+    tma_prefetch_desc(&p.out);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kBarT + kRollAccBufs; ++s) mbar_init(bar_base + 8u * s, 1);
+      for (int b = 0; b < kRollAccBufs; ++b) mbar_init(t_empty(b), kEpiWarps * 2);
+      if (XF) for (int s = 0; s < Cfg::kAStages; ++s) mbar_init(a_ready(s), kXfWarps * 2);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // ---- static schedule: unit = (strip pair, N tile), N fastest --------------------------------------------------
+  const int total_units = sch.pairs * p.n_tiles;
+  const int first_unit = (int)blockIdx.x >> 1;
+  const int unit_stride = (int)gridDim.x >> 1;
+  // this CTA's strip of a unit: 128 pixels starting at w0 of rows [h_begin, h_end) of image n
+  auto strip_coords = [&](int unit, int& tw, int& w0, int& n, int& h_begin, int& h_end, int& ncol0) {
+    const int ps = unit / p.n_tiles;
+    ncol0 = (unit - ps * p.n_tiles) * BLOCK_N;
+    const int sid = ps * 2 + (int)cta_rank;
+    const int chunk = sid / sch.combos;
+    const int j = sid - chunk * sch.combos;
+    n = j / p.tiles_w;
+    tw = j - n * p.tiles_w;
+    w0 = tw * kTileM;
+    h_begin = chunk * sch.R;
+    h_end = h_begin + sch.R;
+    if (h_end > p.Ho) h_end = p.Ho;
+  };
+  // taps of input row r that land on output rows of [h_begin, h_end): kh in [kh_lo, kh_hi], output row o = r + 1 - kh
+  auto kh_range = [](int r, int h_begin, int h_end, int& kh_lo, int& kh_hi) {
+    kh_lo = r + 2 - h_end;
+    if (kh_lo < 0) kh_lo = 0;
+    kh_hi = r + 1 - h_begin;
+    if (kh_hi > 2) kh_hi = 2;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one_sync()) {
+      StageRing ra, rb;
+      const uint32_t a_full_leader0 = mapa_shared(a_full(0), 0), b_full_leader0 = mapa_shared(b_full(0), 0);
+      const int bcol_off = (int)cta_rank * (BLOCK_N / 2);
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+        int tw, w0, n, h_begin, h_end, ncol0;
+        strip_coords(unit, tw, w0, n, h_begin, h_end, ncol0);
+        const int bcol = ncol0 + bcol_off;
+        for (int r = h_begin - 1; r <= h_end; ++r) {
+          int kh_lo, kh_hi;
+          kh_range(r, h_begin, h_end, kh_lo, kh_hi);
+          for (int s = 0; s < p.nseg; ++s) {
+            const int taps = p.seg_taps[s];
+            if (taps == 1 && (r < h_begin || r >= h_end)) continue;  // a 1x1 segment only feeds its own row
+            const int C = p.seg_c[s];
+            const int cblocks = (C + kBlockK - 1) / kBlockK;
+            const int t_lo = (taps == 9) ? kh_lo * 3 : 0, t_n = (taps == 9) ? (kh_hi - kh_lo + 1) * 3 : 1;
+            for (int cb = 0; cb < cblocks; ++cb) {
+              mbar_wait(a_empty(ra.idx), ra.phase ^ 1u);
+              if (XF) {  // each CTA's transform warps wait for their own bytes
+                mbar_expect_tx(a_full(ra.idx), Cfg::kATx);
+                tma_load_4d(&p.src[s], a_full(ra.idx), smem_a0 + ra.idx * Cfg::kASlot, cb * kBlockK, w0 - 1, r, n);
+              } else {
+                if (is_leader) mbar_expect_tx(a_full(ra.idx), 2 * Cfg::kATx);
+                tma_load_4d_pair(&p.src[s], a_full_leader0 + 8u * ra.idx, smem_a0 + ra.idx * Cfg::kASlot,
+                                 cb * kBlockK, w0 - 1, r, n);
+              }
+              ra.advance(Cfg::kAStages);
+              int kcol = p.seg_koff[s] + t_lo * C + cb * kBlockK;
+              for (int t = 0; t < t_n; ++t, kcol += C) {
+                mbar_wait(b_empty(rb.idx), rb.phase ^ 1u);
+                if (is_leader) mbar_expect_tx(b_full(rb.idx), 2 * Cfg::kBBytes);
+                tma_load_2d_pair(&p.wgt, b_full_leader0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kcol, bcol);
+                rb.advance(Cfg::kBStages);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && is_leader) {
+    // ================= MMA issuer =================
+    // One thread feeds the tensor cores of both SMs: the loop body per weight tile (4 MMAs = ~256 tensor cycles) is
+    // kept to a few dozen instructions - ring cursors instead of divisions, descriptors advanced by adding to their
+    // lower word.
+    constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM * 2, BLOCK_N);
+    if (elect_one_sync()) {
+      StageRing ra, rb;
+      int oc0 = 0;  // output rows finished by this CTA pair before the current unit
+      const uint32_t a_lo0 = desc_lo_sw128(smem_a0), b_lo0 = desc_lo_sw128(smem_b0);
+      auto issue_tap = [&](uint32_t tmem_d, uint32_t a_lo, uint32_t first_acc) {
+        mbar_wait(b_full(rb.idx), rb.phase);
+        tc_fence_after();
+        const uint32_t b_lo = b_lo0 + rb.idx * (uint32_t)(Cfg::kBBytes >> 4);
+        umma_bf16_ss_pair_lh(tmem_d, a_lo, b_lo, idesc, first_acc);
+        umma_bf16_ss_pair_lh(tmem_d, a_lo + 2, b_lo + 2, idesc, 1u);
+        umma_bf16_ss_pair_lh(tmem_d, a_lo + 4, b_lo + 4, idesc, 1u);
+        umma_bf16_ss_pair_lh(tmem_d, a_lo + 6, b_lo + 6, idesc, 1u);
+        umma_commit_pair(b_empty(rb.idx));
+        rb.advance(Cfg::kBStages);
+      };
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+        int tw, w0, n, h_begin, h_end, ncol0;
+        strip_coords(unit, tw, w0, n, h_begin, h_end, ncol0);
+        for (int r = h_begin - 1; r <= h_end; ++r) {
+          int kh_lo, kh_hi;
+          kh_range(r, h_begin, h_end, kh_lo, kh_hi);
+          const int ocr = oc0 + (r + 1 - h_begin);  // ring position of output row r+1 (kh = 0)
+          if (r + 1 < h_end) {
+            // output row r+1 starts accumulating with this input row: its ring slot must have been drained
+            mbar_wait(t_empty(ocr & 3), ((ocr >> 2) & 1) ^ 1u);
+            tc_fence_after();
+          }
+          for (int s = 0; s < p.nseg; ++s) {
+            const int taps = p.seg_taps[s];
+            if (taps == 1 && (r < h_begin || r >= h_end)) continue;
+            const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
+            for (int cb = 0; cb < cblocks; ++cb) {
+              mbar_wait(XF ? a_ready(ra.idx) : a_full(ra.idx), ra.phase);
+              const uint32_t a_lo = a_lo0 + ra.idx * (uint32_t)(Cfg::kASlot >> 4);
+              if (taps == 9) {
+                for (int kh = kh_lo; kh <= kh_hi; ++kh) {
+                  const uint32_t tmem_d = tmem_base + (uint32_t)(((ocr - kh) & 3) * BLOCK_N);
+                  // the very first MMA into an output row (kh = 0 of segment 0, channel block 0, kw = 0) overwrites
+                  const uint32_t acc0 = (kh == 0 && s == 0 && cb == 0) ? 0u : 1u;
+                  issue_tap(tmem_d, a_lo, acc0);                                // kw = 0: slot rows 0..127
+                  issue_tap(tmem_d, a_lo + (kARowBytes >> 4), 1u);              // kw = 1: rows 1..128
+                  issue_tap(tmem_d, a_lo + 2 * (kARowBytes >> 4), 1u);          // kw = 2: rows 2..129
+                }
+              } else {  // 1x1 segment: centre pixel, own row (kh = 1)
+                issue_tap(tmem_base + (uint32_t)(((ocr - 1) & 3) * BLOCK_N), a_lo + (kARowBytes >> 4), 1u);
+              }
+              umma_commit_pair(a_empty(ra.idx));
+              ra.advance(Cfg::kAStages);
+            }
+          }
+          if (r - 1 >= h_begin) umma_commit_pair(t_full((ocr - 2) & 3));  // output row r-1 received its last tap
+        }
+        oc0 += h_end - h_begin;
+      }
+    }
+  } else if (XF && warp >= 2 + kEpiWarps) {
+    // ================= operand transform =================
+    const int tt = (int)threadIdx.x - (64 + kEpiThreads);
+    const int lc = tt & 7;   // this thread's 8-channel chunk of the 64-channel block
+    const int r0 = tt >> 3;  // first slot row, step 16
+    const uint32_t ready_bar0 = mapa_shared(a_ready(0), 0);
+    int ia = 0;
+    for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+      int tw, w0, n, h_begin, h_end, ncol0;
+      strip_coords(unit, tw, w0, n, h_begin, h_end, ncol0);
+      for (int r = h_begin - 1; r <= h_end; ++r) {
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          if (taps == 1 && (r < h_begin || r >= h_end)) continue;
+          const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
+          const float* na = p.seg_na[s];
+          const float* nb = p.seg_nb[s];
+          const bool silu = p.seg_nact[s] != 0;
+          const bool live = (na != nullptr) && ((unsigned)r < (unsigned)p.Ho) && (n < p.B);
+          for (int cb = 0; cb < cblocks; ++cb, ++ia) {
+            const int sa = ia % Cfg::kAStages;
+            float a[8], b[8];
+            if (live) {  // coefficient loads overlap the wait for the slot
+              const size_t co = (size_t)n * p.seg_nstride[s] + cb * kBlockK + lc * 8;
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(na + co));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(na + co + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(nb + co));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(nb + co + 4));
+              const float k = silu ? 0.5f : 1.0f;
+              a[0] = a0.x * k; a[1] = a0.y * k; a[2] = a0.z * k; a[3] = a0.w * k;
+              a[4] = a1.x * k; a[5] = a1.y * k; a[6] = a1.z * k; a[7] = a1.w * k;
+              b[0] = b0.x * k; b[1] = b0.y * k; b[2] = b0.z * k; b[3] = b0.w * k;
+              b[4] = b1.x * k; b[5] = b1.y * k; b[6] = b1.z * k; b[7] = b1.w * k;
+            }
+            mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
+            if (live) {
+              uint8_t* slot = smem_gen + sa * Cfg::kASlot;
+              const int wbase = w0 - 1;  // input pixel of slot row 0
+              // rows r0, r0+16, ..., r0+112 (< 128 for every thread): four chunks in flight, stores predicated on the
+              // pixel lying inside the image (padding must stay zero)
+#pragma unroll
+              for (int i0 = 0; i0 < 8; i0 += 4) {
+                uint4* ptr[4];
+                uint4 u[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int rr = r0 + 16 * (i0 + j);
+                  ptr[j] = reinterpret_cast<uint4*>(slot + rr * 128 + ((lc ^ (rr & 7)) << 4));
+                  u[j] = *ptr[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int rr = r0 + 16 * (i0 + j);
+                  const uint4 o = silu ? xf_chunk<true>(u[j], a, b) : xf_chunk<false>(u[j], a, b);
+                  if ((unsigned)(wbase + rr) < (unsigned)p.Wo) *ptr[j] = o;
+                }
+              }
+              if (r0 < 2) {  // slot rows 128, 129
+                const int rr = r0 + 128;
+                uint4* ptr = reinterpret_cast<uint4*>(slot + rr * 128 + ((lc ^ (rr & 7)) << 4));
+                const uint4 o = silu ? xf_chunk<true>(*ptr, a, b) : xf_chunk<false>(*ptr, a, b);
+                if ((unsigned)(wbase + rr) < (unsigned)p.Wo) *ptr = o;
+              }
+              fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            }
+            __syncwarp();
+            if (lane == 0)
+              asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ready_bar0 + 8u * sa)
+                           : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // ================= epilogue (warps 2..9): one output row tile (128 pixels x BLOCK_N) at a time =================
+    const int quad = warp & 3;
+    const int cgrp = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    const bool store_issuer = (warp == 2) && elect_one_sync();
+    const uint32_t t_empty_leader0 = mapa_shared(t_empty(0), 0);
+    constexpr int kWarpCols = BLOCK_N / 2;
+    constexpr int kWarpChunks = kWarpCols / 8;
+    int oc = 0, stage_use = 0;
+    for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+      int tw, w0, n0, h_begin, h_end, ncol0;
+      strip_coords(unit, tw, w0, n0, h_begin, h_end, ncol0);
+      for (int h0 = h_begin; h0 < h_end; ++h0, ++oc, ++stage_use) {
+        const int buf = oc & 3;
+        const int m_tile = (n0 * p.Ho + h0) * p.tiles_w + tw;
+        const int ow = w0 + row;
+        const bool valid = (ow < p.Wo) && (n0 < p.B);
+
+        if (etid < BLOCK_N) {
+          const int col = ncol0 + etid;
+          float bv = 0.f;
+          if (col < p.Cout) {
+            if (p.bias != nullptr) bv = __ldg(p.bias + col);
+            if (p.addvec != nullptr && n0 < p.B) bv += __ldg(p.addvec + (size_t)n0 * p.addvec_stride + col);
+          }
+          sbias[etid] = bv;
+        }
+        uint8_t* stg = out_gen + (stage_use & 1) * Cfg::kOutBytes;
+        const uint32_t stg_u32 = smem_out + (stage_use & 1) * Cfg::kOutBytes;
+        // the TMA store that last read THIS staging buffer (two tiles ago) must be done reading it
+        if (store_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+
+        if (p.residual != nullptr) {
+          // coalesced 16-byte reads of this warp's 32 rows x kWarpCols columns, staged into the swizzled tile
+          // (issued before the accumulator wait: the global latency hides behind the main loop)
+#pragma unroll
+          for (int i0 = 0; i0 < kWarpChunks; i0 += 8) {
+            constexpr int kU = kWarpChunks < 8 ? kWarpChunks : 8;
+            uint4 buf4[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const int idx = (i0 + u) * 32 + lane;
+              const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
+              const int pw = w0 + quad * 32 + rl;
+              const int col = ncol0 + ch * 8;
+              buf4[u] = make_uint4(0, 0, 0, 0);
+              if (pw < p.Wo && n0 < p.B && col < p.Cout)
+                buf4[u] = *reinterpret_cast<const uint4*>(p.residual +
+                                                          (((size_t)n0 * p.Ho + h0) * p.Wo + pw) * p.Cout + col);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const int idx = (i0 + u) * 32 + lane;
+              const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
+              const int rr = quad * 32 + rl;
+              uint8_t* dst = stg + (ch >> 3) * (kTileM * 128) + rr * 128 + (((ch & 7) ^ (rr & 7)) * 16);
+              *reinterpret_cast<uint4*>(dst) = buf4[u];
+            }
+          }
+          __syncwarp();
+        }
+
+        mbar_wait(t_full(buf), (oc >> 2) & 1);
+        tc_fence_after();
+
+        // pull this warp's whole share of the accumulator into registers and hand the ring slot back to the MMA issuer
+        // at once: with three of the four accumulators live, the drain latency (not its throughput) would otherwise
+        // stall the next input row
+        uint32_t rg[kWarpCols];
+#pragma unroll
+        for (int i = 0; i < kWarpCols / 32; ++i)
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                 (uint32_t)(buf * BLOCK_N + cgrp * kWarpCols + i * 32), rg + i * 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(t_empty_leader0 + 8u * buf)
+                       : "memory");
+
+#pragma unroll
+        for (int i = 0; i < kWarpCols / 32; ++i) {
+          const int c0 = cgrp * kWarpCols + i * 32;
+          const int col0 = ncol0 + c0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rg[i * 32 + j]);
+          const int slab = c0 >> 6;
+          const int chunk0 = (c0 & 63) >> 3;
+          uint8_t* rowp = stg + slab * (kTileM * 128) + row * 128;
+          const float* sb = sbias + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb + j4 * 4);
+            v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
+              const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
+              const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
+              v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
+              v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
+            }
+          }
+          if (p.gn_partial != nullptr) {
+            float red[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = valid ? v[4 * j + 0] : 0.f, a1 = valid ? v[4 * j + 1] : 0.f;
+              const float a2 = valid ? v[4 * j + 2] : 0.f, a3 = valid ? v[4 * j + 3] : 0.f;
+              red[j] = (a0 + a1) + (a2 + a3);
+              red[8 + j] = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
+            }
+#pragma unroll
+            for (int width = 8, mask = 16; width >= 1; width >>= 1, mask >>= 1) {
+              const bool upper = (lane & mask) != 0;
+#pragma unroll
+              for (int i = 0; i < width; ++i) {
+                const float keep = upper ? red[i + width] : red[i];
+                const float give = upper ? red[i] : red[i + width];
+                red[i] = keep + __shfl_xor_sync(0xffffffffu, give, mask);
+              }
+            }
+            red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
+            const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const int qcol = col0 + (vidx & 7) * 4;
+            if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
+              p.gn_partial[(((size_t)m_tile * 4 + quad) * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = red[0];
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (chunk0 + j) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+                make_uint4(pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (store_issuer) {
+#pragma unroll
+          for (int slab = 0; slab < BLOCK_N / 64; ++slab) {
+            if (ncol0 + slab * 64 < p.Cout)
+              tma_store_4d(&p.out, stg_u32 + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (store_issuer) tma_store_wait_read0();
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// Rows per strip: the largest R in {32, 16, 8, 4} whose static round-robin over the SM pairs loses <= 4 % to the last
+// partial round (halo rows cost (R+2)/R operand loads and transforms, but no extra MMAs), else the best of them.
+static RollSched roll_schedule(int B, int Ho, int tiles_w, int n_tiles, int sm_pairs) {
+  RollSched best{};
+  double best_cost = 1e30;
+  const int combos = (B * tiles_w + 1) & ~1;
+  for (int R = 32; R >= 4; R >>= 1) {
+    const int chunks = (Ho + R - 1) / R;
+    const int pairs = chunks * combos / 2;
+    const long units = (long)pairs * n_tiles;
+    const long rounds = (units + sm_pairs - 1) / sm_pairs;
+    // time ~ rounds * (R rows of MMAs) with a small penalty for the two halo rows' operand traffic
+    const double cost = (double)rounds * (R + 0.25 * 2.0);
+    if (cost < best_cost * 0.96) {
+      best_cost = cost;
+      best = RollSched{R, chunks, combos, pairs};
+    }
+  }
+  return best;
+}
+
+template <int BLOCK_N, int XF>
+static int launch_conv_rolling(const ConvKernelParams& kp, const RollSched& sch, cudaStream_t st) {
+  using Cfg = RConvCfg<BLOCK_N, XF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_rolling_kernel<BLOCK_N, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_rolling)");
+    attr_set = true;
+  }
+  const int units = sch.pairs * kp.n_tiles;
+  int ctas = (sm_count() / 2) * 2;
+  if (ctas > units * 2) ctas = units * 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kPConvThreads + XF * kXfThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_rolling_kernel<BLOCK_N, XF>, kp, sch);
+  count_launch();
+  if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_rolling)");
+  return 0;
+}
+
+}  // namespace fm

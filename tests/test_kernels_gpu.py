@@ -106,6 +106,27 @@ def test_conv2d_igemm_two_m_tiles_per_cta(case, monkeypatch):
     assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 0.05
 
 
+ROLLING_CASES = [c for c in CONV_CASES if c[6] == 1 and c[2] > 64 and c[5][0] == 3] + [
+    (2, 37, 128, [64], 64, [3], 1, True, True, True),
+    (3, 70, 200, [128, 64], 128, [3, 3], 1, True, True, False),
+    (1, 33, 512, [128, 128, 128], 256, [3, 1, 1], 1, True, False, False),
+    (5, 1, 128, [64], 128, [3], 1, True, False, True),          # single-row images, odd strip count
+    (1, 2, 130, [64], 192, [3], 1, False, False, False),
+]
+
+
+@pytest.mark.parametrize("mode", ["0", "3"], ids=["per_tile", "rolling"])
+@pytest.mark.parametrize("case", ROLLING_CASES, ids=lambda c: "B{}_{}x{}_cin{}_cout{}_k{}".format(
+    c[0], c[1], c[2], "+".join(map(str, c[3])), c[4], "".join(map(str, c[5]))))
+def test_conv2d_igemm_rolling_rows(case, mode, monkeypatch):
+    """Row-mode shapes through both schedules: per-tile K loop and the rolling-row strips (forced for every Cout)."""
+    monkeypatch.setenv("FMDM_CONV_ROLLING", mode)
+    out, ref = _conv_case(*case)
+    err = _rel_l2(out, ref)
+    assert err < 6e-3, f"rel L2 {err}"
+    assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 0.05
+
+
 def test_group_norm_silu():
     g = torch.Generator().manual_seed(1)
     for (B, C, H, W, groups) in [(2, 128, 32, 32, 32), (3, 64, 7, 7, 32), (2, 512, 16, 16, 32), (1, 256, 64, 64, 32)]:
@@ -304,13 +325,10 @@ NORM_CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mt,pair", [("1", "1"), ("2", "1"), ("1", "0")], ids=["pair", "pair_mt2", "single"])
 @pytest.mark.parametrize("case", NORM_CONV_CASES, ids=lambda c: "B{}_{}x{}_cin{}_cout{}".format(
     c[0], c[1], c[2], "+".join(map(str, c[3])), c[5]))
-def test_conv2d_operand_norm(case, mt, pair, monkeypatch):
+def test_conv2d_operand_norm(case):
     """conv(act(a*x+b)) with the transform running inside the conv kernel == the same conv on a pre-activated input."""
-    monkeypatch.setenv("FMDM_CONV_MT", mt)
-    monkeypatch.setenv("FMDM_CONV_PAIR", pair)
     out, ref = _norm_conv_case(*case)
     err = _rel_l2(out, ref)
     assert err < 6e-3, f"rel L2 {err}"

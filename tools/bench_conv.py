@@ -32,14 +32,21 @@ def main():
         bias = torch.randn(cout, device=dev)
         Ho = (H + s - 1) // s
         out = ops.empty_nhwc(B, cout, Ho, Ho, dev)
+        norm = None
+        if os.environ.get("NORM") and s == 1 and k == 3:
+            tab = ops.NormTable(torch.rand(B, 2, sum(cins), device=dev) + 0.5, True)
+            norm, off = [], 0
+            for c in cins:
+                norm.append((tab, off))
+                off += c
         for _ in range(3):
-            ops.conv2d(xs, pw, stride=s, bias=bias, out=out)
+            ops.conv2d(xs, pw, stride=s, bias=bias, out=out, norm=norm)
         ts = []
         for _ in range(5):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv2d(xs, pw, stride=s, bias=bias, out=out)
+            ops.conv2d(xs, pw, stride=s, bias=bias, out=out, norm=norm)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
