@@ -501,63 +501,68 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   if (warp == 0) {
     // ================= TMA producer (runs ahead across tiles) =================
     if (elect_one_sync()) {
-      int ia = 0, ib = 0;
+      StageRing ra, rb;
+      const uint32_t a_full_dst0 = (CG == 2) ? mapa_shared(a_full(0), 0) : a_full(0);  // pair: the leader's barriers
+      const uint32_t b_full_dst0 = (CG == 2) ? mapa_shared(b_full(0), 0) : b_full(0);
+      const bool arm = (CG == 1) || is_leader;  // pair: only the leader arms, with both CTAs' bytes
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
         int m_tile, w0, h0, n0, ncol0, w1 = 0, h1 = 0, n1 = 0;
         tile_coords(unit, 0, m_tile, w0, h0, n0, ncol0);
         if (MT == 2) tile_coords(unit, 1, m_tile, w1, h1, n1, ncol0);
+        const int bcol = ncol0 + ((CG == 2) ? (int)cta_rank * (BLOCK_N / 2) : 0);
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_taps[s];
           const int C = p.seg_c[s];
           const int cblocks = (C + kBlockK - 1) / kBlockK;
           const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
           const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
+          int dh = (taps == 9) ? -1 : 0, dw = (MODE == 1 || taps == 9) ? -1 : 0;
           for (int as = 0; as < asteps; ++as) {
-            int dh, dw;
-            if (MODE == 1) { dh = (taps == 9) ? as - 1 : 0; dw = -1; }
-            else { dh = (taps == 9) ? (as / 3 - 1) : 0; dw = (taps == 9) ? (as % 3 - 1) : 0; }
-            for (int cb = 0; cb < cblocks; ++cb, ++ia) {
-              const int sa = ia % Cfg::kAStages;
-              mbar_wait(a_empty(sa), ((ia / Cfg::kAStages) & 1) ^ 1u);
+            for (int cb = 0; cb < cblocks; ++cb) {
+              mbar_wait(a_empty(ra.idx), ra.phase ^ 1u);
+              if (arm) mbar_expect_tx(a_full(ra.idx), CG * Cfg::kATx);
+              const uint32_t bar = a_full_dst0 + 8u * ra.idx, dst = smem_a0 + ra.idx * Cfg::kASlot;
               if (CG == 2) {
-                if (is_leader) mbar_expect_tx(a_full(sa), 2 * Cfg::kATx);
-                tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot, cb * kBlockK,
-                                 w0 * p.stride + dw, h0 * p.stride + dh, n0);
+                tma_load_4d_pair(&p.src[s], bar, dst, cb * kBlockK, w0 * p.stride + dw, h0 * p.stride + dh, n0);
                 if (MT == 2)
-                  tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot + Cfg::kASub,
-                                   cb * kBlockK, w1 * p.stride + dw, h1 * p.stride + dh, n1);
-              } else {  // single CTA, or XF: each CTA's own transform warps wait for its own bytes
-                mbar_expect_tx(a_full(sa), Cfg::kATx);
-                tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot, cb * kBlockK, w0 * p.stride + dw,
-                            h0 * p.stride + dh, n0);
+                  tma_load_4d_pair(&p.src[s], bar, dst + Cfg::kASub, cb * kBlockK, w1 * p.stride + dw,
+                                   h1 * p.stride + dh, n1);
+              } else {
+                tma_load_4d(&p.src[s], bar, dst, cb * kBlockK, w0 * p.stride + dw, h0 * p.stride + dh, n0);
                 if (MT == 2)
-                  tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot + Cfg::kASub, cb * kBlockK,
-                              w1 * p.stride + dw, h1 * p.stride + dh, n1);
+                  tma_load_4d(&p.src[s], bar, dst + Cfg::kASub, cb * kBlockK, w1 * p.stride + dw, h1 * p.stride + dh,
+                              n1);
               }
-              for (int bs = 0; bs < bsteps; ++bs, ++ib) {
-                const int tap = (MODE == 1) ? (taps == 9 ? as * 3 + bs : 0) : as;
-                const int sb = ib % Cfg::kBStages;
-                mbar_wait(b_empty(sb), ((ib / Cfg::kBStages) & 1) ^ 1u);
-                if (CG == 2) {
-                  if (is_leader) mbar_expect_tx(b_full(sb), 2 * Cfg::kBBytes);
-                  tma_load_2d_pair(&p.wgt, mapa_shared(b_full(sb), 0), smem_b0 + sb * Cfg::kBBytes,
-                                   p.seg_koff[s] + tap * C + cb * kBlockK, ncol0 + (int)cta_rank * (BLOCK_N / 2));
-                } else {
-                  mbar_expect_tx(b_full(sb), Cfg::kBBytes);
-                  tma_load_2d(&p.wgt, b_full(sb), smem_b0 + sb * Cfg::kBBytes,
-                              p.seg_koff[s] + tap * C + cb * kBlockK, ncol0);
-                }
+              ra.advance(Cfg::kAStages);
+              // weight tiles of this A step: MODE 1 -> the three kw taps of row kh = as; MODE 0 -> tap = as
+              int kcol = p.seg_koff[s] + ((MODE == 1) ? as * 3 : as) * C + cb * kBlockK;
+              for (int bs = 0; bs < bsteps; ++bs, kcol += C) {
+                mbar_wait(b_empty(rb.idx), rb.phase ^ 1u);
+                if (arm) mbar_expect_tx(b_full(rb.idx), CG * Cfg::kBBytes);
+                if (CG == 2)
+                  tma_load_2d_pair(&p.wgt, b_full_dst0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kcol, bcol);
+                else
+                  tma_load_2d(&p.wgt, b_full_dst0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kcol, bcol);
+                rb.advance(Cfg::kBStages);
               }
             }
+            // next A step: MODE 1 walks kh (dh), MODE 0 walks the nine taps row-major
+            if (MODE == 1) { ++dh; }
+            else if (taps == 9) { if (++dw == 2) { dw = -1; ++dh; } }
           }
         }
       }
     }
   } else if (warp == 1 && is_leader) {
     // ================= MMA issuer =================
+    // One thread feeds the tensor core(s); the body per weight tile stays at a few dozen instructions (ring cursors
+    // instead of divisions, descriptors advanced by adding to their lower word) - measured: the longer form made the
+    // issuing thread, not the tensor pipe, the pacer of 128-column tiles.
     constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM * CG, BLOCK_N);
     if (elect_one_sync()) {
-      int ia = 0, ib = 0, it = 0;
+      StageRing ra, rb;
+      const uint32_t a_lo0 = desc_lo_sw128(smem_a0), b_lo0 = desc_lo_sw128(smem_b0);
+      int it = 0;
       for (int unit = first_unit; unit < total_units; unit += unit_stride, ++it) {
         const int buf = it & 1;
         mbar_wait(t_empty(buf), ((it >> 1) & 1) ^ 1u);  // epilogue(s) drained this accumulator buffer
@@ -569,33 +574,37 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
           const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
           const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
-          for (int as = 0; as < asteps; ++as) {
-            for (int cb = 0; cb < cblocks; ++cb, ++ia) {
-              const int sa = ia % Cfg::kAStages;
-              mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
-              for (int bs = 0; bs < bsteps; ++bs, ++ib) {
-                const int sb = ib % Cfg::kBStages;
-                mbar_wait(b_full(sb), (ib / Cfg::kBStages) & 1);
-                tc_fence_after();
-                const int a_row = (MODE == 1) ? (taps == 9 ? bs : 1) : 0;
-                const uint32_t a_addr = smem_a0 + sa * Cfg::kASlot + a_row * kARowBytes;
-                const uint32_t b_addr = smem_b0 + sb * Cfg::kBBytes;
+          // MODE 1: tap kw reads the halo row starting kw pixels in (a 1x1 segment reads the centre, kw = 1)
+          const uint32_t a_row0 = (MODE == 1 && taps != 9) ? (uint32_t)(kARowBytes >> 4) : 0u;
+          for (int ac = 0; ac < asteps * cblocks; ++ac) {
+            mbar_wait(a_full(ra.idx), ra.phase);
+            uint32_t a_lo = a_lo0 + ra.idx * (uint32_t)(Cfg::kASlot >> 4) + a_row0;
+            for (int bs = 0; bs < bsteps; ++bs, a_lo += (uint32_t)(kARowBytes >> 4)) {
+              mbar_wait(b_full(rb.idx), rb.phase);
+              tc_fence_after();
+              const uint32_t b_lo = b_lo0 + rb.idx * (uint32_t)(Cfg::kBBytes >> 4);
 #pragma unroll
-                for (int sub = 0; sub < MT; ++sub) {
-#pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t da = make_sw128_kmajor_desc(a_addr + sub * Cfg::kASub + k * 32);
-                    const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
-                    const uint32_t acc = accumulate | (uint32_t)(k > 0);  // first k-step of a unit overwrites
-                    if (CG == 2) umma_bf16_ss_pair(tmem_d + sub * BLOCK_N, da, db, idesc, acc);
-                    else umma_bf16_ss(tmem_d + sub * BLOCK_N, da, db, idesc, acc);
-                  }
+              for (int sub = 0; sub < MT; ++sub) {
+                const uint32_t al = a_lo + (uint32_t)(sub * (Cfg::kASub >> 4));
+                const uint32_t td = tmem_d + (uint32_t)(sub * BLOCK_N);
+                if (CG == 2) {
+                  umma_bf16_ss_pair_lh(td, al, b_lo, idesc, accumulate);  // first k-step of a unit overwrites
+                  umma_bf16_ss_pair_lh(td, al + 2, b_lo + 2, idesc, 1u);
+                  umma_bf16_ss_pair_lh(td, al + 4, b_lo + 4, idesc, 1u);
+                  umma_bf16_ss_pair_lh(td, al + 6, b_lo + 6, idesc, 1u);
+                } else {
+                  umma_bf16_ss_lh(td, al, b_lo, idesc, accumulate);
+                  umma_bf16_ss_lh(td, al + 2, b_lo + 2, idesc, 1u);
+                  umma_bf16_ss_lh(td, al + 4, b_lo + 4, idesc, 1u);
+                  umma_bf16_ss_lh(td, al + 6, b_lo + 6, idesc, 1u);
                 }
-                accumulate = 1;
-                if (CG == 2) umma_commit_pair(b_empty(sb)); else umma_commit(b_empty(sb));
               }
-              if (CG == 2) umma_commit_pair(a_empty(sa)); else umma_commit(a_empty(sa));
+              accumulate = 1;
+              if (CG == 2) umma_commit_pair(b_empty(rb.idx)); else umma_commit(b_empty(rb.idx));
+              rb.advance(Cfg::kBStages);
             }
+            if (CG == 2) umma_commit_pair(a_empty(ra.idx)); else umma_commit(a_empty(ra.idx));
+            ra.advance(Cfg::kAStages);
           }
         }
         if (CG == 2) umma_commit_pair(t_full(buf)); else umma_commit(t_full(buf));

@@ -3,6 +3,8 @@
 // bandwidth kernels on CUDA cores.  The stem also absorbs the torch.cat([x, cond], 1) of the sampling loop
 // (src/pipelines/utils.py:204-205), the optional 2x-1 centering (unet_diffusers_nd.py:155-157), the fp32->bf16
 // cast and the NCHW->NHWC layout change; the head emits the fp32 NCHW prediction the scheduler step consumes.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fm {
@@ -191,6 +193,129 @@ __global__ void __launch_bounds__(kHeadThreads) conv_head_kernel(const uint4* __
   }
 }
 
+
+// Head, Cout = 1, Cin in {64, 128}: "dot-then-gather".  Phase 1: every input pixel of the (16+2) x (64+2) halo tile is
+// read ONCE, straight from global memory into registers (LPP lanes per pixel, 16 bytes each, coalesced), passed through
+// the fused output norm (act(a*x+b)) and dotted with the nine per-tap weight vectors, which live in registers for the
+// whole kernel (72 floats per lane); the nine partial sums are reduced across the LPP lanes with a recursive-halving
+// butterfly and parked in shared memory (36 bytes per pixel instead of 2*Cin).  Phase 2: out(h, w) = bias +
+// sum over taps of P[h+kh][w+kw][tap], nine conflict-free shared loads per output pixel.  Against the tile-staging
+// kernel above this removes the 9x re-read of the activations from shared memory.
+constexpr int kHd2TH = 16, kHd2TW = 64, kHd2Threads = 256;
+constexpr int kHd2Pix = (kHd2TH + 2) * (kHd2TW + 2);
+
+template <int LPP>
+__global__ void __launch_bounds__(kHd2Threads, 2) conv_head_dot_kernel(const uint4* __restrict__ x,
+                                                                      const float* __restrict__ w_oihw,
+                                                                      const float* __restrict__ bias,
+                                                                      float* __restrict__ out, int H, int W,
+                                                                      const float* __restrict__ norm_ab,
+                                                                      int norm_act) {
+  constexpr int C = LPP * 8;
+  constexpr int PPW = 32 / LPP;  // pixels per warp iteration
+  __shared__ float P[kHd2Pix * 9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c8 = lane % LPP, sub = lane / LPP;
+  const int w0 = blockIdx.x * kHd2TW, h0 = blockIdx.y * kHd2TH, n = blockIdx.z;
+
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(w_oihw + (c8 * 8 + j) * 9 + t);
+  float a[8], b[8];
+  const bool has_norm = norm_ab != nullptr;
+  const bool silu = has_norm && norm_act != 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float k = silu ? 0.5f : 1.0f;
+    a[j] = has_norm ? k * __ldg(norm_ab + (size_t)n * 2 * C + c8 * 8 + j) : 1.0f;
+    b[j] = has_norm ? k * __ldg(norm_ab + (size_t)n * 2 * C + C + c8 * 8 + j) : 0.0f;
+  }
+
+  constexpr int kWP = kHd2TW + 2;
+  constexpr int kPixPerIter = (kHd2Threads / 32) * PPW;
+  constexpr int kIters = (kHd2Pix + kPixPerIter - 1) / kPixPerIter;
+  constexpr int kUnroll = 4;  // independent 16-byte loads in flight per lane
+  for (int it0 = 0; it0 < kIters; it0 += kUnroll) {
+    uint4 v[kUnroll];
+    bool inb[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pi = (it0 + u) * kPixPerIter + warp * PPW + sub;
+      const int ph = pi / kWP, pw = pi - ph * kWP;
+      const int ih = h0 + ph - 1, iw = w0 + pw - 1;
+      inb[u] = pi < kHd2Pix && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (inb[u]) v[u] = __ldg(x + (((size_t)n * H + ih) * W + iw) * LPP + c8);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pi = (it0 + u) * kPixPerIter + warp * PPW + sub;
+      if ((it0 + u) * kPixPerIter + warp * PPW >= kHd2Pix) break;  // warp-uniform
+      const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float xv[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float h0v = fmaf(__uint_as_float(wd[j] << 16), a[2 * j], b[2 * j]);
+        float h1v = fmaf(__uint_as_float(wd[j] & 0xffff0000u), a[2 * j + 1], b[2 * j + 1]);
+        if (silu) {
+          float t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0v));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1v));
+          h0v = fmaf(h0v, t0, h0v);
+          h1v = fmaf(h1v, t1, h1v);
+        }
+        // zero padding applies AFTER the activation: an out-of-image pixel contributes nothing
+        xv[2 * j] = inb[u] ? h0v : 0.f;
+        xv[2 * j + 1] = inb[u] ? h1v : 0.f;
+      }
+      float red[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float acc = xv[0] * wr[t][0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc = fmaf(xv[j], wr[t][j], acc);
+        red[t] = acc;
+      }
+      // recursive halving over the top three lane bits of the pixel's lane group: 8 values -> 1 per lane
+#pragma unroll
+      for (int width = 4, mask = LPP / 2; width >= 1; width >>= 1, mask >>= 1) {
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < width; ++i) {
+          const float keep = upper ? red[i + width] : red[i];
+          const float give = upper ? red[i] : red[i + width];
+          red[i] = keep + __shfl_xor_sync(0xffffffffu, give, mask);
+        }
+      }
+#pragma unroll
+      for (int mask = LPP / 16; mask >= 1; mask >>= 1) red[0] += __shfl_xor_sync(0xffffffffu, red[0], mask);
+#pragma unroll
+      for (int mask = LPP / 2; mask >= 1; mask >>= 1) red[8] += __shfl_xor_sync(0xffffffffu, red[8], mask);
+      if (pi < kHd2Pix) {
+        const int hi = c8 / (LPP / 8);  // the three halving bits: tap index 4*b2 + 2*b1 + b0
+        const int tap = ((hi >> 2) & 1) * 4 + ((hi >> 1) & 1) * 2 + (hi & 1);
+        if (c8 % (LPP / 8) == 0) P[pi * 9 + tap] = red[0];
+        if (c8 == 0) P[pi * 9 + 8] = red[8];
+      }
+    }
+  }
+  __syncthreads();
+  const float bv = bias ? __ldg(bias) : 0.f;
+  for (int o = threadIdx.x; o < kHd2TH * kHd2TW; o += kHd2Threads) {
+    const int ty = o / kHd2TW, tx = o - ty * kHd2TW;
+    const int oh = h0 + ty, ow = w0 + tx;
+    if (oh >= H || ow >= W) continue;
+    float acc = bv;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) acc += P[((ty + kh) * kWP + tx + kw) * 9 + kh * 3 + kw];
+    out[((size_t)n * H + oh) * W + ow] = acc;
+  }
+}
+
 }  // namespace fm
 
 using namespace fm;
@@ -229,6 +354,17 @@ extern "C" int fm_conv_head_bf16_f32(const void* x, const float* weight_oihw, co
   FM_REQUIRE(Cin > 0 && Cin % 8 == 0, "conv_head: Cin=%d must be a multiple of 8", Cin);
   FM_REQUIRE(Cout >= 1 && Cout <= 4, "conv_head: Cout=%d must be in 1..4", Cout);
   FM_REQUIRE(B <= 65535, "conv_head: batch too large for the grid");
+  if (Cout == 1 && (Cin == 64 || Cin == 128) && getenv("FMDM_HEAD_TILE") == nullptr) {
+    dim3 grid2((W + kHd2TW - 1) / kHd2TW, (H + kHd2TH - 1) / kHd2TH, B);
+    if (Cin == 64)
+      conv_head_dot_kernel<8><<<grid2, kHd2Threads, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const uint4*>(x), weight_oihw, bias, out, H, W, norm_ab, norm_act);
+    else
+      conv_head_dot_kernel<16><<<grid2, kHd2Threads, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const uint4*>(x), weight_oihw, bias, out, H, W, norm_ab, norm_act);
+    FM_LAUNCH_CHECK("conv_head_dot_kernel");
+    return 0;
+  }
   const size_t wbytes = ((size_t)9 * Cin * Cout * sizeof(float) + 15) & ~(size_t)15;
   const size_t smem =
       wbytes + (size_t)2 * Cin * sizeof(float) + (size_t)(kHeadTH + 2) * (kHeadTW + 2) * (Cin * 2 + 16);

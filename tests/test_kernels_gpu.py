@@ -365,3 +365,27 @@ def test_group_norm_table_and_head():
     out = ops.conv_head(_nhwc(x), wh, bh, norm=tab)
     ref = F.conv2d(F.silu(F.group_norm(x, 32, gamma, beta, 1e-5)), wh, bh, padding=1)
     assert _rel_l2(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("cin,H,W,norm", [(128, 40, 36, False), (64, 17, 130, True), (128, 33, 200, True),
+                                          (128, 16, 64, True), (64, 1, 5, False)])
+def test_conv_head_dot_kernel(cin, H, W, norm):
+    """Cout = 1 head (dot-then-gather kernel) with and without the fused output norm, ragged tiles included."""
+    g = torch.Generator().manual_seed(7)
+    B = 3
+    x = _bf16r(torch.randn(B, cin, H, W, generator=g) * 1.3 + 0.2).to(DEV)
+    wh = (torch.randn(1, cin, 3, 3, generator=g) / 20).to(DEV)
+    bh = torch.randn(1, generator=g).to(DEV)
+    tab = None
+    y = x
+    if norm:
+        ab = torch.empty(B, 2, cin)
+        ab[:, 0] = torch.rand(B, cin, generator=g) + 0.5
+        ab[:, 1] = torch.randn(B, cin, generator=g) * 0.5
+        ab = ab.to(DEV)
+        tab = ops.NormTable(ab, True)
+        y = F.silu(x * ab[:, 0, :, None, None] + ab[:, 1, :, None, None])
+    ref = F.conv2d(y, wh, bh, padding=1)
+    out = ops.conv_head(_nhwc(x), wh, bh, norm=tab)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert _rel_l2(out, ref) < (2e-3 if norm else 1e-4)
