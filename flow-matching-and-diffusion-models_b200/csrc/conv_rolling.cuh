@@ -10,7 +10,11 @@
 // traffic from L2 and - the point - the number of times an input element passes the operand transform by 3x, so the
 // fused GroupNorm-apply + SiLU (XF) needs one pass per element and its four transform warps keep up with the MMAs.
 //
-// Warp roles: 0 TMA producer, 1 MMA issuer (leader CTA), 2..9 epilogue, 10..13 operand transform (XF only).
+// Warp roles: 0 weight (B) TMA producer, 1 MMA issuer (leader CTA), 2..9 epilogue, 10..13 operand transform (XF only),
+// last warp: activation (A) TMA producer.  A and B have separate producer threads because one in-order thread cannot
+// run the A loads further ahead than its B ring allows (11 tiles ~ 1.2 input rows); with the operand transform between
+// the TMA landing and the MMA, A needs the deeper prefetch (measured: the MMA issuer waited on a_ready while the
+// transform warps idled on a_full).
 #pragma once
 
 namespace fm {
@@ -73,7 +77,7 @@ struct RollSched {
 };
 
 template <int BLOCK_N, int XF>
-__global__ void __launch_bounds__(kPConvThreads + XF * kXfThreads, 1)
+__global__ void __launch_bounds__(kPConvThreads + XF * kXfThreads + 32, 1)
 conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched sch) {
   using Cfg = RConvCfg<BLOCK_N, XF>;
   const uint32_t cta_rank = cluster_ctarank();
@@ -149,10 +153,10 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
   };
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= weight (B) TMA producer =================
     if (elect_one_sync()) {
-      StageRing ra, rb;
-      const uint32_t a_full_leader0 = mapa_shared(a_full(0), 0), b_full_leader0 = mapa_shared(b_full(0), 0);
+      StageRing rb;
+      const uint32_t b_full_leader0 = mapa_shared(b_full(0), 0);
       const int bcol_off = (int)cta_rank * (BLOCK_N / 2);
       for (int unit = first_unit; unit < total_units; unit += unit_stride) {
         int tw, w0, n, h_begin, h_end, ncol0;
@@ -168,6 +172,31 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
             const int cblocks = (C + kBlockK - 1) / kBlockK;
             const int t_lo = (taps == 9) ? kh_lo * 3 : 0, t_n = (taps == 9) ? (kh_hi - kh_lo + 1) * 3 : 1;
             for (int cb = 0; cb < cblocks; ++cb) {
+              int kcol = p.seg_koff[s] + t_lo * C + cb * kBlockK;
+              for (int t = 0; t < t_n; ++t, kcol += C) {
+                mbar_wait(b_empty(rb.idx), rb.phase ^ 1u);
+                if (is_leader) mbar_expect_tx(b_full(rb.idx), 2 * Cfg::kBBytes);
+                tma_load_2d_pair(&p.wgt, b_full_leader0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kcol, bcol);
+                rb.advance(Cfg::kBStages);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2 + kEpiWarps + XF * kXfWarps) {
+    // ================= activation (A) TMA producer: one 130-pixel halo row of 64 channels per slot =================
+    if (elect_one_sync()) {
+      StageRing ra;
+      const uint32_t a_full_leader0 = mapa_shared(a_full(0), 0);
+      for (int unit = first_unit; unit < total_units; unit += unit_stride) {
+        int tw, w0, n, h_begin, h_end, ncol0;
+        strip_coords(unit, tw, w0, n, h_begin, h_end, ncol0);
+        for (int r = h_begin - 1; r <= h_end; ++r) {
+          for (int s = 0; s < p.nseg; ++s) {
+            if (p.seg_taps[s] == 1 && (r < h_begin || r >= h_end)) continue;
+            const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
+            for (int cb = 0; cb < cblocks; ++cb) {
               mbar_wait(a_empty(ra.idx), ra.phase ^ 1u);
               if (XF) {  // each CTA's transform warps wait for their own bytes
                 mbar_expect_tx(a_full(ra.idx), Cfg::kATx);
@@ -178,13 +207,6 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
                                  cb * kBlockK, w0 - 1, r, n);
               }
               ra.advance(Cfg::kAStages);
-              int kcol = p.seg_koff[s] + t_lo * C + cb * kBlockK;
-              for (int t = 0; t < t_n; ++t, kcol += C) {
-                mbar_wait(b_empty(rb.idx), rb.phase ^ 1u);
-                if (is_leader) mbar_expect_tx(b_full(rb.idx), 2 * Cfg::kBBytes);
-                tma_load_2d_pair(&p.wgt, b_full_leader0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kcol, bcol);
-                rb.advance(Cfg::kBStages);
-              }
             }
           }
         }
@@ -252,7 +274,7 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
       }
     }
   } else if (XF && warp >= 2 + kEpiWarps) {
-    // ================= operand transform =================
+    // ================= operand transform (warps 10..13) =================
     const int tt = (int)threadIdx.x - (64 + kEpiThreads);
     const int lc = tt & 7;   // this thread's 8-channel chunk of the 64-channel block
     const int r0 = tt >> 3;  // first slot row, step 16
@@ -529,7 +551,7 @@ static int launch_conv_rolling(const ConvKernelParams& kp, const RollSched& sch,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas);
-  cfg.blockDim = dim3(kPConvThreads + XF * kXfThreads);
+  cfg.blockDim = dim3(kPConvThreads + XF * kXfThreads + 32);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -223,8 +223,10 @@ def conv2d(
     return out
 
 
-def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0) -> torch.Tensor:
-    """fp32 NCHW (x0 [, x1]) -> bf16 NHWC, 3x3 s1 p1; fuses the conditioning concat and the 2x-1 centering."""
+def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0, want_stats: bool = True) -> torch.Tensor:
+    """fp32 NCHW (x0 [, x1]) -> bf16 NHWC, 3x3 s1 p1; fuses the conditioning concat and the 2x-1 centering.
+
+    want_stats: also emit the GroupNorm partial statistics of the output (`out._fm_stats`, as `conv2d` does)."""
     lib = _lib.lib()
     require_cuda(x0, "conv_stem")
     x0 = x0.to(torch.float32).contiguous()
@@ -235,15 +237,22 @@ def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0) -> torch
         c1 = x1.shape[1]
     cout = weight_oihw.shape[0]
     out = empty_nhwc(b, cout, h, w, x0.device)
+    stats_ws, rows = None, 0
+    if want_stats and cout % 8 == 0:
+        rows = int(lib.fm_conv_stem_stats_rows(b, h, w, cout))
+        if rows > 0:
+            stats_ws = torch.empty((b * rows, cout // 4, 2), dtype=torch.float32, device=x0.device)
     e0 = _prof_begin()
     _lib.check(
         lib.fm_conv_stem_f32_bf16(
             x0.data_ptr(), c0, _ptr(x1), c1, float(in_scale), float(in_shift), weight_oihw.data_ptr(), _ptr(bias),
-            out.data_ptr(), b, h, w, cout, _stream(),
+            out.data_ptr(), b, h, w, cout, _ptr(stats_ws), _stream(),
         ),
         "conv_stem",
     )
     _prof_end("conv_stem", 2.0 * b * h * w * (c0 + c1) * 9 * cout, e0)
+    if stats_ws is not None:
+        out._fm_stats = (stats_ws, rows)
     return out
 
 

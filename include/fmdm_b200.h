@@ -106,10 +106,14 @@ int fm_weight_prepack_bf16(void* dst, int64_t dst_row_stride, int64_t koff, cons
                            int32_t Cin_total, int32_t c_begin, int32_t Cseg, int32_t ksize, fm_stream_t stream);
 
 /* Stem conv (tiny Cin): fp32 NCHW inputs (x and optional concatenated conditioning, src/pipelines/utils.py:204-205,
- * unet_diffusers_nd.py:148-158,173) -> bf16 NHWC.  3x3, stride 1, pad 1.  weight fp32 OIHW, bias fp32. */
+ * unet_diffusers_nd.py:148-158,173) -> bf16 NHWC.  3x3, stride 1, pad 1.  weight fp32 OIHW, bias fp32.
+ * gn_stats (or NULL): fp32 [B * fm_conv_stem_stats_rows(...)][Cout/4][2] receiving the channel-quad (sum, sumsq)
+ * partials of the output for the consumer GroupNorm (same format as fm_conv_params.gn_stats). */
 int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale, float in_shift,
                           const float* weight_oihw, const float* bias, void* out_nhwc_bf16, int32_t B, int32_t H,
-                          int32_t W, int32_t Cout, fm_stream_t stream);
+                          int32_t W, int32_t Cout, float* gn_stats, fm_stream_t stream);
+/* rows of statistics partials per image the stem kernel writes for this problem size (0 = unsupported) */
+int fm_conv_stem_stats_rows(int32_t B, int32_t H, int32_t W, int32_t Cout);
 
 /* Head conv (tiny Cout): bf16 NHWC -> fp32 NCHW (unet_diffusers_nd.py:190, unet.py:288-292). 3x3 s1 p1.
  * norm_ab != NULL ([B][2][Cin], fm_groupnorm_affine_f32): the input is read as SiLU(a*x+b) (norm_act=1) or a*x+b,

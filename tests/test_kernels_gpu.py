@@ -389,3 +389,21 @@ def test_conv_head_dot_kernel(cin, H, W, norm):
     out = ops.conv_head(_nhwc(x), wh, bh, norm=tab)
     assert out.shape == ref.shape and out.dtype == torch.float32
     assert _rel_l2(out, ref) < (2e-3 if norm else 1e-4)
+
+
+def test_stem_fused_groupnorm_statistics():
+    """GroupNorm table from the stem kernel's partial statistics == table from a statistics pass over its output."""
+    g = torch.Generator().manual_seed(12)
+    for (B, H, W, cout) in [(2, 40, 36, 128), (3, 17, 130, 64), (1, 128, 128, 128)]:
+        x0 = torch.randn(B, 1, H, W, generator=g).to(DEV)
+        x1 = torch.rand(B, 1, H, W, generator=g).to(DEV)
+        w = (torch.randn(cout, 2, 3, 3, generator=g) / 4).to(DEV)
+        b = torch.randn(cout, generator=g).to(DEV)
+        y = ops.conv_stem(x0, x1, w, b)
+        assert hasattr(y, "_fm_stats")
+        gamma = torch.randn(cout, generator=g).to(DEV)
+        beta = torch.randn(cout, generator=g).to(DEV)
+        t_fused = ops.group_norm_table([y], 32, 1e-5, gamma, beta, silu=True)
+        t_plain = ops.group_norm_table([y.clone(memory_format=torch.preserve_format)], 32, 1e-5, gamma, beta, silu=True)
+        # the fused statistics see the fp32 accumulators, the plain pass their bf16 rounding
+        assert float((t_fused.ab - t_plain.ab).abs().max()) < 5e-3 * float(t_plain.ab.abs().max())

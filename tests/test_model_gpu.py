@@ -113,6 +113,7 @@ def test_attention_blocks():
     ("mnist28_uncond", MNIST_UNET, None, 28, 4),
     ("mnist32_concat", MNIST_UNET, "concatenate", 32, 3),
     ("ldct64_concat", LDCT_SMALL, "concatenate", 64, 2),
+    ("ldct160_concat", LDCT_SMALL, "concatenate", 160, 1),  # rows >= 65 px: rolling-row convs with the fused GroupNorm
     ("compvis32_concat", COMPVIS_SMALL, "concatenate", 32, 2),
 ])
 def test_denoiser_forward_parity(name, cfg, cond, hw, B):
