@@ -13,19 +13,16 @@ constexpr int kStemMaxCin = 8;
 constexpr int kStemThreads = 256;
 constexpr int kStemPix = 4;
 
-// One thread = 16 output channels x kStemPix consecutive pixels of a row.  The 32 lanes of a warp hold 32 consecutive
-// pixel groups of the SAME 16-channel block, so every weight fetch from shared memory ([ci*9+tap][co]) is a broadcast
-// (one wavefront; with lanes spread over channels the kernel was shared-memory-wavefront bound) and every store is a
-// whole 32-byte sector.  A block works on ONE image (grid.y), so the optional GroupNorm partial statistics of the
-// output (sum, sum of squares per channel quad, one row per block: stats[(n*gridDim.x + block)][Cout/4][2]) need no
-// atomics.
+// One thread = 8 output channels x kStemPix consecutive pixels of a row; weights live in shared memory as
+// [ci*9+tap][co]; a block works on ONE image (grid.y), so the optional GroupNorm partial statistics of the output
+// (sum, sum of squares per channel quad, one row per block: stats[(n*gridDim.x + block)][Cout/4][2]) need no atomics.
 __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __restrict__ x0, int C0,
                                                                 const float* __restrict__ x1, int C1,
                                                                 float in_scale, float in_shift,
                                                                 const float* __restrict__ w_oihw,
                                                                 const float* __restrict__ bias,
-                                                                __nv_bfloat16* __restrict__ out, int H, int W,
-                                                                int Cout, float* __restrict__ stats) {
+                                                                uint4* __restrict__ out, int H, int W, int Cout,
+                                                                float* __restrict__ stats) {
   extern __shared__ float sw[];  // [Cin*9][Cout] + bias[Cout] (+ statistics scratch, reusing the weights at the end)
   const int Cin = C0 + C1;
   const int K = Cin * 9;
@@ -37,36 +34,30 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sbias[i] = bias ? bias[i] : 0.f;
   __syncthreads();
 
-  constexpr int kWarps = kStemThreads / 32;
-  const int nblk = Cout >> 4;                       // 16-channel blocks
-  int wps = 1;                                      // warps per pixel-group set: largest power of two <= min(8, nblk)
-  while (wps * 2 <= nblk && wps * 2 <= kWarps) wps *= 2;
-  const int sets = kWarps / wps;                    // pixel-group sets (of 32 groups) per block iteration
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int set = warp / wps, wis = warp % wps;
+  const int chunks = Cout >> 3;
+  const int gpb = kStemThreads / chunks;  // pixel groups per block iteration
+  const int c8 = threadIdx.x % chunks;
+  const int gl = threadIdx.x / chunks;
   const int n = blockIdx.y;
   const int HW = H * W;
   const int WG = (W + kStemPix - 1) / kStemPix;
   const int groups_per_img = H * WG;
-  const int nq = Cout >> 2;
-
-  for (int cbk = wis; cbk < nblk; cbk += wps) {
-    float bi[16];
+  float bi[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) bi[j] = sbias[cbk * 16 + j];
-    float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};  // this thread's four channel quads
-    for (int g0 = (blockIdx.x * sets + set) * 32; g0 < groups_per_img; g0 += gridDim.x * sets * 32) {
-      const int grp = g0 + lane;
-      const bool live = grp < groups_per_img;
-      const int h = live ? grp / WG : 0;
-      const int wbase = live ? (grp - h * WG) * kStemPix : 0;
-      float acc[kStemPix][16];
+  for (int j = 0; j < 8; ++j) bi[j] = sbias[c8 * 8 + j];
+  float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};  // this thread's two channel quads
+  if (gl < gpb) {
+    for (int grp = blockIdx.x * gpb + gl; grp < groups_per_img; grp += gridDim.x * gpb) {
+      const int h = grp / WG;
+      const int wbase = (grp - h * WG) * kStemPix;
+      float acc[kStemPix][8];
 #pragma unroll
       for (int p = 0; p < kStemPix; ++p)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[p][j] = bi[j];
+        for (int j = 0; j < 8; ++j) acc[p][j] = bi[j];
       for (int ci = 0; ci < Cin; ++ci) {
         const float* src = (ci < C0) ? x0 + ((size_t)n * C0 + ci) * HW : x1 + ((size_t)n * C1 + (ci - C0)) * HW;
+        // all 3 x (kStemPix+2) inputs of this channel first (one exposed memory latency per channel, not per row)
         float xin[3][kStemPix + 2];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
@@ -75,7 +66,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __
           for (int q = 0; q < kStemPix + 2; ++q) {
             const int iw = wbase + q - 1;
             // zero padding applies AFTER the optional 2x-1 centering (the reference centres, then convolves)
-            xin[kh][q] = (live && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+            xin[kh][q] = ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
                              ? fmaf(__ldg(src + ih * W + iw), in_scale, in_shift) : 0.f;
           }
         }
@@ -83,71 +74,56 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __
         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            const float* wp = sw + (ci * 9 + kh * 3 + kw) * Cout + cbk * 16;  // warp-uniform address: broadcast
+            const float* wp = sw + (ci * 9 + kh * 3 + kw) * Cout + c8 * 8;
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wp + j4 * 4);
-#pragma unroll
-              for (int p = 0; p < kStemPix; ++p) {
-                const float xv = xin[kh][p + kw];
-                acc[p][j4 * 4 + 0] = fmaf(xv, w4.x, acc[p][j4 * 4 + 0]);
-                acc[p][j4 * 4 + 1] = fmaf(xv, w4.y, acc[p][j4 * 4 + 1]);
-                acc[p][j4 * 4 + 2] = fmaf(xv, w4.z, acc[p][j4 * 4 + 2]);
-                acc[p][j4 * 4 + 3] = fmaf(xv, w4.w, acc[p][j4 * 4 + 3]);
-              }
+            for (int p = 0; p < kStemPix; ++p) {
+              const float xv = xin[kh][p + kw];
+              acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]);
+              acc[p][2] = fmaf(xv, w0.z, acc[p][2]); acc[p][3] = fmaf(xv, w0.w, acc[p][3]);
+              acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
+              acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
             }
           }
         }
       }
-      if (live) {
-        __nv_bfloat16* op = out + (((size_t)n * H + h) * W + wbase) * Cout + cbk * 16;
+      const size_t pix0 = ((size_t)n * H + h) * W + wbase;
 #pragma unroll
-        for (int p = 0; p < kStemPix; ++p) {
-          if (wbase + p < W) {
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(acc[p][0], acc[p][1]); o0.y = pack_bf16x2(acc[p][2], acc[p][3]);
-            o0.z = pack_bf16x2(acc[p][4], acc[p][5]); o0.w = pack_bf16x2(acc[p][6], acc[p][7]);
-            o1.x = pack_bf16x2(acc[p][8], acc[p][9]); o1.y = pack_bf16x2(acc[p][10], acc[p][11]);
-            o1.z = pack_bf16x2(acc[p][12], acc[p][13]); o1.w = pack_bf16x2(acc[p][14], acc[p][15]);
-            uint4* dst = reinterpret_cast<uint4*>(op + (size_t)p * Cout);
-            dst[0] = o0;
-            dst[1] = o1;
-            if (stats != nullptr) {
+      for (int p = 0; p < kStemPix; ++p) {
+        if (wbase + p < W) {
+          uint4 o;
+          o.x = pack_bf16x2(acc[p][0], acc[p][1]); o.y = pack_bf16x2(acc[p][2], acc[p][3]);
+          o.z = pack_bf16x2(acc[p][4], acc[p][5]); o.w = pack_bf16x2(acc[p][6], acc[p][7]);
+          out[(pix0 + p) * chunks + c8] = o;
+          if (stats != nullptr) {
 #pragma unroll
-              for (int hq = 0; hq < 4; ++hq) {
-                const float a0 = acc[p][4 * hq], a1 = acc[p][4 * hq + 1], a2 = acc[p][4 * hq + 2],
-                            a3 = acc[p][4 * hq + 3];
-                st_s[hq] += (a0 + a1) + (a2 + a3);
-                st_q[hq] += fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
-              }
+            for (int hq = 0; hq < 2; ++hq) {
+              const float a0 = acc[p][4 * hq], a1 = acc[p][4 * hq + 1], a2 = acc[p][4 * hq + 2], a3 = acc[p][4 * hq + 3];
+              st_s[hq] += (a0 + a1) + (a2 + a3);
+              st_q[hq] += fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
             }
           }
-        }
-      }
-    }
-    if (stats != nullptr) {
-      // lanes hold the same channels: fixed-order butterfly, then one slot per (set, quad) in shared memory
-#pragma unroll
-      for (int hq = 0; hq < 4; ++hq) {
-        st_s[hq] = warp_sum(st_s[hq]);
-        st_q[hq] = warp_sum(st_q[hq]);
-      }
-      if (lane == 0) {
-        float* red = sw + K * Cout + Cout;  // [sets][nq][2], behind the weights and the bias
-#pragma unroll
-        for (int hq = 0; hq < 4; ++hq) {
-          red[((set * nq) + cbk * 4 + hq) * 2 + 0] = st_s[hq];
-          red[((set * nq) + cbk * 4 + hq) * 2 + 1] = st_q[hq];
         }
       }
     }
   }
   if (stats == nullptr) return;
+  // fold the block's threads per channel quad in a fixed order (deterministic), one row of partials per block
+  __syncthreads();           // the weights in shared memory are no longer needed
+  float* red = sw;           // [gpb][chunks*2][2]
+  if (gl < gpb) {
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {
+      red[((gl * chunks + c8) * 2 + hq) * 2 + 0] = st_s[hq];
+      red[((gl * chunks + c8) * 2 + hq) * 2 + 1] = st_q[hq];
+    }
+  }
   __syncthreads();
-  const float* red = sw + K * Cout + Cout;
+  const int nq = Cout >> 2;
   for (int i = threadIdx.x; i < nq * 2; i += blockDim.x) {
     float t = 0.f;
-    for (int g = 0; g < sets; ++g) t += red[g * nq * 2 + i];
+    for (int g = 0; g < gpb; ++g) t += red[g * nq * 2 + i];
     stats[((size_t)n * gridDim.x + blockIdx.x) * nq * 2 + i] = t;
   }
 }
@@ -375,12 +351,9 @@ __global__ void __launch_bounds__(kHd2Threads, 2) conv_head_dot_kernel(const uin
 using namespace fm;
 
 static int stem_blocks_per_image(int B, int H, int W, int Cout) {
-  const int nblk = Cout / 16;
-  int wps = 1;
-  while (wps * 2 <= nblk && wps * 2 <= kStemThreads / 32) wps *= 2;
-  const int sets = (kStemThreads / 32) / wps;
+  const int gpb = kStemThreads / (Cout / 8);
   const int64_t groups = (int64_t)H * ((W + kStemPix - 1) / kStemPix);
-  int64_t bpi = (groups + sets * 32 - 1) / (sets * 32);
+  int64_t bpi = (groups + gpb - 1) / gpb;
   int64_t cap = ((int64_t)sm_count() * 8 + B - 1) / B;  // ~8 resident-CTA rounds' worth across the batch
   if (cap < 1) cap = 1;
   if (bpi > cap) bpi = cap;
@@ -388,7 +361,7 @@ static int stem_blocks_per_image(int B, int H, int W, int Cout) {
 }
 
 extern "C" int fm_conv_stem_stats_rows(int32_t B, int32_t H, int32_t W, int32_t Cout) {
-  if (B <= 0 || H <= 0 || W <= 0 || Cout <= 0 || Cout % 16 || Cout > 512) return 0;
+  if (B <= 0 || H <= 0 || W <= 0 || Cout <= 0 || Cout % 8 || Cout > 512) return 0;
   return stem_blocks_per_image(B, H, W, Cout);
 }
 
@@ -398,12 +371,13 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x0 && C0 > 0 && (x1 != nullptr) == (C1 > 0), "conv_stem: inconsistent sources");
   FM_REQUIRE(C0 + C1 <= kStemMaxCin, "conv_stem: Cin=%d exceeds %d", C0 + C1, kStemMaxCin);
-  FM_REQUIRE(Cout > 0 && Cout % 16 == 0 && Cout <= 512, "conv_stem: Cout=%d must be a multiple of 16 (<=512)", Cout);
+  FM_REQUIRE(Cout > 0 && Cout % 8 == 0 && Cout <= 512, "conv_stem: Cout=%d must be a multiple of 8 (<=512)", Cout);
   FM_REQUIRE(weight_oihw && out && B > 0 && H > 0 && W > 0, "conv_stem: bad argument");
   FM_REQUIRE((int64_t)H * W < (1ll << 31) && B <= 65535, "conv_stem: image too large for 32-bit indexing");
-  FM_REQUIRE(((uintptr_t)out & 15) == 0, "conv_stem: out must be 16B aligned");
-  // weights + bias + statistics scratch [sets <= 8][Cout/4][2]
-  const size_t smem = ((size_t)(C0 + C1) * 9 * Cout + Cout + 8 * (Cout / 4) * 2) * sizeof(float);
+  const int gpb = kStemThreads / (Cout / 8);
+  size_t smem = ((size_t)(C0 + C1) * 9 * Cout + Cout) * sizeof(float);
+  const size_t red_bytes = (size_t)gpb * (Cout / 4) * 2 * sizeof(float);
+  if (gn_stats != nullptr && red_bytes > smem) smem = red_bytes;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -412,8 +386,7 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
   }
   const int bpi = stem_blocks_per_image(B, H, W, Cout);
   conv_stem_kernel<<<dim3(bpi, B), kStemThreads, smem, (cudaStream_t)stream>>>(
-      x0, C0, x1, C1, in_scale, in_shift, weight_oihw, bias, reinterpret_cast<__nv_bfloat16*>(out), H, W, Cout,
-      gn_stats);
+      x0, C0, x1, C1, in_scale, in_shift, weight_oihw, bias, reinterpret_cast<uint4*>(out), H, W, Cout, gn_stats);
   FM_LAUNCH_CHECK("conv_stem_kernel");
   return 0;
 }

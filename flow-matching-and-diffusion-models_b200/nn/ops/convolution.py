@@ -66,7 +66,7 @@ class ConvND(nn.Module):
             if self.spatial_dims == 2 and _as_int(c.kernel_size) == 3 and _as_int(c.stride) == 1 \
                     and _as_int(c.padding) == 1 and c.groups == 1 and _as_int(c.dilation) == 1 \
                     and addvec is None and residual is None:
-                if c.in_channels <= 8 and c.out_channels % 16 == 0 and len(srcs) <= 2:
+                if c.in_channels <= 8 and c.out_channels % 8 == 0 and len(srcs) <= 2:
                     xs = [s.float() for s in srcs]
                     return ops.conv_stem(xs[0], xs[1] if len(xs) == 2 else None, f32(c.weight), f32(c.bias))
                 if c.out_channels <= 4 and c.in_channels % 8 == 0 and len(srcs) == 1:
