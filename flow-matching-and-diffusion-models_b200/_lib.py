@@ -67,7 +67,7 @@ SIGNATURES = {
         C.c_int,
         [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     ),
-    "fm_conv_stats_layout": (C.c_int, [_i32, _i32, _i32, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "fm_conv_stats_rows": (C.c_int, [C.POINTER(ConvParams), C.POINTER(C.c_int32)]),
     "fm_groupnorm_finalize_partials": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i64, _i32, _f32, _vp, _vp]),
     "fm_weight_prepack_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_conv_stem_f32_bf16": (

@@ -46,7 +46,6 @@ struct alignas(64) ConvKernelParams {
   const __nv_bfloat16* residual;
   float* gn_partial;                // [m_tiles*4][Cout/4][2] quad statistics, or null
   int log_wt, log_ht;               // Wt, Ht are powers of two
-  int desc_base_offset;             // row mode: encode the swizzle phase of row-shifted A views in the descriptor
   int num_k_blocks;
   int m_tiles, n_tiles;             // persistent kernel: real tile counts (M tiles padded to even for CTA pairs)
   // fused operand transform (XF kernels): per segment a*x+b table rows [B][.] and activation, or null
@@ -66,334 +65,13 @@ constexpr int kARowBytes = 128;
 constexpr int kARowSlot = 17 * 1024;  // 130 rows * 128 B = 16640 B, rounded up to keep every slot 1024 B aligned
 constexpr int kARowTx = 130 * 128;
 
-// CG = 2: a CTA pair (cluster of two) computes a 256-row tile with tcgen05.mma.cta_group::2; each CTA stages its own
-//         128 (130) A rows and HALF of the weight tile, so weight traffic from L2 per CTA halves and one MMA
-//         instruction covers twice the work (the single issuing thread of the leader CTA is no longer the pacer).
-template <int BLOCK_N, int MODE, int CG>
-struct ConvCfg {
-  static constexpr int kBBytes = (BLOCK_N / CG) * kBlockK * 2;  // per CTA
-  static constexpr int kASlot = (MODE == 1) ? kARowSlot : kABytes;
-  static constexpr int kATx = (MODE == 1) ? kARowTx : kABytes;
-  static constexpr int kAStages =
-      (CG == 2) ? ((MODE == 1) ? ((BLOCK_N == 256) ? 4 : 3) : ((BLOCK_N == 256) ? 6 : 4))
-                : ((MODE == 1) ? ((BLOCK_N == 256) ? 3 : 2) : ((BLOCK_N == 128) ? 3 : 4));
-  static constexpr int kBStages =
-      (CG == 2) ? ((MODE == 1) ? ((BLOCK_N == 256) ? 8 : 6) : kAStages)
-                : ((MODE == 1) ? ((BLOCK_N == 256) ? 5 : 4) : kAStages);
-  static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
-  static constexpr int kOutBytes = kTileM * BLOCK_N * 2;
-  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 1;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kPipeBytes + 256;
-  static_assert(kOutBytes <= kPipeBytes, "output staging reuses the pipeline buffers");
-  static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
-};
-
-template <int BLOCK_N, int MODE, int CG>
-__global__ void __launch_bounds__(kConvThreads, 1)
-conv_igemm_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N, MODE, CG>;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
-  const bool is_leader = (cta_rank == 0);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t smem_a0 = smem_base;
-  const uint32_t smem_b0 = smem_base + Cfg::kAStages * Cfg::kASlot;
-  const uint32_t bar_base = smem_base + Cfg::kPipeBytes;
-  // barriers: a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full; then the TMEM base address word
-  auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
-  auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (Cfg::kNumBars - 1);
-  const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
-  volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kPipeBytes + 8 * Cfg::kNumBars);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates ----
-  const int tiles_per_img_group = p.tiles_w * p.tiles_h;
-  const int m_tile = blockIdx.x;
-  const int tn = m_tile / tiles_per_img_group;
-  const int rem = m_tile - tn * tiles_per_img_group;
-  const int th = rem / p.tiles_w;
-  const int tw = rem - th * p.tiles_w;
-  const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt;
-  const int ncol0 = blockIdx.y * BLOCK_N;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.src[s]);
-    tma_prefetch_desc(&p.wgt);
-    tma_prefetch_desc(&p.out);
-  }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < Cfg::kNumBars; ++s) mbar_init(bar_base + 8u * s, 1);
-      fence_barrier_init();
-    }
-    __syncwarp();
-    if (CG == 2) tmem_alloc_pair<BLOCK_N>(tmem_slot); else tmem_alloc<BLOCK_N>(tmem_slot);
-  }
-  tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();  // pair: the peer's barriers must exist before remote arrivals
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  // K loop shape shared by the producer and the MMA issuer.  Per segment: `asteps` A loads per channel block
-  // (MODE 0: one per tap; MODE 1: one per kh), each feeding `bsteps` weight tiles (MODE 0: 1; MODE 1: the kw taps).
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (elect_one_sync()) {
-      int ia = 0, ib = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int taps = p.seg_taps[s];
-        const int C = p.seg_c[s];
-        const int cblocks = (C + kBlockK - 1) / kBlockK;
-        const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
-        const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
-        for (int as = 0; as < asteps; ++as) {
-          int dh, dw;
-          if (MODE == 1) { dh = (taps == 9) ? as - 1 : 0; dw = -1; }
-          else { dh = (taps == 9) ? (as / 3 - 1) : 0; dw = (taps == 9) ? (as % 3 - 1) : 0; }
-          for (int cb = 0; cb < cblocks; ++cb, ++ia) {
-            const int sa = ia % Cfg::kAStages;
-            mbar_wait(a_empty(sa), ((ia / Cfg::kAStages) & 1) ^ 1u);
-            if (CG == 2) {
-              // both CTAs' bytes land on the LEADER's full barrier; only the leader arms it (with the pair's total)
-              if (is_leader) mbar_expect_tx(a_full(sa), 2 * Cfg::kATx);
-              tma_load_4d_pair(&p.src[s], mapa_shared(a_full(sa), 0), smem_a0 + sa * Cfg::kASlot, cb * kBlockK,
-                               w0 * p.stride + dw, h0 * p.stride + dh, n0);
-            } else {
-              mbar_expect_tx(a_full(sa), Cfg::kATx);
-              tma_load_4d(&p.src[s], a_full(sa), smem_a0 + sa * Cfg::kASlot, cb * kBlockK, w0 * p.stride + dw,
-                          h0 * p.stride + dh, n0);
-            }
-            for (int bs = 0; bs < bsteps; ++bs, ++ib) {
-              const int tap = (MODE == 1) ? (taps == 9 ? as * 3 + bs : 0) : as;
-              const int sb = ib % Cfg::kBStages;
-              mbar_wait(b_empty(sb), ((ib / Cfg::kBStages) & 1) ^ 1u);
-              if (CG == 2) {
-                if (is_leader) mbar_expect_tx(b_full(sb), 2 * Cfg::kBBytes);
-                tma_load_2d_pair(&p.wgt, mapa_shared(b_full(sb), 0), smem_b0 + sb * Cfg::kBBytes,
-                                 p.seg_koff[s] + tap * C + cb * kBlockK, ncol0 + (int)cta_rank * (BLOCK_N / 2));
-              } else {
-                mbar_expect_tx(b_full(sb), Cfg::kBBytes);
-                tma_load_2d(&p.wgt, b_full(sb), smem_b0 + sb * Cfg::kBBytes, p.seg_koff[s] + tap * C + cb * kBlockK,
-                            ncol0);
-              }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1 && is_leader) {
-    // ================= MMA issuer (pair: leader CTA only) =================
-    constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM * CG, BLOCK_N);
-    int ia = 0, ib = 0;
-    uint32_t accumulate = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      const int taps = p.seg_taps[s];
-      const int cblocks = (p.seg_c[s] + kBlockK - 1) / kBlockK;
-      const int asteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : taps;
-      const int bsteps = (MODE == 1) ? (taps == 9 ? 3 : 1) : 1;
-      for (int as = 0; as < asteps; ++as) {
-        for (int cb = 0; cb < cblocks; ++cb, ++ia) {
-          const int sa = ia % Cfg::kAStages;
-          mbar_wait(a_full(sa), (ia / Cfg::kAStages) & 1);
-          for (int bs = 0; bs < bsteps; ++bs, ++ib) {
-            const int sb = ib % Cfg::kBStages;
-            mbar_wait(b_full(sb), (ib / Cfg::kBStages) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-              // MODE 1: tap kw reads the halo row starting kw pixels in (a 1x1 segment reads the centre, kw = 1)
-              const int a_row = (MODE == 1) ? (taps == 9 ? bs : 1) : 0;
-              const uint32_t a_addr = smem_a0 + sa * Cfg::kASlot + a_row * kARowBytes;
-              const uint32_t b_addr = smem_b0 + sb * Cfg::kBBytes;
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                uint64_t da = make_sw128_kmajor_desc(a_addr + k * 32);
-                // a start address that is not 1024 B aligned needs the swizzle phase ("matrix base offset",
-                // descriptor bits [49,52)) = (address >> 7) & 7, per the PTX matrix-descriptor rules
-                if (MODE == 1 && p.desc_base_offset) da |= (uint64_t)((a_addr >> 7) & 7) << 49;
-                const uint64_t db = make_sw128_kmajor_desc(b_addr + k * 32);
-                if (CG == 2) umma_bf16_ss_pair(tmem_base, da, db, idesc, accumulate);
-                else umma_bf16_ss(tmem_base, da, db, idesc, accumulate);
-                accumulate = 1;
-              }
-              // frees the weight slot (in both CTAs of a pair) once these MMAs retire
-              if (CG == 2) umma_commit_pair(b_empty(sb)); else umma_commit(b_empty(sb));
-            }
-            __syncwarp();
-          }
-          if (lane == 0) { if (CG == 2) umma_commit_pair(a_empty(sa)); else umma_commit(a_empty(sa)); }
-          __syncwarp();
-        }
-      }
-    }
-    if (lane == 0) { if (CG == 2) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar); }
-    __syncwarp();
-  } else if (warp == 1) {
-    // peer CTA of a pair: its tensor core is driven by the leader's instructions
-  } else if (warp >= 2) {
-    // ================= epilogue (warps 2..5) =================
-    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;    // row of the 128-row tile == TMEM lane
-    // pixel of this row
-    const int rw = row % p.Wt;
-    const int rh = (row / p.Wt) % p.Ht;
-    const int rn = row / (p.Wt * p.Ht);
-    const int ow = w0 + rw, oh = h0 + rh, on = n0 + rn;
-    const bool valid = (ow < p.Wo) && (oh < p.Ho) && (on < p.B);
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-
-    // ---- residual tile: coalesced global reads (each lane 16 B, a warp covers whole 2*BLOCK_N-byte rows) staged
-    //      into this warp's 32 rows of the swizzled output tile; the pipeline buffers are free once tmem_full fired
-    constexpr int kChunksPerRow = BLOCK_N / 8;
-    if (p.residual != nullptr) {
-      constexpr int kLoads = kChunksPerRow;  // (32 rows * kChunksPerRow) / 32 lanes
-#pragma unroll 1
-      for (int i0 = 0; i0 < kLoads; i0 += 8) {
-        uint4 buf[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int idx = (i0 + u) * 32 + lane;
-          const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
-          const int rr = quad * 32 + rl;
-          const int pw = w0 + (rr & (p.Wt - 1));
-          const int ph = h0 + ((rr >> p.log_wt) & (p.Ht - 1));
-          const int pn = n0 + (rr >> (p.log_wt + p.log_ht));
-          const int col = ncol0 + ch * 8;
-          buf[u] = make_uint4(0, 0, 0, 0);
-          if (pw < p.Wo && ph < p.Ho && pn < p.B && col < p.Cout)
-            buf[u] = *reinterpret_cast<const uint4*>(p.residual + (((size_t)pn * p.Ho + ph) * p.Wo + pw) * p.Cout + col);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int idx = (i0 + u) * 32 + lane;
-          const int rl = idx / kChunksPerRow, ch = idx % kChunksPerRow;
-          const int rr = quad * 32 + rl;
-          uint8_t* dst = smem_gen + (ch >> 3) * (kTileM * 128) + rr * 128 + (((ch & 7) ^ (rr & 7)) * 16);
-          *reinterpret_cast<uint4*>(dst) = buf[u];
-        }
-      }
-      __syncwarp();
-    }
-
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const int col0 = ncol0 + c0;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const int slab = c0 >> 6;                 // which 64-channel slab
-      const int chunk0 = (c0 & 63) >> 3;        // first 16-byte chunk within the 128-byte row (0 or 4)
-      uint8_t* rowp = smem_gen + slab * (kTileM * 128) + row * 128;
-      if (col0 < p.Cout) {  // Cout % 8 == 0, handle in groups of 8 columns
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const int col = col0 + j8 * 8;
-          if (col < p.Cout) {
-            if (p.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-              v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
-              v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
-            }
-            if (p.addvec != nullptr && valid) {
-              const float* av = p.addvec + (size_t)on * p.addvec_stride + col;
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(av));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(av + 4));
-              v[j8 * 8 + 0] += b0.x; v[j8 * 8 + 1] += b0.y; v[j8 * 8 + 2] += b0.z; v[j8 * 8 + 3] += b0.w;
-              v[j8 * 8 + 4] += b1.x; v[j8 * 8 + 5] += b1.y; v[j8 * 8 + 6] += b1.z; v[j8 * 8 + 7] += b1.w;
-            }
-            if (p.residual != nullptr) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
-              const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
-              const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
-              v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
-              v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
-            }
-          }
-        }
-      }
-
-      if (p.gn_partial != nullptr) {
-        // GroupNorm statistics for the consumer norm: per channel quad (4 channels) sum and sum of squares over this
-        // warp's 32 rows, reduced with a recursive-halving butterfly (16 values -> 16 shuffles), written without
-        // atomics to partial[(m_tile*4 + quad)][Cout/4][2] (deterministic; folded by fm_groupnorm_finalize_partials).
-        float red[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a0 = valid ? v[4 * j + 0] : 0.f, a1 = valid ? v[4 * j + 1] : 0.f;
-          const float a2 = valid ? v[4 * j + 2] : 0.f, a3 = valid ? v[4 * j + 3] : 0.f;
-          red[j] = (a0 + a1) + (a2 + a3);
-          red[8 + j] = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
-        }
-#pragma unroll
-        for (int width = 8, mask = 16; width >= 1; width >>= 1, mask >>= 1) {
-          const bool upper = (lane & mask) != 0;
-#pragma unroll
-          for (int i = 0; i < width; ++i) {
-            const float keep = upper ? red[i + width] : red[i];
-            const float give = upper ? red[i] : red[i + width];
-            red[i] = keep + __shfl_xor_sync(0xffffffffu, give, mask);
-          }
-        }
-        red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
-        const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        const int qcol = col0 + (vidx & 7) * 4;
-        if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
-          p.gn_partial[(((size_t)m_tile * 4 + quad) * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = red[0];
-      }
-
-      // pack to bf16 and stage (128B-swizzled rows of 64 channels, one 16 KB slab per 64 output channels)
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int chunk = (chunk0 + j) ^ (row & 7);
-        *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-            make_uint4(pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-      }
-    }
-    // make the generic-proxy smem writes visible to the async proxy, then one thread issues the TMA stores
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) {
-#pragma unroll
-      for (int slab = 0; slab < BLOCK_N / 64; ++slab) {
-        if (ncol0 + slab * 64 < p.Cout)
-          tma_store_4d(&p.out, smem_base + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
-      }
-      tma_store_commit();
-      tma_store_wait_read0();
-    }
-  }
-
-  // ---- teardown ----
-  tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();  // pair: both CTAs' smem/TMEM/barriers stay alive until both are done
-  if (warp == 1) {
-    tc_fence_after();
-    if (CG == 2) tmem_dealloc_pair<BLOCK_N>(tmem_base); else tmem_dealloc<BLOCK_N>(tmem_base);
-  }
-}
-
-
 // =================================================================================================================
-// Persistent variant.  One CTA (or CTA pair) per SM walks a static round-robin list of output tiles; the TMA/MMA
-// pipeline never drains between tiles and the accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the
-// epilogue of tile i (TMEM -> registers -> bias/temb/residual/GroupNorm statistics -> bf16 -> TMA store) overlaps
-// the main loop of tile i+1.  Measured on the one-tile-per-CTA kernel above, the per-tile prologue + pipeline fill +
-// epilogue + teardown cost 31 % (single CTA) / 58 % (CTA pair) of the run time of a K = 1152 conv; this removes it.
+// Persistent per-tile kernel.  One CTA (or CTA pair, CG = 2: tcgen05 cta_group::2, 256-row tiles, each CTA stages its
+// own A rows and HALF of the weight tile) per SM walks a static round-robin list of output tiles; the TMA/MMA pipeline
+// never drains between tiles and the accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the epilogue of
+// tile i (TMEM -> registers -> bias/temb/residual/GroupNorm statistics -> bf16 -> TMA store) overlaps the main loop
+// of tile i+1.  (A first one-tile-per-CTA version spent 31 % / 58 % (single / pair) of a K = 1152 conv in prologue,
+// pipeline fill, epilogue and teardown.)
 // =================================================================================================================
 constexpr int kStageCols = 128;  // output columns staged (and TMA-stored) at a time
 
@@ -664,9 +342,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           // coalesced 16-byte reads of this warp's 32 rows x kWarpCols columns, staged into the swizzled tile
 #pragma unroll
           for (int i0 = 0; i0 < kWarpChunks; i0 += 8) {
-            uint4 buf4[8];
+            // 32 rows x kWarpChunks chunks per warp = kWarpChunks loads per lane (4 for 64-wide tiles: the batch
+            // must not run past the warp's own rows)
+            constexpr int kU = kWarpChunks < 8 ? kWarpChunks : 8;
+            uint4 buf4[kU];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kU; ++u) {
               const int idx = (i0 + u) * 32 + lane;
               const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
               const int rr = quad * 32 + rl;
@@ -680,7 +361,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
                                                           (((size_t)pn * p.Ho + ph) * p.Wo + pw) * p.Cout + col);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kU; ++u) {
               const int idx = (i0 + u) * 32 + lane;
               const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
               const int rr = quad * 32 + rl;
@@ -860,40 +541,6 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-template <int BLOCK_N, int MODE, int CG>
-static int launch_conv(const ConvKernelParams& kp, int m_tiles, int n_tiles, cudaStream_t st) {
-  using Cfg = ConvCfg<BLOCK_N, MODE, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, MODE, CG>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_igemm)");
-    attr_set = true;
-  }
-  if (CG == 2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((m_tiles + 1) & ~1, n_tiles);  // pairs of M tiles; a padded tile is fully out of bounds
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, MODE, CG>, kp);
-    count_launch();
-    if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_igemm pair)");
-    return 0;
-  }
-  conv_igemm_kernel<BLOCK_N, MODE, CG><<<dim3(m_tiles, n_tiles), kConvThreads, Cfg::kSmemBytes, st>>>(kp);
-  FM_LAUNCH_CHECK("conv_igemm_kernel");
-  return 0;
-}
-
 template <int BLOCK_N, int MODE, int CG, int MT>
 static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
   using Cfg = PConvCfg<BLOCK_N, MODE, CG, MT>;
@@ -930,19 +577,101 @@ static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
 
 #include "conv_rolling.cuh"
 
-extern "C" int fm_conv_stats_layout(int32_t B, int32_t H, int32_t W, int32_t stride, int32_t* rows_per_image,
-                                    int32_t* total_rows) {
-  using namespace fm;
-  if (B <= 0 || H <= 0 || W <= 0 || (stride != 1 && stride != 2) || !rows_per_image || !total_rows) return FM_ERR_BAD_ARG;
-  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-  const int Wt = pow2_ceil(Wo) < kTileM ? pow2_ceil(Wo) : kTileM;
-  const int rest = kTileM / Wt;
-  const int Ht = pow2_ceil(Ho) < rest ? pow2_ceil(Ho) : rest;
-  if (rest / Ht != 1) return FM_ERR_UNSUPPORTED;  // several images per tile: no fused statistics
-  const int tiles = ((Wo + Wt - 1) / Wt) * ((Ho + Ht - 1) / Ht);
-  *rows_per_image = tiles * 4;
-  *total_rows = tiles * 4 * B;
+namespace fm {
+
+// Everything about a conv launch that follows from shapes, kernel sizes and the presence of operand transforms (no
+// pointers): shared by the launcher and by fm_conv_stats_rows so the statistics workspace always matches the kernel.
+struct ConvPlan {
+  int Ho, Wo, Wt, Ht, Nt, tiles_w, tiles_h, tiles_n;
+  bool row_mode, xf, rolling, pair;
+  int block_n, n_tiles, mt, m_tiles;
+  RollSched sch;
+  int stats_rows;  // rows of GroupNorm partials per image (0: fused statistics unavailable)
+};
+
+static int plan_conv(const fm_conv_params* p, ConvPlan* pl) {
+  FM_REQUIRE(p != nullptr, "conv: null params");
+  FM_REQUIRE(p->nseg >= 1 && p->nseg <= FM_CONV_MAX_SEG, "conv: nseg=%d out of range", p->nseg);
+  FM_REQUIRE(p->stride == 1 || p->stride == 2, "conv: stride must be 1 or 2 (got %d)", p->stride);
+  FM_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0, "conv: empty input %dx%dx%d", p->B, p->H, p->W);
+  FM_REQUIRE(p->Cout > 0 && p->Cout % 8 == 0, "conv: Cout=%d must be a positive multiple of 8", p->Cout);
+  memset(pl, 0, sizeof(*pl));
+  pl->Ho = (p->H + p->stride - 1) / p->stride;
+  pl->Wo = (p->W + p->stride - 1) / p->stride;
+  // M-tile box: 128 output pixels as (Wt, Ht, Nt), powers of two
+  pl->Wt = pow2_ceil(pl->Wo) < kTileM ? pow2_ceil(pl->Wo) : kTileM;
+  const int rest = kTileM / pl->Wt;
+  pl->Ht = pow2_ceil(pl->Ho) < rest ? pow2_ceil(pl->Ho) : rest;
+  pl->Nt = rest / pl->Ht;
+  pl->tiles_w = (pl->Wo + pl->Wt - 1) / pl->Wt;
+  pl->tiles_h = (pl->Ho + pl->Ht - 1) / pl->Ht;
+  pl->tiles_n = (p->B + pl->Nt - 1) / pl->Nt;
+  bool any3 = false;
+  for (int s = 0; s < p->nseg; ++s) {
+    const fm_conv_seg& sg = p->seg[s];
+    FM_REQUIRE(sg.C > 0 && sg.C % 8 == 0, "conv: segment %d channels=%d must be a positive multiple of 8", s, sg.C);
+    FM_REQUIRE(sg.ksize == 1 || sg.ksize == 3, "conv: segment %d ksize=%d unsupported", s, sg.ksize);
+    FM_REQUIRE(!(sg.ksize == 1 && p->stride != 1 && p->nseg > 1), "conv: fused 1x1 segment needs stride 1");
+    if (sg.upsample) { set_error("conv: upsample-fused segments are not implemented yet"); return FM_ERR_UNSUPPORTED; }
+    any3 |= (sg.ksize == 3);
+    if (sg.norm_a != nullptr) {
+      FM_REQUIRE(sg.norm_b != nullptr && sg.C % kBlockK == 0 && sg.norm_stride % 4 == 0 &&
+                     ((uintptr_t)sg.norm_a & 15) == 0 && ((uintptr_t)sg.norm_b & 15) == 0,
+                 "conv: segment %d operand transform needs C %% 64 == 0 and 16B-aligned a/b rows", s);
+      pl->xf = true;
+    }
+  }
+  // row mode (kw tap reuse): stride 1, M tile = 128 consecutive pixels of one row, at least one 3x3 segment
+  pl->row_mode = p->stride == 1 && pl->Wt == kTileM && any3 && getenv("FMDM_CONV_NO_ROW_MODE") == nullptr;
+  pl->block_n = (p->Cout > 128) ? 256 : (p->Cout > 64 ? 128 : 64);
+  // rolling-row kernel: row-mode convs led by a 3x3 segment; N tiles of at most 128 columns
+  pl->rolling = pl->row_mode && p->seg[0].ksize == 3;
+  {
+    const char* re = getenv("FMDM_CONV_ROLLING");  // 0/1: only where the operand transform is requested; 3: always
+    const int rv = re ? atoi(re) : 2;
+    if ((rv == 0 || rv == 1) && !pl->xf) pl->rolling = false;
+    if (p->Cout > 128 && !pl->xf && rv != 3) pl->rolling = false;  // wide layers: the 256-column pair kernel unless fused
+  }
+  FM_REQUIRE(!pl->xf || pl->rolling, "conv: fused operand transform needs a leading 3x3 segment at stride 1 on image "
+                                     "rows of >= 65 pixels (fm_conv_operand_norm_supported)");
+  if (pl->rolling && pl->block_n == 256) pl->block_n = 128;
+  // CTA pairs (cta_group::2): the 128/256-wide tiles when there are at least two M tiles; always for rolling rows
+  const int m_tiles = pl->tiles_w * pl->tiles_h * pl->tiles_n;
+  pl->pair = (pl->block_n >= 128) && (m_tiles >= 2);
+  {
+    const char* pe = getenv("FMDM_CONV_PAIR");  // 0 disables, 1 (default) enables
+    if (pe && atoi(pe) == 0) pl->pair = false;
+  }
+  if (pl->rolling) pl->pair = true;
+  pl->n_tiles = (p->Cout + pl->block_n - 1) / pl->block_n;
+  // two M tiles per CTA (MT = 2) for 128-wide N tiles when every SM pair still gets several work units
+  pl->mt = (pl->pair && pl->block_n == 128 && m_tiles >= 8 * sm_count()) ? 2 : 1;
+  {
+    const char* me = getenv("FMDM_CONV_MT");  // 1 forces one M tile per CTA, 2 forces two wherever the variant exists
+    if (me && atoi(me) == 1) pl->mt = 1;
+    if (me && atoi(me) == 2 && pl->pair && pl->block_n == 128) pl->mt = 2;
+  }
+  const int m_round = (pl->pair ? 2 : 1) * pl->mt;
+  pl->m_tiles = (m_tiles + m_round - 1) / m_round * m_round;
+  if (pl->rolling) {
+    pl->sch = roll_schedule(p->B, pl->Ho, pl->tiles_w, pl->n_tiles, sm_count() / 2);
+    pl->stats_rows = pl->sch.chunks * pl->tiles_w * 4;      // one row per (strip, TMEM lane quadrant)
+  } else {
+    pl->stats_rows = (pl->Nt == 1) ? pl->tiles_w * pl->tiles_h * 4 : 0;  // one row per (M tile, lane quadrant)
+  }
+  if (p->Cout % 4) pl->stats_rows = 0;
   return 0;
+}
+
+}  // namespace fm
+
+extern "C" int fm_conv_stats_rows(const fm_conv_params* p, int32_t* rows_per_image) {
+  using namespace fm;
+  FM_REQUIRE(rows_per_image != nullptr, "conv_stats_rows: null output");
+  ConvPlan pl;
+  if (int e = plan_conv(p, &pl)) return e;
+  *rows_per_image = pl.stats_rows;
+  return pl.stats_rows > 0 ? 0 : FM_ERR_UNSUPPORTED;
 }
 
 extern "C" int fm_conv_operand_norm_supported(int32_t H, int32_t W, int32_t stride, int32_t has_3x3) {
@@ -955,52 +684,22 @@ extern "C" int fm_conv_operand_norm_supported(int32_t H, int32_t W, int32_t stri
 extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream) {
   using namespace fm;
   if (int e = ensure_device()) return e;
-  FM_REQUIRE(p != nullptr, "conv: null params");
-  FM_REQUIRE(p->nseg >= 1 && p->nseg <= FM_CONV_MAX_SEG, "conv: nseg=%d out of range", p->nseg);
-  FM_REQUIRE(p->stride == 1 || p->stride == 2, "conv: stride must be 1 or 2 (got %d)", p->stride);
-  FM_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0, "conv: empty input %dx%dx%d", p->B, p->H, p->W);
-  FM_REQUIRE(p->Cout > 0 && p->Cout % 8 == 0, "conv: Cout=%d must be a positive multiple of 8", p->Cout);
+  ConvPlan pl;
+  if (int e = plan_conv(p, &pl)) return e;
   FM_REQUIRE(p->weight && p->out, "conv: null weight/out");
   FM_REQUIRE(((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->out & 15) == 0, "conv: weight/out not 16B aligned");
-  const int Ho = (p->H + p->stride - 1) / p->stride, Wo = (p->W + p->stride - 1) / p->stride;
 
   ConvKernelParams kp;
   memset(&kp, 0, sizeof(kp));
-  // tile box
-  kp.Wt = pow2_ceil(Wo) < kTileM ? pow2_ceil(Wo) : kTileM;
-  int rest = kTileM / kp.Wt;
-  kp.Ht = pow2_ceil(Ho) < rest ? pow2_ceil(Ho) : rest;
-  kp.Nt = rest / kp.Ht;
-  kp.tiles_w = (Wo + kp.Wt - 1) / kp.Wt;
-  kp.tiles_h = (Ho + kp.Ht - 1) / kp.Ht;
-  const int tiles_n = (p->B + kp.Nt - 1) / kp.Nt;
+  kp.Wt = pl.Wt; kp.Ht = pl.Ht; kp.Nt = pl.Nt;
+  kp.tiles_w = pl.tiles_w; kp.tiles_h = pl.tiles_h;
   kp.stride = p->stride;
-  kp.B = p->B; kp.Ho = Ho; kp.Wo = Wo; kp.Cout = p->Cout;
+  kp.B = p->B; kp.Ho = pl.Ho; kp.Wo = pl.Wo; kp.Cout = p->Cout;
   kp.nseg = p->nseg;
-  // row mode (kw tap reuse): stride 1, M tile = 128 consecutive pixels of one row, at least one 3x3 segment
-  bool row_mode = (p->stride == 1 && kp.Wt == kTileM && getenv("FMDM_CONV_NO_ROW_MODE") == nullptr);
-  {
-    bool any3 = false;
-    for (int s = 0; s < p->nseg; ++s) any3 |= (p->seg[s].ksize == 3);
-    row_mode = row_mode && any3;
-  }
   int ktot = 0, nk = 0;
-  bool xf = false;
   for (int s = 0; s < p->nseg; ++s) {
     const fm_conv_seg& sg = p->seg[s];
     FM_REQUIRE(sg.src != nullptr && ((uintptr_t)sg.src & 15) == 0, "conv: segment %d source null/unaligned", s);
-    FM_REQUIRE(sg.C > 0 && sg.C % 8 == 0, "conv: segment %d channels=%d must be a positive multiple of 8", s, sg.C);
-    FM_REQUIRE(sg.ksize == 1 || sg.ksize == 3, "conv: segment %d ksize=%d unsupported", s, sg.ksize);
-    FM_REQUIRE(!(sg.ksize == 1 && p->stride != 1 && p->nseg > 1), "conv: fused 1x1 segment needs stride 1");
-    if (sg.upsample) { set_error("conv: upsample-fused segments are not implemented yet"); return FM_ERR_UNSUPPORTED; }
-    if (sg.norm_a != nullptr) {
-      FM_REQUIRE(row_mode, "conv: fused operand transform needs stride 1 and image rows of >= 65 pixels "
-                           "(fm_conv_operand_norm_supported)");
-      FM_REQUIRE(sg.norm_b != nullptr && sg.C % kBlockK == 0 && sg.norm_stride % 4 == 0 &&
-                     ((uintptr_t)sg.norm_a & 15) == 0 && ((uintptr_t)sg.norm_b & 15) == 0,
-                 "conv: segment %d operand transform needs C %% 64 == 0 and 16B-aligned a/b rows", s);
-      xf = true;
-    }
     kp.seg_na[s] = sg.norm_a;
     kp.seg_nb[s] = sg.norm_b;
     kp.seg_nstride[s] = sg.norm_stride;
@@ -1010,32 +709,14 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
     kp.seg_koff[s] = ktot;
     ktot += kp.seg_taps[s] * sg.C;
     nk += kp.seg_taps[s] * ((sg.C + kBlockK - 1) / kBlockK);
-    if (int e = encode_act_map(&kp.src[s], sg.src, sg.C, p->W, p->H, p->B, row_mode ? kTileM + 2 : kp.Wt, kp.Ht, kp.Nt,
-                               p->stride))
+    if (int e = encode_act_map(&kp.src[s], sg.src, sg.C, p->W, p->H, p->B, pl.row_mode ? kTileM + 2 : kp.Wt, kp.Ht,
+                               kp.Nt, p->stride))
       return e;
   }
   kp.num_k_blocks = nk;
-  int block_n = (p->Cout > 128) ? 256 : (p->Cout > 64 ? 128 : 64);
-  // rolling-row kernel: stride-1 row-mode convs led by a 3x3 segment, >= 2 strips; N tiles of at most 128 columns
-  bool rolling = row_mode && p->seg[0].ksize == 3 && (kp.tiles_w * p->B >= 2 || Ho >= 8);
-  {
-    const char* re = getenv("FMDM_CONV_ROLLING");  // 0 disables, 1 = only where the operand transform is requested
-    const int rv = re ? atoi(re) : 2;
-    if ((rv == 0 || rv == 1) && !xf) rolling = false;
-    if (p->Cout > 128 && !xf && rv != 3) rolling = false;  // wide layers: the 256-column pair kernel unless fused (3 forces)
-  }
-  FM_REQUIRE(!xf || rolling, "conv: fused operand transform needs a leading 3x3 segment at stride 1 on image rows of "
-                             ">= 65 pixels (fm_conv_operand_norm_supported)");
-  if (rolling && block_n == 256) block_n = 128;
-  // CTA pairs (cta_group::2): enabled for the 128/256-wide tiles when there are at least two M tiles
-  const int m_tiles_total = kp.tiles_w * kp.tiles_h * tiles_n;
-  bool pair = ((block_n >= 128) && (m_tiles_total >= 2)) || rolling;
-  {
-    const char* pe = getenv("FMDM_CONV_PAIR");  // 0 disables, 1 (default) enables
-    if (pe && atoi(pe) == 0) pair = false;
-  }
-  if (int e = encode_wgt_map(&kp.wgt, p->weight, ktot, p->Cout, pair ? block_n / 2 : block_n)) return e;
-  if (int e = encode_act_map(&kp.out, p->out, p->Cout, Wo, Ho, p->B, kp.Wt, kp.Ht, kp.Nt, 1)) return e;
+  const int block_n = pl.block_n;
+  if (int e = encode_wgt_map(&kp.wgt, p->weight, ktot, p->Cout, pl.pair ? block_n / 2 : block_n)) return e;
+  if (int e = encode_act_map(&kp.out, p->out, p->Cout, pl.Wo, pl.Ho, p->B, kp.Wt, kp.Ht, kp.Nt, 1)) return e;
   kp.bias = p->bias;
   kp.addvec = p->addvec;
   kp.addvec_stride = p->addvec_stride;
@@ -1044,71 +725,30 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   FM_REQUIRE(p->bias == nullptr || ((uintptr_t)p->bias & 15) == 0, "conv: bias must be 16B aligned");
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
   FM_REQUIRE(p->residual == nullptr || ((uintptr_t)p->residual & 15) == 0, "conv: residual must be 16B aligned");
-  {
-    const char* bo = getenv("FMDM_CONV_DESC_BASE_OFFSET");
-    kp.desc_base_offset = bo ? atoi(bo) : 0;  // measured on B200: the swizzle is address-based, phase bits must stay 0
-  }
   kp.gn_partial = p->gn_stats;
   kp.log_wt = 0; while ((1 << kp.log_wt) < kp.Wt) ++kp.log_wt;
   kp.log_ht = 0; while ((1 << kp.log_ht) < kp.Ht) ++kp.log_ht;
-  if (p->gn_stats) {
-    FM_REQUIRE(kp.Nt == 1, "conv: fused GroupNorm statistics need >= 128 pixels per image (use "
-                           "fm_groupnorm_stats_bf16 for tiny images)");
-    FM_REQUIRE(p->Cout % 4 == 0, "conv: fused GroupNorm statistics need Cout %% 4 == 0");
-  }
-  const int m_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
-  const int n_tiles = (p->Cout + block_n - 1) / block_n;
+  FM_REQUIRE(p->gn_stats == nullptr || pl.stats_rows > 0,
+             "conv: fused GroupNorm statistics need >= 128 pixels per image and Cout %% 4 == 0 (fm_conv_stats_rows)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  kp.n_tiles = n_tiles;
-  // two M tiles per CTA (MT = 2) for 128-wide N tiles when every SM pair still gets several work units
-  int mt = (pair && block_n == 128 && m_tiles >= 8 * sm_count()) ? 2 : 1;
-  {
-    const char* me = getenv("FMDM_CONV_MT");  // 1 forces one M tile per CTA, 2 forces two wherever the variant exists
-    if (me && atoi(me) == 1) mt = 1;
-    if (me && atoi(me) == 2 && pair && block_n == 128) mt = 2;
+  kp.n_tiles = pl.n_tiles;
+  kp.m_tiles = pl.m_tiles;
+  if (pl.rolling) {
+    if (pl.xf)
+      return block_n == 64 ? launch_conv_rolling<64, 1>(kp, pl.sch, st) : launch_conv_rolling<128, 1>(kp, pl.sch, st);
+    return block_n == 64 ? launch_conv_rolling<64, 0>(kp, pl.sch, st) : launch_conv_rolling<128, 0>(kp, pl.sch, st);
   }
-  const int m_round = (pair ? 2 : 1) * mt;
-  kp.m_tiles = (m_tiles + m_round - 1) / m_round * m_round;
-  {
-    const char* pe = getenv("FMDM_CONV_PERSISTENT");  // 0 selects the one-tile-per-CTA kernel
-    const bool persistent = !(pe && atoi(pe) == 0);
-    if (rolling) {
-      const RollSched sch = roll_schedule(p->B, Ho, kp.tiles_w, n_tiles, sm_count() / 2);
-      if (xf) return block_n == 64 ? launch_conv_rolling<64, 1>(kp, sch, st) : launch_conv_rolling<128, 1>(kp, sch, st);
-      return block_n == 64 ? launch_conv_rolling<64, 0>(kp, sch, st) : launch_conv_rolling<128, 0>(kp, sch, st);
-    }
-    if (persistent) {
 #define FM_PC(N, M, G) return launch_conv_persistent<N, M, G, 1>(kp, st)
-      if (pair && mt == 2) {
-        if (row_mode) return launch_conv_persistent<128, 1, 2, 2>(kp, st);
-        return launch_conv_persistent<128, 0, 2, 2>(kp, st);
-      } else if (pair) {
-        if (row_mode) { if (block_n == 128) FM_PC(128, 1, 2); else FM_PC(256, 1, 2); }
-        else { if (block_n == 128) FM_PC(128, 0, 2); else FM_PC(256, 0, 2); }
-      } else if (row_mode) {
-        if (block_n == 64) FM_PC(64, 1, 1); else if (block_n == 128) FM_PC(128, 1, 1); else FM_PC(256, 1, 1);
-      } else {
-        if (block_n == 64) FM_PC(64, 0, 1); else if (block_n == 128) FM_PC(128, 0, 1); else FM_PC(256, 0, 1);
-      }
+  if (pl.pair && pl.mt == 2) {
+    if (pl.row_mode) return launch_conv_persistent<128, 1, 2, 2>(kp, st);
+    return launch_conv_persistent<128, 0, 2, 2>(kp, st);
+  } else if (pl.pair) {
+    if (pl.row_mode) { if (block_n == 128) FM_PC(128, 1, 2); else FM_PC(256, 1, 2); }
+    else { if (block_n == 128) FM_PC(128, 0, 2); else FM_PC(256, 0, 2); }
+  } else if (pl.row_mode) {
+    if (block_n == 64) FM_PC(64, 1, 1); else if (block_n == 128) FM_PC(128, 1, 1); else FM_PC(256, 1, 1);
+  } else {
+    if (block_n == 64) FM_PC(64, 0, 1); else if (block_n == 128) FM_PC(128, 0, 1); else FM_PC(256, 0, 1);
+  }
 #undef FM_PC
-    }
-  }
-  if (pair) {
-    if (row_mode) return block_n == 128 ? launch_conv<128, 1, 2>(kp, m_tiles, n_tiles, st)
-                                        : launch_conv<256, 1, 2>(kp, m_tiles, n_tiles, st);
-    return block_n == 128 ? launch_conv<128, 0, 2>(kp, m_tiles, n_tiles, st)
-                          : launch_conv<256, 0, 2>(kp, m_tiles, n_tiles, st);
-  }
-  if (row_mode) {
-    switch (block_n) {
-      case 64: return launch_conv<64, 1, 1>(kp, m_tiles, n_tiles, st);
-      case 128: return launch_conv<128, 1, 1>(kp, m_tiles, n_tiles, st);
-      default: return launch_conv<256, 1, 1>(kp, m_tiles, n_tiles, st);
-    }
-  }
-  switch (block_n) {
-    case 64: return launch_conv<64, 0, 1>(kp, m_tiles, n_tiles, st);
-    case 128: return launch_conv<128, 0, 1>(kp, m_tiles, n_tiles, st);
-    default: return launch_conv<256, 0, 1>(kp, m_tiles, n_tiles, st);
-  }
 }

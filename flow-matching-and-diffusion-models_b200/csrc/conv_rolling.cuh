@@ -131,11 +131,13 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
   const int first_unit = (int)blockIdx.x >> 1;
   const int unit_stride = (int)gridDim.x >> 1;
   // this CTA's strip of a unit: 128 pixels starting at w0 of rows [h_begin, h_end) of image n
+  int strip_chunk = 0;  // row chunk of the strip decoded last (epilogue: statistics row)
   auto strip_coords = [&](int unit, int& tw, int& w0, int& n, int& h_begin, int& h_end, int& ncol0) {
     const int ps = unit / p.n_tiles;
     ncol0 = (unit - ps * p.n_tiles) * BLOCK_N;
     const int sid = ps * 2 + (int)cta_rank;
     const int chunk = sid / sch.combos;
+    strip_chunk = chunk;
     const int j = sid - chunk * sch.combos;
     n = j / p.tiles_w;
     tw = j - n * p.tiles_w;
@@ -360,9 +362,13 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
     for (int unit = first_unit; unit < total_units; unit += unit_stride) {
       int tw, w0, n0, h_begin, h_end, ncol0;
       strip_coords(unit, tw, w0, n0, h_begin, h_end, ncol0);
+      // GroupNorm partial statistics accumulate over the rows of the strip (one global row per strip and lane quadrant)
+      float st_acc[kWarpCols / 32];
+#pragma unroll
+      for (int i = 0; i < kWarpCols / 32; ++i) st_acc[i] = 0.f;
+      const size_t stat_row = ((size_t)(n0 * sch.chunks + strip_chunk) * p.tiles_w + tw) * 4 + quad;
       for (int h0 = h_begin; h0 < h_end; ++h0, ++oc, ++stage_use) {
         const int buf = oc & 3;
-        const int m_tile = (n0 * p.Ho + h0) * p.tiles_w + tw;
         const int ow = w0 + row;
         const bool valid = (ow < p.Wo) && (n0 < p.B);
 
@@ -475,10 +481,13 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
               }
             }
             red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
-            const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            const int qcol = col0 + (vidx & 7) * 4;
-            if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
-              p.gn_partial[(((size_t)m_tile * 4 + quad) * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = red[0];
+            st_acc[i] += red[0];
+            if (h0 == h_end - 1) {
+              const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              const int qcol = col0 + (vidx & 7) * 4;
+              if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
+                p.gn_partial[(stat_row * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = st_acc[i];
+            }
           }
           uint32_t pk[16];
 #pragma unroll

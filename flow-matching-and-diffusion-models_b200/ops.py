@@ -210,11 +210,10 @@ def conv2d(
     p.gn_stats = None
     p.gn_groups = 0
     stats_ws = None
-    if want_stats and weight.cout % 4 == 0:
-        rpi, tot = C.c_int32(0), C.c_int32(0)
-        if lib.fm_conv_stats_layout(b, h, w, stride, C.byref(rpi), C.byref(tot)) == 0:
-            stats_ws = torch.empty((tot.value, weight.cout // 4, 2), dtype=torch.float32, device=srcs[0].device)
-            p.gn_stats = stats_ws.data_ptr()
+    rpi = C.c_int32(0)
+    if want_stats and weight.cout % 4 == 0 and lib.fm_conv_stats_rows(C.byref(p), C.byref(rpi)) == 0:
+        stats_ws = torch.empty((b * rpi.value, weight.cout // 4, 2), dtype=torch.float32, device=srcs[0].device)
+        p.gn_stats = stats_ws.data_ptr()
     e0 = _prof_begin()
     _lib.check(lib.fm_conv2d_igemm_bf16(C.byref(p), _stream()), "conv2d_igemm_bf16")
     _prof_end("conv_igemm", 2.0 * b * ho * wo * weight.cout * weight.mat.shape[1], e0)

@@ -83,7 +83,7 @@ typedef struct fm_conv_params {
   int32_t _pad1;
   const void* residual;    /* bf16 NHWC [B][Ho][Wo][Cout] or NULL                        */
   void* out;               /* bf16 NHWC [B][Ho][Wo][Cout]                                */
-  float* gn_stats;         /* fp32 [total_rows][Cout/4][2] workspace (fm_conv_stats_layout) receiving, per 32-row
+  float* gn_stats;         /* fp32 [B*rows][Cout/4][2] workspace (fm_conv_stats_rows) receiving, per 32-row
                               group of every M tile, the channel-quad (sum, sumsq) of `out` for the consumer
                               GroupNorm (no atomics; folded by fm_groupnorm_finalize_partials), or NULL */
   int32_t gn_groups;       /* unused (kept for layout stability) */
@@ -91,11 +91,12 @@ typedef struct fm_conv_params {
 } fm_conv_params;
 
 int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream);
-/* Row-group layout of the fused GroupNorm statistics for a conv with this input size/stride: 4 rows per M tile.
- * Returns FM_ERR_UNSUPPORTED when an M tile would span several images (fewer than 128 output pixels per image). */
-int fm_conv_stats_layout(int32_t B, int32_t H, int32_t W, int32_t stride, int32_t* rows_per_image,
-                         int32_t* total_rows);
-
+/* Rows of fused GroupNorm partial statistics PER IMAGE the conv described by `p` will write (pointers in `p` other
+ * than the norm_a/norm_b markers are ignored): gn_stats must hold B * rows * (Cout/4) * 2 floats.  The count follows
+ * the kernel the launcher picks for these shapes (one row per M tile and TMEM lane quadrant, or per strip and
+ * quadrant for the rolling-row kernel).  Returns FM_ERR_UNSUPPORTED when an M tile would span several images (fewer
+ * than 128 output pixels per image) or Cout % 4 != 0. */
+int fm_conv_stats_rows(const fm_conv_params* p, int32_t* rows_per_image);
 /* 1 if a conv with this input size / stride / kernel mix can take fused operand transforms (fm_conv_seg.norm_a):
  * stride 1, rows of >= 65 pixels (the M tile is 128 consecutive pixels of one image row) and a 3x3 segment. */
 int fm_conv_operand_norm_supported(int32_t H, int32_t W, int32_t stride, int32_t has_3x3);
