@@ -61,6 +61,7 @@ SIGNATURES = {
     "fm_last_error": (C.c_char_p, []),
     "fm_launch_count": (C.c_longlong, []),
     "fm_conv2d_igemm_bf16": (C.c_int, [C.POINTER(ConvParams), _vp]),
+    "fm_conv_kernel_kind": (C.c_int, [C.POINTER(ConvParams)]),
     "fm_conv_operand_norm_supported": (C.c_int, [_i32, _i32, _i32, _i32]),
     "fm_groupnorm_affine_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "fm_groupnorm_finalize_partials_affine": (

@@ -674,6 +674,13 @@ extern "C" int fm_conv_stats_rows(const fm_conv_params* p, int32_t* rows_per_ima
   return pl.stats_rows > 0 ? 0 : FM_ERR_UNSUPPORTED;
 }
 
+extern "C" int fm_conv_kernel_kind(const fm_conv_params* p) {
+  using namespace fm;
+  ConvPlan pl;
+  if (int e = plan_conv(p, &pl)) return e;
+  return pl.rolling ? (pl.xf ? 2 : 1) : 0;
+}
+
 extern "C" int fm_conv_operand_norm_supported(int32_t H, int32_t W, int32_t stride, int32_t has_3x3) {
   using namespace fm;
   if (H <= 0 || W <= 0) return 0;

@@ -216,7 +216,10 @@ def conv2d(
         p.gn_stats = stats_ws.data_ptr()
     e0 = _prof_begin()
     _lib.check(lib.fm_conv2d_igemm_bf16(C.byref(p), _stream()), "conv2d_igemm_bf16")
-    _prof_end("conv_igemm", 2.0 * b * ho * wo * weight.cout * weight.mat.shape[1], e0)
+    if e0 is not None:
+        kind = lib.fm_conv_kernel_kind(C.byref(p))
+        tag = {1: "conv_rolling", 2: "conv_rolling_xf"}.get(kind, "conv_tile")
+        _prof_end(tag, 2.0 * b * ho * wo * weight.cout * weight.mat.shape[1], e0)
     if stats_ws is not None:
         out._fm_stats = (stats_ws, rpi.value)
     return out

@@ -97,6 +97,9 @@ int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream);
  * quadrant for the rolling-row kernel).  Returns FM_ERR_UNSUPPORTED when an M tile would span several images (fewer
  * than 128 output pixels per image) or Cout % 4 != 0. */
 int fm_conv_stats_rows(const fm_conv_params* p, int32_t* rows_per_image);
+/* Which kernel the launcher picks for `p`: 0 persistent per-tile kernel, 1 rolling-row kernel, 2 rolling-row kernel with
+ * the fused operand transform; negative = error.  (Diagnostics: bench.py tags its per-kernel timings with it.) */
+int fm_conv_kernel_kind(const fm_conv_params* p);
 /* 1 if a conv with this input size / stride / kernel mix can take fused operand transforms (fm_conv_seg.norm_a):
  * stride 1, rows of >= 65 pixels (the M tile is 128 consecutive pixels of one image row) and a 3x3 segment. */
 int fm_conv_operand_norm_supported(int32_t H, int32_t W, int32_t stride, int32_t has_3x3);

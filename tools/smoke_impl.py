@@ -64,7 +64,18 @@ def run_smoke():
     psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
     assert launched > 0, "no fmdm_b200 kernels were launched"
     assert psnr >= 40.0, f"smoke: PSNR vs oracle {psnr:.1f} dB < 40 dB"
-    print(f"smoke ok: 8-step flow-matching sample, PSNR vs oracle {psnr:.1f} dB, {launched} kernel launches (eager part)")
+    # one denoiser forward on rows >= 65 px: the rolling-row tcgen05 conv with the fused GroupNorm operand transform
+    g2 = torch.Generator().manual_seed(43)
+    x = torch.randn(1, 1, 96, 160, generator=g2).to(dev)
+    c = torch.rand(1, 1, 96, 160, generator=g2).to(dev)
+    t = torch.full((1,), 321.5, device=dev)
+    with torch.no_grad():
+        mine = model(x, t, context=c)
+        orc = OD.unet_diffusers_nd_forward(sd, CFG, x, t, conditioning="concatenate", channels=1, context=c)
+    rel = float((mine - orc).norm() / orc.norm())
+    assert rel < 1.2e-2, f"smoke: 96x160 forward rel-L2 {rel:.4f} vs oracle"
+    print(f"smoke ok: 8-step flow-matching sample, PSNR vs oracle {psnr:.1f} dB, {launched} kernel launches (eager part); "
+          f"96x160 forward rel-L2 {rel:.2e}")
 
 
 if __name__ == "__main__":
