@@ -265,11 +265,14 @@ def run_b200_arm(args):
             allw = sum(by[k][0] for k in conv_tags)
             allms = sum(by[k][1] for k in conv_tags)
             gn = by.get("groupnorm", [0.0, 1e-9, 1])
-            traffic = None
+            traffic = traffic_note = None
             tpath = os.path.join(ROOT, "profiles", "dominant_kernel_dram.json")
-            if os.path.exists(tpath):  # dram bytes per launch of the dominant kernel from the committed ncu capture
+            if os.path.exists(tpath):  # dram bytes of one launch of the dominant kernel from the committed ncu capture
                 with open(tpath) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
+                    tj = json.load(f)
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = (f"ncu dram read+write of one launch ({tj.get('instance')}); algorithmic bytes of that "
+                                f"launch {tj.get('algorithmic_bytes_per_launch')}, FLOP {tj.get('flop_per_launch')}")
             kernel_names = {"conv_rolling_xf": "conv_rolling_kernel<128,1> (tcgen05 rolling-row implicit GEMM + fused "
                                                "GroupNorm/SiLU operand transform)",
                             "conv_rolling": "conv_rolling_kernel<128,0> (tcgen05 rolling-row implicit GEMM)",
@@ -277,7 +280,7 @@ def run_b200_arm(args):
             roof = {
                 "bound": "tensor", "kernel": kernel_names[top],
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+                "frac": achieved / peaks["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["src"] + " sustained",
                 "flop_per_launch": cw / cn, "avg_launch_ms": cms / cn, "launches_per_forward": cn,
                 "share_of_forward": cms / fwd_ms,
