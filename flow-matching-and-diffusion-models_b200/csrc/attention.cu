@@ -129,6 +129,13 @@ constexpr int kAtt8Threads = kAtt8Warps * 32;
 constexpr int kAtt8KeyChunk = 1024;            // keys staged per pass
 constexpr int kAtt8VtStride = kAtt8KeyChunk + 8;  // +8 bf16 (16 B) padding: conflict-free transposed reads
 
+// 2^x on the special-function unit without exp2f()'s range fix-ups (inputs are <= 0 after the running-max shift; -inf -> 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void mma_m16n8k8_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -202,16 +209,16 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0 * scale_log2e), mn1 = fmaxf(m1, mx1 * scale_log2e);
-      const float corr0 = exp2f(m0 - mn0), corr1 = exp2f(m1 - mn1);
+      const float corr0 = ex2_approx(m0 - mn0), corr1 = ex2_approx(m1 - mn1);
       m0 = mn0; m1 = mn1;
       l0 *= corr0; l1 *= corr1;
       o[0] *= corr0; o[1] *= corr0; o[2] *= corr1; o[3] *= corr1;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -mn0));
-        const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -mn0));
-        const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -mn1));
-        const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -mn1));
+        const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, -mn0));
+        const float p1 = ex2_approx(fmaf(s[j][1], scale_log2e, -mn0));
+        const float p2 = ex2_approx(fmaf(s[j][2], scale_log2e, -mn1));
+        const float p3 = ex2_approx(fmaf(s[j][3], scale_log2e, -mn1));
         l0 += p0 + p1;
         l1 += p2 + p3;
         const uint32_t pa0 = pack_bf16x2(p0, p1), pa1 = pack_bf16x2(p2, p3);

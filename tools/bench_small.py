@@ -55,6 +55,14 @@ def main():
     res["gn_apply_level0_ms"] = timeit(lambda: ops.group_norm([yc], 32, 1e-5, gamma, beta, silu=True), flush)
     xs = torch.randn(B, 256, 256, 128, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2)
     res["upsample_256to512_c128_ms"] = timeit(lambda: ops.upsample_nearest2x(xs), flush)
+    # attention as in the LDCT level-4 blocks: 64 heads x head_dim 8, T = 1024, qkv packed [B][T][3C]
+    C_, T = 512, 1024
+    qkv = torch.randn(B, T, 3 * C_, device=dev, dtype=torch.bfloat16)
+    o = torch.empty(B, T, C_, device=dev, dtype=torch.bfloat16)
+    res["attention_T1024_h64_d8_ms"] = timeit(
+        lambda: ops.attention(qkv, qkv[:, :, C_:], qkv[:, :, 2 * C_:], o, batch=B, heads=64, tq=T, tk=T, head_dim=8,
+                              q_strides=(T * 3 * C_, 8, 3 * C_), kv_strides=(T * 3 * C_, 8, 3 * C_),
+                              o_strides=(T * C_, 8, C_)), flush)
     print(json.dumps({k: round(v, 4) for k, v in res.items()}))
 
 
