@@ -125,6 +125,43 @@ def cpu_port_rate(n_euler: int, repeats: int, warmup: int, batch: int = 1):
     return batch / (per_euler * EULER_STEPS), per_euler, cores
 
 
+def gpu_eager_rate(dev, batch: int, mode: str, repeats: int = 3):
+    """Reported context, not the product: the oracle's plain-PyTorch restatement of the reference denoiser run EAGERLY
+    on the same B200 (cuDNN / cuBLAS / ATen kernels, NCHW fp32 with TF32 convs, or autocast bf16 + channels_last),
+    i.e. what the unmodified reference modules would do on this GPU.  samples/s extrapolated from the forward time
+    (the scheduler step is < 0.1 % of it)."""
+    from oracle import denoiser as OD
+
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.to(dev) for k, v in _random_state_dict().items()}
+    noise, cond = synthetic_inputs(batch, 42, dev)
+    if mode == "bf16":
+        sd = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+        noise = noise.contiguous(memory_format=torch.channels_last)
+        cond = cond.contiguous(memory_format=torch.channels_last)
+    t = torch.full((batch,), 500.0, device=dev)
+
+    def fwd():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            return OD.unet_diffusers_nd_forward(sd, LDCT_UNET, noise, t, conditioning="concatenate", channels=1,
+                                                context=cond)
+
+    with torch.no_grad():
+        for _ in range(2):
+            fwd()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            fwd()
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / repeats
+    return batch / (ms * 1e-3 * EULER_STEPS), ms
+
+
 def _random_state_dict():
     """Reference-format random-init state_dict (seed 0) without needing a GPU: built from the module mirror's
     parameter shapes (identical to the reference's under the same seed, tests/test_api_conformance.py)."""
@@ -295,6 +332,14 @@ def run_b200_arm(args):
                                       "write bf16"},
                 "per_kernel_ms_per_forward": {k: round(v[1], 3) for k, v in by.items()},
             }
+            if args.eager_baseline:
+                eager = {}
+                for mode in ("fp32_tf32", "bf16"):
+                    rate, ms = gpu_eager_rate(dev, B, mode)
+                    eager[mode] = {"value": rate, "unit": "samples/s", "forward_ms": ms}
+                roof["gpu_eager_reference"] = dict(
+                    eager, note="oracle restatement of the reference modules, eager PyTorch on the same B200 "
+                                "(fp32_tf32: NCHW fp32 weights, TF32 convs; bf16: autocast + channels_last); context only")
             if not args.no_cpu_baseline:
                 rate, per_euler, cores = cpu_port_rate(1, repeats=2, warmup=0)
                 cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
@@ -337,6 +382,8 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=("b200", "reference"))
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU (headline: 16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-baseline", action="store_true",
+                    help="also time the reference's plain-PyTorch path eagerly on the GPU (context figure)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
