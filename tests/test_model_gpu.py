@@ -114,6 +114,7 @@ def test_attention_blocks():
     ("mnist32_concat", MNIST_UNET, "concatenate", 32, 3),
     ("ldct64_concat", LDCT_SMALL, "concatenate", 64, 2),
     ("ldct160_concat", LDCT_SMALL, "concatenate", 160, 1),  # rows >= 65 px: rolling-row convs with the fused GroupNorm
+    ("ldct512_concat", LDCT_SMALL, "concatenate", 512, 2),  # the headline resolution (BASELINE configs[1]), full arch
     ("compvis32_concat", COMPVIS_SMALL, "concatenate", 32, 2),
 ])
 def test_denoiser_forward_parity(name, cfg, cond, hw, B):
@@ -226,3 +227,32 @@ def test_sampling_loop_parity(sched, steps):
     b = sample_with_scheduler(model, mine, steps, noise.shape, torch.device(DEV), conditioning_mode="concatenate",
                               conditioning_batch=cond, init_sample=noise, use_cuda_graph=False, **kw)
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_full_size_properties():
+    """Size-independent properties at the headline size (LDCT arch, 512x512): run-to-run determinism (bit for bit),
+    per-sample independence of the batch (sample i of a batch of 3 == the same sample run alone up to the bf16 rounding
+    noise: the strip height of the conv schedule, hence the fp32 summation order of the GroupNorm partials, depends on
+    the batch size), and graph-replayed == step-by-step sampling for a short trajectory (bit for bit)."""
+    from fmdm_b200.pipelines.utils import build_scheduler, sample_with_scheduler
+
+    model, _ = build(LDCT_SMALL, "concatenate", seed=4)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(3, 1, 512, 512, generator=g).to(DEV)
+    c = torch.rand(3, 1, 512, 512, generator=g).to(DEV)
+    t = torch.full((3,), 640.25, device=DEV)
+    with torch.no_grad():
+        full = model(x, t, context=c)
+        again = model(x, t, context=c)
+        one = model(x[1:2], t[1:2], context=c[1:2])
+    assert torch.equal(full, again)
+    assert rel_l2(full[1:2], one) < 1e-2
+    assert not torch.equal(full[0:1], full[1:2])
+    assert torch.isfinite(full).all() and float(full.std()) > 0
+    sched, _ = build_scheduler({"name": "flow_match_euler", "params": {}}, {})
+    with torch.no_grad():
+        a = sample_with_scheduler(model, sched, 3, tuple(x.shape), torch.device(DEV), conditioning_mode="concatenate",
+                                  conditioning_batch=c, init_sample=x)
+        b = sample_with_scheduler(model, sched, 3, tuple(x.shape), torch.device(DEV), conditioning_mode="concatenate",
+                                  conditioning_batch=c, init_sample=x, use_cuda_graph=False)
+    assert torch.equal(a, b)
