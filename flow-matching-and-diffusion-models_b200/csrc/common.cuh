@@ -99,9 +99,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -144,14 +141,6 @@ __device__ __forceinline__ void tma_load_4d(const void* desc, uint32_t bar, uint
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
-      "%7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 __device__ __forceinline__ void tma_store_4d(const void* desc, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(desc)),
@@ -175,16 +164,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
 template <int kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, single-CTA.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 // ---- CTA-pair (cta_group::2) variants ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -229,16 +208,6 @@ template <int kCols>
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
-// D[tmem of both CTAs] (+)= A[smem of both CTAs, 128 rows each] * B[smem, N/2 rows in each CTA]; leader CTA only.
-__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                  uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // Arrive on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair once the MMAs have completed.
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   asm volatile(
@@ -264,21 +233,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128B-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B).
-// Field layout follows cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64).
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;            // LBO (unused for swizzled K-major; CUTLASS sets 1)
-  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: 8 rows * 128 B
-  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-  return d;
-}
-// The same descriptor split into its constant upper word and the address-dependent lower word, for single-thread issue
-// loops that must stay short (the issuing thread has ~64 cycles per MMA): lower word = start>>4 | LBO; advancing the
-// start address by 32 B (one K = 16 step) adds 2 to it.
+// K-major, 128B-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B), field
+// layout of cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major; 1), SBO>>4 [32,46)
+// = 8 rows * 128 B, version 1 [46,48), layout SWIZZLE_128B (2) [61,64).  It is kept split into its constant upper word
+// and the address-dependent lower word, because the single issuing thread has ~64 cycles per MMA and its loop must stay
+// short: lower word = start>>4 | LBO; advancing the start address by 32 B (one K = 16 step) adds 2 to it.  The swizzle is
+// a function of the absolute shared-memory address, so a start address that is a whole number of 128-byte rows into a
+// TMA-written tile (the kw-shifted views of a halo row) is still a valid operand (measured: phase bits must stay 0).
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) {
   return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);

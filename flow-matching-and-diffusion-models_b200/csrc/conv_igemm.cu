@@ -1,19 +1,19 @@
 // K1: conv2d (3x3 s1/s2, 1x1) as an implicit GEMM on tcgen05 tensor cores.
 //
 //   M = B*Ho*Wo output pixels, N = Cout, K = sum over segments of taps*C.
-//   A (activations, NHWC bf16) is never im2col'ed in memory: for every (tap, 64-channel block) one TMA tiled load
-//   of the box (64 ch, Wt, Ht, Nt) shifted by (kw-pad, kh-pad) lands a 128x64 K-major, 128B-swizzled operand tile
-//   in shared memory; TMA's out-of-bounds zero fill implements the conv padding, the ragged image edge and the
-//   channel tail.  Stride-2 convs use the tensor map's element strides.  The skip-connection torch.cat
-//   (legacy_unet.py:150) is a second K segment (another tensor map), never a copy.
+//   A (activations, NHWC bf16) is never im2col'ed in memory: TMA tiled loads of shifted boxes land K-major,
+//   128B-swizzled operand tiles in shared memory; TMA's out-of-bounds zero fill implements the conv padding, the
+//   ragged image edge and the channel tail.  Stride-2 convs use the tensor map's element strides.  The
+//   skip-connection torch.cat (legacy_unet.py:150) is a second K segment (another tensor map), never a copy.
 //   B (weights) is a pre-packed [Cout][Ktot] K-major bf16 matrix, TMA-loaded as (64, BLOCK_N) boxes.
 //   D accumulates in TMEM (fp32, 128 lanes x BLOCK_N columns); one elected thread issues tcgen05.mma.
 //   Epilogue warps read TMEM with tcgen05.ld, add bias / per-sample time-embedding vector / residual, optionally
 //   accumulate GroupNorm partial sums for the consumer norm, convert to bf16, stage the tile in 128B-swizzled
 //   shared memory and write it with one TMA store per 64-channel slab (the store clips ragged tiles).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (warp w owns TMEM lanes 32*(w%4)..+31).  Reference op replaced: nn.Conv2d via ConvND.forward
+// Two kernels share this file's host code: the persistent per-tile kernel below (any tile box, stride 1/2, 1x1) and
+// the rolling-row kernel of conv_rolling.cuh (stride-1 3x3 on rows >= 65 px, optional fused GroupNorm operand
+// transform).  plan_conv() picks one from the shapes.  Reference op replaced: nn.Conv2d via ConvND.forward
 // (src/nn/ops/convolution.py:53-54) and the adds around it in ResBlockND.forward (src/nn/blocks/residual.py:97-120).
 #include <cstdarg>
 #include <cstdlib>
@@ -26,7 +26,6 @@ namespace fm {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                      // 64 bf16 = 128 B = one swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;    // 16 KB
-constexpr int kConvThreads = 192;
 
 struct alignas(64) ConvKernelParams {
   CUtensorMap src[FM_CONV_MAX_SEG];
