@@ -48,7 +48,7 @@ class ConvParams(C.Structure):
         ("residual", C.c_void_p),
         ("out", C.c_void_p),
         ("gn_stats", C.c_void_p),
-        ("gn_groups", C.c_int32),
+        ("out_upsample", C.c_int32),
         ("_pad2", C.c_int32),
     ]
 

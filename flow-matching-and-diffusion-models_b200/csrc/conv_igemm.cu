@@ -31,6 +31,8 @@ struct alignas(64) ConvKernelParams {
   CUtensorMap src[FM_CONV_MAX_SEG];
   CUtensorMap wgt;
   CUtensorMap out;
+  CUtensorMap out_up[3];            // out_upsample: the (dy, dx) = (0,1), (1,0), (1,1) phases of the 2x output
+  int n_out;                        // 1, or 4 with out_upsample
   int nseg;
   int seg_c[FM_CONV_MAX_SEG];       // channels per segment
   int seg_taps[FM_CONV_MAX_SEG];    // 1 or 9
@@ -459,7 +461,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
 #pragma unroll
           for (int slab = 0; slab < Cfg::kHalfCols / 64; ++slab) {
             if (ncol0 + slab * 64 < p.Cout)
-              tma_store_4d(&p.out, stg_u32 + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
+              for (int u = 0; u < p.n_out; ++u)
+                tma_store_4d(u == 0 ? &p.out : &p.out_up[u - 1], stg_u32 + slab * (kTileM * 128), ncol0 + slab * 64,
+                             w0, h0, n0);
           }
           tma_store_commit();
         }
@@ -512,6 +516,28 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, 
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d N=%d box=%d,%d,%d stride=%d) failed: %d", C, W, H, N, bw, bh,
               bn, estride, (int)r);
+    return (int)r;
+  }
+  return 0;
+}
+
+// Output map of one phase (dy, dx) of a nearest-2x upsampled store: the pixels (2h+dy, 2w+dx) of [N][2H][2W][C] seen as
+// an [N][H][W][C] tensor with doubled pixel / row strides.
+static int encode_up_phase_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bn,
+                               int dy, int dx) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return FM_ERR_NO_DEVICE; }
+  const char* base = static_cast<const char*>(ptr) + ((size_t)dy * 2 * W + dx) * C * 2;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)2 * C * 2, (cuuint64_t)4 * W * C * 2, (cuuint64_t)4 * H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(upsampled out C=%d W=%d H=%d N=%d phase %d,%d) failed: %d", C, W, H, N, dy, dx,
+              (int)r);
     return (int)r;
   }
   return 0;
@@ -722,7 +748,16 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   kp.num_k_blocks = nk;
   const int block_n = pl.block_n;
   if (int e = encode_wgt_map(&kp.wgt, p->weight, ktot, p->Cout, pl.pair ? block_n / 2 : block_n)) return e;
-  if (int e = encode_act_map(&kp.out, p->out, p->Cout, pl.Wo, pl.Ho, p->B, kp.Wt, kp.Ht, kp.Nt, 1)) return e;
+  kp.n_out = 1;
+  if (p->out_upsample) {
+    for (int u = 0; u < 4; ++u)
+      if (int e = encode_up_phase_map(u == 0 ? &kp.out : &kp.out_up[u - 1], p->out, p->Cout, pl.Wo, pl.Ho, p->B, kp.Wt,
+                                      kp.Ht, kp.Nt, u >> 1, u & 1))
+        return e;
+    kp.n_out = 4;
+  } else if (int e = encode_act_map(&kp.out, p->out, p->Cout, pl.Wo, pl.Ho, p->B, kp.Wt, kp.Ht, kp.Nt, 1)) {
+    return e;
+  }
   kp.bias = p->bias;
   kp.addvec = p->addvec;
   kp.addvec_stride = p->addvec_stride;

@@ -505,7 +505,9 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
 #pragma unroll
           for (int slab = 0; slab < BLOCK_N / 64; ++slab) {
             if (ncol0 + slab * 64 < p.Cout)
-              tma_store_4d(&p.out, stg_u32 + slab * (kTileM * 128), ncol0 + slab * 64, w0, h0, n0);
+              for (int u = 0; u < p.n_out; ++u)
+                tma_store_4d(u == 0 ? &p.out : &p.out_up[u - 1], stg_u32 + slab * (kTileM * 128), ncol0 + slab * 64,
+                             w0, h0, n0);
           }
           tma_store_commit();
         }

@@ -186,17 +186,22 @@ class DiffusersAttentionND(nn.Module):
         self.dropout = dropout
         self._cache = ParamCache()
 
-    def forward(self, hidden_states: torch.Tensor, context: torch.Tensor | None = None) -> torch.Tensor:
+    def forward(self, hidden_states: torch.Tensor, context: torch.Tensor | None = None,
+                upsample_out: bool = False) -> torch.Tensor:
+        """upsample_out (fast path only): return the block output nearest-2x upsampled, folded into the store of the
+        output projection (a following UpsampleND's F.interpolate)."""
         b, c = hidden_states.shape[:2]
         spatial = hidden_states.shape[2:]
         if self.context_dim is not None:
             if context is None:
                 raise ValueError("DiffusersAttentionND cross-attention requires a non-empty context tensor.")
             out_of_scope("DiffusersAttentionND cross-attention")
-            return self._eager(hidden_states.float(), context.float())
+            y = self._eager(hidden_states.float(), context.float())
+            return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
         if len(spatial) != 2 or c % 8 or self.head_dim not in (8, 16, 32, 64) or (self.training and self.dropout > 0):
             out_of_scope(f"DiffusersAttentionND(spatial={tuple(spatial)}, head_dim={self.head_dim})")
-            return self._eager(hidden_states.float(), None)
+            y = self._eager(hidden_states.float(), None)
+            return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
         x = ops.to_nhwc_bf16(hidden_states)
         hh, ww = spatial
         t = hh * ww
@@ -219,7 +224,8 @@ class DiffusersAttentionND(nn.Module):
         ops.attention(flat, flat[c:], flat[2 * c:], att.permute(0, 2, 3, 1).reshape(-1), batch=b, heads=self.heads,
                       tq=t, tk=t, head_dim=hd, q_strides=(t * 3 * c, hd, 3 * c), kv_strides=(t * 3 * c, hd, 3 * c),
                       o_strides=(t * c, hd, c))
-        return ops.conv2d([att], wout, bias=f32(self.to_out[0].bias), residual=x, want_stats=True)
+        return ops.conv2d([att], wout, bias=f32(self.to_out[0].bias), residual=x, want_stats=not upsample_out,
+                          upsample_out=upsample_out)
 
     def _eager(self, hidden_states, context):
         b, c = hidden_states.shape[:2]

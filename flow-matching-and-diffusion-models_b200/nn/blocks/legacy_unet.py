@@ -76,14 +76,23 @@ class UpBlock2DCompat(nn.Module):
     def forward(self, hidden_states: torch.Tensor, res_hidden_states_tuple, temb: torch.Tensor,
                 context: torch.Tensor | None = None):
         pending = list(res_hidden_states_tuple)
+        # the nearest-2x of the upsampler is folded into the store of whichever conv produces its input (the last
+        # ResBlock's conv2 or the last attention's output projection)
+        fuse_up = (self.upsamplers is not None and len(self.upsamplers) == 1 and hidden_states.is_cuda
+                   and self.upsamplers[0].can_fuse_into_producer() and context is None)
+        last = len(self.resnets) - 1
         for idx, resnet in enumerate(self.resnets):
             skip = pending.pop()
-            hidden_states = resnet((hidden_states, skip), temb)  # virtual concat, hidden first
+            up_here = fuse_up and idx == last and self.attentions is None
+            hidden_states = resnet((hidden_states, skip), temb, upsample_out=up_here) if up_here \
+                else resnet((hidden_states, skip), temb)  # virtual concat, hidden first
             if self.attentions is not None:
-                hidden_states = self.attentions[idx](hidden_states, context=context)
+                up_here = fuse_up and idx == last
+                hidden_states = self.attentions[idx](hidden_states, context=context, upsample_out=True) if up_here \
+                    else self.attentions[idx](hidden_states, context=context)
         if self.upsamplers is not None:
             for up in self.upsamplers:
-                hidden_states = up(hidden_states)
+                hidden_states = up(hidden_states, upsampled=True) if fuse_up else up(hidden_states)
         return hidden_states
 
 

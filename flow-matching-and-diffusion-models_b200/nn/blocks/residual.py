@@ -143,8 +143,9 @@ class ResBlockND(TimestepBlock):
         key = "tail:" + ",".join(map(str, split))
         return self._cache.get(key, [w2, ws, self.conv2.conv.bias, skip.conv.bias], build)
 
-    def forward(self, x, emb: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x: (N, C, H, W) tensor, or a tuple of tensors read as their channel concat (never materialised)."""
+    def forward(self, x, emb: Optional[torch.Tensor] = None, upsample_out: bool = False) -> torch.Tensor:
+        """x: (N, C, H, W) tensor, or a tuple of tensors read as their channel concat (never materialised).
+        upsample_out (fast path only): return the result nearest-2x upsampled (folded into conv2's store)."""
         srcs = list(x) if isinstance(x, (tuple, list)) else [x]
         if not self._fast_ok() or not srcs[0].is_cuda:
             if srcs[0].is_cuda:
@@ -152,7 +153,8 @@ class ResBlockND(TimestepBlock):
                              f"act={self.act_name}, training dropout={self.dropout})")
             else:
                 ops.require_cuda(srcs[0], "ResBlockND.forward")
-            return self._eager(torch.cat([s.float() for s in srcs], 1), emb)
+            y = self._eager(torch.cat([s.float() for s in srcs], 1), emb)
+            return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
         srcs = [ops.to_nhwc_bf16(s) for s in srcs]
         if sum(s.shape[1] for s in srcs) != self.channels:
             raise ValueError(f"ResBlockND expected {self.channels} input channels")
@@ -205,10 +207,10 @@ class ResBlockND(TimestepBlock):
             if len(srcs) != 1:
                 srcs = [ops.to_nhwc_bf16(torch.cat(srcs, 1))]
             return ops.conv2d([h], self.conv2.packed([self.out_channels]), bias=f32(self.conv2.conv.bias),
-                              residual=srcs[0], want_stats=True, norm=n2)
+                              residual=srcs[0], want_stats=not upsample_out, norm=n2, upsample_out=upsample_out)
         pw, bias = self._fused_tail_weight(split)
-        return ops.conv2d([h] + srcs, pw, bias=bias, want_stats=True,
-                          norm=None if n2 is None else n2 + [None] * len(srcs))
+        return ops.conv2d([h] + srcs, pw, bias=bias, want_stats=not upsample_out,
+                          norm=None if n2 is None else n2 + [None] * len(srcs), upsample_out=upsample_out)
 
     # eager PyTorch restatement used only for out-of-scope variants (FMDM_B200_ALLOW_EAGER=1)
     def _eager(self, x: torch.Tensor, emb):

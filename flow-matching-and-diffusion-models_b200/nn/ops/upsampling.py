@@ -21,8 +21,15 @@ class UpsampleND(nn.Module):
         if use_conv:
             self.conv = ConvND(spatial_dims, channels, channels, kernel_size=3, padding=1)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def can_fuse_into_producer(self) -> bool:
+        """True when the producer of the input may store it already upsampled (`ops.conv2d(upsample_out=True)`) and
+        call `forward(x, upsampled=True)`."""
+        return self.spatial_dims == 2 and self.channels % 8 == 0 and self.use_conv and self.conv.fast_path_ok()
+
+    def forward(self, x: torch.Tensor, upsampled: bool = False) -> torch.Tensor:
         assert x.shape[1] == self.channels
+        if upsampled:
+            return self.conv(ops.to_nhwc_bf16(x), want_stats=True)
         if self.spatial_dims != 2 or self.channels % 8:
             out_of_scope(f"UpsampleND(spatial_dims={self.spatial_dims}, channels={self.channels})")
             y = F.interpolate(x.float(), scale_factor=2, mode="nearest")

@@ -155,8 +155,12 @@ def conv2d(
     out: Optional[torch.Tensor] = None,
     want_stats: bool = False,
     norm: Optional[Sequence] = None,
+    upsample_out: bool = False,
 ) -> torch.Tensor:
     """Implicit-GEMM conv over the virtual channel concat of `srcs` (one K segment per source).
+
+    upsample_out: the result is stored nearest-2x upsampled ([B, Cout, 2Ho, 2Wo]): the F.interpolate of a following
+    UpsampleND folded into this conv's store (4 TMA stores of each staged tile).
 
     norm: per source, None or a `NormTable` slice `(table, channel_offset)` — that source is read through the fused
     operand transform act(a*x+b) (GroupNorm apply + SiLU folded into the conv; see `conv_operand_norm_ok`).
@@ -190,10 +194,13 @@ def conv2d(
     p.stride = stride
     p.Cout = weight.cout
     ho, wo = (h + stride - 1) // stride, (w + stride - 1) // stride
+    oh, ow = (2 * ho, 2 * wo) if upsample_out else (ho, wo)
     if out is None:
-        out = empty_nhwc(b, weight.cout, ho, wo, srcs[0].device)
+        out = empty_nhwc(b, weight.cout, oh, ow, srcs[0].device)
     else:
         _check_act(out, "conv2d(out)")
+        if tuple(out.shape) != (b, weight.cout, oh, ow):
+            raise ValueError("conv2d: out shape mismatch")
     p.weight = weight.mat.data_ptr()
     p.bias = _ptr(bias)
     if addvec is not None:
@@ -203,12 +210,12 @@ def conv2d(
         p.addvec_stride = addvec.stride(0)
     if residual is not None:
         _check_act(residual, "conv2d(residual)")
-        if residual.shape != out.shape:
+        if tuple(residual.shape) != (b, weight.cout, ho, wo):
             raise ValueError("conv2d: residual shape mismatch")
         p.residual = residual.data_ptr()
     p.out = out.data_ptr()
     p.gn_stats = None
-    p.gn_groups = 0
+    p.out_upsample = int(bool(upsample_out))
     stats_ws = None
     rpi = C.c_int32(0)
     if want_stats and weight.cout % 4 == 0 and lib.fm_conv_stats_rows(C.byref(p), C.byref(rpi)) == 0:
@@ -221,7 +228,10 @@ def conv2d(
         tag = {1: "conv_rolling", 2: "conv_rolling_xf"}.get(kind, "conv_tile")
         _prof_end(tag, 2.0 * b * ho * wo * weight.cout * weight.mat.shape[1], e0)
     if stats_ws is not None:
-        out._fm_stats = (stats_ws, rpi.value)
+        # with upsample_out the partials describe the [Ho][Wo] result; each value appears 4x in `out`, so the
+        # consumer's per-pixel count (out.H * out.W) must be divided by 4: not wired, no consumer norms an upsample
+        if not upsample_out:
+            out._fm_stats = (stats_ws, rpi.value)
     return out
 
 

@@ -86,7 +86,11 @@ typedef struct fm_conv_params {
   float* gn_stats;         /* fp32 [B*rows][Cout/4][2] workspace (fm_conv_stats_rows) receiving, per 32-row
                               group of every M tile, the channel-quad (sum, sumsq) of `out` for the consumer
                               GroupNorm (no atomics; folded by fm_groupnorm_finalize_partials), or NULL */
-  int32_t gn_groups;       /* unused (kept for layout stability) */
+  int32_t out_upsample;    /* 1: `out` is [B][2*Ho][2*Wo][Cout] and every output pixel is stored to its 2x2 block, i.e.
+                              the nearest-neighbour F.interpolate(scale_factor=2) that UpsampleND applies to this
+                              tensor (src/nn/ops/upsampling.py:27) is folded into the producer's store; residual
+                              and gn_stats still refer to the [Ho][Wo] result (its statistics equal the upsampled
+                              tensor's) */
   int32_t _pad2;
 } fm_conv_params;
 

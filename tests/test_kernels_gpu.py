@@ -407,3 +407,28 @@ def test_stem_fused_groupnorm_statistics():
         t_plain = ops.group_norm_table([y.clone(memory_format=torch.preserve_format)], 32, 1e-5, gamma, beta, silu=True)
         # the fused statistics see the fp32 accumulators, the plain pass their bf16 rounding
         assert float((t_fused.ab - t_plain.ab).abs().max()) < 5e-3 * float(t_plain.ab.abs().max())
+
+
+@pytest.mark.parametrize("case", [
+    (2, 5, 256, [128], 128, [3], 1, True, True, True),           # rolling rows
+    (1, 6, 200, [64, 128], 256, [3, 3], 1, True, True, False),   # rolling, two N tiles, ragged W
+    (3, 14, 14, [128], 128, [3], 1, True, True, True),           # per-tile kernel, several rows per tile
+    (2, 16, 16, [1024], 512, [3], 1, True, False, True),
+    (2, 32, 32, [256], 256, [1], 1, True, False, True),          # attention output projection shape (1x1 + residual)
+    (3, 7, 7, [128], 128, [3], 1, True, False, False),           # several images per tile
+], ids=lambda c: "B{}_{}x{}_cout{}".format(c[0], c[1], c[2], c[4]))
+def test_conv2d_upsampled_store(case):
+    """conv with the nearest-2x of a following UpsampleND folded into its store == interpolate(conv)."""
+    B, H, W, cins, cout, ks, stride, bias, addvec, residual = case
+    g = torch.Generator(device="cpu").manual_seed(5)
+    xs = [_bf16r(torch.randn(B, c, H, W, generator=g)).to(DEV) for c in cins]
+    ws = [_bf16r(torch.randn(cout, c, k, k, generator=g) / math.sqrt(c * k * k)).to(DEV) for c, k in zip(cins, ks)]
+    bvec = torch.randn(cout, generator=g).to(DEV)
+    av = torch.randn(B, cout, generator=g).to(DEV) if addvec else None
+    res = _bf16r(torch.randn(B, cout, H, W, generator=g)).to(DEV) if residual else None
+    packed = ops.pack_conv_weight([(w, 0, c) for w, c in zip(ws, cins)])
+    kw = dict(bias=bvec, addvec=av, residual=_nhwc(res) if residual else None)
+    plain = ops.conv2d([_nhwc(x) for x in xs], packed, **kw)
+    up = ops.conv2d([_nhwc(x) for x in xs], packed, upsample_out=True, **kw)
+    assert up.shape == (B, cout, 2 * H, 2 * W)
+    assert torch.equal(up.float(), F.interpolate(plain.float(), scale_factor=2, mode="nearest"))
