@@ -32,6 +32,7 @@ struct alignas(64) ConvKernelParams {
   CUtensorMap wgt;
   CUtensorMap out;
   CUtensorMap out_up[3];            // out_upsample: the (dy, dx) = (0,1), (1,0), (1,1) phases of the 2x output
+  CUtensorMap res;                  // residual, same geometry as the (un-upsampled) output (rolling kernel: TMA loads)
   int n_out;                        // 1, or 4 with out_upsample
   int nseg;
   int seg_c[FM_CONV_MAX_SEG];       // channels per segment
@@ -765,6 +766,8 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
              "conv: addvec must be 16B aligned with stride %% 4 == 0");
   FM_REQUIRE(p->bias == nullptr || ((uintptr_t)p->bias & 15) == 0, "conv: bias must be 16B aligned");
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
+  if (p->residual != nullptr && pl.rolling)
+    if (int e = encode_act_map(&kp.res, p->residual, p->Cout, pl.Wo, pl.Ho, p->B, kp.Wt, kp.Ht, kp.Nt, 1)) return e;
   FM_REQUIRE(p->residual == nullptr || ((uintptr_t)p->residual & 15) == 0, "conv: residual must be 16B aligned");
   kp.gn_partial = p->gn_stats;
   kp.log_wt = 0; while ((1 << kp.log_wt) < kp.Wt) ++kp.log_wt;

@@ -57,14 +57,16 @@ struct RConvCfg {
   static constexpr int kOutBufs = 2;
   static constexpr int kTailBytes = 512 + BLOCK_N * 4;
   static constexpr int kBudget = 227 * 1024 - 1024 - kTailBytes - kOutBufs * kOutBytes;
-  static constexpr int kAStages = 4;
+  // six A slots: a 1x1 segment's slot holds only 4 MMAs (256 tensor cycles); with four, a run of such slots drained the
+  // ring faster than TMA + transform refill it (level-0 ResBlock tails: +10 % with six, plain 3x3 convs unchanged)
+  static constexpr int kAStages = 6;
   static constexpr int kBStagesRaw = (kBudget - kAStages * kASlot) / kBBytes;
   static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
   static constexpr int kPipeBytes = kAStages * kASlot + kBStages * kBBytes;
-  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 2 * kRollAccBufs + XF * kAStages;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 2 * kRollAccBufs + 2 + XF * kAStages;
   static constexpr int kSmemBytes = 1024 + kPipeBytes + kOutBufs * kOutBytes + kTailBytes;
   static constexpr int kTmemCols = kRollAccBufs * BLOCK_N;
-  static_assert(kBStages >= 6, "weight pipeline too shallow");
+  static_assert(kBStages >= 7, "weight pipeline too shallow");
   static_assert(kNumBars * 8 + 8 <= 512, "barrier area");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -98,7 +100,8 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
   auto t_full = [&](int b) { return bar_base + 8u * (kBarT + b); };
   auto t_empty = [&](int b) { return bar_base + 8u * (kBarT + kRollAccBufs + b); };
-  auto a_ready = [&](int s) { return bar_base + 8u * (kBarT + 2 * kRollAccBufs + s); };  // XF only
+  auto r_full = [&](int b) { return bar_base + 8u * (kBarT + 2 * kRollAccBufs + b); };   // residual tile landed
+  auto a_ready = [&](int s) { return bar_base + 8u * (kBarT + 2 * kRollAccBufs + 2 + s); };  // XF only
   const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(out_gen + Cfg::kOutBufs * Cfg::kOutBytes + 8 * Cfg::kNumBars);
@@ -110,11 +113,14 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.src[s]);
     tma_prefetch_desc(&p.wgt);
     tma_prefetch_desc(&p.out);
+    if (p.residual != nullptr) tma_prefetch_desc(&p.res);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kBarT + kRollAccBufs; ++s) mbar_init(bar_base + 8u * s, 1);
       for (int b = 0; b < kRollAccBufs; ++b) mbar_init(t_empty(b), kEpiWarps * 2);
+      mbar_init(r_full(0), 1);
+      mbar_init(r_full(1), 1);
       if (XF) for (int s = 0; s < Cfg::kAStages; ++s) mbar_init(a_ready(s), kXfWarps * 2);
       fence_barrier_init();
     }
@@ -131,13 +137,11 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
   const int first_unit = (int)blockIdx.x >> 1;
   const int unit_stride = (int)gridDim.x >> 1;
   // this CTA's strip of a unit: 128 pixels starting at w0 of rows [h_begin, h_end) of image n
-  int strip_chunk = 0;  // row chunk of the strip decoded last (epilogue: statistics row)
   auto strip_coords = [&](int unit, int& tw, int& w0, int& n, int& h_begin, int& h_end, int& ncol0) {
     const int ps = unit / p.n_tiles;
     ncol0 = (unit - ps * p.n_tiles) * BLOCK_N;
     const int sid = ps * 2 + (int)cta_rank;
     const int chunk = sid / sch.combos;
-    strip_chunk = chunk;
     const int j = sid - chunk * sch.combos;
     n = j / p.tiles_w;
     tw = j - n * p.tiles_w;
@@ -145,6 +149,7 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
     h_begin = chunk * sch.R;
     h_end = h_begin + sch.R;
     if (h_end > p.Ho) h_end = p.Ho;
+    return chunk;
   };
   // taps of input row r that land on output rows of [h_begin, h_end): kh in [kh_lo, kh_hi], output row o = r + 1 - kh
   auto kh_range = [](int r, int h_begin, int h_end, int& kh_lo, int& kh_hi) {
@@ -359,9 +364,24 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
     constexpr int kWarpCols = BLOCK_N / 2;
     constexpr int kWarpChunks = kWarpCols / 8;
     int oc = 0, stage_use = 0;
+    // Residual tiles arrive by TMA, in the staging buffer's own swizzled layout, ONE TILE AHEAD of their use (issued by
+    // the store thread while the previous tile is processed): with synchronous loads the epilogue paid a global-memory
+    // latency per tile and became the pacer of every conv with an identity skip (+20 % run time at level 0).
+    auto load_residual = [&](int use, int rw0, int rh0, int rn0, int rncol0) {
+      const uint32_t dst = smem_out + (use & 1) * Cfg::kOutBytes, bar = r_full(use & 1);
+      mbar_expect_tx(bar, Cfg::kOutBytes);
+#pragma unroll
+      for (int slab = 0; slab < BLOCK_N / 64; ++slab)  // slabs past Cout are zero-filled by TMA (bytes still counted)
+        tma_load_4d(&p.res, bar, dst + slab * (kTileM * 128), rncol0 + slab * 64, rw0, rh0, rn0);
+    };
+    if (store_issuer && p.residual != nullptr && first_unit < total_units) {
+      int tw, w0, n0, h_begin, h_end, ncol0;
+      strip_coords(first_unit, tw, w0, n0, h_begin, h_end, ncol0);
+      load_residual(0, w0, h_begin, n0, ncol0);
+    }
     for (int unit = first_unit; unit < total_units; unit += unit_stride) {
       int tw, w0, n0, h_begin, h_end, ncol0;
-      strip_coords(unit, tw, w0, n0, h_begin, h_end, ncol0);
+      const int strip_chunk = strip_coords(unit, tw, w0, n0, h_begin, h_end, ncol0);
       // GroupNorm partial statistics accumulate over the rows of the strip (one global row per strip and lane quadrant)
       float st_acc[kWarpCols / 32];
 #pragma unroll
@@ -387,36 +407,6 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
         if (store_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
 
-        if (p.residual != nullptr) {
-          // coalesced 16-byte reads of this warp's 32 rows x kWarpCols columns, staged into the swizzled tile
-          // (issued before the accumulator wait: the global latency hides behind the main loop)
-#pragma unroll
-          for (int i0 = 0; i0 < kWarpChunks; i0 += 8) {
-            constexpr int kU = kWarpChunks < 8 ? kWarpChunks : 8;
-            uint4 buf4[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const int idx = (i0 + u) * 32 + lane;
-              const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
-              const int pw = w0 + quad * 32 + rl;
-              const int col = ncol0 + ch * 8;
-              buf4[u] = make_uint4(0, 0, 0, 0);
-              if (pw < p.Wo && n0 < p.B && col < p.Cout)
-                buf4[u] = *reinterpret_cast<const uint4*>(p.residual +
-                                                          (((size_t)n0 * p.Ho + h0) * p.Wo + pw) * p.Cout + col);
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const int idx = (i0 + u) * 32 + lane;
-              const int rl = idx / kWarpChunks, ch = cgrp * kWarpChunks + idx % kWarpChunks;
-              const int rr = quad * 32 + rl;
-              uint8_t* dst = stg + (ch >> 3) * (kTileM * 128) + rr * 128 + (((ch & 7) ^ (rr & 7)) * 16);
-              *reinterpret_cast<uint4*>(dst) = buf4[u];
-            }
-          }
-          __syncwarp();
-        }
-
         mbar_wait(t_full(buf), (oc >> 2) & 1);
         tc_fence_after();
 
@@ -434,6 +424,24 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
         if (lane == 0)
           asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(t_empty_leader0 + 8u * buf)
                        : "memory");
+        if (p.residual != nullptr) {
+          if (store_issuer) {
+            // next tile of this CTA: next row of the strip, else the first row of its next strip
+            int nw0 = w0, nh0 = h0 + 1, nn0 = n0, nncol0 = ncol0;
+            bool has_next = nh0 < h_end;
+            if (!has_next && unit + unit_stride < total_units) {
+              int ntw, nh_end;
+              strip_coords(unit + unit_stride, ntw, nw0, nn0, nh0, nh_end, nncol0);
+              has_next = true;
+            }
+            if (has_next) {
+              // the other staging buffer was last read by the previous tile's TMA store
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              load_residual(stage_use + 1, nw0, nh0, nn0, nncol0);
+            }
+          }
+          mbar_wait(r_full(stage_use & 1), (stage_use >> 1) & 1);
+        }
 
 #pragma unroll
         for (int i = 0; i < kWarpCols / 32; ++i) {

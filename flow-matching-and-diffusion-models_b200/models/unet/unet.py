@@ -26,13 +26,25 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
     """Sequential that routes `emb` to TimestepBlocks and `context` to ContextBlocks (`unet.py:18-39`)."""
 
     def forward(self, x, emb: torch.Tensor, context: Optional[torch.Tensor] = None):
-        for layer in self:
+        layers = list(self)
+        i = 0
+        while i < len(layers):
+            layer = layers[i]
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            first = x[0] if isinstance(x, (tuple, list)) else x
+            if (isinstance(layer, ResBlockND) and isinstance(nxt, UpsampleND) and nxt.can_fuse_into_producer()
+                    and first.is_cuda and layer._fast_ok()):
+                # the upsampler's nearest-2x is folded into the store of the ResBlock's last conv
+                x = nxt(layer(x, emb, upsample_out=True), upsampled=True)
+                i += 2
+                continue
             if isinstance(layer, TimestepBlock):
                 x = layer(x, emb)
             elif isinstance(layer, ContextBlock):
                 x = layer(x, context)
             else:
                 x = layer(x)
+            i += 1
         return x
 
 

@@ -14,6 +14,8 @@ SHAPES = [  # (Cin segments, Cout, k, stride, H(in), count per forward)
     ([128, 128], 128, 3, 1, 256, 2), ([256, 128], 128, 3, 1, 256, 1), ([128, 128], 128, 1, 1, 512, 3),
     ([256], 256, 3, 1, 64, 7), ([512], 512, 3, 1, 32, 7), ([512], 512, 3, 1, 16, 11), ([512, 512], 512, 3, 1, 32, 2),
     ([128], 128, 3, 2, 512, 1), ([512], 1536, 1, 1, 32, 5),
+    # ResBlock tail of the level-0 up blocks: conv2 3x3 (128 ch) + fused 1x1 skip conv over the (h, skip) concat
+    ([128, 128, 128], 128, (3, 1, 1), 1, 512, 3), ([128, 128, 128], 128, (3, 1, 1), 1, 256, 3),
 ]
 
 
@@ -27,31 +29,35 @@ def main():
     shapes = SHAPES if not sel else [SHAPES[int(i)] for i in sel.split(",")]
     for cins, cout, k, s, H, cnt in shapes:
         xs = [torch.randn(B, H, H, c, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2) for c in cins]
-        ws = [torch.randn(cout, c, k, k, device=dev) * 0.05 for c in cins]
+        ks = list(k) if isinstance(k, (tuple, list)) else [k] * len(cins)
+        ws = [torch.randn(cout, c, kk, kk, device=dev) * 0.05 for c, kk in zip(cins, ks)]
         pw = ops.pack_conv_weight([(w, 0, c) for w, c in zip(ws, cins)])
         bias = torch.randn(cout, device=dev)
         Ho = (H + s - 1) // s
         out = ops.empty_nhwc(B, cout, Ho, Ho, dev)
         norm = None
-        if os.environ.get("NORM") and s == 1 and k == 3:
+        if os.environ.get("NORM") and s == 1 and ks[0] == 3:
             tab = ops.NormTable(torch.rand(B, 2, sum(cins), device=dev) + 0.5, True)
             norm, off = [], 0
-            for c in cins:
-                norm.append((tab, off))
+            for c, kk in zip(cins, ks):
+                norm.append((tab, off) if kk == 3 else None)  # 1x1 skip segments read the raw input
                 off += c
+        res = None
+        if os.environ.get("RESIDUAL") and s == 1:
+            res = torch.randn(B, H, H, cout, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2)
         for _ in range(3):
-            ops.conv2d(xs, pw, stride=s, bias=bias, out=out, norm=norm)
+            ops.conv2d(xs, pw, stride=s, bias=bias, out=out, norm=norm, residual=res)
         ts = []
         for _ in range(5):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv2d(xs, pw, stride=s, bias=bias, out=out, norm=norm)
+            ops.conv2d(xs, pw, stride=s, bias=bias, out=out, norm=norm, residual=res)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         t = sorted(ts)[len(ts) // 2]
-        flops = 2.0 * B * Ho * Ho * cout * sum(cins) * k * k
+        flops = 2.0 * B * Ho * Ho * cout * sum(c * kk * kk for c, kk in zip(cins, ks))
         rows.append(dict(cin=cins, cout=cout, k=k, stride=s, H=H, ms=round(t, 4), tflops=round(flops / t / 1e9, 1)))
         tot_t += t * cnt
         tot_f += flops * cnt
