@@ -1,0 +1,61 @@
+"""Throughput of the other BASELINE.json configs through the same public API (context figures; the headline metric is
+bench.py's).  One JSON line per config: samples/s of complete graph-replayed sampling runs, inputs resident on the GPU."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import LDCT_UNET  # noqa: E402
+from fmdm_b200.models.generators import DiffusionUNetFactory  # noqa: E402
+from fmdm_b200.pipelines.utils import build_scheduler, sample_with_scheduler  # noqa: E402
+
+DEV = torch.device("cuda")
+MNIST = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layers_per_block": 2,
+         "block_out_channels": [64, 128, 128], "down_block_types": ["DownBlock2D", "AttnDownBlock2D", "DownBlock2D"],
+         "up_block_types": ["UpBlock2D", "AttnUpBlock2D", "UpBlock2D"]}
+COMPVIS = {"in_channels": 1, "out_channels": 1, "num_res_blocks": 2, "channel_mult": [1, 1, 2, 2, 4, 4],
+           "model_channels": 128, "attention_resolutions": [], "block_out_channels": [128, 128, 256, 256, 512, 512]}
+
+
+def run(name, cfg, cond, B, hw, sched_name, steps, reps=3, flop_per_sample_fwd=None):
+    torch.manual_seed(0)
+    m = DiffusionUNetFactory().build(cfg, cond, 1).to(DEV).eval()
+    for p in m.parameters():  # EfficientUNetND zero-initialises 74 tensors
+        if float(p.abs().sum()) == 0:
+            torch.nn.init.normal_(p, 0, 0.02)
+    params = {"beta_start": 1e-4, "beta_end": 0.02} if sched_name != "flow_match_euler" else {}
+    sch, _ = build_scheduler({"name": sched_name, "params": params}, {})
+    x = torch.randn(B, 1, hw, hw, device=DEV)
+    c = torch.rand(B, 1, hw, hw, device=DEV) if cond else None
+    kw = dict(conditioning_mode=cond, conditioning_batch=c, init_sample=x)
+    with torch.no_grad():
+        for _ in range(2):
+            sample_with_scheduler(m, sch, steps, tuple(x.shape), DEV, **kw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sample_with_scheduler(m, sch, steps, tuple(x.shape), DEV, **kw)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+    line = {"config": name, "batch": B, "hw": hw, "scheduler": sched_name, "steps": steps, "s_per_run": round(dt, 4),
+            "samples_per_s": round(B / dt, 2)}
+    if flop_per_sample_fwd:
+        line["model_tflops"] = round(B / dt * flop_per_sample_fwd * steps / 1e12, 1)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    run("configs[0] MNIST 28x28 uncond flow-matching, 50 Euler", MNIST, None, 64, 28, "flow_match_euler", 50,
+        flop_per_sample_fwd=2.3969e9)
+    run("configs[3] LDCT 256x256 DDIM 50", LDCT_UNET, "concatenate", 16, 256, "ddim", 50, flop_per_sample_fwd=4.9657e11)
+    run("configs[3] LDCT 256x256 DPM-Solver++ 20", LDCT_UNET, "concatenate", 16, 256, "dpm_multistep", 20,
+        flop_per_sample_fwd=4.9657e11)
+    run("configs[3] LDCT 512x512 DDIM 50", LDCT_UNET, "concatenate", 16, 512, "ddim", 50, reps=2,
+        flop_per_sample_fwd=1.9944e12)
+    run("configs[3] LDCT 512x512 DPM-Solver++ 20", LDCT_UNET, "concatenate", 16, 512, "dpm_multistep", 20, reps=2,
+        flop_per_sample_fwd=1.9944e12)
+    run("EfficientUNetND (compvis) LDCT 512x512 flow-matching, 50 Euler", COMPVIS, "concatenate", 16, 512,
+        "flow_match_euler", 50, reps=2, flop_per_sample_fwd=1.9726e12)
