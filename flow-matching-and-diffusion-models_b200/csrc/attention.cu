@@ -4,6 +4,8 @@
 // src/nn/blocks/legacy_unet.py:32) the op is exp-bound, not MMA-bound, so this CUDA-core
 // formulation is the baseline; a tensor-core variant is future work.
 // Replaces F.scaled_dot_product_attention (src/nn/blocks/attention.py:41-44).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fm {
@@ -240,6 +242,170 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
     *reinterpret_cast<uint32_t*>(ob + (int64_t)(q0 + g + 8) * o_st + 2 * t) = pack_bf16x2(o[2] * i1, o[3] * i1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// head_dim 16 / 32 / 64 (SpatialSelfAttention: 4 heads x 64 in the EfficientUNetND mid block and in the KL decoder,
+// where T = 4096 makes the scalar kernel above the largest item of the decode): flash attention on mma.sync m16n8k16
+// (bf16 in, fp32 accumulate).  One warp owns 16 query rows; per block of 64 keys S = Q K^T is HD/16 k-steps into
+// eight m16n8 accumulators, which - converted to bf16 - are exactly the A fragments of P V (two adjacent n-tiles form
+// one k = 16 step); K is staged row-major with 16 bytes of row padding, V transposed ([dim][key]), so every fragment
+// load is one conflict-free 32-bit shared-memory read.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kAttMWarps = 8;
+constexpr int kAttMThreads = kAttMWarps * 32;
+constexpr int kAttMKeyChunk = 128;  // keys staged per pass
+
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttMThreads) attention_mma_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+    __nv_bfloat16* __restrict__ out, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
+    int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float scale_log2e) {
+  constexpr int kKS = HD + 8;                  // K row stride (elements): +16 B => the 8 keys of a fragment hit 8 bank groups
+  constexpr int kVS = kAttMKeyChunk + 8;       // V^T row stride
+  constexpr int kSteps = HD / 16;              // k-steps of Q K^T
+  constexpr int kDimTiles = HD / 8;            // n-tiles of P V
+  __shared__ __align__(16) __nv_bfloat16 sK[kAttMKeyChunk * kKS];
+  __shared__ __align__(16) __nv_bfloat16 sVt[HD * kVS];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * (kAttMWarps * 16) + warp * 16;
+  const __nv_bfloat16* qb = q + b * q_sb + h * q_sh;
+  const __nv_bfloat16* kb = k + b * kv_sb + h * kv_sh;
+  const __nv_bfloat16* vb = v + b * kv_sb + h * kv_sh;
+
+  // Q fragments for every k-step (rows clamped; stores are masked)
+  const int r0 = min(q0 + g, Tq - 1), r1 = min(q0 + g + 8, Tq - 1);
+  uint32_t qa[kSteps][4];
+#pragma unroll
+  for (int kk = 0; kk < kSteps; ++kk) {
+    qa[kk][0] = *reinterpret_cast<const uint32_t*>(qb + (int64_t)r0 * q_st + kk * 16 + 2 * t);
+    qa[kk][1] = *reinterpret_cast<const uint32_t*>(qb + (int64_t)r1 * q_st + kk * 16 + 2 * t);
+    qa[kk][2] = *reinterpret_cast<const uint32_t*>(qb + (int64_t)r0 * q_st + kk * 16 + 8 + 2 * t);
+    qa[kk][3] = *reinterpret_cast<const uint32_t*>(qb + (int64_t)r1 * q_st + kk * 16 + 8 + 2 * t);
+  }
+  float o[kDimTiles][4];
+#pragma unroll
+  for (int n = 0; n < kDimTiles; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int c0 = 0; c0 < Tk; c0 += kAttMKeyChunk) {
+    const int nk = min(kAttMKeyChunk, Tk - c0);
+    const int nk_pad = (nk + 63) & ~63;
+    __syncthreads();
+    // stage K rows (16-byte chunks) and V transposed
+    for (int i = threadIdx.x; i < nk_pad * (HD / 8); i += kAttMThreads) {
+      const int j = i / (HD / 8), ch = i % (HD / 8);
+      uint4 kk4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
+      if (j < nk) {
+        kk4 = *reinterpret_cast<const uint4*>(kb + (int64_t)(c0 + j) * kv_st + ch * 8);
+        vv4 = *reinterpret_cast<const uint4*>(vb + (int64_t)(c0 + j) * kv_st + ch * 8);
+      }
+      *reinterpret_cast<uint4*>(sK + j * kKS + ch * 8) = kk4;
+      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv4);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) sVt[(ch * 8 + d) * kVS + j] = ve[d];
+    }
+    __syncthreads();
+
+    for (int kb0 = 0; kb0 < nk_pad; kb0 += 64) {
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const __nv_bfloat16* krow = sK + (kb0 + j * 8 + g) * kKS + 2 * t;
+#pragma unroll
+        for (int kk = 0; kk < kSteps; ++kk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + kk * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + kk * 16 + 8);
+          mma_m16n8k16_bf16(s[j], qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b0, b1);
+        }
+      }
+      if (kb0 + 64 > nk) {  // mask the padded keys of the last block
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int key = kb0 + j * 8 + 2 * t;
+          if (key >= nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+          if (key + 1 >= nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        }
+      }
+      float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0 * scale_log2e), mn1 = fmaxf(m1, mx1 * scale_log2e);
+      const float corr0 = ex2_approx(m0 - mn0), corr1 = ex2_approx(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      l0 *= corr0; l1 *= corr1;
+#pragma unroll
+      for (int n = 0; n < kDimTiles; ++n) { o[n][0] *= corr0; o[n][1] *= corr0; o[n][2] *= corr1; o[n][3] *= corr1; }
+      uint32_t pa[8][2];  // P as bf16x2: [n-tile][row g | row g+8]
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, -mn0));
+        const float p1 = ex2_approx(fmaf(s[j][1], scale_log2e, -mn0));
+        const float p2 = ex2_approx(fmaf(s[j][2], scale_log2e, -mn1));
+        const float p3 = ex2_approx(fmaf(s[j][3], scale_log2e, -mn1));
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        pa[j][0] = pack_bf16x2(p0, p1);
+        pa[j][1] = pack_bf16x2(p2, p3);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {  // 16 keys per step = n-tiles 2ks, 2ks+1 of S
+        const int key0 = kb0 + ks * 16 + 2 * t;
+#pragma unroll
+        for (int n = 0; n < kDimTiles; ++n) {
+          const __nv_bfloat16* vrow = sVt + (n * 8 + g) * kVS + key0;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + 8);
+          mma_m16n8k16_bf16(o[n], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], b0, b1);
+        }
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  __nv_bfloat16* ob = out + b * o_sb + h * o_sh;
+#pragma unroll
+  for (int n = 0; n < kDimTiles; ++n) {
+    if (q0 + g < Tq)
+      *reinterpret_cast<uint32_t*>(ob + (int64_t)(q0 + g) * o_st + n * 8 + 2 * t) = pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
+    if (q0 + g + 8 < Tq)
+      *reinterpret_cast<uint32_t*>(ob + (int64_t)(q0 + g + 8) * o_st + n * 8 + 2 * t) =
+          pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+
+template <int HD>
+static int launch_attention_mma(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq,
+                                int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb, int64_t kv_sh,
+                                int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float scale, cudaStream_t st) {
+  dim3 grid((Tq + kAttMWarps * 16 - 1) / (kAttMWarps * 16), heads, B);
+  attention_mma_kernel<HD><<<grid, kAttMThreads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+      reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Tq, Tk, q_sb, q_sh, q_st,
+      kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale * 1.4426950408889634f);
+  FM_LAUNCH_CHECK("attention_mma_kernel");
+  return 0;
+}
+
 template <int HD>
 static int launch_attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk,
                             int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb, int64_t kv_sh, int64_t kv_st,
@@ -273,6 +439,7 @@ extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, vo
   FM_REQUIRE(((q_sb | q_sh | q_st | kv_sb | kv_sh | kv_st | o_sb | o_sh | o_st) & 7) == 0,
              "attention: strides must be multiples of 8 elements");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool scalar = getenv("FMDM_ATTENTION_SCALAR") != nullptr;  // A/B switch: the CUDA-core kernel for head_dim >= 16
 #define FM_ATT_ARGS q, k, v, out, B, heads, Tq, Tk, q_sb, q_sh, q_st, kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale, st
   switch (head_dim) {
     case 8: {
@@ -284,9 +451,9 @@ extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, vo
       FM_LAUNCH_CHECK("attention_hd8_mma_kernel");
       return 0;
     }
-    case 16: return launch_attention<16>(FM_ATT_ARGS);
-    case 32: return launch_attention<32>(FM_ATT_ARGS);
-    case 64: return launch_attention<64>(FM_ATT_ARGS);
+    case 16: return scalar ? launch_attention<16>(FM_ATT_ARGS) : launch_attention_mma<16>(FM_ATT_ARGS);
+    case 32: return scalar ? launch_attention<32>(FM_ATT_ARGS) : launch_attention_mma<32>(FM_ATT_ARGS);
+    case 64: return scalar ? launch_attention<64>(FM_ATT_ARGS) : launch_attention_mma<64>(FM_ATT_ARGS);
     default:
       set_error("attention: head_dim=%d unsupported (8, 16, 32, 64)", head_dim);
       return FM_ERR_UNSUPPORTED;

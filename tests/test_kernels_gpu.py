@@ -191,7 +191,8 @@ def test_upsample_transpose():
     assert torch.equal(ops.transpose_bf16(t), t.transpose(1, 2).contiguous())
 
 
-@pytest.mark.parametrize("hd,heads,T", [(8, 64, 1024), (8, 16, 256), (64, 4, 256), (16, 8, 100), (32, 2, 77)])
+@pytest.mark.parametrize("hd,heads,T", [(8, 64, 1024), (8, 16, 256), (64, 4, 256), (16, 8, 100), (32, 2, 77),
+                                        (64, 4, 4096), (64, 1, 130), (32, 3, 1000), (16, 2, 64)])
 def test_attention(hd, heads, T):
     g = torch.Generator().manual_seed(5)
     B = 2

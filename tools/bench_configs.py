@@ -47,7 +47,50 @@ def run(name, cfg, cond, B, hw, sched_name, steps, reps=3, flop_per_sample_fwd=N
     print(json.dumps(line), flush=True)
 
 
+def run_latent_config(B=128, lat=64, steps=50, reps=2):
+    """configs[2]: latent flow matching on AutoencoderKL f=8 latents (64x64x4, concat conditioning latents -> 8 input
+    channels), 50 Euler steps, then KL decode to 512x512."""
+    from fmdm_b200.models.vae import AutoencoderKL
+
+    torch.manual_seed(0)
+    cfg = dict(LDCT_UNET, in_channels=4, out_channels=4)
+    unet = DiffusionUNetFactory().build(cfg, "concatenate", 4).to(DEV).eval()
+    vae = AutoencoderKL(in_channels=1, out_channels=1, resolution=256, down_channels=(128, 256, 512, 512),
+                        num_res_blocks=2, z_channels=4, embed_dim=4, attn_heads=4, attn_dim_head=64)
+    for p in vae.parameters():
+        if float(p.abs().sum()) == 0:
+            torch.nn.init.normal_(p, 0, 0.02)
+    vae = vae.to(DEV).eval()
+    sch, _ = build_scheduler({"name": "flow_match_euler", "params": {}}, {})
+    x = torch.randn(B, 4, lat, lat, device=DEV)
+    c = torch.randn(B, 4, lat, lat, device=DEV)
+    kw = dict(conditioning_mode="concatenate", conditioning_batch=c, init_sample=x)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps, out
+
+    with torch.no_grad():
+        t_unet, z = timed(lambda: sample_with_scheduler(unet, sch, steps, tuple(x.shape), DEV, **kw))
+        t_dec, img = timed(lambda: vae.raw_output_to_image(vae.decode(z, denorm=True)))
+    assert img.shape == (B, 1, 8 * lat, 8 * lat) and torch.isfinite(img).all()
+    flop = B * (3.1091e10 * steps + 2.4918e12)
+    print(json.dumps({"config": "configs[2] latent flow matching 64x64x4 (50 Euler) + AutoencoderKL decode to 512x512",
+                      "batch": B, "s_unet_50_steps": round(t_unet, 4), "s_kl_decode": round(t_dec, 4),
+                      "samples_per_s": round(B / (t_unet + t_dec), 2),
+                      "model_tflops": round(flop / (t_unet + t_dec) / 1e12, 1)}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "latent":
+        run_latent_config()
+        sys.exit(0)
     run("configs[0] MNIST 28x28 uncond flow-matching, 50 Euler", MNIST, None, 64, 28, "flow_match_euler", 50,
         flop_per_sample_fwd=2.3969e9)
     run("configs[3] LDCT 256x256 DDIM 50", LDCT_UNET, "concatenate", 16, 256, "ddim", 50, flop_per_sample_fwd=4.9657e11)
