@@ -181,3 +181,47 @@ def test_run_model_sample_cli(tmp_path):
                   str(tmp_path / "o2")])
     out2 = torch.load(tmp_path / "o2" / "sample" / "samples.pt", weights_only=True)
     assert torch.allclose(out, out2, atol=2e-2)
+
+
+def test_evaluation_metrics_formulas(tmp_path):
+    from fmdm_b200 import run_model as RM
+
+    gen = torch.tensor([[[[0.5, 1.5], [0.0, -1.0]]], [[[0.25, 0.25], [0.25, 0.25]]]])
+    tgt = torch.tensor([[[[0.5, 1.0], [0.5, 0.0]]], [[[0.25, 0.25], [0.25, 0.25]]]])
+    mse, psnr = RM.evaluation_rows(gen, tgt)
+    assert abs(float(mse[0]) - 0.0625) < 1e-7 and float(mse[1]) == 0.0            # clamped to [0, 1] first
+    assert abs(float(psnr[0]) - 10 * torch.log10(torch.tensor(16.0)).item()) < 1e-4
+    assert abs(float(psnr[1]) - 120.0) < 1e-3                                       # mse floor 1e-12
+    row = RM.write_eval_metrics(tmp_path, gen, tgt, {"model_seconds": 2.0, "model_calls": 10})
+    assert row["model_samples_per_second"] == "1.000000" and row["samples"] == 2
+    head = (tmp_path / "eval_metrics.csv").read_text().splitlines()[0]
+    assert head == ("samples,mse,psnr,ssim,ssim_enabled,model_seconds,model_samples_per_second,"
+                    "model_seconds_per_sample,model_calls")
+    assert len((tmp_path / "eval_metrics_per_image.csv").read_text().splitlines()) == 3
+
+
+@pytest.mark.gpu
+def test_run_model_evaluate_cli(tmp_path):
+    from fmdm_b200 import run_model as RM
+
+    cfg = json.loads(json.dumps(CFG))
+    cfg["model"]["unet"]["block_out_channels"] = [64, 128]
+    cfg["model"]["scheduler"] = {"name": "ddim", "params": {"beta_start": 1e-4, "beta_end": 0.02}}
+    cfg["model"]["model_type"] = "diffusion"
+    (tmp_path / "train_config.json").write_text(json.dumps(cfg))
+    torch.manual_seed(2)
+    model = DiffusionUNetFactory().build(cfg["model"]["unet"], "concatenate", 1)
+    torch.save({"model": model.state_dict()}, tmp_path / "diff_last.pt")
+    g = torch.Generator().manual_seed(0)
+    cond = torch.rand(4, 1, 32, 32, generator=g)
+    tgt = torch.rand(4, 1, 32, 32, generator=g)
+    torch.save(cond, tmp_path / "cond.pt")
+    torch.save(tgt, tmp_path / "tgt.pt")
+    rc = RM.main(["--ckpt_dir", str(tmp_path), "--mode", "evaluate", "--conditioning_pt", str(tmp_path / "cond.pt"),
+                  "--targets_pt", str(tmp_path / "tgt.pt"), "--batch_size", "4", "--num_inference_steps", "10",
+                  "--start_step", "300"])   # partial trajectory from the noised targets (add_noise init)
+    assert rc == 0
+    rows = (tmp_path / "outputs" / "evaluate" / "eval_metrics.csv").read_text().splitlines()
+    vals = dict(zip(rows[0].split(","), rows[1].split(",")))
+    assert vals["samples"] == "4" and float(vals["psnr"]) > 0 and float(vals["model_samples_per_second"]) > 0
+    assert int(vals["model_calls"]) == 4  # ddim, 10 steps, leading spacing: timesteps <= 300 are 300, 200, 100, 0
