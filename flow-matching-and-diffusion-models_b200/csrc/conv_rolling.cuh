@@ -453,59 +453,18 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
           const int slab = c0 >> 6;
           const int chunk0 = (c0 & 63) >> 3;
           uint8_t* rowp = stg + slab * (kTileM * 128) + row * 128;
-          const float* sb = sbias + c0;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(sb + j4 * 4);
-            v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
-          }
-          if (p.residual != nullptr) {
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
-              const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
-              const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
-              v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
-              v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
-            }
-          }
+          epi_add_bias(v, sbias + c0);
+          if (p.residual != nullptr) epi_add_residual(v, rowp, chunk0, row);
           if (p.gn_partial != nullptr) {
-            float red[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a0 = valid ? v[4 * j + 0] : 0.f, a1 = valid ? v[4 * j + 1] : 0.f;
-              const float a2 = valid ? v[4 * j + 2] : 0.f, a3 = valid ? v[4 * j + 3] : 0.f;
-              red[j] = (a0 + a1) + (a2 + a3);
-              red[8 + j] = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3);
-            }
-#pragma unroll
-            for (int width = 8, mask = 16; width >= 1; width >>= 1, mask >>= 1) {
-              const bool upper = (lane & mask) != 0;
-#pragma unroll
-              for (int i = 0; i < width; ++i) {
-                const float keep = upper ? red[i + width] : red[i];
-                const float give = upper ? red[i] : red[i + width];
-                red[i] = keep + __shfl_xor_sync(0xffffffffu, give, mask);
-              }
-            }
-            red[0] += __shfl_xor_sync(0xffffffffu, red[0], 1);
-            st_acc[i] += red[0];
-            if (h0 == h_end - 1) {
-              const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            int vidx;
+            st_acc[i] += epi_quad_stats(v, valid, lane, vidx);
+            if (h0 == h_end - 1) {  // last row of the strip: one row of partials per (strip, lane quadrant)
               const int qcol = col0 + (vidx & 7) * 4;
               if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
                 p.gn_partial[(stat_row * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = st_acc[i];
             }
           }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int chunk = (chunk0 + j) ^ (row & 7);
-            *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-                make_uint4(pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
+          epi_pack_store(v, rowp, chunk0, row);
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
