@@ -38,6 +38,8 @@ EULER_STEPS = 50
 IMG = 512
 BATCH_PER_GPU = 16
 METRIC = "LDCT 512^2 flow-matching samples/s @50 Euler steps"
+WORKLOAD = ("LDCT 512x512 concat flow-matching UNetDiffusersND (128,128,256,256,512,512), 50 Euler steps "
+            "(BASELINE configs[1])")
 
 
 def read_peaks():
@@ -183,8 +185,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_euler * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LDCT 512x512 concat flow-matching UNetDiffusersND, 50 Euler steps (configs[1])",
-                   "batch": 1, "euler_steps_timed": n_euler, "extrapolated_to_euler_steps": EULER_STEPS},
+        "config": {"workload": WORKLOAD, "euler_steps": EULER_STEPS, "sample_batch": 1,
+                   "euler_steps_timed_per_bench_step": n_euler,
+                   "note": "bounded sample: B=1, one Euler step per bench step, samples/s = 1/(t_euler*50)"},
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"B=1, {n_euler} Euler step(s) of 50 per bench step at 512x512, fp32, torch CPU "
                                    f"({cores} threads); samples/s = 1/(t_euler*50)"},
@@ -354,9 +357,7 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "LDCT 512x512 concat flow-matching UNetDiffusersND "
-                                   "(128,128,256,256,512,512), 50 Euler steps (BASELINE configs[1])",
-                       "batch_per_gpu": B, "global_batch": total, "euler_steps": EULER_STEPS,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": total, "euler_steps": EULER_STEPS,
                        "l2": "inputs larger than L2 (activations 1-2 GiB per tensor at level 0)",
                        "parallelism": f"batch sharded over {world} GPU(s), final all-gather"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 2 * B * IMG * IMG * 4,
