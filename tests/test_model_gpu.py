@@ -131,7 +131,7 @@ def test_denoiser_forward_parity(name, cfg, cond, hw, B):
             out2 = model(torch.cat([x, c], 1), t) if cond else out
         assert out.dtype == torch.float32 and out.shape == ref.shape
         err = rel_l2(out, ref)
-        # north-star tolerance 1e-2 (bf16 vs fp32 oracle).  Measured (tools/diag_error.py): LDCT arch 0.7-0.97e-2,
+        # north-star tolerance 1e-2 (bf16 vs fp32 oracle).  Measured: LDCT arch 0.7-0.97e-2,
         # of which 0.5e-2 is the bf16 rounding of the WEIGHTS alone; the shallow/narrow MNIST arch sits at
         # 0.99-1.04e-2, i.e. at the bf16 noise floor, so it gets 1.2e-2.
         tol = 1.2e-2 if name.startswith("mnist") else 1e-2
