@@ -33,16 +33,15 @@ __device__ __forceinline__ uint4 xf_chunk(uint4 u, const float (&a)[8], const fl
   uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float h0 = fmaf(__uint_as_float(w[j] << 16), a[2 * j], b[2 * j]);
-    float h1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), a[2 * j + 1], b[2 * j + 1]);
+    float2 h = ffma2(make_float2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u)),
+                     make_float2(a[2 * j], a[2 * j + 1]), make_float2(b[2 * j], b[2 * j + 1]));
     if (kSilu) {
-      float t0, t1;
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
-      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
-      h0 = fmaf(h0, t0, h0);
-      h1 = fmaf(h1, t1, h1);
+      float2 t;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+      h = ffma2(h, t, h);
     }
-    w[j] = pack_bf16x2(h0, h1);
+    w[j] = pack_bf16x2(h.x, h.y);
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }

@@ -79,11 +79,12 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __
             const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
             for (int p = 0; p < kStemPix; ++p) {
-              const float xv = xin[kh][p + kw];
-              acc[p][0] = fmaf(xv, w0.x, acc[p][0]); acc[p][1] = fmaf(xv, w0.y, acc[p][1]);
-              acc[p][2] = fmaf(xv, w0.z, acc[p][2]); acc[p][3] = fmaf(xv, w0.w, acc[p][3]);
-              acc[p][4] = fmaf(xv, w1.x, acc[p][4]); acc[p][5] = fmaf(xv, w1.y, acc[p][5]);
-              acc[p][6] = fmaf(xv, w1.z, acc[p][6]); acc[p][7] = fmaf(xv, w1.w, acc[p][7]);
+              const float2 xv = make_float2(xin[kh][p + kw], xin[kh][p + kw]);
+              float2* ap = reinterpret_cast<float2*>(acc[p]);  // packed FMAs: two output channels per instruction
+              ap[0] = ffma2(xv, make_float2(w0.x, w0.y), ap[0]);
+              ap[1] = ffma2(xv, make_float2(w0.z, w0.w), ap[1]);
+              ap[2] = ffma2(xv, make_float2(w1.x, w1.y), ap[2]);
+              ap[3] = ffma2(xv, make_float2(w1.z, w1.w), ap[3]);
             }
           }
         }
@@ -248,11 +249,14 @@ __global__ void __launch_bounds__(kHd2Threads, 2) conv_head_dot_kernel(const uin
   const int c8 = lane % LPP, sub = lane / LPP;
   const int w0 = blockIdx.x * kHd2TW, h0 = blockIdx.y * kHd2TH, n = blockIdx.z;
 
-  float wr[9][8];
+  // taps paired for packed FMAs: wr[tp][j] = (w[tap 2tp][j], w[tap 2tp+1][j]); the tenth slot is zero
+  float2 wr[5][8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int tp = 0; tp < 5; ++tp)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wr[t][j] = __ldg(w_oihw + (c8 * 8 + j) * 9 + t);
+    for (int j = 0; j < 8; ++j)
+      wr[tp][j] = make_float2(__ldg(w_oihw + (c8 * 8 + j) * 9 + 2 * tp),
+                              (2 * tp + 1 < 9) ? __ldg(w_oihw + (c8 * 8 + j) * 9 + 2 * tp + 1) : 0.f);
   float a[8], b[8];
   const bool has_norm = norm_ab != nullptr;
   const bool silu = has_norm && norm_act != 0;
@@ -300,13 +304,14 @@ __global__ void __launch_bounds__(kHd2Threads, 2) conv_head_dot_kernel(const uin
         xv[2 * j] = inb[u] ? h0v : 0.f;
         xv[2 * j + 1] = inb[u] ? h1v : 0.f;
       }
-      float red[9];
+      float red[10];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        float acc = xv[0] * wr[t][0];
+      for (int tp = 0; tp < 5; ++tp) {
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 1; j < 8; ++j) acc = fmaf(xv[j], wr[t][j], acc);
-        red[t] = acc;
+        for (int j = 0; j < 8; ++j) acc = ffma2(make_float2(xv[j], xv[j]), wr[tp][j], acc);
+        red[2 * tp] = acc.x;
+        red[2 * tp + 1] = acc.y;
       }
       // recursive halving over the top three lane bits of the pixel's lane group: 8 values -> 1 per lane
 #pragma unroll
