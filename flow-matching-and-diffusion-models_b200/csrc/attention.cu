@@ -217,10 +217,11 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
       o[0] *= corr0; o[1] *= corr0; o[2] *= corr1; o[3] *= corr1;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, -mn0));
-        const float p1 = ex2_approx(fmaf(s[j][1], scale_log2e, -mn0));
-        const float p2 = ex2_approx(fmaf(s[j][2], scale_log2e, -mn1));
-        const float p3 = ex2_approx(fmaf(s[j][3], scale_log2e, -mn1));
+        const float2 e01 = ffma2(make_float2(s[j][0], s[j][1]), make_float2(scale_log2e, scale_log2e),
+                                 make_float2(-mn0, -mn0));
+        const float2 e23 = ffma2(make_float2(s[j][2], s[j][3]), make_float2(scale_log2e, scale_log2e),
+                                 make_float2(-mn1, -mn1));
+        const float p0 = ex2_approx(e01.x), p1 = ex2_approx(e01.y), p2 = ex2_approx(e23.x), p3 = ex2_approx(e23.y);
         l0 += p0 + p1;
         l1 += p2 + p3;
         const uint32_t pa0 = pack_bf16x2(p0, p1), pa1 = pack_bf16x2(p2, p3);
@@ -355,10 +356,11 @@ __global__ void __launch_bounds__(kAttMThreads) attention_mma_kernel(
       uint32_t pa[8][2];  // P as bf16x2: [n-tile][row g | row g+8]
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, -mn0));
-        const float p1 = ex2_approx(fmaf(s[j][1], scale_log2e, -mn0));
-        const float p2 = ex2_approx(fmaf(s[j][2], scale_log2e, -mn1));
-        const float p3 = ex2_approx(fmaf(s[j][3], scale_log2e, -mn1));
+        const float2 e01 = ffma2(make_float2(s[j][0], s[j][1]), make_float2(scale_log2e, scale_log2e),
+                                 make_float2(-mn0, -mn0));
+        const float2 e23 = ffma2(make_float2(s[j][2], s[j][3]), make_float2(scale_log2e, scale_log2e),
+                                 make_float2(-mn1, -mn1));
+        const float p0 = ex2_approx(e01.x), p1 = ex2_approx(e01.y), p2 = ex2_approx(e23.x), p3 = ex2_approx(e23.y);
         l0 += p0 + p1;
         l1 += p2 + p3;
         pa[j][0] = pack_bf16x2(p0, p1);

@@ -11,7 +11,9 @@ __device__ __forceinline__ void epi_add_bias(float (&v)[32], const float* sb) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 b = *reinterpret_cast<const float4*>(sb + j4 * 4);
-    v[j4 * 4 + 0] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
+    const float2 s0 = fadd2(make_float2(v[j4 * 4 + 0], v[j4 * 4 + 1]), make_float2(b.x, b.y));
+    const float2 s1 = fadd2(make_float2(v[j4 * 4 + 2], v[j4 * 4 + 3]), make_float2(b.z, b.w));
+    v[j4 * 4 + 0] = s0.x; v[j4 * 4 + 1] = s0.y; v[j4 * 4 + 2] = s1.x; v[j4 * 4 + 3] = s1.y;
   }
 }
 
@@ -20,10 +22,13 @@ __device__ __forceinline__ void epi_add_residual(float (&v)[32], const uint8_t* 
 #pragma unroll
   for (int j8 = 0; j8 < 4; ++j8) {
     const uint4 rr = *reinterpret_cast<const uint4*>(rowp + (((chunk0 + j8) ^ (row & 7)) * 16));
-    const float2 f0 = unpack_bf16x2(rr.x), f1 = unpack_bf16x2(rr.y);
-    const float2 f2 = unpack_bf16x2(rr.z), f3 = unpack_bf16x2(rr.w);
-    v[j8 * 8 + 0] += f0.x; v[j8 * 8 + 1] += f0.y; v[j8 * 8 + 2] += f1.x; v[j8 * 8 + 3] += f1.y;
-    v[j8 * 8 + 4] += f2.x; v[j8 * 8 + 5] += f2.y; v[j8 * 8 + 6] += f3.x; v[j8 * 8 + 7] += f3.y;
+    const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 s = fadd2(make_float2(v[j8 * 8 + 2 * k], v[j8 * 8 + 2 * k + 1]), unpack_bf16x2(w[k]));
+      v[j8 * 8 + 2 * k] = s.x;
+      v[j8 * 8 + 2 * k + 1] = s.y;
+    }
   }
 }
 
