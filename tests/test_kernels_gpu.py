@@ -433,3 +433,73 @@ def test_conv2d_upsampled_store(case):
     up = ops.conv2d([_nhwc(x) for x in xs], packed, upsample_out=True, **kw)
     assert up.shape == (B, cout, 2 * H, 2 * W)
     assert torch.equal(up.float(), F.interpolate(plain.float(), scale_factor=2, mode="nearest"))
+
+
+def test_conv2d_rolling_random_shapes():
+    """Seeded random sweep over the rolling-row kernel's argument space (ragged widths, odd heights / batches, 1-3 K
+    segments with and without the fused operand transform, residual, per-sample vector, upsampled store, fused
+    statistics) against the fp32 reference."""
+    import random
+
+    rnd = random.Random(1234)
+    g = torch.Generator(device="cpu").manual_seed(99)
+    for it in range(24):
+        B = rnd.choice([1, 2, 3, 5])
+        H = rnd.choice([1, 2, 7, 16, 33])
+        W = rnd.choice([65, 100, 128, 130, 200, 256, 300])
+        nseg = rnd.choice([1, 1, 2, 3])
+        cins = [rnd.choice([64, 128, 192]) for _ in range(nseg)]
+        ks = [3] + [rnd.choice([1, 3]) for _ in range(nseg - 1)]
+        cout = rnd.choice([64, 128, 192, 256])
+        use_norm = rnd.random() < 0.6
+        residual = rnd.random() < 0.5
+        addvec = rnd.random() < 0.5
+        up = rnd.random() < 0.3
+        xs = [_bf16r(torch.randn(B, c, H, W, generator=g) * 1.2 + 0.1).to(DEV) for c in cins]
+        ws = [_bf16r(torch.randn(cout, c, k, k, generator=g) / math.sqrt(c * k * k)).to(DEV) for c, k in zip(cins, ks)]
+        bvec = torch.randn(cout, generator=g).to(DEV)
+        av = torch.randn(B, cout, generator=g).to(DEV) if addvec else None
+        res = _bf16r(torch.randn(B, cout, H, W, generator=g)).to(DEV) if residual else None
+        norm = None
+        ys = list(xs)
+        if use_norm:
+            normed = [k == 3 and rnd.random() < 0.8 for k in ks]
+            normed[0] = True
+            ctot = sum(c for c, n in zip(cins, normed) if n)
+            ab = torch.empty(B, 2, ctot)
+            ab[:, 0] = torch.rand(B, ctot, generator=g) + 0.5
+            ab[:, 1] = torch.randn(B, ctot, generator=g) * 0.5
+            ab = ab.to(DEV)
+            table = ops.NormTable(ab, True)
+            norm, off = [], 0
+            for i, (c, n) in enumerate(zip(cins, normed)):
+                if n:
+                    y = xs[i] * ab[:, 0, off:off + c, None, None] + ab[:, 1, off:off + c, None, None]
+                    ys[i] = _bf16r(F.silu(y))
+                    norm.append((table, off))
+                    off += c
+                else:
+                    norm.append(None)
+        ref = torch.zeros(B, cout, H, W, device=DEV)
+        for y, w, k in zip(ys, ws, ks):
+            ref = ref + F.conv2d(y, w, None, padding=k // 2)
+        ref = ref + bvec.view(1, -1, 1, 1)
+        if addvec:
+            ref = ref + av.view(B, cout, 1, 1)
+        if residual:
+            ref = ref + res
+        packed = ops.pack_conv_weight([(w, 0, c) for w, c in zip(ws, cins)])
+        out = ops.conv2d([_nhwc(x) for x in xs], packed, bias=bvec, addvec=av, residual=_nhwc(res) if residual else None,
+                         norm=norm, upsample_out=up, want_stats=not up)
+        if up:
+            ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+        err = _rel_l2(out.float(), ref)
+        tag = (it, B, H, W, cins, ks, cout, use_norm, residual, addvec, up)
+        assert err < 6e-3, (tag, err)
+        if not up and hasattr(out, "_fm_stats"):
+            gamma = torch.ones(cout, device=DEV)
+            beta = torch.zeros(cout, device=DEV)
+            tab = ops.group_norm_table([out], 32, 1e-5, gamma, beta, silu=False)
+            y = out.float() * tab.ab[:, 0, :, None, None] + tab.ab[:, 1, :, None, None]
+            want = F.group_norm(out.float(), 32, None, None, 1e-5)
+            assert float((y - want).abs().max()) < 2e-2, tag
