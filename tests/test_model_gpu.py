@@ -256,3 +256,29 @@ def test_full_size_properties():
         b = sample_with_scheduler(model, sched, 3, tuple(x.shape), torch.device(DEV), conditioning_mode="concatenate",
                                   conditioning_batch=c, init_sample=x, use_cuda_graph=False)
     assert torch.equal(a, b)
+
+
+def test_ldct_flowmatch_final_sample_psnr():
+    """North-star tolerance on the headline architecture: final samples of the full 50-Euler-step flow-matching run
+    (full LDCT UNetDiffusersND, 256x256, graph-replayed B200 path) >= 40 dB PSNR against the fp32 oracle loop."""
+    from fmdm_b200.pipelines.utils import build_scheduler, sample_with_scheduler
+
+    model, sd = build(LDCT_SMALL, "concatenate", seed=6)
+    g = torch.Generator().manual_seed(31)
+    B, hw, steps = 1, 256, 50
+    noise = torch.randn(B, 1, hw, hw, generator=g).to(DEV)
+    cond = torch.rand(B, 1, hw, hw, generator=g).to(DEV)
+    sched, _ = build_scheduler({"name": "flow_match_euler", "params": {}}, {})
+    with torch.no_grad():
+        out = sample_with_scheduler(model, sched, steps, noise.shape, torch.device(DEV),
+                                    conditioning_mode="concatenate", conditioning_batch=cond, init_sample=noise)
+    orc = make_scheduler("flowmatch", 1000, {})
+    orc.set_timesteps(steps)
+    x = noise.clone()
+    with torch.no_grad():
+        for t in orc.timesteps:
+            pred = OD.denoiser_forward(sd, LDCT_SMALL, x, t.expand(B).to(DEV).float(), conditioning="concatenate",
+                                       channels=1, context=cond)
+            x = orc.step(pred.cpu(), t, x.cpu()).prev_sample.to(DEV)
+    p = psnr(out.clamp(0, 1), x.clamp(0, 1))
+    assert p >= 40.0, p
