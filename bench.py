@@ -212,6 +212,19 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # the first collective creates the NCCL communicator, and NCCL prints its version banner to STDOUT; keep
+        # stdout to the one JSON line by pointing fd 1 at stderr while that happens
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     peaks = read_peaks()
     B = args.batch
     total = B * world
