@@ -740,9 +740,11 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   kp.n_tiles = pl.n_tiles;
   kp.m_tiles = pl.m_tiles;
   if (pl.rolling) {
-    if (pl.xf)
-      return block_n == 64 ? launch_conv_rolling<64, 1>(kp, pl.sch, st) : launch_conv_rolling<128, 1>(kp, pl.sch, st);
-    return block_n == 64 ? launch_conv_rolling<64, 0>(kp, pl.sch, st) : launch_conv_rolling<128, 0>(kp, pl.sch, st);
+    const bool res = p->residual != nullptr;  // two staging buffers only where the residual prefetch needs them
+#define FM_RC(N, X) (res ? launch_conv_rolling<N, X, 2>(kp, pl.sch, st) : launch_conv_rolling<N, X, 1>(kp, pl.sch, st))
+    if (pl.xf) return block_n == 64 ? FM_RC(64, 1) : FM_RC(128, 1);
+    return block_n == 64 ? FM_RC(64, 0) : FM_RC(128, 0);
+#undef FM_RC
   }
 #define FM_PC(N, M, G) return launch_conv_persistent<N, M, G, 1>(kp, st)
   if (pl.pair && pl.mt == 2) {
