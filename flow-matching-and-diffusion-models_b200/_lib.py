@@ -96,6 +96,27 @@ SIGNATURES = {
     "fm_sched_add_noise_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "fm_counter_add": (C.c_int, [_vp, _i32, _vp]),
     "fm_clamp_f32": (C.c_int, [_vp, _vp, _f32, _f32, _i64, _vp]),
+    # training step (backward / loss / optimiser)
+    "fm_conv_wgrad_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "fm_conv_wgrad_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "fm_colsum_workspace_elems": (C.c_int64, [_i32, _i64, _i32]),
+    "fm_colsum_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),
+    "fm_zero_insert2x_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "fm_sumpool2x2_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "fm_groupnorm_bwd_workspace_elems": (C.c_int64, [_i32, _i64, _i32]),
+    "fm_groupnorm_bwd_bf16": (
+        C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fm_attention_bwd_bf16": (
+        C.c_int, [_vp] * 8 + [_i32, _i32, _i32, _i32] + [_i64] * 6 + [_f32, _vp]),
+    "fm_silu_bwd_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "fm_conv_stem_wgrad_workspace_elems": (C.c_int64, [_i32, _i32]),
+    "fm_conv_stem_wgrad_f32": (
+        C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "fm_conv_head_bwd_workspace_elems": (C.c_int64, [_i32]),
+    "fm_conv_head_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "fm_sum_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, C.c_double, _vp]),
+    "fm_mse_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "fm_adamw_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp]),
 }
 
 _LIB = None

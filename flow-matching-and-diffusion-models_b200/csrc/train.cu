@@ -1,0 +1,1114 @@
+// Backward / optimiser kernels of the training step (reference: the autograd graph PyTorch builds for
+// `flow_matching_lib.py:138-182`, i.e. F.conv2d / F.group_norm / SiLU / SDPA / F.linear / F.mse_loss backward + AdamW).
+//
+//   conv wgrad    dW[co][ci][kh][kw] = sum_p dY[p][co] * X[p (+) tap][ci]  -- a GEMM whose K dimension is the pixel axis.
+//                 Both operands are pixel-major in HBM (NHWC), so they are "MN-major" for the tensor cores; this first
+//                 version runs them through mma.sync.m16n8k16 with ldmatrix.trans (split-K over pixel ranges, fp32
+//                 partials in a workspace, fixed-order second-stage reduction: deterministic, no atomics).
+//   conv dgrad    is the forward implicit-GEMM kernel (conv_igemm.cu) run on dY with flipped/transposed weights; the
+//                 helpers here are the zero-insertion that turns a stride-2 dgrad into a stride-1 conv and the 2x2
+//                 sum-pool that is the backward of the nearest-2x upsample.
+//   GroupNorm+SiLU backward, attention backward (fp32 CUDA cores, one CTA per (sample, head)), stem/head conv
+//   backward, column sums (bias / time-embedding gradients), fused MSE loss + gradient, flat AdamW.
+#include "common.cuh"
+
+namespace fm {
+
+// =============================================================================================================
+// generic fixed-order reduction of partials: out[o][i] = sum_p in[o][p][i]
+// =============================================================================================================
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                               int parts, int64_t inner, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = idx / inner, i = idx - o * inner;
+    const float* src = in + (o * parts) * inner + i;
+    float acc = 0.f;
+    for (int p = 0; p < parts; ++p) acc += src[(int64_t)p * inner];
+    out[idx] = acc;
+  }
+}
+
+static int launch_reduce(const float* in, float* out, int64_t outer, int parts, int64_t inner, cudaStream_t st) {
+  const int64_t total = outer * inner;
+  if (total == 0) return 0;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  reduce_partials_kernel<<<blocks, 256, 0, st>>>(in, out, parts, inner, total);
+  FM_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+
+// =============================================================================================================
+// conv wgrad (mma.sync m16n8k16, bf16 x bf16 -> fp32)
+// =============================================================================================================
+namespace wg {
+constexpr int kCo = 128;      // M tile (output channels)
+constexpr int kCi = 64;       // N tile (input channels)
+constexpr int kPx = 64;       // K chunk (output pixels) per pipeline stage
+constexpr int kStages = 3;
+constexpr int kDyRow = (kCo + 8) * 2;  // padded smem row pitch in bytes (conflict-free ldmatrix)
+constexpr int kXRow = (kCi + 8) * 2;
+constexpr int kDyBytes = kPx * kDyRow;
+constexpr int kXBytes = kPx * kXRow;   // per kw tap
+__host__ __device__ constexpr int stage_bytes(int ntaps) { return kDyBytes + ntaps * kXBytes; }
+}  // namespace wg
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct WgradParams {
+  const __nv_bfloat16* dy;  // [B][Ho][Wo][Cout]
+  const __nv_bfloat16* x;   // [B][H][W][Cin]
+  float* part;              // [splits][KS*KS][Cout][Cin]
+  int B, H, W, Ho, Wo, Cin, Cout, stride, pad;
+  int n_ci, n_co, chunks, chunks_per_split;
+  int64_t total_px;
+};
+
+// grid.x = n_ci * n_co * KS (kh), grid.y = splits.  NT = taps along kw handled by one CTA (3 for 3x3, 1 for 1x1).
+template <int NT>
+__global__ void __launch_bounds__(256, 1) conv_wgrad_mma_kernel(const WgradParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps: warp tile 32 (co) x 32 (ci) x NT taps
+  int tile = blockIdx.x;
+  const int ci_t = tile % p.n_ci;
+  tile /= p.n_ci;
+  const int co_t = tile % p.n_co;
+  const int kh = tile / p.n_co;
+  const int co0 = co_t * wg::kCo, ci0 = ci_t * wg::kCi;
+  const int c_begin = blockIdx.y * p.chunks_per_split;
+  const int c_end = min(p.chunks, c_begin + p.chunks_per_split);
+  const int hw_o = p.Ho * p.Wo;
+  constexpr int kStage = wg::stage_bytes(NT);
+
+  float acc[NT][2][4][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[t][i][j][k] = 0.f;
+
+  auto load_stage = [&](int chunk, int slot) {
+    const uint32_t sdy = smem_base + slot * kStage;
+    const uint32_t sx = sdy + wg::kDyBytes;
+    const int64_t px0 = (int64_t)chunk * wg::kPx;  // flattened output pixel (b, yo, xo)
+    // dY tile: 64 pixels x 128 co = 64 x 16 chunks of 16 B
+#pragma unroll
+    for (int it = 0; it < (wg::kPx * (wg::kCo / 8)) / 256; ++it) {
+      const int idx = it * 256 + tid;
+      const int r = idx >> 4, cc = idx & 15;
+      const int co = co0 + cc * 8;
+      const bool ok = co < p.Cout && px0 + r < p.total_px;
+      const __nv_bfloat16* src = ok ? p.dy + (px0 + r) * p.Cout + co : p.dy;
+      cp_async16(sdy + r * wg::kDyRow + cc * 16, src, ok);
+    }
+    // X tiles, one per kw tap: 64 pixels x 64 ci = 64 x 8 chunks of 16 B
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+      for (int it = 0; it < (wg::kPx * (wg::kCi / 8)) / 256; ++it) {
+        const int idx = it * 256 + tid;
+        const int r = idx >> 3, cc = idx & 7;
+        const int64_t pp = px0 + r;
+        const int b = (int)(pp / hw_o);
+        const int rem = (int)(pp - (int64_t)b * hw_o);
+        const int yo = rem / p.Wo, xo = rem - yo * p.Wo;
+        const int yi = yo * p.stride + kh - p.pad, xi = xo * p.stride + t - p.pad;
+        const int ci = ci0 + cc * 8;
+        const bool ok = ci < p.Cin && yi >= 0 && yi < p.H && xi >= 0 && xi < p.W && pp < p.total_px;
+        const __nv_bfloat16* src = ok ? p.x + (((int64_t)b * p.H + yi) * p.W + xi) * p.Cin + ci : p.x;
+        cp_async16(sx + t * wg::kXBytes + r * wg::kXRow + cc * 16, src, ok);
+      }
+    }
+  };
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < wg::kStages - 1; ++s) {
+    if (c_begin + s < c_end) load_stage(c_begin + s, s);
+    cp_async_commit();
+  }
+  const int lj = lane >> 3, lr = lane & 7;
+  for (int c = c_begin; c < c_end; ++c) {
+    const int slot = (c - c_begin) % wg::kStages;
+    cp_async_wait<wg::kStages - 2>();
+    __syncthreads();
+    {
+      const int nc = c + wg::kStages - 1;
+      if (nc < c_end) load_stage(nc, (nc - c_begin) % wg::kStages);
+      cp_async_commit();
+    }
+    const uint32_t sdy = smem_base + slot * kStage;
+    const uint32_t sx = sdy + wg::kDyBytes;
+#pragma unroll
+    for (int ks = 0; ks < wg::kPx / 16; ++ks) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        // matrix j: m-half = j & 1, k-half = j >> 1; stored rows are pixels (k), columns are channels (m)
+        const int px = ks * 16 + (lj >> 1) * 8 + lr;
+        const int co = wm * 32 + mi * 16 + (lj & 1) * 8;
+        ldsm_x4_t(sdy + px * wg::kDyRow + co * 2, a[mi][0], a[mi][1], a[mi][2], a[mi][3]);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          // matrix j: k-half = j & 1, n-block = j >> 1
+          const int px = ks * 16 + (lj & 1) * 8 + lr;
+          const int ci = wn * 32 + nb * 16 + (lj >> 1) * 8;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(sx + t * wg::kXBytes + px * wg::kXRow + ci * 2, b0, b1, b2, b3);
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            mma_bf16_16816(acc[t][mi][nb * 2 + 0], a[mi], b0, b1);
+            mma_bf16_16816(acc[t][mi][nb * 2 + 1], a[mi], b2, b3);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // partial tile -> workspace [split][tap][Cout][Cin]
+  const int g = lane >> 2, tq = lane & 3;
+  const int ks_total = (NT == 3) ? 9 : 1;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int tap = (NT == 3) ? kh * 3 + t : 0;
+    float* base = p.part + ((int64_t)blockIdx.y * ks_total + tap) * p.Cout * p.Cin;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj) {
+        const int ci = ci0 + wn * 32 + nj * 8 + tq * 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int co = co0 + wm * 32 + mi * 16 + g + h * 8;
+          if (co < p.Cout && ci < p.Cin)
+            *reinterpret_cast<float2*>(base + (int64_t)co * p.Cin + ci) =
+                make_float2(acc[t][mi][nj][h * 2 + 0], acc[t][mi][nj][h * 2 + 1]);
+        }
+      }
+  }
+}
+
+// dw[co][c_begin + ci][tap] = sum_split part[split][tap][co][ci]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
+                                                            int splits, int taps, int Cout, int Cin, int cin_total,
+                                                            int c_begin) {
+  const int64_t per = (int64_t)taps * Cout * Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cin);
+    const int64_t r = idx / Cin;
+    const int co = (int)(r % Cout);
+    const int tap = (int)(r / Cout);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * per + idx];
+    dw[((int64_t)co * cin_total + c_begin + ci) * taps + tap] = acc;
+  }
+}
+
+static int wgrad_plan(int B, int Ho, int Wo, int Cin, int Cout, int ksize, int* splits, int* chunks_per_split,
+                      int* chunks, int* base) {
+  const int64_t px = (int64_t)B * Ho * Wo;
+  if (px <= 0) return FM_ERR_UNSUPPORTED;
+  *chunks = (int)((px + wg::kPx - 1) / wg::kPx);  // a ragged last chunk is zero-filled
+  const int n_ci = (Cin + wg::kCi - 1) / wg::kCi, n_co = (Cout + wg::kCo - 1) / wg::kCo;
+  *base = n_ci * n_co * ksize;
+  int s = (2 * sm_count() + *base - 1) / *base;  // about two waves of CTAs
+  if (s > *chunks) s = *chunks;
+  if (s < 1) s = 1;
+  *chunks_per_split = (*chunks + s - 1) / s;
+  *splits = (*chunks + *chunks_per_split - 1) / *chunks_per_split;
+  return 0;
+}
+
+// =============================================================================================================
+// column sums: dY [B][HW][C] bf16 -> out[B][C] fp32 (per-sample), two stages
+// =============================================================================================================
+__global__ void __launch_bounds__(1024) colsum_partial_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               float* __restrict__ part, int64_t HW, int C,
+                                                               int rows_per_blk) {
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int64_t r0 = (int64_t)blk * rows_per_blk;
+  const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
+  for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(dy + ((int64_t)b * HW) * C) + cp;
+    for (int64_t r = r0; r < r1; ++r) {
+      const float2 v = unpack_bf16x2(src[r * (C / 2)]);
+      s0 += v.x;
+      s1 += v.y;
+    }
+    float* dst = part + ((int64_t)b * nblk + blk) * C + cp * 2;
+    dst[0] = s0;
+    dst[1] = s1;
+  }
+}
+
+// =============================================================================================================
+// zero insertion (stride-2 dgrad) and 2x2 sum-pool (nearest-2x upsample backward), bf16 NHWC, 8 channels / thread
+// =============================================================================================================
+__global__ void __launch_bounds__(256) zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                             int B, int H, int W, int C8) {
+  const int64_t total = (int64_t)B * 2 * H * 2 * W * C8;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8);
+    int64_t r = idx / C8;
+    const int x = (int)(r % (2 * W));
+    r /= 2 * W;
+    const int y = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(x & 1) && !(y & 1)) v = in[(((int64_t)b * H + (y >> 1)) * W + (x >> 1)) * C8 + c];
+    out[idx] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) sumpool2x2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                          int B, int H, int W, int C8) {  // H, W: output size
+  const int64_t total = (int64_t)B * H * W * C8;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8);
+    int64_t r = idx / C8;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const uint4 v = in[(((int64_t)b * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * C8 + c];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(w[k]);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
+        }
+      }
+    out[idx] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                          pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// =============================================================================================================
+// GroupNorm (+ scale-shift) (+ SiLU) backward
+// =============================================================================================================
+__device__ __forceinline__ float silu_grad_f(float n) {
+  const float s = 1.f / (1.f + __expf(-n));
+  return s * (1.f + n * (1.f - s));
+}
+
+// coefficient table per (sample, channel), 8 floats: a, b (forward affine n = a*x + b), mean, rstd, A, m1, m2, pad
+constexpr int kGnTab = 8;
+
+// stage 1: S1[b][c] = sum_p dn, S2[b][c] = sum_p dn * xhat   (partials per row block)
+__global__ void __launch_bounds__(512) gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const __nv_bfloat16* __restrict__ da,
+                                                              const float* __restrict__ tab, float* __restrict__ part,
+                                                              int64_t HW, int C, int rows_per_blk, int silu) {
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int64_t r0 = (int64_t)blk * rows_per_blk;
+  const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
+  for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
+    const float* t0 = tab + ((int64_t)b * C + cp * 2) * kGnTab;
+    const float a0 = t0[0], b0 = t0[1], mu0 = t0[2], rs0 = t0[3];
+    const float a1 = t0[kGnTab + 0], b1 = t0[kGnTab + 1], mu1 = t0[kGnTab + 2], rs1 = t0[kGnTab + 3];
+    const uint32_t* xs = reinterpret_cast<const uint32_t*>(x + ((int64_t)b * HW) * C) + cp;
+    const uint32_t* ds = reinterpret_cast<const uint32_t*>(da + ((int64_t)b * HW) * C) + cp;
+    float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const float2 xv = unpack_bf16x2(xs[r * (C / 2)]);
+      const float2 dv = unpack_bf16x2(ds[r * (C / 2)]);
+      float d0 = dv.x, d1 = dv.y;
+      if (silu) {
+        d0 *= silu_grad_f(fmaf(a0, xv.x, b0));
+        d1 *= silu_grad_f(fmaf(a1, xv.y, b1));
+      }
+      s1a += d0;
+      s2a = fmaf(d0, (xv.x - mu0) * rs0, s2a);
+      s1b += d1;
+      s2b = fmaf(d1, (xv.y - mu1) * rs1, s2b);
+    }
+    float* dst = part + (((int64_t)b * nblk + blk) * 2) * C + cp * 2;
+    dst[0] = s1a;
+    dst[1] = s1b;
+    dst[C] = s2a;
+    dst[C + 1] = s2b;
+  }
+}
+
+// forward table: a, b, mean, rstd per (sample, channel).  One block per sample.
+__global__ void __launch_bounds__(1024) gn_bwd_table_kernel(const float* __restrict__ stats,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ ss, int64_t ss_stride, int C,
+                                                             int groups, float* __restrict__ tab) {
+  const int b = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = stats[((int64_t)b * groups + g) * 2 + 0];
+    const float rstd = stats[((int64_t)b * groups + g) * 2 + 1];
+    float ga = gamma[c], be = beta[c];
+    if (ss != nullptr) {
+      const float sc = 1.f + ss[b * ss_stride + c];
+      ga *= sc;
+      be = fmaf(be, sc, ss[b * ss_stride + C + c]);
+    }
+    float* t = tab + ((int64_t)b * C + c) * kGnTab;
+    const float a = rstd * ga;
+    t[0] = a;
+    t[1] = fmaf(-mean, a, be);
+    t[2] = mean;
+    t[3] = rstd;
+  }
+}
+
+// stage 2: group sums -> A, m1, m2 of the table; per-sample parameter gradients.  One block per sample.
+// S: [B][2][C] (S1 then S2).  dgb_part: [B][2][C] (per-sample dgamma, dbeta); dss: [B][2C] or NULL.
+__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ S,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                const float* __restrict__ ss, int64_t ss_stride,
+                                                                int C, int groups, float inv_n,
+                                                                float* __restrict__ tab, float* __restrict__ dgb_part,
+                                                                float* __restrict__ dss) {
+  extern __shared__ float sh[];  // [2][C]
+  const int b = blockIdx.x;
+  const int cpg = C / groups;
+  const float* S1 = S + ((int64_t)b * 2) * C;
+  const float* S2 = S1 + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ga = gamma[c];
+    float sc = 1.f;
+    if (ss != nullptr) sc = 1.f + ss[b * ss_stride + c];
+    const float gp = ga * sc;
+    sh[c] = gp * S1[c];
+    sh[C + c] = gp * S2[c];
+    dgb_part[((int64_t)b * 2) * C + c] = S2[c] * sc;      // dgamma contribution
+    dgb_part[((int64_t)b * 2 + 1) * C + c] = S1[c] * sc;  // dbeta contribution
+    if (dss != nullptr) {
+      dss[(int64_t)b * 2 * C + c] = fmaf(S2[c], ga, S1[c] * beta[c]);  // d scale
+      dss[(int64_t)b * 2 * C + C + c] = S1[c];                         // d shift
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    float g1 = 0.f, g2 = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      g1 += sh[g0 + k];
+      g2 += sh[C + g0 + k];
+    }
+    float* t = tab + ((int64_t)b * C + c) * kGnTab;
+    const float rstd = t[3];
+    t[4] = t[0];  // A = rstd * gamma'
+    t[5] = rstd * g1 * inv_n;
+    t[6] = rstd * g2 * inv_n;
+  }
+}
+
+// stage 3: dx = A*dn - m1 - m2*xhat
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ da,
+                                                            const float* __restrict__ tab, uint4* __restrict__ dx,
+                                                            int64_t HW, int C8, int silu, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    const int64_t row = idx / C8;
+    const int b = (int)(row / HW);
+    const float4* t = reinterpret_cast<const float4*>(tab + ((int64_t)b * C8 * 8 + c8 * 8) * kGnTab);
+    const uint4 xv = x[idx], dv = da[idx];
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 t0 = __ldg(t + 2 * k), t1 = __ldg(t + 2 * k + 1);  // (a, b, mean, rstd), (A, m1, m2, -)
+      const float2 xf = unpack_bf16x2(xw[k >> 1]), df = unpack_bf16x2(dw[k >> 1]);
+      const float xx = (k & 1) ? xf.y : xf.x;
+      float d = (k & 1) ? df.y : df.x;
+      if (silu) d *= silu_grad_f(fmaf(t0.x, xx, t0.y));
+      const float xh = (xx - t0.z) * t0.w;
+      o[k] = fmaf(t1.x, d, -t1.y) - t1.z * xh;
+    }
+    dx[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                         pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// =============================================================================================================
+// attention backward: one CTA per (sample, head); Q, K, V, dO staged in shared memory as bf16, math in fp32
+// =============================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(256) attention_bwd_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+    const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dq,
+    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int heads, int T, int64_t qs_b, int64_t qs_h,
+    int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sk = sq + (size_t)T * HD;
+  __nv_bfloat16* sv = sk + (size_t)T * HD;
+  __nv_bfloat16* sdo = sv + (size_t)T * HD;
+  float* lse = reinterpret_cast<float*>(sdo + (size_t)T * HD);
+  float* dsum = lse + T;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int64_t qoff = b * qs_b + h * qs_h, ooff = b * os_b + h * os_h;
+  for (int idx = threadIdx.x; idx < T * HD; idx += blockDim.x) {
+    const int t = idx / HD, d = idx - t * HD;
+    sq[idx] = q[qoff + t * qs_t + d];
+    sk[idx] = k[qoff + t * qs_t + d];
+    sv[idx] = v[qoff + t * qs_t + d];
+    sdo[idx] = dout[ooff + t * os_t + d];
+  }
+  __syncthreads();
+  // phase 1+2: per query row i: log-sum-exp, D_i = dO_i . O_i, then dQ_i
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    float qi[HD], doi[HD];
+    float D = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      qi[d] = __bfloat162float(sq[i * HD + d]) * scale;
+      doi[d] = __bfloat162float(sdo[i * HD + d]);
+      D = fmaf(doi[d], __bfloat162float(o[ooff + i * os_t + d]), D);
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) s = fmaf(qi[d], __bfloat162float(sk[j * HD + d]), s);
+      const float mn = fmaxf(m, s);
+      l = l * __expf(m - mn) + __expf(s - mn);
+      m = mn;
+    }
+    const float L = m + __logf(l);
+    lse[i] = L;
+    dsum[i] = D;
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    for (int j = 0; j < T; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        s = fmaf(qi[d], __bfloat162float(sk[j * HD + d]), s);
+        dp = fmaf(doi[d], __bfloat162float(sv[j * HD + d]), dp);
+      }
+      const float ds = __expf(s - L) * (dp - D) * scale;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] = fmaf(ds, __bfloat162float(sk[j * HD + d]), acc[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dq[qoff + i * qs_t + d] = __float2bfloat16(acc[d]);
+  }
+  __syncthreads();
+  // phase 3: per key row j: dK_j, dV_j
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    float kj[HD], vj[HD], ak[HD], av[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      kj[d] = __bfloat162float(sk[j * HD + d]) * scale;
+      vj[d] = __bfloat162float(sv[j * HD + d]);
+      ak[d] = 0.f;
+      av[d] = 0.f;
+    }
+    for (int i = 0; i < T; ++i) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        s = fmaf(kj[d], __bfloat162float(sq[i * HD + d]), s);
+        dp = fmaf(vj[d], __bfloat162float(sdo[i * HD + d]), dp);
+      }
+      const float pr = __expf(s - lse[i]);
+      const float ds = pr * (dp - dsum[i]) * scale;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        av[d] = fmaf(pr, __bfloat162float(sdo[i * HD + d]), av[d]);
+        ak[d] = fmaf(ds, __bfloat162float(sq[i * HD + d]), ak[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      dk[qoff + j * qs_t + d] = __float2bfloat16(ak[d]);
+      dv[qoff + j * qs_t + d] = __float2bfloat16(av[d]);
+    }
+  }
+}
+
+// =============================================================================================================
+// small fp32 elementwise: dx = dy * silu'(x)
+// =============================================================================================================
+__global__ void __launch_bounds__(256) silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                        float* __restrict__ dx, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    const float s = 1.f / (1.f + expf(-xv));
+    dx[i] = dy[i] * (s * (1.f + xv * (1.f - s)));
+  }
+}
+
+// =============================================================================================================
+// stem conv wgrad: x fp32 NCHW (two concatenated sources), dY bf16 NHWC -> partial dW [blk][Cout][CIN*9]
+// =============================================================================================================
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x0, int C0,
+                                                          const float* __restrict__ x1, float in_scale,
+                                                          float in_shift, const __nv_bfloat16* __restrict__ dy,
+                                                          float* __restrict__ part, int B, int H, int W, int Cout,
+                                                          int segs_per_blk) {
+  constexpr int SEG = 64;  // pixels of one image row per step
+  __shared__ float patch[CIN][3][SEG + 2];
+  const int segs_per_row = (W + SEG - 1) / SEG;
+  const int64_t total = (int64_t)B * H * segs_per_row;
+  const int64_t s0 = (int64_t)blockIdx.x * segs_per_blk;
+  const int64_t s1 = s0 + segs_per_blk < total ? s0 + segs_per_blk : total;
+  const int co = threadIdx.x;
+  float acc[CIN * 9];
+#pragma unroll
+  for (int i = 0; i < CIN * 9; ++i) acc[i] = 0.f;
+  for (int64_t s = s0; s < s1; ++s) {
+    const int xs = (int)(s % segs_per_row) * SEG;
+    const int64_t r = s / segs_per_row;
+    const int y = (int)(r % H), b = (int)(r / H);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < CIN * 3 * (SEG + 2); idx += blockDim.x) {
+      const int xx = idx % (SEG + 2);
+      const int kh = (idx / (SEG + 2)) % 3;
+      const int ci = idx / (3 * (SEG + 2));
+      const int yi = y + kh - 1, xi = xs + xx - 1;
+      float v = 0.f;
+      if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+        const float* src = ci < C0 ? x0 + ((int64_t)b * C0 + ci) * H * W : x1 + ((int64_t)b * (CIN - C0) + ci - C0) * H * W;
+        v = fmaf(src[(int64_t)yi * W + xi], in_scale, in_shift);
+      }
+      patch[ci][kh][xx] = v;
+    }
+    __syncthreads();
+    if (co < Cout) {
+      const int npx = min(SEG, W - xs);
+      const __nv_bfloat16* drow = dy + (((int64_t)b * H + y) * W + xs) * Cout + co;
+      for (int px = 0; px < npx; ++px) {
+        const float d = __bfloat162float(drow[(int64_t)px * Cout]);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) acc[ci * 9 + kh * 3 + kw] = fmaf(d, patch[ci][kh][px + kw], acc[ci * 9 + kh * 3 + kw]);
+      }
+    }
+  }
+  if (co < Cout) {
+    float* dst = part + ((int64_t)blockIdx.x * Cout + co) * (CIN * 9);
+#pragma unroll
+    for (int i = 0; i < CIN * 9; ++i) dst[i] = acc[i];
+  }
+}
+
+// =============================================================================================================
+// head conv (Cout = 1) backward: a bf16 NHWC, dy fp32 [B][1][H][W]
+// =============================================================================================================
+// dA[p][ci] = sum_taps dy[y-kh+1][x-kw+1] * w[ci][kh][kw]
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                          uint4* __restrict__ da, int B, int H, int W, int C) {
+  extern __shared__ float shw[];  // [9][C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) shw[i] = w[(i % C) * 9 + i / C];
+  __syncthreads();
+  const int C8 = C / 8;
+  const int64_t total = (int64_t)B * H * W * C8;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    int64_t r = idx / C8;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int yo = y - kh + 1, xo = x - kw + 1;
+        if (yo < 0 || yo >= H || xo < 0 || xo >= W) continue;
+        const float d = __ldg(dy + ((int64_t)b * H + yo) * W + xo);
+        const float* wr = shw + (kh * 3 + kw) * C + c8 * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(d, wr[k], o[k]);
+      }
+    da[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                         pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// dW[ci][kh][kw] = sum_p a[p][ci] * dy[y-kh+1][x-kw+1]; block = (C/2 channel pairs) x (256/(C/2) pixel lanes)
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __restrict__ a,
+                                                          const float* __restrict__ dy, float* __restrict__ part,
+                                                          int B, int H, int W, int C, int px_per_blk) {
+  __shared__ float red[256 * 2];
+  const int cp_n = C / 2;
+  const int lanes = blockDim.x / cp_n;
+  const int cp = threadIdx.x % cp_n, pl = threadIdx.x / cp_n;
+  const int64_t total = (int64_t)B * H * W;
+  const int64_t p0 = (int64_t)blockIdx.x * px_per_blk;
+  const int64_t p1 = p0 + px_per_blk < total ? p0 + px_per_blk : total;
+  float acc[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = 0.f;
+  if (pl < lanes) {
+    for (int64_t p = p0 + pl; p < p1; p += lanes) {
+      const int x = (int)(p % W);
+      const int64_t r = p / W;
+      const int y = (int)(r % H);
+      const int b = (int)(r / H);
+      const float2 av = unpack_bf16x2(reinterpret_cast<const uint32_t*>(a + p * C)[cp]);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int yo = y - kh + 1, xo = x - kw + 1;
+          if (yo < 0 || yo >= H || xo < 0 || xo >= W) continue;
+          const float d = __ldg(dy + ((int64_t)b * H + yo) * W + xo);
+          acc[kh * 3 + kw][0] = fmaf(av.x, d, acc[kh * 3 + kw][0]);
+          acc[kh * 3 + kw][1] = fmaf(av.y, d, acc[kh * 3 + kw][1]);
+        }
+    }
+  }
+  // fixed-order reduction over the pixel lanes, one tap at a time
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+    red[threadIdx.x * 2 + 0] = acc[t][0];
+    red[threadIdx.x * 2 + 1] = acc[t][1];
+    __syncthreads();
+    if (pl == 0) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        s0 += red[(l * cp_n + cp) * 2 + 0];
+        s1 += red[(l * cp_n + cp) * 2 + 1];
+      }
+      float* dst = part + (int64_t)blockIdx.x * C * 9;
+      dst[(cp * 2 + 0) * 9 + t] = s0;
+      dst[(cp * 2 + 1) * 9 + t] = s1;
+    }
+  }
+}
+
+// =============================================================================================================
+// fp32 sums / MSE
+// =============================================================================================================
+// part[blk] = sum over the block's range of f(i); mode 0: x[i]; mode 1: (x[i] - (t1[i] - t2[i]))^2 (t2 may be NULL)
+__global__ void __launch_bounds__(256) sum_partial_kernel(const float* __restrict__ x, const float* __restrict__ t1,
+                                                           const float* __restrict__ t2, double* __restrict__ part,
+                                                           int64_t n, int mode) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (mode == 1) {
+      const float t = t2 != nullptr ? t1[i] - t2[i] : t1[i];
+      v = (v - t) * (v - t);
+    }
+    acc += (double)v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void sum_final_kernel(const double* __restrict__ part, int parts, double scale, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < parts; ++i) acc += part[i];
+    out[0] = (float)(acc * scale);
+  }
+}
+// dpred = (2/n) * g * (pred - target)
+__global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ t1,
+                                                       const float* __restrict__ t2, const float* __restrict__ g,
+                                                       float* __restrict__ dpred, float two_over_n, int64_t n) {
+  const float k = two_over_n * g[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float t = t2 != nullptr ? t1[i] - t2[i] : t1[i];
+    dpred[i] = k * (pred[i] - t);
+  }
+}
+
+// =============================================================================================================
+// flat AdamW (torch.optim.AdamW arithmetic, decoupled weight decay, bias-corrected): one launch for every parameter
+// =============================================================================================================
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                     float decay, float one_m_beta1, float beta2, float one_m_beta2,
+                                                     float step_size, float bc2_sqrt, float eps, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = __fmul_rn(g[i], grad_scale);
+    float pi = __fmul_rn(p[i], decay);                                                // p *= 1 - lr*wd
+    const float mi = fmaf(one_m_beta1, __fsub_rn(gi, m[i]), m[i]);                    // m.lerp_(g, 1-beta1)
+    const float vi = fmaf(one_m_beta2, __fmul_rn(gi, gi), __fmul_rn(v[i], beta2));    // v.mul_(b2).addcmul_(g, g, 1-b2)
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+    pi = fmaf(-step_size, __fdiv_rn(mi, denom), pi);                                  // p.addcdiv_(m, denom, -step)
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+static int ew_grid(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int64_t fm_conv_wgrad_workspace_elems(int32_t B, int32_t Ho, int32_t Wo, int32_t Cin, int32_t Cout,
+                                                 int32_t ksize) {
+  int splits, cps, chunks, base;
+  if (ksize != 1 && ksize != 3) return 0;
+  if (wgrad_plan(B, Ho, Wo, Cin, Cout, ksize, &splits, &cps, &chunks, &base)) return 0;
+  return (int64_t)splits * ksize * ksize * Cout * Cin;
+}
+
+extern "C" int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, float* workspace, int32_t B, int32_t H,
+                                  int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t stride,
+                                  int32_t cin_total, int32_t c_begin, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(dy && x && dw && workspace, "conv_wgrad: null pointer");
+  FM_REQUIRE(ksize == 1 || ksize == 3, "conv_wgrad: ksize must be 1 or 3");
+  FM_REQUIRE(stride == 1 || stride == 2, "conv_wgrad: stride must be 1 or 2");
+  FM_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv_wgrad: channel counts must be multiples of 8");
+  FM_REQUIRE(c_begin >= 0 && c_begin + Cin <= cin_total, "conv_wgrad: channel slice out of range");
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  WgradParams p;
+  int splits, base;
+  if (wgrad_plan(B, Ho, Wo, Cin, Cout, ksize, &splits, &p.chunks_per_split, &p.chunks, &base)) {
+    set_error("conv_wgrad: empty problem (B*Ho*Wo = %lld)", (long long)B * Ho * Wo);
+    return FM_ERR_UNSUPPORTED;
+  }
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.part = workspace;
+  p.B = B, p.H = H, p.W = W, p.Ho = Ho, p.Wo = Wo, p.Cin = Cin, p.Cout = Cout, p.stride = stride;
+  p.pad = ksize / 2;
+  p.total_px = (int64_t)B * Ho * Wo;
+  p.n_ci = (Cin + wg::kCi - 1) / wg::kCi;
+  p.n_co = (Cout + wg::kCo - 1) / wg::kCo;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(base, splits);
+  if (ksize == 3) {
+    constexpr int smem = wg::kStages * wg::stage_bytes(3);
+    static bool attr = false;
+    if (!attr) {
+      if (int e = check_cuda(cudaFuncSetAttribute(conv_wgrad_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "wgrad attr")) return e;
+      attr = true;
+    }
+    conv_wgrad_mma_kernel<3><<<grid, 256, smem, st>>>(p);
+  } else {
+    constexpr int smem = wg::kStages * wg::stage_bytes(1);
+    static bool attr = false;
+    if (!attr) {
+      if (int e = check_cuda(cudaFuncSetAttribute(conv_wgrad_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "wgrad attr")) return e;
+      attr = true;
+    }
+    conv_wgrad_mma_kernel<1><<<grid, 256, smem, st>>>(p);
+  }
+  FM_LAUNCH_CHECK("conv_wgrad_mma_kernel");
+  const int taps = ksize * ksize;
+  const int64_t per = (int64_t)taps * Cout * Cin;
+  wgrad_reduce_kernel<<<ew_grid(per), 256, 0, st>>>(workspace, dw, splits, taps, Cout, Cin, cin_total, c_begin);
+  FM_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return 0;
+}
+
+static int colsum_blocks(int64_t HW, int B) {
+  int nblk = (int)((4LL * sm_count() + B - 1) / B);
+  if (nblk > HW) nblk = (int)HW;
+  if (nblk < 1) nblk = 1;
+  return nblk;
+}
+
+extern "C" int64_t fm_colsum_workspace_elems(int32_t B, int64_t HW, int32_t C) {
+  if (ensure_device()) return 0;
+  return (int64_t)B * colsum_blocks(HW, B) * C;
+}
+
+/* out[b][c] = sum_p dy[b][p][c]; total (or NULL)[c] = sum_b out[b][c] */
+extern "C" int fm_colsum_bf16(const void* dy, float* workspace, float* out, float* total, int32_t B, int64_t HW,
+                              int32_t C, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(dy && workspace && out, "colsum: null pointer");
+  FM_REQUIRE(C % 2 == 0, "colsum: C must be even");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = colsum_blocks(HW, B);
+  const int rows = (int)((HW + nblk - 1) / nblk);
+  int threads = C / 2;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  colsum_partial_kernel<<<dim3(nblk, B), threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), workspace, HW, C,
+                                                          rows);
+  FM_LAUNCH_CHECK("colsum_partial_kernel");
+  if (int e = launch_reduce(workspace, out, B, nblk, C, st)) return e;
+  if (total != nullptr)
+    if (int e = launch_reduce(out, total, 1, B, C, st)) return e;
+  return 0;
+}
+
+extern "C" int fm_zero_insert2x_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                                     fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && out && C % 8 == 0, "zero_insert2x: null pointer or C not a multiple of 8");
+  const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
+  if (total == 0) return 0;
+  zero_insert2x_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                       reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  FM_LAUNCH_CHECK("zero_insert2x_kernel");
+  return 0;
+}
+
+/* x: [B][2H][2W][C] -> out [B][H][W][C] */
+extern "C" int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                                  fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && out && C % 8 == 0, "sumpool2x2: null pointer or C not a multiple of 8");
+  const int64_t total = (int64_t)B * H * W * (C / 8);
+  if (total == 0) return 0;
+  sumpool2x2_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                    reinterpret_cast<uint4*>(out), B, H, W, C / 8);
+  FM_LAUNCH_CHECK("sumpool2x2_kernel");
+  return 0;
+}
+
+static int gn_bwd_blocks(int64_t HW, int B) { return colsum_blocks(HW, B); }
+
+extern "C" int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C) {
+  if (ensure_device()) return 0;
+  /* table [B][C][8] + partials [B][nblk][2][C] + S [B][2][C] + dgb_part [B][2][C] */
+  return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 4LL * B * C;
+}
+
+extern "C" int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const float* stats, const float* gamma,
+                                     const float* beta, const float* scale_shift, int64_t ss_stride, int32_t silu,
+                                     int32_t B, int64_t HW, int32_t C, int32_t groups, float* workspace, void* dx,
+                                     float* dgamma_dbeta, float* dscale_shift, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && dout && stats && gamma && beta && workspace && dx && dgamma_dbeta, "groupnorm_bwd: null pointer");
+  FM_REQUIRE(C % 8 == 0 && groups > 0 && C % groups == 0, "groupnorm_bwd: C must be a multiple of 8 and of groups");
+  FM_REQUIRE(C <= 4096, "groupnorm_bwd: C too large");
+  FM_REQUIRE((scale_shift == nullptr) == (dscale_shift == nullptr), "groupnorm_bwd: scale_shift / dscale_shift mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = gn_bwd_blocks(HW, B);
+  const int rows = (int)((HW + nblk - 1) / nblk);
+  float* tab = workspace;
+  float* part = tab + (int64_t)B * C * kGnTab;
+  float* S = part + (int64_t)B * nblk * 2 * C;
+  float* dgb = S + 2LL * B * C;
+  int cthreads = ((C + 31) / 32) * 32;
+  if (cthreads > 1024) cthreads = 1024;
+  gn_bwd_table_kernel<<<B, cthreads, 0, st>>>(stats, gamma, beta, scale_shift, ss_stride, C, groups, tab);
+  FM_LAUNCH_CHECK("gn_bwd_table_kernel");
+  int pthreads = ((C / 2 + 31) / 32) * 32;
+  if (pthreads > 512) pthreads = 512;
+  gn_bwd_partial_kernel<<<dim3(nblk, B), pthreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                           reinterpret_cast<const __nv_bfloat16*>(dout), tab, part, HW,
+                                                           C, rows, silu);
+  FM_LAUNCH_CHECK("gn_bwd_partial_kernel");
+  if (int e = launch_reduce(part, S, B, nblk, 2LL * C, st)) return e;
+  const float inv_n = 1.f / ((float)HW * (float)(C / groups));
+  gn_bwd_finalize_kernel<<<B, cthreads, 2 * C * sizeof(float), st>>>(S, gamma, beta, scale_shift, ss_stride, C, groups,
+                                                                    inv_n, tab, dgb, dscale_shift);
+  FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
+  /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
+  if (int e = launch_reduce(dgb, dgamma_dbeta, 1, B, 2LL * C, st)) return e;
+  const int64_t total = (int64_t)B * HW * (C / 8);
+  gn_bwd_apply_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const uint4*>(x),
+                                                     reinterpret_cast<const uint4*>(dout), tab,
+                                                     reinterpret_cast<uint4*>(dx), HW, C / 8, silu, total);
+  FM_LAUNCH_CHECK("gn_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                                     void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t T,
+                                     int32_t head_dim, int64_t qs_b, int64_t qs_h, int64_t qs_t, int64_t os_b,
+                                     int64_t os_h, int64_t os_t, float scale, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(q && k && v && o && dout && dq && dk && dv, "attention_bwd: null pointer");
+  const size_t smem = (size_t)4 * T * head_dim * 2 + (size_t)2 * T * 4;
+  if (smem > 200 * 1024) {
+    set_error("attention_bwd: T=%d head_dim=%d exceeds the shared-memory staging budget", T, head_dim);
+    return FM_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+#define FM_ATT_BWD(HD)                                                                                              \
+  case HD: {                                                                                                        \
+    if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                (int)smem), "attention_bwd attr")) return e;                        \
+    attention_bwd_kernel<HD><<<B * heads, 256, smem, st>>>(                                                         \
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,         \
+        (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, T, qs_b, qs_h, \
+        qs_t, os_b, os_h, os_t, scale);                                                                             \
+    break;                                                                                                          \
+  }
+  switch (head_dim) {
+    FM_ATT_BWD(8)
+    FM_ATT_BWD(16)
+    FM_ATT_BWD(32)
+    FM_ATT_BWD(64)
+    default:
+      set_error("attention_bwd: head_dim %d unsupported (8, 16, 32, 64)", head_dim);
+      return FM_ERR_UNSUPPORTED;
+  }
+#undef FM_ATT_BWD
+  FM_LAUNCH_CHECK("attention_bwd_kernel");
+  return 0;
+}
+
+extern "C" int fm_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && dy && dx && n >= 0, "silu_bwd: bad argument");
+  if (n == 0) return 0;
+  silu_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, n);
+  FM_LAUNCH_CHECK("silu_bwd_kernel");
+  return 0;
+}
+
+static int stem_blocks() { return 4 * sm_count(); }
+
+extern "C" int64_t fm_conv_stem_wgrad_workspace_elems(int32_t Cin, int32_t Cout) {
+  if (ensure_device()) return 0;
+  return (int64_t)stem_blocks() * Cout * Cin * 9;
+}
+
+extern "C" int fm_conv_stem_wgrad_f32(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale,
+                                      float in_shift, const void* dy, float* workspace, float* dw, int32_t B, int32_t H,
+                                      int32_t W, int32_t Cout, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x0 && dy && workspace && dw, "stem_wgrad: null pointer");
+  FM_REQUIRE((C1 == 0) == (x1 == nullptr), "stem_wgrad: x1 / C1 mismatch");
+  const int cin = C0 + C1;
+  FM_REQUIRE(cin >= 1 && cin <= 4, "stem_wgrad: 1..4 input channels");
+  FM_REQUIRE(Cout >= 1 && Cout <= 256, "stem_wgrad: Cout must be <= 256");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = stem_blocks();
+  const int64_t segs = (int64_t)B * H * ((W + 63) / 64);
+  const int spb = (int)((segs + nblk - 1) / nblk);
+  switch (cin) {
+    case 1: stem_wgrad_kernel<1><<<nblk, 256, 0, st>>>(x0, C0, x1, in_scale, in_shift, (const __nv_bfloat16*)dy, workspace, B, H, W, Cout, spb); break;
+    case 2: stem_wgrad_kernel<2><<<nblk, 256, 0, st>>>(x0, C0, x1, in_scale, in_shift, (const __nv_bfloat16*)dy, workspace, B, H, W, Cout, spb); break;
+    case 3: stem_wgrad_kernel<3><<<nblk, 256, 0, st>>>(x0, C0, x1, in_scale, in_shift, (const __nv_bfloat16*)dy, workspace, B, H, W, Cout, spb); break;
+    default: stem_wgrad_kernel<4><<<nblk, 256, 0, st>>>(x0, C0, x1, in_scale, in_shift, (const __nv_bfloat16*)dy, workspace, B, H, W, Cout, spb); break;
+  }
+  FM_LAUNCH_CHECK("stem_wgrad_kernel");
+  return launch_reduce(workspace, dw, 1, nblk, (int64_t)Cout * cin * 9, st);
+}
+
+static int head_blocks() { return 4 * sm_count(); }
+
+extern "C" int64_t fm_conv_head_bwd_workspace_elems(int32_t Cin) {
+  if (ensure_device()) return 0;
+  return (int64_t)head_blocks() * Cin * 9;
+}
+
+/* Cout == 1: da (bf16 NHWC, or NULL), dw fp32 [1][Cin][3][3] */
+extern "C" int fm_conv_head_bwd_f32(const void* a, const float* dy, const float* weight, float* workspace, void* da,
+                                    float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(a && dy && weight && workspace && dw, "head_bwd: null pointer");
+  FM_REQUIRE(Cin % 8 == 0 && Cin <= 512 && 512 % Cin == 0, "head_bwd: Cin must divide 512 and be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (da != nullptr) {
+    const int64_t total = (int64_t)B * H * W * (Cin / 8);
+    head_dgrad_kernel<<<ew_grid(total), 256, 9 * Cin * sizeof(float), st>>>(dy, weight, reinterpret_cast<uint4*>(da), B,
+                                                                          H, W, Cin);
+    FM_LAUNCH_CHECK("head_dgrad_kernel");
+  }
+  const int nblk = head_blocks();
+  const int64_t px = (int64_t)B * H * W;
+  const int ppb = (int)((px + nblk - 1) / nblk);
+  head_wgrad_kernel<<<nblk, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a), dy, workspace, B, H, W, Cin, ppb);
+  FM_LAUNCH_CHECK("head_wgrad_kernel");
+  return launch_reduce(workspace, dw, 1, nblk, (int64_t)Cin * 9, st);
+}
+
+/* out[0] = scale * sum(x)  (mode 0)  or  scale * sum((x - (t1 - t2))^2)  (mode 1); workspace: 1024 doubles */
+extern "C" int fm_sum_f32(const float* x, const float* t1, const float* t2, double* workspace, float* out, int64_t n,
+                          int32_t mode, double scale, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && workspace && out && n >= 0, "sum: bad argument");
+  FM_REQUIRE(mode == 0 || (mode == 1 && t1 != nullptr), "sum: mode 1 needs a target");
+  int blocks = ew_grid(n);
+  if (blocks > 1024) blocks = 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  sum_partial_kernel<<<blocks, 256, 0, st>>>(x, t1, t2, workspace, n, mode);
+  FM_LAUNCH_CHECK("sum_partial_kernel");
+  sum_final_kernel<<<1, 32, 0, st>>>(workspace, blocks, scale, out);
+  FM_LAUNCH_CHECK("sum_final_kernel");
+  return 0;
+}
+
+extern "C" int fm_mse_bwd_f32(const float* pred, const float* t1, const float* t2, const float* gscalar, float* dpred,
+                              int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(pred && t1 && gscalar && dpred && n > 0, "mse_bwd: bad argument");
+  mse_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(pred, t1, t2, gscalar, dpred, (float)(2.0 / (double)n), n);
+  FM_LAUNCH_CHECK("mse_bwd_kernel");
+  return 0;
+}
+
+extern "C" int fm_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                            float eps, float weight_decay, int64_t step, float grad_scale, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "adamw: bad argument");
+  if (n == 0) return 0;
+  /* scalar prefactors in double, as torch.optim.adamw._single_tensor_adamw computes them on the host */
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float decay = (float)(1.0 - (double)lr * (double)weight_decay);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  adamw_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, decay, (float)(1.0 - (double)beta1), beta2, (float)(1.0 - (double)beta2),
+                                                            step_size, bc2_sqrt, eps, grad_scale);
+  FM_LAUNCH_CHECK("adamw_kernel");
+  return 0;
+}

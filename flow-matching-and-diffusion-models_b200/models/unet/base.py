@@ -40,6 +40,15 @@ class BaseUNetND(nn.Module, ABC):
         weight, bias, offsets, silu = plan
         return TembPack(emb, ops.linear_f32(emb, weight, bias, silu_in=silu), offsets)
 
+    def _wants_autograd(self, x: torch.Tensor, t_table) -> bool:
+        """Autograd is recording, the module is in training mode and has trainable parameters: run the
+        differentiable graph (`training.graph`).  Sampling runs under `torch.no_grad()` / `.eval()` and is unaffected."""
+        if not (torch.is_grad_enabled() and self.training and x.is_cuda and t_table is None):
+            return False
+        from ...training import graph
+
+        return graph.supported(self) and any(p.requires_grad for p in self.parameters())
+
     @abstractmethod
     def _build_time_embedding(self, t: Optional[torch.Tensor], x: torch.Tensor, *, t_table=None,
                               step_dev=None) -> torch.Tensor:
@@ -57,6 +66,11 @@ class BaseUNetND(nn.Module, ABC):
                 step_dev: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
         """`t_table`/`step_dev` (fp32 device table + int32 device cursor) replace `t` under CUDA-graph replay:
         every sample of the batch then uses the timestep `t_table[*step_dev]`."""
+        if self._wants_autograd(x, t_table):
+            # training step (`flow_matching_lib.py:158-169`): same modules and parameters, differentiable kernels
+            from ...training import graph
+
+            return self._postprocess_output(graph.unet_forward(self, x, t, context))
         if t_table is not None:
             emb = self._build_time_embedding(None, x, t_table=t_table, step_dev=step_dev)
         else:

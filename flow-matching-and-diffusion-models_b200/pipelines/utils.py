@@ -211,6 +211,7 @@ def _graph_sampler(model, scheduler, shape, device, cond_shape) -> GraphSampler:
     return gs
 
 
+@torch.no_grad()
 def sample_with_scheduler(model: torch.nn.Module, scheduler, num_inference_steps: int,
                           sample_shape: Tuple[int, ...], device: torch.device,
                           conditioning_mode: Optional[str] = None,

@@ -1,0 +1,425 @@
+"""Differentiable forms of the B200 ops: `torch.autograd.Function`s whose forward AND backward are the hand-written
+kernels (csrc/train.cu + the forward kernels), so `loss.backward()` of the reference's training step
+(`src/pipelines/train/flow_matching_lib.py:138-182`) runs on them.  torch.autograd is used as the graph engine only
+(gradient routing / accumulation); there is no eager or cuDNN fallback inside these functions.
+
+Activations are bf16 channels_last, parameters fp32 (bf16-autocast semantics: fp32 master weights, bf16 matmul
+inputs, fp32 accumulation; `flow_matching_lib.py:158-164`)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib, ops
+from ..ops import _ptr, _stream
+
+BF16 = torch.bfloat16
+
+
+def _ws(n: int, device, dtype=torch.float32) -> torch.Tensor:
+    return torch.empty((max(int(n), 1),), dtype=dtype, device=device)
+
+
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    return ops.to_nhwc_bf16(t)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# raw kernel wrappers
+# --------------------------------------------------------------------------------------------------------------
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, ksize: int, stride: int, c_begin: int) -> None:
+    """dw[:, c_begin:c_begin+C_x] (fp32 OIHW, or [O][I] for 1x1) += nothing: the slice is overwritten."""
+    lib = _lib.lib()
+    b, cin, h, w = x.shape
+    cout = dy.shape[1]
+    ho, wo = dy.shape[2], dy.shape[3]
+    n = int(lib.fm_conv_wgrad_workspace_elems(b, ho, wo, cin, cout, ksize))
+    if n <= 0:
+        raise RuntimeError(f"fmdm_b200.conv_wgrad: unsupported shape B={b} Ho={ho} Wo={wo} k={ksize}")
+    ws = _ws(n, x.device)
+    _lib.check(
+        lib.fm_conv_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), b, h, w, cin, cout, ksize,
+                               stride, dw.shape[1], c_begin, _stream()),
+        "conv_wgrad",
+    )
+
+
+def colsum(dy: torch.Tensor, want_total: bool):
+    """(per-sample [B][C] fp32 sums over pixels, total [C] or None) of a bf16 NHWC gradient."""
+    lib = _lib.lib()
+    b, c, h, w = dy.shape
+    ws = _ws(lib.fm_colsum_workspace_elems(b, h * w, c), dy.device)
+    out = torch.empty((b, c), dtype=torch.float32, device=dy.device)
+    total = torch.empty((c,), dtype=torch.float32, device=dy.device) if want_total else None
+    _lib.check(lib.fm_colsum_bf16(dy.data_ptr(), ws.data_ptr(), out.data_ptr(), _ptr(total), b, h * w, c, _stream()),
+               "colsum")
+    return out, total
+
+
+def zero_insert2x(x: torch.Tensor) -> torch.Tensor:
+    b, c, h, w = x.shape
+    out = ops.empty_nhwc(b, c, 2 * h, 2 * w, x.device)
+    _lib.check(_lib.lib().fm_zero_insert2x_bf16(x.data_ptr(), out.data_ptr(), b, h, w, c, _stream()), "zero_insert2x")
+    return out
+
+
+def sumpool2x2(x: torch.Tensor) -> torch.Tensor:
+    b, c, h2, w2 = x.shape
+    out = ops.empty_nhwc(b, c, h2 // 2, w2 // 2, x.device)
+    _lib.check(_lib.lib().fm_sumpool2x2_bf16(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, _stream()),
+               "sumpool2x2")
+    return out
+
+
+def _dgrad_weight(w: torch.Tensor, c_begin: int, c_count: int) -> ops.PackedConvWeight:
+    """Packed weights of the data-gradient conv: in/out channels swapped, taps mirrored (tiny host-side views)."""
+    ws = w.detach()[:, c_begin:c_begin + c_count]
+    if ws.dim() == 2:
+        wt = ws.t().contiguous()
+    else:
+        wt = ws.flip(2, 3).transpose(0, 1).contiguous()
+    return ops.pack_conv_weight([(wt, 0, wt.shape[1])])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# conv
+# --------------------------------------------------------------------------------------------------------------
+class _ConvFn(Function):
+    """out = conv(virtual concat of srcs) + bias + addvec[b] + residual   (ops.conv2d), all segments 'same' padding."""
+
+    @staticmethod
+    def forward(ctx, meta, *args):
+        stride, segs, nsrc, nw = meta  # segs: per source (weight index, c_begin, c_count)
+        srcs = [_nhwc(a) for a in args[:nsrc]]
+        weights = list(args[nsrc:nsrc + nw])
+        bias, addvec, residual = args[nsrc + nw:nsrc + nw + 3]
+        pw = ops.pack_conv_weight([(weights[wi], cb, cc) for wi, cb, cc in segs])
+        if residual is not None:
+            residual = _nhwc(residual)
+        out = ops.conv2d(srcs, pw, stride=stride, bias=None if bias is None else bias.detach().float().contiguous(),
+                         addvec=None if addvec is None else addvec.detach().float().contiguous(), residual=residual)
+        ctx.meta = meta
+        ctx.flags = (bias is not None, addvec is not None, residual is not None)
+        ctx.save_for_backward(*srcs, *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        stride, segs, nsrc, nw = ctx.meta
+        has_bias, has_addvec, has_res = ctx.flags
+        saved = ctx.saved_tensors
+        srcs, weights = saved[:nsrc], saved[nsrc:]
+        dy = _nhwc(dy)
+        need = ctx.needs_input_grad  # index 0 is `meta`
+        grads = [None] * (nsrc + nw + 3)
+        dyz = None
+        for i, (wi, cb, cc) in enumerate(segs):
+            if not need[1 + i]:
+                continue
+            pw = _dgrad_weight(weights[wi], cb, cc)
+            if stride == 1:
+                grads[i] = ops.conv2d([dy], pw)
+            else:
+                if dyz is None:
+                    dyz = zero_insert2x(dy)
+                grads[i] = ops.conv2d([dyz], pw)
+        dws = {}
+        for i, (wi, cb, cc) in enumerate(segs):
+            if not need[1 + nsrc + wi]:
+                continue
+            w = weights[wi]
+            if wi not in dws:
+                covered = sum(c for j, _, c in segs if j == wi)
+                dws[wi] = (torch.empty if covered == w.shape[1] else torch.zeros)(
+                    w.shape, dtype=torch.float32, device=w.device)
+            ks = 1 if w.dim() == 2 else int(w.shape[-1])
+            conv_wgrad(dy, srcs[i], dws[wi], ksize=ks, stride=stride, c_begin=cb)
+        for wi, dw in dws.items():
+            grads[nsrc + wi] = dw
+        if (has_bias and need[1 + nsrc + nw]) or (has_addvec and need[1 + nsrc + nw + 1]):
+            per_sample, total = colsum(dy, has_bias)
+            if has_bias:
+                grads[nsrc + nw] = total
+            if has_addvec:
+                grads[nsrc + nw + 1] = per_sample
+        if has_res and need[1 + nsrc + nw + 2]:
+            grads[nsrc + nw + 2] = dy
+        return (None, *grads)
+
+
+def conv(srcs: Sequence[torch.Tensor], weights: Sequence[tuple], *, bias=None, stride: int = 1, addvec=None,
+         residual=None) -> torch.Tensor:
+    """srcs[i] is convolved with weights[i] = (param, c_begin, c_count): the channel slice of an OIHW (or [O][I])
+    fp32 parameter; several sources may slice the same parameter (virtual concat) or different ones (conv2 + skip)."""
+    uniq, segs = [], []
+    for w, cb, cc in weights:
+        for j, u in enumerate(uniq):
+            if u is w:
+                segs.append((j, int(cb), int(cc)))
+                break
+        else:
+            uniq.append(w)
+            segs.append((len(uniq) - 1, int(cb), int(cc)))
+    meta = (int(stride), tuple(segs), len(srcs), len(uniq))
+    return _ConvFn.apply(meta, *srcs, *uniq, bias, addvec, residual)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GroupNorm (+ scale-shift) (+ SiLU)
+# --------------------------------------------------------------------------------------------------------------
+class _GroupNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu):
+        lib = _lib.lib()
+        x = _nhwc(x)
+        b, c, h, w = x.shape
+        g32 = gamma.detach().float().contiguous()
+        b32 = beta.detach().float().contiguous()
+        ss = None if scale_shift is None else scale_shift.detach().float().contiguous()
+        st = _stream()
+        n = int(lib.fm_groupnorm_workspace_elems(b, h * w, c, groups))
+        if n <= 0:
+            raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={c} groups={groups}")
+        ws = _ws(n, x.device)
+        stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x.device)
+        _lib.check(lib.fm_groupnorm_stats_bf16(x.data_ptr(), c, None, 0, b, h * w, groups, float(eps), ws.data_ptr(),
+                                               stats.data_ptr(), st), "groupnorm_stats")
+        out = ops.empty_nhwc(b, c, h, w, x.device)
+        _lib.check(lib.fm_groupnorm_apply_bf16(x.data_ptr(), c, None, 0, b, h * w, groups, stats.data_ptr(),
+                                               g32.data_ptr(), b32.data_ptr(), _ptr(ss),
+                                               0 if ss is None else ss.stride(0), int(silu), out.data_ptr(), st),
+                   "groupnorm_apply")
+        ctx.cfg = (groups, bool(silu), ss is not None)
+        ctx.save_for_backward(x, stats, g32, b32, *([ss] if ss is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        groups, silu, has_ss = ctx.cfg
+        x, stats, g32, b32, *rest = ctx.saved_tensors
+        ss = rest[0] if has_ss else None
+        dout = _nhwc(dout)
+        b, c, h, w = x.shape
+        ws = _ws(lib.fm_groupnorm_bwd_workspace_elems(b, h * w, c), x.device)
+        dx = ops.empty_nhwc(b, c, h, w, x.device)
+        dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
+        dss = torch.empty((b, 2 * c), dtype=torch.float32, device=x.device) if has_ss else None
+        _lib.check(
+            lib.fm_groupnorm_bwd_bf16(x.data_ptr(), dout.data_ptr(), stats.data_ptr(), g32.data_ptr(), b32.data_ptr(),
+                                      _ptr(ss), 0 if ss is None else ss.stride(0), int(silu), b, h * w, c, groups,
+                                      ws.data_ptr(), dx.data_ptr(), dgb.data_ptr(), _ptr(dss), _stream()),
+            "groupnorm_bwd",
+        )
+        return dx, dgb[0], dgb[1], dss, None, None, None
+
+
+def group_norm(x, gamma, beta, *, groups: int, eps: float, silu: bool, scale_shift=None) -> torch.Tensor:
+    return _GroupNormFn.apply(x, gamma, beta, scale_shift, int(groups), float(eps), bool(silu))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# self-attention over a fused qkv projection (DiffusersAttentionND layout: NHWC [b][T][3C], head h at h*dh)
+# --------------------------------------------------------------------------------------------------------------
+class _AttentionFn(Function):
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        qkv = _nhwc(qkv)
+        b, c3, hh, ww = qkv.shape
+        c = c3 // 3
+        t, hd = hh * ww, c // heads
+        att = ops.empty_nhwc(b, c, hh, ww, qkv.device)
+        flat = qkv.permute(0, 2, 3, 1).reshape(-1)
+        ops.attention(flat, flat[c:], flat[2 * c:], att.permute(0, 2, 3, 1).reshape(-1), batch=b, heads=heads, tq=t,
+                      tk=t, head_dim=hd, q_strides=(t * 3 * c, hd, 3 * c), kv_strides=(t * 3 * c, hd, 3 * c),
+                      o_strides=(t * c, hd, c))
+        ctx.heads = heads
+        ctx.save_for_backward(qkv, att)
+        return att
+
+    @staticmethod
+    def backward(ctx, datt):
+        qkv, att = ctx.saved_tensors
+        heads = ctx.heads
+        datt = _nhwc(datt)
+        b, c3, hh, ww = qkv.shape
+        c = c3 // 3
+        t, hd = hh * ww, c // heads
+        dqkv = ops.empty_nhwc(b, c3, hh, ww, qkv.device)
+        esz = 2
+        q, dq = qkv.data_ptr(), dqkv.data_ptr()
+        _lib.check(
+            _lib.lib().fm_attention_bwd_bf16(q, q + c * esz, q + 2 * c * esz, att.data_ptr(), datt.data_ptr(), dq,
+                                             dq + c * esz, dq + 2 * c * esz, b, heads, t, hd, t * 3 * c, hd, 3 * c,
+                                             t * c, hd, c, 1.0 / math.sqrt(hd), _stream()),
+            "attention_bwd",
+        )
+        return dqkv, None
+
+
+def attention_qkv(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    return _AttentionFn.apply(qkv, int(heads))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# tiny fp32 Linear (time MLP, per-block embedding projections): y = f(x) W^T + b, f = SiLU if silu_in
+# --------------------------------------------------------------------------------------------------------------
+class _LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu_in):
+        x32 = x.detach().float().contiguous()
+        w32 = weight.detach().float().contiguous()
+        y = ops.linear_f32(x32, w32, None if bias is None else bias.detach().float().contiguous(), silu_in=silu_in)
+        ctx.silu_in = bool(silu_in)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x32, w32)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        dx = dw = db = None
+        dyt = dy.t().contiguous()                                              # [O][B]
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear_f32(dy, w.t().contiguous())                        # [B][I] = dy W
+            if ctx.silu_in:
+                out = torch.empty_like(dx)
+                _lib.check(_lib.lib().fm_silu_bwd_f32(x.data_ptr(), dx.data_ptr(), out.data_ptr(), dx.numel(),
+                                                      _stream()), "silu_bwd")
+                dx = out
+        if ctx.needs_input_grad[1]:
+            # dW^T[i][o] = sum_b f(x[b][i]) dy[b][o]: the same kernel with the batch as the reduction axis
+            dw = ops.linear_f32(x.t().contiguous(), dyt, silu_in=ctx.silu_in).t().contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            ones = torch.ones((1, dy.shape[0]), dtype=torch.float32, device=dy.device)
+            db = ops.linear_f32(ones, dyt).reshape(-1)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, *, silu_in: bool = False) -> torch.Tensor:
+    return _LinearFn.apply(x, weight, bias, bool(silu_in))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# stem / head convs, nearest upsample
+# --------------------------------------------------------------------------------------------------------------
+class _StemFn(Function):
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, in_scale, in_shift):
+        x0 = x0.detach().float().contiguous()
+        x1 = None if x1 is None else x1.detach().float().contiguous()
+        w32 = weight.detach().float().contiguous()
+        out = ops.conv_stem(x0, x1, w32, None if bias is None else bias.detach().float().contiguous(),
+                            in_scale=in_scale, in_shift=in_shift, want_stats=False)
+        ctx.cfg = (float(in_scale), float(in_shift), x1 is not None, bias is not None, tuple(weight.shape))
+        ctx.save_for_backward(x0, *([x1] if x1 is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        in_scale, in_shift, has_x1, has_bias, wshape = ctx.cfg
+        x0, *rest = ctx.saved_tensors
+        x1 = rest[0] if has_x1 else None
+        dy = _nhwc(dy)
+        b, c0, h, w = x0.shape
+        c1 = x1.shape[1] if x1 is not None else 0
+        cout = wshape[0]
+        ws = _ws(lib.fm_conv_stem_wgrad_workspace_elems(c0 + c1, cout), dy.device)
+        dw = torch.empty(wshape, dtype=torch.float32, device=dy.device)
+        _lib.check(lib.fm_conv_stem_wgrad_f32(x0.data_ptr(), c0, _ptr(x1), c1, in_scale, in_shift, dy.data_ptr(),
+                                              ws.data_ptr(), dw.data_ptr(), b, h, w, cout, _stream()), "stem_wgrad")
+        db = colsum(dy, True)[1] if has_bias else None
+        return None, None, dw, db, None, None
+
+
+def conv_stem(x0, x1, weight, bias, *, in_scale: float = 1.0, in_shift: float = 0.0) -> torch.Tensor:
+    return _StemFn.apply(x0, x1, weight, bias, float(in_scale), float(in_shift))
+
+
+def sum_f32(x: torch.Tensor, *, t1=None, t2=None, mode: int = 0, scale: float = 1.0) -> torch.Tensor:
+    ws = _ws(1024, x.device, torch.float64)
+    out = torch.empty((1,), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().fm_sum_f32(x.data_ptr(), _ptr(t1), _ptr(t2), ws.data_ptr(), out.data_ptr(), x.numel(), mode,
+                                     float(scale), _stream()), "sum_f32")
+    return out
+
+
+class _HeadFn(Function):
+    """3x3 head conv to ONE output channel: bf16 NHWC -> fp32 NCHW."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias):
+        a = _nhwc(a)
+        w32 = weight.detach().float().contiguous()
+        out = ops.conv_head(a, w32, None if bias is None else bias.detach().float().contiguous())
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(a, w32)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        a, w32 = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        b, cin, h, w = a.shape
+        ws = _ws(lib.fm_conv_head_bwd_workspace_elems(cin), a.device)
+        da = ops.empty_nhwc(b, cin, h, w, a.device) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w32)
+        _lib.check(lib.fm_conv_head_bwd_f32(a.data_ptr(), dy.data_ptr(), w32.data_ptr(), ws.data_ptr(), _ptr(da),
+                                            dw.data_ptr(), b, h, w, cin, _stream()), "head_bwd")
+        db = sum_f32(dy) if ctx.has_bias else None
+        return da, dw, db
+
+
+def conv_head(a, weight, bias) -> torch.Tensor:
+    if weight.shape[0] != 1:
+        raise RuntimeError("fmdm_b200.training: the head conv backward supports out_channels == 1")
+    return _HeadFn.apply(a, weight, bias)
+
+
+class _UpsampleFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample_nearest2x(_nhwc(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return sumpool2x2(_nhwc(dy))
+
+
+def upsample_nearest2x(x) -> torch.Tensor:
+    return _UpsampleFn.apply(x)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# fused velocity-target MSE (flow_matching_lib.py:163-164): mean((pred - (noise - clean))^2)
+# --------------------------------------------------------------------------------------------------------------
+class _MseFn(Function):
+    @staticmethod
+    def forward(ctx, pred, t1, t2):
+        pred = pred.float().contiguous()
+        t1 = t1.detach().float().contiguous()
+        t2 = None if t2 is None else t2.detach().float().contiguous()
+        ctx.save_for_backward(pred, t1, *([t2] if t2 is not None else []))
+        return sum_f32(pred, t1=t1, t2=t2, mode=1, scale=1.0 / pred.numel()).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, t1, *rest = ctx.saved_tensors
+        t2 = rest[0] if rest else None
+        g = g.float().reshape(1).contiguous()
+        dpred = torch.empty_like(pred)
+        _lib.check(_lib.lib().fm_mse_bwd_f32(pred.data_ptr(), t1.data_ptr(), _ptr(t2), g.data_ptr(), dpred.data_ptr(),
+                                             pred.numel(), _stream()), "mse_bwd")
+        return dpred, None, None
+
+
+def mse_loss(pred: torch.Tensor, target: torch.Tensor, minus: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mean((pred - (target - minus))^2); `minus=None` is plain F.mse_loss(pred, target)."""
+    return _MseFn.apply(pred, target, minus)

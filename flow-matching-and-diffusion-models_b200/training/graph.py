@@ -1,0 +1,142 @@
+"""Differentiable forward of the denoiser for the training step (BASELINE config 5).
+
+`BaseUNetND.forward` routes here when autograd is recording and the model is in training mode: the same modules and
+parameters (`state_dict` unchanged), but every op is one of `training.functions` so that `loss.backward()` runs the
+hand-written backward kernels.  The inference-only fusions that have no backward (operand-transform GroupNorm, the
+batched time-embedding projection, the nearest-2x folded into a producer's store, CUDA-graph replay) are not used:
+the normalised activations are materialised because the weight-gradient GEMMs need them anyway.
+
+Reference call chain restated: `unet_diffusers_nd.py:146-191`, `legacy_unet.py:60-160`, `residual.py:92-121`,
+`attention.py:220-274`, `upsampling.py:24-62`."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._runtime import out_of_scope
+from . import functions as F
+
+
+def supported(model) -> bool:
+    from ..models.unet.unet_diffusers_nd import UNetDiffusersND
+
+    return isinstance(model, UNetDiffusersND) and model.spatial_dims == 2 and model.cross_attention_dim is None
+
+
+def _gn(norm: nn.GroupNorm, x, *, silu: bool, scale_shift=None):
+    return F.group_norm(x, norm.weight, norm.bias, groups=norm.num_groups, eps=norm.eps, silu=silu,
+                        scale_shift=scale_shift)
+
+
+def resblock(blk, x: torch.Tensor, emb: torch.Tensor) -> torch.Tensor:
+    """`residual.py:92-121` (GroupNorm / SiLU variant)."""
+    if not (blk.spatial_dims == 2 and blk.norm_type == "gn" and blk.act_name in ("silu", "swish")) \
+            or blk.dropout > 0:
+        out_of_scope(f"training ResBlockND(norm={blk.norm_type}, act={blk.act_name}, dropout={blk.dropout})")
+        raise RuntimeError("fmdm_b200.training: unsupported ResBlockND variant")
+    c, oc = blk.channels, blk.out_channels
+    h = _gn(blk.norm1, x, silu=True)
+    addvec = scale_shift = None
+    if blk.uses_embedding:
+        if emb is None:
+            raise ValueError("ResBlockND expects `emb` when emb_channels is set.")
+        e = F.linear(emb, blk.emb_layers.weight, blk.emb_layers.bias, silu_in=blk.emb_activation_before_proj)
+        if blk.use_scale_shift_norm:
+            scale_shift = e
+        elif blk.add_embedding_to_hidden:
+            addvec = e
+    h = F.conv([h], [(blk.conv1.conv.weight, 0, c)], bias=blk.conv1.conv.bias, addvec=addvec)
+    h = _gn(blk.norm2, h, silu=True, scale_shift=scale_shift)
+    w2, b2 = blk.conv2.conv.weight, blk.conv2.conv.bias
+    if isinstance(blk.skip_connection, nn.Identity):
+        return F.conv([h], [(w2, 0, oc)], bias=b2, residual=x)
+    skip = blk.skip_connection.conv
+    ws = skip.weight if skip.weight.shape[-1] == 3 else skip.weight.reshape(oc, c)
+    bias = b2
+    if skip.bias is not None:
+        bias = skip.bias if b2 is None else b2 + skip.bias
+    return F.conv([h, x], [(w2, 0, oc), (ws, 0, c)], bias=bias)
+
+
+def attention(att, x: torch.Tensor) -> torch.Tensor:
+    """`attention.py:220-274` (self-attention)."""
+    b, c, hh, ww = x.shape
+    if att.context_dim is not None or att.head_dim not in (8, 16, 32, 64) or att.dropout > 0:
+        out_of_scope("training DiffusersAttentionND (cross-attention / dropout / head_dim)")
+        raise RuntimeError("fmdm_b200.training: unsupported attention variant")
+    gn = att.group_norm
+    n = _gn(gn, x, silu=False)
+    w = torch.cat([att.to_q.weight, att.to_k.weight, att.to_v.weight], 0)
+    bias = torch.cat([att.to_q.bias, att.to_k.bias, att.to_v.bias], 0)
+    qkv = F.conv([n], [(w, 0, c)], bias=bias)
+    a = F.attention_qkv(qkv, att.heads)
+    return F.conv([a], [(att.to_out[0].weight, 0, c)], bias=att.to_out[0].bias, residual=x)
+
+
+def downsample(down, x):
+    if not down.use_conv:
+        out_of_scope("training DownsampleND(use_conv=False)")
+        raise RuntimeError("fmdm_b200.training: unsupported downsampler")
+    conv = down.op.conv
+    return F.conv([x], [(conv.weight, 0, down.channels)], bias=conv.bias, stride=2)
+
+
+def upsample(up, x):
+    y = F.upsample_nearest2x(x)
+    if not up.use_conv:
+        return y
+    conv = up.conv.conv
+    return F.conv([y], [(conv.weight, 0, up.channels)], bias=conv.bias)
+
+
+def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
+    """`UNetDiffusersND.forward` with autograd: returns the fp32 NCHW prediction."""
+    if not supported(model):
+        out_of_scope(f"training {type(model).__name__}")
+        raise RuntimeError("fmdm_b200.training: only UNetDiffusersND (2-D, self-attention) has a training path")
+    ops.require_cuda(x, "training.unet_forward")
+    t = model._normalize_timesteps(t, x)
+    feats = ops.timestep_embedding(t, model.time_proj_dim, 10000.0, flip_sin_to_cos=model.flip_sin_to_cos,
+                                   freq_shift=float(model.freq_shift))
+    te = model.time_embedding
+    emb = F.linear(feats, te.linear_1.weight, te.linear_1.bias)
+    emb = F.linear(emb, te.linear_2.weight, te.linear_2.bias, silu_in=True)  # SiLU between the two layers
+
+    scale, shift = (2.0, -1.0) if model.center_input_sample else (1.0, 0.0)
+    cin = x.shape[1] + (context.shape[1] if context is not None else 0)
+    if cin != model.conv_in.in_channels:
+        raise ValueError(f"UNetDiffusersND expected {model.conv_in.in_channels} input channels, got {cin}")
+    if cin > 4:
+        out_of_scope(f"training stem conv with {cin} input channels")
+        raise RuntimeError("fmdm_b200.training: the stem backward supports up to 4 input channels")
+    sample = F.conv_stem(x, context, model.conv_in.weight, model.conv_in.bias, in_scale=scale, in_shift=shift)
+
+    skips = [sample]
+    for block in model.down_blocks:
+        for i, res in enumerate(block.resnets):
+            sample = resblock(res, sample, emb)
+            if block.attentions is not None:
+                sample = attention(block.attentions[i], sample)
+            skips.append(sample)
+        if block.downsamplers is not None:
+            for d in block.downsamplers:
+                sample = downsample(d, sample)
+            skips.append(sample)
+    mid = model.mid_block
+    if mid is not None:
+        sample = resblock(mid.resnets[0], sample, emb)
+        if mid.attentions is not None:
+            sample = attention(mid.attentions[0], sample)
+        sample = resblock(mid.resnets[1], sample, emb)
+    for block in model.up_blocks:
+        for i, res in enumerate(block.resnets):
+            skip = skips.pop()
+            sample = resblock(res, torch.cat([sample, skip], 1), emb)  # `legacy_unet.py:150`
+            if block.attentions is not None:
+                sample = attention(block.attentions[i], sample)
+        if block.upsamplers is not None:
+            for u in block.upsamplers:
+                sample = upsample(u, sample)
+    sample = _gn(model.conv_norm_out, sample, silu=True)
+    return F.conv_head(sample, model.conv_out.weight, model.conv_out.bias)

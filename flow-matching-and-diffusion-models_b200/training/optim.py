@@ -1,0 +1,112 @@
+"""AdamW over ONE flat fp32 parameter buffer: a single kernel launch per optimiser step.
+
+Drop-in for the `torch.optim.AdamW(model.parameters(), lr, weight_decay)` of `flow_matching_lib.py:74`: same
+hyper-parameters, same update arithmetic (decoupled weight decay, bias correction, eps outside the square root), same
+`step()/zero_grad()/state_dict()` surface.  The parameters are re-seated as views of one contiguous buffer and their
+`.grad`s as views of a second one, so autograd accumulates gradients straight into the flat buffer, the data-parallel
+all-reduce works on contiguous slices of it (`training.ddp`) and the update is `fm_adamw_f32` over the whole thing."""
+from __future__ import annotations
+
+from typing import Iterable
+
+import torch
+
+from .. import _lib
+from ..ops import _stream
+
+
+class FlatBuffers:
+    """Re-seats `params` (fp32, one device) onto a flat buffer; `.grad`s live in `self.grad`.
+
+    The flat order is the REVERSE of the given order: backward produces gradients roughly last-layer-first, so
+    buckets of consecutive flat ranges complete in order (see `training.ddp.BucketedAllReduce`)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatBuffers: no trainable parameters")
+        dev = self.params[0].device
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FlatBuffers: parameters must be fp32 on one device")
+        order = list(reversed(self.params))
+        self.offsets = {}
+        off = 0
+        for p in order:
+            self.offsets[id(p)] = off
+            off += (p.numel() + 3) // 4 * 4  # keep every slice 16-byte aligned
+        self.numel = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p in order:
+                o, n = self.offsets[id(p)], p.numel()
+                self.data[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.data[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+
+    def slice_of(self, p) -> tuple:
+        return self.offsets[id(p)], p.numel()
+
+    def ensure_grad_views(self) -> None:
+        """Re-attach `.grad` views (after a `zero_grad(set_to_none=True)` from foreign code)."""
+        for p in self.params:
+            o, n = self.slice_of(p)
+            g = p.grad
+            if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * o:
+                view = self.grad[o:o + n].view(p.shape)
+                if g is not None:
+                    view.copy_(g)
+                p.grad = view
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+        params = list(params)
+        if any(isinstance(p, dict) for p in params):
+            raise ValueError("FusedAdamW: a single parameter group (flow_matching_lib.py:74 passes model.parameters())")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.flat = FlatBuffers(self.param_groups[0]["params"])
+        dev = self.flat.data.device
+        self.exp_avg = torch.zeros_like(self.flat.data)
+        self.exp_avg_sq = torch.zeros_like(self.flat.data)
+        self.step_count = 0
+        self.grad_scale = 1.0  # folded into the kernel's gradient read (1/world_size of the data-parallel mean)
+        assert dev.type == "cuda", "FusedAdamW needs CUDA parameters (no CPU implementation)"
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        # the gradients are views of one buffer: clear it in one launch and keep the views
+        self.flat.ensure_grad_views()
+        _lib.check(_lib.lib().fm_memset_f32(self.flat.grad.data_ptr(), self.flat.numel, _stream()), "memset")
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.flat.ensure_grad_views()
+        g = self.param_groups[0]
+        self.step_count += 1
+        b1, b2 = g["betas"]
+        _lib.check(
+            _lib.lib().fm_adamw_f32(self.flat.data.data_ptr(), self.flat.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                    self.exp_avg_sq.data_ptr(), self.flat.numel, float(g["lr"]), float(b1), float(b2),
+                                    float(g["eps"]), float(g["weight_decay"]), self.step_count,
+                                    float(self.grad_scale), _stream()),
+            "adamw",
+        )
+        # the inference-side packed-weight caches key on Parameter._version, which the flat update bypasses
+        torch._C._increment_version(self.flat.params)
+        return loss
+
+    # checkpoint surface (torch.optim state_dict layout is per-parameter; ours is per-buffer)
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+    def load_state_dict(self, state):
+        self.step_count = int(state["step"])
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self.param_groups[0].update(state["param_groups"][0])

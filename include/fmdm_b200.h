@@ -217,6 +217,66 @@ int fm_counter_add(int32_t* ctr, int32_t delta, fm_stream_t stream);
 /* y = clamp(x, lo, hi) fp32 (samplers/diffusion_like.py:135) */
 int fm_clamp_f32(float* y, const float* x, float lo, float hi, int64_t n, fm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step: the backward of the ops above plus the loss and optimiser kernels, i.e. what
+ * torch.autograd executes for src/pipelines/train/flow_matching_lib.py:138-182 (F.conv2d / F.group_norm / SiLU /
+ * SDPA / F.linear / F.mse_loss backward, torch.optim.AdamW.step).  All reductions are two-stage with a fixed
+ * summation order (deterministic, no atomics).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* conv wgrad: dw[co][c_begin+ci][kh][kw] = sum_{b,yo,xo} dy[b][yo][xo][co] * x[b][yo*stride+kh-pad][xo*stride+kw-pad][ci]
+ * dy bf16 NHWC [B][Ho][Wo][Cout], x bf16 NHWC [B][H][W][Cin], dw fp32 OIHW [Cout][cin_total][k][k] (the slice
+ * [c_begin, c_begin+Cin) is written).  ksize 1 or 3 (pad = ksize/2), stride 1 or 2.
+ * workspace: fm_conv_wgrad_workspace_elems(...) floats (split-K partials). */
+int64_t fm_conv_wgrad_workspace_elems(int32_t B, int32_t Ho, int32_t Wo, int32_t Cin, int32_t Cout, int32_t ksize);
+int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, float* workspace, int32_t B, int32_t H, int32_t W,
+                       int32_t Cin, int32_t Cout, int32_t ksize, int32_t stride, int32_t cin_total, int32_t c_begin,
+                       fm_stream_t stream);
+/* out[b][c] = sum_p dy[b][p][c] (bf16 [B][HW][C] -> fp32 [B][C]; the time-embedding add gradient); total (or NULL)
+ * [c] = sum_b out[b][c] (the bias gradient).  workspace: fm_colsum_workspace_elems floats. */
+int64_t fm_colsum_workspace_elems(int32_t B, int64_t HW, int32_t C);
+int fm_colsum_bf16(const void* dy, float* workspace, float* out, float* total, int32_t B, int64_t HW, int32_t C,
+                   fm_stream_t stream);
+/* out[b][2y][2x][c] = x[b][y][x][c], zero elsewhere: turns the dgrad of a stride-2 conv into a stride-1 conv */
+int fm_zero_insert2x_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, fm_stream_t stream);
+/* out[b][y][x][c] = sum of the 2x2 block of x [B][2H][2W][C]: backward of fm_upsample_nearest2x_bf16 */
+int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, fm_stream_t stream);
+/* Backward of fm_groupnorm_apply_bf16 for one source: x, dout bf16 [B][HW][C]; stats as the forward computed them.
+ * dx bf16 [B][HW][C]; dgamma_dbeta fp32 [2][C]; dscale_shift fp32 [B][2C] (NULL iff scale_shift is NULL).
+ * workspace: fm_groupnorm_bwd_workspace_elems floats. */
+int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C);
+int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const float* stats, const float* gamma, const float* beta,
+                          const float* scale_shift, int64_t ss_stride, int32_t silu, int32_t B, int64_t HW, int32_t C,
+                          int32_t groups, float* workspace, void* dx, float* dgamma_dbeta, float* dscale_shift,
+                          fm_stream_t stream);
+/* Backward of fm_attention_bf16 (self-attention, tq == tk == T; q/k/v share the strides qs_*, o/dout share os_*;
+ * dq/dk/dv are written with the q strides).  Strides in elements. */
+int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,
+                          void* dk, void* dv, int32_t B, int32_t heads, int32_t T, int32_t head_dim, int64_t qs_b,
+                          int64_t qs_h, int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale,
+                          fm_stream_t stream);
+/* dx = dy * SiLU'(x), fp32 */
+int fm_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, fm_stream_t stream);
+/* Stem conv wgrad (inputs as fm_conv_stem_f32_bf16; 1..4 input channels): dw fp32 [Cout][C0+C1][3][3] */
+int64_t fm_conv_stem_wgrad_workspace_elems(int32_t Cin, int32_t Cout);
+int fm_conv_stem_wgrad_f32(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale, float in_shift,
+                           const void* dy_nhwc_bf16, float* workspace, float* dw, int32_t B, int32_t H, int32_t W,
+                           int32_t Cout, fm_stream_t stream);
+/* Head conv (Cout == 1) backward: a bf16 NHWC [B][H][W][Cin] (the conv input), dy fp32 [B][1][H][W];
+ * da bf16 NHWC (or NULL), dw fp32 [1][Cin][3][3] */
+int64_t fm_conv_head_bwd_workspace_elems(int32_t Cin);
+int fm_conv_head_bwd_f32(const void* a, const float* dy, const float* weight, float* workspace, void* da, float* dw,
+                         int32_t B, int32_t H, int32_t W, int32_t Cin, fm_stream_t stream);
+/* out[0] = scale * sum_i x[i] (mode 0) or scale * sum_i (x[i] - (t1[i] - t2[i]))^2 (mode 1, t2 may be NULL): the
+ * fused velocity-target MSE of flow_matching_lib.py:163-164.  workspace: 1024 doubles. */
+int fm_sum_f32(const float* x, const float* t1, const float* t2, double* workspace, float* out, int64_t n, int32_t mode,
+               double scale, fm_stream_t stream);
+/* dpred = (2/n) * gscalar[0] * (pred - (t1 - t2)) */
+int fm_mse_bwd_f32(const float* pred, const float* t1, const float* t2, const float* gscalar, float* dpred, int64_t n,
+                   fm_stream_t stream);
+/* torch.optim.AdamW.step over one flat fp32 parameter buffer (g is multiplied by grad_scale first) */
+int fm_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int64_t step, float grad_scale, fm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

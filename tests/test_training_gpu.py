@@ -1,0 +1,233 @@
+"""Training-step kernels against torch fp32 autograd of the same op on the same seeded inputs.
+
+Tolerances: bf16 activations / fp32 accumulation, so gradients are compared by relative L2 (<= 1e-2, the north star's
+per-step tolerance for bf16 tensors); the optimiser update and the MSE are fp32 and compared tightly."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as TF
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def nhwc(x):
+    return x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+@pytest.fixture(scope="module")
+def F():
+    from fmdm_b200.training import functions
+    return functions
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw,b", [
+    (128, 128, 3, 1, 32, 2), (64, 256, 3, 1, 16, 4), (256, 128, 1, 1, 16, 2), (128, 128, 3, 2, 32, 2),
+    (512, 512, 3, 1, 8, 2), (128, 1536, 1, 1, 8, 4), (192, 64, 3, 1, 16, 1),
+])
+def test_conv_backward(F, cin, cout, k, stride, hw, b):
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(b, cin, hw, hw, device=dev)
+    w = torch.randn(cout, cin, k, k, device=dev) * 0.05
+    bias = torch.randn(cout, device=dev)
+    addvec = torch.randn(b, cout, device=dev)
+    ho = hw // stride
+    res = torch.randn(b, cout, ho, ho, device=dev)
+    gy = torch.randn(b, cout, ho, ho, device=dev)
+    xb = nhwc(x).requires_grad_(True)
+    wp = (w if k == 3 else w.reshape(cout, cin)).clone().requires_grad_(True)
+    bp, ap = bias.clone().requires_grad_(True), addvec.clone().requires_grad_(True)
+    rp = nhwc(res).requires_grad_(True)
+    y = F.conv([xb], [(wp, 0, cin)], bias=bp, stride=stride, addvec=ap, residual=rp)
+    y.backward(nhwc(gy))
+    # reference: fp32 autograd on the bf16-rounded operands
+    xr = xb.detach().float().requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    br, ar = bias.clone().requires_grad_(True), addvec.clone().requires_grad_(True)
+    rr = rp.detach().float().requires_grad_(True)
+    yr = TF.conv2d(xr, wr, br, stride=stride, padding=k // 2) + ar[:, :, None, None] + rr
+    yr.backward(nhwc(gy).float())
+    assert rel_l2(y, yr) < 1e-2
+    assert rel_l2(xb.grad, xr.grad) < 1e-2
+    assert rel_l2(wp.grad.reshape(wr.shape), wr.grad) < 1e-2
+    assert rel_l2(bp.grad, br.grad) < 1e-2
+    assert rel_l2(ap.grad, ar.grad) < 1e-2
+    assert rel_l2(rp.grad, rr.grad) < 1e-2
+
+
+def test_conv_backward_two_segments_shared_and_split_weights(F):
+    """conv2 (3x3) + 1x1 skip over a second source accumulate into one output; a virtual concat slices one weight."""
+    torch.manual_seed(1)
+    dev = "cuda"
+    b, hw = 2, 16
+    h = nhwc(torch.randn(b, 128, hw, hw, device=dev)).requires_grad_(True)
+    x = nhwc(torch.randn(b, 256, hw, hw, device=dev)).requires_grad_(True)
+    w2 = (torch.randn(128, 128, 3, 3, device=dev) * 0.05).requires_grad_(True)
+    ws = (torch.randn(128, 256, device=dev) * 0.05).requires_grad_(True)
+    gy = nhwc(torch.randn(b, 128, hw, hw, device=dev))
+    y = F.conv([h, x], [(w2, 0, 128), (ws, 0, 256)])
+    y.backward(gy)
+    hr, xr = h.detach().float().requires_grad_(True), x.detach().float().requires_grad_(True)
+    w2r = w2.detach().to(torch.bfloat16).float().requires_grad_(True)
+    wsr = ws.detach().to(torch.bfloat16).float().requires_grad_(True)
+    yr = TF.conv2d(hr, w2r, padding=1) + TF.conv2d(xr, wsr[:, :, None, None])
+    yr.backward(gy.float())
+    for got, ref in [(y, yr), (h.grad, hr.grad), (x.grad, xr.grad), (w2.grad, w2r.grad), (ws.grad, wsr.grad)]:
+        assert rel_l2(got, ref) < 1e-2
+    # virtual concat: two sources slice ONE weight
+    a = nhwc(torch.randn(b, 128, hw, hw, device=dev)).requires_grad_(True)
+    c = nhwc(torch.randn(b, 64, hw, hw, device=dev)).requires_grad_(True)
+    w = (torch.randn(128, 192, 3, 3, device=dev) * 0.05).requires_grad_(True)
+    y = F.conv([a, c], [(w, 0, 128), (w, 128, 64)])
+    y.backward(gy)
+    ar, cr = a.detach().float().requires_grad_(True), c.detach().float().requires_grad_(True)
+    wr = w.detach().to(torch.bfloat16).float().requires_grad_(True)
+    yr = TF.conv2d(torch.cat([ar, cr], 1), wr, padding=1)
+    yr.backward(gy.float())
+    for got, ref in [(y, yr), (a.grad, ar.grad), (c.grad, cr.grad), (w.grad, wr.grad)]:
+        assert rel_l2(got, ref) < 1e-2
+
+
+@pytest.mark.parametrize("c,groups,hw,b,silu,ss", [
+    (128, 32, 32, 2, True, False), (256, 32, 16, 3, True, True), (512, 32, 8, 2, False, False),
+    (64, 8, 16, 2, True, True), (384, 32, 16, 2, True, False),
+])
+def test_group_norm_backward(F, c, groups, hw, b, silu, ss):
+    torch.manual_seed(2)
+    dev = "cuda"
+    x = nhwc(torch.randn(b, c, hw, hw, device=dev) * 1.5 + 0.3).requires_grad_(True)
+    gamma = (torch.rand(c, device=dev) + 0.5).requires_grad_(True)
+    beta = (torch.randn(c, device=dev) * 0.2).requires_grad_(True)
+    sst = (torch.randn(b, 2 * c, device=dev) * 0.3).requires_grad_(True) if ss else None
+    gy = nhwc(torch.randn(b, c, hw, hw, device=dev))
+    y = F.group_norm(x, gamma, beta, groups=groups, eps=1e-5, silu=silu, scale_shift=sst)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    sr = sst.detach().clone().requires_grad_(True) if ss else None
+    yr = TF.group_norm(xr, groups, gr, br, 1e-5)
+    if ss:
+        yr = yr * (1 + sr[:, :c, None, None]) + sr[:, c:, None, None]
+    if silu:
+        yr = TF.silu(yr)
+    yr.backward(gy.float())
+    assert rel_l2(y, yr) < 1e-2
+    assert rel_l2(x.grad, xr.grad) < 1e-2
+    assert rel_l2(gamma.grad, gr.grad) < 1e-2
+    assert rel_l2(beta.grad, br.grad) < 1e-2
+    if ss:
+        assert rel_l2(sst.grad, sr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("c,heads,hw,b", [(512, 64, 16, 2), (512, 64, 8, 3), (128, 8, 16, 2), (256, 4, 8, 2)])
+def test_attention_backward(F, c, heads, hw, b):
+    torch.manual_seed(3)
+    dev = "cuda"
+    qkv = nhwc(torch.randn(b, 3 * c, hw, hw, device=dev)).requires_grad_(True)
+    gy = nhwc(torch.randn(b, c, hw, hw, device=dev))
+    y = F.attention_qkv(qkv, heads)
+    y.backward(gy)
+    t, hd = hw * hw, c // heads
+    qr = qkv.detach().float().requires_grad_(True)
+    flat = qr.permute(0, 2, 3, 1).reshape(b, t, 3, heads, hd)
+    q, k, v = [flat[:, :, i].transpose(1, 2) for i in range(3)]
+    o = TF.scaled_dot_product_attention(q, k, v)                      # [b][heads][t][hd]
+    yr = o.transpose(1, 2).reshape(b, hw, hw, c).permute(0, 3, 1, 2)
+    yr.backward(gy.float())
+    assert rel_l2(y, yr) < 1e-2
+    assert rel_l2(qkv.grad, qr.grad) < 2e-2
+
+
+def test_linear_backward(F):
+    torch.manual_seed(4)
+    dev = "cuda"
+    for silu_in in (False, True):
+        x = torch.randn(8, 128, device=dev, requires_grad=True)
+        w = (torch.randn(512, 128, device=dev) * 0.1).requires_grad_(True)
+        bias = torch.randn(512, device=dev, requires_grad=True)
+        gy = torch.randn(8, 512, device=dev)
+        y = F.linear(x, w, bias, silu_in=silu_in)
+        y.backward(gy)
+        xr, wr, br = [z.detach().clone().requires_grad_(True) for z in (x, w, bias)]
+        yr = TF.linear(TF.silu(xr) if silu_in else xr, wr, br)
+        yr.backward(gy)
+        for got, ref in [(y, yr), (x.grad, xr.grad), (w.grad, wr.grad), (bias.grad, br.grad)]:
+            assert rel_l2(got, ref) < 1e-5
+
+
+def test_stem_and_head_backward(F):
+    torch.manual_seed(5)
+    dev = "cuda"
+    b, hw = 2, 64
+    x0, x1 = torch.randn(b, 1, hw, hw, device=dev), torch.randn(b, 1, hw, hw, device=dev)
+    w = (torch.randn(128, 2, 3, 3, device=dev) * 0.2).requires_grad_(True)
+    bias = torch.randn(128, device=dev, requires_grad=True)
+    gy = nhwc(torch.randn(b, 128, hw, hw, device=dev))
+    y = F.conv_stem(x0, x1, w, bias, in_scale=2.0, in_shift=-1.0)
+    y.backward(gy)
+    wr, br = w.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    yr = TF.conv2d(2 * torch.cat([x0, x1], 1) - 1, wr, br, padding=1)
+    yr.backward(gy.float())
+    assert rel_l2(y, yr) < 1e-2 and rel_l2(w.grad, wr.grad) < 1e-3 and rel_l2(bias.grad, br.grad) < 1e-3
+    # head: bf16 NHWC -> fp32 NCHW, one output channel
+    a = nhwc(torch.randn(b, 128, hw, hw, device=dev)).requires_grad_(True)
+    wh = (torch.randn(1, 128, 3, 3, device=dev) * 0.1).requires_grad_(True)
+    bh = torch.randn(1, device=dev, requires_grad=True)
+    g = torch.randn(b, 1, hw, hw, device=dev)
+    y = F.conv_head(a, wh, bh)
+    y.backward(g)
+    ar = a.detach().float().requires_grad_(True)
+    whr, bhr = wh.detach().clone().requires_grad_(True), bh.detach().clone().requires_grad_(True)
+    yr = TF.conv2d(ar, whr, bhr, padding=1)
+    yr.backward(g)
+    assert rel_l2(y, yr) < 1e-2
+    assert rel_l2(a.grad, ar.grad) < 1e-2 and rel_l2(wh.grad, whr.grad) < 1e-3 and rel_l2(bh.grad, bhr.grad) < 1e-4
+
+
+def test_upsample_backward_and_mse(F):
+    torch.manual_seed(6)
+    dev = "cuda"
+    x = nhwc(torch.randn(2, 64, 8, 8, device=dev)).requires_grad_(True)
+    gy = nhwc(torch.randn(2, 64, 16, 16, device=dev))
+    F.upsample_nearest2x(x).backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    TF.interpolate(xr, scale_factor=2, mode="nearest").backward(gy.float())
+    assert rel_l2(x.grad, xr.grad) < 1e-2
+    pred = torch.randn(4, 1, 32, 32, device=dev, requires_grad=True)
+    noise, clean = torch.randn_like(pred), torch.randn_like(pred)
+    loss = F.mse_loss(pred, noise, clean)
+    (loss * 3.0).backward()
+    pr = pred.detach().clone().requires_grad_(True)
+    lr = TF.mse_loss(pr, noise - clean)
+    (lr * 3.0).backward()
+    assert abs(loss.item() - lr.item()) < 1e-6 * abs(lr.item()) + 1e-7
+    assert rel_l2(pred.grad, pr.grad) < 1e-6
+
+
+def test_fused_adamw_matches_torch():
+    from fmdm_b200.training import FusedAdamW
+
+    torch.manual_seed(7)
+    dev = "cuda"
+    shapes = [(128, 2, 3, 3), (128,), (512, 128), (7,), (256, 256, 3, 3)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    pr = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt = FusedAdamW(ps, lr=1e-3, weight_decay=0.01)
+    ref = torch.optim.AdamW(pr, lr=1e-3, weight_decay=0.01)
+    for step in range(5):
+        opt.zero_grad()
+        ref.zero_grad(set_to_none=True)
+        for p, r in zip(ps, pr):
+            g = torch.randn_like(p)
+            p.grad.add_(g)
+            r.grad = g.clone()
+        opt.step()
+        ref.step()
+    for p, r in zip(ps, pr):
+        assert torch.allclose(p, r, rtol=2e-6, atol=2e-7), (p - r).abs().max().item()
