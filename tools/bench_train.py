@@ -1,0 +1,67 @@
+"""BASELINE config 5: LDCT 256x256 flow-matching training step (fwd + bwd + AdamW, gradient all-reduce when launched
+under torchrun), batch 16 per GPU, synthetic data.  Prints one JSON line (samples/s over all ranks)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import LDCT_UNET  # noqa: E402
+
+
+def main():
+    import torch.distributed as dist
+
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+    from fmdm_b200.training import FlowMatchingTrainer
+
+    steps = int(os.environ.get("STEPS", 5))
+    warmup = int(os.environ.get("WARMUP", 3))
+    B = int(os.environ.get("BATCH", 16))
+    hw = int(os.environ.get("HW", 256))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.manual_seed(0)
+    model = DiffusionUNetFactory().build(LDCT_UNET, "concatenate", 1).to(dev).train()
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    tr = FlowMatchingTrainer(model, lr=1e-4)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    clean = torch.rand(B, 1, hw, hw, device=dev, generator=g)
+    ldct = torch.rand(B, 1, hw, hw, device=dev, generator=g)
+    losses = []
+    for _ in range(warmup):
+        losses.append(tr.step(clean, ldct))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses.append(tr.step(clean, ldct))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ls = [float(x) for x in losses]
+        print(json.dumps({"metric": "training_samples_per_s", "value": round(B * world / (ms.item() / 1e3), 2),
+                          "unit": "samples/s", "n_gpus": world, "ms_per_step": round(ms.item(), 2), "steps": steps,
+                          "warmup": warmup, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"LDCT {hw}x{hw} flow-matching training step, batch {B}/GPU",
+                                     "optimizer": "AdamW (flat, fused)", "loss_first": ls[0], "loss_last": ls[-1]},
+                          "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
