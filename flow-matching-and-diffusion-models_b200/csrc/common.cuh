@@ -17,6 +17,10 @@ int check_cuda(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 int ensure_device();  // 0 if an sm_100 device is current, else FM_ERR_NO_DEVICE
 int sm_count();
+// tcgen05 conv wgrad (conv_wgrad_tc.cuh, compiled in conv_igemm.cu); FM_ERR_UNSUPPORTED = geometry not covered
+int wgrad_tc_launch(const void* dy, const void* x, float* workspace, int64_t workspace_elems, int B, int H, int W,
+                    int Cin, int Cout, int ksize, int stride, int* splits_out, cudaStream_t st);
+int wgrad_tc_max_splits(int B, int Ho, int Wo, int Cin, int Cout, int ksize);
 
 #define FM_REQUIRE(cond, ...)          \
   do {                                 \

@@ -651,6 +651,8 @@ static int plan_conv(const fm_conv_params* p, ConvPlan* pl) {
   return 0;
 }
 
+#include "conv_wgrad_tc.cuh"
+
 }  // namespace fm
 
 extern "C" int fm_conv_stats_rows(const fm_conv_params* p, int32_t* rows_per_image) {

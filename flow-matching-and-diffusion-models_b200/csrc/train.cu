@@ -10,6 +10,8 @@
 //                 sum-pool that is the backward of the nearest-2x upsample.
 //   GroupNorm+SiLU backward, attention backward (fp32 CUDA cores, one CTA per (sample, head)), stem/head conv
 //   backward, column sums (bias / time-embedding gradients), fused MSE loss + gradient, flat AdamW.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fm {
@@ -332,39 +334,72 @@ __device__ __forceinline__ float silu_grad_f(float n) {
 // coefficient table per (sample, channel), 8 floats: a, b (forward affine n = a*x + b), mean, rstd, A, m1, m2, pad
 constexpr int kGnTab = 8;
 
+// SiLU'(n) with one special-function op: sigma(n) = 0.5 + 0.5 * tanh(n / 2)
+__device__ __forceinline__ float silu_grad_fast(float n) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * n));
+  const float s = fmaf(0.5f, t, 0.5f);
+  return s * fmaf(n, 1.f - s, 1.f);
+}
+
+// Thread layout of the two streaming passes: a block covers all C channels of a run of rows; thread = (8-channel
+// group c8 = tid % C8, row lane = tid / C8), so its per-channel coefficients stay in registers for the whole run and
+// every global access is a 16-byte vector.
 // stage 1: S1[b][c] = sum_p dn, S2[b][c] = sum_p dn * xhat   (partials per row block)
-__global__ void __launch_bounds__(512) gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              const __nv_bfloat16* __restrict__ da,
+__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ da,
                                                               const float* __restrict__ tab, float* __restrict__ part,
-                                                              int64_t HW, int C, int rows_per_blk, int silu) {
+                                                              int64_t HW, int C8, int lanes, int rows_per_blk,
+                                                              int silu) {
+  extern __shared__ float red[];  // [lanes][C8*16]
   const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
-  const int64_t r0 = (int64_t)blk * rows_per_blk;
-  const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
-  for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
-    const float* t0 = tab + ((int64_t)b * C + cp * 2) * kGnTab;
-    const float a0 = t0[0], b0 = t0[1], mu0 = t0[2], rs0 = t0[3];
-    const float a1 = t0[kGnTab + 0], b1 = t0[kGnTab + 1], mu1 = t0[kGnTab + 2], rs1 = t0[kGnTab + 3];
-    const uint32_t* xs = reinterpret_cast<const uint32_t*>(x + ((int64_t)b * HW) * C) + cp;
-    const uint32_t* ds = reinterpret_cast<const uint32_t*>(da + ((int64_t)b * HW) * C) + cp;
-    float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const float2 xv = unpack_bf16x2(xs[r * (C / 2)]);
-      const float2 dv = unpack_bf16x2(ds[r * (C / 2)]);
-      float d0 = dv.x, d1 = dv.y;
-      if (silu) {
-        d0 *= silu_grad_f(fmaf(a0, xv.x, b0));
-        d1 *= silu_grad_f(fmaf(a1, xv.y, b1));
-      }
-      s1a += d0;
-      s2a = fmaf(d0, (xv.x - mu0) * rs0, s2a);
-      s1b += d1;
-      s2b = fmaf(d1, (xv.y - mu1) * rs1, s2b);
+  const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
+  const int C = C8 * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  if (lane < lanes) {
+    float ca[8], cb[8], mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 t0 = *reinterpret_cast<const float4*>(tab + ((int64_t)b * C + c8 * 8 + k) * kGnTab);
+      ca[k] = t0.x, cb[k] = t0.y, mu[k] = t0.z, rs[k] = t0.w;
     }
-    float* dst = part + (((int64_t)b * nblk + blk) * 2) * C + cp * 2;
-    dst[0] = s1a;
-    dst[1] = s1b;
-    dst[C] = s2a;
-    dst[C + 1] = s2b;
+    const int64_t r0 = (int64_t)blk * rows_per_blk;
+    const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
+    const uint4* xs = x + ((int64_t)b * HW) * C8 + c8;
+    const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
+#pragma unroll 2
+    for (int64_t r = r0 + lane; r < r1; r += lanes) {
+      const uint4 xv = __ldg(xs + r * C8), dv = __ldg(ds + r * C8);
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
+        float d0 = df.x, d1 = df.y;
+        if (silu) {
+          d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
+          d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
+        }
+        s1[2 * k] += d0;
+        s2[2 * k] = fmaf(d0, (xf.x - mu[2 * k]) * rs[2 * k], s2[2 * k]);
+        s1[2 * k + 1] += d1;
+        s2[2 * k + 1] = fmaf(d1, (xf.y - mu[2 * k + 1]) * rs[2 * k + 1], s2[2 * k + 1]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[(lane * C8 + c8) * 16 + k] = s1[k];
+      red[(lane * C8 + c8) * 16 + 8 + k] = s2[k];
+    }
+  }
+  __syncthreads();
+  // fixed-order sum over the row lanes; thread -> (c8, j in 0..15)
+  for (int idx = threadIdx.x; idx < C8 * 16; idx += blockDim.x) {
+    const int cc = idx >> 4, j = idx & 15;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[(l * C8 + cc) * 16 + j];
+    float* dst = part + (((int64_t)b * nblk + blk) * 2) * C;
+    dst[(j >> 3) * C + cc * 8 + (j & 7)] = acc;
   }
 }
 
@@ -439,31 +474,47 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
   }
 }
 
-// stage 3: dx = A*dn - m1 - m2*xhat
+// stage 3: dx = A*dn - m1 - m2*xhat = A*dn + P + Q*x  (P = m2*mean*rstd - m1, Q = -m2*rstd)
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ da,
                                                             const float* __restrict__ tab, uint4* __restrict__ dx,
-                                                            int64_t HW, int C8, int silu, int64_t total) {
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % C8);
-    const int64_t row = idx / C8;
-    const int b = (int)(row / HW);
-    const float4* t = reinterpret_cast<const float4*>(tab + ((int64_t)b * C8 * 8 + c8 * 8) * kGnTab);
-    const uint4 xv = x[idx], dv = da[idx];
-    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-    float o[8];
+                                                            int64_t HW, int C8, int lanes, int rows_per_blk,
+                                                            int silu) {
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
+  if (lane >= lanes) return;
+  const int C = C8 * 8;
+  float ca[8], cb[8], cA[8], cP[8], cQ[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 t0 = __ldg(t + 2 * k), t1 = __ldg(t + 2 * k + 1);  // (a, b, mean, rstd), (A, m1, m2, -)
-      const float2 xf = unpack_bf16x2(xw[k >> 1]), df = unpack_bf16x2(dw[k >> 1]);
-      const float xx = (k & 1) ? xf.y : xf.x;
-      float d = (k & 1) ? df.y : df.x;
-      if (silu) d *= silu_grad_f(fmaf(t0.x, xx, t0.y));
-      const float xh = (xx - t0.z) * t0.w;
-      o[k] = fmaf(t1.x, d, -t1.y) - t1.z * xh;
+  for (int k = 0; k < 8; ++k) {
+    const float4* t = reinterpret_cast<const float4*>(tab + ((int64_t)b * C + c8 * 8 + k) * kGnTab);
+    const float4 t0 = t[0], t1 = t[1];  // (a, b, mean, rstd), (A, m1, m2, -)
+    ca[k] = t0.x, cb[k] = t0.y, cA[k] = t1.x;
+    cP[k] = fmaf(t1.z, t0.z * t0.w, -t1.y);
+    cQ[k] = -t1.z * t0.w;
+  }
+  const int64_t r0 = (int64_t)blk * rows_per_blk;
+  const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
+  const uint4* xs = x + ((int64_t)b * HW) * C8 + c8;
+  const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
+  uint4* os = dx + ((int64_t)b * HW) * C8 + c8;
+#pragma unroll 2
+  for (int64_t r = r0 + lane; r < r1; r += lanes) {
+    const uint4 xv = __ldg(xs + r * C8), dv = __ldg(ds + r * C8);
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
+      float d0 = df.x, d1 = df.y;
+      if (silu) {
+        d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
+        d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
+      }
+      const float o0 = fmaf(cA[2 * k], d0, fmaf(cQ[2 * k], xf.x, cP[2 * k]));
+      const float o1 = fmaf(cA[2 * k + 1], d1, fmaf(cQ[2 * k + 1], xf.y, cP[2 * k + 1]));
+      ow[k] = pack_bf16x2(o0, o1);
     }
-    dx[idx] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                         pack_bf16x2(o[6], o[7]));
+    os[r * C8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
@@ -806,7 +857,10 @@ extern "C" int64_t fm_conv_wgrad_workspace_elems(int32_t B, int32_t Ho, int32_t 
                                                  int32_t ksize) {
   int splits, cps, chunks, base;
   if (ksize != 1 && ksize != 3) return 0;
+  if (ensure_device()) return 0;
   if (wgrad_plan(B, Ho, Wo, Cin, Cout, ksize, &splits, &cps, &chunks, &base)) return 0;
+  const int tc = wgrad_tc_max_splits(B, Ho, Wo, Cin, Cout, ksize);
+  if (tc > splits) splits = tc;
   return (int64_t)splits * ksize * ksize * Cout * Cin;
 }
 
@@ -820,6 +874,21 @@ extern "C" int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, floa
   FM_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv_wgrad: channel counts must be multiples of 8");
   FM_REQUIRE(c_begin >= 0 && c_begin + Cin <= cin_total, "conv_wgrad: channel slice out of range");
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = ksize * ksize;
+  const int64_t per = (int64_t)taps * Cout * Cin;
+  static const bool force_mma = getenv("FMDM_WGRAD_MMA") != nullptr;  // A/B switch: the mma.sync kernel everywhere
+  if (!force_mma) {
+    int tc_splits = 0;
+    const int64_t ws_elems = fm_conv_wgrad_workspace_elems(B, Ho, Wo, Cin, Cout, ksize);
+    const int rc = wgrad_tc_launch(dy, x, workspace, ws_elems, B, H, W, Cin, Cout, ksize, stride, &tc_splits, st);
+    if (rc == 0) {
+      wgrad_reduce_kernel<<<ew_grid(per), 256, 0, st>>>(workspace, dw, tc_splits, taps, Cout, Cin, cin_total, c_begin);
+      FM_LAUNCH_CHECK("wgrad_reduce_kernel");
+      return 0;
+    }
+    if (rc != FM_ERR_UNSUPPORTED) return rc;
+  }
   WgradParams p;
   int splits, base;
   if (wgrad_plan(B, Ho, Wo, Cin, Cout, ksize, &splits, &p.chunks_per_split, &p.chunks, &base)) {
@@ -834,7 +903,6 @@ extern "C" int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, floa
   p.total_px = (int64_t)B * Ho * Wo;
   p.n_ci = (Cin + wg::kCi - 1) / wg::kCi;
   p.n_co = (Cout + wg::kCo - 1) / wg::kCo;
-  cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(base, splits);
   if (ksize == 3) {
     constexpr int smem = wg::kStages * wg::stage_bytes(3);
@@ -854,8 +922,6 @@ extern "C" int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, floa
     conv_wgrad_mma_kernel<1><<<grid, 256, smem, st>>>(p);
   }
   FM_LAUNCH_CHECK("conv_wgrad_mma_kernel");
-  const int taps = ksize * ksize;
-  const int64_t per = (int64_t)taps * Cout * Cin;
   wgrad_reduce_kernel<<<ew_grid(per), 256, 0, st>>>(workspace, dw, splits, taps, Cout, Cin, cin_total, c_begin);
   FM_LAUNCH_CHECK("wgrad_reduce_kernel");
   return 0;
@@ -934,8 +1000,7 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const floa
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x && dout && stats && gamma && beta && workspace && dx && dgamma_dbeta, "groupnorm_bwd: null pointer");
   FM_REQUIRE(C % 8 == 0 && groups > 0 && C % groups == 0, "groupnorm_bwd: C must be a multiple of 8 and of groups");
-  FM_REQUIRE(C <= 4096, "groupnorm_bwd: C too large");
-  FM_REQUIRE((scale_shift == nullptr) == (dscale_shift == nullptr), "groupnorm_bwd: scale_shift / dscale_shift mismatch");
+    FM_REQUIRE((scale_shift == nullptr) == (dscale_shift == nullptr), "groupnorm_bwd: scale_shift / dscale_shift mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = gn_bwd_blocks(HW, B);
   const int rows = (int)((HW + nblk - 1) / nblk);
@@ -947,11 +1012,12 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const floa
   if (cthreads > 1024) cthreads = 1024;
   gn_bwd_table_kernel<<<B, cthreads, 0, st>>>(stats, gamma, beta, scale_shift, ss_stride, C, groups, tab);
   FM_LAUNCH_CHECK("gn_bwd_table_kernel");
-  int pthreads = ((C / 2 + 31) / 32) * 32;
-  if (pthreads > 512) pthreads = 512;
-  gn_bwd_partial_kernel<<<dim3(nblk, B), pthreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                           reinterpret_cast<const __nv_bfloat16*>(dout), tab, part, HW,
-                                                           C, rows, silu);
+  const int C8 = C / 8;
+  const int lanes = C8 >= 256 ? 1 : 256 / C8;
+  const int sthreads = ((C8 * lanes + 31) / 32) * 32;
+  FM_REQUIRE(C8 <= 256, "groupnorm_bwd: C must be <= 2048");
+  gn_bwd_partial_kernel<<<dim3(nblk, B), sthreads, (size_t)lanes * C8 * 16 * sizeof(float), st>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dout), tab, part, HW, C8, lanes, rows, silu);
   FM_LAUNCH_CHECK("gn_bwd_partial_kernel");
   if (int e = launch_reduce(part, S, B, nblk, 2LL * C, st)) return e;
   const float inv_n = 1.f / ((float)HW * (float)(C / groups));
@@ -960,10 +1026,9 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const floa
   FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
   /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
   if (int e = launch_reduce(dgb, dgamma_dbeta, 1, B, 2LL * C, st)) return e;
-  const int64_t total = (int64_t)B * HW * (C / 8);
-  gn_bwd_apply_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const uint4*>(x),
-                                                     reinterpret_cast<const uint4*>(dout), tab,
-                                                     reinterpret_cast<uint4*>(dx), HW, C / 8, silu, total);
+  gn_bwd_apply_kernel<<<dim3(nblk, B), sthreads, 0, st>>>(reinterpret_cast<const uint4*>(x),
+                                                         reinterpret_cast<const uint4*>(dout), tab,
+                                                         reinterpret_cast<uint4*>(dx), HW, C8, lanes, rows, silu);
   FM_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return 0;
 }
