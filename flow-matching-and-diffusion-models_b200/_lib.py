@@ -97,6 +97,7 @@ SIGNATURES = {
     "fm_counter_add": (C.c_int, [_vp, _i32, _vp]),
     "fm_clamp_f32": (C.c_int, [_vp, _vp, _f32, _f32, _i64, _vp]),
     # training step (backward / loss / optimiser)
+    "fm_weight_prepack_dgrad_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_conv_wgrad_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "fm_conv_wgrad_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_colsum_workspace_elems": (C.c_int64, [_i32, _i64, _i32]),

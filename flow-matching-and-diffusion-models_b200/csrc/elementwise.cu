@@ -207,6 +207,21 @@ __global__ void weight_prepack_kernel(__nv_bfloat16* __restrict__ dst, int64_t d
   dst[(int64_t)co * dst_row_stride + koff + (int64_t)tap * Cseg + c] = __float2bfloat16_rn(v);
 }
 
+// Packed weights of the data-gradient conv of a channel slice: dst[ci][tap' * Cout + co] = w[co][c_begin + ci][taps-1-tap']
+// (input/output channels swapped, taps mirrored), K-major bf16 [Cseg][taps * Cout].
+__global__ void weight_prepack_dgrad_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int Cout,
+                                            int Cin_total, int c_begin, int Cseg, int ks) {
+  const int taps = ks * ks;
+  const int64_t total = (int64_t)Cseg * taps * Cout;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = (int)(i % Cout);
+  const int tap = (int)((i / Cout) % taps);
+  const int ci = (int)(i / ((int64_t)Cout * taps));
+  const float v = src[((int64_t)co * Cin_total + c_begin + ci) * taps + (taps - 1 - tap)];
+  dst[i] = __float2bfloat16_rn(v);
+}
+
 // ---- nearest 2x upsample, NHWC bf16, 16 B per thread -----------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B,
                                                         int H, int W, int C8) {
@@ -367,6 +382,19 @@ extern "C" int fm_weight_prepack_bf16(void* dst, int64_t dst_row_stride, int64_t
   weight_prepack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<__nv_bfloat16*>(dst), dst_row_stride, koff, src_oihw, Cout, Cin_total, c_begin, Cseg, ksize);
   FM_LAUNCH_CHECK("weight_prepack_kernel");
+  return 0;
+}
+
+extern "C" int fm_weight_prepack_dgrad_bf16(void* dst, const float* src_oihw, int32_t Cout, int32_t Cin_total,
+                                            int32_t c_begin, int32_t Cseg, int32_t ksize, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(dst && src_oihw && Cout > 0 && Cseg > 0 && c_begin >= 0 && c_begin + Cseg <= Cin_total,
+             "weight_prepack_dgrad: bad channel range");
+  FM_REQUIRE(ksize == 1 || ksize == 3, "weight_prepack_dgrad: ksize must be 1 or 3");
+  const int64_t total = (int64_t)Cout * ksize * ksize * Cseg;
+  weight_prepack_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(dst), src_oihw, Cout, Cin_total, c_begin, Cseg, ksize);
+  FM_LAUNCH_CHECK("weight_prepack_dgrad_kernel");
   return 0;
 }
 

@@ -1047,8 +1047,13 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
   cudaStream_t st = (cudaStream_t)stream;
 #define FM_ATT_BWD(HD)                                                                                              \
   case HD: {                                                                                                        \
-    if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                (int)smem), "attention_bwd attr")) return e;                        \
+    static size_t attr_smem = 0;                                                                                    \
+    if (smem > attr_smem) {                                                                                         \
+      if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_kernel<HD>,                                         \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),          \
+                             "attention_bwd attr")) return e;                                                       \
+      attr_smem = smem;                                                                                             \
+    }                                                                                                               \
     attention_bwd_kernel<HD><<<B * heads, 256, smem, st>>>(                                                         \
         (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,         \
         (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, T, qs_b, qs_h, \

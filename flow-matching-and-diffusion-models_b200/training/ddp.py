@@ -72,6 +72,15 @@ class BucketedAllReduce:
             h.wait()
         self._handles = []
 
+    def reduce_all(self) -> None:
+        """Non-overlapped form (after a CUDA-graph replay of the backward): every bucket, then wait."""
+        if self.world == 1:
+            return
+        hs = [dist.all_reduce(self.flat.grad[b:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+              for b, e, _ in self.buckets]
+        for h in hs:
+            h.wait()
+
     def remove(self) -> None:
         for h in self._hooks:
             h.remove()

@@ -24,6 +24,14 @@ def _ws(n: int, device, dtype=torch.float32) -> torch.Tensor:
     return torch.empty((max(int(n), 1),), dtype=dtype, device=device)
 
 
+def _rows_f32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D tensor with unit inner stride and 16-byte aligned rows (column slices of a wider matrix pass through)."""
+    t = t.detach()
+    if t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    return t.float().contiguous()
+
+
 def _nhwc(t: torch.Tensor) -> torch.Tensor:
     return ops.to_nhwc_bf16(t)
 
@@ -76,13 +84,16 @@ def sumpool2x2(x: torch.Tensor) -> torch.Tensor:
 
 
 def _dgrad_weight(w: torch.Tensor, c_begin: int, c_count: int) -> ops.PackedConvWeight:
-    """Packed weights of the data-gradient conv: in/out channels swapped, taps mirrored (tiny host-side views)."""
-    ws = w.detach()[:, c_begin:c_begin + c_count]
-    if ws.dim() == 2:
-        wt = ws.t().contiguous()
-    else:
-        wt = ws.flip(2, 3).transpose(0, 1).contiguous()
-    return ops.pack_conv_weight([(wt, 0, wt.shape[1])])
+    """Packed weights of the data-gradient conv: in/out channels swapped, taps mirrored (one launch)."""
+    w32 = w.detach()
+    if w32.dtype != torch.float32 or not w32.is_contiguous():
+        w32 = w32.float().contiguous()
+    cout, cin_total = w32.shape[0], w32.shape[1]
+    ks = 1 if w32.dim() == 2 else int(w32.shape[-1])
+    mat = torch.empty((c_count, ks * ks * cout), dtype=BF16, device=w32.device)
+    _lib.check(_lib.lib().fm_weight_prepack_dgrad_bf16(mat.data_ptr(), w32.data_ptr(), cout, cin_total, c_begin,
+                                                       c_count, ks, _stream()), "weight_prepack_dgrad")
+    return ops.PackedConvWeight(mat, [cout], [ks], c_count)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -101,7 +112,7 @@ class _ConvFn(Function):
         if residual is not None:
             residual = _nhwc(residual)
         out = ops.conv2d(srcs, pw, stride=stride, bias=None if bias is None else bias.detach().float().contiguous(),
-                         addvec=None if addvec is None else addvec.detach().float().contiguous(), residual=residual)
+                         addvec=None if addvec is None else _rows_f32(addvec), residual=residual)
         ctx.meta = meta
         ctx.flags = (bias is not None, addvec is not None, residual is not None)
         ctx.save_for_backward(*srcs, *weights)
@@ -179,7 +190,7 @@ class _GroupNormFn(Function):
         b, c, h, w = x.shape
         g32 = gamma.detach().float().contiguous()
         b32 = beta.detach().float().contiguous()
-        ss = None if scale_shift is None else scale_shift.detach().float().contiguous()
+        ss = None if scale_shift is None else _rows_f32(scale_shift)
         st = _stream()
         n = int(lib.fm_groupnorm_workspace_elems(b, h * w, c, groups))
         if n <= 0:
@@ -303,6 +314,32 @@ class _LinearFn(Function):
 
 def linear(x, weight, bias=None, *, silu_in: bool = False) -> torch.Tensor:
     return _LinearFn.apply(x, weight, bias, bool(silu_in))
+
+
+class _SplitColsFn(Function):
+    """Column slices of a [B][sum(sizes)] matrix as views; the backward gathers the slice gradients with one concat
+    (autograd's own slice backward would pad and add one full-width matrix per slice)."""
+
+    @staticmethod
+    def forward(ctx, x, sizes):
+        ctx.sizes = sizes
+        ctx.rows = x.shape[0]
+        outs, off = [], 0
+        for n in sizes:
+            outs.append(x[:, off:off + n])
+            off += n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ref = next(g for g in grads if g is not None)
+        parts = [g if g is not None else torch.zeros((ctx.rows, n), dtype=ref.dtype, device=ref.device)
+                 for g, n in zip(grads, ctx.sizes)]
+        return torch.cat(parts, 1), None
+
+
+def split_cols(x: torch.Tensor, sizes: Sequence[int]):
+    return _SplitColsFn.apply(x, tuple(int(n) for n in sizes))
 
 
 # --------------------------------------------------------------------------------------------------------------

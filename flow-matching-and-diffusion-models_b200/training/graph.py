@@ -29,8 +29,43 @@ def _gn(norm: nn.GroupNorm, x, *, silu: bool, scale_shift=None):
                         scale_shift=scale_shift)
 
 
-def resblock(blk, x: torch.Tensor, emb: torch.Tensor) -> torch.Tensor:
-    """`residual.py:92-121` (GroupNorm / SiLU variant)."""
+class EmbProjections:
+    """Every ResBlock's `emb_layers` projection of the time embedding in ONE launch (`residual.py:99-108` runs one
+    Linear per block on the same input): the weights are concatenated per step, the result is split into per-block
+    column views, and the backward is one dX / dW / db GEMM over the concatenation."""
+
+    def __init__(self, model, emb: torch.Tensor):
+        from ..nn.blocks.residual import ResBlockND
+
+        blocks = [m for m in model.modules() if isinstance(m, ResBlockND) and m.uses_embedding
+                  and (m.use_scale_shift_norm or m.add_embedding_to_hidden)]
+        self.slices = {}
+        groups = {}
+        for blk in blocks:
+            groups.setdefault(bool(blk.emb_activation_before_proj), []).append(blk)
+        for silu_in, blks in groups.items():
+            sizes = [(b.emb_layers.weight.shape[0] + 3) // 4 * 4 for b in blks]  # 16-byte aligned column slices
+            ws, bs = [], []
+            for b, n in zip(blks, sizes):
+                w, bias = b.emb_layers.weight, b.emb_layers.bias
+                pad = n - w.shape[0]
+                if pad:
+                    w = torch.cat([w, w.new_zeros(pad, w.shape[1])], 0)
+                    bias = torch.cat([bias, bias.new_zeros(pad)], 0)
+                ws.append(w)
+                bs.append(bias)
+            e_all = F.linear(emb, torch.cat(ws, 0), torch.cat(bs, 0), silu_in=silu_in)
+            for b, e in zip(blks, F.split_cols(e_all, sizes)):
+                self.slices[id(b)] = e[:, :b.emb_layers.weight.shape[0]]
+
+        self.raw = emb
+
+    def get(self, blk):
+        return self.slices.get(id(blk))
+
+
+def resblock(blk, x: torch.Tensor, emb) -> torch.Tensor:
+    """`residual.py:92-121` (GroupNorm / SiLU variant).  `emb`: the time embedding or an `EmbProjections`."""
     if not (blk.spatial_dims == 2 and blk.norm_type == "gn" and blk.act_name in ("silu", "swish")) \
             or blk.dropout > 0:
         out_of_scope(f"training ResBlockND(norm={blk.norm_type}, act={blk.act_name}, dropout={blk.dropout})")
@@ -41,7 +76,10 @@ def resblock(blk, x: torch.Tensor, emb: torch.Tensor) -> torch.Tensor:
     if blk.uses_embedding:
         if emb is None:
             raise ValueError("ResBlockND expects `emb` when emb_channels is set.")
-        e = F.linear(emb, blk.emb_layers.weight, blk.emb_layers.bias, silu_in=blk.emb_activation_before_proj)
+        e = emb.get(blk) if isinstance(emb, EmbProjections) else None
+        if e is None:
+            raw = emb.raw if isinstance(emb, EmbProjections) else emb
+            e = F.linear(raw, blk.emb_layers.weight, blk.emb_layers.bias, silu_in=blk.emb_activation_before_proj)
         if blk.use_scale_shift_norm:
             scale_shift = e
         elif blk.add_embedding_to_hidden:
@@ -102,6 +140,7 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
     te = model.time_embedding
     emb = F.linear(feats, te.linear_1.weight, te.linear_1.bias)
     emb = F.linear(emb, te.linear_2.weight, te.linear_2.bias, silu_in=True)  # SiLU between the two layers
+    emb = EmbProjections(model, emb)
 
     scale, shift = (2.0, -1.0) if model.center_input_sample else (1.0, 0.0)
     cin = x.shape[1] + (context.shape[1] if context is not None else 0)

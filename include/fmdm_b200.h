@@ -223,6 +223,10 @@ int fm_clamp_f32(float* y, const float* x, float lo, float hi, int64_t n, fm_str
  * SDPA / F.linear / F.mse_loss backward, torch.optim.AdamW.step).  All reductions are two-stage with a fixed
  * summation order (deterministic, no atomics).
  * ---------------------------------------------------------------------------------------------------------- */
+/* K-major bf16 weights of the data-gradient conv of the channel slice [c_begin, c_begin+Cseg) of an OIHW fp32
+ * weight: dst [Cseg][k*k*Cout], in/out channels swapped and taps mirrored (dX = conv(dY, dst) for stride 1) */
+int fm_weight_prepack_dgrad_bf16(void* dst, const float* src_oihw, int32_t Cout, int32_t Cin_total, int32_t c_begin,
+                                 int32_t Cseg, int32_t ksize, fm_stream_t stream);
 /* conv wgrad: dw[co][c_begin+ci][kh][kw] = sum_{b,yo,xo} dy[b][yo][xo][co] * x[b][yo*stride+kh-pad][xo*stride+kw-pad][ci]
  * dy bf16 NHWC [B][Ho][Wo][Cout], x bf16 NHWC [B][H][W][Cin], dw fp32 OIHW [Cout][cin_total][k][k] (the slice
  * [c_begin, c_begin+Cin) is written).  ksize 1 or 3 (pad = ksize/2), stride 1 or 2.
