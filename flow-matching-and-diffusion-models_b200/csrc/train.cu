@@ -346,7 +346,8 @@ __device__ __forceinline__ float silu_grad_fast(float n) {
 // group c8 = tid % C8, row lane = tid / C8), so its per-channel coefficients stay in registers for the whole run and
 // every global access is a 16-byte vector.
 // stage 1: S1[b][c] = sum_p dn, S2[b][c] = sum_p dn * xhat   (partials per row block)
-__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ da,
+__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __restrict__ x0, int C0_8,
+                                                              const uint4* __restrict__ x1, const uint4* __restrict__ da,
                                                               const float* __restrict__ tab, float* __restrict__ part,
                                                               int64_t HW, int C8, int lanes, int rows_per_blk,
                                                               int silu) {
@@ -366,11 +367,13 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __rest
     }
     const int64_t r0 = (int64_t)blk * rows_per_blk;
     const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
-    const uint4* xs = x + ((int64_t)b * HW) * C8 + c8;
+    // the input is the virtual channel concat of (x0 [C0], x1 [C - C0]); this thread's 8 channels lie in one of them
+    const int xC8 = c8 < C0_8 ? C0_8 : C8 - C0_8;
+    const uint4* xs = (c8 < C0_8 ? x0 + c8 : x1 + (c8 - C0_8)) + ((int64_t)b * HW) * xC8;
     const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
 #pragma unroll 2
     for (int64_t r = r0 + lane; r < r1; r += lanes) {
-      const uint4 xv = __ldg(xs + r * C8), dv = __ldg(ds + r * C8);
+      const uint4 xv = __ldg(xs + r * xC8), dv = __ldg(ds + r * C8);
       const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -475,10 +478,11 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
 }
 
 // stage 3: dx = A*dn - m1 - m2*xhat = A*dn + P + Q*x  (P = m2*mean*rstd - m1, Q = -m2*rstd)
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ da,
-                                                            const float* __restrict__ tab, uint4* __restrict__ dx,
-                                                            int64_t HW, int C8, int lanes, int rows_per_blk,
-                                                            int silu) {
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x0, int C0_8,
+                                                            const uint4* __restrict__ x1, const uint4* __restrict__ da,
+                                                            const float* __restrict__ tab, uint4* __restrict__ dx0,
+                                                            uint4* __restrict__ dx1, int64_t HW, int C8, int lanes,
+                                                            int rows_per_blk, int silu) {
   const int b = blockIdx.y, blk = blockIdx.x;
   const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
   if (lane >= lanes) return;
@@ -494,12 +498,14 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
   }
   const int64_t r0 = (int64_t)blk * rows_per_blk;
   const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
-  const uint4* xs = x + ((int64_t)b * HW) * C8 + c8;
+  const int xC8 = c8 < C0_8 ? C0_8 : C8 - C0_8;
+  const int64_t xoff = ((int64_t)b * HW) * xC8 + (c8 < C0_8 ? c8 : c8 - C0_8);
+  const uint4* xs = (c8 < C0_8 ? x0 : x1) + xoff;
   const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
-  uint4* os = dx + ((int64_t)b * HW) * C8 + c8;
+  uint4* os = (c8 < C0_8 ? dx0 : dx1) + xoff;
 #pragma unroll 2
   for (int64_t r = r0 + lane; r < r1; r += lanes) {
-    const uint4 xv = __ldg(xs + r * C8), dv = __ldg(ds + r * C8);
+    const uint4 xv = __ldg(xs + r * xC8), dv = __ldg(ds + r * C8);
     const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
     uint32_t ow[4];
 #pragma unroll
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
       const float o1 = fmaf(cA[2 * k + 1], d1, fmaf(cQ[2 * k + 1], xf.y, cP[2 * k + 1]));
       ow[k] = pack_bf16x2(o0, o1);
     }
-    os[r * C8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    os[r * xC8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
@@ -993,13 +999,17 @@ extern "C" int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32
   return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 4LL * B * C;
 }
 
-extern "C" int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const float* stats, const float* gamma,
-                                     const float* beta, const float* scale_shift, int64_t ss_stride, int32_t silu,
-                                     int32_t B, int64_t HW, int32_t C, int32_t groups, float* workspace, void* dx,
-                                     float* dgamma_dbeta, float* dscale_shift, fm_stream_t stream) {
+extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout,
+                                     const float* stats, const float* gamma, const float* beta,
+                                     const float* scale_shift, int64_t ss_stride, int32_t silu, int32_t B, int64_t HW,
+                                     int32_t groups, float* workspace, void* dx0, void* dx1, float* dgamma_dbeta,
+                                     float* dscale_shift, fm_stream_t stream) {
+  const int32_t C = C0 + C1;
   if (int e = ensure_device()) return e;
-  FM_REQUIRE(x && dout && stats && gamma && beta && workspace && dx && dgamma_dbeta, "groupnorm_bwd: null pointer");
-  FM_REQUIRE(C % 8 == 0 && groups > 0 && C % groups == 0, "groupnorm_bwd: C must be a multiple of 8 and of groups");
+  FM_REQUIRE(x0 && dout && stats && gamma && beta && workspace && dx0 && dgamma_dbeta, "groupnorm_bwd: null pointer");
+  FM_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && groups > 0 && C % groups == 0,
+             "groupnorm_bwd: channel counts must be multiples of 8 and C of groups");
+  FM_REQUIRE((C1 == 0) == (x1 == nullptr) && (C1 == 0) == (dx1 == nullptr), "groupnorm_bwd: second source mismatch");
     FM_REQUIRE((scale_shift == nullptr) == (dscale_shift == nullptr), "groupnorm_bwd: scale_shift / dscale_shift mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = gn_bwd_blocks(HW, B);
@@ -1017,7 +1027,8 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const floa
   const int sthreads = ((C8 * lanes + 31) / 32) * 32;
   FM_REQUIRE(C8 <= 256, "groupnorm_bwd: C must be <= 2048");
   gn_bwd_partial_kernel<<<dim3(nblk, B), sthreads, (size_t)lanes * C8 * 16 * sizeof(float), st>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dout), tab, part, HW, C8, lanes, rows, silu);
+      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
+      reinterpret_cast<const uint4*>(dout), tab, part, HW, C8, lanes, rows, silu);
   FM_LAUNCH_CHECK("gn_bwd_partial_kernel");
   if (int e = launch_reduce(part, S, B, nblk, 2LL * C, st)) return e;
   const float inv_n = 1.f / ((float)HW * (float)(C / groups));
@@ -1026,9 +1037,10 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const floa
   FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
   /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
   if (int e = launch_reduce(dgb, dgamma_dbeta, 1, B, 2LL * C, st)) return e;
-  gn_bwd_apply_kernel<<<dim3(nblk, B), sthreads, 0, st>>>(reinterpret_cast<const uint4*>(x),
-                                                         reinterpret_cast<const uint4*>(dout), tab,
-                                                         reinterpret_cast<uint4*>(dx), HW, C8, lanes, rows, silu);
+  gn_bwd_apply_kernel<<<dim3(nblk, B), sthreads, 0, st>>>(
+      reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
+      reinterpret_cast<const uint4*>(dout), tab, reinterpret_cast<uint4*>(dx0), reinterpret_cast<uint4*>(dx1), HW, C8,
+      lanes, rows, silu);
   FM_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return 0;
 }

@@ -183,11 +183,16 @@ def conv(srcs: Sequence[torch.Tensor], weights: Sequence[tuple], *, bias=None, s
 # GroupNorm (+ scale-shift) (+ SiLU)
 # --------------------------------------------------------------------------------------------------------------
 class _GroupNormFn(Function):
+    """GroupNorm over the virtual channel concat of one or two sources; the (materialised) result is one tensor."""
+
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale_shift, groups, eps, silu):
+    def forward(ctx, x0, x1, gamma, beta, scale_shift, groups, eps, silu):
         lib = _lib.lib()
-        x = _nhwc(x)
-        b, c, h, w = x.shape
+        x0 = _nhwc(x0)
+        x1 = None if x1 is None else _nhwc(x1)
+        b, c0, h, w = x0.shape
+        c1 = 0 if x1 is None else x1.shape[1]
+        c = c0 + c1
         g32 = gamma.detach().float().contiguous()
         b32 = beta.detach().float().contiguous()
         ss = None if scale_shift is None else _rows_f32(scale_shift)
@@ -195,42 +200,49 @@ class _GroupNormFn(Function):
         n = int(lib.fm_groupnorm_workspace_elems(b, h * w, c, groups))
         if n <= 0:
             raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={c} groups={groups}")
-        ws = _ws(n, x.device)
-        stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x.device)
-        _lib.check(lib.fm_groupnorm_stats_bf16(x.data_ptr(), c, None, 0, b, h * w, groups, float(eps), ws.data_ptr(),
-                                               stats.data_ptr(), st), "groupnorm_stats")
-        out = ops.empty_nhwc(b, c, h, w, x.device)
-        _lib.check(lib.fm_groupnorm_apply_bf16(x.data_ptr(), c, None, 0, b, h * w, groups, stats.data_ptr(),
+        ws = _ws(n, x0.device)
+        stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x0.device)
+        _lib.check(lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps),
+                                               ws.data_ptr(), stats.data_ptr(), st), "groupnorm_stats")
+        out = ops.empty_nhwc(b, c, h, w, x0.device)
+        _lib.check(lib.fm_groupnorm_apply_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, stats.data_ptr(),
                                                g32.data_ptr(), b32.data_ptr(), _ptr(ss),
                                                0 if ss is None else ss.stride(0), int(silu), out.data_ptr(), st),
                    "groupnorm_apply")
-        ctx.cfg = (groups, bool(silu), ss is not None)
-        ctx.save_for_backward(x, stats, g32, b32, *([ss] if ss is not None else []))
+        ctx.cfg = (groups, bool(silu), ss is not None, x1 is not None)
+        ctx.save_for_backward(x0, stats, g32, b32, *([x1] if x1 is not None else []), *([ss] if ss is not None else []))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         lib = _lib.lib()
-        groups, silu, has_ss = ctx.cfg
-        x, stats, g32, b32, *rest = ctx.saved_tensors
-        ss = rest[0] if has_ss else None
+        groups, silu, has_ss, has_x1 = ctx.cfg
+        x0, stats, g32, b32, *rest = ctx.saved_tensors
+        x1 = rest.pop(0) if has_x1 else None
+        ss = rest.pop(0) if has_ss else None
         dout = _nhwc(dout)
-        b, c, h, w = x.shape
-        ws = _ws(lib.fm_groupnorm_bwd_workspace_elems(b, h * w, c), x.device)
-        dx = ops.empty_nhwc(b, c, h, w, x.device)
-        dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
-        dss = torch.empty((b, 2 * c), dtype=torch.float32, device=x.device) if has_ss else None
+        b, c0, h, w = x0.shape
+        c1 = 0 if x1 is None else x1.shape[1]
+        c = c0 + c1
+        ws = _ws(lib.fm_groupnorm_bwd_workspace_elems(b, h * w, c), x0.device)
+        dx0 = ops.empty_nhwc(b, c0, h, w, x0.device)
+        dx1 = ops.empty_nhwc(b, c1, h, w, x0.device) if has_x1 else None
+        dgb = torch.empty((2, c), dtype=torch.float32, device=x0.device)
+        dss = torch.empty((b, 2 * c), dtype=torch.float32, device=x0.device) if has_ss else None
         _lib.check(
-            lib.fm_groupnorm_bwd_bf16(x.data_ptr(), dout.data_ptr(), stats.data_ptr(), g32.data_ptr(), b32.data_ptr(),
-                                      _ptr(ss), 0 if ss is None else ss.stride(0), int(silu), b, h * w, c, groups,
-                                      ws.data_ptr(), dx.data_ptr(), dgb.data_ptr(), _ptr(dss), _stream()),
+            lib.fm_groupnorm_bwd_bf16(x0.data_ptr(), c0, _ptr(x1), c1, dout.data_ptr(), stats.data_ptr(),
+                                      g32.data_ptr(), b32.data_ptr(), _ptr(ss), 0 if ss is None else ss.stride(0),
+                                      int(silu), b, h * w, groups, ws.data_ptr(), dx0.data_ptr(), _ptr(dx1),
+                                      dgb.data_ptr(), _ptr(dss), _stream()),
             "groupnorm_bwd",
         )
-        return dx, dgb[0], dgb[1], dss, None, None, None
+        return dx0, dx1, dgb[0], dgb[1], dss, None, None, None
 
 
 def group_norm(x, gamma, beta, *, groups: int, eps: float, silu: bool, scale_shift=None) -> torch.Tensor:
-    return _GroupNormFn.apply(x, gamma, beta, scale_shift, int(groups), float(eps), bool(silu))
+    """`x`: a tensor, or a pair of tensors read as their channel concat (never materialised)."""
+    x0, x1 = (x[0], x[1]) if isinstance(x, (tuple, list)) else (x, None)
+    return _GroupNormFn.apply(x0, x1, gamma, beta, scale_shift, int(groups), float(eps), bool(silu))
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -71,7 +71,10 @@ def resblock(blk, x: torch.Tensor, emb) -> torch.Tensor:
         out_of_scope(f"training ResBlockND(norm={blk.norm_type}, act={blk.act_name}, dropout={blk.dropout})")
         raise RuntimeError("fmdm_b200.training: unsupported ResBlockND variant")
     c, oc = blk.channels, blk.out_channels
-    h = _gn(blk.norm1, x, silu=True)
+    xs = list(x) if isinstance(x, (tuple, list)) else [x]   # (hidden, skip): the decoder concat stays virtual
+    if len(xs) == 2 and any((t.shape[1] * blk.norm1.num_groups) % c for t in xs):
+        xs = [torch.cat(xs, 1)]                               # a group would straddle the two sources
+    h = _gn(blk.norm1, xs if len(xs) == 2 else xs[0], silu=True)
     addvec = scale_shift = None
     if blk.uses_embedding:
         if emb is None:
@@ -88,13 +91,17 @@ def resblock(blk, x: torch.Tensor, emb) -> torch.Tensor:
     h = _gn(blk.norm2, h, silu=True, scale_shift=scale_shift)
     w2, b2 = blk.conv2.conv.weight, blk.conv2.conv.bias
     if isinstance(blk.skip_connection, nn.Identity):
-        return F.conv([h], [(w2, 0, oc)], bias=b2, residual=x)
+        return F.conv([h], [(w2, 0, oc)], bias=b2, residual=xs[0] if len(xs) == 1 else torch.cat(xs, 1))
     skip = blk.skip_connection.conv
     ws = skip.weight if skip.weight.shape[-1] == 3 else skip.weight.reshape(oc, c)
     bias = b2
     if skip.bias is not None:
         bias = skip.bias if b2 is None else b2 + skip.bias
-    return F.conv([h, x], [(w2, 0, oc), (ws, 0, c)], bias=bias)
+    segs, off = [(w2, 0, oc)], 0
+    for t in xs:
+        segs.append((ws, off, t.shape[1]))
+        off += t.shape[1]
+    return F.conv([h] + xs, segs, bias=bias)
 
 
 def attention(att, x: torch.Tensor) -> torch.Tensor:
@@ -171,7 +178,7 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
     for block in model.up_blocks:
         for i, res in enumerate(block.resnets):
             skip = skips.pop()
-            sample = resblock(res, torch.cat([sample, skip], 1), emb)  # `legacy_unet.py:150`
+            sample = resblock(res, (sample, skip), emb)  # `legacy_unet.py:150`, concat kept virtual
             if block.attentions is not None:
                 sample = attention(block.attentions[i], sample)
         if block.upsamplers is not None:

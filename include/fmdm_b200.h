@@ -244,14 +244,15 @@ int fm_colsum_bf16(const void* dy, float* workspace, float* out, float* total, i
 int fm_zero_insert2x_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, fm_stream_t stream);
 /* out[b][y][x][c] = sum of the 2x2 block of x [B][2H][2W][C]: backward of fm_upsample_nearest2x_bf16 */
 int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, fm_stream_t stream);
-/* Backward of fm_groupnorm_apply_bf16 for one source: x, dout bf16 [B][HW][C]; stats as the forward computed them.
- * dx bf16 [B][HW][C]; dgamma_dbeta fp32 [2][C]; dscale_shift fp32 [B][2C] (NULL iff scale_shift is NULL).
- * workspace: fm_groupnorm_bwd_workspace_elems floats. */
+/* Backward of fm_groupnorm_apply_bf16 over the virtual channel concat of (x0 [C0], x1 [C1] or NULL/0), bf16
+ * [B][HW][C_s]; dout bf16 [B][HW][C0+C1]; stats as the forward computed them.  dx0 / dx1 bf16 like x0 / x1;
+ * dgamma_dbeta fp32 [2][C]; dscale_shift fp32 [B][2C] (NULL iff scale_shift is NULL).
+ * workspace: fm_groupnorm_bwd_workspace_elems(B, HW, C0+C1) floats. */
 int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C);
-int fm_groupnorm_bwd_bf16(const void* x, const void* dout, const float* stats, const float* gamma, const float* beta,
-                          const float* scale_shift, int64_t ss_stride, int32_t silu, int32_t B, int64_t HW, int32_t C,
-                          int32_t groups, float* workspace, void* dx, float* dgamma_dbeta, float* dscale_shift,
-                          fm_stream_t stream);
+int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout, const float* stats,
+                          const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
+                          int32_t silu, int32_t B, int64_t HW, int32_t groups, float* workspace, void* dx0, void* dx1,
+                          float* dgamma_dbeta, float* dscale_shift, fm_stream_t stream);
 /* Backward of fm_attention_bf16 (self-attention, tq == tk == T; q/k/v share the strides qs_*, o/dout share os_*;
  * dq/dk/dv are written with the q strides).  Strides in elements. */
 int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,

@@ -125,6 +125,26 @@ def test_group_norm_backward(F, c, groups, hw, b, silu, ss):
         assert rel_l2(sst.grad, sr.grad) < 1e-2
 
 
+def test_group_norm_backward_two_sources(F):
+    """decoder concat kept virtual: GroupNorm over (hidden, skip) without materialising the concat."""
+    torch.manual_seed(21)
+    dev = "cuda"
+    b, hw, c0, c1 = 2, 16, 256, 128
+    x0 = nhwc(torch.randn(b, c0, hw, hw, device=dev) + 0.5).requires_grad_(True)
+    x1 = nhwc(torch.randn(b, c1, hw, hw, device=dev) * 2).requires_grad_(True)
+    gamma = (torch.rand(c0 + c1, device=dev) + 0.5).requires_grad_(True)
+    beta = (torch.randn(c0 + c1, device=dev) * 0.2).requires_grad_(True)
+    gy = nhwc(torch.randn(b, c0 + c1, hw, hw, device=dev))
+    y = F.group_norm((x0, x1), gamma, beta, groups=32, eps=1e-5, silu=True)
+    y.backward(gy)
+    r0, r1 = x0.detach().float().requires_grad_(True), x1.detach().float().requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yr = TF.silu(TF.group_norm(torch.cat([r0, r1], 1), 32, gr, br, 1e-5))
+    yr.backward(gy.float())
+    for got, ref in [(y, yr), (x0.grad, r0.grad), (x1.grad, r1.grad), (gamma.grad, gr.grad), (beta.grad, br.grad)]:
+        assert rel_l2(got, ref) < 1e-2
+
+
 @pytest.mark.parametrize("c,heads,hw,b", [(512, 64, 16, 2), (512, 64, 8, 3), (128, 8, 16, 2), (256, 4, 8, 2)])
 def test_attention_backward(F, c, heads, hw, b):
     torch.manual_seed(3)
