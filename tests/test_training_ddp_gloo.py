@@ -1,0 +1,96 @@
+"""Data-parallel gradient reduction of the training step on CPU (world_size 2, gloo): the bucketed, hook-driven
+all-reduce over the flat gradient buffer must equal the sum of the per-rank gradients, whatever the bucket size, and
+parameters that receive no gradient must still be reduced (finish() flushes incomplete buckets)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fmdm_b200.training.ddp import BucketedAllReduce
+from fmdm_b200.training.optim import FlatBuffers
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _model():
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(12, 33), torch.nn.SiLU(), torch.nn.Linear(33, 17), torch.nn.SiLU(),
+                              torch.nn.Linear(17, 5))
+    net.unused = torch.nn.Parameter(torch.ones(7))  # never touched by the loss
+    return net
+
+
+def _data(rank):
+    g = torch.Generator().manual_seed(100 + rank)
+    return torch.randn(6, 12, generator=g), torch.randn(6, 5, generator=g)
+
+
+def _local_grads(rank):
+    net = _model()
+    x, y = _data(rank)
+    torch.nn.functional.mse_loss(net(x), y).backward()
+    return [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in net.parameters()]
+
+
+def _worker(rank, world, port, bucket_bytes, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = _model()
+    flat = FlatBuffers(net.parameters())
+    red = BucketedAllReduce(flat, bucket_bytes=bucket_bytes)
+    x, y = _data(rank)
+    outs = []
+    for _ in range(2):  # two cycles: the hook bookkeeping re-arms correctly
+        flat.grad.zero_()
+        red.arm()
+        torch.nn.functional.mse_loss(net(x), y).backward()
+        red.finish()
+        outs.append([p.grad.clone() for p in net.parameters()])
+    ret[rank] = (outs, len(red.buckets), [tuple(p.shape) for p in net.parameters()])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_bytes", [64, 1024, 1 << 20])
+def test_bucketed_allreduce_sums_rank_gradients(bucket_bytes):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), bucket_bytes, ret), nprocs=2, join=True)
+    want = [a + b for a, b in zip(_local_grads(0), _local_grads(1))]
+    for rank in (0, 1):
+        outs, nb, _ = ret[rank]
+        assert nb >= 1
+        for cycle in outs:
+            for got, ref in zip(cycle, want):
+                assert torch.allclose(got, ref, rtol=1e-6, atol=1e-7)
+    if bucket_bytes == 64:
+        assert ret[0][1] > 3  # small buckets really split the buffer
+
+
+def test_flat_buffers_reseat_parameters_and_gradients():
+    net = _model()
+    before = [p.detach().clone() for p in net.parameters()]
+    flat = FlatBuffers(net.parameters())
+    for p, b in zip(net.parameters(), before):
+        assert torch.equal(p.detach(), b)
+        o, n = flat.slice_of(p)
+        assert p.data_ptr() == flat.data.data_ptr() + 4 * o and o % 4 == 0
+        assert p.grad.data_ptr() == flat.grad.data_ptr() + 4 * o
+    x, y = _data(0)
+    torch.nn.functional.mse_loss(net(x), y).backward()
+    ref = _local_grads(0)
+    for p, r in zip(net.parameters(), ref):
+        assert torch.allclose(p.grad, r)
+    # a foreign zero_grad(set_to_none=True) is repaired
+    for p in net.parameters():
+        p.grad = None
+    flat.ensure_grad_views()
+    assert all(p.grad is not None and p.grad.data_ptr() == flat.grad.data_ptr() + 4 * flat.slice_of(p)[0]
+               for p in net.parameters())
