@@ -273,6 +273,31 @@ __global__ void __launch_bounds__(1024) colsum_partial_kernel(const __nv_bfloat1
   }
 }
 
+// stage 2: out[b][c] = sum_blk part[b][blk][c] (fixed order); total[c] = sum_b out[b][c] (fixed order).
+// block = (32 channels, BY sample lanes)
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                             float* __restrict__ total, int B, int nblk, int C) {
+  __shared__ float sh[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float mine = 0.f;
+  if (c < C) {
+    for (int b = threadIdx.y; b < B; b += blockDim.y) {
+      const float* src = part + ((int64_t)b * nblk) * C + c;
+      float acc = 0.f;
+      for (int k = 0; k < nblk; ++k) acc += src[(int64_t)k * C];
+      out[(int64_t)b * C + c] = acc;
+      mine += acc;
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = mine;
+  __syncthreads();
+  if (total != nullptr && threadIdx.y == 0 && c < C) {
+    float acc = 0.f;
+    for (int y = 0; y < blockDim.y; ++y) acc += sh[y][threadIdx.x];
+    total[c] = acc;
+  }
+}
+
 // =============================================================================================================
 // zero insertion (stride-2 dgrad) and 2x2 sum-pool (nearest-2x upsample backward), bf16 NHWC, 8 channels / thread
 // =============================================================================================================
@@ -371,7 +396,7 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __rest
     const int xC8 = c8 < C0_8 ? C0_8 : C8 - C0_8;
     const uint4* xs = (c8 < C0_8 ? x0 + c8 : x1 + (c8 - C0_8)) + ((int64_t)b * HW) * xC8;
     const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
-#pragma unroll 2
+#pragma unroll 4
     for (int64_t r = r0 + lane; r < r1; r += lanes) {
       const uint4 xv = __ldg(xs + r * xC8), dv = __ldg(ds + r * C8);
       const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -435,7 +460,7 @@ __global__ void __launch_bounds__(1024) gn_bwd_table_kernel(const float* __restr
 
 // stage 2: group sums -> A, m1, m2 of the table; per-sample parameter gradients.  One block per sample.
 // S: [B][2][C] (S1 then S2).  dgb_part: [B][2][C] (per-sample dgamma, dbeta); dss: [B][2C] or NULL.
-__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ S,
+__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ part, int nblk,
                                                                 const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta,
                                                                 const float* __restrict__ ss, int64_t ss_stride,
@@ -445,20 +470,25 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
   extern __shared__ float sh[];  // [2][C]
   const int b = blockIdx.x;
   const int cpg = C / groups;
-  const float* S1 = S + ((int64_t)b * 2) * C;
-  const float* S2 = S1 + C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // fixed-order fold of the row-block partials [b][blk][2][C]
+    const float* src = part + ((int64_t)b * nblk * 2) * C + c;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < nblk; ++k) {
+      s1 += src[(int64_t)k * 2 * C];
+      s2 += src[(int64_t)k * 2 * C + C];
+    }
     float ga = gamma[c];
     float sc = 1.f;
     if (ss != nullptr) sc = 1.f + ss[b * ss_stride + c];
     const float gp = ga * sc;
-    sh[c] = gp * S1[c];
-    sh[C + c] = gp * S2[c];
-    dgb_part[((int64_t)b * 2) * C + c] = S2[c] * sc;      // dgamma contribution
-    dgb_part[((int64_t)b * 2 + 1) * C + c] = S1[c] * sc;  // dbeta contribution
+    sh[c] = gp * s1;
+    sh[C + c] = gp * s2;
+    dgb_part[((int64_t)b * 2) * C + c] = s2 * sc;      // dgamma contribution
+    dgb_part[((int64_t)b * 2 + 1) * C + c] = s1 * sc;  // dbeta contribution
     if (dss != nullptr) {
-      dss[(int64_t)b * 2 * C + c] = fmaf(S2[c], ga, S1[c] * beta[c]);  // d scale
-      dss[(int64_t)b * 2 * C + C + c] = S1[c];                         // d shift
+      dss[(int64_t)b * 2 * C + c] = fmaf(s2, ga, s1 * beta[c]);  // d scale
+      dss[(int64_t)b * 2 * C + C + c] = s1;                      // d shift
     }
   }
   __syncthreads();
@@ -503,7 +533,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
   const uint4* xs = (c8 < C0_8 ? x0 : x1) + xoff;
   const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
   uint4* os = (c8 < C0_8 ? dx0 : dx1) + xoff;
-#pragma unroll 2
+#pragma unroll 4
   for (int64_t r = r0 + lane; r < r1; r += lanes) {
     const uint4 xv = __ldg(xs + r * xC8), dv = __ldg(ds + r * C8);
     const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -527,6 +557,22 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
 // =============================================================================================================
 // attention backward: one CTA per (sample, head); Q, K, V, dO staged in shared memory as bf16, math in fp32
 // =============================================================================================================
+// one row of HD bf16 values from shared memory as fp32 (16-byte vector loads)
+template <int HD>
+__device__ __forceinline__ void att_row(const __nv_bfloat16* row, float* out) {
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    const uint4 v = reinterpret_cast<const uint4*>(row)[c];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      out[c * 8 + 2 * k] = f.x;
+      out[c * 8 + 2 * k + 1] = f.y;
+    }
+  }
+}
+
 template <int HD>
 __global__ void __launch_bounds__(256) attention_bwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
@@ -542,29 +588,40 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
   float* dsum = lse + T;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int64_t qoff = b * qs_b + h * qs_h, ooff = b * os_b + h * os_h;
-  for (int idx = threadIdx.x; idx < T * HD; idx += blockDim.x) {
-    const int t = idx / HD, d = idx - t * HD;
-    sq[idx] = q[qoff + t * qs_t + d];
-    sk[idx] = k[qoff + t * qs_t + d];
-    sv[idx] = v[qoff + t * qs_t + d];
-    sdo[idx] = dout[ooff + t * os_t + d];
+  // rows of HD contiguous bf16 (16-byte aligned by the caller's strides): stage with 16-byte copies
+  for (int idx = threadIdx.x; idx < T * (HD / 8); idx += blockDim.x) {
+    const int t = idx / (HD / 8), c = idx - t * (HD / 8);
+    reinterpret_cast<uint4*>(sq)[idx] = *reinterpret_cast<const uint4*>(q + qoff + t * qs_t + c * 8);
+    reinterpret_cast<uint4*>(sk)[idx] = *reinterpret_cast<const uint4*>(k + qoff + t * qs_t + c * 8);
+    reinterpret_cast<uint4*>(sv)[idx] = *reinterpret_cast<const uint4*>(v + qoff + t * qs_t + c * 8);
+    reinterpret_cast<uint4*>(sdo)[idx] = *reinterpret_cast<const uint4*>(dout + ooff + t * os_t + c * 8);
   }
   __syncthreads();
   // phase 1+2: per query row i: log-sum-exp, D_i = dO_i . O_i, then dQ_i
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
-    float qi[HD], doi[HD];
+    float qi[HD], doi[HD], tmp[HD];
+    att_row<HD>(sq + i * HD, qi);
+    att_row<HD>(sdo + i * HD, doi);
     float D = 0.f;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      qi[d] = __bfloat162float(sq[i * HD + d]) * scale;
-      doi[d] = __bfloat162float(sdo[i * HD + d]);
-      D = fmaf(doi[d], __bfloat162float(o[ooff + i * os_t + d]), D);
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 ov = *reinterpret_cast<const uint4*>(o + ooff + i * os_t + c * 8);
+      const uint32_t w[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 f = unpack_bf16x2(w[kk]);
+        D = fmaf(doi[c * 8 + 2 * kk], f.x, D);
+        D = fmaf(doi[c * 8 + 2 * kk + 1], f.y, D);
+      }
     }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) qi[d] *= scale;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < T; ++j) {
+      att_row<HD>(sk + j * HD, tmp);
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(qi[d], __bfloat162float(sk[j * HD + d]), s);
+      for (int d = 0; d < HD; ++d) s = fmaf(qi[d], tmp[d], s);
       const float mn = fmaxf(m, s);
       l = l * __expf(m - mn) + __expf(s - mn);
       m = mn;
@@ -576,49 +633,63 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
 #pragma unroll
     for (int d = 0; d < HD; ++d) acc[d] = 0.f;
     for (int j = 0; j < T; ++j) {
+      float kj[HD];
+      att_row<HD>(sk + j * HD, kj);
+      att_row<HD>(sv + j * HD, tmp);
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int d = 0; d < HD; ++d) {
-        s = fmaf(qi[d], __bfloat162float(sk[j * HD + d]), s);
-        dp = fmaf(doi[d], __bfloat162float(sv[j * HD + d]), dp);
+        s = fmaf(qi[d], kj[d], s);
+        dp = fmaf(doi[d], tmp[d], dp);
       }
       const float ds = __expf(s - L) * (dp - D) * scale;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = fmaf(ds, __bfloat162float(sk[j * HD + d]), acc[d]);
+      for (int d = 0; d < HD; ++d) acc[d] = fmaf(ds, kj[d], acc[d]);
     }
 #pragma unroll
-    for (int d = 0; d < HD; ++d) dq[qoff + i * qs_t + d] = __float2bfloat16(acc[d]);
+    for (int c = 0; c < HD / 8; ++c)
+      *reinterpret_cast<uint4*>(dq + qoff + i * qs_t + c * 8) =
+          make_uint4(pack_bf16x2(acc[c * 8], acc[c * 8 + 1]), pack_bf16x2(acc[c * 8 + 2], acc[c * 8 + 3]),
+                     pack_bf16x2(acc[c * 8 + 4], acc[c * 8 + 5]), pack_bf16x2(acc[c * 8 + 6], acc[c * 8 + 7]));
   }
   __syncthreads();
   // phase 3: per key row j: dK_j, dV_j
   for (int j = threadIdx.x; j < T; j += blockDim.x) {
     float kj[HD], vj[HD], ak[HD], av[HD];
+    att_row<HD>(sk + j * HD, kj);
+    att_row<HD>(sv + j * HD, vj);
 #pragma unroll
     for (int d = 0; d < HD; ++d) {
-      kj[d] = __bfloat162float(sk[j * HD + d]) * scale;
-      vj[d] = __bfloat162float(sv[j * HD + d]);
+      kj[d] *= scale;
       ak[d] = 0.f;
       av[d] = 0.f;
     }
     for (int i = 0; i < T; ++i) {
+      float qi[HD], doi[HD];
+      att_row<HD>(sq + i * HD, qi);
+      att_row<HD>(sdo + i * HD, doi);
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int d = 0; d < HD; ++d) {
-        s = fmaf(kj[d], __bfloat162float(sq[i * HD + d]), s);
-        dp = fmaf(vj[d], __bfloat162float(sdo[i * HD + d]), dp);
+        s = fmaf(kj[d], qi[d], s);
+        dp = fmaf(vj[d], doi[d], dp);
       }
       const float pr = __expf(s - lse[i]);
       const float ds = pr * (dp - dsum[i]) * scale;
 #pragma unroll
       for (int d = 0; d < HD; ++d) {
-        av[d] = fmaf(pr, __bfloat162float(sdo[i * HD + d]), av[d]);
-        ak[d] = fmaf(ds, __bfloat162float(sq[i * HD + d]), ak[d]);
+        av[d] = fmaf(pr, doi[d], av[d]);
+        ak[d] = fmaf(ds, qi[d], ak[d]);
       }
     }
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      dk[qoff + j * qs_t + d] = __float2bfloat16(ak[d]);
-      dv[qoff + j * qs_t + d] = __float2bfloat16(av[d]);
+    for (int c = 0; c < HD / 8; ++c) {
+      *reinterpret_cast<uint4*>(dk + qoff + j * qs_t + c * 8) =
+          make_uint4(pack_bf16x2(ak[c * 8], ak[c * 8 + 1]), pack_bf16x2(ak[c * 8 + 2], ak[c * 8 + 3]),
+                     pack_bf16x2(ak[c * 8 + 4], ak[c * 8 + 5]), pack_bf16x2(ak[c * 8 + 6], ak[c * 8 + 7]));
+      *reinterpret_cast<uint4*>(dv + qoff + j * qs_t + c * 8) =
+          make_uint4(pack_bf16x2(av[c * 8], av[c * 8 + 1]), pack_bf16x2(av[c * 8 + 2], av[c * 8 + 3]),
+                     pack_bf16x2(av[c * 8 + 4], av[c * 8 + 5]), pack_bf16x2(av[c * 8 + 6], av[c * 8 + 7]));
     }
   }
 }
@@ -960,9 +1031,8 @@ extern "C" int fm_colsum_bf16(const void* dy, float* workspace, float* out, floa
   colsum_partial_kernel<<<dim3(nblk, B), threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), workspace, HW, C,
                                                           rows);
   FM_LAUNCH_CHECK("colsum_partial_kernel");
-  if (int e = launch_reduce(workspace, out, B, nblk, C, st)) return e;
-  if (total != nullptr)
-    if (int e = launch_reduce(out, total, 1, B, C, st)) return e;
+  colsum_final_kernel<<<(C + 31) / 32, dim3(32, B < 32 ? B : 32), 0, st>>>(workspace, out, total, B, nblk, C);
+  FM_LAUNCH_CHECK("colsum_final_kernel");
   return 0;
 }
 
@@ -1030,9 +1100,8 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
       reinterpret_cast<const uint4*>(dout), tab, part, HW, C8, lanes, rows, silu);
   FM_LAUNCH_CHECK("gn_bwd_partial_kernel");
-  if (int e = launch_reduce(part, S, B, nblk, 2LL * C, st)) return e;
   const float inv_n = 1.f / ((float)HW * (float)(C / groups));
-  gn_bwd_finalize_kernel<<<B, cthreads, 2 * C * sizeof(float), st>>>(S, gamma, beta, scale_shift, ss_stride, C, groups,
+  gn_bwd_finalize_kernel<<<B, cthreads, 2 * C * sizeof(float), st>>>(part, nblk, gamma, beta, scale_shift, ss_stride, C, groups,
                                                                     inv_n, tab, dgb, dscale_shift);
   FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
   /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
@@ -1051,6 +1120,10 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
                                      int64_t os_h, int64_t os_t, float scale, fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   FM_REQUIRE(q && k && v && o && dout && dq && dk && dv, "attention_bwd: null pointer");
+  FM_REQUIRE(((qs_b | qs_h | qs_t | os_b | os_h | os_t) % 8) == 0 &&
+                 (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq |
+                   (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+             "attention_bwd: rows must be 16-byte aligned (strides multiples of 8 elements)");
   const size_t smem = (size_t)4 * T * head_dim * 2 + (size_t)2 * T * 4;
   if (smem > 200 * 1024) {
     set_error("attention_bwd: T=%d head_dim=%d exceeds the shared-memory staging budget", T, head_dim);
