@@ -17,7 +17,9 @@ def main():
     dev = "cuda"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tot_t = tot_f = 0.0
-    for cin, cout, k, s, hw in SHAPES:
+    sel = os.environ.get("SHAPES")
+    shapes = SHAPES if not sel else [SHAPES[int(i)] for i in sel.split(",")]
+    for cin, cout, k, s, hw in shapes:
         x = torch.randn(B, hw, hw, cin, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2)
         ho = hw // s
         dy = torch.randn(B, ho, ho, cout, device=dev, dtype=torch.bfloat16).permute(0, 3, 1, 2)
