@@ -396,22 +396,34 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __rest
     const int xC8 = c8 < C0_8 ? C0_8 : C8 - C0_8;
     const uint4* xs = (c8 < C0_8 ? x0 + c8 : x1 + (c8 - C0_8)) + ((int64_t)b * HW) * xC8;
     const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
-#pragma unroll 4
-    for (int64_t r = r0 + lane; r < r1; r += lanes) {
-      const uint4 xv = __ldg(xs + r * xC8), dv = __ldg(ds + r * C8);
-      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+    constexpr int kU = 4;  // independent 16-byte loads in flight per stream and thread
+    for (int64_t r = r0 + lane; r < r1; r += (int64_t)lanes * kU) {
+      uint4 xv[kU], dv[kU];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
-        float d0 = df.x, d1 = df.y;
-        if (silu) {
-          d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
-          d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
+      for (int u = 0; u < kU; ++u) {
+        const int64_t ru = r + (int64_t)u * lanes;
+        xv[u] = dv[u] = make_uint4(0, 0, 0, 0);  // zero gradient rows contribute nothing
+        if (ru < r1) {
+          xv[u] = __ldg(xs + ru * xC8);
+          dv[u] = __ldg(ds + ru * C8);
         }
-        s1[2 * k] += d0;
-        s2[2 * k] = fmaf(d0, (xf.x - mu[2 * k]) * rs[2 * k], s2[2 * k]);
-        s1[2 * k + 1] += d1;
-        s2[2 * k + 1] = fmaf(d1, (xf.y - mu[2 * k + 1]) * rs[2 * k + 1], s2[2 * k + 1]);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
+          float d0 = df.x, d1 = df.y;
+          if (silu) {
+            d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
+            d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
+          }
+          s1[2 * k] += d0;
+          s2[2 * k] = fmaf(d0, (xf.x - mu[2 * k]) * rs[2 * k], s2[2 * k]);
+          s1[2 * k + 1] += d1;
+          s2[2 * k + 1] = fmaf(d1, (xf.y - mu[2 * k + 1]) * rs[2 * k + 1], s2[2 * k + 1]);
+        }
       }
     }
 #pragma unroll
@@ -533,24 +545,37 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
   const uint4* xs = (c8 < C0_8 ? x0 : x1) + xoff;
   const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
   uint4* os = (c8 < C0_8 ? dx0 : dx1) + xoff;
-#pragma unroll 4
-  for (int64_t r = r0 + lane; r < r1; r += lanes) {
-    const uint4 xv = __ldg(xs + r * xC8), dv = __ldg(ds + r * C8);
-    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-    uint32_t ow[4];
+  constexpr int kU = 4;
+  for (int64_t r = r0 + lane; r < r1; r += (int64_t)lanes * kU) {
+    uint4 xv[kU], dv[kU];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
-      float d0 = df.x, d1 = df.y;
-      if (silu) {
-        d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
-        d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
+    for (int u = 0; u < kU; ++u) {
+      const int64_t ru = r + (int64_t)u * lanes;
+      if (ru < r1) {
+        xv[u] = __ldg(xs + ru * xC8);
+        dv[u] = __ldg(ds + ru * C8);
       }
-      const float o0 = fmaf(cA[2 * k], d0, fmaf(cQ[2 * k], xf.x, cP[2 * k]));
-      const float o1 = fmaf(cA[2 * k + 1], d1, fmaf(cQ[2 * k + 1], xf.y, cP[2 * k + 1]));
-      ow[k] = pack_bf16x2(o0, o1);
     }
-    os[r * xC8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t ru = r + (int64_t)u * lanes;
+      if (ru >= r1) break;
+      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
+        float d0 = df.x, d1 = df.y;
+        if (silu) {
+          d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
+          d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
+        }
+        const float o0 = fmaf(cA[2 * k], d0, fmaf(cQ[2 * k], xf.x, cP[2 * k]));
+        const float o1 = fmaf(cA[2 * k + 1], d1, fmaf(cQ[2 * k + 1], xf.y, cP[2 * k + 1]));
+        ow[k] = pack_bf16x2(o0, o1);
+      }
+      os[ru * xC8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
   }
 }
 
@@ -1061,7 +1086,12 @@ extern "C" int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H
   return 0;
 }
 
-static int gn_bwd_blocks(int64_t HW, int B) { return colsum_blocks(HW, B); }
+static int gn_bwd_blocks(int64_t HW, int B) {
+  int nblk = (int)((8LL * sm_count() + B - 1) / B);  // ~8 CTAs per SM across the batch
+  if (nblk > HW / 16) nblk = (int)(HW / 16);
+  if (nblk < 1) nblk = 1;
+  return nblk;
+}
 
 extern "C" int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C) {
   if (ensure_device()) return 0;

@@ -111,8 +111,10 @@ class _ConvFn(Function):
         pw = ops.pack_conv_weight([(weights[wi], cb, cc) for wi, cb, cc in segs])
         if residual is not None:
             residual = _nhwc(residual)
+        # want_stats: the epilogue also emits the GroupNorm partial statistics of the output (`out._fm_stats`), so a
+        # GroupNorm that consumes this tensor skips its statistics pass (as on the inference path)
         out = ops.conv2d(srcs, pw, stride=stride, bias=None if bias is None else bias.detach().float().contiguous(),
-                         addvec=None if addvec is None else _rows_f32(addvec), residual=residual)
+                         addvec=None if addvec is None else _rows_f32(addvec), residual=residual, want_stats=True)
         ctx.meta = meta
         ctx.flags = (bias is not None, addvec is not None, residual is not None)
         ctx.save_for_backward(*srcs, *weights)
@@ -197,13 +199,21 @@ class _GroupNormFn(Function):
         b32 = beta.detach().float().contiguous()
         ss = None if scale_shift is None else _rows_f32(scale_shift)
         st = _stream()
-        n = int(lib.fm_groupnorm_workspace_elems(b, h * w, c, groups))
-        if n <= 0:
-            raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={c} groups={groups}")
-        ws = _ws(n, x0.device)
         stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x0.device)
-        _lib.check(lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps),
-                                               ws.data_ptr(), stats.data_ptr(), st), "groupnorm_stats")
+        fused = [getattr(s, "_fm_stats", None) for s in ((x0,) if x1 is None else (x0, x1))]
+        if all(f is not None for f in fused) and (c // groups) % 4 == 0:
+            # the convs that wrote the sources left channel-quad (sum, sumsq) partials: fold them, no read pass
+            p1 = fused[1] if len(fused) == 2 else (None, 0)
+            _lib.check(lib.fm_groupnorm_finalize_partials(fused[0][0].data_ptr(), fused[0][1], c0, _ptr(p1[0]), p1[1],
+                                                          c1, b, h * w, groups, float(eps), stats.data_ptr(), st),
+                       "groupnorm_finalize_partials")
+        else:
+            n = int(lib.fm_groupnorm_workspace_elems(b, h * w, c, groups))
+            if n <= 0:
+                raise RuntimeError(f"fmdm_b200.group_norm: unsupported shape B={b} HW={h * w} C={c} groups={groups}")
+            ws = _ws(n, x0.device)
+            _lib.check(lib.fm_groupnorm_stats_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, float(eps),
+                                                   ws.data_ptr(), stats.data_ptr(), st), "groupnorm_stats")
         out = ops.empty_nhwc(b, c, h, w, x0.device)
         _lib.check(lib.fm_groupnorm_apply_bf16(x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, stats.data_ptr(),
                                                g32.data_ptr(), b32.data_ptr(), _ptr(ss),
@@ -364,7 +374,7 @@ class _StemFn(Function):
         x1 = None if x1 is None else x1.detach().float().contiguous()
         w32 = weight.detach().float().contiguous()
         out = ops.conv_stem(x0, x1, w32, None if bias is None else bias.detach().float().contiguous(),
-                            in_scale=in_scale, in_shift=in_shift, want_stats=False)
+                            in_scale=in_scale, in_shift=in_shift, want_stats=True)
         ctx.cfg = (float(in_scale), float(in_shift), x1 is not None, bias is not None, tuple(weight.shape))
         ctx.save_for_backward(x0, *([x1] if x1 is not None else []))
         return out

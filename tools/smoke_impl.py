@@ -74,6 +74,24 @@ def run_smoke():
         orc = OD.unet_diffusers_nd_forward(sd, CFG, x, t, conditioning="concatenate", channels=1, context=c)
     rel = float((mine - orc).norm() / orc.norm())
     assert rel < 1.2e-2, f"smoke: 96x160 forward rel-L2 {rel:.4f} vs oracle"
+    # one training step: loss and gradients of the hand-written backward against the oracle's autograd
+    from fmdm_b200.training import flow_matching_loss
+    from oracle import training as OT
+
+    model.train()
+    clean = torch.rand(2, 1, 32, 32, generator=g2).to(dev)
+    nz = torch.randn(2, 1, 32, 32, generator=g2).to(dev)
+    tt = torch.rand(2, generator=g2).to(dev)
+    loss = flow_matching_loss(model, clean, cond, noise=nz, t=tt)
+    loss.backward()
+    ref_loss, ref_grads = OT.loss_and_grads(sd, CFG, clean, cond, nz, tt)
+    got = torch.cat([p.grad.float().reshape(-1) for _, p in model.named_parameters()])
+    want = torch.cat([ref_grads[k].reshape(-1) for k, _ in model.named_parameters()])
+    grel = float((got - want).norm() / want.norm())
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss)), "smoke: training loss vs oracle"
+    assert grel < 5e-2, f"smoke: training gradient rel-L2 {grel:.4f} vs oracle"
+    model.eval()
+    print(f"smoke ok: training step loss {float(loss):.4f} (oracle {float(ref_loss):.4f}), gradient rel-L2 {grel:.2e}")
     print(f"smoke ok: 8-step flow-matching sample, PSNR vs oracle {psnr:.1f} dB, {launched} kernel launches (eager part); "
           f"96x160 forward rel-L2 {rel:.2e}")
 
