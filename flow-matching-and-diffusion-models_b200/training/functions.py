@@ -298,6 +298,63 @@ def attention_qkv(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     return _AttentionFn.apply(qkv, int(heads))
 
 
+class _AttentionRawFn(Function):
+    """SpatialSelfAttention's raw-reshape head split (`attention.py:111-115`): the channel-major (b, 3*inner, T) qkv
+    buffer re-read as (b, heads, T, 3*dh); returns (b, heads, T, dh) contiguous."""
+
+    @staticmethod
+    def forward(ctx, qkv_cm, heads, dh):
+        assert qkv_cm.dtype == BF16 and qkv_cm.is_contiguous() and qkv_cm.dim() == 3
+        b, c3, t = qkv_cm.shape
+        inner = heads * dh
+        assert c3 == 3 * inner
+        att = torch.empty((b, heads, t, dh), dtype=BF16, device=qkv_cm.device)
+        flat = qkv_cm.view(-1)
+        ops.attention(flat, flat[dh:], flat[2 * dh:], att, batch=b, heads=heads, tq=t, tk=t, head_dim=dh,
+                      q_strides=(3 * inner * t, t * 3 * dh, 3 * dh), kv_strides=(3 * inner * t, t * 3 * dh, 3 * dh),
+                      o_strides=(heads * t * dh, t * dh, dh))
+        ctx.cfg = (heads, dh)
+        ctx.save_for_backward(qkv_cm, att)
+        return att
+
+    @staticmethod
+    def backward(ctx, datt):
+        qkv_cm, att = ctx.saved_tensors
+        heads, dh = ctx.cfg
+        b, c3, t = qkv_cm.shape
+        inner = heads * dh
+        datt = datt.to(BF16).contiguous()
+        dqkv = torch.empty_like(qkv_cm)
+        q, dq = qkv_cm.data_ptr(), dqkv.data_ptr()
+        _lib.check(
+            _lib.lib().fm_attention_bwd_bf16(q, q + 2 * dh, q + 4 * dh, att.data_ptr(), datt.data_ptr(), dq, dq + 2 * dh,
+                                             dq + 4 * dh, b, heads, t, dh, 3 * inner * t, t * 3 * dh, 3 * dh,
+                                             heads * t * dh, t * dh, dh, 1.0 / math.sqrt(dh), _stream()),
+            "attention_bwd",
+        )
+        return dqkv, None, None
+
+
+def attention_raw(qkv_cm: torch.Tensor, heads: int, dim_head: int) -> torch.Tensor:
+    return _AttentionRawFn.apply(qkv_cm, int(heads), int(dim_head))
+
+
+class _TransposeFn(Function):
+    """[B][R][C] -> [B][C][R] (bf16, contiguous); the backward is the same kernel."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.transpose_bf16(x.to(BF16).contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.transpose_bf16(dy.to(BF16).contiguous())
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    return _TransposeFn.apply(x)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # tiny fp32 Linear (time MLP, per-block embedding projections): y = f(x) W^T + b, f = SiLU if silu_in
 # --------------------------------------------------------------------------------------------------------------

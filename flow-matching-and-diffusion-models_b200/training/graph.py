@@ -19,9 +19,15 @@ from . import functions as F
 
 
 def supported(model) -> bool:
+    from ..models.unet.unet import EfficientUNetND
     from ..models.unet.unet_diffusers_nd import UNetDiffusersND
 
-    return isinstance(model, UNetDiffusersND) and model.spatial_dims == 2 and model.cross_attention_dim is None
+    if isinstance(model, UNetDiffusersND):
+        return model.spatial_dims == 2 and model.cross_attention_dim is None
+    if isinstance(model, EfficientUNetND):
+        return (model.spatial_dims == 2 and not model.cross_attention_resolutions
+                and not model.cross_attention_in_middle and model.dropout == 0)
+    return False
 
 
 def _gn(norm: nn.GroupNorm, x, *, silu: bool, scale_shift=None):
@@ -119,6 +125,22 @@ def attention(att, x: torch.Tensor) -> torch.Tensor:
     return F.conv([a], [(att.to_out[0].weight, 0, c)], bias=att.to_out[0].bias, residual=x)
 
 
+def spatial_self_attention(att, x: torch.Tensor) -> torch.Tensor:
+    """`attention.py:82-117` (CompVis block: GN -> Conv1d qkv -> raw-reshape head split -> SDPA -> Conv1d -> + x)."""
+    b, c, hh, ww = x.shape
+    if att.use_linear or att.dim_head not in (8, 16, 32, 64):
+        out_of_scope("training SpatialSelfAttention (linear attention / dim_head)")
+        raise RuntimeError("fmdm_b200.training: unsupported SpatialSelfAttention variant")
+    t, inner = hh * ww, att.inner_dim
+    n = _gn(att.norm, x, silu=False)
+    qkv = F.conv([n], [(att.qkv.weight.squeeze(-1), 0, c)], bias=att.qkv.bias)          # NHWC == [b][T][3*inner]
+    qkv_cm = F.transpose(qkv.permute(0, 2, 3, 1).reshape(b, t, 3 * inner))              # [b][3*inner][T]
+    a = F.attention_raw(qkv_cm, att.heads, att.dim_head)                                 # [b][heads][T][dh]
+    h_tc = F.transpose(a.view(b, inner, t))                                              # raw reshape, [b][T][inner]
+    h = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
+    return F.conv([h], [(att.proj_out.weight.squeeze(-1), 0, inner)], bias=att.proj_out.bias, residual=x)
+
+
 def downsample(down, x):
     if not down.use_conv:
         out_of_scope("training DownsampleND(use_conv=False)")
@@ -135,11 +157,64 @@ def upsample(up, x):
     return F.conv([y], [(conv.weight, 0, up.channels)], bias=conv.bias)
 
 
+def _sequential(seq, x, emb):
+    """`TimestepEmbedSequential.forward` (`unet.py:18-39`) over differentiable ops."""
+    from ..nn.blocks.attention import SpatialSelfAttention
+    from ..nn.blocks.residual import ResBlockND
+    from ..nn.ops.upsampling import DownsampleND, UpsampleND
+
+    for layer in seq:
+        if isinstance(layer, ResBlockND):
+            x = resblock(layer, x, emb)
+        elif isinstance(layer, SpatialSelfAttention):
+            x = spatial_self_attention(layer, x)
+        elif isinstance(layer, DownsampleND):
+            x = downsample(layer, x)
+        elif isinstance(layer, UpsampleND):
+            x = upsample(layer, x)
+        else:
+            out_of_scope(f"training {type(layer).__name__} inside EfficientUNetND")
+            raise RuntimeError(f"fmdm_b200.training: no training path for {type(layer).__name__}")
+    return x
+
+
+def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
+    """`EfficientUNetND.forward` (`unet.py:295-326`) with autograd."""
+    ops.require_cuda(x, "training.efficient_unet_forward")
+    t = model._normalize_timesteps(t, x)
+    feats = ops.timestep_embedding(t, model.model_channels, 10000.0, flip_sin_to_cos=False, freq_shift=0.0)
+    emb = F.linear(feats, model.time_embed[0].weight, model.time_embed[0].bias)
+    emb = F.linear(emb, model.time_embed[2].weight, model.time_embed[2].bias, silu_in=True)
+    emb = EmbProjections(model, emb)
+    stem = model.input_blocks[0][0].conv
+    cin = x.shape[1] + (context.shape[1] if context is not None else 0)
+    if cin != stem.in_channels:
+        raise ValueError(f"EfficientUNetND expected {stem.in_channels} input channels, got {cin}")
+    if cin > 4:
+        out_of_scope(f"training stem conv with {cin} input channels")
+        raise RuntimeError("fmdm_b200.training: the stem backward supports up to 4 input channels")
+    h = F.conv_stem(x, context, stem.weight, stem.bias)
+    hs = [h]
+    for block in list(model.input_blocks)[1:]:
+        h = _sequential(block, h, emb)
+        hs.append(h)
+    h = _sequential(model.middle_block, h, emb)
+    for block in model.output_blocks:
+        h = _sequential(block, (h, hs.pop()), emb)   # `unet.py:321-322`, concat kept virtual
+    h = _gn(model.out[0], h, silu=True)
+    head = model.out[2].conv
+    return F.conv_head(h, head.weight, head.bias)
+
+
 def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
-    """`UNetDiffusersND.forward` with autograd: returns the fp32 NCHW prediction."""
+    """`UNetDiffusersND.forward` / `EfficientUNetND.forward` with autograd: returns the fp32 NCHW prediction."""
+    from ..models.unet.unet import EfficientUNetND
+
     if not supported(model):
         out_of_scope(f"training {type(model).__name__}")
-        raise RuntimeError("fmdm_b200.training: only UNetDiffusersND (2-D, self-attention) has a training path")
+        raise RuntimeError("fmdm_b200.training: no training path for this denoiser variant (2-D, self-attention only)")
+    if isinstance(model, EfficientUNetND):
+        return efficient_unet_forward(model, x, t, context)
     ops.require_cuda(x, "training.unet_forward")
     t = model._normalize_timesteps(t, x)
     feats = ops.timestep_embedding(t, model.time_proj_dim, 10000.0, flip_sin_to_cos=model.flip_sin_to_cos,

@@ -27,6 +27,13 @@ LDCT = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layer
         "up_block_types": ["UpBlock2D", "AttnUpBlock2D"] + ["UpBlock2D"] * 4}
 
 
+COMPVIS = {"in_channels": 1, "out_channels": 1, "num_res_blocks": 2, "channel_mult": [1, 1, 2, 2],
+           "model_channels": 64, "attention_resolutions": [], "block_out_channels": [64, 64, 128, 128]}
+COMPVIS_ATTN = {"in_channels": 1, "out_channels": 1, "num_res_blocks": 1, "channel_mult": [1, 2],
+                "model_channels": 64, "attention_resolutions": [2], "use_linear_attn": False,
+                "block_out_channels": [64, 128]}
+
+
 def rel_l2(a, b):
     return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-20))
 
@@ -55,7 +62,8 @@ def batch(b, hw, seed):
     return clean, ldct, noise, t
 
 
-@pytest.mark.parametrize("name,cfg,hw,b", [("small32", SMALL, 32, 4), ("ldct64", LDCT, 64, 2), ("ldct128", LDCT, 128, 1)])
+@pytest.mark.parametrize("name,cfg,hw,b", [("small32", SMALL, 32, 4), ("ldct64", LDCT, 64, 2), ("ldct128", LDCT, 128, 1),
+                                           ("compvis32", COMPVIS, 32, 2), ("compvis_attn32", COMPVIS_ATTN, 32, 2)])
 def test_training_gradients_match_oracle(name, cfg, hw, b):
     from fmdm_b200.training import flow_matching_loss
 

@@ -10,6 +10,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import LDCT_UNET  # noqa: E402
 
 
+COMPVIS = {"in_channels": 1, "out_channels": 1, "num_res_blocks": 2, "channel_mult": [1, 1, 2, 2, 4, 4],
+           "model_channels": 128, "attention_resolutions": [], "block_out_channels": [128, 128, 256, 256, 512, 512]}
+
+
+def model_cfg():
+    """MODEL=compvis selects EfficientUNetND (configs/LDCT/LDCT_flow_matching_compvis.json); default UNetDiffusersND."""
+    return COMPVIS if os.environ.get("MODEL", "").lower() in ("compvis", "efficient_nd") else LDCT_UNET
+
+
 def eager_reference(B, hw, steps, warmup, dev):
     """The same step on the same GPU with stock PyTorch kernels (cuDNN / cuBLAS / SDPA under bf16 autocast, fused
     torch.optim.AdamW), through the oracle's functional restatement of the reference denoiser: context for the
@@ -20,7 +29,7 @@ def eager_reference(B, hw, steps, warmup, dev):
     from oracle import denoiser as OD
 
     torch.manual_seed(0)
-    model = DiffusionUNetFactory().build(LDCT_UNET, "concatenate", 1)
+    model = DiffusionUNetFactory().build(model_cfg(), "concatenate", 1)
     params = {k: torch.nn.Parameter(v.detach().clone().to(dev).to(memory_format=torch.channels_last)
                                     if v.dim() == 4 else v.detach().clone().to(dev))
               for k, v in model.state_dict().items()}
@@ -36,7 +45,7 @@ def eager_reference(B, hw, steps, warmup, dev):
         timesteps = (t * 999).long()
         x_t = (1.0 - t[:, None, None, None]) * clean + t[:, None, None, None] * noise
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            pred = OD.denoiser_forward(params, LDCT_UNET, x_t, timesteps, conditioning="concatenate", channels=1,
+            pred = OD.denoiser_forward(params, model_cfg(), x_t, timesteps, conditioning="concatenate", channels=1,
                                        context=ldct)
             loss = TF.mse_loss(pred.float(), noise - clean)
         loss.backward()
@@ -75,10 +84,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.manual_seed(0)
-    model = DiffusionUNetFactory().build(LDCT_UNET, "concatenate", 1).to(dev).train()
+    model = DiffusionUNetFactory().build(model_cfg(), "concatenate", 1).to(dev).train()
     if world > 1:
         for p in model.parameters():
             dist.broadcast(p.data, 0)
+    model_name = type(model).__name__
     tr = FlowMatchingTrainer(model, lr=1e-4, cuda_graph=not os.environ.get("NO_GRAPH"))
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     clean = torch.rand(B, 1, hw, hw, device=dev, generator=g)
@@ -112,6 +122,7 @@ def main():
                           "unit": "samples/s", "n_gpus": world, "ms_per_step": round(ms.item(), 2), "steps": steps,
                           "warmup": warmup, "dtype": "bf16", "data": "synthetic",
                           "config": {"workload": f"LDCT {hw}x{hw} flow-matching training step, batch {B}/GPU",
+                                     "model": model_name,
                                      "optimizer": "AdamW (flat, fused)", "cuda_graph": not os.environ.get("NO_GRAPH"), "loss_first": ls[0], "loss_last": ls[-1]},
                           "host_enqueue_ms_per_step": round(enqueue_ms, 2), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
                           "gpu_eager_reference": eager}))

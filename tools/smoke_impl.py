@@ -88,6 +88,7 @@ def run_smoke():
     got = torch.cat([p.grad.float().reshape(-1) for _, p in model.named_parameters()])
     want = torch.cat([ref_grads[k].reshape(-1) for k, _ in model.named_parameters()])
     grel = float((got - want).norm() / want.norm())
+    loss = loss.detach()
     assert abs(float(loss) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss)), "smoke: training loss vs oracle"
     assert grel < 5e-2, f"smoke: training gradient rel-L2 {grel:.4f} vs oracle"
     model.eval()
