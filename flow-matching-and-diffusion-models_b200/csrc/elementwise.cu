@@ -361,10 +361,18 @@ extern "C" int fm_linear_f32(const float* x, const float* W, const float* bias, 
                              fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x && W && y && B > 0 && I > 0 && O > 0, "linear: bad argument B=%d I=%d O=%d", B, I, O);
-  int rows = (48 * 1024) / (I * (int)sizeof(float));
+  // input rows staged in shared memory: up to 192 KB (the training step's batched projections reach I ~ 20k)
+  constexpr int kLinSmemMax = 192 * 1024;
+  int rows = kLinSmemMax / (I * (int)sizeof(float));
   if (rows > kLinRows) rows = kLinRows;
   FM_REQUIRE(rows >= 1, "linear: in_features=%d too large", I);
   const size_t smem = (size_t)rows * I * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    if (int e = check_cuda(cudaFuncSetAttribute(linear_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                kLinSmemMax), "linear attr")) return e;
+    attr = true;
+  }
   linear_f32_kernel<<<(O + 3) / 4, 128, smem, (cudaStream_t)stream>>>(x, W, bias, bias2, y, B, I, O, silu_in,
                                                                       silu_out, rows);
   FM_LAUNCH_CHECK("linear_f32_kernel");
