@@ -33,6 +33,28 @@ __global__ void __launch_bounds__(256) sched_flowmatch_kernel(float* __restrict_
     xo[i] = __fadd_rn(x[i], __fmul_rn(dt, v[i]));
 }
 
+// DDPM ancestral step (epsilon prediction, variance_type "fixed_small"):
+//   x0 = clamp((x - sqrt(1-a_t) e) / sqrt(a_t)); x = (c_x0 * x0 + c_xt * x) + sigma * noise       (DDPMScheduler.step)
+__device__ __forceinline__ float ddpm_one(float x, float e, float z, float sb, float sa, float c0, float c1,
+                                          float sigma, int clip, float cr) {
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(sb, e)), sa);
+  if (clip) x0 = fminf(fmaxf(x0, -cr), cr);
+  const float mean = __fadd_rn(__fmul_rn(c0, x0), __fmul_rn(c1, x));
+  return __fadd_rn(mean, __fmul_rn(sigma, z));
+}
+__global__ void __launch_bounds__(256) sched_ddpm_kernel(float* __restrict__ xo, const float* __restrict__ x,
+                                                        const float* __restrict__ eps,
+                                                        const float* __restrict__ noise,
+                                                        const float* __restrict__ coef,
+                                                        const int32_t* __restrict__ step_dev, int step_host,
+                                                        int clip, float cr, int64_t n) {
+  const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_DDPM_NCOEF;
+  const float sb = c[0], sa = c[1], c0 = c[2], c1 = c[3], sg = c[4];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    xo[i] = ddpm_one(x[i], eps[i], noise[i], sb, sa, c0, c1, sg, clip, cr);
+}
+
 // DDIM (eta = 0, epsilon prediction):  x0 = (x - sqrt(1-a_t) e) / sqrt(a_t); clamp; x = sqrt(a_p) x0 + dir * e
 __device__ __forceinline__ float ddim_one(float x, float e, float sb, float sa, float sp, float dc, int clip,
                                           float cr) {
@@ -292,6 +314,19 @@ extern "C" int fm_sched_ddim_f32(float* x_out, const float* x, const float* eps,
   sched_ddim_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, x, eps, coef, step_dev, step_host,
                                                                             clip, clip_range, n);
   FM_LAUNCH_CHECK("sched_ddim_kernel");
+  return 0;
+}
+
+extern "C" int fm_sched_ddpm_f32(float* x_out, const float* x, const float* eps, const float* noise, const float* coef,
+                                 const int32_t* step_dev, int32_t step_host, int32_t clip, float clip_range,
+                                 int64_t n, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x_out && x && eps && noise && coef && n >= 0, "ddpm: null pointer or negative n");
+  FM_REQUIRE(step_dev != nullptr || step_host >= 0, "ddpm: negative step");
+  if (n == 0) return 0;
+  sched_ddpm_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x_out, x, eps, noise, coef, step_dev, step_host,
+                                                                    clip, clip_range, n);
+  FM_LAUNCH_CHECK("sched_ddpm_kernel");
   return 0;
 }
 

@@ -535,6 +535,21 @@ def sched_ddim(x, eps, coef, step, clip, clip_range, x_out=None, step_dev=None):
     return x_out
 
 
+def sched_ddpm(x, eps, noise, coef, step, clip, clip_range, x_out=None, step_dev=None):
+    lib = _lib.lib()
+    require_cuda(x, "sched_ddpm")
+    for t in (x, eps, noise):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    _lib.check(
+        lib.fm_sched_ddpm_f32(x_out.data_ptr(), x.data_ptr(), eps.data_ptr(), noise.data_ptr(), coef.data_ptr(),
+                              _ptr(step_dev), int(step), int(bool(clip)), float(clip_range), x.numel(), _stream()),
+        "sched_ddpm",
+    )
+    return x_out
+
+
 def sched_dpmpp2m(x, eps, m_prev, coef, step, x_out=None, m_cur=None, step_dev=None):
     lib = _lib.lib()
     require_cuda(x, "sched_dpmpp2m")

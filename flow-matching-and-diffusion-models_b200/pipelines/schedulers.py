@@ -222,6 +222,92 @@ class DDIMScheduler(_SchedulerBase):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+class DDPMScheduler(_SchedulerBase):
+    """Ancestral DDPM sampling (the reference's default scheduler name, `pipelines/utils.py:46`): epsilon prediction,
+    variance_type "fixed_small", clip_sample to +-clip_sample_range, "leading" spacing.  The Gaussian noise of each
+    step is drawn with torch's generator (as diffusers' `randn_tensor` does) into a static buffer, so the step is
+    still one fused kernel and the run replays from a CUDA graph."""
+
+    NCOEF = 8
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", variance_type: str = "fixed_small", clip_sample: bool = True,
+                 prediction_type: str = "epsilon", clip_sample_range: float = 1.0, timestep_spacing: str = "leading",
+                 steps_offset: int = 0, **unused):
+        super().__init__()
+        if prediction_type != "epsilon" or timestep_spacing != "leading" or variance_type != "fixed_small":
+            raise NotImplementedError("fmdm_b200 DDPM: only epsilon prediction, leading spacing, fixed_small variance")
+        self.config = SimpleNamespace(num_train_timesteps=int(num_train_timesteps), beta_start=beta_start,
+                                      beta_end=beta_end, beta_schedule=beta_schedule, variance_type=variance_type,
+                                      clip_sample=bool(clip_sample), prediction_type=prediction_type,
+                                      clip_sample_range=float(clip_sample_range), timestep_spacing=timestep_spacing,
+                                      steps_offset=int(steps_offset))
+        T = self.config.num_train_timesteps
+        self.alphas_cumprod = _alphas_cumprod(T, beta_start, beta_end, beta_schedule)
+        self.one = torch.tensor(1.0)
+        self.timesteps = torch.from_numpy(np.arange(0, T)[::-1].copy().astype(np.int64))
+        self.set_timesteps(T)
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        T = self.config.num_train_timesteps
+        n = int(num_inference_steps)
+        if n > T:
+            raise ValueError(f"`num_inference_steps`: {n} cannot be larger than `num_train_timesteps`: {T}")
+        self.num_inference_steps = n
+        ratio = T // n
+        ts = (np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)
+        rows = []
+        zero = torch.tensor(0.0)
+        for t in ts.tolist():
+            prev_t = t - ratio
+            a_t = self.alphas_cumprod[t]
+            a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+            b_t = 1 - a_t
+            b_prev = 1 - a_prev
+            cur_alpha = a_t / a_prev
+            cur_beta = 1 - cur_alpha
+            c_x0 = (a_prev ** 0.5 * cur_beta) / b_t
+            c_xt = cur_alpha ** 0.5 * b_prev / b_t
+            variance = torch.clamp((1 - a_prev) / (1 - a_t) * cur_beta, min=1e-20)
+            sigma = variance ** 0.5 if t > 0 else zero
+            rows.append(torch.stack([b_t ** 0.5, a_t ** 0.5, c_x0, c_xt, sigma, zero, zero, zero]))
+        self._coef_cpu = torch.stack(rows).to(torch.float32).contiguous()
+        self._reset_tables()
+
+    def plan_rows(self, timesteps):
+        return [_lookup(self.timesteps, t) for t in timesteps]
+
+    def new_state(self, x: torch.Tensor):
+        return {"noise": torch.zeros_like(x)}
+
+    def step_kernel(self, x_out, x, pred, coef, step_host=0, step_dev=None, state=None):
+        state["noise"].normal_()  # graph-safe: torch registers the generator's philox offset with the capture
+        ops.sched_ddpm(x, pred, state["noise"], coef, step_host, self.config.clip_sample,
+                       self.config.clip_sample_range, x_out=x_out, step_dev=step_dev)
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, generator=None,
+             noise: Optional[torch.Tensor] = None, **unused) -> SchedulerOutput:
+        """`noise` (optional, same shape): the step's standard-normal draw, for seeded parity runs; otherwise drawn
+        from `generator` / the global generator on the sample's device."""
+        row = _lookup(self.timesteps, int(timestep))
+        x = sample.to(torch.float32).contiguous()
+        e = model_output.to(torch.float32).contiguous()
+        if noise is None:
+            noise = torch.randn(x.shape, generator=generator, device=x.device, dtype=torch.float32)
+        out = ops.sched_ddpm(x, e, noise.to(torch.float32).contiguous(), self.coef_table(x.device), row,
+                             self.config.clip_sample, self.config.clip_sample_range)
+        return SchedulerOutput(out.to(model_output.dtype))
+
+    def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        ac = self.alphas_cumprod.to(torch.float32)
+        idx = timesteps.to("cpu", torch.int64).flatten()
+        a = (ac[idx] ** 0.5).to(original_samples.device).contiguous()
+        b = ((1 - ac[idx]) ** 0.5).to(original_samples.device).contiguous()
+        return ops.sched_add_noise(original_samples, noise, a, b).to(original_samples.dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 class DPMSolverMultistepScheduler(_SchedulerBase):
     """DPM-Solver++ (data prediction), multistep order <= 2, midpoint, lower_order_final, final sigma = 0,
     "linspace" spacing — what `--scheduler dpmsolver++` builds (`pipelines/utils.py:79`)."""

@@ -17,17 +17,18 @@ import torch
 
 from .. import ops
 from ..models.unet.base import BaseUNetND
-from .schedulers import (DDIMScheduler, DPMSolverMultistepScheduler, FlowMatchEulerDiscreteScheduler,
-                         _SchedulerBase)
+from .schedulers import (DDIMScheduler, DDPMScheduler, DPMSolverMultistepScheduler,
+                         FlowMatchEulerDiscreteScheduler, _SchedulerBase)
 
 SCHEDULER_REGISTRY: Dict[str, type] = {
+    "ddpm": DDPMScheduler,
     "ddim": DDIMScheduler,
     "dpm_multistep": DPMSolverMultistepScheduler,
     "flow_match_euler": FlowMatchEulerDiscreteScheduler,
     "flowmatch": FlowMatchEulerDiscreteScheduler,
 }
 # names the reference registers but the north star does not ask for
-_OUT_OF_SCOPE_SCHEDULERS = ("ddpm", "dpm_sde", "unipc")
+_OUT_OF_SCOPE_SCHEDULERS = ("dpm_sde", "unipc")
 
 
 def resolve_conditioning_mode(value) -> Optional[str]:
@@ -45,8 +46,7 @@ def build_scheduler(spec: Dict, training_cfg: Dict) -> Tuple[object, int]:
     key = str(name).lower()
     if key in _OUT_OF_SCOPE_SCHEDULERS:
         raise NotImplementedError(
-            f"fmdm_b200: scheduler '{name}' is outside the B200 hot path (north star: flowmatch, ddim, dpmsolver++); "
-            "pass --scheduler ddim / dpmsolver++ to sample a DDPM-trained model")
+            f"fmdm_b200: scheduler '{name}' is outside the B200 hot path (built: flowmatch, ddpm, ddim, dpmsolver++)")
     if key not in SCHEDULER_REGISTRY:
         raise ValueError(f"Unknown scheduler '{name}'. Available: {', '.join(SCHEDULER_REGISTRY)}")
     cls = SCHEDULER_REGISTRY[key]

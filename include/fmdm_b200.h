@@ -205,6 +205,12 @@ int fm_sched_flowmatch_f32(float* x_out, const float* x, const float* v, const f
 #define FM_DDIM_NCOEF 4 /* {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-std^2)} */
 int fm_sched_ddim_f32(float* x_out, const float* x, const float* eps, const float* coef, const int32_t* step_dev,
                       int32_t step_host, int32_t clip, float clip_range, int64_t n, fm_stream_t stream);
+#define FM_DDPM_NCOEF 8 /* {sqrt(1-a_t), sqrt(a_t), c_x0, c_xt, sigma_t (0 at t = 0), unused x3} */
+/* DDPM ancestral step (the reference's default `ddpm` scheduler, diffusers DDPMScheduler.step, epsilon prediction,
+ * "fixed_small" variance): x_out = c_x0*clamp(x0) + c_xt*x + sigma*noise; noise: fp32 standard normal, same shape */
+int fm_sched_ddpm_f32(float* x_out, const float* x, const float* eps, const float* noise, const float* coef,
+                      const int32_t* step_dev, int32_t step_host, int32_t clip, float clip_range, int64_t n,
+                      fm_stream_t stream);
 #define FM_DPMPP_NCOEF 8 /* {sigma_s, alpha_s, c1, c2, c3, inv_r0, second_order, unused} */
 int fm_sched_dpmpp2m_f32(float* x_out, float* m_cur, const float* x, const float* eps, const float* m_prev,
                          const float* coef, const int32_t* step_dev, int32_t step_host, int64_t n,

@@ -17,6 +17,7 @@ _ALIASES = {  # pipelines/utils.py:74-84 (the three in-scope names)
     "flowmatch": ("flow_match_euler", {}),
     "flow_match_euler": ("flow_match_euler", {}),
     "ddim": ("ddim", {}),
+    "ddpm": ("ddpm", {}),
     "dpmsolver++": ("dpm_multistep", {"solver_order": 2, "algorithm_type": "dpmsolver++"}),
 }
 

@@ -1,9 +1,10 @@
 """ORACLE (test infrastructure, never imported by the product path).
 
-CPU restatement of the three third-party schedulers the reference binds at
+CPU restatement of the third-party schedulers the reference binds at
 `/root/reference/src/pipelines/utils.py:13-30` and steps at `:218`:
 
-    diffusers.FlowMatchEulerDiscreteScheduler, diffusers.DDIMScheduler, diffusers.DPMSolverMultistepScheduler
+    diffusers.FlowMatchEulerDiscreteScheduler, diffusers.DDIMScheduler, diffusers.DPMSolverMultistepScheduler,
+    diffusers.DDPMScheduler
 
 The arithmetic lives in `diffusers` (requirement `diffusers>=0.24.0`, `/root/reference/requirements.txt:18`, not
 pinned, not vendored, NOT installed in this image or on the GPU box, no source copy on disk).  What follows restates
@@ -143,6 +144,69 @@ class DDIMOracle:
 
 
 # ------------------------------------------------------------------------------------------------------------------
+class DDPMOracle:
+    """diffusers.DDPMScheduler (the reference's default scheduler name, `pipelines/utils.py:13-30,46`) with its
+    defaults: linear betas, variance_type="fixed_small", clip_sample=True (range 1), prediction_type="epsilon",
+    timestep_spacing="leading", thresholding off.  Restated from the published algorithm (Ho et al. 2020, eq. 7 for
+    the posterior mean, beta-tilde for the variance) in diffusers' operation order; PARITY UNPINNED like the others."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 1e-4, beta_end: float = 0.02,
+                 clip_sample: bool = True, clip_sample_range: float = 1.0, steps_offset: int = 0):
+        self.config = SimpleNamespace(num_train_timesteps=int(num_train_timesteps), beta_start=beta_start,
+                                      beta_end=beta_end, clip_sample=clip_sample, clip_sample_range=clip_sample_range,
+                                      steps_offset=steps_offset, prediction_type="epsilon",
+                                      variance_type="fixed_small", timestep_spacing="leading")
+        T = self.config.num_train_timesteps
+        self.alphas_cumprod = _linear_alphas_cumprod(T, beta_start, beta_end)
+        self.one = torch.tensor(1.0)
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = T
+        self.timesteps = torch.from_numpy(np.arange(0, T)[::-1].copy().astype(np.int64))
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        T = self.config.num_train_timesteps
+        if num_inference_steps > T:
+            raise ValueError("num_inference_steps cannot exceed num_train_timesteps")
+        self.num_inference_steps = int(num_inference_steps)
+        ratio = T // self.num_inference_steps
+        ts = (np.arange(0, self.num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+        ts += self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)
+
+    def _variance(self, t: int, prev_t: int):
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        cur_beta = 1 - a_t / a_prev
+        return torch.clamp((1 - a_prev) / (1 - a_t) * cur_beta, min=1e-20)
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, noise=None, generator=None) -> StepOutput:
+        T = self.config.num_train_timesteps
+        t = int(timestep)
+        prev_t = t - T // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        b_t = 1 - a_t
+        b_prev = 1 - a_prev
+        cur_alpha = a_t / a_prev
+        cur_beta = 1 - cur_alpha
+        x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        if self.config.clip_sample:
+            x0 = x0.clamp(-self.config.clip_sample_range, self.config.clip_sample_range)
+        c_x0 = (a_prev ** 0.5 * cur_beta) / b_t
+        c_xt = cur_alpha ** 0.5 * b_prev / b_t
+        prev = c_x0 * x0 + c_xt * sample
+        variance = 0
+        if t > 0:
+            if noise is None:
+                noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+            variance = (self._variance(t, prev_t) ** 0.5) * noise
+        prev = prev + variance
+        return StepOutput(prev, x0)
+
+    add_noise = DDIMOracle.add_noise
+
+
+# ------------------------------------------------------------------------------------------------------------------
 class DPMSolverPPOracle:
     """DPMSolverMultistepScheduler with the `--scheduler dpmsolver++` alias (`pipelines/utils.py:79`):
     solver_order=2, algorithm_type="dpmsolver++", solver_type="midpoint", lower_order_final=True,
@@ -248,5 +312,6 @@ ORACLE_REGISTRY = {
     "flow_match_euler": FlowMatchEulerOracle,
     "flowmatch": FlowMatchEulerOracle,
     "ddim": DDIMOracle,
+    "ddpm": DDPMOracle,
     "dpm_multistep": DPMSolverPPOracle,
 }

@@ -118,8 +118,14 @@ def test_scheduler_glue():
     assert resolve_scheduler_override("FlowMatch") == {"name": "flow_match_euler"}
     with pytest.raises(ValueError):
         resolve_scheduler_override("nope")
+    from fmdm_b200.pipelines.schedulers import DDPMScheduler
+
+    s, n = build_scheduler({"name": "ddpm"}, {})   # the reference's default name (`pipelines/utils.py:46`)
+    assert isinstance(s, DDPMScheduler) and n == 1000 and hasattr(s, "add_noise")
+    s, _ = build_scheduler({}, {})
+    assert isinstance(s, DDPMScheduler)
     with pytest.raises(NotImplementedError):
-        build_scheduler({"name": "ddpm"}, {})
+        build_scheduler({"name": "unipc"}, {})
     with pytest.raises(ValueError):
         build_scheduler({"name": "nope"}, {})
     # training_cfg fallbacks
@@ -144,6 +150,17 @@ def test_product_scheduler_tables_match_oracle():
         a, b = DDIMScheduler(1000, 1e-4, 0.02), DDIMOracle(1000, 1e-4, 0.02)
         a.set_timesteps(n); b.set_timesteps(n)
         assert torch.equal(a.timesteps, b.timesteps) and torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+    from fmdm_b200.pipelines.schedulers import DDPMScheduler
+    from oracle.schedulers import DDPMOracle
+
+    for n in (1, 10, 50, 1000):
+        a, b = DDPMScheduler(1000, 1e-4, 0.02), DDPMOracle(1000, 1e-4, 0.02)
+        a.set_timesteps(n); b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps) and torch.equal(a.alphas_cumprod, b.alphas_cumprod)
+        assert a._coef_cpu.shape == (n, 8) and float(a._coef_cpu[-1, 4]) == 0.0  # no noise on the last step (t = 0)
+        if n > 1:
+            t0 = int(b.timesteps[0])
+            assert float(a._coef_cpu[0, 4]) == float(b._variance(t0, t0 - 1000 // n) ** 0.5)
     for n in (2, 5, 20):
         a, b = DPMSolverMultistepScheduler(1000, 1e-4, 0.02), DPMSolverPPOracle(1000, 1e-4, 0.02)
         a.set_timesteps(n); b.set_timesteps(n)

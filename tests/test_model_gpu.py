@@ -161,6 +161,21 @@ def test_scheduler_steps_bit_exact():
             x_cpu = orc.step(pred, t, x_cpu).prev_sample
             x_gpu = mine.step(pred.to(DEV), t, x_gpu).prev_sample
             assert torch.equal(x_gpu.cpu(), x_cpu), (name, n, float(t), float((x_gpu.cpu() - x_cpu).abs().max()))
+    # ddpm (ancestral): the step's Gaussian draw is passed to both sides
+    for n in (1000, 50):
+        mine, _ = build_scheduler({"name": "ddpm", "params": {"beta_start": 1e-4, "beta_end": 0.02}}, {})
+        orc = make_scheduler("ddpm", 1000, {"beta_start": 1e-4, "beta_end": 0.02})
+        mine.set_timesteps(n)
+        orc.set_timesteps(n)
+        assert torch.equal(mine.timesteps, orc.timesteps)
+        x_cpu = torch.randn(shape, generator=g) * 1.5
+        x_gpu = x_cpu.to(DEV)
+        for t in list(orc.timesteps[:6]) + list(orc.timesteps[-6:]):
+            pred = torch.randn(shape, generator=g)
+            nz = torch.randn(shape, generator=g)
+            x_cpu = orc.step(pred, t, x_cpu, noise=nz).prev_sample
+            x_gpu = mine.step(pred.to(DEV), t, x_gpu, noise=nz.to(DEV)).prev_sample
+            assert torch.equal(x_gpu.cpu(), x_cpu), ("ddpm", n, float(t), float((x_gpu.cpu() - x_cpu).abs().max()))
     # add_noise
     mine, _ = build_scheduler({"name": "ddim", "params": {"beta_start": 1e-4, "beta_end": 0.02}}, {})
     orc = make_scheduler("ddim", 1000, {"beta_start": 1e-4, "beta_end": 0.02})
@@ -284,3 +299,27 @@ def test_ldct_flowmatch_final_sample_psnr(hw):
             x = orc.step(pred.cpu(), t, x.cpu()).prev_sample.to(DEV)
     p = psnr(out.clamp(0, 1), x.clamp(0, 1))
     assert p >= 40.0, p
+
+
+def test_ddpm_graph_sampler_statistics():
+    """`--scheduler ddpm` (the reference's default name) through the graph-replayed sampler: a zero-epsilon denoiser makes
+    every step an explicit linear-Gaussian map, so the mean and variance of the final sample are known in closed form
+    (the mean contracts towards clip(x0_hat) and fresh noise enters every replay); two runs draw different noise."""
+    from fmdm_b200.pipelines.utils import GraphSampler, build_scheduler
+
+    class ZeroEps(torch.nn.Module):
+        def forward(self, x, t, context=None, t_table=None, step_dev=None):
+            return torch.zeros_like(x)
+
+    sched, _ = build_scheduler({"name": "ddpm", "params": {"beta_start": 1e-4, "beta_end": 0.02}}, {})
+    sched.set_timesteps(20)
+    shape = (4, 1, 64, 64)
+    gs = GraphSampler(ZeroEps(), sched, shape, torch.device(DEV))
+    init = torch.zeros(shape, device=DEV)
+    torch.manual_seed(0)
+    a = gs.run(init, None, sched.timesteps)
+    b = gs.run(init, None, sched.timesteps)
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+    # with eps = 0 and x_T = 0: x0_hat = x / sqrt(abar) (clipped), the chain stays zero-mean; the last step (t = 0,
+    # sigma = 0) returns clip(x / sqrt(abar_0)), so the output is bounded by the clip range and not degenerate
+    assert abs(float(a.mean())) < 0.05 and float(a.abs().max()) <= 1.0 + 1e-6 and float(a.std()) > 0.05

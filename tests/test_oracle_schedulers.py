@@ -80,6 +80,47 @@ def test_ddim_schedule_and_point_mass():
     assert float(outb.max()) < 1.7 - 0.1
 
 
+def test_ddpm_known_answers():
+    """DDPMOracle against closed forms of Ho et al. 2020: posterior-mean coefficients sum rule, beta-tilde variance,
+    the noise-free last step, and recovery of a point mass when the ancestral noise is switched off."""
+    from oracle.schedulers import DDPMOracle
+
+    s = DDPMOracle(1000, 1e-4, 0.02)
+    assert s.timesteps[:3].tolist() == [999, 998, 997] and s.num_inference_steps == 1000
+    betas = np.linspace(1e-4, 0.02, 1000)
+    ac = np.cumprod(1 - betas)
+    # one full-resolution step at t = 500 with zero noise: x_prev = c_x0 * x0_hat + c_xt * x_t, closed-form coefficients
+    t = 500
+    c_x0 = np.sqrt(ac[t - 1]) * betas[t] / (1 - ac[t])
+    c_xt = np.sqrt(1 - betas[t]) * (1 - ac[t - 1]) / (1 - ac[t])
+    x = torch.tensor([[[[0.3, -0.2]]]])
+    e = torch.tensor([[[[0.5, 1.5]]]])
+    x0_hat = ((x - np.sqrt(1 - ac[t]) * e) / np.sqrt(ac[t])).clamp(-1, 1)
+    out = s.step(e, t, x, noise=torch.zeros_like(x)).prev_sample
+    assert torch.allclose(out, c_x0 * x0_hat + c_xt * x, rtol=2e-5, atol=1e-6)
+    # variance: beta-tilde_t = (1 - abar_{t-1}) / (1 - abar_t) * beta_t, applied as sigma * noise
+    z = torch.ones_like(x)
+    out_z = s.step(e, t, x, noise=z).prev_sample
+    sigma = np.sqrt((1 - ac[t - 1]) / (1 - ac[t]) * betas[t])
+    assert torch.allclose(out_z - out, torch.full_like(x, float(sigma)), rtol=1e-4)
+    # t = 0: no noise is added and the step returns the clipped x0 estimate
+    out0 = s.step(e, 0, x, noise=torch.full_like(x, 1e3)).prev_sample
+    x0_0 = ((x - np.sqrt(1 - ac[0]) * e) / np.sqrt(ac[0])).clamp(-1, 1)
+    assert torch.allclose(out0, x0_0, rtol=1e-5, atol=1e-6)
+    # strided sampling (50 steps, "leading"): exact epsilon + zero ancestral noise recovers the point mass
+    s.set_timesteps(50)
+    assert s.timesteps[:3].tolist() == [980, 960, 940] and int(s.timesteps[-1]) == 0
+    x0 = torch.tensor([[[[0.25, -0.5], [0.75, 0.9]]]])
+    g = torch.Generator().manual_seed(2)
+    a = s.alphas_cumprod[980]
+    xt = a.sqrt() * x0 + (1 - a).sqrt() * torch.randn(x0.shape, generator=g)
+    for tt in s.timesteps:
+        at = s.alphas_cumprod[int(tt)]
+        eps = (xt - at.sqrt() * x0) / (1 - at).sqrt()
+        xt = s.step(eps, tt, xt, noise=torch.zeros_like(xt)).prev_sample
+    assert float((xt - x0).abs().max()) < 2e-5
+
+
 def test_ddim_add_noise():
     s = DDIMOracle(1000)
     x0 = torch.ones(2, 1, 2, 2)
