@@ -424,6 +424,108 @@ static int launch_attention(const void* q, const void* k, const void* v, void* o
   return 0;
 }
 
+// =============================================================================================================
+// Cross-attention context path: GroupNorm over the context tokens + the tiny-K key/value
+// projection (`attention.py:149-165` SpatialCrossAttention.kv_proj, `attention.py:232-262` DiffusersAttentionND
+// to_k/to_v with context_dim): ctx fp32 [B][Cc][Tc] -> bf16 K|V.  Cc (the latent channel count, 4 in the LDCT
+// configs) is far below a tensor-core tile, so this is two small CUDA-core kernels; K/V do not depend on the
+// sampling step, so the host computes them once per run.
+// =============================================================================================================
+constexpr int kCtxMaxC = 16;
+
+// stats[b][g] = (mean, rstd) over the group's (Cc/groups) x Tc values; one block per (group, sample)
+__global__ void __launch_bounds__(256) context_stats_kernel(const float* __restrict__ ctx, float* __restrict__ stats,
+                                                             int Cc, int Tc, int groups, float eps) {
+  __shared__ double red[2][256];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = Cc / groups;
+  const int64_t n = (int64_t)cpg * Tc;
+  const float* src = ctx + ((int64_t)b * Cc + (int64_t)g * cpg) * Tc;  // the group's channels are contiguous
+  double s = 0.0, ss = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = src[i];
+    s += v;
+    ss += v * v;
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = ss;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + k];
+      red[1][threadIdx.x] += red[1][threadIdx.x + k];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = red[0][0] / (double)n;
+    double var = red[1][0] / (double)n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((int64_t)b * groups + g) * 2 + 0] = (float)mean;
+    stats[((int64_t)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// out[b][t][o] (token-major, LAYOUT 0) or out[b][o][t] (channel-major, LAYOUT 1)
+//   = bias[o] + sum_c W[o][c] * ((ctx[b][c][t] - mean) * rstd * gamma[c] + beta[c])
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) context_proj_kernel(const float* __restrict__ ctx,
+                                                            const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ W, const float* __restrict__ bias,
+                                                            __nv_bfloat16* __restrict__ out, int Cc, int Tc, int O,
+                                                            int groups) {
+  constexpr int kTok = 64;
+  __shared__ float sn[kCtxMaxC][kTok];
+  const int b = blockIdx.y, t0 = blockIdx.x * kTok;
+  const int cpg = Cc / groups;
+  for (int i = threadIdx.x; i < Cc * kTok; i += blockDim.x) {
+    const int c = i / kTok, tt = i - c * kTok;
+    float v = 0.f;
+    if (t0 + tt < Tc) {
+      const int g = c / cpg;
+      const float mean = stats[((int64_t)b * groups + g) * 2 + 0], rstd = stats[((int64_t)b * groups + g) * 2 + 1];
+      v = fmaf((ctx[((int64_t)b * Cc + c) * Tc + t0 + tt] - mean) * rstd, gamma[c], beta[c]);
+    }
+    sn[c][tt] = v;
+  }
+  __syncthreads();
+  const int ntok = min(kTok, Tc - t0);
+  if (LAYOUT == 0) {
+    // thread = output feature (its weight row in registers); tokens in the inner loop: stores coalesce over o
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+      float w[kCtxMaxC];
+#pragma unroll
+      for (int c = 0; c < kCtxMaxC; ++c) w[c] = c < Cc ? W[(int64_t)o * Cc + c] : 0.f;
+      const float bo = bias != nullptr ? bias[o] : 0.f;
+      for (int tt = 0; tt < ntok; ++tt) {
+        float acc = bo;
+#pragma unroll
+        for (int c = 0; c < kCtxMaxC; ++c)
+          if (c < Cc) acc = fmaf(w[c], sn[c][tt], acc);
+        out[((int64_t)b * Tc + t0 + tt) * O + o] = __float2bfloat16_rn(acc);
+      }
+    }
+  } else {
+    // thread = (token, feature lane); the token's normalised context vector in registers: stores coalesce over tokens
+    const int tt = threadIdx.x % kTok, lane = threadIdx.x / kTok;
+    float n[kCtxMaxC];
+#pragma unroll
+    for (int c = 0; c < kCtxMaxC; ++c) n[c] = c < Cc ? sn[c][tt] : 0.f;
+    if (tt < ntok) {
+      for (int o = lane; o < O; o += blockDim.x / kTok) {
+        float acc = bias != nullptr ? bias[o] : 0.f;
+#pragma unroll
+        for (int c = 0; c < kCtxMaxC; ++c)
+          if (c < Cc) acc = fmaf(__ldg(W + (int64_t)o * Cc + c), n[c], acc);
+        out[((int64_t)b * O + o) * Tc + t0 + tt] = __float2bfloat16_rn(acc);
+      }
+    }
+  }
+}
+
+
 }  // namespace fm
 
 using namespace fm;
@@ -461,4 +563,26 @@ extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, vo
       return FM_ERR_UNSUPPORTED;
   }
 #undef FM_ATT_ARGS
+}
+
+extern "C" int fm_context_kv_bf16(const float* ctx, const float* gamma, const float* beta, const float* W,
+                                  const float* bias, float* stats_ws, void* out, int32_t B, int32_t Cc, int32_t Tc,
+                                  int32_t O, int32_t groups, float eps, int32_t channel_major, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(ctx && gamma && beta && W && stats_ws && out, "context_kv: null pointer");
+  FM_REQUIRE(B > 0 && Tc > 0 && O > 0 && Cc > 0 && Cc <= kCtxMaxC, "context_kv: context_dim must be 1..%d (got %d)",
+             kCtxMaxC, Cc);
+  FM_REQUIRE(groups > 0 && Cc % groups == 0, "context_kv: groups must divide context_dim");
+  cudaStream_t st = (cudaStream_t)stream;
+  context_stats_kernel<<<dim3(groups, B), 256, 0, st>>>(ctx, stats_ws, Cc, Tc, groups, eps);
+  FM_LAUNCH_CHECK("context_stats_kernel");
+  const dim3 grid((Tc + 63) / 64, B);
+  if (channel_major)
+    context_proj_kernel<1><<<grid, 256, 0, st>>>(ctx, stats_ws, gamma, beta, W, bias,
+                                                 reinterpret_cast<__nv_bfloat16*>(out), Cc, Tc, O, groups);
+  else
+    context_proj_kernel<0><<<grid, 256, 0, st>>>(ctx, stats_ws, gamma, beta, W, bias,
+                                                 reinterpret_cast<__nv_bfloat16*>(out), Cc, Tc, O, groups);
+  FM_LAUNCH_CHECK("context_proj_kernel");
+  return 0;
 }

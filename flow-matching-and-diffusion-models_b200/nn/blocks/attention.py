@@ -2,7 +2,10 @@
 
 In scope: `DiffusersAttentionND` self-attention (GN -> fused QKV 1x1 GEMM on tcgen05 ->
 K3 softmax(QK^T)V -> out-proj GEMM with the residual in its epilogue) and `SpatialSelfAttention` including the
-reference's raw-memory head split.  Cross-attention variants and linear attention keep the API but are out of scope.
+reference's raw-memory head split.  Cross-attention (`SpatialCrossAttention`, `DiffusersAttentionND`
+with `context_dim`): queries as above, keys/values from `ops.context_kv` (GroupNorm over the context tokens + the tiny-K
+projection in one pass, computed once per context tensor and reused over the sampling steps), K3 with Tq != Tk.
+Linear attention keeps the API but is out of scope.
 """
 from __future__ import annotations
 
@@ -55,6 +58,44 @@ class LinearQKVAttention(nn.Module):
         ctx = torch.einsum("...nd,...ne->...de", ks, v.float())
         ctx = ctx / (ks.sum(dim=-2).unsqueeze(-1) + self.eps)
         return F.dropout(torch.einsum("...nd,...de->...ne", qs, ctx), p=self.dropout, training=self.training)
+
+
+def context_tokens(context: torch.Tensor, context_dim: int) -> torch.Tensor:
+    """The context as (B, context_dim, T_ctx), with the reference's shape rules (`attention.py:160-175, 237-252`)."""
+    if context.dim() == 3:
+        if context.shape[1] == context_dim:
+            return context
+        if context.shape[-1] == context_dim:
+            return context.transpose(1, 2)
+        raise ValueError(f"Context channels mismatch: expected {context_dim}, got {tuple(context.shape)}.")
+    if context.shape[1] != context_dim:
+        raise ValueError(f"Context channels mismatch: expected {context_dim}, got {tuple(context.shape)}.")
+    return context.reshape(context.shape[0], context.shape[1], -1)
+
+
+class _ContextKV:
+    """Keys/values of one context tensor: they depend on the context and the projection weights only, not on the
+    sampling step, so they are computed once per (context object, parameter version) and reused."""
+
+    def __init__(self):
+        self._ref, self._sig, self._kv = None, None, None
+
+    def get(self, context: torch.Tensor, params, build):
+        sig = (context._version, context.data_ptr(), tuple(context.shape), ParamCache._sig(params))
+        if self._ref is not None and self._ref() is context and self._sig == sig:
+            return self._kv
+        kv = build()
+        import weakref
+
+        if self._kv is not None and self._kv.shape == kv.shape and self._kv.device == kv.device:
+            # refresh in place: a CUDA graph captured with the previous keys/values keeps reading this buffer
+            self._kv.copy_(kv)
+            kv = self._kv
+        self._ref, self._sig, self._kv = weakref.ref(context), sig, kv
+        return kv
+
+
+CONTEXT_DIM_MAX = 16  # fm_context_kv_bf16 keeps a token's context vector / a weight row in registers
 
 
 class ContextBlock(nn.Module):
@@ -120,7 +161,9 @@ class SpatialSelfAttention(nn.Module):
 
 
 class SpatialCrossAttention(ContextBlock):
-    """API-parity shell of `attention.py:120-189` (conditioning:"attention" configs; out of scope)."""
+    """CompVis-style cross-attention block (`attention.py:120-189`, conditioning:"attention" configs):
+    GN -> Conv1d q -> raw-reshape head split; context GN -> Conv1d kv (one small kernel, cached per context) -> raw
+    reshape -> SDPA (Tq != Tk) -> raw reshape back -> zero-init Conv1d -> + x."""
 
     def __init__(self, dim: int, context_dim: int, heads: int = 4, dim_head: int = 64, use_linear: bool = False,
                  use_efficient_attn: bool = True):
@@ -133,26 +176,55 @@ class SpatialCrossAttention(ContextBlock):
         self.kv_proj = nn.Conv1d(context_dim, self.inner_dim * 2, 1)
         self.attention = LinearQKVAttention() if use_linear else QKVAttention(efficient_attn=use_efficient_attn)
         self.proj_out = zero_module(nn.Conv1d(self.inner_dim, self.dim, 1))
+        self.use_linear = use_linear
+        self._cache = ParamCache()
+        self._kv = _ContextKV()
 
     def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
         if context is None:
             raise ValueError("SpatialCrossAttention requires a non-empty context tensor.")
-        out_of_scope("SpatialCrossAttention")
-        x = x.float()
-        context = context.float()
+        b, c, *spatial = x.shape
+        if (self.use_linear or len(spatial) != 2 or c % 8 or self.dim_head not in (8, 16, 32, 64)
+                or self.context_dim > CONTEXT_DIM_MAX or not x.is_cuda):
+            out_of_scope(f"SpatialCrossAttention(use_linear={self.use_linear}, spatial={spatial}, "
+                         f"dim_head={self.dim_head}, context_dim={self.context_dim})")
+            return self._eager(x.float(), context.float())
+        x = ops.to_nhwc_bf16(x)
+        hh, ww = spatial
+        t, inner, dh, nh = hh * ww, self.inner_dim, self.dim_head, self.heads
+        n = ops.group_norm([x], self.norm.num_groups, self.norm.eps, f32(self.norm.weight), f32(self.norm.bias),
+                           silu=False)
+        wq = self._cache.get("q", [self.q_proj.weight],
+                             lambda: ops.pack_conv_weight([(self.q_proj.weight.squeeze(-1), 0, c)]))
+        wo = self._cache.get("out", [self.proj_out.weight],
+                             lambda: ops.pack_conv_weight([(self.proj_out.weight.squeeze(-1), 0, inner)]))
+        q = ops.conv2d([n], wq, bias=f32(self.q_proj.bias))                            # NHWC == [b][T][inner]
+        q_cm = ops.transpose_bf16(q.permute(0, 2, 3, 1).reshape(b, t, inner))          # [b][inner][T]
+        kv_cm = self.precompute_context(context)
+        tc = kv_cm.shape[-1]
+        # the reference's raw reshapes: q (b, inner, T) -> (b, heads, T, dh); kv (b, 2*inner, Tc) -> (b, heads, Tc, 2*dh)
+        att = torch.empty((b, nh, t, dh), dtype=torch.bfloat16, device=x.device)
+        kvf = kv_cm.view(-1)
+        ops.attention(q_cm.view(-1), kvf, kvf[dh:], att, batch=b, heads=nh, tq=t, tk=tc, head_dim=dh,
+                      q_strides=(inner * t, t * dh, dh), kv_strides=(2 * inner * tc, tc * 2 * dh, 2 * dh),
+                      o_strides=(nh * t * dh, t * dh, dh))
+        h_tc = ops.transpose_bf16(att.view(b, inner, t))                                # [b][T][inner]
+        h_nhwc = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
+        return ops.conv2d([h_nhwc], wo, bias=f32(self.proj_out.bias), residual=x, want_stats=True)
+
+    def precompute_context(self, context: torch.Tensor) -> torch.Tensor:
+        """Keys/values of `context`, channel-major (b, 2*inner, Tc); cached per context object / parameter version."""
+        cn = self.context_norm
+        cf = context_tokens(context, self.context_dim)
+        return self._kv.get(context, [self.kv_proj.weight, self.kv_proj.bias, cn.weight, cn.bias],
+                            lambda: ops.context_kv(cf, f32(cn.weight), f32(cn.bias),
+                                                   f32(self.kv_proj.weight.squeeze(-1)), f32(self.kv_proj.bias),
+                                                   groups=cn.num_groups, eps=cn.eps, channel_major=True))
+
+    def _eager(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
         b, c, *spatial = x.shape
         xf = x.reshape(b, c, -1)
-        if context.dim() == 3:
-            if context.shape[1] == self.context_dim:
-                cf = context
-            elif context.shape[-1] == self.context_dim:
-                cf = context.transpose(1, 2)
-            else:
-                raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {context.shape}.")
-        else:
-            if context.shape[1] != self.context_dim:
-                raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {context.shape}.")
-            cf = context.reshape(context.shape[0], context.shape[1], -1)
+        cf = context_tokens(context, self.context_dim)
         q = self.q_proj(self.norm(xf))
         kv = self.kv_proj(self.context_norm(cf))
         q = q.reshape(b, self.heads, q.shape[-1], -1)
@@ -185,6 +257,7 @@ class DiffusersAttentionND(nn.Module):
         self.attention = QKVAttention(efficient_attn=use_efficient_attn, dropout=dropout)
         self.dropout = dropout
         self._cache = ParamCache()
+        self._kv = _ContextKV()
 
     def forward(self, hidden_states: torch.Tensor, context: torch.Tensor | None = None,
                 upsample_out: bool = False) -> torch.Tensor:
@@ -195,9 +268,13 @@ class DiffusersAttentionND(nn.Module):
         if self.context_dim is not None:
             if context is None:
                 raise ValueError("DiffusersAttentionND cross-attention requires a non-empty context tensor.")
-            out_of_scope("DiffusersAttentionND cross-attention")
-            y = self._eager(hidden_states.float(), context.float())
-            return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
+            if (len(spatial) != 2 or c % 8 or self.head_dim not in (8, 16, 32, 64) or self.context_dim > CONTEXT_DIM_MAX
+                    or (self.training and self.dropout > 0) or not hidden_states.is_cuda):
+                out_of_scope(f"DiffusersAttentionND cross-attention(spatial={tuple(spatial)}, head_dim={self.head_dim}, "
+                             f"context_dim={self.context_dim})")
+                y = self._eager(hidden_states.float(), context.float())
+                return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
+            return self._cross(hidden_states, context, upsample_out)
         if len(spatial) != 2 or c % 8 or self.head_dim not in (8, 16, 32, 64) or (self.training and self.dropout > 0):
             out_of_scope(f"DiffusersAttentionND(spatial={tuple(spatial)}, head_dim={self.head_dim})")
             y = self._eager(hidden_states.float(), None)
@@ -226,6 +303,41 @@ class DiffusersAttentionND(nn.Module):
                       o_strides=(t * c, hd, c))
         return ops.conv2d([att], wout, bias=f32(self.to_out[0].bias), residual=x, want_stats=not upsample_out,
                           upsample_out=upsample_out)
+
+    def _cross(self, hidden_states: torch.Tensor, context: torch.Tensor, upsample_out: bool) -> torch.Tensor:
+        """`attention.py:232-274` with `context_dim`: q from the image tokens, k/v from the normalised context."""
+        b, c, hh, ww = hidden_states.shape
+        x = ops.to_nhwc_bf16(hidden_states)
+        t, hd = hh * ww, self.head_dim
+        gn = self.group_norm
+        n = ops.group_norm([x], gn.num_groups, gn.eps, f32(gn.weight), f32(gn.bias), silu=False)
+        wq = self._cache.get("q", [self.to_q.weight], lambda: ops.pack_conv_weight([(self.to_q.weight, 0, c)]))
+        wout = self._cache.get("out", [self.to_out[0].weight],
+                               lambda: ops.pack_conv_weight([(self.to_out[0].weight, 0, c)]))
+        q = ops.conv2d([n], wq, bias=f32(self.to_q.bias))                                # NHWC == [b][T][C]
+        kv = self.precompute_context(context)                                            # [b][Tc][2C]: K | V
+        tc = kv.shape[1]
+        att = ops.empty_nhwc(b, c, hh, ww, x.device)
+        kvf = kv.view(-1)
+        ops.attention(q.permute(0, 2, 3, 1).reshape(-1), kvf, kvf[c:], att.permute(0, 2, 3, 1).reshape(-1), batch=b,
+                      heads=self.heads, tq=t, tk=tc, head_dim=hd, q_strides=(t * c, hd, c),
+                      kv_strides=(tc * 2 * c, hd, 2 * c), o_strides=(t * c, hd, c))
+        return ops.conv2d([att], wout, bias=f32(self.to_out[0].bias), residual=x, want_stats=not upsample_out,
+                          upsample_out=upsample_out)
+
+    def precompute_context(self, context: torch.Tensor) -> torch.Tensor:
+        """Keys/values of `context`, token-major (b, Tc, 2C); cached per context object / parameter version."""
+        cn = self.context_norm
+        cf = context_tokens(context, self.context_dim)
+
+        def build_kv():
+            w = torch.cat([self.to_k.weight, self.to_v.weight], 0).detach().float().contiguous()
+            bias = torch.cat([self.to_k.bias, self.to_v.bias], 0).detach().float().contiguous()
+            return ops.context_kv(cf, f32(cn.weight), f32(cn.bias), w, bias, groups=cn.num_groups, eps=cn.eps,
+                                  channel_major=False)
+
+        return self._kv.get(context, [self.to_k.weight, self.to_k.bias, self.to_v.weight, self.to_v.bias, cn.weight,
+                                      cn.bias], build_kv)
 
     def _eager(self, hidden_states, context):
         b, c = hidden_states.shape[:2]

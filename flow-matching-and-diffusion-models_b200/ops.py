@@ -466,6 +466,27 @@ def attention(q, k, v, out, *, batch, heads, tq, tk, head_dim, q_strides, kv_str
     return out
 
 
+def context_kv(ctx: torch.Tensor, gamma, beta, weight, bias, *, groups: int, eps: float,
+               channel_major: bool) -> torch.Tensor:
+    """GroupNorm over the context tokens + key/value projection: ctx fp32 [B][Cc][Tc] -> bf16 [B][Tc][O]
+    (or [B][O][Tc] when channel_major); weight fp32 [O][Cc]."""
+    lib = _lib.lib()
+    require_cuda(ctx, "context_kv")
+    ctx = ctx.to(torch.float32).contiguous()
+    b, cc, tc = ctx.shape
+    o = weight.shape[0]
+    assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.shape[1] == cc
+    out = torch.empty((b, o, tc) if channel_major else (b, tc, o), dtype=BF16, device=ctx.device)
+    ws = torch.empty((b, groups, 2), dtype=torch.float32, device=ctx.device)
+    _lib.check(
+        lib.fm_context_kv_bf16(ctx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), weight.data_ptr(), _ptr(bias),
+                               ws.data_ptr(), out.data_ptr(), b, cc, tc, o, int(groups), float(eps),
+                               int(bool(channel_major)), _stream()),
+        "context_kv",
+    )
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------
 # time embedding path
 # --------------------------------------------------------------------------------------------------------------

@@ -128,11 +128,14 @@ class GraphSampler:
     The sampler state x (fp32), the conditioning, the per-run coefficient table, the per-run timestep table and the
     int32 step cursor all live in static device buffers; nothing crosses the host between steps."""
 
-    def __init__(self, model: BaseUNetND, scheduler: _SchedulerBase, shape, device, cond_shape=None):
+    def __init__(self, model: BaseUNetND, scheduler: _SchedulerBase, shape, device, cond_shape=None, ctx_shape=None):
         self.model, self.scheduler = model, scheduler
         self.shape, self.device = tuple(shape), device
         self.x = torch.zeros(self.shape, dtype=torch.float32, device=device)
         self.cond = None if cond_shape is None else torch.zeros(cond_shape, dtype=torch.float32, device=device)
+        # conditioning: "attention": the cross-attention context lives in a static buffer; its keys/values are
+        # (re)computed in place by the attention modules before the replays (`precompute_context`), never per step
+        self.ctx = None if ctx_shape is None else torch.zeros(ctx_shape, dtype=torch.float32, device=device)
         self.cursor = torch.zeros(1, dtype=torch.int32, device=device)
         self.state = scheduler.new_state(self.x)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -142,7 +145,8 @@ class GraphSampler:
         self.launches_per_step = 0
 
     def _one_step(self):
-        pred = self.model(self.x, None, context=self.cond, t_table=self.tvals, step_dev=self.cursor)
+        pred = self.model(self.x, None, context=self.cond, context_ca=self.ctx, t_table=self.tvals,
+                          step_dev=self.cursor)
         self.scheduler.step_kernel(self.x, self.x, pred, self.coef, step_dev=self.cursor, state=self.state)
         ops.counter_add(self.cursor, 1)
 
@@ -180,11 +184,17 @@ class GraphSampler:
             for k, v in saved_state.items():
                 self.state[k].copy_(v)
 
-    def run(self, init: torch.Tensor, cond: Optional[torch.Tensor], timesteps: torch.Tensor) -> torch.Tensor:
+    def run(self, init: torch.Tensor, cond: Optional[torch.Tensor], timesteps: torch.Tensor,
+            ctx: Optional[torch.Tensor] = None) -> torch.Tensor:
         n = self._load_plan(timesteps)
         self.x.copy_(init.to(device=self.device, dtype=torch.float32))
         if self.cond is not None:
             self.cond.copy_(cond.to(device=self.device, dtype=torch.float32))
+        if self.ctx is not None:
+            self.ctx.copy_(ctx.to(device=self.device, dtype=torch.float32))
+            for m in self.model.modules():
+                if hasattr(m, "precompute_context"):
+                    m.precompute_context(self.ctx)
         if self.state is not None:
             for v in self.state.values():
                 v.zero_()
@@ -200,13 +210,14 @@ class GraphSampler:
 _GRAPH_CACHE: Dict[tuple, GraphSampler] = {}
 
 
-def _graph_sampler(model, scheduler, shape, device, cond_shape) -> GraphSampler:
-    key = (id(model), id(scheduler), tuple(shape), str(device), None if cond_shape is None else tuple(cond_shape))
+def _graph_sampler(model, scheduler, shape, device, cond_shape, ctx_shape=None) -> GraphSampler:
+    key = (id(model), id(scheduler), tuple(shape), str(device), None if cond_shape is None else tuple(cond_shape),
+           None if ctx_shape is None else tuple(ctx_shape))
     gs = _GRAPH_CACHE.get(key)
     if gs is None:
         if len(_GRAPH_CACHE) >= 2:
             _GRAPH_CACHE.clear()
-        gs = GraphSampler(model, scheduler, shape, device, cond_shape)
+        gs = GraphSampler(model, scheduler, shape, device, cond_shape, ctx_shape)
         _GRAPH_CACHE[key] = gs
     return gs
 
@@ -246,12 +257,13 @@ def sample_with_scheduler(model: torch.nn.Module, scheduler, num_inference_steps
     concat = conditioning_mode == "concatenate" and cond is not None
 
     graphable = (use_cuda_graph and device.type == "cuda" and isinstance(model, BaseUNetND)
-                 and isinstance(scheduler, _SchedulerBase) and attention_ctx is None and not model.training)
+                 and isinstance(scheduler, _SchedulerBase) and not model.training)
     if graphable:
-        gs = _graph_sampler(model, scheduler, current.shape, device, cond.shape if concat else None)
+        gs = _graph_sampler(model, scheduler, current.shape, device, cond.shape if concat else None,
+                            None if attention_ctx is None else attention_ctx.shape)
         sync_if_cuda(device)
         t0 = time.perf_counter()
-        out = gs.run(current, cond if concat else None, timesteps)
+        out = gs.run(current, cond if concat else None, timesteps, ctx=attention_ctx)
         sync_if_cuda(device)
         if timing is not None:
             timing["model_seconds"] = timing.get("model_seconds", 0.0) + (time.perf_counter() - t0)

@@ -193,6 +193,14 @@ int fm_timestep_embedding_f32(const float* t, const float* t_table, const int32_
 int fm_linear_f32(const float* x, const float* W, const float* bias, const float* bias2, float* y, int32_t B,
                   int32_t I, int32_t O, int32_t silu_in, int32_t silu_out, fm_stream_t stream);
 
+/* Cross-attention context path (attention.py:149-165, 232-262): GroupNorm over the context tokens and
+ * the key/value projection in one pass.  ctx fp32 [B][Cc][Tc] (Cc <= 16), gamma/beta fp32 [Cc], W fp32 [O][Cc] (the
+ * concatenated to_k|to_v or kv_proj weight), bias fp32 [O] or NULL, stats_ws fp32 [B][groups][2].
+ * out bf16: [B][Tc][O] (channel_major = 0) or [B][O][Tc] (channel_major = 1, SpatialCrossAttention's raw reshape). */
+int fm_context_kv_bf16(const float* ctx, const float* gamma, const float* beta, const float* W, const float* bias,
+                       float* stats_ws, void* out, int32_t B, int32_t Cc, int32_t Tc, int32_t O, int32_t groups,
+                       float eps, int32_t channel_major, fm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K4: one fused elementwise kernel per sampler step (fp32 state, round-to-nearest mul/add, no FMA contraction).
  * Replaces diffusers' Scheduler.step called at src/pipelines/utils.py:218.  Coefficients are precomputed on the

@@ -34,6 +34,42 @@ CASES = {
 }
 
 
+# conditioning: "attention" (SURVEY.md §8f N4): cross-attention blocks over a latent context (B, 4, h, w)
+CA_CASES = {
+    "ca_diffusers_nd": dict(cfg={"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layers_per_block": 1,
+                                 "block_out_channels": [64, 128], "cross_attention_dim": 4,
+                                 "down_block_types": ["DownBlock2D", "CrossAttnDownBlock2D"],
+                                 "mid_block_type": "UNetMidBlock2DCrossAttn",
+                                 "up_block_types": ["CrossAttnUpBlock2D", "UpBlock2D"]}, hw=16, B=2, ctx_hw=8),
+    "ca_efficient_nd": dict(cfg={"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1, "num_res_blocks": 1,
+                                 "channel_mult": [1, 2], "model_channels": 64, "block_out_channels": [64, 128],
+                                 "attention_resolutions": [2], "cross_attention_resolutions": [2],
+                                 "cross_attention_in_middle": True, "cross_attention_dim": 4,
+                                 "use_linear_attn": False}, hw=16, B=2, ctx_hw=8),
+}
+
+
+def main_ca():
+    for name, c in CA_CASES.items():
+        cfg = c["cfg"]
+        torch.manual_seed(0)
+        model = DiffusionUNetFactory().build(cfg, "attention", 1).eval()
+        keys = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+        with open(os.path.join(GOLD, f"state_keys_{name}.json"), "w") as f:
+            json.dump({"cfg": cfg, "conditioning": "attention", "keys": keys}, f)
+        seed = 13
+        model.load_state_dict(reinit_state_dict(model.state_dict(), seed))
+        g = torch.Generator().manual_seed(77)
+        x = torch.randn(c["B"], 1, c["hw"], c["hw"], generator=g)
+        ctx = torch.randn(c["B"], 4, c["ctx_hw"], c["ctx_hw"], generator=g)
+        t = torch.tensor([700.0, 12.0][: c["B"]])
+        with torch.no_grad():
+            out = model(x, t, context_ca=ctx)
+        torch.save({"cfg": cfg, "conditioning": "attention", "seed": seed, "x": x, "t": t, "context": None,
+                    "context_ca": ctx, "out": out}, os.path.join(GOLD, f"denoiser_{name}.pt"))
+        print(name, tuple(out.shape), float(out.abs().max()), len(keys))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     for name, c in CASES.items():
@@ -58,4 +94,6 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--ca-only" not in sys.argv:
+        main()
+    main_ca()

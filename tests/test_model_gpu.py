@@ -323,3 +323,87 @@ def test_ddpm_graph_sampler_statistics():
     # with eps = 0 and x_T = 0: x0_hat = x / sqrt(abar) (clipped), the chain stays zero-mean; the last step (t = 0,
     # sigma = 0) returns clip(x / sqrt(abar_0)), so the output is bounded by the clip range and not degenerate
     assert abs(float(a.mean())) < 0.05 and float(a.abs().max()) <= 1.0 + 1e-6 and float(a.std()) > 0.05
+
+
+CA_DIFFUSERS = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layers_per_block": 1,
+                "block_out_channels": [64, 128], "cross_attention_dim": 4,
+                "down_block_types": ["DownBlock2D", "CrossAttnDownBlock2D"], "mid_block_type": "UNetMidBlock2DCrossAttn",
+                "up_block_types": ["CrossAttnUpBlock2D", "UpBlock2D"]}
+CA_EFFICIENT = {"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1, "num_res_blocks": 1,
+                "channel_mult": [1, 2], "model_channels": 64, "block_out_channels": [64, 128],
+                "attention_resolutions": [2], "cross_attention_resolutions": [2], "cross_attention_in_middle": True,
+                "cross_attention_dim": 4, "use_linear_attn": False}
+
+
+@pytest.mark.parametrize("name,cfg", [("ca_diffusers_nd", CA_DIFFUSERS), ("ca_efficient_nd", CA_EFFICIENT)])
+def test_cross_attention_conditioning_parity(name, cfg):
+    """conditioning: "attention" (SURVEY 8f N4): cross-attention blocks over a latent context, against the oracle
+    (itself pinned to the reference's golden outputs for the same configs) and against the golden fixture directly."""
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+
+    model = DiffusionUNetFactory().build(cfg, "attention", 1)
+    sd = OD.reinit_state_dict(model.state_dict(), 13)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(31)
+    for hw, ctx_shape in ((32, (2, 4, 8, 8)), (64, (2, 4, 16, 16)), (32, (2, 4, 50)), (32, (2, 50, 4))):
+        x = torch.randn(2, 1, hw, hw, generator=g).to(DEV)
+        ctx = torch.randn(ctx_shape, generator=g).to(DEV)
+        t = torch.tensor([812.0, 33.0], device=DEV)
+        ref = OD.denoiser_forward(sdd, cfg, x, t, conditioning="attention", channels=1, context_ca=ctx)
+        with torch.no_grad():
+            out = model(x, t, context_ca=ctx)
+            again = model(x, t, context_ca=ctx)          # keys/values of the same context object come from the cache
+        assert out.shape == ref.shape and torch.equal(out, again)
+        assert rel_l2(out, ref) < 1.2e-2, (name, hw, ctx_shape, rel_l2(out, ref))
+        ctx.mul_(0.5)                                     # in-place change of the context invalidates the cache
+        ref2 = OD.denoiser_forward(sdd, cfg, x, t, conditioning="attention", channels=1, context_ca=ctx)
+        with torch.no_grad():
+            out2 = model(x, t, context_ca=ctx)
+        assert rel_l2(out2, ref2) < 1.2e-2 and rel_l2(out2, out) > 1e-3
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"denoiser_{name}.pt"),
+                      weights_only=False)
+    with torch.no_grad():
+        out = model(gold["x"].to(DEV), gold["t"].to(DEV), context_ca=gold["context_ca"].to(DEV))
+    assert rel_l2(out.cpu(), gold["out"]) < 1.2e-2
+
+
+def test_context_kv_kernel():
+    """GroupNorm over the context tokens + tiny-K projection, both output layouts, against torch fp32."""
+    from fmdm_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    for cc, tc, o, groups in ((4, 64, 256, 4), (4, 1000, 1024, 4), (8, 77, 512, 8), (16, 256, 96, 16), (6, 33, 64, 2)):
+        ctx = (torch.randn(3, cc, tc, generator=g) * 2 + 0.5).to(DEV)
+        gamma, beta = torch.rand(cc, generator=g).to(DEV) + 0.5, torch.randn(cc, generator=g).to(DEV)
+        w, bias = (torch.randn(o, cc, generator=g) * 0.3).to(DEV), torch.randn(o, generator=g).to(DEV)
+        ref = torch.nn.functional.linear(torch.nn.functional.group_norm(ctx, groups, gamma, beta, 1e-5).transpose(1, 2),
+                                         w, bias)                                     # [B][Tc][O]
+        tm = ops.context_kv(ctx, gamma, beta, w, bias, groups=groups, eps=1e-5, channel_major=False)
+        cm = ops.context_kv(ctx, gamma, beta, w, bias, groups=groups, eps=1e-5, channel_major=True)
+        assert tm.shape == (3, tc, o) and cm.shape == (3, o, tc)
+        assert rel_l2(tm, ref) < 4e-3 and rel_l2(cm, ref.transpose(1, 2)) < 4e-3
+
+
+def test_attention_conditioned_sampling_graph_matches_stepwise():
+    """conditioning: "attention" through `sample_with_scheduler`: the graph-replayed run (keys/values of the context
+    refreshed in place between runs) is bit-identical to the step-by-step run, for two different contexts in a row."""
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+    from fmdm_b200.pipelines.utils import build_scheduler, sample_with_scheduler
+
+    for cfg in (CA_DIFFUSERS, CA_EFFICIENT):
+        model = DiffusionUNetFactory().build(cfg, "attention", 1)
+        model.load_state_dict(OD.reinit_state_dict(model.state_dict(), 21))
+        model = model.to(DEV).eval()
+        sched, _ = build_scheduler({"name": "flow_match_euler", "params": {}}, {})
+        g = torch.Generator().manual_seed(3)
+        init = torch.randn(2, 1, 32, 32, generator=g).to(DEV)
+        for k in range(2):
+            ctx = (torch.randn(2, 4, 8, 8, generator=g) * (1.0 + k)).to(DEV)
+            a = sample_with_scheduler(model, sched, 6, tuple(init.shape), torch.device(DEV), conditioning_mode="attention",
+                                      conditioning_batch=ctx, latent_norm="standardize", init_sample=init)
+            b = sample_with_scheduler(model, sched, 6, tuple(init.shape), torch.device(DEV), conditioning_mode="attention",
+                                      conditioning_batch=ctx, latent_norm="standardize", init_sample=init,
+                                      use_cuda_graph=False)
+            assert torch.isfinite(a).all() and torch.equal(a, b), (cfg["unet_impl"], k, float((a - b).abs().max()))
