@@ -88,6 +88,10 @@ SIGNATURES = {
         C.c_int,
         [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32] + [_i64] * 9 + [_f32, _vp],
     ),
+    "fm_linear_attention_bf16": (
+        C.c_int,
+        [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32] + [_i64] * 9 + [_f32, _vp],
+    ),
     "fm_context_kv_bf16": (C.c_int, [_vp] * 7 + [_i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "fm_timestep_embedding_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _f32, _vp]),
     "fm_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -526,6 +526,123 @@ __global__ void __launch_bounds__(256) context_proj_kernel(const float* __restri
 }
 
 
+// =============================================================================================================
+// Linear attention (`attention.py:53-70` LinearQKVAttention; EfficientUNetND's default inside its levels):
+//   ks = softmax(k over tokens), qs = softmax(q over features), ctx = ks^T v / (sum_n ks + eps), out = qs ctx.
+// O(T * d^2): one CTA per (sample, head); the d x d context matrix lives in shared memory.  fp32 CUDA-core math.
+// =============================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(256) linear_attention_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+    __nv_bfloat16* __restrict__ out, int heads, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
+    int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float eps) {
+  constexpr int kLanes = 256 / HD;   // token lanes per feature column
+  constexpr int kChunk = 32;         // tokens staged per step of the context accumulation
+  constexpr int kPairs = HD * HD / 256 > 0 ? HD * HD / 256 : 1;
+  __shared__ float ctx[HD][HD + 1];
+  __shared__ float red[256];
+  __shared__ float cmax[HD], csum[HD], cden[HD];
+  __shared__ float sk[kChunk][HD], sv[kChunk][HD];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const __nv_bfloat16* kb = k + b * kv_sb + h * kv_sh;
+  const __nv_bfloat16* vb = v + b * kv_sb + h * kv_sh;
+  const __nv_bfloat16* qb = q + b * q_sb + h * q_sh;
+  __nv_bfloat16* ob = out + b * o_sb + h * o_sh;
+  const int d = threadIdx.x % HD, lane = threadIdx.x / HD;
+  // column (per-feature) max of k over the tokens
+  float m = -INFINITY;
+  for (int n = lane; n < Tk; n += kLanes) m = fmaxf(m, __bfloat162float(kb[n * kv_st + d]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < kLanes; ++l) m = fmaxf(m, red[l * HD + d]);
+    cmax[d] = m;
+  }
+  __syncthreads();
+  float s = 0.f;
+  const float cm = cmax[d];
+  for (int n = lane; n < Tk; n += kLanes) s += __expf(__bfloat162float(kb[n * kv_st + d]) - cm);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < kLanes; ++l) s += red[l * HD + d];
+    csum[d] = s;
+  }
+  __syncthreads();
+  // ctx[d][e] = sum_n ks[n][d] v[n][e]; den[d] = sum_n ks[n][d]
+  float acc[kPairs];
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) acc[j] = 0.f;
+  float den = 0.f;
+  for (int n0 = 0; n0 < Tk; n0 += kChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk * HD; i += 256) {
+      const int nn = i / HD, dd = i - nn * HD;
+      float kv_ = 0.f, vv = 0.f;
+      if (n0 + nn < Tk) {
+        kv_ = __expf(__bfloat162float(kb[(n0 + nn) * kv_st + dd]) - cmax[dd]) / csum[dd];
+        vv = __bfloat162float(vb[(n0 + nn) * kv_st + dd]);
+      }
+      sk[nn][dd] = kv_;
+      sv[nn][dd] = vv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) {
+      const int p = threadIdx.x + 256 * j;
+      if (p < HD * HD) {
+        const int dd = p / HD, ee = p - dd * HD;
+        float a = acc[j];
+#pragma unroll 8
+        for (int nn = 0; nn < kChunk; ++nn) a = fmaf(sk[nn][dd], sv[nn][ee], a);
+        acc[j] = a;
+      }
+    }
+    if (threadIdx.x < HD)
+      for (int nn = 0; nn < kChunk; ++nn) den += sk[nn][threadIdx.x];
+  }
+  if (threadIdx.x < HD) cden[threadIdx.x] = den + eps;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) {
+    const int p = threadIdx.x + 256 * j;
+    if (p < HD * HD) {
+      const int dd = p / HD, ee = p - dd * HD;
+      ctx[dd][ee] = acc[j] / cden[dd];
+    }
+  }
+  __syncthreads();
+  // out[n][e] = sum_d softmax_d(q[n])[d] ctx[d][e]
+  for (int n = threadIdx.x; n < Tq; n += 256) {
+    float qr[HD];
+    float qm = -INFINITY;
+#pragma unroll
+    for (int dd = 0; dd < HD; ++dd) {
+      qr[dd] = __bfloat162float(qb[n * q_st + dd]);
+      qm = fmaxf(qm, qr[dd]);
+    }
+    float qs = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < HD; ++dd) {
+      qr[dd] = __expf(qr[dd] - qm);
+      qs += qr[dd];
+    }
+    const float inv = 1.f / qs;
+    for (int e0 = 0; e0 < HD; e0 += 8) {
+      float o8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) {
+        const float w = qr[dd] * inv;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = fmaf(w, ctx[dd][e0 + e], o8[e]);
+      }
+      *reinterpret_cast<uint4*>(ob + n * o_st + e0) =
+          make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]), pack_bf16x2(o8[4], o8[5]),
+                     pack_bf16x2(o8[6], o8[7]));
+    }
+  }
+}
+
 }  // namespace fm
 
 using namespace fm;
@@ -584,5 +701,36 @@ extern "C" int fm_context_kv_bf16(const float* ctx, const float* gamma, const fl
     context_proj_kernel<0><<<grid, 256, 0, st>>>(ctx, stats_ws, gamma, beta, W, bias,
                                                  reinterpret_cast<__nv_bfloat16*>(out), Cc, Tc, O, groups);
   FM_LAUNCH_CHECK("context_proj_kernel");
+  return 0;
+}
+
+extern "C" int fm_linear_attention_bf16(const void* q, const void* k, const void* v, void* out, int32_t B,
+                                        int32_t heads, int32_t Tq, int32_t Tk, int32_t head_dim, int64_t q_sb,
+                                        int64_t q_sh, int64_t q_st, int64_t kv_sb, int64_t kv_sh, int64_t kv_st,
+                                        int64_t o_sb, int64_t o_sh, int64_t o_st, float eps, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(q && k && v && out, "linear_attention: null pointer");
+  FM_REQUIRE(B > 0 && heads > 0 && Tq > 0 && Tk > 0, "linear_attention: empty problem");
+  FM_REQUIRE((((uintptr_t)out) & 15) == 0 && ((o_sb | o_sh | o_st) & 7) == 0,
+             "linear_attention: output rows must be 16B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+#define FM_LIN(HD)                                                                                                  \
+  case HD:                                                                                                          \
+    linear_attention_kernel<HD><<<B * heads, 256, 0, st>>>(                                                         \
+        reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),                       \
+        reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), heads, Tq, Tk, q_sb, q_sh, \
+        q_st, kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, eps);                                                          \
+    break;
+  switch (head_dim) {
+    FM_LIN(8)
+    FM_LIN(16)
+    FM_LIN(32)
+    FM_LIN(64)
+    default:
+      set_error("linear_attention: head_dim=%d unsupported (8, 16, 32, 64)", head_dim);
+      return FM_ERR_UNSUPPORTED;
+  }
+#undef FM_LIN
+  FM_LAUNCH_CHECK("linear_attention_kernel");
   return 0;
 }

@@ -45,7 +45,8 @@ class QKVAttention(nn.Module):
 
 
 class LinearQKVAttention(nn.Module):
-    """Softmax-factorised linear attention (`attention.py:53-70`); not on any BASELINE path (out of scope)."""
+    """Softmax-factorised linear attention (`attention.py:53-70`), EfficientUNetND's default inside its levels
+    (SURVEY §8f N4): one small CUDA-core kernel per call (O(T d^2))."""
 
     def __init__(self, dropout: float = 0.0, eps: float = 1e-6):
         super().__init__()
@@ -53,11 +54,21 @@ class LinearQKVAttention(nn.Module):
         self.eps = eps
 
     def forward(self, q, k, v):
-        out_of_scope("LinearQKVAttention")
-        ks, qs = F.softmax(k.float(), dim=-2), F.softmax(q.float(), dim=-1)
-        ctx = torch.einsum("...nd,...ne->...de", ks, v.float())
-        ctx = ctx / (ks.sum(dim=-2).unsqueeze(-1) + self.eps)
-        return F.dropout(torch.einsum("...nd,...de->...ne", qs, ctx), p=self.dropout, training=self.training)
+        if q.dim() != 4 or (self.training and self.dropout > 0) or q.shape[-1] not in (8, 16, 32, 64) \
+                or v.shape[-1] != q.shape[-1] or not q.is_cuda:
+            out_of_scope(f"LinearQKVAttention on {tuple(q.shape)} (dropout={self.dropout})")
+            ks, qs = F.softmax(k.float(), dim=-2), F.softmax(q.float(), dim=-1)
+            ctx = torch.einsum("...nd,...ne->...de", ks, v.float())
+            ctx = ctx / (ks.sum(dim=-2).unsqueeze(-1) + self.eps)
+            return F.dropout(torch.einsum("...nd,...de->...ne", qs, ctx), p=self.dropout, training=self.training)
+        b, h, tq, d = q.shape
+        tk = k.shape[2]
+        q, k, v = [t.to(torch.bfloat16).contiguous() for t in (q, k, v)]
+        out = torch.empty((b, h, tq, d), dtype=torch.bfloat16, device=q.device)
+        ops.linear_attention(q, k, v, out, batch=b, heads=h, tq=tq, tk=tk, head_dim=d,
+                             q_strides=(h * tq * d, tq * d, d), kv_strides=(h * tk * d, tk * d, d),
+                             o_strides=(h * tq * d, tq * d, d), eps=self.eps)
+        return out
 
 
 def context_tokens(context: torch.Tensor, context_dim: int) -> torch.Tensor:
@@ -125,8 +136,8 @@ class SpatialSelfAttention(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         b, c, *spatial = x.shape
-        if self.use_linear or len(spatial) != 2 or c % 8 or self.dim_head not in (8, 16, 32, 64):
-            out_of_scope(f"SpatialSelfAttention(use_linear={self.use_linear}, spatial={spatial}, dim_head={self.dim_head})")
+        if len(spatial) != 2 or c % 8 or self.dim_head not in (8, 16, 32, 64):
+            out_of_scope(f"SpatialSelfAttention(spatial={spatial}, dim_head={self.dim_head})")
             return self._eager(x.float())
         x = ops.to_nhwc_bf16(x)
         hh, ww = spatial
@@ -142,9 +153,10 @@ class SpatialSelfAttention(nn.Module):
         qkv_cm = ops.transpose_bf16(qkv.permute(0, 2, 3, 1).reshape(b, t, 3 * inner))  # [b][3*inner][T]
         att = torch.empty((b, nh, t, dh), dtype=torch.bfloat16, device=x.device)
         flat = qkv_cm.view(-1)
-        ops.attention(flat, flat[dh:], flat[2 * dh:], att, batch=b, heads=nh, tq=t, tk=t, head_dim=dh,
-                      q_strides=(3 * inner * t, t * 3 * dh, 3 * dh), kv_strides=(3 * inner * t, t * 3 * dh, 3 * dh),
-                      o_strides=(nh * t * dh, t * dh, dh))
+        kernel = ops.linear_attention if self.use_linear else ops.attention
+        kernel(flat, flat[dh:], flat[2 * dh:], att, batch=b, heads=nh, tq=t, tk=t, head_dim=dh,
+               q_strides=(3 * inner * t, t * 3 * dh, 3 * dh), kv_strides=(3 * inner * t, t * 3 * dh, 3 * dh),
+               o_strides=(nh * t * dh, t * dh, dh))
         # raw reshape (b, heads, T, dh) -> (b, inner, T), then back to NHWC for the projection GEMM
         h_tc = ops.transpose_bf16(att.view(b, inner, t))                          # [b][T][inner]
         h_nhwc = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
@@ -184,10 +196,10 @@ class SpatialCrossAttention(ContextBlock):
         if context is None:
             raise ValueError("SpatialCrossAttention requires a non-empty context tensor.")
         b, c, *spatial = x.shape
-        if (self.use_linear or len(spatial) != 2 or c % 8 or self.dim_head not in (8, 16, 32, 64)
+        if (len(spatial) != 2 or c % 8 or self.dim_head not in (8, 16, 32, 64)
                 or self.context_dim > CONTEXT_DIM_MAX or not x.is_cuda):
-            out_of_scope(f"SpatialCrossAttention(use_linear={self.use_linear}, spatial={spatial}, "
-                         f"dim_head={self.dim_head}, context_dim={self.context_dim})")
+            out_of_scope(f"SpatialCrossAttention(spatial={spatial}, dim_head={self.dim_head}, "
+                         f"context_dim={self.context_dim})")
             return self._eager(x.float(), context.float())
         x = ops.to_nhwc_bf16(x)
         hh, ww = spatial
@@ -205,9 +217,10 @@ class SpatialCrossAttention(ContextBlock):
         # the reference's raw reshapes: q (b, inner, T) -> (b, heads, T, dh); kv (b, 2*inner, Tc) -> (b, heads, Tc, 2*dh)
         att = torch.empty((b, nh, t, dh), dtype=torch.bfloat16, device=x.device)
         kvf = kv_cm.view(-1)
-        ops.attention(q_cm.view(-1), kvf, kvf[dh:], att, batch=b, heads=nh, tq=t, tk=tc, head_dim=dh,
-                      q_strides=(inner * t, t * dh, dh), kv_strides=(2 * inner * tc, tc * 2 * dh, 2 * dh),
-                      o_strides=(nh * t * dh, t * dh, dh))
+        kernel = ops.linear_attention if self.use_linear else ops.attention
+        kernel(q_cm.view(-1), kvf, kvf[dh:], att, batch=b, heads=nh, tq=t, tk=tc, head_dim=dh,
+               q_strides=(inner * t, t * dh, dh), kv_strides=(2 * inner * tc, tc * 2 * dh, 2 * dh),
+               o_strides=(nh * t * dh, t * dh, dh))
         h_tc = ops.transpose_bf16(att.view(b, inner, t))                                # [b][T][inner]
         h_nhwc = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
         return ops.conv2d([h_nhwc], wo, bias=f32(self.proj_out.bias), residual=x, want_stats=True)

@@ -466,6 +466,23 @@ def attention(q, k, v, out, *, batch, heads, tq, tk, head_dim, q_strides, kv_str
     return out
 
 
+def linear_attention(q, k, v, out, *, batch, heads, tq, tk, head_dim, q_strides, kv_strides, o_strides, eps=1e-6):
+    """LinearQKVAttention on strided bf16 operands (same conventions as `attention`)."""
+    lib = _lib.lib()
+    for t in (q, k, v, out):
+        require_cuda(t, "linear_attention")
+        assert t.dtype == BF16
+    _lib.check(
+        lib.fm_linear_attention_bf16(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), batch, heads, tq, tk, head_dim,
+            *[int(s) for s in q_strides], *[int(s) for s in kv_strides], *[int(s) for s in o_strides], float(eps),
+            _stream(),
+        ),
+        "linear_attention",
+    )
+    return out
+
+
 def context_kv(ctx: torch.Tensor, gamma, beta, weight, bias, *, groups: int, eps: float,
                channel_major: bool) -> torch.Tensor:
     """GroupNorm over the context tokens + key/value projection: ctx fp32 [B][Cc][Tc] -> bf16 [B][Tc][O]

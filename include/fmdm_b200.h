@@ -193,6 +193,12 @@ int fm_timestep_embedding_f32(const float* t, const float* t_table, const int32_
 int fm_linear_f32(const float* x, const float* W, const float* bias, const float* bias2, float* y, int32_t B,
                   int32_t I, int32_t O, int32_t silu_in, int32_t silu_out, fm_stream_t stream);
 
+/* Linear attention (attention.py:53-70 LinearQKVAttention): out = softmax_features(q) (softmax_tokens(k)^T v / (sum_tokens
+ * softmax_tokens(k) + eps)); same strided bf16 operands as fm_attention_bf16, no 1/sqrt(d) scaling. */
+int fm_linear_attention_bf16(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t heads, int32_t Tq,
+                             int32_t Tk, int32_t head_dim, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
+                             int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float eps,
+                             fm_stream_t stream);
 /* Cross-attention context path (attention.py:149-165, 232-262): GroupNorm over the context tokens and
  * the key/value projection in one pass.  ctx fp32 [B][Cc][Tc] (Cc <= 16), gamma/beta fp32 [Cc], W fp32 [O][Cc] (the
  * concatenated to_k|to_v or kv_proj weight), bias fp32 [O] or NULL, stats_ws fp32 [B][groups][2].

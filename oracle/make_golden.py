@@ -46,6 +46,12 @@ CA_CASES = {
                                  "attention_resolutions": [2], "cross_attention_resolutions": [2],
                                  "cross_attention_in_middle": True, "cross_attention_dim": 4,
                                  "use_linear_attn": False}, hw=16, B=2, ctx_hw=8),
+    # EfficientUNetND's default: linear attention inside the levels, softmax in the middle block
+    "ca_efficient_nd_linear": dict(cfg={"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1,
+                                        "num_res_blocks": 1, "channel_mult": [1, 2], "model_channels": 64,
+                                        "block_out_channels": [64, 128], "attention_resolutions": [1, 2],
+                                        "cross_attention_resolutions": [2], "cross_attention_in_middle": True,
+                                        "cross_attention_dim": 4}, hw=16, B=2, ctx_hw=8),
 }
 
 

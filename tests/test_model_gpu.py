@@ -335,7 +335,30 @@ CA_EFFICIENT = {"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1
                 "cross_attention_dim": 4, "use_linear_attn": False}
 
 
-@pytest.mark.parametrize("name,cfg", [("ca_diffusers_nd", CA_DIFFUSERS), ("ca_efficient_nd", CA_EFFICIENT)])
+CA_EFFICIENT_LINEAR = {"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1, "num_res_blocks": 1,
+                       "channel_mult": [1, 2], "model_channels": 64, "block_out_channels": [64, 128],
+                       "attention_resolutions": [1, 2], "cross_attention_resolutions": [2],
+                       "cross_attention_in_middle": True, "cross_attention_dim": 4}
+
+
+def test_linear_attention_kernel():
+    """LinearQKVAttention (`attention.py:53-70`) against its fp32 definition, self- and cross-shaped."""
+    from fmdm_b200.nn.blocks.attention import LinearQKVAttention
+
+    g = torch.Generator().manual_seed(9)
+    att = LinearQKVAttention()
+    for b, h, tq, tk, d in ((2, 4, 64, 64, 64), (1, 4, 256, 100, 64), (3, 2, 33, 77, 8), (2, 8, 128, 128, 32),
+                            (1, 1, 300, 40, 16)):
+        q = torch.randn(b, h, tq, d, generator=g).to(DEV).to(torch.bfloat16)
+        k = torch.randn(b, h, tk, d, generator=g).to(DEV).to(torch.bfloat16)
+        v = torch.randn(b, h, tk, d, generator=g).to(DEV).to(torch.bfloat16)
+        out = att(q, k, v)
+        ref = OD._linear_qkv_attention(q.float(), k.float(), v.float())
+        assert out.shape == ref.shape and rel_l2(out, ref) < 6e-3, (b, h, tq, tk, d, rel_l2(out, ref))
+
+
+@pytest.mark.parametrize("name,cfg", [("ca_diffusers_nd", CA_DIFFUSERS), ("ca_efficient_nd", CA_EFFICIENT),
+                                      ("ca_efficient_nd_linear", CA_EFFICIENT_LINEAR)])
 def test_cross_attention_conditioning_parity(name, cfg):
     """conditioning: "attention" (SURVEY 8f N4): cross-attention blocks over a latent context, against the oracle
     (itself pinned to the reference's golden outputs for the same configs) and against the golden fixture directly."""
