@@ -145,8 +145,8 @@ class GraphSampler:
         self.launches_per_step = 0
 
     def _one_step(self):
-        pred = self.model(self.x, None, context=self.cond, context_ca=self.ctx, t_table=self.tvals,
-                          step_dev=self.cursor)
+        kw = {} if self.ctx is None else {"context_ca": self.ctx}
+        pred = self.model(self.x, None, context=self.cond, t_table=self.tvals, step_dev=self.cursor, **kw)
         self.scheduler.step_kernel(self.x, self.x, pred, self.coef, step_dev=self.cursor, state=self.state)
         ops.counter_add(self.cursor, 1)
 
