@@ -47,6 +47,46 @@ def run(name, cfg, cond, B, hw, sched_name, steps, reps=3, flop_per_sample_fwd=N
     print(json.dumps(line), flush=True)
 
 
+def run_attention_configs(B=16, hw=256, steps=50, reps=2):
+    """the reference's `configs/LDCT/PixelAttention/*` (conditioning: "attention", latent context 4x32x32)
+    through `sample_with_scheduler`: EfficientUNetND with linear self-/cross-attention at 16x16 and 8x8 and a softmax
+    cross-attention middle block; flow-match Euler and the default `ddpm` ancestral sampler (50-step strided)."""
+    import os
+
+    cfg_path = "/root/reference/configs/LDCT/PixelAttention/LDCT_flow_matching_attention_compvis.json"
+    if os.path.exists(cfg_path):
+        cfg = json.load(open(cfg_path))["model"]["unet"]
+    else:  # the same dictionary, for the GPU box where the reference tree does not exist
+        cfg = {"unet_impl": "efficient_nd", "sample_size": 256, "in_channels": 1, "out_channels": 1,
+               "layers_per_block": 2, "block_out_channels": [128, 128, 256, 256, 512, 512],
+               "attention_resolutions": [16, 32], "cross_attention_resolutions": [16], "cross_attention_dim": 4,
+               "cross_attention_in_middle": True, "emb_activation_before_proj": False}
+    torch.manual_seed(0)
+    m = DiffusionUNetFactory().build(cfg, "attention", 1).to(DEV).eval()
+    for p in m.parameters():
+        if float(p.abs().sum()) == 0:
+            torch.nn.init.normal_(p, 0, 0.02)
+    x = torch.randn(B, 1, hw, hw, device=DEV)
+    ctx = torch.randn(B, 4, 32, 32, device=DEV)
+    for sched_name in ("flow_match_euler", "ddpm"):
+        params = {"beta_start": 1e-4, "beta_end": 0.02} if sched_name != "flow_match_euler" else {}
+        sch, _ = build_scheduler({"name": sched_name, "params": params}, {})
+        kw = dict(conditioning_mode="attention", conditioning_batch=ctx, latent_norm="standardize", init_sample=x)
+        with torch.no_grad():
+            for _ in range(2):
+                out = sample_with_scheduler(m, sch, steps, tuple(x.shape), DEV, **kw)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = sample_with_scheduler(m, sch, steps, tuple(x.shape), DEV, **kw)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+        assert torch.isfinite(out).all()
+        print(json.dumps({"config": "PixelAttention compvis (conditioning: attention, context 4x32x32), LDCT 256x256",
+                          "model": type(m).__name__, "batch": B, "scheduler": sched_name, "steps": steps,
+                          "s_per_run": round(dt, 4), "samples_per_s": round(B / dt, 2)}), flush=True)
+
+
 def run_latent_config(B=128, lat=64, steps=50, reps=2):
     """configs[2]: latent flow matching on AutoencoderKL f=8 latents (64x64x4, concat conditioning latents -> 8 input
     channels), 50 Euler steps, then KL decode to 512x512."""
@@ -90,6 +130,9 @@ def run_latent_config(B=128, lat=64, steps=50, reps=2):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "latent":
         run_latent_config()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "attention":
+        run_attention_configs()
         sys.exit(0)
     run("configs[0] MNIST 28x28 uncond flow-matching, 50 Euler", MNIST, None, 64, 28, "flow_match_euler", 50,
         flop_per_sample_fwd=2.3969e9)
