@@ -524,11 +524,15 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
                                                             const uint4* __restrict__ x1, const uint4* __restrict__ da,
                                                             const float* __restrict__ tab, uint4* __restrict__ dx0,
                                                             uint4* __restrict__ dx1, int64_t HW, int C8, int lanes,
-                                                            int rows_per_blk, int silu) {
-  const int b = blockIdx.y, blk = blockIdx.x;
+                                                            int rows_per_blk, int silu, float* __restrict__ colpart) {
+  // colpart (optional): per-block column sums of dx, [B][nblk][C] -- the bias / time-embedding-add gradient of the conv
+  // that produced x, so that conv's backward needs no column-sum pass over dx
+  extern __shared__ float cred[];  // [lanes][C8*8], only when colpart != NULL
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
-  if (lane >= lanes) return;
   const int C = C8 * 8;
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < lanes) {
   float ca[8], cb[8], cA[8], cP[8], cQ[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -573,53 +577,85 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
         const float o0 = fmaf(cA[2 * k], d0, fmaf(cQ[2 * k], xf.x, cP[2 * k]));
         const float o1 = fmaf(cA[2 * k + 1], d1, fmaf(cQ[2 * k + 1], xf.y, cP[2 * k + 1]));
         ow[k] = pack_bf16x2(o0, o1);
+        cs[2 * k] += o0;
+        cs[2 * k + 1] += o1;
       }
       os[ru * xC8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
+  }
+  }
+  if (colpart == nullptr) return;
+  if (lane < lanes) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cred[(lane * C8 + c8) * 8 + k] = cs[k];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += cred[l * C + idx];
+    colpart[((int64_t)b * nblk + blk) * C + idx] = acc;
   }
 }
 
 // =============================================================================================================
 // attention backward: one CTA per (sample, head); Q, K, V, dO staged in shared memory as bf16, math in fp32
 // =============================================================================================================
-// one row of HD bf16 values from shared memory as fp32 (16-byte vector loads)
-template <int HD>
-__device__ __forceinline__ void att_row(const __nv_bfloat16* row, float* out) {
+// one row of HD staged values as fp32 (16-byte vector loads); the tiles are staged as fp32 when they fit in shared
+// memory (no per-use bf16 unpacking in the T^2 loops), else as bf16
+template <int HD, typename ST>
+__device__ __forceinline__ void att_row(const ST* row, float* out) {
+  if constexpr (sizeof(ST) == 4) {
 #pragma unroll
-  for (int c = 0; c < HD / 8; ++c) {
-    const uint4 v = reinterpret_cast<const uint4*>(row)[c];
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 v = reinterpret_cast<const float4*>(row)[c];
+      out[c * 4] = v.x, out[c * 4 + 1] = v.y, out[c * 4 + 2] = v.z, out[c * 4 + 3] = v.w;
+    }
+  } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16x2(w[k]);
-      out[c * 8 + 2 * k] = f.x;
-      out[c * 8 + 2 * k + 1] = f.y;
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 v = reinterpret_cast<const uint4*>(row)[c];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(w[k]);
+        out[c * 8 + 2 * k] = f.x;
+        out[c * 8 + 2 * k + 1] = f.y;
+      }
     }
   }
 }
+__device__ __forceinline__ void att_stage8(float* dst, const __nv_bfloat16* src) {
+  const uint4 v = *reinterpret_cast<const uint4*>(src);
+  const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+  reinterpret_cast<float4*>(dst)[0] = make_float4(a.x, a.y, b.x, b.y);
+  reinterpret_cast<float4*>(dst)[1] = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ void att_stage8(__nv_bfloat16* dst, const __nv_bfloat16* src) {
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+}
 
-template <int HD>
+template <int HD, typename ST>
 __global__ void __launch_bounds__(256) attention_bwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dq,
     __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int heads, int T, int64_t qs_b, int64_t qs_h,
     int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale) {
   extern __shared__ __align__(16) uint8_t smem_att[];
-  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_att);
-  __nv_bfloat16* sk = sq + (size_t)T * HD;
-  __nv_bfloat16* sv = sk + (size_t)T * HD;
-  __nv_bfloat16* sdo = sv + (size_t)T * HD;
+  ST* sq = reinterpret_cast<ST*>(smem_att);
+  ST* sk = sq + (size_t)T * HD;
+  ST* sv = sk + (size_t)T * HD;
+  ST* sdo = sv + (size_t)T * HD;
   float* lse = reinterpret_cast<float*>(sdo + (size_t)T * HD);
   float* dsum = lse + T;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int64_t qoff = b * qs_b + h * qs_h, ooff = b * os_b + h * os_h;
-  // rows of HD contiguous bf16 (16-byte aligned by the caller's strides): stage with 16-byte copies
+  // rows of HD contiguous bf16 (16-byte aligned by the caller's strides)
   for (int idx = threadIdx.x; idx < T * (HD / 8); idx += blockDim.x) {
     const int t = idx / (HD / 8), c = idx - t * (HD / 8);
-    reinterpret_cast<uint4*>(sq)[idx] = *reinterpret_cast<const uint4*>(q + qoff + t * qs_t + c * 8);
-    reinterpret_cast<uint4*>(sk)[idx] = *reinterpret_cast<const uint4*>(k + qoff + t * qs_t + c * 8);
-    reinterpret_cast<uint4*>(sv)[idx] = *reinterpret_cast<const uint4*>(v + qoff + t * qs_t + c * 8);
-    reinterpret_cast<uint4*>(sdo)[idx] = *reinterpret_cast<const uint4*>(dout + ooff + t * os_t + c * 8);
+    att_stage8(sq + idx * 8, q + qoff + t * qs_t + c * 8);
+    att_stage8(sk + idx * 8, k + qoff + t * qs_t + c * 8);
+    att_stage8(sv + idx * 8, v + qoff + t * qs_t + c * 8);
+    att_stage8(sdo + idx * 8, dout + ooff + t * os_t + c * 8);
   }
   __syncthreads();
   // phase 1+2: per query row i: log-sum-exp, D_i = dO_i . O_i, then dQ_i
@@ -1093,17 +1129,34 @@ static int gn_bwd_blocks(int64_t HW, int B) {
   return nblk;
 }
 
+extern "C" int32_t fm_groupnorm_bwd_blocks(int32_t B, int64_t HW) {
+  if (ensure_device()) return 0;
+  return gn_bwd_blocks(HW, B);
+}
+
+/* out[b][c] = sum_blk partials[b][blk][c]; total (or NULL)[c] = sum_b out[b][c]  (second stage of fm_colsum_bf16, also
+ * fed by fm_groupnorm_bwd_bf16's dx_colsum_partials) */
+extern "C" int fm_colsum_finish_f32(const float* partials, float* out, float* total, int32_t B, int32_t nblk, int32_t C,
+                                    fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(partials && out && B > 0 && nblk > 0 && C > 0, "colsum_finish: bad argument");
+  colsum_final_kernel<<<(C + 31) / 32, dim3(32, B < 32 ? B : 32), 0, (cudaStream_t)stream>>>(partials, out, total, B,
+                                                                                           nblk, C);
+  FM_LAUNCH_CHECK("colsum_final_kernel");
+  return 0;
+}
+
 extern "C" int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C) {
   if (ensure_device()) return 0;
-  /* table [B][C][8] + partials [B][nblk][2][C] + S [B][2][C] + dgb_part [B][2][C] */
-  return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 4LL * B * C;
+  /* table [B][C][8] + partials [B][nblk][2][C] + dgb_part [B][2][C] */
+  return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 2LL * B * C;
 }
 
 extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout,
                                      const float* stats, const float* gamma, const float* beta,
                                      const float* scale_shift, int64_t ss_stride, int32_t silu, int32_t B, int64_t HW,
                                      int32_t groups, float* workspace, void* dx0, void* dx1, float* dgamma_dbeta,
-                                     float* dscale_shift, fm_stream_t stream) {
+                                     float* dscale_shift, float* dx_colsum_partials, fm_stream_t stream) {
   const int32_t C = C0 + C1;
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x0 && dout && stats && gamma && beta && workspace && dx0 && dgamma_dbeta, "groupnorm_bwd: null pointer");
@@ -1116,8 +1169,7 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
   const int rows = (int)((HW + nblk - 1) / nblk);
   float* tab = workspace;
   float* part = tab + (int64_t)B * C * kGnTab;
-  float* S = part + (int64_t)B * nblk * 2 * C;
-  float* dgb = S + 2LL * B * C;
+  float* dgb = part + (int64_t)B * nblk * 2 * C;  // per-sample (dgamma, dbeta) contributions [B][2][C]
   int cthreads = ((C + 31) / 32) * 32;
   if (cthreads > 1024) cthreads = 1024;
   gn_bwd_table_kernel<<<B, cthreads, 0, st>>>(stats, gamma, beta, scale_shift, ss_stride, C, groups, tab);
@@ -1136,10 +1188,11 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
   FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
   /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
   if (int e = launch_reduce(dgb, dgamma_dbeta, 1, B, 2LL * C, st)) return e;
-  gn_bwd_apply_kernel<<<dim3(nblk, B), sthreads, 0, st>>>(
+  gn_bwd_apply_kernel<<<dim3(nblk, B), sthreads,
+                        dx_colsum_partials ? (size_t)lanes * C * sizeof(float) : 0, st>>>(
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
       reinterpret_cast<const uint4*>(dout), tab, reinterpret_cast<uint4*>(dx0), reinterpret_cast<uint4*>(dx1), HW, C8,
-      lanes, rows, silu);
+      lanes, rows, silu, dx_colsum_partials);
   FM_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return 0;
 }
@@ -1154,27 +1207,34 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
                  (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq |
                    (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
              "attention_bwd: rows must be 16-byte aligned (strides multiples of 8 elements)");
-  const size_t smem = (size_t)4 * T * head_dim * 2 + (size_t)2 * T * 4;
+  // fp32 staging (no unpacking in the T^2 loops) when the four tiles fit in 96 KB, else bf16 staging
+  const size_t tiles = (size_t)4 * T * head_dim;
+  const bool f32 = tiles * 4 + (size_t)2 * T * 4 <= 96 * 1024;
+  const size_t smem = tiles * (f32 ? 4 : 2) + (size_t)2 * T * 4;
   if (smem > 200 * 1024) {
     set_error("attention_bwd: T=%d head_dim=%d exceeds the shared-memory staging budget", T, head_dim);
     return FM_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-#define FM_ATT_BWD(HD)                                                                                              \
-  case HD: {                                                                                                        \
+#define FM_ATT_BWD_ST(HD, ST)                                                                                       \
+  {                                                                                                                 \
     static size_t attr_smem = 0;                                                                                    \
     if (smem > attr_smem) {                                                                                         \
-      if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_kernel<HD>,                                         \
+      if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_kernel<HD, ST>,                                     \
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),          \
                              "attention_bwd attr")) return e;                                                       \
       attr_smem = smem;                                                                                             \
     }                                                                                                               \
-    attention_bwd_kernel<HD><<<B * heads, 256, smem, st>>>(                                                         \
+    attention_bwd_kernel<HD, ST><<<B * heads, 256, smem, st>>>(                                                     \
         (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,         \
         (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, T, qs_b, qs_h, \
         qs_t, os_b, os_h, os_t, scale);                                                                             \
-    break;                                                                                                          \
   }
+#define FM_ATT_BWD(HD)                                  \
+  case HD:                                              \
+    if (f32) FM_ATT_BWD_ST(HD, float)                   \
+    else FM_ATT_BWD_ST(HD, __nv_bfloat16)               \
+    break;
   switch (head_dim) {
     FM_ATT_BWD(8)
     FM_ATT_BWD(16)
@@ -1184,6 +1244,7 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
       set_error("attention_bwd: head_dim %d unsupported (8, 16, 32, 64)", head_dim);
       return FM_ERR_UNSUPPORTED;
   }
+#undef FM_ATT_BWD_ST
 #undef FM_ATT_BWD
   FM_LAUNCH_CHECK("attention_bwd_kernel");
   return 0;

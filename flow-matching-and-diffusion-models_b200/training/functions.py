@@ -7,7 +7,6 @@ Activations are bf16 channels_last, parameters fp32 (bf16-autocast semantics: fp
 inputs, fp32 accumulation; `flow_matching_lib.py:158-164`)."""
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Optional, Sequence
 
@@ -40,7 +39,7 @@ def _nhwc(t: torch.Tensor) -> torch.Tensor:
 # raw kernel wrappers
 # --------------------------------------------------------------------------------------------------------------
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, ksize: int, stride: int, c_begin: int) -> None:
-    """dw[:, c_begin:c_begin+C_x] (fp32 OIHW, or [O][I] for 1x1) += nothing: the slice is overwritten."""
+    """Weight gradient of one source: writes dw[:, c_begin:c_begin+C_x] (fp32 OIHW, or [O][I] for 1x1; overwritten)."""
     lib = _lib.lib()
     b, cin, h, w = x.shape
     cout = dy.shape[1]
@@ -154,7 +153,17 @@ class _ConvFn(Function):
         for wi, dw in dws.items():
             grads[nsrc + wi] = dw
         if (has_bias and need[1 + nsrc + nw]) or (has_addvec and need[1 + nsrc + nw + 1]):
-            per_sample, total = colsum(dy, has_bias)
+            tagged = getattr(dy, "_fm_colsum", None)
+            part = tagged[0] if tagged is not None and tagged[1] == dy._version else None
+            if part is not None and tuple(part.shape[::2]) == (dy.shape[0], dy.shape[1]):
+                # dy is the dx of a GroupNorm backward that already summed its columns per row block
+                per_sample = torch.empty((dy.shape[0], dy.shape[1]), dtype=torch.float32, device=dy.device)
+                total = torch.empty((dy.shape[1],), dtype=torch.float32, device=dy.device) if has_bias else None
+                _lib.check(_lib.lib().fm_colsum_finish_f32(part.data_ptr(), per_sample.data_ptr(), _ptr(total),
+                                                           dy.shape[0], part.shape[1], dy.shape[1], _stream()),
+                           "colsum_finish")
+            else:
+                per_sample, total = colsum(dy, has_bias)
             if has_bias:
                 grads[nsrc + nw] = total
             if has_addvec:
@@ -239,13 +248,21 @@ class _GroupNormFn(Function):
         dx1 = ops.empty_nhwc(b, c1, h, w, x0.device) if has_x1 else None
         dgb = torch.empty((2, c), dtype=torch.float32, device=x0.device)
         dss = torch.empty((b, 2 * c), dtype=torch.float32, device=x0.device) if has_ss else None
+        # single source: also emit the column sums of dx (first stage); if x came straight out of a conv, that conv's
+        # backward turns them into its bias / embedding-add gradients without another pass over dx
+        nblk = int(lib.fm_groupnorm_bwd_blocks(b, h * w)) if not has_x1 else 0
+        colpart = torch.empty((b, nblk, c), dtype=torch.float32, device=x0.device) if nblk > 0 else None
         _lib.check(
             lib.fm_groupnorm_bwd_bf16(x0.data_ptr(), c0, _ptr(x1), c1, dout.data_ptr(), stats.data_ptr(),
                                       g32.data_ptr(), b32.data_ptr(), _ptr(ss), 0 if ss is None else ss.stride(0),
                                       int(silu), b, h * w, groups, ws.data_ptr(), dx0.data_ptr(), _ptr(dx1),
-                                      dgb.data_ptr(), _ptr(dss), _stream()),
+                                      dgb.data_ptr(), _ptr(dss), _ptr(colpart), _stream()),
             "groupnorm_bwd",
         )
+        if colpart is not None:
+            # valid only for this exact tensor state: autograd may accumulate another branch's gradient into dx0 in
+            # place, which bumps `_version` and invalidates the sums
+            dx0._fm_colsum = (colpart, dx0._version)
         return dx0, dx1, dgb[0], dgb[1], dss, None, None, None
 
 

@@ -18,6 +18,8 @@ from ..ops import _stream
 class FlatBuffers:
     """Re-seats `params` (fp32, one device) onto a flat buffer; `.grad`s live in `self.grad`.
 
+    Call after the model is on its final device (a later `.to()` / `load_state_dict(assign=True)` would detach the
+    parameters from the buffer; plain `load_state_dict` copies in place and is fine).
     The flat order is the REVERSE of the given order: backward produces gradients roughly last-layer-first, so
     buckets of consecutive flat ranges complete in order (see `training.ddp.BucketedAllReduce`)."""
 

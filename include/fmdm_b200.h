@@ -272,7 +272,12 @@ int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C);
 int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout, const float* stats,
                           const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
                           int32_t silu, int32_t B, int64_t HW, int32_t groups, float* workspace, void* dx0, void* dx1,
-                          float* dgamma_dbeta, float* dscale_shift, fm_stream_t stream);
+                          float* dgamma_dbeta, float* dscale_shift, float* dx_colsum_partials, fm_stream_t stream);
+/* dx_colsum_partials (or NULL): fp32 [B][fm_groupnorm_bwd_blocks(B, HW)][C] per-block column sums of dx, i.e. the
+ * first stage of the bias / time-embedding-add gradient of the conv that produced x; fold with fm_colsum_finish_f32 */
+int32_t fm_groupnorm_bwd_blocks(int32_t B, int64_t HW);
+int fm_colsum_finish_f32(const float* partials, float* out, float* total, int32_t B, int32_t nblk, int32_t C,
+                         fm_stream_t stream);
 /* Backward of fm_attention_bf16 (self-attention, tq == tk == T; q/k/v share the strides qs_*, o/dout share os_*;
  * dq/dk/dv are written with the q strides).  Strides in elements. */
 int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,
