@@ -53,6 +53,21 @@ class ConvParams(C.Structure):
     ]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("dst", C.c_void_p),
+        ("dst_row_stride", C.c_int64),
+        ("koff", C.c_int64),
+        ("Cout", C.c_int32),
+        ("Cin_total", C.c_int32),
+        ("c_begin", C.c_int32),
+        ("Cseg", C.c_int32),
+        ("ksize", C.c_int32),
+        ("mode", C.c_int32),
+    ]
+
+
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); must list every symbol declared in include/fmdm_b200.h
@@ -104,6 +119,8 @@ SIGNATURES = {
     "fm_clamp_f32": (C.c_int, [_vp, _vp, _f32, _f32, _i64, _vp]),
     # training step (backward / loss / optimiser)
     "fm_weight_prepack_dgrad_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "fm_weight_prepack_batch_block_elems": (C.c_int32, []),
+    "fm_weight_prepack_batch_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "fm_conv_wgrad_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "fm_conv_wgrad_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_colsum_workspace_elems": (C.c_int64, [_i32, _i64, _i32]),

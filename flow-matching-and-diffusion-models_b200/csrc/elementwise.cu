@@ -244,6 +244,38 @@ __global__ void weight_prepack_dgrad_kernel(__nv_bfloat16* __restrict__ dst, con
   dst[i] = __float2bfloat16_rn(v);
 }
 
+// Batched form of the two pack kernels above: every conv weight of a training step (forward matrices and data-gradient
+// matrices) re-packed from the fp32 master parameters in ONE launch.  Blocks are pre-assigned to (entry, offset) pairs
+// on the host; an entry is one K segment of one packed matrix.
+constexpr int kPackPerBlock = 256 * 16;
+__global__ void __launch_bounds__(256) weight_prepack_batch_kernel(const fm_pack_entry* __restrict__ entries,
+                                                                   const int32_t* __restrict__ block_entry,
+                                                                   const int64_t* __restrict__ block_offset) {
+  const fm_pack_entry e = entries[block_entry[blockIdx.x]];
+  const int64_t base = block_offset[blockIdx.x];
+  const int taps = e.ksize * e.ksize;
+  const int64_t total = (int64_t)e.Cout * taps * e.Cseg;
+  const float* __restrict__ src = reinterpret_cast<const float*>(e.src);
+  __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
+#pragma unroll 4
+  for (int k = 0; k < 16; ++k) {
+    const int64_t i = base + k * 256 + threadIdx.x;
+    if (i >= total) break;
+    if (e.mode == 0) {  // forward: dst[co][koff + tap * Cseg + c] = w[co][c_begin + c][tap]
+      const int c = (int)(i % e.Cseg);
+      const int tap = (int)((i / e.Cseg) % taps);
+      const int co = (int)(i / ((int64_t)e.Cseg * taps));
+      dst[(int64_t)co * e.dst_row_stride + e.koff + (int64_t)tap * e.Cseg + c] =
+          __float2bfloat16_rn(src[((int64_t)co * e.Cin_total + e.c_begin + c) * taps + tap]);
+    } else {            // dgrad: dst[ci][tap' * Cout + co] = w[co][c_begin + ci][taps - 1 - tap']
+      const int co = (int)(i % e.Cout);
+      const int tap = (int)((i / e.Cout) % taps);
+      const int ci = (int)(i / ((int64_t)e.Cout * taps));
+      dst[i] = __float2bfloat16_rn(src[((int64_t)co * e.Cin_total + e.c_begin + ci) * taps + (taps - 1 - tap)]);
+    }
+  }
+}
+
 // ---- nearest 2x upsample, NHWC bf16, 16 B per thread -----------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B,
                                                         int H, int W, int C8) {
@@ -438,6 +470,19 @@ extern "C" int fm_weight_prepack_dgrad_bf16(void* dst, const float* src_oihw, in
   weight_prepack_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<__nv_bfloat16*>(dst), src_oihw, Cout, Cin_total, c_begin, Cseg, ksize);
   FM_LAUNCH_CHECK("weight_prepack_dgrad_kernel");
+  return 0;
+}
+
+extern "C" int32_t fm_weight_prepack_batch_block_elems(void) { return kPackPerBlock; }
+
+extern "C" int fm_weight_prepack_batch_bf16(const fm_pack_entry* entries_dev, const int32_t* block_entry_dev,
+                                            const int64_t* block_offset_dev, int32_t n_blocks, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(entries_dev && block_entry_dev && block_offset_dev && n_blocks >= 0, "weight_prepack_batch: bad argument");
+  if (n_blocks == 0) return 0;
+  weight_prepack_batch_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(entries_dev, block_entry_dev,
+                                                                          block_offset_dev);
+  FM_LAUNCH_CHECK("weight_prepack_batch_kernel");
   return 0;
 }
 

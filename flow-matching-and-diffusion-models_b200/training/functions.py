@@ -82,8 +82,16 @@ def sumpool2x2(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _dgrad_weight(w: torch.Tensor, c_begin: int, c_count: int) -> ops.PackedConvWeight:
+# the pack plan of the model whose training forward is running (training.packplan); None = pack per call
+ACTIVE_PLAN = None
+
+
+def _dgrad_weight(w: torch.Tensor, c_begin: int, c_count: int, plan=None) -> ops.PackedConvWeight:
     """Packed weights of the data-gradient conv: in/out channels swapped, taps mirrored (one launch)."""
+    if plan is not None:
+        pw = plan.dgrad_matrix(w, c_begin, c_count, lambda: _dgrad_weight(w, c_begin, c_count))
+        if pw is not None:
+            return pw
     w32 = w.detach()
     if w32.dtype != torch.float32 or not w32.is_contiguous():
         w32 = w32.float().contiguous()
@@ -107,7 +115,11 @@ class _ConvFn(Function):
         srcs = [_nhwc(a) for a in args[:nsrc]]
         weights = list(args[nsrc:nsrc + nw])
         bias, addvec, residual = args[nsrc + nw:nsrc + nw + 3]
-        pw = ops.pack_conv_weight([(weights[wi], cb, cc) for wi, cb, cc in segs])
+        plan = ACTIVE_PLAN
+        pw = plan.forward_matrix(segs, weights) if plan is not None else None
+        if pw is None:
+            pw = ops.pack_conv_weight([(weights[wi], cb, cc) for wi, cb, cc in segs])
+        ctx.plan = plan
         if residual is not None:
             residual = _nhwc(residual)
         # want_stats: the epilogue also emits the GroupNorm partial statistics of the output (`out._fm_stats`), so a
@@ -116,6 +128,7 @@ class _ConvFn(Function):
                          addvec=None if addvec is None else _rows_f32(addvec), residual=residual, want_stats=True)
         ctx.meta = meta
         ctx.flags = (bias is not None, addvec is not None, residual is not None)
+        ctx.params = weights  # the tensors as passed (Parameters / views of them): the pack plan keys on their storage
         ctx.save_for_backward(*srcs, *weights)
         return out
 
@@ -132,7 +145,7 @@ class _ConvFn(Function):
         for i, (wi, cb, cc) in enumerate(segs):
             if not need[1 + i]:
                 continue
-            pw = _dgrad_weight(weights[wi], cb, cc)
+            pw = _dgrad_weight(ctx.params[wi], cb, cc, ctx.plan)
             if stride == 1:
                 grads[i] = ops.conv2d([dy], pw)
             else:

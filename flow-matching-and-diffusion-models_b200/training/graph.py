@@ -209,10 +209,17 @@ def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Ten
 def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
     """`UNetDiffusersND.forward` / `EfficientUNetND.forward` with autograd: returns the fp32 NCHW prediction."""
     from ..models.unet.unet import EfficientUNetND
+    from .packplan import PackPlan
 
     if not supported(model):
         out_of_scope(f"training {type(model).__name__}")
         raise RuntimeError("fmdm_b200.training: no training path for this denoiser variant (2-D, self-attention only)")
+    # every conv-weight pack of the step in one launch (recorded on the first step, see training.packplan)
+    plan = model.__dict__.get("_fm_pack_plan")
+    if plan is None:
+        plan = model.__dict__["_fm_pack_plan"] = PackPlan()
+    plan.begin_step(x.device)
+    F.ACTIVE_PLAN = plan
     if isinstance(model, EfficientUNetND):
         return efficient_unet_forward(model, x, t, context)
     ops.require_cuda(x, "training.unet_forward")

@@ -247,6 +247,20 @@ int fm_clamp_f32(float* y, const float* x, float lo, float hi, int64_t n, fm_str
  * weight: dst [Cseg][k*k*Cout], in/out channels swapped and taps mirrored (dX = conv(dY, dst) for stride 1) */
 int fm_weight_prepack_dgrad_bf16(void* dst, const float* src_oihw, int32_t Cout, int32_t Cin_total, int32_t c_begin,
                                  int32_t Cseg, int32_t ksize, fm_stream_t stream);
+/* One launch for every weight pack of a training step.  An entry is one K segment of one packed matrix: mode 0 =
+ * fm_weight_prepack_bf16 arguments, mode 1 = fm_weight_prepack_dgrad_bf16 arguments (dst_row_stride / koff unused).
+ * The host pre-assigns blocks: block b packs elements [block_offset[b], block_offset[b] +
+ * fm_weight_prepack_batch_block_elems()) of entry block_entry[b] (element count = Cout * ksize^2 * Cseg). */
+typedef struct fm_pack_entry {
+  const void* src;          /* fp32 OIHW (or [O][I]) master weight */
+  void* dst;                /* bf16 packed matrix base */
+  int64_t dst_row_stride;
+  int64_t koff;
+  int32_t Cout, Cin_total, c_begin, Cseg, ksize, mode;
+} fm_pack_entry;
+int32_t fm_weight_prepack_batch_block_elems(void);
+int fm_weight_prepack_batch_bf16(const fm_pack_entry* entries_dev, const int32_t* block_entry_dev,
+                                 const int64_t* block_offset_dev, int32_t n_blocks, fm_stream_t stream);
 /* conv wgrad: dw[co][c_begin+ci][kh][kw] = sum_{b,yo,xo} dy[b][yo][xo][co] * x[b][yo*stride+kh-pad][xo*stride+kw-pad][ci]
  * dy bf16 NHWC [B][Ho][Wo][Cout], x bf16 NHWC [B][H][W][Cin], dw fp32 OIHW [Cout][cin_total][k][k] (the slice
  * [c_begin, c_begin+Cin) is written).  ksize 1 or 3 (pad = ksize/2), stride 1 or 2.

@@ -37,7 +37,8 @@ def test_struct_layout_matches_header(tmp_path):
     from fmdm_b200 import _lib
 
     root = Path(__file__).resolve().parent.parent
-    fields = {"fm_conv_seg": [f[0] for f in _lib.ConvSeg._fields_], "fm_conv_params": [f[0] for f in _lib.ConvParams._fields_]}
+    fields = {"fm_conv_seg": [f[0] for f in _lib.ConvSeg._fields_], "fm_conv_params": [f[0] for f in _lib.ConvParams._fields_],
+              "fm_pack_entry": [f[0] for f in _lib.PackEntry._fields_]}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "fmdm_b200.h"', 'int main(void) {']
     for st, names in fields.items():
         src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
@@ -49,7 +50,7 @@ def test_struct_layout_matches_header(tmp_path):
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", str(root / "include"), str(cfile), "-o", str(exe)], check=True)
     got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
-    mirror = {"fm_conv_seg": _lib.ConvSeg, "fm_conv_params": _lib.ConvParams}
+    mirror = {"fm_conv_seg": _lib.ConvSeg, "fm_conv_params": _lib.ConvParams, "fm_pack_entry": _lib.PackEntry}
     for st, cls in mirror.items():
         assert int(got[st]) == ctypes.sizeof(cls), st
         for n in fields[st]:
