@@ -9,7 +9,7 @@ matrix up.  A request whose source moved (parameters re-seated, `.to()`) or that
 and the step falls back to individual packs while a new plan is recorded."""
 from __future__ import annotations
 
-import ctypes as C
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -30,6 +30,7 @@ class PackPlan:
     def __init__(self):
         self.mats: Dict[tuple, tuple] = {}     # key -> (PackedConvWeight, source pointers)
         self.entries = []                      # _lib.PackEntry, in request order
+        self.sources = {}                      # id(parameter) -> (weakref, data_ptr) of every master weight used
         self.ready = False
         self._tables = None
 
@@ -48,6 +49,7 @@ class PackPlan:
         pw = ops.pack_conv_weight([(w, cb, cc) for w, (_, cb, cc) in zip(ws, segs)])
         ktot, koff = pw.mat.shape[1], 0
         for w, (_, cb, cc) in zip(ws, segs):
+            self._track(w)
             ks = 1 if w.dim() == 2 else int(w.shape[-1])
             self.entries.append(_lib.PackEntry(w.data_ptr(), pw.mat.data_ptr(), ktot, koff, w.shape[0], w.shape[1], cb,
                                                cc, ks, 0))
@@ -65,17 +67,31 @@ class PackPlan:
         if self.ready:
             self.invalidate()
         pw = build()
+        self._track(w)
         ks = 1 if w.dim() == 2 else int(w.shape[-1])
         self.entries.append(_lib.PackEntry(w.data_ptr(), pw.mat.data_ptr(), 0, 0, w.shape[0], w.shape[1], cb, cc, ks, 1))
         self.mats[key] = pw
         return pw
 
+    def _track(self, w: torch.Tensor) -> None:
+        base = w._base if w._base is not None else w
+        self.sources[id(base)] = (weakref.ref(base), base.data_ptr())
+
+    def _sources_moved(self) -> bool:
+        for ref, ptr in self.sources.values():
+            p = ref()
+            if p is None or p.data_ptr() != ptr:
+                return True
+        return False
+
     def invalidate(self) -> None:
-        self.mats, self.entries, self.ready, self._tables = {}, [], False, None
+        self.mats, self.entries, self.sources, self.ready, self._tables = {}, [], {}, False, None
 
     # ---- per-step refresh ---------------------------------------------------------------------------------
     def begin_step(self, device) -> None:
         """Call at the start of every training forward: refresh every recorded matrix from the master weights."""
+        if self.sources and self._sources_moved():  # parameters re-seated (optimiser created later, .to(), ...)
+            self.invalidate()
         if not self.ready:
             # the first forward + backward after (re)starting records the requests; the next forward freezes the plan
             if not self.entries:

@@ -193,3 +193,33 @@ def test_training_step_against_reference_golden(name):
     # near-zero gradients), so they are held to a looser band
     for a, b in zip(losses[1:], gold["losses"][1:]):
         assert abs(a - b) <= 0.15 * abs(b), (losses, gold["losses"])
+
+
+def test_pack_plan_survives_parameter_reseating():
+    """A forward/backward before the optimiser exists records weight packs at the parameters' original addresses;
+    creating FusedAdamW re-seats them onto the flat buffer: the plan must notice and re-record, never read the old
+    storage, and later steps must use the one-launch refresh (fewer kernel launches than the recording step)."""
+    from fmdm_b200 import ops
+    from fmdm_b200.training import FlowMatchingTrainer, flow_matching_loss
+
+    model, sd = build(SMALL, seed=6)
+    clean, ldct, noise, t = batch(4, 32, 12)
+    flow_matching_loss(model, clean, ldct, noise=noise, t=t).backward()       # records at the original addresses
+    plan = model.__dict__["_fm_pack_plan"]
+    assert plan.entries and not plan.ready
+    tr = FlowMatchingTrainer(model, lr=1e-3, cuda_graph=False)                # re-seats every parameter
+    n0 = ops.launch_count()
+    l1 = float(tr.step(clean, ldct, noise=noise, t=t))                        # plan invalidated -> recording step
+    n1 = ops.launch_count()
+    l2 = float(tr.step(clean, ldct, noise=noise, t=t))                        # frozen plan: one refresh launch
+    n2 = ops.launch_count()
+    assert plan.ready, "the plan was not frozen on the second step"
+    assert (n2 - n1) < (n1 - n0) - 20, (n0, n1, n2)
+    ref1, _, _ = oracle_loss_and_grads(sd, SMALL, clean, ldct, noise, t)
+    assert abs(l1 - float(ref1)) <= 2e-2 * abs(float(ref1)), (l1, float(ref1))
+    # the refreshed matrices carry the UPDATED weights: the loss of the next step matches the oracle on the current
+    # parameters (two optimiser steps in)
+    cur = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ref3, _, _ = oracle_loss_and_grads(cur, SMALL, clean, ldct, noise, t)
+    l3 = float(tr.step(clean, ldct, noise=noise, t=t))
+    assert abs(l3 - float(ref3)) <= 2e-2 * abs(float(ref3)), (l1, l2, l3, float(ref3))
