@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import LDCT_UNET  # noqa: E402
+from bench import LDCT_UNET, ClockSampler  # noqa: E402
 
 
 COMPVIS = {"in_channels": 1, "out_channels": 1, "num_res_blocks": 2, "channel_mult": [1, 1, 2, 2, 4, 4],
@@ -101,6 +101,9 @@ def main():
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     import time
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
     e0.record()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -108,6 +111,25 @@ def main():
     enqueue_ms = (time.perf_counter() - t0) * 1e3 / steps  # host time to issue one step (no sync inside)
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
+    # end to end: every step takes its batch from pinned host memory and hands the loss back to the host
+    h_clean, h_ldct = clean.cpu().pin_memory(), ldct.cpu().pin_memory()
+    d_clean, d_ldct = torch.empty_like(clean), torch.empty_like(ldct)
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(steps):
+        d_clean.copy_(h_clean, non_blocking=True)
+        d_ldct.copy_(h_ldct, non_blocking=True)
+        h_loss.copy_(tr.step(d_clean, d_ldct), non_blocking=True)
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([f0.elapsed_time(f1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -124,7 +146,10 @@ def main():
                           "config": {"workload": f"LDCT {hw}x{hw} flow-matching training step, batch {B}/GPU",
                                      "model": model_name,
                                      "optimizer": "AdamW (flat, fused)", "cuda_graph": not os.environ.get("NO_GRAPH"), "loss_first": ls[0], "loss_last": ls[-1]},
-                          "host_enqueue_ms_per_step": round(enqueue_ms, 2), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
+                          "host_enqueue_ms_per_step": round(enqueue_ms, 2),
+                          "e2e": {"value": round(B * world / (e2e_ms.item() / 1e3), 2), "unit": "samples/s",
+                                  "h2d_bytes_per_step": int(clean.numel() + ldct.numel()) * 4, "d2h_bytes_per_step": 4},
+                          "clocks": clocks, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
                           "gpu_eager_reference": eager}))
     if world > 1:
         dist.destroy_process_group()
