@@ -1148,8 +1148,8 @@ extern "C" int fm_colsum_finish_f32(const float* partials, float* out, float* to
 
 extern "C" int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C) {
   if (ensure_device()) return 0;
-  /* table [B][C][8] + partials [B][nblk][2][C] + dgb_part [B][2][C] */
-  return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 2LL * B * C;
+  /* table [B][C][8] + partials [B][nblk][2][C] + folded sums [B][2][C] + dgb_part [B][2][C] */
+  return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 4LL * B * C;
 }
 
 extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout,
@@ -1169,7 +1169,8 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
   const int rows = (int)((HW + nblk - 1) / nblk);
   float* tab = workspace;
   float* part = tab + (int64_t)B * C * kGnTab;
-  float* dgb = part + (int64_t)B * nblk * 2 * C;  // per-sample (dgamma, dbeta) contributions [B][2][C]
+  float* S = part + (int64_t)B * nblk * 2 * C;     // row-block partials folded in a fixed order, [B][2][C]
+  float* dgb = S + 2LL * B * C;                    // per-sample (dgamma, dbeta) contributions [B][2][C]
   int cthreads = ((C + 31) / 32) * 32;
   if (cthreads > 1024) cthreads = 1024;
   gn_bwd_table_kernel<<<B, cthreads, 0, st>>>(stats, gamma, beta, scale_shift, ss_stride, C, groups, tab);
@@ -1183,7 +1184,9 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
       reinterpret_cast<const uint4*>(dout), tab, part, HW, C8, lanes, rows, silu);
   FM_LAUNCH_CHECK("gn_bwd_partial_kernel");
   const float inv_n = 1.f / ((float)HW * (float)(C / groups));
-  gn_bwd_finalize_kernel<<<B, cthreads, 2 * C * sizeof(float), st>>>(part, nblk, gamma, beta, scale_shift, ss_stride, C, groups,
+  // fold the partials with a wide launch first: the finalize kernel has only B blocks, a serial nblk loop there costs more
+  if (int e = launch_reduce(part, S, B, nblk, 2LL * C, st)) return e;
+  gn_bwd_finalize_kernel<<<B, cthreads, 2 * C * sizeof(float), st>>>(S, 1, gamma, beta, scale_shift, ss_stride, C, groups,
                                                                     inv_n, tab, dgb, dscale_shift);
   FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
   /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
