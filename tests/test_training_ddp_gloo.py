@@ -94,3 +94,19 @@ def test_flat_buffers_reseat_parameters_and_gradients():
     flat.ensure_grad_views()
     assert all(p.grad is not None and p.grad.data_ptr() == flat.grad.data_ptr() + 4 * flat.slice_of(p)[0]
                for p in net.parameters())
+
+
+def test_data_parallel_mean_equals_single_process_gradient_of_the_concatenated_batch():
+    """"8-GPU grads == 1-GPU grads on the concatenated batch".  Every rank back-propagates the MEAN loss of
+    its shard; the all-reduce sums the shard gradients and the optimiser folds in 1/world (`FusedAdamW.grad_scale`), which
+    is the gradient of the mean loss over the concatenated batch when the shards have equal size."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), 256, ret), nprocs=2, join=True)
+    reduced = ret[0][0][0]                                  # rank 0, first cycle: summed shard gradients
+    net = _model()
+    (x0, y0), (x1, y1) = _data(0), _data(1)
+    torch.nn.functional.mse_loss(net(torch.cat([x0, x1])), torch.cat([y0, y1])).backward()
+    for got, p in zip(reduced, net.parameters()):
+        want = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert torch.allclose(got * 0.5, want, rtol=1e-5, atol=1e-7)

@@ -66,6 +66,28 @@ def eager_reference(B, hw, steps, warmup, dev):
             "what": "torch eager bf16 autocast (cuDNN/cuBLAS/SDPA) + fused torch AdamW, same GPU, same step"}
 
 
+def cpu_reference(hw):
+    """The reference's training-step arithmetic on the box's host cores (oracle/training.py: the functional restatement
+    of the reference denoiser under torch autograd + the AdamW update), B=1, one step timed after one warm-up: the
+    reported CPU baseline of SURVEY.md 8d for config 5 (not a target)."""
+    import time
+
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+    from oracle import training as OT
+
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in DiffusionUNetFactory().build(model_cfg(), "concatenate", 1).state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    batch = (torch.rand(1, 1, hw, hw, generator=g), torch.rand(1, 1, hw, hw, generator=g),
+             torch.randn(1, 1, hw, hw, generator=g), torch.rand(1, generator=g))
+    OT.train_steps(sd, model_cfg(), [batch], lr=1e-4, weight_decay=0.0)
+    t0 = time.perf_counter()
+    OT.train_steps(sd, model_cfg(), [batch], lr=1e-4, weight_decay=0.0)
+    dt = time.perf_counter() - t0
+    return {"value": round(1.0 / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"B=1, one fwd+bwd+AdamW step at {hw}x{hw}, fp32 torch CPU oracle port, all host threads"}
+
+
 def main():
     import torch.distributed as dist
 
@@ -138,6 +160,7 @@ def main():
         del tr, model
         torch.cuda.empty_cache()
         eager = eager_reference(B, hw, steps, warmup, dev)
+    cpu = cpu_reference(hw) if rank == 0 and world == 1 and os.environ.get("CPU_BASELINE") else None
     if rank == 0:
         ls = [float(x) for x in losses]
         print(json.dumps({"metric": "training_samples_per_s", "value": round(B * world / (ms.item() / 1e3), 2),
@@ -150,7 +173,7 @@ def main():
                           "e2e": {"value": round(B * world / (e2e_ms.item() / 1e3), 2), "unit": "samples/s",
                                   "h2d_bytes_per_step": int(clean.numel() + ldct.numel()) * 4, "d2h_bytes_per_step": 4},
                           "clocks": clocks, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
-                          "gpu_eager_reference": eager}))
+                          "gpu_eager_reference": eager, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 
