@@ -135,6 +135,8 @@ SIGNATURES = {
     "fm_colsum_finish_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "fm_attention_bwd_bf16": (
         C.c_int, [_vp] * 8 + [_i32, _i32, _i32, _i32] + [_i64] * 6 + [_f32, _vp]),
+    "fm_linear_bwd_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),
+    "fm_linear_bwd_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "fm_silu_bwd_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "fm_conv_stem_wgrad_workspace_elems": (C.c_int64, [_i32, _i32]),
     "fm_conv_stem_wgrad_f32": (

@@ -976,6 +976,113 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+// =============================================================================================================
+// backward of the small-batch fp32 Linear (time MLP, the batched per-block embedding projections): B <= 32 rows,
+// up to ~20k output features.  y = f(x) W^T + b, f = SiLU or identity.
+// =============================================================================================================
+__device__ __forceinline__ float silu_exact(float x) { return x / (1.f + expf(-x)); }
+
+// dW[o][i] = sum_b dy[b][o] * f(x[b][i]);  db[o] = sum_b dy[b][o].   block tile: 32 o x 128 i
+__global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                            float* __restrict__ dw, float* __restrict__ db, int B,
+                                                            int I, int O, int silu_in) {
+  __shared__ float sdy[32][32 + 1];
+  __shared__ float sfx[32][128 + 1];
+  const int i0 = blockIdx.x * 128, o0 = blockIdx.y * 32;
+  for (int idx = threadIdx.x; idx < B * 32; idx += 256) {
+    const int b = idx / 32, oo = idx % 32;
+    sdy[b][oo] = o0 + oo < O ? dy[(int64_t)b * O + o0 + oo] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < B * 128; idx += 256) {
+    const int b = idx / 128, ii = idx % 128;
+    float v = i0 + ii < I ? x[(int64_t)b * I + i0 + ii] : 0.f;
+    if (silu_in) v = silu_exact(v);
+    sfx[b][ii] = v;
+  }
+  __syncthreads();
+  const int ti = threadIdx.x % 32, to = threadIdx.x / 32;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float d[4], f[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) d[a] = sdy[b][to + 8 * a];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) f[c] = sfx[b][ti + 32 * c];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(d[a], f[c], acc[a][c]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int o = o0 + to + 8 * a;
+    if (o >= O) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = i0 + ti + 32 * c;
+      if (i < I) dw[(int64_t)o * I + i] = acc[a][c];
+    }
+  }
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < 32 && o0 + threadIdx.x < O) {
+    float sum = 0.f;
+    for (int b = 0; b < B; ++b) sum += sdy[b][threadIdx.x];
+    db[o0 + threadIdx.x] = sum;
+  }
+}
+
+// part[chunk][b][i] = sum_{o in chunk} dy[b][o] * W[o][i];  chunk = 256 output features, block tile: 128 i x all b
+constexpr int kLinChunk = 256;
+__global__ void __launch_bounds__(256) linear_dgrad_partial_kernel(const float* __restrict__ dy,
+                                                                    const float* __restrict__ W,
+                                                                    float* __restrict__ part, int B, int I, int O) {
+  __shared__ float sdy[32][kLinChunk];
+  const int i = blockIdx.x * 128 + threadIdx.x % 128, half = threadIdx.x / 128;
+  const int oc0 = blockIdx.y * kLinChunk;
+  const int no = min(kLinChunk, O - oc0);
+  for (int idx = threadIdx.x; idx < B * kLinChunk; idx += 256) {
+    const int b = idx / kLinChunk, oo = idx % kLinChunk;
+    sdy[b][oo] = oo < no ? dy[(int64_t)b * O + oc0 + oo] : 0.f;
+  }
+  __syncthreads();
+  float acc[16];  // rows b = half, half + 2, ...
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  if (i < I) {
+    for (int oo = 0; oo < no; ++oo) {
+      const float w = __ldg(W + (int64_t)(oc0 + oo) * I + i);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int b = half + 2 * k;
+        if (b < B) acc[k] = fmaf(sdy[b][oo], w, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int b = half + 2 * k;
+      if (b < B) part[((int64_t)blockIdx.y * B + b) * I + i] = acc[k];
+    }
+  }
+}
+// dx[b][i] = f'(x[b][i]) * sum_chunk part[chunk][b][i]
+__global__ void __launch_bounds__(256) linear_dgrad_finish_kernel(const float* __restrict__ part,
+                                                                   const float* __restrict__ x, float* __restrict__ dx,
+                                                                   int nchunk, int64_t n, int silu_in) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < nchunk; ++c) acc += part[(int64_t)c * n + idx];
+    if (silu_in) {
+      const float xv = x[idx];
+      const float sg = 1.f / (1.f + expf(-xv));
+      acc *= sg * (1.f + xv * (1.f - sg));
+    }
+    dx[idx] = acc;
+  }
+}
+
 static int ew_grid(int64_t n) {
   int64_t b = (n + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -1359,5 +1466,33 @@ extern "C" int fm_adamw_f32(float* p, const float* g, float* m, float* v, int64_
   adamw_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, decay, (float)(1.0 - (double)beta1), beta2, (float)(1.0 - (double)beta2),
                                                             step_size, bc2_sqrt, eps, grad_scale);
   FM_LAUNCH_CHECK("adamw_kernel");
+  return 0;
+}
+
+extern "C" int64_t fm_linear_bwd_workspace_elems(int32_t B, int32_t I, int32_t O) {
+  return (int64_t)((O + kLinChunk - 1) / kLinChunk) * B * I;
+}
+
+/* Backward of fm_linear_f32 for B <= 32 rows: dx (or NULL) [B][I], dw [O][I], db (or NULL) [O]; workspace:
+ * fm_linear_bwd_workspace_elems floats (only for dx). */
+extern "C" int fm_linear_bwd_f32(const float* x, const float* W, const float* dy, float* workspace, float* dx, float* dw,
+                                 float* db, int32_t B, int32_t I, int32_t O, int32_t silu_in, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x && W && dy && B > 0 && I > 0 && O > 0, "linear_bwd: bad argument");
+  FM_REQUIRE(B <= 32, "linear_bwd: at most 32 rows (got %d)", B);
+  FM_REQUIRE(dx == nullptr || workspace != nullptr, "linear_bwd: dx needs the workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dw != nullptr) {
+    linear_wgrad_kernel<<<dim3((I + 127) / 128, (O + 31) / 32), 256, 0, st>>>(x, dy, dw, db, B, I, O, silu_in);
+    FM_LAUNCH_CHECK("linear_wgrad_kernel");
+  }
+  if (dx != nullptr) {
+    const int nchunk = (O + kLinChunk - 1) / kLinChunk;
+    linear_dgrad_partial_kernel<<<dim3((I + 127) / 128, nchunk), 256, 0, st>>>(dy, W, workspace, B, I, O);
+    FM_LAUNCH_CHECK("linear_dgrad_partial_kernel");
+    const int64_t n = (int64_t)B * I;
+    linear_dgrad_finish_kernel<<<ew_grid(n), 256, 0, st>>>(workspace, x, dx, nchunk, n, silu_in);
+    FM_LAUNCH_CHECK("linear_dgrad_finish_kernel");
+  }
   return 0;
 }

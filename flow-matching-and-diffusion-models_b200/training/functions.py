@@ -404,6 +404,20 @@ class _LinearFn(Function):
         x, w = ctx.saved_tensors
         dy = dy.float().contiguous()
         dx = dw = db = None
+        if x.shape[0] <= 32:
+            # small-batch kernels: dW (+db) in one launch, dX as a split-K pair
+            lib = _lib.lib()
+            b, i = x.shape
+            o = w.shape[0]
+            want_dx = ctx.needs_input_grad[0]
+            ws = _ws(lib.fm_linear_bwd_workspace_elems(b, i, o), x.device) if want_dx else None
+            dx = torch.empty_like(x) if want_dx else None
+            dw = torch.empty_like(w)
+            db = torch.empty((o,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            _lib.check(lib.fm_linear_bwd_f32(x.data_ptr(), w.data_ptr(), dy.data_ptr(), _ptr(ws), _ptr(dx),
+                                             dw.data_ptr(), _ptr(db), b, i, o, int(ctx.silu_in), _stream()),
+                       "linear_bwd")
+            return dx, dw, db, None
         dyt = dy.t().contiguous()                                              # [O][B]
         if ctx.needs_input_grad[0]:
             dx = ops.linear_f32(dy, w.t().contiguous())                        # [B][I] = dy W

@@ -298,6 +298,11 @@ int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const voi
                           void* dk, void* dv, int32_t B, int32_t heads, int32_t T, int32_t head_dim, int64_t qs_b,
                           int64_t qs_h, int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale,
                           fm_stream_t stream);
+/* Backward of fm_linear_f32 (y = f(x) W^T + b, f = SiLU if silu_in) for B <= 32 rows: dx fp32 [B][I] (or NULL), dw fp32
+ * [O][I], db fp32 [O] (or NULL).  workspace: fm_linear_bwd_workspace_elems floats (needed for dx only). */
+int64_t fm_linear_bwd_workspace_elems(int32_t B, int32_t I, int32_t O);
+int fm_linear_bwd_f32(const float* x, const float* W, const float* dy, float* workspace, float* dx, float* dw, float* db,
+                      int32_t B, int32_t I, int32_t O, int32_t silu_in, fm_stream_t stream);
 /* dx = dy * SiLU'(x), fp32 */
 int fm_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, fm_stream_t stream);
 /* Stem conv wgrad (inputs as fm_conv_stem_f32_bf16; 1..4 input channels): dw fp32 [Cout][C0+C1][3][3] */
