@@ -67,6 +67,9 @@ class FusedAdamW(torch.optim.Optimizer):
         params = list(params)
         if any(isinstance(p, dict) for p in params):
             raise ValueError("FusedAdamW: a single parameter group (flow_matching_lib.py:74 passes model.parameters())")
+        if any(p.device.type != "cuda" for p in params):
+            raise RuntimeError("fmdm_b200.training.FusedAdamW: parameters must live on a CUDA device (the optimiser is "
+                               "one sm_100a kernel; there is no CPU implementation)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.flat = FlatBuffers(self.param_groups[0]["params"])
         dev = self.flat.data.device

@@ -1,0 +1,68 @@
+"""Host-side logic of the training path that needs no GPU: routing of `BaseUNetND.forward` to the differentiable graph,
+which denoiser variants have a training path, the pack plan's notion of a stable weight source, and the loud refusal to
+optimise CPU parameters (no CPU implementation)."""
+import pytest
+import torch
+
+from fmdm_b200.models.generators import DiffusionUNetFactory
+from fmdm_b200.training import FusedAdamW, graph
+from fmdm_b200.training.packplan import PackPlan, _stable_source
+
+SMALL = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layers_per_block": 1,
+         "block_out_channels": [32, 64], "down_block_types": ["DownBlock2D", "AttnDownBlock2D"],
+         "up_block_types": ["AttnUpBlock2D", "UpBlock2D"]}
+
+
+def test_which_variants_have_a_training_path():
+    f = DiffusionUNetFactory()
+    assert graph.supported(f.build(SMALL, "concatenate", 1))
+    assert graph.supported(f.build({"in_channels": 1, "out_channels": 1, "num_res_blocks": 1, "channel_mult": [1, 2],
+                                    "model_channels": 32, "attention_resolutions": []}, "concatenate", 1))
+    ca = dict(SMALL, cross_attention_dim=4, down_block_types=["DownBlock2D", "CrossAttnDownBlock2D"])
+    assert not graph.supported(f.build(ca, "attention", 1))          # cross-attention: inference only
+    assert not graph.supported(torch.nn.Linear(2, 2))
+
+
+def test_forward_routes_to_the_differentiable_graph_only_when_training_with_grad(monkeypatch):
+    model = DiffusionUNetFactory().build(SMALL, "concatenate", 1)
+    x = torch.zeros(1, 1, 8, 8)
+    # CPU tensors never take the training route (and the inference route refuses CPU tensors loudly)
+    assert not model._wants_autograd(x, None)
+
+    class Probe:  # the predicate only looks at `.is_cuda`
+        is_cuda = True
+
+    model.train()
+    assert model._wants_autograd(Probe(), None)
+    with torch.no_grad():
+        assert not model._wants_autograd(Probe(), None)
+    model.eval()
+    assert not model._wants_autograd(Probe(), None)
+    model.train()
+    assert not model._wants_autograd(Probe(), torch.zeros(1))        # graph-replay form (t_table) is inference
+    for p in model.parameters():
+        p.requires_grad_(False)
+    assert not model._wants_autograd(Probe(), None)
+
+
+def test_pack_plan_only_plans_stable_sources():
+    p = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+    lin = torch.nn.Parameter(torch.randn(8, 4, 1, 1))
+    assert _stable_source(p)
+    assert _stable_source(lin.reshape(8, 4))                          # a view of a Parameter keeps its address
+    assert not _stable_source(torch.cat([p, p], 0))                   # rebuilt every step: packed per call
+    assert not _stable_source(p.detach().clone())
+    assert not _stable_source(torch.nn.Parameter(torch.randn(4, 4).half()))
+    plan = PackPlan()
+    plan.begin_step(torch.device("cpu"))                              # nothing recorded: nothing to launch
+    assert not plan.ready and not plan.entries
+
+
+def test_fused_adamw_refuses_cpu_parameters():
+    net = torch.nn.Linear(3, 3)
+    before = [p.data_ptr() for p in net.parameters()]
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        FusedAdamW(net.parameters(), lr=1e-3)
+    assert [p.data_ptr() for p in net.parameters()] == before         # parameters were not re-seated
+    with pytest.raises(ValueError):
+        FusedAdamW([{"params": list(net.parameters())}])
