@@ -9,9 +9,8 @@ buckets; the 1/world_size of the mean is folded into the optimiser kernel (`Fuse
 Backend-agnostic (`nccl` on the GPUs, `gloo` in the CPU tests)."""
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
-import torch
 import torch.distributed as dist
 
 

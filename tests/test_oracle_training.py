@@ -39,3 +39,19 @@ def test_training_oracle_matches_reference_golden(name):
         assert abs(a - b) <= 2e-4 * abs(b), (losses, gold["losses"])
     for k, (s, a) in gold["param_checksums"].items():
         assert abs(float(final[k].double().abs().sum()) - a) <= 1e-4 * a + 1e-6, k
+
+
+def test_oracle_adamw_matches_torch_optim():
+    """The oracle's AdamW restatement (oracle/training.py::adamw_step) against torch.optim.AdamW on CPU, several steps,
+    weight decay on: pins the optimiser arithmetic independently of the model fixtures."""
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(257, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=3e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 8):
+        grad = torch.randn(257, generator=g)
+        ref.grad = grad.clone()
+        opt.step()
+        p, m, v = OT.adamw_step(p, grad, m, v, step, lr=3e-3, weight_decay=0.05)
+        assert torch.allclose(p, ref.detach(), rtol=2e-6, atol=1e-7), step
