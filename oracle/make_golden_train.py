@@ -27,11 +27,15 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 CASES = {
     "ldct_diffusers_nd": dict(cfg_path="LDCT/LDCT_flow_matching_diffusers_nd.json", hw=32, B=2, steps=2),
     "mnist_diffusers_nd": dict(cfg_path="MNIST/mnist_flow_matching_diffusers_nd.json", hw=16, B=3, steps=3),
+    "ldct_compvis": dict(cfg_path="LDCT/LDCT_flow_matching_compvis.json", hw=32, B=2, steps=2),  # EfficientUNetND
 }
 
 
 def main():
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         cfg = json.load(open(os.path.join("/root/reference/configs", c["cfg_path"])))["model"]["unet"]
         torch.manual_seed(0)
         model = DiffusionUNetFactory().build(cfg, "concatenate", 1).train()
