@@ -13,7 +13,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "csrc" / "libfmdm_b200.so"
 
-FM_CONV_MAX_SEG = 4
+FM_CONV_MAX_SEG = 8
 
 
 class ConvSeg(C.Structure):
@@ -86,6 +86,7 @@ SIGNATURES = {
     "fm_conv_stats_rows": (C.c_int, [C.POINTER(ConvParams), C.POINTER(C.c_int32)]),
     "fm_groupnorm_finalize_partials": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i64, _i32, _f32, _vp, _vp]),
     "fm_weight_prepack_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "fm_weight_prepack_lo_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_conv_stem_f32_bf16": (
         C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fm_conv_stem_stats_rows": (C.c_int, [_i32, _i32, _i32, _i32]),
@@ -162,6 +163,8 @@ def lib() -> C.CDLL:
             f"fmdm_b200: CUDA extension not built ({path} missing). Run `python -c 'import __graft_entry__ as g; "
             f"g.build()'` or `make -C {LIB_PATH.parent}`. There is no CPU fallback for the sampling hot path."
         )
+    import torch  # noqa: F401  (maps libcudart.so.12, a DT_NEEDED of the library, into the process)
+
     handle = C.CDLL(str(path))
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(handle, name)  # AttributeError if the symbol is missing

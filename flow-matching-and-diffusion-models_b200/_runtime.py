@@ -1,8 +1,7 @@
 """Host-side runtime helpers shared by the module mirror: packed-weight caches and the out-of-scope policy."""
 from __future__ import annotations
 
-import os
-from typing import Callable, Dict, Tuple
+from typing import Callable, Dict, NoReturn, Tuple
 
 import torch
 
@@ -11,15 +10,13 @@ class OutOfScopeError(NotImplementedError):
     """Raised when a module variant outside the accelerated hot path is executed."""
 
 
-def out_of_scope(what: str):
-    """Variants the north star does not name (1-D/3-D convs, cross-attention, RMSNorm blocks, ...) have no sm_100a
-    kernel.  They are refused loudly unless FMDM_B200_ALLOW_EAGER=1, in which case the caller runs plain PyTorch ops
-    on the GPU (never on the hot path of any BASELINE config)."""
-    if os.environ.get("FMDM_B200_ALLOW_EAGER", "0") != "1":
-        raise OutOfScopeError(
-            f"fmdm_b200: {what} is outside the B200 hot path (SURVEY.md §8, marked out of scope). "
-            "Set FMDM_B200_ALLOW_EAGER=1 to run it with eager PyTorch ops instead."
-        )
+def out_of_scope(what: str) -> NoReturn:
+    """Variants the north star does not name (1-D/3-D convs, RMSNorm blocks, pooling, ...) have no sm_100a kernel and
+    are refused loudly: there is no eager-PyTorch, library or CPU path anywhere in this package."""
+    raise OutOfScopeError(
+        f"fmdm_b200: {what} is outside the B200 hot path (SURVEY.md §8, marked out of scope); this package has no "
+        "eager/CPU fallback - use the reference implementation for it."
+    )
 
 
 class ParamCache:

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(128) linear_f32_kernel(const float* __restrict
 }
 
 // ---- weight pre-pack: OIHW fp32 -> [Cout][K] bf16, K = (tap, channel) ------------------------------------------
+template <bool LO>
 __global__ void weight_prepack_kernel(__nv_bfloat16* __restrict__ dst, int64_t dst_row_stride, int64_t koff,
                                       const float* __restrict__ src, int Cout, int Cin_total, int c_begin, int Cseg,
                                       int ks) {
@@ -226,7 +227,10 @@ __global__ void weight_prepack_kernel(__nv_bfloat16* __restrict__ dst, int64_t d
   const int tap = (int)((i / Cseg) % taps);
   const int co = (int)(i / ((int64_t)Cseg * taps));
   const float v = src[((int64_t)co * Cin_total + c_begin + c) * taps + tap];
-  dst[(int64_t)co * dst_row_stride + koff + (int64_t)tap * Cseg + c] = __float2bfloat16_rn(v);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  // LO: the rounding residual of the bf16 weight (split-bf16 weights: x*w ~= x*hi + x*lo)
+  dst[(int64_t)co * dst_row_stride + koff + (int64_t)tap * Cseg + c] =
+      LO ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
 }
 
 // Packed weights of the data-gradient conv of a channel slice: dst[ci][tap' * Cout + co] = w[co][c_begin + ci][taps-1-tap']
@@ -454,9 +458,23 @@ extern "C" int fm_weight_prepack_bf16(void* dst, int64_t dst_row_stride, int64_t
              "weight_prepack: bad channel range");
   FM_REQUIRE(ksize == 1 || ksize == 3, "weight_prepack: ksize must be 1 or 3");
   const int64_t total = (int64_t)Cout * ksize * ksize * Cseg;
-  weight_prepack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  weight_prepack_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<__nv_bfloat16*>(dst), dst_row_stride, koff, src_oihw, Cout, Cin_total, c_begin, Cseg, ksize);
   FM_LAUNCH_CHECK("weight_prepack_kernel");
+  return 0;
+}
+
+extern "C" int fm_weight_prepack_lo_bf16(void* dst, int64_t dst_row_stride, int64_t koff, const float* src_oihw,
+                                         int32_t Cout, int32_t Cin_total, int32_t c_begin, int32_t Cseg, int32_t ksize,
+                                         fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(dst && src_oihw && Cout > 0 && Cseg > 0 && c_begin >= 0 && c_begin + Cseg <= Cin_total,
+             "weight_prepack_lo: bad channel range");
+  FM_REQUIRE(ksize == 1 || ksize == 3, "weight_prepack_lo: ksize must be 1 or 3");
+  const int64_t total = (int64_t)Cout * ksize * ksize * Cseg;
+  weight_prepack_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(dst), dst_row_stride, koff, src_oihw, Cout, Cin_total, c_begin, Cseg, ksize);
+  FM_LAUNCH_CHECK("weight_prepack_lo_kernel");
   return 0;
 }
 

@@ -21,6 +21,17 @@ class BaseUNetND(nn.Module, ABC):
     def _prepare_input(self, x, context, context_ca):
         return x
 
+    # narrow denoisers (MNIST, the PixelAttention configs) sit AT the north star's 1e-2 per-step tolerance with plain
+    # bf16 weights: half of their error is the weight rounding, and with <= 128 channels there is little averaging.
+    # They are launch-bound, so their GEMMs read split-bf16 weights (w_hi + w_lo, `ops.PackedConvWeight`) for free.
+    SPLIT_WEIGHT_MAX_CHANNELS = 128
+
+    def set_weight_split(self, flag: bool) -> None:
+        self.weight_split = bool(flag)
+        for m in self.modules():
+            if m is not self and hasattr(type(m), "weight_split"):
+                m.weight_split = bool(flag)
+
     def _pack_temb(self, emb: torch.Tensor):
         """Project `emb` for every ResBlock of the model with one batched fp32 kernel (see nn.blocks.TembPack)."""
         from ... import ops
@@ -66,6 +77,10 @@ class BaseUNetND(nn.Module, ABC):
                 step_dev: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
         """`t_table`/`step_dev` (fp32 device table + int32 device cursor) replace `t` under CUDA-graph replay:
         every sample of the batch then uses the timestep `t_table[*step_dev]`."""
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            # the kernels launch on the current device's stream: follow the input tensor (run_model --device cuda:1)
+            with torch.cuda.device(x.device):
+                return self.forward(x, t, context, context_ca, t_table=t_table, step_dev=step_dev, **kwargs)
         if self._wants_autograd(x, t_table):
             # training step (`flow_matching_lib.py:158-169`): same modules and parameters, differentiable kernels
             from ...training import graph

@@ -129,6 +129,7 @@ class EfficientUNetND(BaseUNetND):
                                  zero_module(ConvND(spatial_dims, model_channels, out_channels, 3, padding=1)))
         self.unpool = nn.Identity()
         self._cache = ParamCache()
+        self.set_weight_split(model_channels * max(channel_mult) <= self.SPLIT_WEIGHT_MAX_CHANNELS)
 
     # ------------------------------------------------------------------------------------------------------
     def _prepare_input(self, x, context, context_ca):

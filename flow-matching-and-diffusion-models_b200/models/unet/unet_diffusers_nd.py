@@ -86,6 +86,7 @@ class UNetDiffusersND(BaseUNetND):
         self.conv_norm_out = make_group_norm(chans[0], groups=norm_num_groups, eps=norm_eps)
         self.conv_act = nn.SiLU()
         self.conv_out = ConvND(spatial_dims, chans[0], out_channels, kernel_size=3, padding=1).conv
+        self.set_weight_split(max(chans) <= self.SPLIT_WEIGHT_MAX_CHANNELS)
 
     # ------------------------------------------------------------------------------------------------------
     def _prepare_input(self, x, context=None, context_ca=None):
@@ -116,8 +117,6 @@ class UNetDiffusersND(BaseUNetND):
             full = 2 * full - 1.0
         if cin % 8:
             out_of_scope(f"stem conv with {cin} input channels")
-            return ops.to_nhwc_bf16(torch.nn.functional.conv2d(full.float(), self.conv_in.weight, self.conv_in.bias,
-                                                              padding=1))
         pw = self._stem_pack()
         return ops.conv2d([ops.to_nhwc_bf16(full)], pw, bias=f32(self.conv_in.bias))
 
@@ -157,7 +156,6 @@ class UNetDiffusersND(BaseUNetND):
             return ops.conv_head(sample, f32(co.weight), f32(co.bias))
         if co.out_channels % 8:
             out_of_scope(f"head conv with {co.out_channels} output channels")
-            return torch.nn.functional.conv2d(sample.float(), co.weight, co.bias, padding=1)
         if not hasattr(self, "_head_cache"):
             from ..._runtime import ParamCache
 

@@ -61,7 +61,6 @@ class AutoencoderKL(nn.Module):
 
     def encode(self, x: torch.Tensor, normalize: bool = False):
         out_of_scope("AutoencoderKL.encode (training-side encoder)")
-        raise NotImplementedError("fmdm_b200: AutoencoderKL.encode is outside the sampling hot path")
 
     def decode(self, z: torch.Tensor, denorm: bool = False) -> torch.Tensor:
         """z: (B, embed_dim, h, w) fp32 latents -> raw (B, out_channels, 8h, 8w) fp32 (kl.py:126-130)."""
@@ -71,4 +70,3 @@ class AutoencoderKL(nn.Module):
 
     def forward(self, x: torch.Tensor, sample_posterior: bool = True):
         out_of_scope("AutoencoderKL.forward (encode + decode)")
-        raise NotImplementedError("fmdm_b200: AutoencoderKL.forward needs the encoder, which is out of scope")

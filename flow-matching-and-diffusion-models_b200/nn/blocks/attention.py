@@ -14,7 +14,6 @@ import warnings
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ... import ops
 from ..._runtime import ParamCache, f32, out_of_scope
@@ -33,7 +32,6 @@ class QKVAttention(nn.Module):
         if q.dim() != 4 or (self.training and self.dropout > 0) or q.shape[-1] not in (8, 16, 32, 64) \
                 or v.shape[-1] != q.shape[-1]:
             out_of_scope(f"QKVAttention on {tuple(q.shape)} (dropout={self.dropout})")
-            return F.scaled_dot_product_attention(q, k, v, dropout_p=self.dropout if self.training else 0.0)
         ops.require_cuda(q, "QKVAttention")
         b, h, tq, d = q.shape
         tk = k.shape[2]
@@ -57,10 +55,6 @@ class LinearQKVAttention(nn.Module):
         if q.dim() != 4 or (self.training and self.dropout > 0) or q.shape[-1] not in (8, 16, 32, 64) \
                 or v.shape[-1] != q.shape[-1] or not q.is_cuda:
             out_of_scope(f"LinearQKVAttention on {tuple(q.shape)} (dropout={self.dropout})")
-            ks, qs = F.softmax(k.float(), dim=-2), F.softmax(q.float(), dim=-1)
-            ctx = torch.einsum("...nd,...ne->...de", ks, v.float())
-            ctx = ctx / (ks.sum(dim=-2).unsqueeze(-1) + self.eps)
-            return F.dropout(torch.einsum("...nd,...de->...ne", qs, ctx), p=self.dropout, training=self.training)
         b, h, tq, d = q.shape
         tk = k.shape[2]
         q, k, v = [t.to(torch.bfloat16).contiguous() for t in (q, k, v)]
@@ -122,6 +116,8 @@ class SpatialSelfAttention(nn.Module):
     as (b, heads, T, 3*dh); we reproduce it exactly by transposing the NHWC GEMM output to channel-major once and
     handing K3 the matching strides."""
 
+    weight_split = False  # split-bf16 projection weights (see ConvND.weight_split)
+
     def __init__(self, dim: int, heads: int = 4, dim_head: int = 64, use_linear: bool = False,
                  use_efficient_attn: bool = True):
         super().__init__()
@@ -138,17 +134,18 @@ class SpatialSelfAttention(nn.Module):
         b, c, *spatial = x.shape
         if len(spatial) != 2 or c % 8 or self.dim_head not in (8, 16, 32, 64):
             out_of_scope(f"SpatialSelfAttention(spatial={spatial}, dim_head={self.dim_head})")
-            return self._eager(x.float())
         x = ops.to_nhwc_bf16(x)
         hh, ww = spatial
         t = hh * ww
         inner, dh, nh = self.inner_dim, self.dim_head, self.heads
         n = ops.group_norm([x], self.norm.num_groups, self.norm.eps, f32(self.norm.weight), f32(self.norm.bias),
                            silu=False)
-        wq = self._cache.get("qkv", [self.qkv.weight],
-                             lambda: ops.pack_conv_weight([(self.qkv.weight.squeeze(-1), 0, c)]))
-        wo = self._cache.get("out", [self.proj_out.weight],
-                             lambda: ops.pack_conv_weight([(self.proj_out.weight.squeeze(-1), 0, inner)]))
+        wq = self._cache.get(f"qkv{int(self.weight_split)}", [self.qkv.weight],
+                             lambda: ops.pack_conv_weight([(self.qkv.weight.squeeze(-1), 0, c)],
+                                                          split=self.weight_split))
+        wo = self._cache.get(f"out{int(self.weight_split)}", [self.proj_out.weight],
+                             lambda: ops.pack_conv_weight([(self.proj_out.weight.squeeze(-1), 0, inner)],
+                                                          split=self.weight_split))
         qkv = ops.conv2d([n], wq, bias=f32(self.qkv.bias))                      # NHWC == [b][T][3*inner]
         qkv_cm = ops.transpose_bf16(qkv.permute(0, 2, 3, 1).reshape(b, t, 3 * inner))  # [b][3*inner][T]
         att = torch.empty((b, nh, t, dh), dtype=torch.bfloat16, device=x.device)
@@ -162,20 +159,12 @@ class SpatialSelfAttention(nn.Module):
         h_nhwc = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
         return ops.conv2d([h_nhwc], wo, bias=f32(self.proj_out.bias), residual=x, want_stats=True)
 
-    def _eager(self, x):
-        b, c, *spatial = x.shape
-        t = x.reshape(b, c, -1)
-        qkv = self.qkv(self.norm(t))
-        qkv = qkv.reshape(b, self.heads, qkv.shape[-1], -1)
-        q, k, v = qkv.chunk(3, dim=-1)
-        h = self.attention(q, k, v).float().reshape(b, self.inner_dim, -1)
-        return (t + self.proj_out(h)).reshape(b, c, *spatial)
-
-
 class SpatialCrossAttention(ContextBlock):
     """CompVis-style cross-attention block (`attention.py:120-189`, conditioning:"attention" configs):
     GN -> Conv1d q -> raw-reshape head split; context GN -> Conv1d kv (one small kernel, cached per context) -> raw
     reshape -> SDPA (Tq != Tk) -> raw reshape back -> zero-init Conv1d -> + x."""
+
+    weight_split = False  # split-bf16 projection weights (see ConvND.weight_split)
 
     def __init__(self, dim: int, context_dim: int, heads: int = 4, dim_head: int = 64, use_linear: bool = False,
                  use_efficient_attn: bool = True):
@@ -200,16 +189,17 @@ class SpatialCrossAttention(ContextBlock):
                 or self.context_dim > CONTEXT_DIM_MAX or not x.is_cuda):
             out_of_scope(f"SpatialCrossAttention(spatial={spatial}, dim_head={self.dim_head}, "
                          f"context_dim={self.context_dim})")
-            return self._eager(x.float(), context.float())
         x = ops.to_nhwc_bf16(x)
         hh, ww = spatial
         t, inner, dh, nh = hh * ww, self.inner_dim, self.dim_head, self.heads
         n = ops.group_norm([x], self.norm.num_groups, self.norm.eps, f32(self.norm.weight), f32(self.norm.bias),
                            silu=False)
-        wq = self._cache.get("q", [self.q_proj.weight],
-                             lambda: ops.pack_conv_weight([(self.q_proj.weight.squeeze(-1), 0, c)]))
-        wo = self._cache.get("out", [self.proj_out.weight],
-                             lambda: ops.pack_conv_weight([(self.proj_out.weight.squeeze(-1), 0, inner)]))
+        wq = self._cache.get(f"q{int(self.weight_split)}", [self.q_proj.weight],
+                             lambda: ops.pack_conv_weight([(self.q_proj.weight.squeeze(-1), 0, c)],
+                                                          split=self.weight_split))
+        wo = self._cache.get(f"out{int(self.weight_split)}", [self.proj_out.weight],
+                             lambda: ops.pack_conv_weight([(self.proj_out.weight.squeeze(-1), 0, inner)],
+                                                          split=self.weight_split))
         q = ops.conv2d([n], wq, bias=f32(self.q_proj.bias))                            # NHWC == [b][T][inner]
         q_cm = ops.transpose_bf16(q.permute(0, 2, 3, 1).reshape(b, t, inner))          # [b][inner][T]
         kv_cm = self.precompute_context(context)
@@ -234,23 +224,12 @@ class SpatialCrossAttention(ContextBlock):
                                                    f32(self.kv_proj.weight.squeeze(-1)), f32(self.kv_proj.bias),
                                                    groups=cn.num_groups, eps=cn.eps, channel_major=True))
 
-    def _eager(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
-        b, c, *spatial = x.shape
-        xf = x.reshape(b, c, -1)
-        cf = context_tokens(context, self.context_dim)
-        q = self.q_proj(self.norm(xf))
-        kv = self.kv_proj(self.context_norm(cf))
-        q = q.reshape(b, self.heads, q.shape[-1], -1)
-        kv = kv.reshape(b, self.heads, kv.shape[-1], -1)
-        k, v = kv.chunk(2, dim=-1)
-        h = F.scaled_dot_product_attention(q, k, v).reshape(b, self.inner_dim, -1)
-        return (xf + self.proj_out(h)).reshape(b, c, *spatial)
-
-
 class DiffusersAttentionND(nn.Module):
     """Diffusers-style attention over flattened spatial tokens (`attention.py:192-274`), self-attention on the
     B200 kernels: q/k/v Linear layers run as ONE 1x1 implicit GEMM (N = 3C), to_out as another with the residual
     add in its epilogue.  Children / state_dict keys: group_norm, to_q, to_k, to_v, to_out.0."""
+
+    weight_split = False  # split-bf16 projection weights (see ConvND.weight_split)
 
     def __init__(self, channels: int, heads: int = 1, context_dim: int | None = None, norm_num_groups: int = 32,
                  eps: float = 1e-5, dropout: float = 0.0, use_efficient_attn: bool = True):
@@ -285,13 +264,9 @@ class DiffusersAttentionND(nn.Module):
                     or (self.training and self.dropout > 0) or not hidden_states.is_cuda):
                 out_of_scope(f"DiffusersAttentionND cross-attention(spatial={tuple(spatial)}, head_dim={self.head_dim}, "
                              f"context_dim={self.context_dim})")
-                y = self._eager(hidden_states.float(), context.float())
-                return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
             return self._cross(hidden_states, context, upsample_out)
         if len(spatial) != 2 or c % 8 or self.head_dim not in (8, 16, 32, 64) or (self.training and self.dropout > 0):
             out_of_scope(f"DiffusersAttentionND(spatial={tuple(spatial)}, head_dim={self.head_dim})")
-            y = self._eager(hidden_states.float(), None)
-            return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
         x = ops.to_nhwc_bf16(hidden_states)
         hh, ww = spatial
         t = hh * ww
@@ -301,12 +276,13 @@ class DiffusersAttentionND(nn.Module):
         def build_qkv():
             w = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0).detach()
             bias = torch.cat([self.to_q.bias, self.to_k.bias, self.to_v.bias], 0).detach().float().contiguous()
-            return ops.pack_conv_weight([(w, 0, c)]), bias
+            return ops.pack_conv_weight([(w, 0, c)], split=self.weight_split), bias
 
-        wqkv, bqkv = self._cache.get("qkv", [self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias,
+        wqkv, bqkv = self._cache.get(f"qkv{int(self.weight_split)}",
+                                     [self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias,
                                              self.to_k.bias, self.to_v.bias], build_qkv)
-        wout = self._cache.get("out", [self.to_out[0].weight],
-                               lambda: ops.pack_conv_weight([(self.to_out[0].weight, 0, c)]))
+        wout = self._cache.get(f"out{int(self.weight_split)}", [self.to_out[0].weight],
+                               lambda: ops.pack_conv_weight([(self.to_out[0].weight, 0, c)], split=self.weight_split))
         qkv = ops.conv2d([n], wqkv, bias=bqkv)                                   # NHWC == [b][T][3C]
         flat = qkv.permute(0, 2, 3, 1).reshape(-1)
         att = ops.empty_nhwc(b, c, hh, ww, x.device)                             # [b][T][C]
@@ -324,9 +300,10 @@ class DiffusersAttentionND(nn.Module):
         t, hd = hh * ww, self.head_dim
         gn = self.group_norm
         n = ops.group_norm([x], gn.num_groups, gn.eps, f32(gn.weight), f32(gn.bias), silu=False)
-        wq = self._cache.get("q", [self.to_q.weight], lambda: ops.pack_conv_weight([(self.to_q.weight, 0, c)]))
-        wout = self._cache.get("out", [self.to_out[0].weight],
-                               lambda: ops.pack_conv_weight([(self.to_out[0].weight, 0, c)]))
+        wq = self._cache.get(f"q{int(self.weight_split)}", [self.to_q.weight],
+                             lambda: ops.pack_conv_weight([(self.to_q.weight, 0, c)], split=self.weight_split))
+        wout = self._cache.get(f"out{int(self.weight_split)}", [self.to_out[0].weight],
+                               lambda: ops.pack_conv_weight([(self.to_out[0].weight, 0, c)], split=self.weight_split))
         q = ops.conv2d([n], wq, bias=f32(self.to_q.bias))                                # NHWC == [b][T][C]
         kv = self.precompute_context(context)                                            # [b][Tc][2C]: K | V
         tc = kv.shape[1]
@@ -351,28 +328,3 @@ class DiffusersAttentionND(nn.Module):
 
         return self._kv.get(context, [self.to_k.weight, self.to_k.bias, self.to_v.weight, self.to_v.bias, cn.weight,
                                       cn.bias], build_kv)
-
-    def _eager(self, hidden_states, context):
-        b, c = hidden_states.shape[:2]
-        spatial = hidden_states.shape[2:]
-        x = self.group_norm(hidden_states.reshape(b, c, -1)).transpose(1, 2)
-        q = self.to_q(x)
-        src = x
-        if self.context_dim is not None:
-            if context.dim() == 3:
-                if context.shape[1] == self.context_dim:
-                    ctx = context
-                elif context.shape[-1] == self.context_dim:
-                    ctx = context.transpose(1, 2)
-                else:
-                    raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {tuple(context.shape)}.")
-            else:
-                if context.shape[1] != self.context_dim:
-                    raise ValueError(f"Context channels mismatch: expected {self.context_dim}, got {tuple(context.shape)}.")
-                ctx = context.reshape(context.shape[0], context.shape[1], -1)
-            src = self.context_norm(ctx).transpose(1, 2)
-        k, v = self.to_k(src), self.to_v(src)
-        q, k, v = [z.view(b, -1, self.heads, self.head_dim).transpose(1, 2) for z in (q, k, v)]
-        out = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, -1, c)
-        out = self.to_out[1](self.to_out[0](out))
-        return out.transpose(1, 2).reshape(b, c, *spatial) + hidden_states

@@ -73,6 +73,8 @@ class TembPack:
 
 
 class ResBlockND(TimestepBlock):
+    weight_split = False  # split-bf16 weights for the fused conv2 + skip matrix (see ConvND.weight_split)
+
     def __init__(self, channels: int, emb_channels: Optional[int], dropout: float, out_channels: int = None,
                  use_conv: bool = False, use_scale_shift_norm: bool = False, spatial_dims: int = 2,
                  norm_type: str = "gn", act: str = "silu", norm_groups: int = 32, norm_eps: float = 1e-5,
@@ -134,13 +136,13 @@ class ResBlockND(TimestepBlock):
             for c in split:
                 parts.append((ws, c0, c))
                 c0 += c
-            pw = ops.pack_conv_weight(parts)
+            pw = ops.pack_conv_weight(parts, split=self.weight_split)
             bias = f32(self.conv2.conv.bias)
             if skip.conv.bias is not None:
                 bias = bias + f32(skip.conv.bias) if bias is not None else f32(skip.conv.bias)
             return pw, bias
 
-        key = "tail:" + ",".join(map(str, split))
+        key = f"tail{int(self.weight_split)}:" + ",".join(map(str, split))
         return self._cache.get(key, [w2, ws, self.conv2.conv.bias, skip.conv.bias], build)
 
     def forward(self, x, emb: Optional[torch.Tensor] = None, upsample_out: bool = False) -> torch.Tensor:
@@ -148,13 +150,9 @@ class ResBlockND(TimestepBlock):
         upsample_out (fast path only): return the result nearest-2x upsampled (folded into conv2's store)."""
         srcs = list(x) if isinstance(x, (tuple, list)) else [x]
         if not self._fast_ok() or not srcs[0].is_cuda:
-            if srcs[0].is_cuda:
-                out_of_scope(f"ResBlockND(spatial_dims={self.spatial_dims}, norm={self.norm_type}, "
-                             f"act={self.act_name}, training dropout={self.dropout})")
-            else:
-                ops.require_cuda(srcs[0], "ResBlockND.forward")
-            y = self._eager(torch.cat([s.float() for s in srcs], 1), emb)
-            return torch.nn.functional.interpolate(y, scale_factor=2, mode="nearest") if upsample_out else y
+            ops.require_cuda(srcs[0], "ResBlockND.forward")
+            out_of_scope(f"ResBlockND(spatial_dims={self.spatial_dims}, norm={self.norm_type}, "
+                         f"act={self.act_name}, training dropout={self.dropout})")
         srcs = [ops.to_nhwc_bf16(s) for s in srcs]
         if sum(s.shape[1] for s in srcs) != self.channels:
             raise ValueError(f"ResBlockND expected {self.channels} input channels")
@@ -211,27 +209,6 @@ class ResBlockND(TimestepBlock):
         pw, bias = self._fused_tail_weight(split)
         return ops.conv2d([h] + srcs, pw, bias=bias, want_stats=not upsample_out,
                           norm=None if n2 is None else n2 + [None] * len(srcs), upsample_out=upsample_out)
-
-    # eager PyTorch restatement used only for out-of-scope variants (FMDM_B200_ALLOW_EAGER=1)
-    def _eager(self, x: torch.Tensor, emb):
-        h = self.conv1.conv(self.act1(self.norm1(x)))
-        scale = shift = None
-        if self.uses_embedding:
-            if emb is None:
-                raise ValueError("ResBlockND expects `emb` when emb_channels is set.")
-            e = self.emb_act(emb) if self.emb_activation_before_proj else emb
-            e = self.emb_layers(e.float())
-            e = e.view(*e.shape, *([1] * (h.ndim - e.ndim)))
-            if self.use_scale_shift_norm:
-                scale, shift = torch.chunk(e, 2, dim=1)
-            elif self.add_embedding_to_hidden:
-                h = h + e
-        h = self.norm2(h)
-        if scale is not None:
-            h = h * (1 + scale) + shift
-        h = self.conv2.conv(self.dropout_layer(self.act2(h)))
-        skip = x if isinstance(self.skip_connection, nn.Identity) else self.skip_connection.conv(x)
-        return skip + h
 
     @staticmethod
     def _make_norm(norm_type: str, channels: int, norm_groups: int, norm_eps: float) -> nn.Module:

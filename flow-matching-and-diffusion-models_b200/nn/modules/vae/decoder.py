@@ -97,9 +97,6 @@ class Decoder(nn.Module):
             return self.conv_in(z)
         if z.shape[1] + 1 > 8 or ci.out_channels % 8:
             out_of_scope(f"Decoder stem with {z.shape[1]} latent channels / {ci.out_channels} features")
-            y = z.float() * z_scale
-            y = pre(y) if pre is not None else y
-            return ops.to_nhwc_bf16(ci(y))
 
         def build():
             w_in = ci.weight.detach().float()                       # [O][M][3][3]
@@ -151,5 +148,4 @@ class Decoder(nn.Module):
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         if self.spatial_dims != 2:
             out_of_scope("Decoder with spatial_dims != 2")
-            raise NotImplementedError("fmdm_b200: Decoder supports spatial_dims == 2 only")
         return self._run(self._stem(z))

@@ -24,6 +24,8 @@ def _as_int(v) -> Optional[int]:
 
 
 class ConvND(nn.Module):
+    weight_split = False  # split-bf16 weights (ops.PackedConvWeight); set per model by BaseUNetND.set_weight_split
+
     def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, kernel_size: SizeArg = 3,
                  stride: SizeArg = 1, padding: Optional[SizeArg] = None, dilation: SizeArg = 1, groups: int = 1,
                  bias: bool = True):
@@ -55,9 +57,9 @@ class ConvND(nn.Module):
             for c in split:
                 parts.append((w, c0, c))
                 c0 += c
-            return ops.pack_conv_weight(parts)
+            return ops.pack_conv_weight(parts, split=self.weight_split)
 
-        return self._cache.get("w:" + ",".join(map(str, split)), [w], build)
+        return self._cache.get(f"w{int(self.weight_split)}:" + ",".join(map(str, split)), [w], build)
 
     def forward(self, x, *, addvec=None, residual=None, want_stats: bool = False) -> torch.Tensor:
         srcs = list(x) if isinstance(x, (tuple, list)) else [x]
@@ -73,12 +75,6 @@ class ConvND(nn.Module):
                     return ops.conv_head(ops.to_nhwc_bf16(srcs[0]), f32(c.weight), f32(c.bias))
             out_of_scope(f"ConvND(spatial_dims={self.spatial_dims}, k={c.kernel_size}, s={c.stride}, "
                          f"groups={c.groups}, {c.in_channels}->{c.out_channels})")
-            y = self.conv(torch.cat([s.to(c.weight.dtype) for s in srcs], 1))
-            if addvec is not None:
-                y = y + addvec[:, : y.shape[1], None, None].to(y.dtype)
-            if residual is not None:
-                y = y + residual.to(y.dtype)
-            return y
         srcs = [ops.to_nhwc_bf16(s) for s in srcs]
         pw = self.packed([s.shape[1] for s in srcs])
         return ops.conv2d(srcs, pw, stride=_as_int(self.conv.stride), bias=f32(self.conv.bias), addvec=addvec,
@@ -100,4 +96,3 @@ class ConvTransposeND(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         out_of_scope("ConvTransposeND")
-        return self.convT(x.to(self.convT.weight.dtype))

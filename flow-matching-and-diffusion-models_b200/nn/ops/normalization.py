@@ -26,12 +26,6 @@ def fused_group_norm(norm: nn.GroupNorm, srcs: Sequence[torch.Tensor], *, silu: 
         srcs = [ops.to_nhwc_bf16(torch.cat(srcs, 1))]
     if any(s.shape[1] % 8 for s in srcs):
         out_of_scope(f"GroupNorm over {[s.shape[1] for s in srcs]} channels (needs multiples of 8)")
-        x = torch.cat([s.float() for s in srcs], 1)
-        y = torch.nn.functional.group_norm(x, norm.num_groups, norm.weight.float(), norm.bias.float(), norm.eps)
-        if scale_shift is not None:
-            c = y.shape[1]
-            y = y * (1 + scale_shift[:, :c, None, None]) + scale_shift[:, c:, None, None]
-        return torch.nn.functional.silu(y) if silu else y
     return ops.group_norm(srcs, norm.num_groups, norm.eps, f32(norm.weight), f32(norm.bias), silu=silu,
                           scale_shift=scale_shift)
 
@@ -56,6 +50,3 @@ class RMSNormND(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         out_of_scope("RMSNormND")
-        x = x.float()
-        rms = torch.sqrt(torch.mean(x.pow(2), dim=tuple(range(1, x.ndim)), keepdim=True) + self.eps)
-        return self.weight.view(1, -1, *([1] * (x.ndim - 2))) * x / rms

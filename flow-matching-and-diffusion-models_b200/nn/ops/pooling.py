@@ -1,5 +1,5 @@
 """API-parity shells of `src/nn/ops/pooling.py` (patchify pooling / plain pooling).  None of them is reached by a
-BASELINE config (out of scope), so they only run under FMDM_B200_ALLOW_EAGER=1."""
+BASELINE config (out of scope): calling them raises OutOfScopeError."""
 from __future__ import annotations
 
 from typing import Optional, Tuple, Union
@@ -52,7 +52,6 @@ class AvgPoolND(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         out_of_scope("AvgPoolND")
-        return self.pool(x.float())
 
 
 class MaxPoolND(nn.Module):
@@ -67,4 +66,3 @@ class MaxPoolND(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         out_of_scope("MaxPoolND")
-        return self.pool(x.float())

@@ -3,7 +3,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ... import ops
 from ..._runtime import out_of_scope
@@ -32,8 +31,6 @@ class UpsampleND(nn.Module):
             return self.conv(ops.to_nhwc_bf16(x), want_stats=True)
         if self.spatial_dims != 2 or self.channels % 8:
             out_of_scope(f"UpsampleND(spatial_dims={self.spatial_dims}, channels={self.channels})")
-            y = F.interpolate(x.float(), scale_factor=2, mode="nearest")
-            return self.conv(y) if self.use_conv else y
         y = ops.upsample_nearest2x(ops.to_nhwc_bf16(x))
         return self.conv(y, want_stats=True) if self.use_conv else y
 
@@ -56,5 +53,4 @@ class DownsampleND(nn.Module):
         assert x.shape[1] == self.channels
         if not self.use_conv:
             out_of_scope("DownsampleND(use_conv=False)")
-            return self.op(x.float())
         return self.op(x, want_stats=True)

@@ -18,6 +18,10 @@ BF16 = torch.bfloat16
 
 
 def _stream() -> int:
+    """Raw handle of torch's current stream on the CURRENT device.  Every entry point checks (`require_cuda`) that its
+    tensors live on that device: the C-ABI launches on the current device, so a tensor of another GPU would otherwise
+    be read through a foreign pointer on the wrong stream.  Callers switch devices with `torch.cuda.device(...)`
+    (`BaseUNetND.forward`, `sample_with_scheduler` and the trainers do it from their input tensor)."""
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -69,6 +73,12 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
             f"fmdm_b200.{what}: tensor is on {t.device}; the B200 hot path has no CPU implementation "
             "(use the oracle/ package or the reference for CPU runs)."
         )
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f"fmdm_b200.{what}: tensor is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            "kernels launch on the current device's stream - wrap the call in `torch.cuda.device(tensor.device)` or "
+            "call `torch.cuda.set_device` first."
+        )
 
 
 def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -100,19 +110,25 @@ def _check_act(x: torch.Tensor, what: str) -> None:
 # conv2d implicit GEMM
 # --------------------------------------------------------------------------------------------------------------
 class PackedConvWeight:
-    """K-major bf16 weight matrix [Cout][Ktot] for fm_conv2d_igemm_bf16, K = (segment, tap, channel)."""
+    """K-major bf16 weight matrix [Cout][Ktot] for fm_conv2d_igemm_bf16, K = (segment, tap, channel).
 
-    def __init__(self, mat: torch.Tensor, seg_channels: Sequence[int], seg_ksize: Sequence[int], cout: int):
+    split: the matrix holds every segment twice - the bf16 weights, then their bf16 rounding residuals
+    (`fm_weight_prepack_lo_bf16`); `conv2d` reads each source through both, i.e. multiplies by w_hi + w_lo."""
+
+    def __init__(self, mat: torch.Tensor, seg_channels: Sequence[int], seg_ksize: Sequence[int], cout: int,
+                 split: bool = False):
         self.mat = mat
         self.seg_channels = tuple(int(c) for c in seg_channels)
         self.seg_ksize = tuple(int(k) for k in seg_ksize)
         self.cout = int(cout)
+        self.split = bool(split)
 
 
-def pack_conv_weight(parts: Sequence[tuple]) -> PackedConvWeight:
+def pack_conv_weight(parts: Sequence[tuple], split: bool = False) -> PackedConvWeight:
     """parts: [(weight_oihw_fp32 [Cout][Cin][k][k] (or [Cout][Cin] for linear), c_begin, c_count), ...]
 
     Each part becomes one K segment reading `c_count` input channels starting at `c_begin` of that weight.
+    split: split-bf16 weights (see `PackedConvWeight`); at most FM_CONV_MAX_SEG / 2 parts.
     """
     lib = _lib.lib()
     cout = parts[0][0].shape[0]
@@ -127,21 +143,23 @@ def pack_conv_weight(parts: Sequence[tuple]) -> PackedConvWeight:
         ktot += ks * ks * int(c_count)
     dev = parts[0][0].device
     require_cuda(parts[0][0], "pack_conv_weight")
-    mat = torch.empty((cout, ktot), dtype=BF16, device=dev)
+    split = bool(split) and 2 * len(parts) <= _lib.FM_CONV_MAX_SEG
+    kall = ktot * (2 if split else 1)
+    mat = torch.empty((cout, kall), dtype=BF16, device=dev)
     koff = 0
     keep = []
-    for (w, c_begin, c_count), ks in zip(parts, seg_k):
-        w32 = w.detach().to(dtype=torch.float32).contiguous()
-        keep.append(w32)
-        cin_total = w32.shape[1]
-        _lib.check(
-            lib.fm_weight_prepack_bf16(
-                mat.data_ptr(), ktot, koff, w32.data_ptr(), cout, cin_total, int(c_begin), int(c_count), ks, _stream()
-            ),
-            "weight_prepack",
-        )
-        koff += ks * ks * int(c_count)
-    return PackedConvWeight(mat, seg_c, seg_k, cout)
+    for fn in ((lib.fm_weight_prepack_bf16, lib.fm_weight_prepack_lo_bf16) if split else (lib.fm_weight_prepack_bf16,)):
+        for (w, c_begin, c_count), ks in zip(parts, seg_k):
+            w32 = w.detach().to(dtype=torch.float32).contiguous()
+            keep.append(w32)
+            cin_total = w32.shape[1]
+            _lib.check(
+                fn(mat.data_ptr(), kall, koff, w32.data_ptr(), cout, cin_total, int(c_begin), int(c_count), ks,
+                   _stream()),
+                "weight_prepack",
+            )
+            koff += ks * ks * int(c_count)
+    return PackedConvWeight(mat, seg_c, seg_k, cout, split)
 
 
 def conv2d(
@@ -168,11 +186,15 @@ def conv2d(
     want_stats: also emit, from the epilogue, the GroupNorm partial statistics of the output; they ride on the
     returned tensor (`out._fm_stats`) and let the consumer `group_norm` skip its statistics pass."""
     lib = _lib.lib()
-    if len(srcs) != len(weight.seg_channels) or len(srcs) > _lib.FM_CONV_MAX_SEG:
+    if len(srcs) != len(weight.seg_channels) or len(srcs) * (2 if weight.split else 1) > _lib.FM_CONV_MAX_SEG:
         raise ValueError(f"conv2d: {len(srcs)} sources for {len(weight.seg_channels)} weight segments")
     b, _, h, w = srcs[0].shape
     p = _lib.ConvParams()
-    for i, (s, c, ks) in enumerate(zip(srcs, weight.seg_channels, weight.seg_ksize)):
+    seg_channels, seg_ksize = weight.seg_channels, weight.seg_ksize
+    if weight.split:  # every source once per weight half (hi segments first, then the residual segments)
+        srcs, seg_channels, seg_ksize = list(srcs) * 2, seg_channels * 2, seg_ksize * 2
+        norm = None if norm is None else list(norm) * 2
+    for i, (s, c, ks) in enumerate(zip(srcs, seg_channels, seg_ksize)):
         _check_act(s, "conv2d")
         if s.shape != (b, c, h, w):
             raise ValueError(f"conv2d: segment {i} has shape {tuple(s.shape)}, expected {(b, c, h, w)}")

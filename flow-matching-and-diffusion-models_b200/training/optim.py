@@ -105,13 +105,50 @@ class FusedAdamW(torch.optim.Optimizer):
         torch._C._increment_version(self.flat.params)
         return loss
 
-    # checkpoint surface (torch.optim state_dict layout is per-parameter; ours is per-buffer)
+    # checkpoint surface: the torch.optim layout, so the 'optimizer' entry of the reference's {flow,diff}_{best,last}.pt
+    # (`flow_matching_lib.py:197-211`, written by torch.optim.AdamW) resumes here and checkpoints written here resume
+    # in the reference.  state[i] are per-parameter COPIES of the flat moment buffers, i = position in param_groups.
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+        params = self.param_groups[0]["params"]
+        state = {}
+        if self.step_count > 0:
+            for i, p in enumerate(params):
+                if id(p) not in self.flat.offsets:
+                    continue
+                o, n = self.flat.slice_of(p)
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(params)))
+        return {"state": state, "param_groups": [group]}
 
-    def load_state_dict(self, state):
-        self.step_count = int(state["step"])
-        self.exp_avg.copy_(state["exp_avg"])
-        self.exp_avg_sq.copy_(state["exp_avg_sq"])
-        self.param_groups[0].update(state["param_groups"][0])
+    def load_state_dict(self, state_dict):
+        if not isinstance(state_dict, dict) or "state" not in state_dict or "param_groups" not in state_dict:
+            raise ValueError("FusedAdamW.load_state_dict expects the torch.optim layout {'state', 'param_groups'} "
+                             f"(got keys {sorted(state_dict) if isinstance(state_dict, dict) else type(state_dict)})")
+        groups = state_dict["param_groups"]
+        params = self.param_groups[0]["params"]
+        if len(groups) != 1 or len(groups[0].get("params", [])) != len(params):
+            raise ValueError("FusedAdamW.load_state_dict: expected one parameter group with "
+                             f"{len(params)} parameters, got {[len(g.get('params', [])) for g in groups]}")
+        ids = list(groups[0]["params"])
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, p in enumerate(params):
+            st = state_dict["state"].get(ids[i])
+            if st is None or id(p) not in self.flat.offsets:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"FusedAdamW.load_state_dict: state {ids[i]} has shape {tuple(st['exp_avg'].shape)}, "
+                                 f"parameter has {tuple(p.shape)}")
+            o, n = self.flat.slice_of(p)
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdamW.load_state_dict: per-parameter step counts differ ({sorted(steps)}); the flat "
+                             "update keeps one step counter")
+        self.step_count = steps.pop() if steps else 0
+        self.param_groups[0].update({k: v for k, v in groups[0].items() if k != "params"})

@@ -1,6 +1,7 @@
 """One optimisation step of flow-matching training: the loop body of `src/pipelines/train/flow_matching_lib.py:138-182`
 (noise / time sampling, x_t mixing, conditioning concat, denoiser forward, MSE on the velocity target, backward,
-optimiser step), with the data-parallel gradient all-reduce of BASELINE config 5 overlapped with the backward."""
+optimiser step), with the data-parallel gradient all-reduce of BASELINE config 5 overlapped with the backward - and
+its epsilon-target twin, the loop body of `src/pipelines/train/diffusion_lib.py:141-185` (`DiffusionTrainer`)."""
 from __future__ import annotations
 
 import math
@@ -30,6 +31,23 @@ def flow_matching_loss(model, clean: torch.Tensor, ldct: Optional[torch.Tensor],
     return F.mse_loss(pred, noise, clean)
 
 
+def diffusion_loss(model, clean: torch.Tensor, ldct: Optional[torch.Tensor], sqrt_ac: torch.Tensor,
+                   sqrt_1m_ac: torch.Tensor, *, noise=None, timesteps=None) -> torch.Tensor:
+    """`diffusion_lib.py:153-171`: timesteps ~ U{0..T-1}, noisy = scheduler.add_noise(clean, noise, timesteps)
+    (= sqrt(abar_t) clean + sqrt(1-abar_t) noise), loss = MSE(model(noisy, timesteps), noise).
+
+    `sqrt_ac` / `sqrt_1m_ac`: the scheduler's fp32 sqrt(abar) / sqrt(1-abar) tables on the device (gathered there, so
+    the step has no host round trip and can be captured into the step graph)."""
+    if noise is None:
+        noise = torch.randn_like(clean)
+    if timesteps is None:
+        timesteps = torch.randint(0, sqrt_ac.numel(), (clean.size(0),), device=clean.device).long()
+    noisy = ops.sched_add_noise(clean.float().contiguous(), noise.float().contiguous(),
+                                sqrt_ac[timesteps].contiguous(), sqrt_1m_ac[timesteps].contiguous())
+    pred = model(noisy, timesteps, context=ldct) if ldct is not None else model(noisy, timesteps)
+    return F.mse_loss(pred, noise)
+
+
 class FlowMatchingTrainer:
     """Owns the optimiser and the gradient reducer of one rank; `step()` is one `optimizer.step()` worth of work.
 
@@ -45,6 +63,16 @@ class FlowMatchingTrainer:
         self.model = model
         self.optimizer = FusedAdamW(model.parameters(), lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)
         self.reducer = BucketedAllReduce(self.optimizer.flat, bucket_bytes=bucket_bytes, group=group)
+        if self.reducer.world > 1:
+            # what torch DDP does at construction: every replica starts from rank 0's parameters and buffers (ranks
+            # that seeded differently, or where only rank 0 loaded a checkpoint, would otherwise diverge silently)
+            import torch.distributed as dist
+
+            dist.broadcast(self.optimizer.flat.data, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                           group=group)
+            for buf in model.buffers():
+                dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            torch._C._increment_version(self.optimizer.flat.params)
         self.optimizer.grad_scale = 1.0 / self.reducer.world
         self.grad_accum = max(1, int(grad_accum))
         self.num_train_timesteps = int(num_train_timesteps)
@@ -56,6 +84,10 @@ class FlowMatchingTrainer:
         self._static = None
 
     # ---------------------------------------------------------------------------------------------------------
+    def _loss(self, clean, ldct, noise, t) -> torch.Tensor:
+        return flow_matching_loss(self.model, clean, ldct, noise=noise, t=t,
+                                  num_train_timesteps=self.num_train_timesteps)
+
     def _eager_step(self, clean, ldct, noise, t) -> torch.Tensor:
         bs = clean.size(0)
         chunk = max(1, math.ceil(bs / self.grad_accum))
@@ -68,7 +100,7 @@ class FlowMatchingTrainer:
         for i, (c, l, n, tt) in enumerate(zip(cc, lc, nc, tc)):
             if i == len(cc) - 1:
                 self.reducer.arm()
-            loss = flow_matching_loss(self.model, c, l, noise=n, t=tt, num_train_timesteps=self.num_train_timesteps)
+            loss = self._loss(c, l, n, tt)
             (loss / self.grad_accum).backward()
             w = loss.detach() * (c.size(0) / bs)
             total = w if total is None else total + w
@@ -83,7 +115,7 @@ class FlowMatchingTrainer:
         self.optimizer.flat.ensure_grad_views()
         with torch.cuda.graph(graph):
             self.optimizer.zero_grad()
-            loss = flow_matching_loss(self.model, sc, sl, num_train_timesteps=self.num_train_timesteps)
+            loss = self._loss(sc, sl, None, None)
             loss.backward()
             self._static_loss = loss.detach()
         self._graph = graph
@@ -113,3 +145,24 @@ class FlowMatchingTrainer:
             self.reducer.reduce_all()
         self.optimizer.step()
         return self._static_loss.clone()
+
+
+class DiffusionTrainer(FlowMatchingTrainer):
+    """The epsilon-target step of `src/pipelines/train/diffusion_lib.py:141-185`: same optimiser / reducer / step-graph
+    machinery as `FlowMatchingTrainer`, the loss is `diffusion_loss` over the noise schedule of `scheduler` (any object
+    with `alphas_cumprod` and `config.num_train_timesteps`: `DDPMScheduler`, `DDIMScheduler`, ...).  `step(clean, ldct,
+    noise=..., t=...)`: `t` are the integer timesteps."""
+
+    def __init__(self, model, scheduler, **kw):
+        ac = getattr(scheduler, "alphas_cumprod", None)
+        if ac is None:
+            raise ValueError("DiffusionTrainer needs a scheduler with `alphas_cumprod` (ddpm / ddim / dpm_multistep)")
+        kw.setdefault("num_train_timesteps", int(scheduler.config.num_train_timesteps))
+        super().__init__(model, **kw)
+        dev = next(model.parameters()).device
+        ac = ac.to(torch.float32)
+        self.sqrt_ac = (ac ** 0.5).to(dev).contiguous()
+        self.sqrt_1m_ac = ((1 - ac) ** 0.5).to(dev).contiguous()
+
+    def _loss(self, clean, ldct, noise, t) -> torch.Tensor:
+        return diffusion_loss(self.model, clean, ldct, self.sqrt_ac, self.sqrt_1m_ac, noise=noise, timesteps=t)

@@ -50,7 +50,7 @@ long long fm_launch_count(void);
  *                   + bias[co] + addvec[n,co] + residual[n,ho,wo,co]
  * W is the pre-packed K-major weight matrix [Cout][Ktot] bf16, K ordered (segment, tap=kh*3+kw, channel).
  * ---------------------------------------------------------------------------------------------------------- */
-#define FM_CONV_MAX_SEG 4
+#define FM_CONV_MAX_SEG 8
 
 typedef struct fm_conv_seg {
   const void* src;   /* bf16 NHWC [B][H][W][C]                                        */
@@ -112,6 +112,12 @@ int fm_conv_operand_norm_supported(int32_t H, int32_t W, int32_t stride, int32_t
  * conv kernel reads: dst[co][koff + tap*Cseg + c] = src[co][c_begin + c][kh][kw]. */
 int fm_weight_prepack_bf16(void* dst, int64_t dst_row_stride, int64_t koff, const float* src_oihw, int32_t Cout,
                            int32_t Cin_total, int32_t c_begin, int32_t Cseg, int32_t ksize, fm_stream_t stream);
+/* Same layout, but stores the bf16 ROUNDING RESIDUAL of each weight: dst = bf16(w - float(bf16(w))).  A conv whose K
+ * axis carries the ordinary pack followed by this one over the same sources (two segments per source) computes
+ * x * (w_hi + w_lo), i.e. uses ~16 mantissa bits of the fp32 master weight ("split-bf16 weights"): the precision mode
+ * of the narrow (<= 128 channel) denoisers, whose per-step error otherwise sits at the bf16 noise floor. */
+int fm_weight_prepack_lo_bf16(void* dst, int64_t dst_row_stride, int64_t koff, const float* src_oihw, int32_t Cout,
+                              int32_t Cin_total, int32_t c_begin, int32_t Cseg, int32_t ksize, fm_stream_t stream);
 
 /* Stem conv (tiny Cin): fp32 NCHW inputs (x and optional concatenated conditioning, src/pipelines/utils.py:204-205,
  * unet_diffusers_nd.py:148-158,173) -> bf16 NHWC.  3x3, stride 1, pad 1.  weight fp32 OIHW, bias fp32.

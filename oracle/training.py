@@ -1,4 +1,5 @@
-"""ORACLE (test infrastructure, not product code): CPU/fp32 restatement of one flow-matching optimisation step.
+"""ORACLE (test infrastructure, not product code): CPU/fp32 restatement of one flow-matching optimisation step (and of
+the epsilon-target diffusion step, `diffusion_loss`).
 
 Follows `src/pipelines/train/flow_matching_lib.py` of the reference:
   :150-153  timesteps = (t * (num_train_timesteps - 1)).long();  x_t = (1 - t) * clean + t * noise
@@ -35,9 +36,30 @@ def flow_matching_loss(params: SD, cfg: dict, clean: torch.Tensor, ldct: Optiona
     return F.mse_loss(pred, noise - clean), pred
 
 
-def loss_and_grads(sd: SD, cfg: dict, clean, ldct, noise, t, num_train_timesteps: int = 1000) -> Tuple[torch.Tensor, SD]:
+def diffusion_loss(params: SD, cfg: dict, clean: torch.Tensor, ldct: Optional[torch.Tensor], noise: torch.Tensor,
+                   timesteps: torch.Tensor, alphas_cumprod: torch.Tensor):
+    """The epsilon-target step of `src/pipelines/train/diffusion_lib.py:153-171` -> (loss, pred):
+      :155-157  timesteps = randint(0, num_train_timesteps);  :158 noisy = scheduler.add_noise(clean, noise, timesteps)
+                (diffusers DDPM/DDIM add_noise: sqrt(abar_t) * clean + sqrt(1 - abar_t) * noise)
+      :161-162  conditioning "concatenate": model_input = cat([noisy, ldct], dim=1)
+      :168-171  pred = model(model_input, timesteps);  loss = F.mse_loss(pred, noise)"""
+    ac = alphas_cumprod.to(clean.device, torch.float32)
+    sa = (ac[timesteps] ** 0.5)[:, None, None, None]
+    sb = ((1 - ac[timesteps]) ** 0.5)[:, None, None, None]
+    noisy = sa * clean + sb * noise
+    pred = OD.denoiser_forward(params, cfg, noisy, timesteps, conditioning="concatenate" if ldct is not None else None,
+                               channels=clean.shape[1], context=ldct)
+    return F.mse_loss(pred, noise), pred
+
+
+def loss_and_grads(sd: SD, cfg: dict, clean, ldct, noise, t, num_train_timesteps: int = 1000,
+                   alphas_cumprod: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, SD]:
+    """`alphas_cumprod` given: the epsilon-target diffusion step with integer timesteps `t`; else flow matching."""
     params = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
-    loss, _ = flow_matching_loss(params, cfg, clean, ldct, noise, t, num_train_timesteps)
+    if alphas_cumprod is not None:
+        loss, _ = diffusion_loss(params, cfg, clean, ldct, noise, t, alphas_cumprod)
+    else:
+        loss, _ = flow_matching_loss(params, cfg, clean, ldct, noise, t, num_train_timesteps)
     loss.backward()
     return loss.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}
 
