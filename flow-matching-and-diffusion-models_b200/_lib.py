@@ -115,6 +115,7 @@ SIGNATURES = {
     "fm_sched_ddim_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i64, _vp]),
     "fm_sched_ddpm_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i64, _vp]),
     "fm_sched_dpmpp2m_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
+    "fm_sched_unipc_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "fm_sched_add_noise_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "fm_counter_add": (C.c_int, [_vp, _i32, _vp]),
     "fm_clamp_f32": (C.c_int, [_vp, _vp, _f32, _f32, _i64, _vp]),

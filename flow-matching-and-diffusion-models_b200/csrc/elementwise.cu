@@ -87,9 +87,10 @@ __global__ void __launch_bounds__(256) sched_ddim_kernel(float* __restrict__ xo,
 
 // DPM-Solver++(2M), midpoint, data prediction.  m = (x - sigma_s e)/alpha_s;
 //   first order : x = c1 x - c2 m ;  second order: x = c1 x - c2 m - c3 * (inv_r0 * (m - m_prev))
+// raw (algorithm_type "dpmsolver", noise prediction): the solver integrates epsilon itself, m = e.
 __device__ __forceinline__ float dpmpp_one(float x, float e, float mp, float ss, float as, float c1, float c2,
-                                           float c3, float ir, bool second, float* m_out) {
-  const float m = __fdiv_rn(__fsub_rn(x, __fmul_rn(ss, e)), as);
+                                           float c3, float ir, bool second, bool raw, float* m_out) {
+  const float m = raw ? e : __fdiv_rn(__fsub_rn(x, __fmul_rn(ss, e)), as);
   *m_out = m;
   float r = __fsub_rn(__fmul_rn(c1, x), __fmul_rn(c2, m));
   if (second) r = __fsub_rn(r, __fmul_rn(c3, __fmul_rn(ir, __fsub_rn(m, mp))));
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) sched_dpmpp_kernel(float* __restrict__ xo
                                                          int64_t n) {
   const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_DPMPP_NCOEF;
   const float ss = c[0], as = c[1], c1 = c[2], c2 = c[3], c3 = c[4], ir = c[5];
-  const bool second = c[6] != 0.0f;
+  const bool second = c[6] != 0.0f, raw = c[7] != 0.0f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -113,17 +114,65 @@ __global__ void __launch_bounds__(256) sched_dpmpp_kernel(float* __restrict__ xo
     float4 mp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (second) mp = reinterpret_cast<const float4*>(m_prev)[i];
     float4 o, m;
-    o.x = dpmpp_one(a.x, b.x, mp.x, ss, as, c1, c2, c3, ir, second, &m.x);
-    o.y = dpmpp_one(a.y, b.y, mp.y, ss, as, c1, c2, c3, ir, second, &m.y);
-    o.z = dpmpp_one(a.z, b.z, mp.z, ss, as, c1, c2, c3, ir, second, &m.z);
-    o.w = dpmpp_one(a.w, b.w, mp.w, ss, as, c1, c2, c3, ir, second, &m.w);
+    o.x = dpmpp_one(a.x, b.x, mp.x, ss, as, c1, c2, c3, ir, second, raw, &m.x);
+    o.y = dpmpp_one(a.y, b.y, mp.y, ss, as, c1, c2, c3, ir, second, raw, &m.y);
+    o.z = dpmpp_one(a.z, b.z, mp.z, ss, as, c1, c2, c3, ir, second, raw, &m.z);
+    o.w = dpmpp_one(a.w, b.w, mp.w, ss, as, c1, c2, c3, ir, second, raw, &m.w);
     reinterpret_cast<float4*>(xo)[i] = o;
     reinterpret_cast<float4*>(m_cur)[i] = m;
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float m;
-    xo[i] = dpmpp_one(x[i], eps[i], second ? m_prev[i] : 0.f, ss, as, c1, c2, c3, ir, second, &m);
+    xo[i] = dpmpp_one(x[i], eps[i], second ? m_prev[i] : 0.f, ss, as, c1, c2, c3, ir, second, raw, &m);
     m_cur[i] = m;
+  }
+}
+
+// UniPC (bh2, data prediction, order <= 2): corrector on the incoming sample with the new model output, then predictor.
+//   m_t = (x - sigma e)/alpha
+//   corrector (c[2]): xc = (ca*last - cb*m1) - cc*((c[6] ? rho0*((m2 - m1)/rkc) : 0) + rhoL*(m_t - m1))   else xc = x
+//   predictor:        xo = (pa*xc - pb*m_t) - pc*(c[13] ? half*((m1 - m_t)/rkp) : 0)
+//   state update:     last <- xc, m2 <- m1, m1 <- m_t
+struct UniPCCoef {
+  float sg, al, ca, cb, cc, rkc, rho0, rhoL, pa, pb, pc, rkp, half;
+  bool corr, corr2, pred2;
+};
+__device__ __forceinline__ float unipc_one(float x, float e, float last, float m1, float m2, const UniPCCoef& k,
+                                           float* xc_out, float* mt_out) {
+  const float mt = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sg, e)), k.al);
+  float xc = x;
+  if (k.corr) {
+    const float xt_ = __fsub_rn(__fmul_rn(k.ca, last), __fmul_rn(k.cb, m1));
+    const float d1t = __fmul_rn(k.rhoL, __fsub_rn(mt, m1));
+    const float inner = k.corr2 ? __fadd_rn(__fmul_rn(k.rho0, __fdiv_rn(__fsub_rn(m2, m1), k.rkc)), d1t) : d1t;
+    xc = __fsub_rn(xt_, __fmul_rn(k.cc, inner));
+  }
+  *xc_out = xc;
+  *mt_out = mt;
+  const float pt_ = __fsub_rn(__fmul_rn(k.pa, xc), __fmul_rn(k.pb, mt));
+  if (!k.pred2) return pt_;
+  return __fsub_rn(pt_, __fmul_rn(k.pc, __fmul_rn(k.half, __fdiv_rn(__fsub_rn(m1, mt), k.rkp))));
+}
+__global__ void __launch_bounds__(256) sched_unipc_kernel(float* __restrict__ xo, float* __restrict__ last,
+                                                         float* __restrict__ m1, float* __restrict__ m2,
+                                                         const float* __restrict__ x, const float* __restrict__ eps,
+                                                         const float* __restrict__ coef,
+                                                         const int32_t* __restrict__ step_dev, int step_host,
+                                                         int64_t n) {
+  const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_UNIPC_NCOEF;
+  UniPCCoef k;
+  k.sg = c[0]; k.al = c[1]; k.corr = c[2] != 0.0f; k.ca = c[3]; k.cb = c[4]; k.cc = c[5]; k.corr2 = c[6] != 0.0f;
+  k.rkc = c[7]; k.rho0 = c[8]; k.rhoL = c[9]; k.pa = c[10]; k.pb = c[11]; k.pc = c[12]; k.pred2 = c[13] != 0.0f;
+  k.rkp = c[14]; k.half = c[15];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float xc, mt;
+    const float a1 = m1[i];
+    const float r = unipc_one(x[i], __ldcs(eps + i), k.corr ? last[i] : 0.f, a1, k.corr2 ? m2[i] : 0.f, k, &xc, &mt);
+    xo[i] = r;
+    last[i] = xc;
+    m2[i] = a1;
+    m1[i] = mt;
   }
 }
 
@@ -378,6 +427,19 @@ extern "C" int fm_sched_dpmpp2m_f32(float* x_out, float* m_cur, const float* x, 
   sched_dpmpp_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, m_cur, x, eps, m_prev, coef,
                                                                              step_dev, step_host, n);
   FM_LAUNCH_CHECK("sched_dpmpp_kernel");
+  return 0;
+}
+
+extern "C" int fm_sched_unipc_f32(float* x_out, float* last, float* m1, float* m2, const float* x, const float* eps,
+                                  const float* coef, const int32_t* step_dev, int32_t step_host, int64_t n,
+                                  fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x_out && last && m1 && m2 && x && eps && coef && n >= 0, "unipc: null pointer or negative n");
+  FM_REQUIRE(step_dev != nullptr || step_host >= 0, "unipc: negative step");
+  if (n == 0) return 0;
+  sched_unipc_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x_out, last, m1, m2, x, eps, coef, step_dev,
+                                                                     step_host, n);
+  FM_LAUNCH_CHECK("sched_unipc_kernel");
   return 0;
 }
 

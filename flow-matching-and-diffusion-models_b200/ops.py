@@ -627,6 +627,22 @@ def sched_dpmpp2m(x, eps, m_prev, coef, step, x_out=None, m_cur=None, step_dev=N
     return x_out, m_cur
 
 
+def sched_unipc(x, eps, last, m1, m2, coef, step, x_out=None, step_dev=None):
+    """One UniPC step (corrector + predictor); `last`, `m1`, `m2` are updated in place."""
+    lib = _lib.lib()
+    require_cuda(x, "sched_unipc")
+    for t in (x, eps, last, m1, m2):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    _lib.check(
+        lib.fm_sched_unipc_f32(x_out.data_ptr(), last.data_ptr(), m1.data_ptr(), m2.data_ptr(), x.data_ptr(),
+                               eps.data_ptr(), coef.data_ptr(), _ptr(step_dev), int(step), x.numel(), _stream()),
+        "sched_unipc",
+    )
+    return x_out
+
+
 def sched_add_noise(x0, noise, a, b):
     lib = _lib.lib()
     require_cuda(x0, "sched_add_noise")

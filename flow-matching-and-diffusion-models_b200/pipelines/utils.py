@@ -18,17 +18,18 @@ import torch
 from .. import ops
 from ..models.unet.base import BaseUNetND
 from .schedulers import (DDIMScheduler, DDPMScheduler, DPMSolverMultistepScheduler,
-                         FlowMatchEulerDiscreteScheduler, _SchedulerBase)
+                         FlowMatchEulerDiscreteScheduler, UniPCMultistepScheduler, _SchedulerBase)
 
 SCHEDULER_REGISTRY: Dict[str, type] = {
     "ddpm": DDPMScheduler,
     "ddim": DDIMScheduler,
     "dpm_multistep": DPMSolverMultistepScheduler,
+    "unipc": UniPCMultistepScheduler,
     "flow_match_euler": FlowMatchEulerDiscreteScheduler,
     "flowmatch": FlowMatchEulerDiscreteScheduler,
 }
 # names the reference registers but the north star does not ask for
-_OUT_OF_SCOPE_SCHEDULERS = ("dpm_sde", "unipc")
+_OUT_OF_SCOPE_SCHEDULERS = ("dpm_sde",)
 
 
 def resolve_conditioning_mode(value) -> Optional[str]:
@@ -46,7 +47,8 @@ def build_scheduler(spec: Dict, training_cfg: Dict) -> Tuple[object, int]:
     key = str(name).lower()
     if key in _OUT_OF_SCOPE_SCHEDULERS:
         raise NotImplementedError(
-            f"fmdm_b200: scheduler '{name}' is outside the B200 hot path (built: flowmatch, ddpm, ddim, dpmsolver++)")
+            f"fmdm_b200: scheduler '{name}' is outside the B200 hot path (built: flowmatch, ddpm, ddim, dpmsolver++, "
+            "dpmsolver1/2, unipc)")
     if key not in SCHEDULER_REGISTRY:
         raise ValueError(f"Unknown scheduler '{name}'. Available: {', '.join(SCHEDULER_REGISTRY)}")
     cls = SCHEDULER_REGISTRY[key]
@@ -61,8 +63,13 @@ def build_scheduler(spec: Dict, training_cfg: Dict) -> Tuple[object, int]:
 _OVERRIDES = {
     "ddpm": {"name": "ddpm"},
     "ddim": {"name": "ddim"},
-    "dpmsolver1": {"name": "dpm_multistep", "params": {"solver_order": 1, "algorithm_type": "dpmsolver"}},
-    "dpmsolver2": {"name": "dpm_multistep", "params": {"solver_order": 2, "algorithm_type": "dpmsolver"}},
+    # the reference's aliases carry only solver_order + algorithm_type (`pipelines/utils.py:76-78`); with those alone
+    # diffusers >= 0.26 raises "`final_sigmas_type` zero is not supported for `algorithm_type` dpmsolver. Please choose
+    # `sigma_min` instead." - the aliases here add exactly that, so the names run
+    "dpmsolver1": {"name": "dpm_multistep", "params": {"solver_order": 1, "algorithm_type": "dpmsolver",
+                                                      "final_sigmas_type": "sigma_min"}},
+    "dpmsolver2": {"name": "dpm_multistep", "params": {"solver_order": 2, "algorithm_type": "dpmsolver",
+                                                      "final_sigmas_type": "sigma_min"}},
     "dpmsolver++": {"name": "dpm_multistep", "params": {"solver_order": 2, "algorithm_type": "dpmsolver++"}},
     "dpmsolversde": {"name": "dpm_sde"},
     "unipc": {"name": "unipc"},

@@ -231,10 +231,20 @@ int fm_sched_ddim_f32(float* x_out, const float* x, const float* eps, const floa
 int fm_sched_ddpm_f32(float* x_out, const float* x, const float* eps, const float* noise, const float* coef,
                       const int32_t* step_dev, int32_t step_host, int32_t clip, float clip_range, int64_t n,
                       fm_stream_t stream);
-#define FM_DPMPP_NCOEF 8 /* {sigma_s, alpha_s, c1, c2, c3, inv_r0, second_order, unused} */
+#define FM_DPMPP_NCOEF 8 /* {sigma_s, alpha_s, c1, c2, c3, inv_r0, second_order, raw_epsilon} */
+/* DPMSolverMultistepScheduler.step, order <= 2, midpoint.  raw_epsilon = 0: algorithm_type "dpmsolver++" (data
+ * prediction m = (x - sigma_s e)/alpha_s); raw_epsilon != 0: algorithm_type "dpmsolver" (m = e; c1 = alpha_t/alpha_s,
+ * c2 = sigma_t (exp(h) - 1)).  x_out = c1 x - c2 m [- c3 (inv_r0 (m - m_prev))]; m_cur <- m. */
 int fm_sched_dpmpp2m_f32(float* x_out, float* m_cur, const float* x, const float* eps, const float* m_prev,
                          const float* coef, const int32_t* step_dev, int32_t step_host, int64_t n,
                          fm_stream_t stream);
+#define FM_UNIPC_NCOEF 16
+/* UniPCMultistepScheduler.step (bh2, predict_x0, order <= 2): ONE kernel = data-prediction conversion + UniC corrector
+ * of the incoming sample + UniP predictor + history shift.  Row: {sigma, alpha, use_corrector, ca, cb, cc,
+ * corrector_order2, rk_c, rho_0, rho_last, pa, pb, pc, predictor_order2, rk_p, rho_p (0.5)}; state tensors (same shape
+ * as x, updated in place): last = corrected sample of the previous step, m1 / m2 = the last two data predictions. */
+int fm_sched_unipc_f32(float* x_out, float* last, float* m1, float* m2, const float* x, const float* eps,
+                       const float* coef, const int32_t* step_dev, int32_t step_host, int64_t n, fm_stream_t stream);
 /* x_out = a[n]*x0 + b[n]*noise (scheduler.add_noise, src/utils/model_utils/diffusion_utils.py:222) */
 int fm_sched_add_noise_f32(float* x_out, const float* x0, const float* noise, const float* a, const float* b,
                            int32_t B, int64_t per_sample, fm_stream_t stream);

@@ -13,12 +13,15 @@ import torch
 
 from .schedulers import ORACLE_REGISTRY
 
-_ALIASES = {  # pipelines/utils.py:74-84 (the three in-scope names)
+_ALIASES = {  # pipelines/utils.py:74-84
     "flowmatch": ("flow_match_euler", {}),
     "flow_match_euler": ("flow_match_euler", {}),
     "ddim": ("ddim", {}),
     "ddpm": ("ddpm", {}),
+    "dpmsolver1": ("dpm_multistep", {"solver_order": 1, "algorithm_type": "dpmsolver"}),
+    "dpmsolver2": ("dpm_multistep", {"solver_order": 2, "algorithm_type": "dpmsolver"}),
     "dpmsolver++": ("dpm_multistep", {"solver_order": 2, "algorithm_type": "dpmsolver++"}),
+    "unipc": ("unipc", {}),
 }
 
 

@@ -3,8 +3,9 @@
 CPU restatement of the third-party schedulers the reference binds at
 `/root/reference/src/pipelines/utils.py:13-30` and steps at `:218`:
 
-    diffusers.FlowMatchEulerDiscreteScheduler, diffusers.DDIMScheduler, diffusers.DPMSolverMultistepScheduler,
-    diffusers.DDPMScheduler
+    diffusers.FlowMatchEulerDiscreteScheduler, diffusers.DDIMScheduler, diffusers.DPMSolverMultistepScheduler
+    (dpmsolver++ and dpmsolver algorithm types), diffusers.UniPCMultistepScheduler, diffusers.DDPMScheduler,
+    diffusers.DPMSolverSDEScheduler
 
 The arithmetic lives in `diffusers` (requirement `diffusers>=0.24.0`, `/root/reference/requirements.txt:18`, not
 pinned, not vendored, NOT installed in this image or on the GPU box, no source copy on disk).  What follows restates
@@ -208,17 +209,31 @@ class DDPMOracle:
 
 # ------------------------------------------------------------------------------------------------------------------
 class DPMSolverPPOracle:
-    """DPMSolverMultistepScheduler with the `--scheduler dpmsolver++` alias (`pipelines/utils.py:79`):
-    solver_order=2, algorithm_type="dpmsolver++", solver_type="midpoint", lower_order_final=True,
-    final_sigmas_type="zero", timestep_spacing="linspace", epsilon prediction, no thresholding / Karras."""
+    """DPMSolverMultistepScheduler as the reference's aliases build it (`pipelines/utils.py:76-79`):
+      `dpmsolver++`  solver_order=2, algorithm_type="dpmsolver++"  (data prediction)
+      `dpmsolver1/2` solver_order=1/2, algorithm_type="dpmsolver"  (noise prediction)
+    with diffusers' other defaults: solver_type="midpoint", lower_order_final=True, euler_at_final=False,
+    timestep_spacing="linspace", epsilon prediction, no thresholding / Karras sigmas, final_sigmas_type="zero".
+
+    diffusers (>= 0.26) REJECTS algorithm_type="dpmsolver" with final_sigmas_type="zero" at construction ("`final_sigmas_
+    type` zero is not supported for `algorithm_type` dpmsolver. Please choose `sigma_min` instead."): the update would
+    multiply sigma_t = 0 by exp(h) = inf.  The restatement raises the same ValueError; `final_sigmas_type="sigma_min"`
+    (last sigma = sigma of training step 0) is the runnable form of the noise-prediction solver."""
 
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 1e-4, beta_end: float = 0.02,
-                 solver_order: int = 2, algorithm_type: str = "dpmsolver++"):
-        if algorithm_type != "dpmsolver++" or solver_order not in (1, 2):
-            raise NotImplementedError("oracle restates dpmsolver++ of order 1 or 2 only")
+                 solver_order: int = 2, algorithm_type: str = "dpmsolver++", final_sigmas_type: str = "zero",
+                 lower_order_final: bool = True):
+        if algorithm_type not in ("dpmsolver++", "dpmsolver") or solver_order not in (1, 2):
+            raise NotImplementedError("oracle restates dpmsolver++ / dpmsolver of order 1 or 2 only")
+        if algorithm_type != "dpmsolver++" and final_sigmas_type == "zero":
+            raise ValueError(f"`final_sigmas_type` {final_sigmas_type} is not supported for `algorithm_type` "
+                             f"{algorithm_type}. Please choose `sigma_min` instead.")
+        if final_sigmas_type not in ("zero", "sigma_min"):
+            raise ValueError(f"`final_sigmas_type` must be one of 'zero', or 'sigma_min', but got {final_sigmas_type}")
         self.config = SimpleNamespace(num_train_timesteps=int(num_train_timesteps), beta_start=beta_start,
                                       beta_end=beta_end, solver_order=solver_order, algorithm_type=algorithm_type,
-                                      solver_type="midpoint", lower_order_final=True, final_sigmas_type="zero",
+                                      solver_type="midpoint", lower_order_final=bool(lower_order_final),
+                                      euler_at_final=False, final_sigmas_type=final_sigmas_type,
                                       prediction_type="epsilon", timestep_spacing="linspace")
         T = self.config.num_train_timesteps
         self.alphas_cumprod = _linear_alphas_cumprod(T, beta_start, beta_end)
@@ -237,7 +252,11 @@ class DPMSolverPPOracle:
         ts = np.linspace(0, last_timestep - 1, N + 1).round()[::-1][:-1].copy().astype(np.int64)
         sig_all = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig_all)), sig_all)
-        sig = np.concatenate([sig, [0.0]]).astype(np.float32)  # final_sigmas_type == "zero"
+        if self.config.final_sigmas_type == "sigma_min":
+            sigma_last = ((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5
+        else:
+            sigma_last = 0
+        sig = np.concatenate([sig, [sigma_last]]).astype(np.float32)
         self.sigmas = torch.from_numpy(sig)
         self.timesteps = torch.from_numpy(ts).to(dtype=torch.int64)
         self.num_inference_steps = len(ts)
@@ -258,7 +277,9 @@ class DPMSolverPPOracle:
         lam_t = torch.log(alpha_t) - torch.log(sigma_t)
         lam_s = torch.log(alpha_s) - torch.log(sigma_s)
         h = lam_t - lam_s
-        return (sigma_t / sigma_s) * sample - (alpha_t * (torch.exp(-h) - 1.0)) * m0
+        if self.config.algorithm_type == "dpmsolver++":
+            return (sigma_t / sigma_s) * sample - (alpha_t * (torch.exp(-h) - 1.0)) * m0
+        return (alpha_t / alpha_s) * sample - (sigma_t * (torch.exp(h) - 1.0)) * m0
 
     def _second_order(self, sample):
         i = self._step_index
@@ -272,25 +293,32 @@ class DPMSolverPPOracle:
         h, h_0 = lam_t - lam_s0, lam_s0 - lam_s1
         r0 = h_0 / h
         D0, D1 = m0, (1.0 / r0) * (m0 - m1)
-        return ((sigma_t / sigma_s0) * sample - (alpha_t * (torch.exp(-h) - 1.0)) * D0
-                - 0.5 * (alpha_t * (torch.exp(-h) - 1.0)) * D1)
+        if self.config.algorithm_type == "dpmsolver++":
+            return ((sigma_t / sigma_s0) * sample - (alpha_t * (torch.exp(-h) - 1.0)) * D0
+                    - 0.5 * (alpha_t * (torch.exp(-h) - 1.0)) * D1)
+        return ((alpha_t / alpha_s0) * sample - (sigma_t * (torch.exp(h) - 1.0)) * D0
+                - 0.5 * (sigma_t * (torch.exp(h) - 1.0)) * D1)
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor) -> StepOutput:
         if self._step_index is None:
             self._step_index = _index_for_timestep(self.timesteps, timestep)
         n = len(self.timesteps)
-        lower_order_final = self._step_index == n - 1  # final_sigmas_type == "zero"
+        lower_order_final = (self._step_index == n - 1) and (
+            self.config.euler_at_final or (self.config.lower_order_final and n < 15)
+            or self.config.final_sigmas_type == "zero")
         lower_order_second = (self._step_index == n - 2) and self.config.lower_order_final and n < 15
-        # data prediction from epsilon
-        sigma = self.sigmas[self._step_index]
-        alpha_t, sigma_t = self._alpha_sigma(sigma)
-        x0 = (sample - sigma_t * model_output) / alpha_t
+        if self.config.algorithm_type == "dpmsolver++":  # data prediction from epsilon
+            sigma = self.sigmas[self._step_index]
+            alpha_t, sigma_t = self._alpha_sigma(sigma)
+            converted = (sample - sigma_t * model_output) / alpha_t
+        else:                                            # "dpmsolver": the solver integrates epsilon itself
+            converted = model_output
         for k in range(self.config.solver_order - 1):
             self.model_outputs[k] = self.model_outputs[k + 1]
-        self.model_outputs[-1] = x0
+        self.model_outputs[-1] = converted
         sample = sample.to(torch.float32)
         if self.config.solver_order == 1 or self.lower_order_nums < 1 or lower_order_final:
-            prev = self._first_order(x0, sample)
+            prev = self._first_order(converted, sample)
         else:  # solver_order == 2 (lower_order_second also lands here for order 2)
             prev = self._second_order(sample)
         del lower_order_second
@@ -308,10 +336,148 @@ class DPMSolverPPOracle:
         return alpha_t * original + sigma_t * noise
 
 
+# ------------------------------------------------------------------------------------------------------------------
+class UniPCOracle:
+    """diffusers.UniPCMultistepScheduler (`--scheduler unipc`, `pipelines/utils.py:28,82`) with its defaults:
+    solver_order=2, predict_x0=True, solver_type="bh2", lower_order_final=True, disable_corrector=[], solver_p=None,
+    timestep_spacing="linspace", final_sigmas_type="zero", epsilon prediction, no thresholding / Karras sigmas.
+    Restated from the published UniPC algorithm (Zhao et al. 2023: B(h) = expm1(-h) predictor UniP-p and corrector UniC-p
+    on the data prediction) in diffusers' operation order; every step first corrects the incoming sample with the new
+    model output (order = the previous step's), then predicts.  PARITY UNPINNED like the others."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 1e-4, beta_end: float = 0.02,
+                 solver_order: int = 2, lower_order_final: bool = True):
+        if solver_order not in (1, 2):
+            raise NotImplementedError("oracle restates UniPC of order 1 or 2 only")
+        self.config = SimpleNamespace(num_train_timesteps=int(num_train_timesteps), beta_start=beta_start,
+                                      beta_end=beta_end, solver_order=solver_order, predict_x0=True, solver_type="bh2",
+                                      lower_order_final=bool(lower_order_final), disable_corrector=[],
+                                      prediction_type="epsilon", timestep_spacing="linspace", final_sigmas_type="zero")
+        T = self.config.num_train_timesteps
+        self.alphas_cumprod = _linear_alphas_cumprod(T, beta_start, beta_end)
+        self.init_noise_sigma = 1.0
+        self.sigmas = ((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5
+        self.timesteps = torch.from_numpy(np.linspace(0, T - 1, T, dtype=np.float32)[::-1].copy())
+        self.num_inference_steps = None
+        self.model_outputs = [None] * solver_order
+        self.lower_order_nums = 0
+        self.last_sample = None
+        self.this_order = None
+        self._step_index = None
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        T = self.config.num_train_timesteps
+        N = int(num_inference_steps)
+        ts = np.linspace(0, T - 1, N + 1).round()[::-1][:-1].copy().astype(np.int64)
+        sig_all = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        sig = np.interp(ts, np.arange(0, len(sig_all)), sig_all)
+        sig = np.concatenate([sig, [0]]).astype(np.float32)  # final_sigmas_type == "zero"
+        self.sigmas = torch.from_numpy(sig)
+        self.timesteps = torch.from_numpy(ts).to(dtype=torch.int64)
+        self.num_inference_steps = len(ts)
+        self.model_outputs = [None] * self.config.solver_order
+        self.lower_order_nums = 0
+        self.last_sample = None
+        self._step_index = None
+
+    _alpha_sigma = staticmethod(DPMSolverPPOracle._alpha_sigma)
+
+    def _lambda(self, sigma):
+        alpha_t, sigma_t = self._alpha_sigma(sigma)
+        return torch.log(alpha_t) - torch.log(sigma_t)
+
+    @staticmethod
+    def _bh2(h):
+        """(h_phi_1, B_h, R-matrix builder inputs) for predict_x0 / bh2: hh = -h."""
+        hh = -h
+        h_phi_1 = torch.expm1(hh)
+        return hh, h_phi_1, torch.expm1(hh)
+
+    def _rhos(self, rks, hh, h_phi_1, B_h, order):
+        """R (order x order) and b (order) of the UniPC linear system."""
+        R, b = [], []
+        h_phi_k = h_phi_1 / hh - 1
+        factorial_i = 1
+        for i in range(1, order + 1):
+            R.append(torch.pow(rks, i - 1))
+            b.append(h_phi_k * factorial_i / B_h)
+            factorial_i *= i + 1
+            h_phi_k = h_phi_k / hh - 1 / factorial_i
+        return torch.stack(R), torch.stack(b)
+
+    def _predict(self, sample, order):
+        i = self._step_index
+        m0 = self.model_outputs[-1]
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i + 1])
+        alpha_s0, sigma_s0 = self._alpha_sigma(self.sigmas[i])
+        lam_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        h = (torch.log(alpha_t) - torch.log(sigma_t)) - lam_s0
+        D1 = None
+        if order == 2:
+            rk = (self._lambda(self.sigmas[i - 1]) - lam_s0) / h
+            D1 = (self.model_outputs[-2] - m0) / rk
+        hh, h_phi_1, B_h = self._bh2(h)
+        x_t_ = sigma_t / sigma_s0 * sample - alpha_t * h_phi_1 * m0
+        pred_res = torch.tensor(0.5) * D1 if D1 is not None else 0  # order 2: rhos_p = [0.5] (diffusers' shortcut)
+        return x_t_ - alpha_t * B_h * pred_res
+
+    def _correct(self, model_t, last_sample, order):
+        i = self._step_index
+        m0 = self.model_outputs[-1]  # the previous step's data prediction (history not shifted yet)
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i])
+        alpha_s0, sigma_s0 = self._alpha_sigma(self.sigmas[i - 1])
+        lam_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        h = (torch.log(alpha_t) - torch.log(sigma_t)) - lam_s0
+        rks, D1 = [], None
+        if order == 2:
+            rk = (self._lambda(self.sigmas[i - 2]) - lam_s0) / h
+            rks.append(rk)
+            D1 = (self.model_outputs[-2] - m0) / rk
+        rks.append(torch.tensor(1.0))
+        rks = torch.stack(rks)
+        hh, h_phi_1, B_h = self._bh2(h)
+        if order == 1:
+            rhos_c = torch.tensor([0.5])
+        else:
+            R, b = self._rhos(rks, hh, h_phi_1, B_h, order)
+            rhos_c = torch.linalg.solve(R, b)
+        x_t_ = sigma_t / sigma_s0 * last_sample - alpha_t * h_phi_1 * m0
+        corr_res = rhos_c[0] * D1 if D1 is not None else 0
+        D1_t = model_t - m0
+        return x_t_ - alpha_t * B_h * (corr_res + rhos_c[-1] * D1_t)
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor) -> StepOutput:
+        if self._step_index is None:
+            self._step_index = _index_for_timestep(self.timesteps, timestep)
+        i = self._step_index
+        use_corrector = i > 0 and self.last_sample is not None
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i])
+        converted = (sample - sigma_t * model_output) / alpha_t
+        if use_corrector:
+            sample = self._correct(converted, self.last_sample, self.this_order)
+        for k in range(self.config.solver_order - 1):
+            self.model_outputs[k] = self.model_outputs[k + 1]
+        self.model_outputs[-1] = converted
+        if self.config.lower_order_final:
+            this_order = min(self.config.solver_order, len(self.timesteps) - i)
+        else:
+            this_order = self.config.solver_order
+        self.this_order = min(this_order, self.lower_order_nums + 1)
+        self.last_sample = sample
+        prev = self._predict(sample, self.this_order)
+        if self.lower_order_nums < self.config.solver_order:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        return StepOutput(prev.to(model_output.dtype))
+
+    add_noise = DPMSolverPPOracle.add_noise
+
+
 ORACLE_REGISTRY = {
     "flow_match_euler": FlowMatchEulerOracle,
     "flowmatch": FlowMatchEulerOracle,
     "ddim": DDIMOracle,
     "ddpm": DDPMOracle,
     "dpm_multistep": DPMSolverPPOracle,
+    "unipc": UniPCOracle,
 }

@@ -124,8 +124,21 @@ def test_scheduler_glue():
     assert isinstance(s, DDPMScheduler) and n == 1000 and hasattr(s, "add_noise")
     s, _ = build_scheduler({}, {})
     assert isinstance(s, DDPMScheduler)
+    from fmdm_b200.pipelines.schedulers import UniPCMultistepScheduler
+
+    s, _ = build_scheduler({"name": "unipc"}, {})
+    assert isinstance(s, UniPCMultistepScheduler)
     with pytest.raises(NotImplementedError):
-        build_scheduler({"name": "unipc"}, {})
+        build_scheduler({"name": "dpm_sde"}, {})
+    # dpmsolver1 / dpmsolver2: diffusers refuses algorithm_type "dpmsolver" with a zero final sigma; the aliases add the
+    # `sigma_min` its error message asks for
+    with pytest.raises(ValueError, match="sigma_min"):
+        build_scheduler({"name": "dpm_multistep", "params": {"algorithm_type": "dpmsolver"}}, {})
+    for alias, order in (("dpmsolver1", 1), ("dpmsolver2", 2)):
+        ov = resolve_scheduler_override(alias)
+        assert ov["params"]["algorithm_type"] == "dpmsolver" and ov["params"]["solver_order"] == order
+        s, _ = build_scheduler({"name": ov["name"], "params": ov["params"]}, {})
+        assert s.config.final_sigmas_type == "sigma_min" and s.config.solver_order == order
     with pytest.raises(ValueError):
         build_scheduler({"name": "nope"}, {})
     # training_cfg fallbacks
@@ -167,5 +180,29 @@ def test_product_scheduler_tables_match_oracle():
         assert torch.equal(a.timesteps, b.timesteps) and torch.equal(a.sigmas, b.sigmas)
         rows = a.plan_rows(a.timesteps)
         assert rows[0] == 0 and rows[-1] == n - 1 and all(r >= n for r in rows[1:-1])
+        kw = dict(algorithm_type="dpmsolver", final_sigmas_type="sigma_min")
+        a, b = DPMSolverMultistepScheduler(1000, 1e-4, 0.02, **kw), DPMSolverPPOracle(1000, 1e-4, 0.02, **kw)
+        a.set_timesteps(n); b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps) and torch.equal(a.sigmas, b.sigmas) and float(a.sigmas[-1]) > 0
+        rows = a.plan_rows(a.timesteps)
+        assert rows[0] == 0 and all(r >= n for r in rows[1:-1]) and (rows[-1] == n - 1) == (n < 15 or n == 1)
+        assert torch.isfinite(a._coef_cpu).all()
+    from fmdm_b200.pipelines.schedulers import UniPCMultistepScheduler
+    from oracle.schedulers import UniPCOracle
+
+    for n in (1, 2, 5, 20):
+        a, b = UniPCMultistepScheduler(1000, 1e-4, 0.02), UniPCOracle(1000, 1e-4, 0.02)
+        a.set_timesteps(n); b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps) and torch.equal(a.sigmas, b.sigmas)
+        rows = a.plan_rows(a.timesteps)
+        variants = [a._VARIANTS[r // n] for r in rows]
+        want_pred = [1] + [2] * max(n - 2, 0) + ([1] if n > 1 else [])
+        assert [v[0] for v in variants] == want_pred
+        assert [v[1] for v in variants] == [0] + want_pred[:-1]
+        assert torch.isfinite(a._coef_cpu[rows]).all()
+        # a partial trajectory starts without a last sample: no corrector on its first step
+        if n >= 5:
+            sub = a.plan_rows(a.timesteps[2:])
+            assert a._VARIANTS[sub[0] // n] == (1, 0) and a._VARIANTS[sub[1] // n] == (2, 1)
     with pytest.raises(ValueError):
         FlowMatchEulerDiscreteScheduler(1000).step(torch.zeros(1), 3, torch.zeros(1))

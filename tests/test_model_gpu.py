@@ -26,6 +26,11 @@ LDCT_SMALL = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, 
               "up_block_types": ["UpBlock2D", "AttnUpBlock2D"] + ["UpBlock2D"] * 4}
 COMPVIS_SMALL = {"in_channels": 1, "out_channels": 1, "num_res_blocks": 2, "channel_mult": [1, 1, 2, 2],
                  "model_channels": 64, "attention_resolutions": [], "block_out_channels": [64, 64, 128, 128]}
+# configs/LDCT/LDCT_flow_matching_compvis.json (EfficientUNetND, scale-shift ResBlocks, SpatialSelfAttention middle block)
+COMPVIS_LDCT = {"in_channels": 1, "out_channels": 1, "num_res_blocks": 2, "channel_mult": [1, 1, 2, 2, 4, 4],
+                "model_channels": 128, "attention_resolutions": [], "block_out_channels": [128, 128, 256, 256, 512, 512]}
+TOL_STEP = 1e-2     # north star: per-step velocity / epsilon within 1e-2 relative L2 (bf16 path vs fp32 oracle)
+PSNR_MIN = 40.0     # north star: final samples >= 40 dB PSNR
 
 
 def rel_l2(a, b):
@@ -115,7 +120,13 @@ def test_attention_blocks():
     ("ldct64_concat", LDCT_SMALL, "concatenate", 64, 2),
     ("ldct160_concat", LDCT_SMALL, "concatenate", 160, 1),  # rows >= 65 px: rolling-row convs with the fused GroupNorm
     ("ldct512_concat", LDCT_SMALL, "concatenate", 512, 2),  # the headline resolution (BASELINE configs[1]), full arch
+    # the exact bench configuration: B = 16 per GPU (the strip schedule, hence the fp32 summation order of the fused
+    # GroupNorm statistics, depends on the batch size); the fp32 oracle runs on the same GPU (TF32 off)
+    ("ldct512_concat_b16", LDCT_SMALL, "concatenate", 512, 16),
     ("compvis32_concat", COMPVIS_SMALL, "concatenate", 32, 2),
+    # EfficientUNetND on rows >= 65 px: rolling-row convs with the scale-shift folded into the operand-transform table
+    ("compvis_ldct128_concat", COMPVIS_LDCT, "concatenate", 128, 2),
+    ("compvis_ldct256_concat", COMPVIS_LDCT, "concatenate", 256, 1),
 ])
 def test_denoiser_forward_parity(name, cfg, cond, hw, B):
     """per-step prediction within 1e-2 relative L2 of the fp32 oracle (north-star tolerance)."""
@@ -125,17 +136,18 @@ def test_denoiser_forward_parity(name, cfg, cond, hw, B):
     c = torch.rand(B, 1, hw, hw, generator=g).to(DEV) if cond else None
     for tval in (999.0, 500.5, 1.0):
         t = torch.full((B,), tval, device=DEV)
-        ref = OD.denoiser_forward(sd, cfg, x, t, conditioning=cond, channels=1, context=c)
         with torch.no_grad():
+            ref = OD.denoiser_forward(sd, cfg, x, t, conditioning=cond, channels=1, context=c)
             out = model(x, t, context=c)
             out2 = model(torch.cat([x, c], 1), t) if cond else out
         assert out.dtype == torch.float32 and out.shape == ref.shape
         err = rel_l2(out, ref)
-        # north-star tolerance 1e-2 (bf16 vs fp32 oracle).  Measured: LDCT arch 0.7-0.97e-2,
-        # of which 0.5e-2 is the bf16 rounding of the WEIGHTS alone; the shallow/narrow MNIST arch sits at
-        # 0.99-1.04e-2, i.e. at the bf16 noise floor, so it gets 1.2e-2.
-        tol = 1.2e-2 if name.startswith("mnist") else 1e-2
-        assert err < tol, (name, tval, err)
+        # north-star tolerance, nothing relaxed.  Measured: LDCT arch 0.7-0.97e-2 (0.78e-2 at B=16, 512^2), EfficientUNetND
+        # 0.58-0.80e-2 at 128..512 px; the narrow MNIST arch 0.66-0.88e-2 with its split-bf16 weights (it sat at
+        # 0.98-1.00e-2, the bf16 noise floor, with plain bf16 weights: `BaseUNetND.set_weight_split`).
+        assert err < TOL_STEP, (name, tval, err)
+        worst_sample = max(rel_l2(out[i], ref[i]) for i in range(B))
+        assert worst_sample < TOL_STEP, (name, tval, worst_sample)
         assert torch.equal(out, out2)
 
 
@@ -145,12 +157,13 @@ def test_scheduler_steps_bit_exact():
 
     g = torch.Generator().manual_seed(8)
     shape = (3, 1, 33, 31)
-    for name, n in (("flowmatch", 50), ("ddim", 50), ("dpmsolver++", 20), ("dpmsolver++", 5)):
+    for name, n in (("flowmatch", 50), ("ddim", 50), ("dpmsolver++", 20), ("dpmsolver++", 5), ("dpmsolver1", 20),
+                    ("dpmsolver2", 20), ("dpmsolver2", 5), ("unipc", 20), ("unipc", 5), ("unipc", 2)):
         ov = resolve_scheduler_override(name)
         params = {"beta_start": 1e-4, "beta_end": 0.02}
         params.update(ov.get("params", {}))
         mine, _ = build_scheduler({"name": ov["name"], "params": params, "num_train_timesteps": 1000}, {})
-        orc = make_scheduler(name, 1000, {"beta_start": 1e-4, "beta_end": 0.02})
+        orc = make_scheduler(name, 1000, params)
         mine.set_timesteps(n)
         orc.set_timesteps(n)
         assert torch.equal(mine.timesteps, orc.timesteps)
@@ -185,7 +198,8 @@ def test_scheduler_steps_bit_exact():
     assert torch.equal(mine.add_noise(x0.to(DEV), nz.to(DEV), ts).cpu(), orc.add_noise(x0, nz, ts))
 
 
-@pytest.mark.parametrize("sched,steps", [("flowmatch", 50), ("ddim", 50), ("dpmsolver++", 20)])
+@pytest.mark.parametrize("sched,steps", [("flowmatch", 50), ("ddim", 50), ("dpmsolver++", 20), ("dpmsolver2", 20),
+                                         ("unipc", 20)])
 def test_sampling_loop_parity(sched, steps):
     """Graph-replayed sampling vs the oracle loop (fp32 oracle denoiser).
 
@@ -214,7 +228,7 @@ def test_sampling_loop_parity(sched, steps):
                                  conditioning_batch=cond, init_sample=noise, use_cuda_graph=False)
     assert torch.equal(out, out2), float((out - out2).abs().max())
 
-    orc = make_scheduler(sched, 1000, {"beta_start": 1e-4, "beta_end": 0.02})
+    orc = make_scheduler(sched, 1000, params)
     mine2, _ = build_scheduler({"name": ov["name"], "params": params}, {})
     mine2.set_timesteps(steps)
     orc.set_timesteps(steps)
@@ -231,10 +245,10 @@ def test_sampling_loop_parity(sched, steps):
         mine_next = mine2.step(ref_pred, t, x.to(DEV)).prev_sample
         assert torch.equal(mine_next.cpu(), x_next)
         x = x_next
-    assert worst < 1.2e-2, (sched, worst)  # MNIST arch: bf16 noise floor ~1.0e-2, see test_denoiser_forward_parity
+    assert worst < TOL_STEP, (sched, worst)  # measured 0.59 / 0.89 / 0.51e-2 (flowmatch / ddim / dpmsolver++)
     if sched == "flowmatch":
         p = psnr(out.clamp(0, 1).cpu(), x.clamp(0, 1))
-        assert p >= 40.0, (sched, p)
+        assert p >= PSNR_MIN, (sched, p)
     # start_step / last_n_steps subsets run and agree between the two product paths
     kw = dict(last_n_steps=3) if sched == "flowmatch" else dict(start_step=500)
     a = sample_with_scheduler(model, mine, steps, noise.shape, torch.device(DEV), conditioning_mode="concatenate",
@@ -273,16 +287,17 @@ def test_full_size_properties():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("hw", [256, 512])
-def test_ldct_flowmatch_final_sample_psnr(hw):
+@pytest.mark.parametrize("hw,B", [(256, 1), (512, 1), (512, 16)])
+def test_ldct_flowmatch_final_sample_psnr(hw, B):
     """North-star tolerance on the headline architecture: final samples of the full 50-Euler-step flow-matching run
     (full LDCT UNetDiffusersND at 256x256 and at the headline 512x512, graph-replayed B200 path) >= 40 dB PSNR against
-    the fp32 oracle loop."""
+    the fp32 oracle loop - including the exact bench configuration, B = 16 at 512x512 (BASELINE configs[1]; every
+    sample of the batch is held to the bar, measured 58 dB)."""
     from fmdm_b200.pipelines.utils import build_scheduler, sample_with_scheduler
 
     model, sd = build(LDCT_SMALL, "concatenate", seed=6)
     g = torch.Generator().manual_seed(31)
-    B, steps = 1, 50
+    steps = 50
     noise = torch.randn(B, 1, hw, hw, generator=g).to(DEV)
     cond = torch.rand(B, 1, hw, hw, generator=g).to(DEV)
     sched, _ = build_scheduler({"name": "flow_match_euler", "params": {}}, {})
@@ -296,9 +311,54 @@ def test_ldct_flowmatch_final_sample_psnr(hw):
         for t in orc.timesteps:
             pred = OD.denoiser_forward(sd, LDCT_SMALL, x, t.expand(B).to(DEV).float(), conditioning="concatenate",
                                        channels=1, context=cond)
-            x = orc.step(pred.cpu(), t, x.cpu()).prev_sample.to(DEV)
-    p = psnr(out.clamp(0, 1), x.clamp(0, 1))
-    assert p >= 40.0, p
+            x = orc.step(pred, t, x).prev_sample
+    for i in range(B):
+        p = psnr(out[i].clamp(0, 1), x[i].clamp(0, 1))
+        assert p >= PSNR_MIN, (hw, B, i, p)
+
+
+def test_config3_ddim_and_dpmsolver_final_sample_psnr():
+    """BASELINE configs[3]: the DDPM-trained LDCT UNet (`configs/LDCT/LDCT_ddpm_diffusers_nd.json`: full architecture,
+    256x256, betas 1e-4..0.02) sampled with `--scheduler ddim` (50 steps) and `--scheduler dpmsolver++` (20 steps):
+    final samples of the graph-replayed B200 path >= 40 dB PSNR against the fp32 oracle loop on the same weights, and
+    every step's epsilon within 1e-2 relative L2 along the oracle trajectory.  The weights are a conditioned fixture:
+    200 seeded epsilon-target training steps on synthetic LDCT pairs (tests/_fixtures.py; measured loss 0.009,
+    DDIM 59.5 dB, DPM-Solver++ 48.6 dB, per-step error <= 0.22e-2)."""
+    from _fixtures import synthetic_pair, train_epsilon_denoiser
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+    from fmdm_b200.pipelines.utils import build_scheduler, resolve_scheduler_override, sample_with_scheduler
+
+    hw, B = 256, 2
+    torch.manual_seed(0)
+    model = DiffusionUNetFactory().build(LDCT_SMALL, "concatenate", 1).to(DEV)
+    loss = train_epsilon_denoiser(model, hw=hw, batch=16, steps=200)
+    assert loss < 0.05, f"the epsilon fixture did not train (loss {loss})"
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    geval = torch.Generator(device=DEV).manual_seed(77)
+    _, cond = synthetic_pair(B, hw, geval)
+    noise = torch.randn(B, 1, hw, hw, generator=geval, device=DEV)
+    for sname, steps in (("ddim", 50), ("dpmsolver++", 20)):
+        ov = resolve_scheduler_override(sname)
+        params = {"beta_start": 1e-4, "beta_end": 0.02}
+        params.update(ov.get("params", {}))
+        mine, _ = build_scheduler({"name": ov["name"], "params": params}, {})
+        with torch.no_grad():
+            out = sample_with_scheduler(model, mine, steps, noise.shape, torch.device(DEV),
+                                        conditioning_mode="concatenate", conditioning_batch=cond, init_sample=noise)
+        orc = make_scheduler(sname, 1000, {"beta_start": 1e-4, "beta_end": 0.02})
+        orc.set_timesteps(steps)
+        x = noise.clone()
+        worst = 0.0
+        with torch.no_grad():
+            for t in orc.timesteps:
+                tt = t.expand(B).to(DEV).float()
+                pred = OD.denoiser_forward(sd, LDCT_SMALL, x, tt, conditioning="concatenate", channels=1, context=cond)
+                worst = max(worst, rel_l2(model(x, tt, context=cond), pred))
+                x = orc.step(pred.cpu(), t, x.cpu()).prev_sample.to(DEV)
+        assert worst < TOL_STEP, (sname, worst)
+        for i in range(B):
+            p = psnr(out[i].clamp(0, 1), x[i].clamp(0, 1))
+            assert p >= PSNR_MIN, (sname, i, p)
 
 
 def test_ddpm_graph_sampler_statistics():
@@ -379,17 +439,17 @@ def test_cross_attention_conditioning_parity(name, cfg):
             out = model(x, t, context_ca=ctx)
             again = model(x, t, context_ca=ctx)          # keys/values of the same context object come from the cache
         assert out.shape == ref.shape and torch.equal(out, again)
-        assert rel_l2(out, ref) < 1.2e-2, (name, hw, ctx_shape, rel_l2(out, ref))
+        assert rel_l2(out, ref) < TOL_STEP, (name, hw, ctx_shape, rel_l2(out, ref))
         ctx.mul_(0.5)                                     # in-place change of the context invalidates the cache
         ref2 = OD.denoiser_forward(sdd, cfg, x, t, conditioning="attention", channels=1, context_ca=ctx)
         with torch.no_grad():
             out2 = model(x, t, context_ca=ctx)
-        assert rel_l2(out2, ref2) < 1.2e-2 and rel_l2(out2, out) > 1e-3
+        assert rel_l2(out2, ref2) < TOL_STEP and rel_l2(out2, out) > 1e-3
     gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"denoiser_{name}.pt"),
                       weights_only=False)
     with torch.no_grad():
         out = model(gold["x"].to(DEV), gold["t"].to(DEV), context_ca=gold["context_ca"].to(DEV))
-    assert rel_l2(out.cpu(), gold["out"]) < 1.2e-2
+    assert rel_l2(out.cpu(), gold["out"]) < TOL_STEP  # measured 0.56 / 0.97 / 0.90e-2 (split-bf16 weights, <= 128 ch)
 
 
 def test_context_kv_kernel():

@@ -167,6 +167,103 @@ def test_dpmpp_orders():
     assert calls == [1, 2, 2, 2, 1]
 
 
+def _run_point_mass(s, n, x0, seed=3):
+    """Exact epsilon of a point-mass data distribution along the scheduler's own sigmas; returns (final x, c) with
+    c = the constant noise direction (x_t = alpha_t x0 + sigma_t c for every exact solver)."""
+    s.set_timesteps(n)
+    g = torch.Generator().manual_seed(seed)
+    a0, s0 = s._alpha_sigma(s.sigmas[0])
+    c = torch.randn(x0.shape, generator=g)
+    x = a0 * x0 + s0 * c
+    for i, t in enumerate(s.timesteps):
+        a, sg = s._alpha_sigma(s.sigmas[i])
+        x = s.step((x - a * x0) / sg, t, x).prev_sample
+    return x, c
+
+
+def test_dpmsolver_noise_prediction_known_answers():
+    """algorithm_type "dpmsolver" (the dpmsolver1 / dpmsolver2 aliases): construction with the zero final sigma raises
+    as diffusers does; with final_sigmas_type="sigma_min" the solver is exact on a point mass - epsilon is constant
+    along the trajectory, so x_end = alpha_min x0 + sigma_min c - for order 1 and order 2, and the order sequence follows
+    lower_order_final only below 15 steps."""
+    with pytest.raises(ValueError, match="sigma_min"):
+        make_scheduler("dpmsolver2")
+    with pytest.raises(ValueError, match="sigma_min"):
+        DPMSolverPPOracle(1000, algorithm_type="dpmsolver", solver_order=1)
+    x0 = torch.tensor([[[[0.25, -0.5], [0.75, 0.9]]]])
+    for name in ("dpmsolver1", "dpmsolver2"):
+        for n in (5, 20):
+            s = make_scheduler(name, 1000, {"beta_start": 1e-4, "beta_end": 0.02, "final_sigmas_type": "sigma_min"})
+            out, c = _run_point_mass(s, n, x0)
+            a_end, s_end = s._alpha_sigma(s.sigmas[-1])
+            assert float(s.sigmas[-1]) == pytest.approx(float(((1 - s.alphas_cumprod[0]) / s.alphas_cumprod[0]) ** 0.5))
+            assert float((out - (a_end * x0 + s_end * c)).abs().max()) < 2e-5, (name, n)
+    s = make_scheduler("dpmsolver2", 1000, {"final_sigmas_type": "sigma_min"})
+    for n, want in ((5, [1, 2, 2, 2, 1]), (20, [1] + [2] * 19)):
+        s.set_timesteps(n)
+        calls = []
+        first, second = s._first_order, s._second_order
+        s._first_order = lambda m0, sample: (calls.append(1), first(m0, sample))[1]
+        s._second_order = lambda sample: (calls.append(2), second(sample))[1]
+        x = torch.zeros(1, 1, 1, 1)
+        for t in s.timesteps:
+            x = s.step(torch.ones_like(x), t, x).prev_sample
+        assert calls == want
+        s._first_order, s._second_order = first, second
+
+
+def test_unipc_known_answers():
+    """UniPC (bh2, data prediction): same linspace schedule as DPM-Solver++, exact recovery of a point mass (the data
+    prediction is constant, so predictor and corrector both return alpha x0 + sigma c and the last step returns x0),
+    order sequence [1, 2, ..., 2, 1] with the corrector one order behind, and a closed-form first step: with order 1
+    UniP is DDIM in lambda space, x_1 = (sigma_1/sigma_0) x - alpha_1 expm1(-h) m0."""
+    from oracle.schedulers import UniPCOracle
+
+    s = UniPCOracle(1000, 1e-4, 0.02)
+    s.set_timesteps(20)
+    d = DPMSolverPPOracle(1000, 1e-4, 0.02)
+    d.set_timesteps(20)
+    assert torch.equal(s.timesteps, d.timesteps) and torch.equal(s.sigmas, d.sigmas)
+    x0 = torch.tensor([[[[0.25, -0.5], [0.75, 0.9]]]])
+    for order in (1, 2):
+        for n in (2, 5, 20):
+            out, _ = _run_point_mass(UniPCOracle(1000, 1e-4, 0.02, solver_order=order), n, x0)
+            assert float((out - x0).abs().max()) < 1e-5, (order, n)
+    # orders used by predictor / corrector over a 5-step run
+    s = UniPCOracle(1000)
+    s.set_timesteps(5)
+    pred, corr = [], []
+    p0, c0 = s._predict, s._correct
+    s._predict = lambda sample, order: (pred.append(order), p0(sample, order))[1]
+    s._correct = lambda m, last, order: (corr.append(order), c0(m, last, order))[1]
+    x = torch.full((1, 1, 1, 1), 0.3)
+    g = torch.Generator().manual_seed(0)
+    for t in s.timesteps:
+        x = s.step(torch.randn(1, 1, 1, 1, generator=g), t, x).prev_sample
+    assert pred == [1, 2, 2, 2, 1] and corr == [1, 2, 2, 2]
+    assert torch.isfinite(x).all()
+    # first step in closed form
+    s = UniPCOracle(1000, 1e-4, 0.02)
+    s.set_timesteps(10)
+    x = torch.tensor([[[[0.4, -1.2]]]])
+    e = torch.tensor([[[[0.7, 0.1]]]])
+    a0, s0 = s._alpha_sigma(s.sigmas[0].double())
+    a1, s1 = s._alpha_sigma(s.sigmas[1].double())
+    h = (a1.log() - s1.log()) - (a0.log() - s0.log())
+    m0 = (x.double() - s0 * e.double()) / a0
+    want = (s1 / s0) * x.double() - a1 * torch.expm1(-h) * m0
+    got = s.step(e, s.timesteps[0], x).prev_sample
+    assert torch.allclose(got.double(), want, rtol=1e-5, atol=1e-6)
+    # the corrector is consistent: fed the exact data prediction at the new point it leaves an exact sample unchanged
+    # (covered by the point-mass runs above) and it changes an inexact one
+    s = UniPCOracle(1000, 1e-4, 0.02)
+    s.set_timesteps(10)
+    x = torch.tensor([[[[0.4, -1.2]]]])
+    x1 = s.step(e, s.timesteps[0], x).prev_sample
+    x2 = s.step(e * 0.5, s.timesteps[1], x1).prev_sample
+    assert not torch.equal(s.last_sample, x1) and torch.isfinite(x2).all()
+
+
 def test_select_timesteps():
     s = make_scheduler("ddim")
     s.set_timesteps(50)

@@ -64,16 +64,25 @@ def batch(b, hw, seed):
 
 @pytest.mark.parametrize("name,cfg,hw,b", [("small32", SMALL, 32, 4), ("ldct64", LDCT, 64, 2), ("ldct128", LDCT, 128, 1),
                                            ("compvis32", COMPVIS, 32, 2), ("compvis_attn32", COMPVIS_ATTN, 32, 2)])
-def test_training_gradients_match_oracle(name, cfg, hw, b):
-    from fmdm_b200.training import flow_matching_loss
+@pytest.mark.parametrize("kind", ["fm", "eps"])
+def test_training_gradients_match_oracle(name, cfg, hw, b, kind):
+    """Loss and EVERY parameter gradient of one step against torch fp32 autograd through the oracle, for the
+    flow-matching loss (`flow_matching_lib.py:150-169`) and the epsilon-target loss (`diffusion_lib.py:153-176`)."""
+    from fmdm_b200.training import diffusion_loss, flow_matching_loss
 
     model, sd = build(cfg)
     clean, ldct, noise, t = batch(b, hw, 11)
-    loss = flow_matching_loss(model, clean, ldct, noise=noise, t=t)
+    if kind == "fm":
+        loss = flow_matching_loss(model, clean, ldct, noise=noise, t=t)
+        ref_loss, ref_grads = OT.loss_and_grads(sd, cfg, clean, ldct, noise, t, 1000)
+    else:
+        ac = torch.cumprod(1 - torch.linspace(1e-4, 0.02, 1000), 0).to(DEV)
+        ts = (t * 999).long()
+        loss = diffusion_loss(model, clean, ldct, ac ** 0.5, (1 - ac) ** 0.5, noise=noise, timesteps=ts)
+        ref_loss, ref_grads = OT.loss_and_grads(sd, cfg, clean, ldct, noise, ts, 1000, alphas_cumprod=ac)
     loss.backward()
-    ref_loss, ref_grads, _ = oracle_loss_and_grads(sd, cfg, clean, ldct, noise, t)
-    assert abs(loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
-    worst, flat_a, flat_b = 0.0, [], []
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())  # measured <= 6e-4
+    flat_a, flat_b = [], []
     for k, p in model.named_parameters():
         assert p.grad is not None, k
         g, r = p.grad.float(), ref_grads[k]
@@ -81,12 +90,22 @@ def test_training_gradients_match_oracle(name, cfg, hw, b):
         assert torch.isfinite(g).all(), k
         flat_a.append(g.reshape(-1))
         flat_b.append(r.reshape(-1))
-        if r.norm() > 1e-3 * max(1.0, float(r.numel()) ** 0.5) * 1e-3:
-            worst = max(worst, rel_l2(g, r))
+    total_norm = float(torch.cat(flat_b).norm())
+    worst_rel = worst_abs = 0.0
+    for k, p in model.named_parameters():
+        g, r = p.grad.float(), ref_grads[k]
+        # every parameter: its gradient error measured against the whole gradient (measured <= 6.0e-3)
+        worst_abs = max(worst_abs, float((g - r).norm()) / total_norm)
+        assert float((g - r).norm()) / total_norm < 1e-2, (name, kind, k)
+        # every parameter that carries a measurable share of the gradient: its own relative error (measured <= 2.9e-2).
+        # (key biases of softmax attention have an exactly zero gradient - softmax is invariant to them - so their
+        # fp32 reference is pure rounding noise of order 1e-10 and carries no relative information.)
+        if float(r.norm()) >= 1e-4 * total_norm:
+            worst_rel = max(worst_rel, rel_l2(g, r))
+            assert rel_l2(g, r) < 3.5e-2, (name, kind, k, rel_l2(g, r))
     total = rel_l2(torch.cat(flat_a), torch.cat(flat_b))
-    # bf16 activations + bf16-rounded weights through ~60 layers forward and back: the whole-gradient error stays
-    # within a few 1e-2 relative L2 (the forward alone sits at ~0.8e-2 against the same oracle)
-    assert total < 5e-2, (name, total, worst)
+    # bf16 activations + bf16-rounded weights through ~60 layers forward and back (measured 0.36-1.5e-2)
+    assert total < 2e-2, (name, kind, total, worst_rel, worst_abs)
 
 
 def test_training_step_reduces_loss_and_tracks_torch_adamw():
@@ -223,3 +242,113 @@ def test_pack_plan_survives_parameter_reseating():
     ref3, _, _ = oracle_loss_and_grads(cur, SMALL, clean, ldct, noise, t)
     l3 = float(tr.step(clean, ldct, noise=noise, t=t))
     assert abs(l3 - float(ref3)) <= 2e-2 * abs(float(ref3)), (l1, l2, l3, float(ref3))
+
+
+def test_graph_sampler_recaptures_after_weight_updates():
+    """sample -> optimiser step / load_state_dict -> sample (the reference's periodic visual sampling during training):
+    the graph-replayed sampler must re-capture when the parameters change - its captured kernels hold raw pointers to
+    packed bf16 weights and fp32 parameters - and agree bit for bit with the step-by-step path on the NEW weights."""
+    from fmdm_b200.pipelines import utils as PU
+    from fmdm_b200.training import FlowMatchingTrainer
+
+    model, sd = build(SMALL, seed=5)
+    clean, ldct, noise, t = batch(4, 32, 7)
+    sched, _ = PU.build_scheduler({"name": "flow_match_euler", "params": {}}, {})
+    dev = torch.device(DEV)
+
+    def sample(graph):
+        model.eval()
+        with torch.no_grad():
+            return PU.sample_with_scheduler(model, sched, 6, tuple(noise.shape), dev, conditioning_mode="concatenate",
+                                            conditioning_batch=ldct, init_sample=noise, use_cuda_graph=graph)
+
+    a0 = sample(True)
+    assert torch.equal(a0, sample(False))
+    gs = next(iter(PU._GRAPH_CACHE.values()))
+    caps = gs.captures
+    assert torch.equal(sample(True), a0) and gs.captures == caps          # unchanged weights: no re-capture
+    tr = FlowMatchingTrainer(model, lr=1e-3, cuda_graph=False)            # re-seats every parameter (new addresses)
+    a1 = sample(True)
+    assert gs.captures == caps + 1 and torch.equal(a1, a0)                # same values at new addresses: same samples
+    for _ in range(2):
+        tr.step(clean, ldct, noise=noise, t=t)                            # in-place update at fixed addresses
+    a2 = sample(True)
+    assert gs.captures == caps + 2
+    assert torch.equal(a2, sample(False)) and not torch.equal(a2, a1)
+    model.load_state_dict(sd)                                             # in-place load of the original weights
+    a3 = sample(True)
+    assert gs.captures == caps + 3 and torch.equal(a3, a0)
+    # a second scheduler object with the same config replays from the same graph (decode_diffusion_batch builds a new
+    # scheduler per batch)
+    sched2, _ = PU.build_scheduler({"name": "flow_match_euler", "params": {}}, {})
+    with torch.no_grad():
+        a4 = PU.sample_with_scheduler(model, sched2, 6, tuple(noise.shape), dev, conditioning_mode="concatenate",
+                                      conditioning_batch=ldct, init_sample=noise)
+    assert gs.captures == caps + 3 and torch.equal(a4, a0)
+    # one-step plans (last_n_steps=1) fit the two-row minimum of the static tables
+    with torch.no_grad():
+        b1 = PU.sample_with_scheduler(model, sched2, 6, tuple(noise.shape), dev, conditioning_mode="concatenate",
+                                      conditioning_batch=ldct, init_sample=noise, last_n_steps=1)
+        b2 = PU.sample_with_scheduler(model, sched2, 6, tuple(noise.shape), dev, conditioning_mode="concatenate",
+                                      conditioning_batch=ldct, init_sample=noise, last_n_steps=1, use_cuda_graph=False)
+    assert torch.equal(b1, b2)
+
+
+def test_fused_adamw_state_dict_is_torch_layout():
+    """`FusedAdamW.state_dict()` is the torch.optim layout: a torch.optim.AdamW over the same parameters loads it and
+    continues identically, and FusedAdamW resumes from a torch.optim.AdamW checkpoint (the 'optimizer' entry of the
+    reference's {flow,diff}_{best,last}.pt, `flow_matching_lib.py:197-211`)."""
+    from fmdm_b200.training import FlowMatchingTrainer, FusedAdamW
+
+    model, sd = build(SMALL, seed=9)
+    tr = FlowMatchingTrainer(model, lr=2e-4, weight_decay=0.01, cuda_graph=False)
+    clean, ldct, noise, t = batch(4, 32, 13)
+    for _ in range(3):
+        tr.step(clean, ldct, noise=noise, t=t)
+    state = tr.optimizer.state_dict()
+    assert set(state) == {"state", "param_groups"} and len(state["state"]) == len(list(model.parameters()))
+    assert state["param_groups"][0]["params"] == list(range(len(state["state"])))
+    # torch.optim.AdamW accepts it
+    clone = {k: torch.nn.Parameter(v.detach().clone()) for k, v in model.named_parameters()}
+    ref_opt = torch.optim.AdamW(clone.values(), lr=2e-4, weight_decay=0.01)
+    ref_opt.load_state_dict(state)
+    first = next(iter(clone.values()))
+    assert float(ref_opt.state[first]["step"]) == 3.0
+    o, n = tr.optimizer.flat.slice_of(next(iter(model.parameters())))
+    assert torch.equal(ref_opt.state[first]["exp_avg"].reshape(-1), tr.optimizer.exp_avg[o:o + n])
+    # one more step on both from the same gradients: same parameters
+    tr.step(clean, ldct, noise=noise, t=t)
+    for (k, p), q in zip(model.named_parameters(), clone.values()):
+        q.grad = p.grad.detach().clone()
+    ref_opt.step()
+    for (k, p), q in zip(model.named_parameters(), clone.values()):
+        assert torch.allclose(p.detach(), q.detach(), rtol=2e-5, atol=1e-7), k
+    # and the way back: a fresh FusedAdamW resumes from torch's state_dict
+    model2, _ = build(SMALL, seed=9)
+    opt2 = FusedAdamW(model2.parameters(), lr=2e-4, weight_decay=0.01)
+    opt2.load_state_dict(ref_opt.state_dict())
+    assert opt2.step_count == 4
+    p0 = next(iter(model2.parameters()))
+    o, n = opt2.flat.slice_of(p0)
+    assert torch.equal(opt2.exp_avg_sq[o:o + n], ref_opt.state[first]["exp_avg_sq"].reshape(-1))
+    with pytest.raises(ValueError, match="torch.optim layout"):
+        opt2.load_state_dict({"step": 1, "exp_avg": None, "exp_avg_sq": None})
+
+
+def test_diffusion_trainer_epsilon_target():
+    """`DiffusionTrainer` (`diffusion_lib.py:141-185`): the step's loss equals the oracle's on the same noise / timesteps,
+    graph-replayed steps draw fresh noise and timesteps on the device and keep training."""
+    from fmdm_b200.pipelines.utils import build_scheduler
+    from fmdm_b200.training import DiffusionTrainer
+
+    model, sd = build(SMALL, seed=10)
+    sched, _ = build_scheduler({"name": "ddpm", "params": {"beta_start": 1e-4, "beta_end": 0.02}}, {})
+    tr = DiffusionTrainer(model, sched, lr=2e-4, cuda_graph=True, graph_warmup=2)
+    clean, ldct, noise, t = batch(8, 32, 15)
+    ts = (t * 999).long()
+    ref, _ = OT.loss_and_grads(sd, SMALL, clean, ldct, noise, ts, 1000, alphas_cumprod=sched.alphas_cumprod.to(DEV))
+    got = float(tr.step(clean, ldct, noise=noise, t=ts))
+    assert abs(got - float(ref)) <= 2e-3 * abs(float(ref)), (got, float(ref))
+    losses = [float(tr.step(clean, ldct)) for _ in range(14)]
+    assert tr._graph is not None and all(torch.isfinite(torch.tensor(losses)))
+    assert sum(losses[-4:]) / 4 < sum(losses[:4]) / 4
