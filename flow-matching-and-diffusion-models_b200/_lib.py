@@ -89,6 +89,7 @@ SIGNATURES = {
     "fm_weight_prepack_lo_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_conv_stem_f32_bf16": (
         C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "fm_stem_im2col_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "fm_conv_stem_stats_rows": (C.c_int, [_i32, _i32, _i32, _i32]),
     "fm_conv_head_bf16_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "fm_groupnorm_workspace_elems": (C.c_int64, [_i32, _i64, _i32, _i32]),
@@ -132,7 +133,7 @@ SIGNATURES = {
     "fm_groupnorm_bwd_workspace_elems": (C.c_int64, [_i32, _i64, _i32]),
     "fm_groupnorm_bwd_bf16": (
         C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
-                  _vp, _vp]),
+                  _vp, _vp, _vp]),
     "fm_groupnorm_bwd_blocks": (C.c_int32, [_i32, _i64]),
     "fm_colsum_finish_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "fm_attention_bwd_bf16": (

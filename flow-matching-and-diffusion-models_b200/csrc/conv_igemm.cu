@@ -404,7 +404,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
             int vidx;
             const float red0 = epi_quad_stats(v, valid, lane, vidx);
             const int qcol = col0 + (vidx & 7) * 4;
-            if ((lane & 1) == 0 && qcol < p.Cout && n0 < p.B)
+            // (tiles of 2 or 4 whole images: a lane quadrant never straddles images, and row m_tile*4 + quad is row
+            // quad % (4/Nt) of image n0 + quad / (4/Nt), i.e. the per-image rows stay contiguous)
+            if ((lane & 1) == 0 && qcol < p.Cout && n0 + ((quad * p.Nt) >> 2) < p.B)
               p.gn_partial[(((size_t)m_tile * 4 + quad) * (p.Cout >> 2) + (qcol >> 2)) * 2 + (vidx >> 3)] = red0;
           }
           epi_pack_store(v, rowp, chunk0, row);
@@ -645,7 +647,8 @@ static int plan_conv(const fm_conv_params* p, ConvPlan* pl) {
     pl->sch = roll_schedule(p->B, pl->Ho, pl->tiles_w, pl->n_tiles, sm_count() / 2);
     pl->stats_rows = pl->sch.chunks * pl->tiles_w * 4;      // one row per (strip, TMEM lane quadrant)
   } else {
-    pl->stats_rows = (pl->Nt == 1) ? pl->tiles_w * pl->tiles_h * 4 : 0;  // one row per (M tile, lane quadrant)
+    // one row per (M tile, lane quadrant); tiny images (2 or 4 per tile, >= 32 tile rows each): 4/Nt rows per image
+    pl->stats_rows = (pl->Nt == 1) ? pl->tiles_w * pl->tiles_h * 4 : ((pl->Nt == 2 || pl->Nt == 4) ? 4 / pl->Nt : 0);
   }
   if (p->Cout % 4) pl->stats_rows = 0;
   return 0;
@@ -737,7 +740,7 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
   kp.log_wt = 0; while ((1 << kp.log_wt) < kp.Wt) ++kp.log_wt;
   kp.log_ht = 0; while ((1 << kp.log_ht) < kp.Ht) ++kp.log_ht;
   FM_REQUIRE(p->gn_stats == nullptr || pl.stats_rows > 0,
-             "conv: fused GroupNorm statistics need >= 128 pixels per image and Cout %% 4 == 0 (fm_conv_stats_rows)");
+             "conv: fused GroupNorm statistics need >= 32 tile rows per image and Cout %% 4 == 0 (fm_conv_stats_rows)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   kp.n_tiles = pl.n_tiles;
   kp.m_tiles = pl.m_tiles;

@@ -129,6 +129,54 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __
   }
 }
 
+// Stem on the tensor cores, step 1: the 3x3 neighbourhoods of the (tiny-Cin) fp32 NCHW inputs as a bf16 NHWC tensor
+// [B][H][W][Kp], column k = ci*9 + kh*3 + kw (the OIHW inner order, so the weight matrix is w.reshape(Cout, Cin*9)),
+// columns >= 9*Cin zero.  The 1x1 implicit-GEMM kernel then does the contraction (K padded to one 64-deep block by
+// TMA zero fill) and writes the first big activation tensor at store bandwidth; the CUDA-core stem above spends 19
+// GFLOP of fp32 FMAs on it (0.97 ms at B=16, 512x512 against a 0.17 ms write floor).  One thread per pixel: its 9*Cin
+// loads are coalesced along the row and hit L1 for the 3x3 overlap.
+template <int KP>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x0, int C0,
+                                                         const float* __restrict__ x1, int C1, float in_scale,
+                                                         float in_shift, uint4* __restrict__ out, int H, int W,
+                                                         int64_t total) {
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int HW = H * W;
+  const int n = (int)(pix / HW);
+  const int rem = (int)(pix - (int64_t)n * HW);
+  const int h = rem / W, w = rem - h * W;
+  const int Cin = C0 + C1;
+  float v[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < KP / 9; ++ci) {
+    if (ci < Cin) {
+      const float* src = (ci < C0) ? x0 + ((size_t)n * C0 + ci) * HW : x1 + ((size_t)n * C1 + (ci - C0)) * HW;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int iw = w + kw - 1;
+          // zero padding applies AFTER the optional 2x-1 centering
+          if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+            v[ci * 9 + kh * 3 + kw] = fmaf(__ldg(src + ih * W + iw), in_scale, in_shift);
+        }
+      }
+    }
+  }
+  uint4* dst = out + pix * (KP / 8);
+#pragma unroll
+  for (int c = 0; c < KP / 8; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); o.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+    o.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); o.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    dst[c] = o;
+  }
+}
+
 // Head: a block computes a 32 x 4 tile of output pixels from a (34 x 6)-pixel halo tile staged in shared memory
 // (row pitch Cin*2+16 bytes => conflict-free 16-byte reads with one thread per pixel); weights fp32 in smem as
 // [tap][ci][co].  Global reads are fully coalesced (NHWC rows are contiguous), every input byte is read once per tile.
@@ -393,6 +441,31 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
   conv_stem_kernel<<<dim3(bpi, B), kStemThreads, smem, (cudaStream_t)stream>>>(
       x0, C0, x1, C1, in_scale, in_shift, weight_oihw, bias, reinterpret_cast<uint4*>(out), H, W, Cout, gn_stats);
   FM_LAUNCH_CHECK("conv_stem_kernel");
+  return 0;
+}
+
+extern "C" int fm_stem_im2col_bf16(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale,
+                                   float in_shift, void* out, int32_t B, int32_t H, int32_t W, int32_t Kp,
+                                   fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x0 && C0 > 0 && (x1 != nullptr) == (C1 > 0), "stem_im2col: inconsistent sources");
+  FM_REQUIRE(out && B > 0 && H > 0 && W > 0, "stem_im2col: bad argument");
+  FM_REQUIRE(Kp % 8 == 0 && Kp >= 9 * (C0 + C1) && Kp <= 72, "stem_im2col: Kp=%d must be a multiple of 8 covering 9*Cin "
+             "(<= 72)", Kp);
+  FM_REQUIRE((int64_t)H * W < (1ll << 31), "stem_im2col: image too large for 32-bit indexing");
+  const int64_t total = (int64_t)B * H * W;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint4* o = reinterpret_cast<uint4*>(out);
+#define FM_IM2COL_CASE(K)                                                                                            \
+  case K: stem_im2col_kernel<K><<<blocks, 256, 0, st>>>(x0, C0, x1, C1, in_scale, in_shift, o, H, W, total); break;
+  switch (Kp) {
+    FM_IM2COL_CASE(16) FM_IM2COL_CASE(24) FM_IM2COL_CASE(32) FM_IM2COL_CASE(40) FM_IM2COL_CASE(48) FM_IM2COL_CASE(56)
+    FM_IM2COL_CASE(64) FM_IM2COL_CASE(72)
+    default: set_error("stem_im2col: unsupported Kp=%d", Kp); return FM_ERR_UNSUPPORTED;
+  }
+#undef FM_IM2COL_CASE
+  FM_LAUNCH_CHECK("stem_im2col_kernel");
   return 0;
 }
 

@@ -19,23 +19,28 @@ namespace fm {
 // =============================================================================================================
 // generic fixed-order reduction of partials: out[o][i] = sum_p in[o][p][i]
 // =============================================================================================================
+// out2 (optional): results with index >= split go to out2[idx - split] (two destinations for one reduction, e.g. the
+// dgamma / dbeta rows written straight into two parameter-gradient slices)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                               int parts, int64_t inner, int64_t total) {
+                                                               int parts, int64_t inner, int64_t total,
+                                                               float* __restrict__ out2, int64_t split) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t o = idx / inner, i = idx - o * inner;
     const float* src = in + (o * parts) * inner + i;
     float acc = 0.f;
     for (int p = 0; p < parts; ++p) acc += src[(int64_t)p * inner];
-    out[idx] = acc;
+    if (out2 != nullptr && idx >= split) out2[idx - split] = acc;
+    else out[idx] = acc;
   }
 }
 
-static int launch_reduce(const float* in, float* out, int64_t outer, int parts, int64_t inner, cudaStream_t st) {
+static int launch_reduce(const float* in, float* out, int64_t outer, int parts, int64_t inner, cudaStream_t st,
+                         float* out2 = nullptr, int64_t split = 0) {
   const int64_t total = outer * inner;
   if (total == 0) return 0;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  reduce_partials_kernel<<<blocks, 256, 0, st>>>(in, out, parts, inner, total);
+  reduce_partials_kernel<<<blocks, 256, 0, st>>>(in, out, parts, inner, total, out2, split);
   FM_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }
@@ -1263,7 +1268,8 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
                                      const float* stats, const float* gamma, const float* beta,
                                      const float* scale_shift, int64_t ss_stride, int32_t silu, int32_t B, int64_t HW,
                                      int32_t groups, float* workspace, void* dx0, void* dx1, float* dgamma_dbeta,
-                                     float* dscale_shift, float* dx_colsum_partials, fm_stream_t stream) {
+                                     float* dscale_shift, float* dx_colsum_partials, float* dbeta,
+                                     fm_stream_t stream) {
   const int32_t C = C0 + C1;
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x0 && dout && stats && gamma && beta && workspace && dx0 && dgamma_dbeta, "groupnorm_bwd: null pointer");
@@ -1297,7 +1303,7 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
                                                                     inv_n, tab, dgb, dscale_shift);
   FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
   /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
-  if (int e = launch_reduce(dgb, dgamma_dbeta, 1, B, 2LL * C, st)) return e;
+  if (int e = launch_reduce(dgb, dgamma_dbeta, 1, B, 2LL * C, st, dbeta, C)) return e;
   gn_bwd_apply_kernel<<<dim3(nblk, B), sthreads,
                         dx_colsum_partials ? (size_t)lanes * C * sizeof(float) : 0, st>>>(
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),

@@ -49,7 +49,11 @@ class BaseUNetND(nn.Module, ABC):
         if plan is None:
             return emb
         weight, bias, offsets, silu = plan
-        return TembPack(emb, ops.linear_f32(emb, weight, bias, silu_in=silu), offsets)
+        if emb.stride(0) == 0:  # one timestep for the whole batch (sampling loop): project one row, broadcast it
+            proj = ops.linear_f32(emb[:1], weight, bias, silu_in=silu).expand(emb.shape[0], -1)
+        else:
+            proj = ops.linear_f32(emb, weight, bias, silu_in=silu)
+        return TembPack(emb, proj, offsets)
 
     def _wants_autograd(self, x: torch.Tensor, t_table) -> bool:
         """Autograd is recording, the module is in training mode and has trainable parameters: run the
@@ -87,7 +91,9 @@ class BaseUNetND(nn.Module, ABC):
 
             return self._postprocess_output(graph.unet_forward(self, x, t, context))
         if t_table is not None:
-            emb = self._build_time_embedding(None, x, t_table=t_table, step_dev=step_dev)
+            # the sampling loop feeds one timestep to the whole batch (`pipelines/utils.py:206-209` expands a scalar):
+            # the time embedding and every projection of it are computed for ONE row and broadcast (stride 0)
+            emb = self._build_time_embedding(None, x[:1], t_table=t_table, step_dev=step_dev).expand(x.shape[0], -1)
         else:
             t = self._normalize_timesteps(t, x)
             emb = self._build_time_embedding(t, x)

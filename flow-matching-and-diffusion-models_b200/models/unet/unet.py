@@ -153,7 +153,9 @@ class EfficientUNetND(BaseUNetND):
         if cin != stem.in_channels:
             raise ValueError(f"EfficientUNetND expected {stem.in_channels} input channels, got {cin}")
         if cin <= 8:
-            h = ops.conv_stem(x, context, f32(stem.weight), f32(stem.bias))
+            packed = None if self.weight_split else self._cache.get("stem_tc", [stem.weight],
+                                                                    lambda: ops.stem_pack(stem.weight))
+            h = ops.conv_stem(x, context, f32(stem.weight), f32(stem.bias), packed=packed)
         else:
             h = self.input_blocks[0][0](x if context is None else torch.cat([x, context.to(x.dtype)], 1))
         hs = [h]

@@ -110,8 +110,11 @@ class UNetDiffusersND(BaseUNetND):
         if self.spatial_dims != 2:
             out_of_scope("UNetDiffusersND with spatial_dims != 2")
         if cin <= 8:
-            return ops.conv_stem(x, context, f32(self.conv_in.weight), f32(self.conv_in.bias), in_scale=scale,
-                                 in_shift=shift)
+            w = self.conv_in.weight
+            # split-weight (narrow) models keep the fp32 CUDA-core stem; the others take the tensor-core stem when large
+            packed = None if self.weight_split else self._stem_cache_get("stem_tc", [w], lambda: ops.stem_pack(w))
+            return ops.conv_stem(x, context, f32(w), f32(self.conv_in.bias), in_scale=scale, in_shift=shift,
+                                 packed=packed)
         full = x if context is None else torch.cat([x, context.to(x.dtype)], 1)
         if self.center_input_sample:
             full = 2 * full - 1.0
@@ -120,13 +123,16 @@ class UNetDiffusersND(BaseUNetND):
         pw = self._stem_pack()
         return ops.conv2d([ops.to_nhwc_bf16(full)], pw, bias=f32(self.conv_in.bias))
 
-    def _stem_pack(self):
+    def _stem_cache_get(self, key, params, build):
         if not hasattr(self, "_stem_cache"):
             from ..._runtime import ParamCache
 
             self._stem_cache = ParamCache()
+        return self._stem_cache.get(key, params, build)
+
+    def _stem_pack(self):
         w = self.conv_in.weight
-        return self._stem_cache.get("stem", [w], lambda: ops.pack_conv_weight([(w, 0, w.shape[1])]))
+        return self._stem_cache_get("stem", [w], lambda: ops.pack_conv_weight([(w, 0, w.shape[1])]))
 
     def _run_network(self, x, emb: torch.Tensor, context_ca) -> torch.Tensor:
         x, context = x

@@ -174,6 +174,7 @@ def conv2d(
     want_stats: bool = False,
     norm: Optional[Sequence] = None,
     upsample_out: bool = False,
+    prof_tag: Optional[str] = None,
 ) -> torch.Tensor:
     """Implicit-GEMM conv over the virtual channel concat of `srcs` (one K segment per source).
 
@@ -247,7 +248,7 @@ def conv2d(
     _lib.check(lib.fm_conv2d_igemm_bf16(C.byref(p), _stream()), "conv2d_igemm_bf16")
     if e0 is not None:
         kind = lib.fm_conv_kernel_kind(C.byref(p))
-        tag = {1: "conv_rolling", 2: "conv_rolling_xf"}.get(kind, "conv_tile")
+        tag = prof_tag or {1: "conv_rolling", 2: "conv_rolling_xf"}.get(kind, "conv_tile")
         _prof_end(tag, 2.0 * b * ho * wo * weight.cout * weight.mat.shape[1], e0)
     if stats_ws is not None:
         # with upsample_out the partials describe the [Ho][Wo] result; each value appears 4x in `out`, so the
@@ -257,10 +258,26 @@ def conv2d(
     return out
 
 
-def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0, want_stats: bool = True) -> torch.Tensor:
+STEM_TENSOR_MIN_PIXELS = 1 << 18  # B*H*W from which conv_in runs as im2col + 1x1 tensor-core GEMM
+
+
+def stem_pack(weight_oihw: torch.Tensor) -> PackedConvWeight:
+    """conv_in's weight as the K-major matrix of the tensor-core stem: w.reshape(Cout, Cin*9), zero-padded to Kp."""
+    cout, cin = weight_oihw.shape[0], weight_oihw.shape[1]
+    kp = (9 * cin + 7) // 8 * 8
+    w2 = torch.zeros((cout, kp), dtype=torch.float32, device=weight_oihw.device)
+    w2[:, :9 * cin] = weight_oihw.detach().to(torch.float32).reshape(cout, 9 * cin)
+    return pack_conv_weight([(w2, 0, kp)])
+
+
+def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0, want_stats: bool = True,
+              packed: Optional[PackedConvWeight] = None) -> torch.Tensor:
     """fp32 NCHW (x0 [, x1]) -> bf16 NHWC, 3x3 s1 p1; fuses the conditioning concat and the 2x-1 centering.
 
-    want_stats: also emit the GroupNorm partial statistics of the output (`out._fm_stats`, as `conv2d` does)."""
+    want_stats: also emit the GroupNorm partial statistics of the output (`out._fm_stats`, as `conv2d` does).
+    packed (`stem_pack(weight)`): on large inputs the conv runs on the tensor cores - `fm_stem_im2col_bf16` writes the
+    3x3 neighbourhoods as a [B][H][W][Kp] bf16 tensor and the 1x1 implicit GEMM contracts it (store-bandwidth bound
+    instead of fp32-FMA bound); small inputs keep the fp32 CUDA-core kernel."""
     lib = _lib.lib()
     require_cuda(x0, "conv_stem")
     x0 = x0.to(torch.float32).contiguous()
@@ -270,6 +287,17 @@ def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0, want_sta
         x1 = x1.to(torch.float32).contiguous()
         c1 = x1.shape[1]
     cout = weight_oihw.shape[0]
+    if packed is not None and b * h * w >= STEM_TENSOR_MIN_PIXELS and 9 * (c0 + c1) <= 72:
+        kp = packed.seg_channels[0]
+        cols = empty_nhwc(b, kp, h, w, x0.device)
+        e0 = _prof_begin()
+        _lib.check(
+            lib.fm_stem_im2col_bf16(x0.data_ptr(), c0, _ptr(x1), c1, float(in_scale), float(in_shift), cols.data_ptr(),
+                                    b, h, w, kp, _stream()),
+            "stem_im2col",
+        )
+        _prof_end("conv_stem_im2col", 2.0 * b * h * w * kp, e0)
+        return conv2d([cols], packed, bias=bias, want_stats=want_stats, prof_tag="conv_stem")
     out = empty_nhwc(b, cout, h, w, x0.device)
     stats_ws, rows = None, 0
     if want_stats and cout % 8 == 0:

@@ -19,6 +19,33 @@ from ..ops import _ptr, _stream
 BF16 = torch.bfloat16
 
 
+# Direct parameter gradients.  The trainers keep every `.grad` as a view of one flat, pre-zeroed buffer
+# (`training.optim.FlatBuffers`).  With DIRECT_PARAM_GRADS set (one backward per optimiser step, every parameter used
+# once per step - true for both denoisers), the backward kernels write parameter gradients STRAIGHT into those views
+# and the Functions return None for them: autograd's AccumulateGrad - one ATen `add` launch per parameter, ~450 per
+# step, plus a temporary of the gradient's size - disappears from the step.  GRAD_READY_HOOK (the bucketed all-reduce's
+# countdown) is then called by hand, since no accumulate-grad hook fires for a None gradient.
+DIRECT_PARAM_GRADS = False
+GRAD_READY_HOOK = None
+
+
+def _grad_target(param, shape=None):
+    """The `.grad` view of `param` to write into directly, or None (autograd accumulates the returned gradient)."""
+    if not DIRECT_PARAM_GRADS or not isinstance(param, torch.nn.Parameter) or not param.requires_grad:
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() % 16:
+        return None
+    if shape is not None and tuple(g.shape) != tuple(shape):
+        return None
+    return g
+
+
+def _grad_written(param) -> None:
+    if GRAD_READY_HOOK is not None:
+        GRAD_READY_HOOK(param)
+
+
 def _ws(n: int, device, dtype=torch.float32) -> torch.Tensor:
     return torch.empty((max(int(n), 1),), dtype=dtype, device=device)
 
@@ -55,13 +82,14 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, ksize: in
     )
 
 
-def colsum(dy: torch.Tensor, want_total: bool):
-    """(per-sample [B][C] fp32 sums over pixels, total [C] or None) of a bf16 NHWC gradient."""
+def colsum(dy: torch.Tensor, want_total: bool, total: Optional[torch.Tensor] = None):
+    """(per-sample [B][C] fp32 sums over pixels, total [C] or None) of a bf16 NHWC gradient; `total` may be given."""
     lib = _lib.lib()
     b, c, h, w = dy.shape
     ws = _ws(lib.fm_colsum_workspace_elems(b, h * w, c), dy.device)
     out = torch.empty((b, c), dtype=torch.float32, device=dy.device)
-    total = torch.empty((c,), dtype=torch.float32, device=dy.device) if want_total else None
+    if total is None and want_total:
+        total = torch.empty((c,), dtype=torch.float32, device=dy.device)
     _lib.check(lib.fm_colsum_bf16(dy.data_ptr(), ws.data_ptr(), out.data_ptr(), _ptr(total), b, h * w, c, _stream()),
                "colsum")
     return out, total
@@ -129,6 +157,7 @@ class _ConvFn(Function):
         ctx.meta = meta
         ctx.flags = (bias is not None, addvec is not None, residual is not None)
         ctx.params = weights  # the tensors as passed (Parameters / views of them): the pack plan keys on their storage
+        ctx.bias_param = bias
         ctx.save_for_backward(*srcs, *weights)
         return out
 
@@ -152,32 +181,44 @@ class _ConvFn(Function):
                 if dyz is None:
                     dyz = zero_insert2x(dy)
                 grads[i] = ops.conv2d([dyz], pw)
-        dws = {}
+        dws, direct = {}, set()
         for i, (wi, cb, cc) in enumerate(segs):
             if not need[1 + nsrc + wi]:
                 continue
             w = weights[wi]
             if wi not in dws:
-                covered = sum(c for j, _, c in segs if j == wi)
-                dws[wi] = (torch.empty if covered == w.shape[1] else torch.zeros)(
-                    w.shape, dtype=torch.float32, device=w.device)
+                target = _grad_target(ctx.params[wi], w.shape)
+                if target is not None:      # the flat gradient view (pre-zeroed): written in place, nothing returned
+                    dws[wi] = target
+                    direct.add(wi)
+                else:
+                    covered = sum(c for j, _, c in segs if j == wi)
+                    dws[wi] = (torch.empty if covered == w.shape[1] else torch.zeros)(
+                        w.shape, dtype=torch.float32, device=w.device)
             ks = 1 if w.dim() == 2 else int(w.shape[-1])
             conv_wgrad(dy, srcs[i], dws[wi], ksize=ks, stride=stride, c_begin=cb)
         for wi, dw in dws.items():
-            grads[nsrc + wi] = dw
+            if wi in direct:
+                _grad_written(ctx.params[wi])
+            else:
+                grads[nsrc + wi] = dw
         if (has_bias and need[1 + nsrc + nw]) or (has_addvec and need[1 + nsrc + nw + 1]):
             tagged = getattr(dy, "_fm_colsum", None)
             part = tagged[0] if tagged is not None and tagged[1] == dy._version else None
+            btarget = _grad_target(ctx.bias_param, (dy.shape[1],)) if has_bias and need[1 + nsrc + nw] else None
             if part is not None and tuple(part.shape[::2]) == (dy.shape[0], dy.shape[1]):
                 # dy is the dx of a GroupNorm backward that already summed its columns per row block
                 per_sample = torch.empty((dy.shape[0], dy.shape[1]), dtype=torch.float32, device=dy.device)
-                total = torch.empty((dy.shape[1],), dtype=torch.float32, device=dy.device) if has_bias else None
+                total = btarget if btarget is not None else (
+                    torch.empty((dy.shape[1],), dtype=torch.float32, device=dy.device) if has_bias else None)
                 _lib.check(_lib.lib().fm_colsum_finish_f32(part.data_ptr(), per_sample.data_ptr(), _ptr(total),
                                                            dy.shape[0], part.shape[1], dy.shape[1], _stream()),
                            "colsum_finish")
             else:
-                per_sample, total = colsum(dy, has_bias)
-            if has_bias:
+                per_sample, total = colsum(dy, has_bias, total=btarget)
+            if btarget is not None:
+                _grad_written(ctx.bias_param)
+            elif has_bias:
                 grads[nsrc + nw] = total
             if has_addvec:
                 grads[nsrc + nw + 1] = per_sample
@@ -242,6 +283,7 @@ class _GroupNormFn(Function):
                                                0 if ss is None else ss.stride(0), int(silu), out.data_ptr(), st),
                    "groupnorm_apply")
         ctx.cfg = (groups, bool(silu), ss is not None, x1 is not None)
+        ctx.affine = (gamma, beta)
         ctx.save_for_backward(x0, stats, g32, b32, *([x1] if x1 is not None else []), *([ss] if ss is not None else []))
         return out
 
@@ -259,7 +301,10 @@ class _GroupNormFn(Function):
         ws = _ws(lib.fm_groupnorm_bwd_workspace_elems(b, h * w, c), x0.device)
         dx0 = ops.empty_nhwc(b, c0, h, w, x0.device)
         dx1 = ops.empty_nhwc(b, c1, h, w, x0.device) if has_x1 else None
-        dgb = torch.empty((2, c), dtype=torch.float32, device=x0.device)
+        gamma, beta = ctx.affine
+        tg, tb = _grad_target(gamma, (c,)), _grad_target(beta, (c,))
+        direct = tg is not None and tb is not None   # dgamma / dbeta land in the flat gradient, no AccumulateGrad
+        dgb = None if direct else torch.empty((2, c), dtype=torch.float32, device=x0.device)
         dss = torch.empty((b, 2 * c), dtype=torch.float32, device=x0.device) if has_ss else None
         # single source: also emit the column sums of dx (first stage); if x came straight out of a conv, that conv's
         # backward turns them into its bias / embedding-add gradients without another pass over dx
@@ -269,13 +314,18 @@ class _GroupNormFn(Function):
             lib.fm_groupnorm_bwd_bf16(x0.data_ptr(), c0, _ptr(x1), c1, dout.data_ptr(), stats.data_ptr(),
                                       g32.data_ptr(), b32.data_ptr(), _ptr(ss), 0 if ss is None else ss.stride(0),
                                       int(silu), b, h * w, groups, ws.data_ptr(), dx0.data_ptr(), _ptr(dx1),
-                                      dgb.data_ptr(), _ptr(dss), _ptr(colpart), _stream()),
+                                      tg.data_ptr() if direct else dgb.data_ptr(), _ptr(dss), _ptr(colpart),
+                                      tb.data_ptr() if direct else None, _stream()),
             "groupnorm_bwd",
         )
         if colpart is not None:
             # valid only for this exact tensor state: autograd may accumulate another branch's gradient into dx0 in
             # place, which bumps `_version` and invalidates the sums
             dx0._fm_colsum = (colpart, dx0._version)
+        if direct:
+            _grad_written(gamma)
+            _grad_written(beta)
+            return dx0, dx1, None, None, dss, None, None, None
         return dx0, dx1, dgb[0], dgb[1], dss, None, None, None
 
 
@@ -396,6 +446,7 @@ class _LinearFn(Function):
         y = ops.linear_f32(x32, w32, None if bias is None else bias.detach().float().contiguous(), silu_in=silu_in)
         ctx.silu_in = bool(silu_in)
         ctx.has_bias = bias is not None
+        ctx.wb = (weight, bias)
         ctx.save_for_backward(x32, w32)
         return y
 
@@ -412,12 +463,20 @@ class _LinearFn(Function):
             want_dx = ctx.needs_input_grad[0]
             ws = _ws(lib.fm_linear_bwd_workspace_elems(b, i, o), x.device) if want_dx else None
             dx = torch.empty_like(x) if want_dx else None
-            dw = torch.empty_like(w)
-            db = torch.empty((o,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            wp, bp = ctx.wb
+            tw = _grad_target(wp, w.shape)
+            tb = _grad_target(bp, (o,)) if ctx.has_bias else None
+            dw = tw if tw is not None else torch.empty_like(w)
+            db = tb if tb is not None else (torch.empty((o,), dtype=torch.float32, device=x.device)
+                                            if ctx.has_bias else None)
             _lib.check(lib.fm_linear_bwd_f32(x.data_ptr(), w.data_ptr(), dy.data_ptr(), _ptr(ws), _ptr(dx),
                                              dw.data_ptr(), _ptr(db), b, i, o, int(ctx.silu_in), _stream()),
                        "linear_bwd")
-            return dx, dw, db, None
+            if tw is not None:
+                _grad_written(wp)
+            if tb is not None:
+                _grad_written(bp)
+            return dx, None if tw is not None else dw, None if tb is not None else db, None
         dyt = dy.t().contiguous()                                              # [O][B]
         if ctx.needs_input_grad[0]:
             dx = ops.linear_f32(dy, w.t().contiguous())                        # [B][I] = dy W
@@ -477,6 +536,7 @@ class _StemFn(Function):
         out = ops.conv_stem(x0, x1, w32, None if bias is None else bias.detach().float().contiguous(),
                             in_scale=in_scale, in_shift=in_shift, want_stats=True)
         ctx.cfg = (float(in_scale), float(in_shift), x1 is not None, bias is not None, tuple(weight.shape))
+        ctx.wb = (weight, bias)
         ctx.save_for_backward(x0, *([x1] if x1 is not None else []))
         return out
 
@@ -491,11 +551,18 @@ class _StemFn(Function):
         c1 = x1.shape[1] if x1 is not None else 0
         cout = wshape[0]
         ws = _ws(lib.fm_conv_stem_wgrad_workspace_elems(c0 + c1, cout), dy.device)
-        dw = torch.empty(wshape, dtype=torch.float32, device=dy.device)
+        wp, bp = ctx.wb
+        tw = _grad_target(wp, wshape)
+        tb = _grad_target(bp, (cout,)) if has_bias else None
+        dw = tw if tw is not None else torch.empty(wshape, dtype=torch.float32, device=dy.device)
         _lib.check(lib.fm_conv_stem_wgrad_f32(x0.data_ptr(), c0, _ptr(x1), c1, in_scale, in_shift, dy.data_ptr(),
                                               ws.data_ptr(), dw.data_ptr(), b, h, w, cout, _stream()), "stem_wgrad")
-        db = colsum(dy, True)[1] if has_bias else None
-        return None, None, dw, db, None, None
+        db = colsum(dy, True, total=tb)[1] if has_bias else None
+        if tw is not None:
+            _grad_written(wp)
+        if tb is not None:
+            _grad_written(bp)
+        return None, None, None if tw is not None else dw, None if tb is not None else db, None, None
 
 
 def conv_stem(x0, x1, weight, bias, *, in_scale: float = 1.0, in_shift: float = 0.0) -> torch.Tensor:
@@ -519,6 +586,7 @@ class _HeadFn(Function):
         w32 = weight.detach().float().contiguous()
         out = ops.conv_head(a, w32, None if bias is None else bias.detach().float().contiguous())
         ctx.has_bias = bias is not None
+        ctx.wb = (weight, bias)
         ctx.save_for_backward(a, w32)
         return out
 
@@ -530,11 +598,15 @@ class _HeadFn(Function):
         b, cin, h, w = a.shape
         ws = _ws(lib.fm_conv_head_bwd_workspace_elems(cin), a.device)
         da = ops.empty_nhwc(b, cin, h, w, a.device) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w32)
+        wp, bp = ctx.wb
+        tw = _grad_target(wp, w32.shape)
+        dw = tw if tw is not None else torch.empty_like(w32)
         _lib.check(lib.fm_conv_head_bwd_f32(a.data_ptr(), dy.data_ptr(), w32.data_ptr(), ws.data_ptr(), _ptr(da),
                                             dw.data_ptr(), b, h, w, cin, _stream()), "head_bwd")
         db = sum_f32(dy) if ctx.has_bias else None
-        return da, dw, db
+        if tw is not None:
+            _grad_written(wp)
+        return da, None if tw is not None else dw, db
 
 
 def conv_head(a, weight, bias) -> torch.Tensor:

@@ -88,6 +88,23 @@ class FlowMatchingTrainer:
         return flow_matching_loss(self.model, clean, ldct, noise=noise, t=t,
                                   num_train_timesteps=self.num_train_timesteps)
 
+    def _direct_grads(self):
+        """Backward kernels write parameter gradients straight into the flat buffer (`functions.DIRECT_PARAM_GRADS`):
+        valid when the optimiser step follows ONE backward (no gradient accumulation across micro-batches)."""
+        trainer = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.saved = (F.DIRECT_PARAM_GRADS, F.GRAD_READY_HOOK)
+                F.DIRECT_PARAM_GRADS = trainer.grad_accum == 1
+                F.GRAD_READY_HOOK = trainer.reducer._on_grad if trainer.grad_accum == 1 else None
+
+            def __exit__(self, *exc):
+                F.DIRECT_PARAM_GRADS, F.GRAD_READY_HOOK = self.saved
+                return False
+
+        return _Ctx()
+
     def _eager_step(self, clean, ldct, noise, t) -> torch.Tensor:
         bs = clean.size(0)
         chunk = max(1, math.ceil(bs / self.grad_accum))
@@ -101,7 +118,8 @@ class FlowMatchingTrainer:
             if i == len(cc) - 1:
                 self.reducer.arm()
             loss = self._loss(c, l, n, tt)
-            (loss / self.grad_accum).backward()
+            with self._direct_grads():
+                (loss / self.grad_accum).backward()
             w = loss.detach() * (c.size(0) / bs)
             total = w if total is None else total + w
         self.reducer.finish()
@@ -116,7 +134,8 @@ class FlowMatchingTrainer:
         with torch.cuda.graph(graph):
             self.optimizer.zero_grad()
             loss = self._loss(sc, sl, None, None)
-            loss.backward()
+            with self._direct_grads():
+                loss.backward()
             self._static_loss = loss.detach()
         self._graph = graph
 

@@ -98,8 +98,8 @@ int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream);
 /* Rows of fused GroupNorm partial statistics PER IMAGE the conv described by `p` will write (pointers in `p` other
  * than the norm_a/norm_b markers are ignored): gn_stats must hold B * rows * (Cout/4) * 2 floats.  The count follows
  * the kernel the launcher picks for these shapes (one row per M tile and TMEM lane quadrant, or per strip and
- * quadrant for the rolling-row kernel).  Returns FM_ERR_UNSUPPORTED when an M tile would span several images (fewer
- * than 128 output pixels per image) or Cout % 4 != 0. */
+ * quadrant for the rolling-row kernel; images of <= 64 / <= 32 padded pixels share an M tile two / four at a time and
+ * get 2 / 1 rows).  Returns FM_ERR_UNSUPPORTED when an M tile would span more than four images or Cout % 4 != 0. */
 int fm_conv_stats_rows(const fm_conv_params* p, int32_t* rows_per_image);
 /* Which kernel the launcher picks for `p`: 0 persistent per-tile kernel, 1 rolling-row kernel, 2 rolling-row kernel with
  * the fused operand transform; negative = error.  (Diagnostics: bench.py tags its per-kernel timings with it.) */
@@ -128,6 +128,12 @@ int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t 
                           int32_t W, int32_t Cout, float* gn_stats, fm_stream_t stream);
 /* rows of statistics partials per image the stem kernel writes for this problem size (0 = unsupported) */
 int fm_conv_stem_stats_rows(int32_t B, int32_t H, int32_t W, int32_t Cout);
+/* Stem on the tensor cores, step 1 (large inputs): the 3x3 neighbourhoods of the fp32 NCHW inputs (same x0 / x1 /
+ * in_scale / in_shift meaning as fm_conv_stem_f32_bf16) as a bf16 NHWC tensor out[B][H][W][Kp], column ci*9 + kh*3 + kw
+ * (zero beyond 9*Cin; Kp a multiple of 8, <= 72).  Step 2 is fm_conv2d_igemm_bf16 as a 1x1 conv over it with the
+ * weight matrix w.reshape(Cout, 9*Cin) zero-padded to Kp columns: conv_in runs at store bandwidth. */
+int fm_stem_im2col_bf16(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale, float in_shift,
+                        void* out, int32_t B, int32_t H, int32_t W, int32_t Kp, fm_stream_t stream);
 
 /* Head conv (tiny Cout): bf16 NHWC -> fp32 NCHW (unet_diffusers_nd.py:190, unet.py:288-292). 3x3 s1 p1.
  * norm_ab != NULL ([B][2][Cin], fm_groupnorm_affine_f32): the input is read as SiLU(a*x+b) (norm_act=1) or a*x+b,
@@ -302,7 +308,10 @@ int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C);
 int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout, const float* stats,
                           const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
                           int32_t silu, int32_t B, int64_t HW, int32_t groups, float* workspace, void* dx0, void* dx1,
-                          float* dgamma_dbeta, float* dscale_shift, float* dx_colsum_partials, fm_stream_t stream);
+                          float* dgamma_dbeta, float* dscale_shift, float* dx_colsum_partials, float* dbeta,
+                          fm_stream_t stream);
+/* dbeta (or NULL): when given, dgamma_dbeta receives only the [C] dgamma row and dbeta the [C] dbeta row (two separate
+ * destinations, e.g. the parameters' slices of a flat gradient buffer) */
 /* dx_colsum_partials (or NULL): fp32 [B][fm_groupnorm_bwd_blocks(B, HW)][C] per-block column sums of dx, i.e. the
  * first stage of the bias / time-embedding-add gradient of the conv that produced x; fold with fm_colsum_finish_f32 */
 int32_t fm_groupnorm_bwd_blocks(int32_t B, int64_t HW);

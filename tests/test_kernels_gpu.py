@@ -234,7 +234,10 @@ def test_conv_fused_groupnorm_statistics():
     """GroupNorm fed by the conv epilogue's channel-quad partial sums == GroupNorm with its own statistics pass."""
     g = torch.Generator().manual_seed(11)
     for (B, H, W, cin, cout, stride) in [(2, 32, 32, 64, 128, 1), (3, 28, 28, 64, 64, 1), (2, 32, 32, 128, 256, 2),
-                                         (1, 16, 48, 64, 512, 1)]:
+                                         (1, 16, 48, 64, 512, 1),
+                                         # tiny images: two / four whole images per 128-row M tile (ragged last tile)
+                                         (5, 7, 7, 128, 128, 1), (3, 8, 8, 64, 256, 1), (7, 4, 8, 64, 64, 1),
+                                         (6, 14, 14, 128, 128, 2)]:
         x = _bf16r(torch.randn(B, cin, H, W, generator=g)).to(DEV)
         w = _bf16r(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(DEV)
         bias = torch.randn(cout, generator=g).to(DEV)
@@ -407,6 +410,40 @@ def test_stem_fused_groupnorm_statistics():
         t_fused = ops.group_norm_table([y], 32, 1e-5, gamma, beta, silu=True)
         t_plain = ops.group_norm_table([y.clone(memory_format=torch.preserve_format)], 32, 1e-5, gamma, beta, silu=True)
         # the fused statistics see the fp32 accumulators, the plain pass their bf16 rounding
+        assert float((t_fused.ab - t_plain.ab).abs().max()) < 5e-3 * float(t_plain.ab.abs().max())
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 512, 512, 2, 128), (6, 256, 200, 1, 128), (2, 300, 444, 4, 64),
+                                             (1, 512, 520, 8, 256)])
+def test_stem_tensor_core_path(B, H, W, cin, cout):
+    """conv_in on large inputs = `fm_stem_im2col_bf16` + the 1x1 implicit GEMM: against F.conv2d on the bf16-rounded
+    operands (tight) and on the fp32 operands (bf16 rounding of inputs and weights only), with the 2x-1 centering, the
+    fused conditioning concat and the GroupNorm partial statistics of the output."""
+    g = torch.Generator().manual_seed(17)
+    c0 = max(1, cin // 2)
+    x0 = torch.randn(B, c0, H, W, generator=g).to(DEV)
+    x1 = torch.rand(B, cin - c0, H, W, generator=g).to(DEV) if cin > c0 else None
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / 4).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    assert B * H * W >= ops.STEM_TENSOR_MIN_PIXELS
+    packed = ops.stem_pack(w)
+    full = x0 if x1 is None else torch.cat([x0, x1], 1)
+    for scale, shift in ((1.0, 0.0), (2.0, -1.0)):
+        n0 = ops.launch_count()
+        y = ops.conv_stem(x0, x1, w, b, in_scale=scale, in_shift=shift, packed=packed)
+        assert ops.launch_count() - n0 == 2                      # im2col + one GEMM launch
+        ref32 = F.conv2d(full * scale + shift, w, b, padding=1)
+        ref16 = F.conv2d(_bf16r(full * scale + shift), _bf16r(w), b, padding=1)
+        assert y.shape == ref32.shape and y.dtype == torch.bfloat16
+        assert _rel_l2(y.float(), ref16) < 3e-3                  # bf16 output rounding
+        assert _rel_l2(y.float(), ref32) < 6e-3
+        old = ops.conv_stem(x0, x1, w, b, in_scale=scale, in_shift=shift)   # fp32 CUDA-core kernel
+        assert _rel_l2(y.float(), old.float()) < 6e-3
+    if cout % 32 == 0:
+        assert hasattr(y, "_fm_stats")
+        gamma, beta = torch.randn(cout, generator=g).to(DEV), torch.randn(cout, generator=g).to(DEV)
+        t_fused = ops.group_norm_table([y], 32, 1e-5, gamma, beta, silu=True)
+        t_plain = ops.group_norm_table([y.clone(memory_format=torch.preserve_format)], 32, 1e-5, gamma, beta, silu=True)
         assert float((t_fused.ab - t_plain.ab).abs().max()) < 5e-3 * float(t_plain.ab.abs().max())
 
 

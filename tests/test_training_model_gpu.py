@@ -264,7 +264,7 @@ def test_graph_sampler_recaptures_after_weight_updates():
 
     a0 = sample(True)
     assert torch.equal(a0, sample(False))
-    gs = next(iter(PU._GRAPH_CACHE.values()))
+    gs = next(g for g in PU._GRAPH_CACHE.values() if g.model is model)
     caps = gs.captures
     assert torch.equal(sample(True), a0) and gs.captures == caps          # unchanged weights: no re-capture
     tr = FlowMatchingTrainer(model, lr=1e-3, cuda_graph=False)            # re-seats every parameter (new addresses)

@@ -309,9 +309,52 @@ def exp_grad_worst():
             print("    worst |dg|/|g_total| = %.3e (%s)" % worst_scaled, flush=True)
 
 
+def exp_attention_micro():
+    from fmdm_b200 import ops
+
+    b, heads, t, hd = 16, 64, 1024, 8
+    c = heads * hd
+    g = torch.Generator().manual_seed(0)
+    qkv = torch.randn(b, t, 3 * c, generator=g).to(DEV).to(torch.bfloat16)
+    out = torch.empty(b, t, c, device=DEV, dtype=torch.bfloat16)
+    flat = qkv.view(-1)
+    def run():
+        ops.attention(flat, flat[c:], flat[2 * c:], out.view(-1), batch=b, heads=heads, tq=t, tk=t, head_dim=hd,
+                      q_strides=(t * 3 * c, hd, 3 * c), kv_strides=(t * 3 * c, hd, 3 * c), o_strides=(t * c, hd, c))
+    for _ in range(5):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    q, k, v = [x.reshape(b, t, heads, hd).transpose(1, 2).float() for x in qkv.split(c, dim=-1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, t, c)
+    print("attention hd8 T=1024 B=16 heads=64: %.4f ms/launch, poly_exp=%s, rel_l2 vs fp32 SDPA %.3e" % (
+        e0.elapsed_time(e1) / 200, os.environ.get("FMDM_ATTENTION_NO_POLY_EXP") is None, rel_l2(out, ref)), flush=True)
+
+
+def exp_mnist_steps():
+    """Two eager sampling steps of the MNIST config (for an ncu launch list) and the graph-replayed run time."""
+    from fmdm_b200.pipelines.utils import build_scheduler, sample_with_scheduler
+
+    model, _ = build(MNIST_UNET, None)
+    sched, _ = build_scheduler({"name": "flow_match_euler", "params": {}}, {})
+    x = torch.randn(64, 1, 28, 28, device=DEV)
+    with torch.no_grad():
+        for graph in (False, True, True):
+            torch.cuda.synchronize(); t0 = time.time()
+            sample_with_scheduler(model, sched, 50, tuple(x.shape), torch.device(DEV), init_sample=x, last_n_steps=2 if not graph else None,
+                                  use_cuda_graph=graph)
+            torch.cuda.synchronize()
+            print("mnist", "graph 50 steps" if graph else "eager 2 steps", "%.2f ms" % ((time.time() - t0) * 1e3), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["split", "compvis", "grad", "eps", "b16"]
     table = {"split": exp_split_weights, "compvis": exp_compvis_large, "grad": exp_grad_worst, "eps": exp_eps_fixture,
-             "b16": exp_b16_512}
+             "b16": exp_b16_512, "att": exp_attention_micro, "mnist": exp_mnist_steps}
     for w in which:
         section(table[w])
