@@ -90,72 +90,176 @@ def test_run_model_config_helpers(tmp_path):
     with pytest.raises(FileNotFoundError):
         RM.load_run_config(tmp_path)
     (tmp_path / "train_config.json").write_text(json.dumps(CFG))
-    assert RM.load_run_config(tmp_path)["model"]["model_type"] == "flow_matching"
-    assert RM.resolve_checkpoint(tmp_path, "flow_matching") is None
+    cfg = RM.load_run_config(tmp_path)
+    assert cfg["model"]["model_type"] == "flow_matching" and cfg["__config_path__"].endswith("train_config.json")
+    with pytest.raises(FileNotFoundError):
+        RM.resolve_checkpoint(tmp_path, "flow_matching")
     (tmp_path / "flow_last.pt").write_bytes(b"x")
     assert RM.resolve_checkpoint(tmp_path, "flow_matching").name == "flow_last.pt"
     (tmp_path / "flow_best.pt").write_bytes(b"x")
     assert RM.resolve_checkpoint(tmp_path, "flow_matching").name == "flow_best.pt"
-    assert RM.resolve_checkpoint(tmp_path, "diffusion") is None
+    with pytest.raises(FileNotFoundError):
+        RM.resolve_checkpoint(tmp_path, "diffusion")
+    assert RM.resolve_checkpoint(tmp_path, "something_else").name == "flow_last.pt"   # last *.pt of the directory
+    (tmp_path / "unet").mkdir()
+    (tmp_path / "unet" / "diffusion_pytorch_model.safetensors").write_bytes(b"x")
+    assert RM.resolve_checkpoint(tmp_path, "diffusion").name == "diffusion_pytorch_model.safetensors"
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("sched,kw", [(None, {}), ("ddim", {"start_step": 500}), ("dpmsolver++", {"last_n_steps": 4}),
-                                      ("flowmatch", {"num_inference_steps": 12})])
-def test_decode_diffusion_batch_matches_oracle_loop(sched, kw):
-    """decode_diffusion_batch == the oracle's restatement of the same call (scheduler override, subset, steps)."""
-    from oracle import denoiser as OD
-    from oracle.sampling import make_scheduler, sample_loop
+def test_legacy_diffusers_run_config(tmp_path):
+    """A diffusers pipeline folder without train_config.json (`sampling_utils.py:17-103`): the run config is rebuilt
+    from model_index / scheduler_config / unet config, builds the same module tree, and the safetensors checkpoint in
+    diffusers' own key names loads through the legacy remap."""
+    from safetensors.torch import save_file
 
-    dev = torch.device("cuda")
-    cfg = json.loads(json.dumps(CFG))
-    cfg["model"]["unet"] = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layers_per_block": 1,
-                            "block_out_channels": [64, 128], "down_block_types": ["DownBlock2D", "AttnDownBlock2D"],
-                            "up_block_types": ["AttnUpBlock2D", "UpBlock2D"]}
-    torch.manual_seed(5)
-    model = DU.build_diffusion_model(cfg, dev)
-    B, hw = 2, 32
-    name = sched or "flowmatch"
-    if name != "flowmatch":
-        # epsilon samplers need a conditioned (trained) denoiser for a final-sample comparison: tests/_fixtures.py
-        from _fixtures import train_epsilon_denoiser
+    from fmdm_b200 import run_model as RM
 
-        loss = train_epsilon_denoiser(model, hw=hw, batch=32, steps=300, lr=3e-4, warmup=50)
-        assert loss < 0.1, f"the epsilon fixture did not train (loss {loss})"
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    g = torch.Generator().manual_seed(11)
-    noise = torch.randn(B, 1, hw, hw, generator=g).to(dev)
-    cond = torch.rand(B, 1, hw, hw, generator=g).to(dev)
-    steps = kw.get("num_inference_steps", 20)
-    with torch.no_grad():
-        out = DU.decode_diffusion_batch(model, cfg["training"], cfg["model"], dev, tuple(noise.shape),
-                                        conditioning_batch=cond, scheduler_override=sched,
-                                        num_inference_steps=steps, start_step=kw.get("start_step"),
-                                        last_n_steps=kw.get("last_n_steps"), init_sample=noise)
+    (tmp_path / "scheduler").mkdir()
+    (tmp_path / "unet").mkdir()
+    (tmp_path / "model_index.json").write_text(json.dumps({"_class_name": "DDPMPipeline"}))
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(
+        {"_class_name": "DDPMScheduler", "_diffusers_version": "0.14.0", "num_train_timesteps": 1000,
+         "beta_start": 1e-4, "beta_end": 0.02, "beta_schedule": "linear", "trained_betas": None}))
+    unet = {"sample_size": 32, "in_channels": 2, "out_channels": 1, "layers_per_block": 1, "block_out_channels": [32, 64],
+            "down_block_types": ["DownBlock2D", "AttnDownBlock2D"], "up_block_types": ["AttnUpBlock2D", "UpBlock2D"]}
+    (tmp_path / "unet" / "config.txt").write_text(json.dumps(unet))   # the .txt spelling is accepted too
+    cfg = RM.load_run_config(tmp_path)
+    assert cfg["model"]["model_type"] == "diffusion" and cfg["model"]["conditioning"] == "concatenate"
+    assert cfg["training"]["load_ldct"] is True and cfg["training"]["channels"] == 1 and cfg["training"]["img_size"] == 32
+    sched = cfg["model"]["scheduler"]
+    assert sched["name"] == "ddpm" and sched["params"] == {"beta_start": 1e-4, "beta_end": 0.02, "beta_schedule": "linear"}
+    u = cfg["model"]["unet"]
+    assert u["in_channels_already_conditioned"] is True and u["in_channels"] == 2 and u["attention_head_dim"] == 8
+    assert u["flip_sin_to_cos"] is True and u["block_out_channels"] == (32, 64)
+    # same module tree as the native config with in_channels 1 + concatenated conditioning
+    torch.manual_seed(4)
+    native = DiffusionUNetFactory().build(SMALL, "concatenate", 1)
+    save_file(_legacy_names({k: v.contiguous() for k, v in native.state_dict().items()}),
+              str(tmp_path / "unet" / "diffusion_pytorch_model.safetensors"))
+    ckpt = RM.resolve_checkpoint(tmp_path, cfg["model"]["model_type"])
+    model = DU.build_diffusion_model(cfg, torch.device("cpu"), ckpt_path=ckpt)
+    got = model.state_dict()
+    assert set(got) == set(native.state_dict())
+    assert all(torch.equal(got[k], v) for k, v in native.state_dict().items())
+    with pytest.raises(FileNotFoundError):
+        RM.load_run_config(tmp_path / "scheduler")
 
-    def oracle_model(inp, t):
-        return OD.unet_diffusers_nd_forward(sd, cfg["model"]["unet"], inp[:, :1], t, conditioning="concatenate",
-                                            channels=1, context=inp[:, 1:])
 
-    class _DevSched:  # oracle scheduler tables live on the CPU
-        def __init__(self, s):
-            self.s, self.set_timesteps = s, s.set_timesteps
+class _DummyHandler:
+    init_kwargs = None
+    called = None
 
-        @property
-        def timesteps(self):
-            return self.s.timesteps
+    def __init__(self, **kwargs):
+        type(self).init_kwargs = kwargs
 
-        def step(self, pred, t, x):
-            r = self.s.step(pred.cpu(), t, x.cpu())
-            r.prev_sample = r.prev_sample.to(dev)
-            return r
+    def encode(self):
+        type(self).called = "encode"
 
-    with torch.no_grad():
-        ref = sample_loop(oracle_model, _DevSched(make_scheduler(name, 1000, {"beta_start": 1e-4, "beta_end": 0.02})),
-                          steps, noise, cond, start_step=kw.get("start_step"), last_n_steps=kw.get("last_n_steps"))
-    assert out.shape == ref.shape and torch.isfinite(out).all()
-    mse = float(((out.clamp(0, 1) - ref.clamp(0, 1)) ** 2).mean())
-    assert mse < 1e-4, (name, mse)  # north star: final samples >= 40 dB PSNR (peak 1.0 after clamp(0, 1))
+    def decode(self):
+        type(self).called = "decode"
+
+    def evaluate(self):
+        type(self).called = "evaluate"
+
+    def sample(self):
+        type(self).called = "sample"
+
+
+def test_run_model_dispatch(monkeypatch, tmp_path):
+    """The reference's `tests/test_run_model_dispatch.py:28-66` against the mirror: flags are forwarded to the handler
+    the registry names for `model.model_type`, under the reference's keyword names."""
+    from fmdm_b200 import run_model as RM
+
+    ckpt_dir = tmp_path / "run"
+    ckpt_dir.mkdir()
+
+    def fake_load(path):
+        assert path == ckpt_dir
+        return {"model": {"model_type": "diffusion"}, "training": {}}
+
+    monkeypatch.setattr(RM, "load_run_config", fake_load)
+    monkeypatch.setattr(RM, "HANDLER_REGISTRY", {"diffusion": _DummyHandler})
+    monkeypatch.setattr("sys.argv", ["run_model.py", "--ckpt_dir", str(ckpt_dir), "--mode", "evaluate", "--batch_size",
+                                     "64", "--num_samples", "128", "--save", "--save_input", "--save_conditioning"])
+    RM.main()
+    kw = _DummyHandler.init_kwargs
+    assert _DummyHandler.called == "evaluate"
+    assert kw["batch_size"] == 64 and kw["num_samples"] == 128
+    assert kw["save"] is True and kw["save_input"] is True and kw["save_conditioning"] is True
+    # exactly the reference's sixteen keyword arguments (`src/run_model.py:75-92`) when no tensor-file flag is given
+    assert set(kw) == {"ckpt_dir", "data_txt", "save", "output_dir", "batch_size", "device", "seed", "timestep",
+                       "num_samples", "save_input", "save_conditioning", "num_inference_steps", "start_step",
+                       "last_n_steps", "scheduler", "save_tensor_cache"}
+    RM.main(["--ckpt_dir", str(ckpt_dir), "--mode", "encode", "--timestep", "250", "--scheduler", "unipc",
+             "--data_txt", "split.txt", "--save_tensor_cache"])
+    kw = _DummyHandler.init_kwargs
+    assert _DummyHandler.called == "encode" and kw["timestep"] == 250 and kw["scheduler"] == "unipc"
+    assert kw["data_txt"] == "split.txt" and kw["save_tensor_cache"] is True
+    monkeypatch.setattr(RM, "load_run_config", lambda p: {"model": {"model_type": "gan"}})
+    with pytest.raises(ValueError, match="Unsupported model_type"):
+        RM.main(["--ckpt_dir", str(ckpt_dir)])
+    assert set(RM.HANDLER_REGISTRY) == {"diffusion"}      # monkeypatched view
+    monkeypatch.undo()
+    assert set(RM.HANDLER_REGISTRY) == {"vae", "diffusion", "flow_matching"}
+
+
+def test_handlers_refuse_what_is_out_of_scope(tmp_path):
+    from fmdm_b200 import run_model as RM
+    from fmdm_b200._runtime import OutOfScopeError
+
+    h = RM.FlowMatchingHandler(ckpt_dir=tmp_path)
+    for mode in ("build_tensor_cache", "debug_compare"):
+        with pytest.raises(OutOfScopeError):
+            getattr(h, mode)()
+    with pytest.raises(OutOfScopeError):
+        RM.VAEHandler(ckpt_dir=tmp_path).sample()
+    with pytest.raises(OutOfScopeError):      # a dataset split file: the readers are not part of the path
+        RM.TensorSource.resolve("train_split.txt", None, None, None, 42)
+    g = torch.Generator().manual_seed(0)
+    torch.save({"image": torch.rand(3, 1, 8, 8, generator=g), "target": torch.rand(3, 1, 8, 8, generator=g)},
+               tmp_path / "bundle.pt")
+    src = RM.TensorSource.resolve(str(tmp_path / "bundle.pt"), None, None, None, 42)
+    assert len(src) == 3 and len(src.take(2)) == 2 and src.take(None) is src
+
+
+def _ssim_by_windows(x, y, win=7, k1=0.01, k2=0.03, r=1.0):
+    """Brute force over every fully inside window: means, unbiased variances and covariance from numpy."""
+    import numpy as np
+
+    vals = []
+    for i in range(x.shape[0] - win + 1):
+        for j in range(x.shape[1] - win + 1):
+            a, b = x[i:i + win, j:j + win].ravel(), y[i:i + win, j:j + win].ravel()
+            c = np.cov(a, b, ddof=1)
+            c1, c2 = (k1 * r) ** 2, (k2 * r) ** 2
+            vals.append((2 * a.mean() * b.mean() + c1) * (2 * c[0, 1] + c2)
+                        / ((a.mean() ** 2 + b.mean() ** 2 + c1) * (c[0, 0] + c[1, 1] + c2)))
+    return float(np.mean(vals))
+
+
+def test_ssim_restatement():
+    """SSIM (`evaluation_utils.py:64-91` calls skimage's `structural_similarity(p, t, channel_axis=None,
+    data_range=1.0)`; scikit-image is not installed here): the restatement against a brute-force window loop and the
+    closed forms for identical and constant images."""
+    import numpy as np
+
+    from fmdm_b200 import run_model as RM
+
+    rng = np.random.default_rng(0)
+    x = rng.random((19, 23))
+    y = np.clip(x + 0.1 * rng.standard_normal(x.shape), 0, 1)
+    assert abs(RM.structural_similarity(x, x) - 1.0) < 1e-12
+    assert abs(RM.structural_similarity(x, y) - _ssim_by_windows(x, y)) < 1e-10
+    a, b = np.full((9, 9), 0.25), np.full((9, 9), 0.75)
+    assert abs(RM.structural_similarity(a, b) - (2 * 0.25 * 0.75 + 1e-4) / (0.25 ** 2 + 0.75 ** 2 + 1e-4)) < 1e-12
+    with pytest.raises(ValueError):
+        RM.structural_similarity(x[:5], y[:5])
+    # channel-first samples: mean over channels; mismatched shapes -> None (`evaluation_utils.py:69-70`)
+    p = torch.tensor(np.stack([x, y]), dtype=torch.float32)
+    t = torch.tensor(np.stack([y, y]), dtype=torch.float32)
+    want = 0.5 * (RM.structural_similarity(p[0].numpy(), t[0].numpy()) + 1.0)
+    assert abs(RM.compute_ssim_sample(p, t, RM.structural_similarity) - want) < 1e-6
+    assert RM.compute_ssim_sample(p, t[:1], RM.structural_similarity) is None
 
 
 @pytest.mark.gpu
@@ -225,3 +329,21 @@ def test_run_model_evaluate_cli(tmp_path):
     vals = dict(zip(rows[0].split(","), rows[1].split(",")))
     assert vals["samples"] == "4" and float(vals["psnr"]) > 0 and float(vals["model_samples_per_second"]) > 0
     assert int(vals["model_calls"]) == 4  # ddim, 10 steps, leading spacing: timesteps <= 300 are 300, 200, 100, 0
+    assert vals["ssim_enabled"] == "True" and -1.0 <= float(vals["ssim"]) <= 1.0
+    per_image = (tmp_path / "outputs" / "evaluate" / "eval_metrics_per_image.csv").read_text().splitlines()
+    assert len(per_image) == 5 and all(row.split(",")[3] != "" for row in per_image[1:])
+    assert json.loads((tmp_path / "outputs" / "evaluate" / "run_config.json").read_text())["start_step"] == 300
+    # the reference's flag names: a tensor bundle through --data_txt, inputs / conditioning saved next to the samples
+    torch.save({"image": cond, "target": tgt}, tmp_path / "bundle.pt")
+    rc = RM.main(["--ckpt_dir", str(tmp_path), "--mode", "decode", "--data_txt", str(tmp_path / "bundle.pt"),
+                  "--batch_size", "2", "--num_inference_steps", "5", "--num_samples", "3", "--save", "--save_input",
+                  "--save_conditioning", "--scheduler", "dpmsolver2", "--output_dir", str(tmp_path / "dec")])
+    assert rc == 0
+    dec = tmp_path / "dec" / "decode"
+    assert torch.load(dec / "samples.pt", weights_only=True).shape == (3, 1, 32, 32)
+    assert torch.equal(torch.load(dec / "input.pt", weights_only=True), tgt[:3])
+    assert torch.equal(torch.load(dec / "conditioning.pt", weights_only=True), cond[:3])
+    rc = RM.main(["--ckpt_dir", str(tmp_path), "--mode", "encode", "--targets_pt", str(tmp_path / "tgt.pt"),
+                  "--timestep", "0", "--save", "--output_dir", str(tmp_path / "enc")])
+    enc = torch.load(tmp_path / "enc" / "encode" / "encoded.pt", weights_only=True)
+    assert rc == 0 and enc.shape == tgt.shape and float((enc - tgt).abs().max()) < 0.1   # abar_0 ~ 0.9999
