@@ -127,15 +127,16 @@ SIGNATURES = {
     "fm_conv_wgrad_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "fm_conv_wgrad_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_colsum_workspace_elems": (C.c_int64, [_i32, _i64, _i32]),
-    "fm_colsum_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),
+    "fm_colsum_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "fm_ticket_ints": (C.c_int32, []),
     "fm_zero_insert2x_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "fm_sumpool2x2_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "fm_groupnorm_bwd_workspace_elems": (C.c_int64, [_i32, _i64, _i32]),
     "fm_groupnorm_bwd_bf16": (
         C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
-                  _vp, _vp, _vp]),
+                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fm_groupnorm_bwd_blocks": (C.c_int32, [_i32, _i64]),
-    "fm_colsum_finish_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "fm_colsum_finish_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fm_attention_bwd_bf16": (
         C.c_int, [_vp] * 8 + [_i32, _i32, _i32, _i32] + [_i64] * 6 + [_f32, _vp]),
     "fm_linear_bwd_workspace_elems": (C.c_int64, [_i32, _i32, _i32]),

@@ -145,6 +145,26 @@ __device__ __forceinline__ void mma_m16n8k8_bf16(float (&d)[4], uint32_t a0, uin
       : "r"(a0), "r"(a1), "r"(b0));
 }
 
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// a pair of probabilities as packed halves: 2^x on the special-function unit in fp32 (`ex2.approx.f16x2` is issued as
+// two MUFU.EX2.F16 plus byte permutes on sm_100a - measured in SASS - so the packed form saves nothing), one pack
+__device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
+  uint32_t y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(ex2_approx(hi)), "f"(ex2_approx(lo)));
+  return y;
+}
+
+// F16P = true: probabilities as packed halves (11 significant bits instead of bf16's 8).  Per 16 keys and thread: no
+// row-sum adds (the row sums come from one extra MMA against a ones matrix, which also folds the four lanes of a
+// row) and P V as ONE m16n8k16 (V staged as fp16).  The loop is issue-bound, so the instruction count is what matters.
+template <bool F16P>
 __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     __nv_bfloat16* __restrict__ out, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
@@ -179,8 +199,14 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
       }
       *reinterpret_cast<uint4*>(sK + j * 8) = kk;
       const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+      if constexpr (F16P) {
+        __half* sVh = reinterpret_cast<__half*>(sVt);
 #pragma unroll
-      for (int d = 0; d < 8; ++d) sVt[d * kAtt8VtStride + j] = ve[d];
+        for (int d = 0; d < 8; ++d) sVh[d * kAtt8VtStride + j] = __float2half_rn(__bfloat162float(ve[d]));
+      } else {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) sVt[d * kAtt8VtStride + j] = ve[d];
+      }
     }
     __syncthreads();
 
@@ -215,6 +241,26 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
       m0 = mn0; m1 = mn1;
       l0 *= corr0; l1 *= corr1;
       o[0] *= corr0; o[1] *= corr0; o[2] *= corr1; o[3] *= corr1;
+      if constexpr (F16P) {
+        float ls[4] = {l0, 0.f, l1, 0.f};   // row sums ride in an accumulator fragment: c0 = row g, c2 = row g + 8
+        const float2 sc = make_float2(scale_log2e, scale_log2e), n0 = make_float2(-mn0, -mn0), n1 = make_float2(-mn1, -mn1);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float2 e0 = ffma2(make_float2(s[j][0], s[j][1]), sc, n0);
+          const float2 e1 = ffma2(make_float2(s[j][2], s[j][3]), sc, n1);
+          const float2 e2 = ffma2(make_float2(s[j + 1][0], s[j + 1][1]), sc, n0);
+          const float2 e3 = ffma2(make_float2(s[j + 1][2], s[j + 1][3]), sc, n1);
+          // A fragment of m16n8k16: (row g, keys 2t..), (row g+8, keys 2t..), (row g, keys 8+2t..), (row g+8, keys 8+2t..)
+          const uint32_t pa0 = ex2_f16x2(e0.x, e0.y), pa1 = ex2_f16x2(e1.x, e1.y);
+          const uint32_t pa2 = ex2_f16x2(e2.x, e2.y), pa3 = ex2_f16x2(e3.x, e3.y);
+          const __half* vt = reinterpret_cast<const __half*>(sVt) + g * kAtt8VtStride + kb0 + j * 8 + 2 * t;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vt), b1 = *reinterpret_cast<const uint32_t*>(vt + 8);
+          mma_m16n8k16_f16(o, pa0, pa1, pa2, pa3, b0, b1);
+          mma_m16n8k16_f16(ls, pa0, pa1, pa2, pa3, 0x3C003C00u, 0x3C003C00u);   // times ones: the row sums
+        }
+        l0 = ls[0], l1 = ls[2];
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 e01 = ffma2(make_float2(s[j][0], s[j][1]), make_float2(scale_log2e, scale_log2e),
@@ -233,10 +279,12 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
       }
     }
   }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  if constexpr (!F16P) {   // (the ones-matrix MMA already summed over the four lanes of a row)
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  }
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
   __nv_bfloat16* ob = out + b * o_sb + h * o_sh;
   if (q0 + g < Tq)
@@ -667,7 +715,10 @@ extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, vo
   switch (head_dim) {
     case 8: {
       dim3 grid((Tq + kAtt8Warps * 16 - 1) / (kAtt8Warps * 16), heads, B);
-      attention_hd8_mma_kernel<<<grid, kAtt8Threads, 0, st>>>(
+      // FMDM_ATTENTION_BF16P=1: the first-generation inner loop (scalar fp32 exponentials, bf16 probabilities), A/B only
+      static const bool bf16p = getenv("FMDM_ATTENTION_BF16P") != nullptr;
+      auto kern = bf16p ? attention_hd8_mma_kernel<false> : attention_hd8_mma_kernel<true>;
+      kern<<<grid, kAtt8Threads, 0, st>>>(
           reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
           reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Tq, Tk, q_sb, q_sh, q_st,
           kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale * 1.4426950408889634f);

@@ -16,31 +16,48 @@
 
 namespace fm {
 
+// self-resetting tickets for "the last CTA finishes the job" (caller-owned int32 buffer of FM_TICKET_INTS, zero on entry
+// and on exit): [0, kTicketGlobal) per-sample counters, one global counter, then per-column-block counters (colsum)
+constexpr int kTicketGlobal = 2048;
+constexpr int kTicketCols = 2049;
+constexpr int kTicketInts = 4096;
+
 // =============================================================================================================
 // generic fixed-order reduction of partials: out[o][i] = sum_p in[o][p][i]
 // =============================================================================================================
 // out2 (optional): results with index >= split go to out2[idx - split] (two destinations for one reduction, e.g. the
 // dgamma / dbeta rows written straight into two parameter-gradient slices)
+// grid (ceil(inner/32), outer), block (32 columns, 8 lanes): lane y folds parts y, y+8, ... in order, then the eight
+// lane sums are folded in order (a thread-per-output loop over hundreds of partial rows is a chain of dependent L2
+// round trips: 230 us for the stem's 592 partial rows)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                               int parts, int64_t inner, int64_t total,
-                                                               float* __restrict__ out2, int64_t split) {
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = idx / inner, i = idx - o * inner;
+                                                               int parts, int64_t inner, float* __restrict__ out2,
+                                                               int64_t split) {
+  __shared__ float sh[8][33];
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  const int64_t o = blockIdx.y;
+  float acc = 0.f;
+  if (i < inner) {
     const float* src = in + (o * parts) * inner + i;
-    float acc = 0.f;
-    for (int p = 0; p < parts; ++p) acc += src[(int64_t)p * inner];
-    if (out2 != nullptr && idx >= split) out2[idx - split] = acc;
-    else out[idx] = acc;
+#pragma unroll 4
+    for (int p = threadIdx.y; p < parts; p += 8) acc += src[(int64_t)p * inner];
+  }
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < inner) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
+    const int64_t idx = o * inner + i;
+    if (out2 != nullptr && idx >= split) out2[idx - split] = t;
+    else out[idx] = t;
   }
 }
 
 static int launch_reduce(const float* in, float* out, int64_t outer, int parts, int64_t inner, cudaStream_t st,
                          float* out2 = nullptr, int64_t split = 0) {
-  const int64_t total = outer * inner;
-  if (total == 0) return 0;
-  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  reduce_partials_kernel<<<blocks, 256, 0, st>>>(in, out, parts, inner, total, out2, split);
+  if (outer * inner == 0) return 0;
+  reduce_partials_kernel<<<dim3((unsigned)((inner + 31) / 32), (unsigned)outer), dim3(32, 8), 0, st>>>(
+      in, out, parts, inner, out2, split);
   FM_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
 }
@@ -224,20 +241,34 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_mma_kernel(const WgradParam
 }
 
 // dw[co][c_begin + ci][tap] = sum_split part[split][tap][co][ci]
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
+// One block = one output channel x 64 input channels: the partials are read tap row by tap row (64 consecutive floats
+// each), transposed through shared memory, and written as ONE contiguous run of 64*taps floats (the OIHW slice) -
+// a thread-per-element version wrote with a stride of `taps` floats and ran at ~1 TB/s.
+constexpr int kWrCi = 64;
+__global__ void __launch_bounds__(192) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
                                                             int splits, int taps, int Cout, int Cin, int cin_total,
                                                             int c_begin) {
+  __shared__ float tile[kWrCi * 9];
+  const int co = blockIdx.y, ci0 = blockIdx.x * kWrCi;
+  const int nci = Cin - ci0 < kWrCi ? Cin - ci0 : kWrCi;
   const int64_t per = (int64_t)taps * Cout * Cin;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int ci = (int)(idx % Cin);
-    const int64_t r = idx / Cin;
-    const int co = (int)(r % Cout);
-    const int tap = (int)(r / Cout);
+  for (int item = threadIdx.x; item < taps * kWrCi; item += blockDim.x) {
+    const int tap = item / kWrCi, i = item - tap * kWrCi;
+    if (i >= nci) continue;
+    const float* src = part + ((int64_t)tap * Cout + co) * Cin + ci0 + i;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += part[(int64_t)s * per + idx];
-    dw[((int64_t)co * cin_total + c_begin + ci) * taps + tap] = acc;
+    for (int sp = 0; sp < splits; ++sp) acc += src[(int64_t)sp * per];
+    tile[i * taps + tap] = acc;
   }
+  __syncthreads();
+  float* dst = dw + ((int64_t)co * cin_total + c_begin + ci0) * taps;
+  for (int j = threadIdx.x; j < nci * taps; j += blockDim.x) dst[j] = tile[j];
+}
+
+static void launch_wgrad_reduce(const float* part, float* dw, int splits, int taps, int Cout, int Cin, int cin_total,
+                                int c_begin, cudaStream_t st) {
+  wgrad_reduce_kernel<<<dim3((Cin + kWrCi - 1) / kWrCi, Cout), 192, 0, st>>>(part, dw, splits, taps, Cout, Cin,
+                                                                             cin_total, c_begin);
 }
 
 static int wgrad_plan(int B, int Ho, int Wo, int Cin, int Cout, int ksize, int* splits, int* chunks_per_split,
@@ -258,49 +289,79 @@ static int wgrad_plan(int B, int Ho, int Wo, int Cin, int Cout, int ksize, int* 
 // =============================================================================================================
 // column sums: dY [B][HW][C] bf16 -> out[B][C] fp32 (per-sample), two stages
 // =============================================================================================================
-__global__ void __launch_bounds__(1024) colsum_partial_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                               float* __restrict__ part, int64_t HW, int C,
-                                                               int rows_per_blk) {
+// thread = (8-channel group, row lane) as in the GroupNorm passes: 16-byte loads, four in flight per thread
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const uint4* __restrict__ dy, float* __restrict__ part,
+                                                              int64_t HW, int C8, int lanes, int rows_per_blk) {
+  extern __shared__ float cred[];  // [lanes][C]
   const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
-  const int64_t r0 = (int64_t)blk * rows_per_blk;
-  const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
-  for (int cp = threadIdx.x; cp < C / 2; cp += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(dy + ((int64_t)b * HW) * C) + cp;
-    for (int64_t r = r0; r < r1; ++r) {
-      const float2 v = unpack_bf16x2(src[r * (C / 2)]);
-      s0 += v.x;
-      s1 += v.y;
+  const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
+  const int C = C8 * 8;
+  if (lane < lanes) {
+    float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t r0 = (int64_t)blk * rows_per_blk;
+    const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
+    const uint4* src = dy + ((int64_t)b * HW) * C8 + c8;
+    constexpr int kU = 4;
+    for (int64_t r = r0 + lane; r < r1; r += (int64_t)lanes * kU) {
+      uint4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t ru = r + (int64_t)u * lanes;
+        v[u] = ru < r1 ? __ldg(src + ru * C8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(w[k]);
+          cs[2 * k] += f.x;
+          cs[2 * k + 1] += f.y;
+        }
+      }
     }
-    float* dst = part + ((int64_t)b * nblk + blk) * C + cp * 2;
-    dst[0] = s0;
-    dst[1] = s1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cred[(lane * C8 + c8) * 8 + k] = cs[k];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += cred[l * C + idx];
+    part[((int64_t)b * nblk + blk) * C + idx] = acc;
   }
 }
 
-// stage 2: out[b][c] = sum_blk part[b][blk][c] (fixed order); total[c] = sum_b out[b][c] (fixed order).
-// block = (32 channels, BY sample lanes)
-__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                                             float* __restrict__ total, int B, int nblk, int C) {
-  __shared__ float sh[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float mine = 0.f;
-  if (c < C) {
-    for (int b = threadIdx.y; b < B; b += blockDim.y) {
-      const float* src = part + ((int64_t)b * nblk) * C + c;
-      float acc = 0.f;
-      for (int k = 0; k < nblk; ++k) acc += src[(int64_t)k * C];
-      out[(int64_t)b * C + c] = acc;
-      mine += acc;
-    }
-  }
-  sh[threadIdx.y][threadIdx.x] = mine;
+// stage 2: out[b][c] = sum_blk part[b][blk][c] (row length ld; fixed order); total[c] = sum_b out[b][c] (fixed order,
+// folded by whichever block of the column group finishes last).  grid (ceil(C/32), B), block (32 channels, 8 lanes).
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, float* out,
+                                                            float* __restrict__ total, int B, int nblk, int C, int ld,
+                                                            int* tickets) {
+  __shared__ float sh[8][33];
+  __shared__ int s_last;
+  const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
+  float acc = 0.f;
+  if (c < C)
+    for (int k = threadIdx.y; k < nblk; k += 8) acc += __ldg(part + ((int64_t)b * nblk + k) * ld + c);
+  sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
-  if (total != nullptr && threadIdx.y == 0 && c < C) {
-    float acc = 0.f;
-    for (int y = 0; y < blockDim.y; ++y) acc += sh[y][threadIdx.x];
-    total[c] = acc;
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += sh[y][threadIdx.x];
+    out[(int64_t)b * C + c] = t;
   }
+  if (total == nullptr) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_last = atomicAdd(tickets + kTicketCols + blockIdx.x, 1) == B - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+    for (int s = 0; s < B; ++s) t += __ldcg(out + (int64_t)s * C + c);
+    total[c] = t;
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) tickets[kTicketCols + blockIdx.x] = 0;
 }
 
 // =============================================================================================================
@@ -361,8 +422,9 @@ __device__ __forceinline__ float silu_grad_f(float n) {
   return s * (1.f + n * (1.f - s));
 }
 
-// coefficient table per (sample, channel), 8 floats: a, b (forward affine n = a*x + b), mean, rstd, A, m1, m2, pad
-constexpr int kGnTab = 8;
+// coefficient table per (sample, channel), written by the partial pass's finalize, read by the apply pass:
+// a, b (forward affine n = a*x + b), P, Q (dx = a*dn + P + Q*x)
+constexpr int kGnTab = 4;
 
 // SiLU'(n) with one special-function op: sigma(n) = 0.5 + 0.5 * tanh(n / 2)
 __device__ __forceinline__ float silu_grad_fast(float n) {
@@ -372,29 +434,91 @@ __device__ __forceinline__ float silu_grad_fast(float n) {
   return s * fmaf(n, 1.f - s, 1.f);
 }
 
+// SiLU'(2h) for a channel pair from h = n/2: t = tanh(h), sigma = (1 + t)/2, SiLU' = sigma * (1 + h*(1 - t))
+__device__ __forceinline__ float2 silu_grad2(float2 h) {
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+  const float2 one = make_float2(1.f, 1.f), half = make_float2(0.5f, 0.5f);
+  const float2 w = ffma2(t, make_float2(-1.f, -1.f), one);  // 1 - t
+  const float2 u = ffma2(h, w, one);
+  return fmul2(ffma2(t, half, half), u);
+}
+
+// forward affine of channel c of sample b: n = a*x + b (GroupNorm, optional scale-shift folded in)
+__device__ __forceinline__ void gn_affine_coef(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, const float* __restrict__ ss,
+                                               int64_t ss_stride, int b, int c, int C, int cpg, int groups, float& a,
+                                               float& bb, float& mean, float& rstd) {
+  const int g = c / cpg;
+  mean = stats[((int64_t)b * groups + g) * 2 + 0];
+  rstd = stats[((int64_t)b * groups + g) * 2 + 1];
+  float ga = gamma[c], be = beta[c];
+  if (ss != nullptr) {
+    const float sc = 1.f + ss[b * ss_stride + c];
+    ga *= sc;
+    be = fmaf(be, sc, ss[b * ss_stride + C + c]);
+  }
+  a = rstd * ga;
+  bb = fmaf(-mean, a, be);
+}
+
+struct GnBwdTail {  // what the last CTA of a sample / of the launch needs
+  const float* stats;
+  const float* gamma;
+  const float* beta;
+  const float* ss;
+  int64_t ss_stride;
+  int groups;
+  float inv_n;
+  float* tab;       // [B][C][kGnTab]
+  float* dgb_part;  // [B][2][C] per-sample (dgamma, dbeta)
+  float* dss;       // [B][2C] or NULL
+  float* dgamma;    // [2][C], or [C] when dbeta is given
+  float* dbeta;     // [C] or NULL
+  int* tickets;
+  int B;
+};
+
 // Thread layout of the two streaming passes: a block covers all C channels of a run of rows; thread = (8-channel
 // group c8 = tid % C8, row lane = tid / C8), so its per-channel coefficients stay in registers for the whole run and
 // every global access is a 16-byte vector.
-// stage 1: S1[b][c] = sum_p dn, S2[b][c] = sum_p dn * xhat   (partials per row block)
-__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __restrict__ x0, int C0_8,
+// pass 1: S1[b][c] = sum_p dn, S2[b][c] = sum_p dn * x (partials per row block; xhat is applied to the folded sums).
+// The LAST block of a sample to finish folds that sample's partials in a fixed order, forms the group sums and
+// writes the apply pass's coefficient table and the per-sample parameter gradients; the last block of the launch
+// folds those over the samples into dgamma / dbeta.  (Tickets only decide WHO folds; the order is fixed.)
+__global__ void __launch_bounds__(256, 2) gn_bwd_partial_kernel(const uint4* __restrict__ x0, int C0_8,
                                                               const uint4* __restrict__ x1, const uint4* __restrict__ da,
-                                                              const float* __restrict__ tab, float* __restrict__ part,
-                                                              int64_t HW, int C8, int lanes, int rows_per_blk,
-                                                              int silu) {
-  extern __shared__ float red[];  // [lanes][C8*16]
+                                                              float* part, int64_t HW, int C8, int lanes,
+                                                              int rows_per_blk, int silu, GnBwdTail tl) {
+  extern __shared__ float red[];  // [lanes][C8*16], reused by the tail as [4][C]
+  __shared__ int s_last;
   const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
   const int C = C8 * 8;
+  const int cpg = C / tl.groups;
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
   if (lane < lanes) {
-    float ca[8], cb[8], mu[8], rs[8];
+    // forward affine pre-halved: h = (a*x + b) / 2, so that SiLU'(2h) = sigma*(1 + h*(1 - t)), t = tanh(h),
+    // sigma = (1 + t)/2 - all of it on packed fp32 pairs (FFMA2 / FMUL2 / FADD2), two channels per instruction
+    float2 cah[4], cbh[4];
+    if (silu) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 t0 = *reinterpret_cast<const float4*>(tab + ((int64_t)b * C + c8 * 8 + k) * kGnTab);
-      ca[k] = t0.x, cb[k] = t0.y, mu[k] = t0.z, rs[k] = t0.w;
+      for (int k = 0; k < 4; ++k) {
+        float a0, b0, a1, b1, mean, rstd;
+        gn_affine_coef(tl.stats, tl.gamma, tl.beta, tl.ss, tl.ss_stride, b, c8 * 8 + 2 * k, C, cpg, tl.groups, a0, b0,
+                       mean, rstd);
+        gn_affine_coef(tl.stats, tl.gamma, tl.beta, tl.ss, tl.ss_stride, b, c8 * 8 + 2 * k + 1, C, cpg, tl.groups, a1,
+                       b1, mean, rstd);
+        cah[k] = make_float2(0.5f * a0, 0.5f * a1);
+        cbh[k] = make_float2(0.5f * b0, 0.5f * b1);
+      }
     }
+    float2 p1[4], p2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p1[k] = p2[k] = make_float2(0.f, 0.f);
     const int64_t r0 = (int64_t)blk * rows_per_blk;
     const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
     // the input is the virtual channel concat of (x0 [C0], x1 [C - C0]); this thread's 8 channels lie in one of them
@@ -418,18 +542,18 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __rest
         const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
-          float d0 = df.x, d1 = df.y;
-          if (silu) {
-            d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
-            d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
-          }
-          s1[2 * k] += d0;
-          s2[2 * k] = fmaf(d0, (xf.x - mu[2 * k]) * rs[2 * k], s2[2 * k]);
-          s1[2 * k + 1] += d1;
-          s2[2 * k + 1] = fmaf(d1, (xf.y - mu[2 * k + 1]) * rs[2 * k + 1], s2[2 * k + 1]);
+          const float2 xf = bf16x2_as_f32x2(xw[k]);
+          float2 dn = bf16x2_as_f32x2(dw[k]);
+          if (silu) dn = fmul2(dn, silu_grad2(ffma2(cah[k], xf, cbh[k])));
+          p1[k] = fadd2(p1[k], dn);
+          p2[k] = ffma2(dn, xf, p2[k]);
         }
       }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s1[2 * k] = p1[k].x, s1[2 * k + 1] = p1[k].y;
+      s2[2 * k] = p2[k].x, s2[2 * k + 1] = p2[k].y;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -446,66 +570,57 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const uint4* __rest
     float* dst = part + (((int64_t)b * nblk + blk) * 2) * C;
     dst[(j >> 3) * C + cc * 8 + (j & 7)] = acc;
   }
-}
-
-// forward table: a, b, mean, rstd per (sample, channel).  One block per sample.
-__global__ void __launch_bounds__(1024) gn_bwd_table_kernel(const float* __restrict__ stats,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta,
-                                                             const float* __restrict__ ss, int64_t ss_stride, int C,
-                                                             int groups, float* __restrict__ tab) {
-  const int b = blockIdx.x;
-  const int cpg = C / groups;
+  // ---- ticket: is this the last block of sample b? -----------------------------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(tl.tickets + b, 1) == nblk - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float* S = red;          // [2][C] folded sums
+  float* G = red + 2 * C;  // [2][C] gamma' * sums, for the group totals
+  {
+    // fold the nblk partial rows of this sample: float4 columns x up to 8 row groups (rows k = grp, grp + ng, ...), then
+    // the groups in order - the summation order depends only on (nblk, C), never on which block got here last
+    const int n4 = (2 * C) >> 2;
+    int ng = (int)blockDim.x / n4;
+    ng = ng < 1 ? 1 : (ng > 8 ? 8 : ng);
+    float4* F = reinterpret_cast<float4*>(red);  // [ng][n4]
+    const float4* src0 = reinterpret_cast<const float4*>(part + ((int64_t)b * nblk * 2) * C);
+    for (int item = threadIdx.x; item < ng * n4; item += blockDim.x) {
+      const int grp = item / n4, col = item - grp * n4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int k = grp; k < nblk; k += ng) {
+        const float4 v = __ldcg(src0 + (int64_t)k * n4 + col);
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
+      F[grp * n4 + col] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+      float acc = red[idx];
+      for (int gq = 1; gq < ng; ++gq) acc += red[gq * 2 * C + idx];
+      S[idx] = acc;  // in place over group 0's row: column idx is touched by this thread only
+    }
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float mean = stats[((int64_t)b * groups + g) * 2 + 0];
-    const float rstd = stats[((int64_t)b * groups + g) * 2 + 1];
-    float ga = gamma[c], be = beta[c];
-    if (ss != nullptr) {
-      const float sc = 1.f + ss[b * ss_stride + c];
-      ga *= sc;
-      be = fmaf(be, sc, ss[b * ss_stride + C + c]);
-    }
-    float* t = tab + ((int64_t)b * C + c) * kGnTab;
-    const float a = rstd * ga;
-    t[0] = a;
-    t[1] = fmaf(-mean, a, be);
-    t[2] = mean;
-    t[3] = rstd;
-  }
-}
-
-// stage 2: group sums -> A, m1, m2 of the table; per-sample parameter gradients.  One block per sample.
-// S: [B][2][C] (S1 then S2).  dgb_part: [B][2][C] (per-sample dgamma, dbeta); dss: [B][2C] or NULL.
-__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ part, int nblk,
-                                                                const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta,
-                                                                const float* __restrict__ ss, int64_t ss_stride,
-                                                                int C, int groups, float inv_n,
-                                                                float* __restrict__ tab, float* __restrict__ dgb_part,
-                                                                float* __restrict__ dss) {
-  extern __shared__ float sh[];  // [2][C]
-  const int b = blockIdx.x;
-  const int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    // fixed-order fold of the row-block partials [b][blk][2][C]
-    const float* src = part + ((int64_t)b * nblk * 2) * C + c;
-    float s1 = 0.f, s2 = 0.f;
-    for (int k = 0; k < nblk; ++k) {
-      s1 += src[(int64_t)k * 2 * C];
-      s2 += src[(int64_t)k * 2 * C + C];
-    }
-    float ga = gamma[c];
-    float sc = 1.f;
-    if (ss != nullptr) sc = 1.f + ss[b * ss_stride + c];
+    const float mean = tl.stats[((int64_t)b * tl.groups + g) * 2 + 0];
+    const float rstd = tl.stats[((int64_t)b * tl.groups + g) * 2 + 1];
+    const float t1 = S[c];
+    const float t2 = rstd * fmaf(-mean, t1, S[C + c]);  // sum dn * xhat
+    const float ga = tl.gamma[c];
+    const float sc = tl.ss != nullptr ? 1.f + tl.ss[b * tl.ss_stride + c] : 1.f;
     const float gp = ga * sc;
-    sh[c] = gp * s1;
-    sh[C + c] = gp * s2;
-    dgb_part[((int64_t)b * 2) * C + c] = s2 * sc;      // dgamma contribution
-    dgb_part[((int64_t)b * 2 + 1) * C + c] = s1 * sc;  // dbeta contribution
-    if (dss != nullptr) {
-      dss[(int64_t)b * 2 * C + c] = fmaf(s2, ga, s1 * beta[c]);  // d scale
-      dss[(int64_t)b * 2 * C + C + c] = s1;                      // d shift
+    G[c] = gp * t1;
+    G[C + c] = gp * t2;
+    tl.dgb_part[((int64_t)b * 2) * C + c] = t2 * sc;      // dgamma contribution
+    tl.dgb_part[((int64_t)b * 2 + 1) * C + c] = t1 * sc;  // dbeta contribution
+    if (tl.dss != nullptr) {
+      tl.dss[(int64_t)b * 2 * C + c] = fmaf(t2, ga, t1 * tl.beta[c]);  // d scale
+      tl.dss[(int64_t)b * 2 * C + C + c] = t1;                         // d shift
     }
   }
   __syncthreads();
@@ -513,23 +628,45 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
     const int g0 = (c / cpg) * cpg;
     float g1 = 0.f, g2 = 0.f;
     for (int k = 0; k < cpg; ++k) {
-      g1 += sh[g0 + k];
-      g2 += sh[C + g0 + k];
+      g1 += G[g0 + k];
+      g2 += G[C + g0 + k];
     }
-    float* t = tab + ((int64_t)b * C + c) * kGnTab;
-    const float rstd = t[3];
-    t[4] = t[0];  // A = rstd * gamma'
-    t[5] = rstd * g1 * inv_n;
-    t[6] = rstd * g2 * inv_n;
+    float a, bb, mean, rstd;
+    gn_affine_coef(tl.stats, tl.gamma, tl.beta, tl.ss, tl.ss_stride, b, c, C, cpg, tl.groups, a, bb, mean, rstd);
+    const float m1 = rstd * g1 * tl.inv_n, m2 = rstd * g2 * tl.inv_n;
+    // dx = A*dn - m1 - m2*xhat = a*dn + P + Q*x  (P = m2*mean*rstd - m1, Q = -m2*rstd)
+    *reinterpret_cast<float4*>(tl.tab + ((int64_t)b * C + c) * kGnTab) =
+        make_float4(a, bb, fmaf(m2, mean * rstd, -m1), -m2 * rstd);
   }
+  // ---- ticket: last sample of the launch folds the parameter gradients over the batch -----------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tl.tickets[b] = 0;
+    s_last = atomicAdd(tl.tickets + kTicketGlobal, 1) == tl.B - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < tl.B; ++s) acc += __ldcg(tl.dgb_part + (int64_t)s * 2 * C + idx);
+    if (tl.dbeta != nullptr && idx >= C) tl.dbeta[idx - C] = acc;
+    else tl.dgamma[idx] = acc;
+  }
+  if (threadIdx.x == 0) tl.tickets[kTicketGlobal] = 0;
 }
 
-// stage 3: dx = A*dn - m1 - m2*xhat = A*dn + P + Q*x  (P = m2*mean*rstd - m1, Q = -m2*rstd)
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restrict__ x0, int C0_8,
+// pass 2: dx = a*dn + P + Q*x (+ the gradients other consumers of x left: add_a / add_b for source 0, add_1 for source 1)
+template <bool ADD>
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const uint4* __restrict__ x0, int C0_8,
                                                             const uint4* __restrict__ x1, const uint4* __restrict__ da,
                                                             const float* __restrict__ tab, uint4* __restrict__ dx0,
                                                             uint4* __restrict__ dx1, int64_t HW, int C8, int lanes,
-                                                            int rows_per_blk, int silu, float* __restrict__ colpart) {
+                                                            int rows_per_blk, int silu, float* __restrict__ colpart,
+                                                            const uint4* __restrict__ add_a,
+                                                            const uint4* __restrict__ add_b,
+                                                            const uint4* __restrict__ add_1) {
   // colpart (optional): per-block column sums of dx, [B][nblk][C] -- the bias / time-embedding-add gradient of the conv
   // that produced x, so that conv's backward needs no column-sum pass over dx
   extern __shared__ float cred[];  // [lanes][C8*8], only when colpart != NULL
@@ -538,56 +675,68 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const uint4* __restri
   const int C = C8 * 8;
   float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane < lanes) {
-  float ca[8], cb[8], cA[8], cP[8], cQ[8];
+    float2 ca[4], cah[4], cbh[4], cP[4], cQ[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float4* t = reinterpret_cast<const float4*>(tab + ((int64_t)b * C + c8 * 8 + k) * kGnTab);
-    const float4 t0 = t[0], t1 = t[1];  // (a, b, mean, rstd), (A, m1, m2, -)
-    ca[k] = t0.x, cb[k] = t0.y, cA[k] = t1.x;
-    cP[k] = fmaf(t1.z, t0.z * t0.w, -t1.y);
-    cQ[k] = -t1.z * t0.w;
-  }
-  const int64_t r0 = (int64_t)blk * rows_per_blk;
-  const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
-  const int xC8 = c8 < C0_8 ? C0_8 : C8 - C0_8;
-  const int64_t xoff = ((int64_t)b * HW) * xC8 + (c8 < C0_8 ? c8 : c8 - C0_8);
-  const uint4* xs = (c8 < C0_8 ? x0 : x1) + xoff;
-  const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
-  uint4* os = (c8 < C0_8 ? dx0 : dx1) + xoff;
-  constexpr int kU = 4;
-  for (int64_t r = r0 + lane; r < r1; r += (int64_t)lanes * kU) {
-    uint4 xv[kU], dv[kU];
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int64_t ru = r + (int64_t)u * lanes;
-      if (ru < r1) {
-        xv[u] = __ldg(xs + ru * xC8);
-        dv[u] = __ldg(ds + ru * C8);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float4 t0 = *reinterpret_cast<const float4*>(tab + ((int64_t)b * C + c8 * 8 + 2 * k) * kGnTab);
+      const float4 t1 = *reinterpret_cast<const float4*>(tab + ((int64_t)b * C + c8 * 8 + 2 * k + 1) * kGnTab);
+      ca[k] = make_float2(t0.x, t1.x);
+      cah[k] = make_float2(0.5f * t0.x, 0.5f * t1.x), cbh[k] = make_float2(0.5f * t0.y, 0.5f * t1.y);
+      cP[k] = make_float2(t0.z, t1.z), cQ[k] = make_float2(t0.w, t1.w);
     }
+    float2 cs2[4];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int64_t ru = r + (int64_t)u * lanes;
-      if (ru >= r1) break;
-      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
-      uint32_t ow[4];
+    for (int k = 0; k < 4; ++k) cs2[k] = make_float2(0.f, 0.f);
+    const int64_t r0 = (int64_t)blk * rows_per_blk;
+    const int64_t r1 = r0 + rows_per_blk < HW ? r0 + rows_per_blk : HW;
+    const bool first = c8 < C0_8;
+    const int xC8 = first ? C0_8 : C8 - C0_8;
+    const int64_t xoff = ((int64_t)b * HW) * xC8 + (first ? c8 : c8 - C0_8);
+    const uint4* xs = (first ? x0 : x1) + xoff;
+    const uint4* ds = da + ((int64_t)b * HW) * C8 + c8;
+    uint4* os = (first ? dx0 : dx1) + xoff;
+    const uint4* ea = ADD ? (first ? add_a : add_1) : nullptr;
+    const uint4* eb = ADD && first ? add_b : nullptr;
+    if (ea != nullptr) ea += xoff;
+    if (eb != nullptr) eb += xoff;
+    constexpr int kU = ADD ? 2 : 4;  // independent row loads in flight per thread (x, dout and the added tensors)
+    constexpr int kA = ADD ? kU : 1;
+    for (int64_t r = r0 + lane; r < r1; r += (int64_t)lanes * kU) {
+      uint4 xv[kU], dv[kU], av[kA], bv[kA];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 xf = unpack_bf16x2(xw[k]), df = unpack_bf16x2(dw[k]);
-        float d0 = df.x, d1 = df.y;
-        if (silu) {
-          d0 *= silu_grad_fast(fmaf(ca[2 * k], xf.x, cb[2 * k]));
-          d1 *= silu_grad_fast(fmaf(ca[2 * k + 1], xf.y, cb[2 * k + 1]));
+      for (int u = 0; u < kU; ++u) {
+        const int64_t ru = r + (int64_t)u * lanes;
+        if (ADD) av[u % kA] = bv[u % kA] = make_uint4(0, 0, 0, 0);
+        if (ru < r1) {
+          xv[u] = __ldg(xs + ru * xC8);
+          dv[u] = __ldg(ds + ru * C8);
+          if (ADD && ea != nullptr) av[u % kA] = __ldg(ea + ru * xC8);
+          if (ADD && eb != nullptr) bv[u % kA] = __ldg(eb + ru * xC8);
         }
-        const float o0 = fmaf(cA[2 * k], d0, fmaf(cQ[2 * k], xf.x, cP[2 * k]));
-        const float o1 = fmaf(cA[2 * k + 1], d1, fmaf(cQ[2 * k + 1], xf.y, cP[2 * k + 1]));
-        ow[k] = pack_bf16x2(o0, o1);
-        cs[2 * k] += o0;
-        cs[2 * k + 1] += o1;
       }
-      os[ru * xC8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t ru = r + (int64_t)u * lanes;
+        if (ru >= r1) break;
+        const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+        const uint32_t aw[4] = {av[u % kA].x, av[u % kA].y, av[u % kA].z, av[u % kA].w};
+        const uint32_t bw[4] = {bv[u % kA].x, bv[u % kA].y, bv[u % kA].z, bv[u % kA].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 xf = bf16x2_as_f32x2(xw[k]);
+          float2 dn = bf16x2_as_f32x2(dw[k]);
+          if (silu) dn = fmul2(dn, silu_grad2(ffma2(cah[k], xf, cbh[k])));
+          float2 o = ffma2(ca[k], dn, ffma2(cQ[k], xf, cP[k]));
+          if (ADD) o = fadd2(o, fadd2(bf16x2_as_f32x2(aw[k]), bf16x2_as_f32x2(bw[k])));  // absent tensors load as zeros
+          ow[k] = pack_bf16x2(o.x, o.y);
+          cs2[k] = fadd2(cs2[k], o);
+        }
+        os[ru * xC8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
     }
-  }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cs[2 * k] = cs2[k].x, cs[2 * k + 1] = cs2[k].y;
   }
   if (colpart == nullptr) return;
   if (lane < lanes) {
@@ -1133,7 +1282,7 @@ extern "C" int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, floa
     const int64_t ws_elems = fm_conv_wgrad_workspace_elems(B, Ho, Wo, Cin, Cout, ksize);
     const int rc = wgrad_tc_launch(dy, x, workspace, ws_elems, B, H, W, Cin, Cout, ksize, stride, &tc_splits, st);
     if (rc == 0) {
-      wgrad_reduce_kernel<<<ew_grid(per), 256, 0, st>>>(workspace, dw, tc_splits, taps, Cout, Cin, cin_total, c_begin);
+      launch_wgrad_reduce(workspace, dw, tc_splits, taps, Cout, Cin, cin_total, c_begin, st);
       FM_LAUNCH_CHECK("wgrad_reduce_kernel");
       return 0;
     }
@@ -1172,7 +1321,7 @@ extern "C" int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, floa
     conv_wgrad_mma_kernel<1><<<grid, 256, smem, st>>>(p);
   }
   FM_LAUNCH_CHECK("conv_wgrad_mma_kernel");
-  wgrad_reduce_kernel<<<ew_grid(per), 256, 0, st>>>(workspace, dw, splits, taps, Cout, Cin, cin_total, c_begin);
+  launch_wgrad_reduce(workspace, dw, splits, taps, Cout, Cin, cin_total, c_begin, st);
   FM_LAUNCH_CHECK("wgrad_reduce_kernel");
   return 0;
 }
@@ -1189,24 +1338,31 @@ extern "C" int64_t fm_colsum_workspace_elems(int32_t B, int64_t HW, int32_t C) {
   return (int64_t)B * colsum_blocks(HW, B) * C;
 }
 
+static int launch_colsum_final(const float* part, float* out, float* total, int B, int nblk, int C, int ld, int* tickets,
+                               cudaStream_t st) {
+  FM_REQUIRE(total == nullptr || tickets != nullptr, "colsum: the batch total needs the ticket buffer");
+  FM_REQUIRE((C + 31) / 32 <= kTicketInts - kTicketCols, "colsum: too many channels");
+  colsum_final_kernel<<<dim3((C + 31) / 32, B), dim3(32, 8), 0, st>>>(part, out, total, B, nblk, C, ld, tickets);
+  FM_LAUNCH_CHECK("colsum_final_kernel");
+  return 0;
+}
+
 /* out[b][c] = sum_p dy[b][p][c]; total (or NULL)[c] = sum_b out[b][c] */
 extern "C" int fm_colsum_bf16(const void* dy, float* workspace, float* out, float* total, int32_t B, int64_t HW,
-                              int32_t C, fm_stream_t stream) {
+                              int32_t C, int32_t* tickets, fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   FM_REQUIRE(dy && workspace && out, "colsum: null pointer");
-  FM_REQUIRE(C % 2 == 0, "colsum: C must be even");
+  FM_REQUIRE(C % 8 == 0 && C <= 2048, "colsum: C must be a multiple of 8, at most 2048");
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = colsum_blocks(HW, B);
   const int rows = (int)((HW + nblk - 1) / nblk);
-  int threads = C / 2;
-  threads = ((threads + 31) / 32) * 32;
-  if (threads > 1024) threads = 1024;
-  colsum_partial_kernel<<<dim3(nblk, B), threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), workspace, HW, C,
-                                                          rows);
+  const int C8 = C / 8;
+  const int lanes = C8 >= 256 ? 1 : 256 / C8;
+  const int threads = ((C8 * lanes + 31) / 32) * 32;
+  colsum_partial_kernel<<<dim3(nblk, B), threads, (size_t)lanes * C * sizeof(float), st>>>(
+      reinterpret_cast<const uint4*>(dy), workspace, HW, C8, lanes, rows);
   FM_LAUNCH_CHECK("colsum_partial_kernel");
-  colsum_final_kernel<<<(C + 31) / 32, dim3(32, B < 32 ? B : 32), 0, st>>>(workspace, out, total, B, nblk, C);
-  FM_LAUNCH_CHECK("colsum_final_kernel");
-  return 0;
+  return launch_colsum_final(workspace, out, total, B, nblk, C, C, tickets, st);
 }
 
 extern "C" int fm_zero_insert2x_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
@@ -1246,69 +1402,68 @@ extern "C" int32_t fm_groupnorm_bwd_blocks(int32_t B, int64_t HW) {
   return gn_bwd_blocks(HW, B);
 }
 
-/* out[b][c] = sum_blk partials[b][blk][c]; total (or NULL)[c] = sum_b out[b][c]  (second stage of fm_colsum_bf16, also
- * fed by fm_groupnorm_bwd_bf16's dx_colsum_partials) */
+/* out[b][c] = sum_blk partials[(b*nblk + blk)*ld + c]; total (or NULL)[c] = sum_b out[b][c]  (second stage of
+ * fm_colsum_bf16, also fed by fm_groupnorm_bwd_bf16's dx_colsum_partials, whose rows hold all C0+C1 channels) */
 extern "C" int fm_colsum_finish_f32(const float* partials, float* out, float* total, int32_t B, int32_t nblk, int32_t C,
-                                    fm_stream_t stream) {
+                                    int32_t ld, int32_t* tickets, fm_stream_t stream) {
   if (int e = ensure_device()) return e;
-  FM_REQUIRE(partials && out && B > 0 && nblk > 0 && C > 0, "colsum_finish: bad argument");
-  colsum_final_kernel<<<(C + 31) / 32, dim3(32, B < 32 ? B : 32), 0, (cudaStream_t)stream>>>(partials, out, total, B,
-                                                                                           nblk, C);
-  FM_LAUNCH_CHECK("colsum_final_kernel");
-  return 0;
+  FM_REQUIRE(partials && out && B > 0 && nblk > 0 && C > 0 && ld >= C, "colsum_finish: bad argument");
+  return launch_colsum_final(partials, out, total, B, nblk, C, ld, tickets, (cudaStream_t)stream);
 }
+
+extern "C" int32_t fm_ticket_ints(void) { return kTicketInts; }
 
 extern "C" int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C) {
   if (ensure_device()) return 0;
-  /* table [B][C][8] + partials [B][nblk][2][C] + folded sums [B][2][C] + dgb_part [B][2][C] */
-  return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 4LL * B * C;
+  /* table [B][C][4] + partials [B][nblk][2][C] + dgb_part [B][2][C] */
+  return (int64_t)B * C * kGnTab + (int64_t)B * gn_bwd_blocks(HW, B) * 2 * C + 2LL * B * C;
 }
 
 extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout,
                                      const float* stats, const float* gamma, const float* beta,
                                      const float* scale_shift, int64_t ss_stride, int32_t silu, int32_t B, int64_t HW,
                                      int32_t groups, float* workspace, void* dx0, void* dx1, float* dgamma_dbeta,
-                                     float* dscale_shift, float* dx_colsum_partials, float* dbeta,
-                                     fm_stream_t stream) {
+                                     float* dscale_shift, float* dx_colsum_partials, float* dbeta, const void* add0_a,
+                                     const void* add0_b, const void* add1, int32_t* tickets, fm_stream_t stream) {
   const int32_t C = C0 + C1;
   if (int e = ensure_device()) return e;
-  FM_REQUIRE(x0 && dout && stats && gamma && beta && workspace && dx0 && dgamma_dbeta, "groupnorm_bwd: null pointer");
+  FM_REQUIRE(x0 && dout && stats && gamma && beta && workspace && dx0 && dgamma_dbeta && tickets,
+             "groupnorm_bwd: null pointer");
   FM_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && groups > 0 && C % groups == 0,
              "groupnorm_bwd: channel counts must be multiples of 8 and C of groups");
   FM_REQUIRE((C1 == 0) == (x1 == nullptr) && (C1 == 0) == (dx1 == nullptr), "groupnorm_bwd: second source mismatch");
-    FM_REQUIRE((scale_shift == nullptr) == (dscale_shift == nullptr), "groupnorm_bwd: scale_shift / dscale_shift mismatch");
+  FM_REQUIRE((scale_shift == nullptr) == (dscale_shift == nullptr), "groupnorm_bwd: scale_shift / dscale_shift mismatch");
+  FM_REQUIRE(add1 == nullptr || x1 != nullptr, "groupnorm_bwd: add1 without a second source");
+  FM_REQUIRE(add0_b == nullptr || add0_a != nullptr, "groupnorm_bwd: add0_b without add0_a");
+  FM_REQUIRE(B < kTicketGlobal, "groupnorm_bwd: batch too large for the ticket buffer");
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = gn_bwd_blocks(HW, B);
   const int rows = (int)((HW + nblk - 1) / nblk);
   float* tab = workspace;
   float* part = tab + (int64_t)B * C * kGnTab;
-  float* S = part + (int64_t)B * nblk * 2 * C;     // row-block partials folded in a fixed order, [B][2][C]
-  float* dgb = S + 2LL * B * C;                    // per-sample (dgamma, dbeta) contributions [B][2][C]
-  int cthreads = ((C + 31) / 32) * 32;
-  if (cthreads > 1024) cthreads = 1024;
-  gn_bwd_table_kernel<<<B, cthreads, 0, st>>>(stats, gamma, beta, scale_shift, ss_stride, C, groups, tab);
-  FM_LAUNCH_CHECK("gn_bwd_table_kernel");
+  float* dgb = part + (int64_t)B * nblk * 2 * C;  // per-sample (dgamma, dbeta) contributions [B][2][C]
   const int C8 = C / 8;
   const int lanes = C8 >= 256 ? 1 : 256 / C8;
   const int sthreads = ((C8 * lanes + 31) / 32) * 32;
   FM_REQUIRE(C8 <= 256, "groupnorm_bwd: C must be <= 2048");
-  gn_bwd_partial_kernel<<<dim3(nblk, B), sthreads, (size_t)lanes * C8 * 16 * sizeof(float), st>>>(
+  GnBwdTail tl;
+  tl.stats = stats, tl.gamma = gamma, tl.beta = beta, tl.ss = scale_shift, tl.ss_stride = ss_stride;
+  tl.groups = groups;
+  tl.inv_n = 1.f / ((float)HW * (float)(C / groups));
+  tl.tab = tab, tl.dgb_part = dgb, tl.dss = dscale_shift, tl.dgamma = dgamma_dbeta, tl.dbeta = dbeta;
+  tl.tickets = tickets, tl.B = B;
+  size_t smem1 = (size_t)lanes * C8 * 16 * sizeof(float);
+  if (smem1 < (size_t)4 * C * sizeof(float)) smem1 = (size_t)4 * C * sizeof(float);
+  gn_bwd_partial_kernel<<<dim3(nblk, B), sthreads, smem1, st>>>(
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
-      reinterpret_cast<const uint4*>(dout), tab, part, HW, C8, lanes, rows, silu);
+      reinterpret_cast<const uint4*>(dout), part, HW, C8, lanes, rows, silu, tl);
   FM_LAUNCH_CHECK("gn_bwd_partial_kernel");
-  const float inv_n = 1.f / ((float)HW * (float)(C / groups));
-  // fold the partials with a wide launch first: the finalize kernel has only B blocks, a serial nblk loop there costs more
-  if (int e = launch_reduce(part, S, B, nblk, 2LL * C, st)) return e;
-  gn_bwd_finalize_kernel<<<B, cthreads, 2 * C * sizeof(float), st>>>(S, 1, gamma, beta, scale_shift, ss_stride, C, groups,
-                                                                    inv_n, tab, dgb, dscale_shift);
-  FM_LAUNCH_CHECK("gn_bwd_finalize_kernel");
-  /* dgamma_dbeta[0 / 1][c]: fixed-order sum over samples of dgb[b][0 / 1][c] */
-  if (int e = launch_reduce(dgb, dgamma_dbeta, 1, B, 2LL * C, st, dbeta, C)) return e;
-  gn_bwd_apply_kernel<<<dim3(nblk, B), sthreads,
-                        dx_colsum_partials ? (size_t)lanes * C * sizeof(float) : 0, st>>>(
+  auto apply = (add0_a || add1) ? gn_bwd_apply_kernel<true> : gn_bwd_apply_kernel<false>;
+  apply<<<dim3(nblk, B), sthreads, dx_colsum_partials ? (size_t)lanes * C * sizeof(float) : 0, st>>>(
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
       reinterpret_cast<const uint4*>(dout), tab, reinterpret_cast<uint4*>(dx0), reinterpret_cast<uint4*>(dx1), HW, C8,
-      lanes, rows, silu, dx_colsum_partials);
+      lanes, rows, silu, dx_colsum_partials, reinterpret_cast<const uint4*>(add0_a),
+      reinterpret_cast<const uint4*>(add0_b), reinterpret_cast<const uint4*>(add1));
   FM_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return 0;
 }

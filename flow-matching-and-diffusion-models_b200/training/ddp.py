@@ -24,6 +24,7 @@ class BucketedAllReduce:
         order = sorted(flat.params, key=lambda p: flat.offsets[id(p)])
         begin, count = 0, 0
         cap = max(1, bucket_bytes // 4)
+        self.bucket_elems = cap
         for p in order:
             o, n = flat.slice_of(p)
             end = o + (n + 3) // 4 * 4
@@ -37,6 +38,7 @@ class BucketedAllReduce:
         self._pending = [0] * len(self.buckets)
         self._handles: List = []
         self._armed = False
+        self._record = None              # set of id(param) while `record()` is active
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in flat.params]
 
     def arm(self) -> None:
@@ -46,6 +48,8 @@ class BucketedAllReduce:
         self._armed = True
 
     def _on_grad(self, p) -> None:
+        if self._record is not None:
+            self._record.add(id(p))
         if not self._armed or self.world == 1:
             return
         i = self.bucket_of[id(p)]
@@ -67,6 +71,59 @@ class BucketedAllReduce:
                 b, e, _ = self.buckets[i]
                 self._handles.append(dist.all_reduce(self.flat.grad[b:e], op=dist.ReduceOp.SUM, group=self.group,
                                                      async_op=True))
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    # ---- staged form (CUDA-graph replayed steps whose backward is cut in two, `training.graph.BackwardCut`) --------
+    def record(self, on: bool):
+        """While on, remember which parameters received their gradient (direct writes and accumulate-grad hooks both
+        end in `_on_grad`); returns the recorded id set when switched off."""
+        got, self._record = self._record, (set() if on else None)
+        return got
+
+    def ranges_of(self, param_ids) -> List[tuple]:
+        """Maximal contiguous flat ranges [(begin, end)] covered by these parameters, split at `bucket` elements."""
+        spans = []
+        for p in self.flat.params:
+            if id(p) in param_ids:
+                o, n = self.flat.slice_of(p)
+                spans.append((o, o + (n + 3) // 4 * 4))
+        spans.sort()
+        merged: List[list] = []
+        for b, e in spans:
+            if merged and merged[-1][1] == b:
+                merged[-1][1] = e
+            else:
+                merged.append([b, e])
+        out = []
+        for b, e in merged:
+            while e - b > self.bucket_elems:
+                out.append((b, b + self.bucket_elems))
+                b += self.bucket_elems
+            out.append((b, e))
+        return out
+
+    def complement(self, ranges) -> List[tuple]:
+        out, pos = [], 0
+        for b, e in sorted(ranges):
+            if b > pos:
+                out.append((pos, b))
+            pos = max(pos, e)
+        if pos < self.flat.numel:
+            out.append((pos, self.flat.numel))
+        return out
+
+    def launch(self, ranges) -> None:
+        """Asynchronous all-reduce of these flat gradient ranges (NCCL's stream waits for the work queued so far on
+        the current stream, then runs beside whatever is queued next); `wait()` joins them."""
+        if self.world == 1:
+            return
+        for b, e in ranges:
+            self._handles.append(dist.all_reduce(self.flat.grad[b:e], op=dist.ReduceOp.SUM, group=self.group,
+                                                 async_op=True))
+
+    def wait(self) -> None:
         for h in self._handles:
             h.wait()
         self._handles = []

@@ -46,6 +46,99 @@ def _grad_written(param) -> None:
         GRAD_READY_HOOK(param)
 
 
+_TICKETS = {}
+
+
+def _tickets(device) -> torch.Tensor:
+    """The per-device ticket buffer of the "last block finishes the job" kernels (`fm_ticket_ints`): allocated and
+    zeroed once (outside any CUDA-graph capture the first eager step reaches it), left zero by every kernel."""
+    key = (device.type, device.index)
+    t = _TICKETS.get(key)
+    if t is None:
+        t = _TICKETS[key] = torch.zeros(int(_lib.lib().fm_ticket_ints()), dtype=torch.int32, device=device)
+    return t
+
+
+# Gradient slots.  A tensor with several consumers (a ResBlock input feeds its GroupNorm AND its residual / skip
+# conv; an encoder output feeds the next block AND a decoder block) would have its gradient summed by autograd with one
+# ATen `add` launch per extra consumer.  Instead the FIRST consumer in forward order - always a GroupNorm or a conv
+# here, and always the last of the consumers to run backward, because every other consumer sits downstream of it -
+# opens a slot on the tensor; later consumers park their contribution in the slot (returning None to autograd) and
+# the first consumer's backward kernel adds the parked tensors while it writes its own dx (`add0_a/b`, `add1` of
+# fm_groupnorm_bwd_bf16, `residual` of the dgrad conv).  The result is bit-for-bit a sum of the same bf16 terms, in
+# fp32, rounded once.
+FUSE_GRAD_ACCUMULATION = True
+
+
+class _Slot:
+    __slots__ = ("parked", "expected", "contributed", "closed")
+
+    def __init__(self):
+        self.parked, self.expected, self.contributed, self.closed = [], 0, 0, False
+
+    def pop_one(self):
+        """A parked tensor for a parking consumer to fold into its own kernel (keeps the parked list short)."""
+        return self.parked.pop() if self.parked else None
+
+    def park(self, g: torch.Tensor) -> None:
+        if self.closed:
+            raise RuntimeError("fmdm_b200.training: a gradient was parked after its accumulating consumer ran backward "
+                               "(consumer order violated); set training.functions.FUSE_GRAD_ACCUMULATION = False")
+        self.parked.append(g)
+        self.contributed += 1
+
+    def take(self, limit: int):
+        """The parked gradients, folded to at most `limit` tensors (more than that is rare: one ATen add each)."""
+        if self.contributed != self.expected:
+            raise RuntimeError(f"fmdm_b200.training: {self.expected} consumers registered on a gradient slot but "
+                               f"{self.contributed} contributed before the accumulating backward ran")
+        self.closed = True
+        got, self.parked = self.parked, []
+        while len(got) > limit:
+            got = [got[0] + got[1]] + got[2:]
+        return got
+
+
+_OPEN_SLOTS = []
+
+
+def assert_slots_drained() -> None:
+    """After a backward pass: every parked gradient must have been consumed (a slot whose accumulating consumer never
+    ran backward would silently drop gradients)."""
+    left = [s for s in _OPEN_SLOTS if s.parked]
+    del _OPEN_SLOTS[:]
+    if left:
+        raise RuntimeError(f"fmdm_b200.training: {len(left)} gradient slot(s) still hold parked gradients after the "
+                           "backward pass; set training.functions.FUSE_GRAD_ACCUMULATION = False")
+
+
+def _slot_eligible(t: torch.Tensor) -> bool:
+    """Only tensors made inside the current forward carry slots: an activation (it has a grad_fn and belongs to one
+    autograd graph) or a `BackwardCut` leaf.  A long-lived leaf (a parameter, an input reused across forwards) could
+    be consumed by several independent backward passes, where a parked gradient would have no one to collect it."""
+    return t.requires_grad and (t.grad_fn is not None or getattr(t, "_fm_fresh_leaf", False))
+
+
+def _slot_open(t: torch.Tensor):
+    """Called by the first consumer of `t`: returns the slot its backward must drain (None if fusion is off)."""
+    if not FUSE_GRAD_ACCUMULATION or not _slot_eligible(t):
+        return None
+    slot = _Slot()
+    t._fm_slot = slot
+    _OPEN_SLOTS.append(slot)
+    return slot
+
+
+def _slot_join(t: torch.Tensor):
+    """Called by a later consumer of `t`: the slot to park into, or None (autograd accumulates as usual)."""
+    slot = getattr(t, "_fm_slot", None) if FUSE_GRAD_ACCUMULATION else None
+    if slot is not None and slot.closed:   # a previous backward already drained it: not part of this graph
+        slot = None
+    if slot is not None:
+        slot.expected += 1
+    return slot
+
+
 def _ws(n: int, device, dtype=torch.float32) -> torch.Tensor:
     return torch.empty((max(int(n), 1),), dtype=dtype, device=device)
 
@@ -90,8 +183,8 @@ def colsum(dy: torch.Tensor, want_total: bool, total: Optional[torch.Tensor] = N
     out = torch.empty((b, c), dtype=torch.float32, device=dy.device)
     if total is None and want_total:
         total = torch.empty((c,), dtype=torch.float32, device=dy.device)
-    _lib.check(lib.fm_colsum_bf16(dy.data_ptr(), ws.data_ptr(), out.data_ptr(), _ptr(total), b, h * w, c, _stream()),
-               "colsum")
+    _lib.check(lib.fm_colsum_bf16(dy.data_ptr(), ws.data_ptr(), out.data_ptr(), _ptr(total), b, h * w, c,
+                                  _tickets(dy.device).data_ptr(), _stream()), "colsum")
     return out, total
 
 
@@ -139,7 +232,7 @@ class _ConvFn(Function):
 
     @staticmethod
     def forward(ctx, meta, *args):
-        stride, segs, nsrc, nw = meta  # segs: per source (weight index, c_begin, c_count)
+        stride, segs, nsrc, nw = meta[:4]  # segs: per source (weight index, c_begin, c_count)
         srcs = [_nhwc(a) for a in args[:nsrc]]
         weights = list(args[nsrc:nsrc + nw])
         bias, addvec, residual = args[nsrc + nw:nsrc + nw + 3]
@@ -163,7 +256,7 @@ class _ConvFn(Function):
 
     @staticmethod
     def backward(ctx, dy):
-        stride, segs, nsrc, nw = ctx.meta
+        stride, segs, nsrc, nw, src_slots, res_slot = ctx.meta
         has_bias, has_addvec, has_res = ctx.flags
         saved = ctx.saved_tensors
         srcs, weights = saved[:nsrc], saved[nsrc:]
@@ -175,12 +268,24 @@ class _ConvFn(Function):
             if not need[1 + i]:
                 continue
             pw = _dgrad_weight(ctx.params[wi], cb, cc, ctx.plan)
+            role, slot = src_slots[i]
+            # gradients other consumers of this source left behind ride in as the dgrad conv's `residual`
+            extra = None
+            if role == "acc":
+                got = slot.take(1)
+                extra = got[0] if got else None
+            elif role == "park":
+                extra = slot.pop_one()
             if stride == 1:
-                grads[i] = ops.conv2d([dy], pw)
+                dx = ops.conv2d([dy], pw, residual=extra)
             else:
                 if dyz is None:
                     dyz = zero_insert2x(dy)
-                grads[i] = ops.conv2d([dyz], pw)
+                dx = ops.conv2d([dyz], pw, residual=extra)
+            if role == "park":
+                slot.park(dx)
+            else:
+                grads[i] = dx
         dws, direct = {}, set()
         for i, (wi, cb, cc) in enumerate(segs):
             if not need[1 + nsrc + wi]:
@@ -212,7 +317,8 @@ class _ConvFn(Function):
                 total = btarget if btarget is not None else (
                     torch.empty((dy.shape[1],), dtype=torch.float32, device=dy.device) if has_bias else None)
                 _lib.check(_lib.lib().fm_colsum_finish_f32(part.data_ptr(), per_sample.data_ptr(), _ptr(total),
-                                                           dy.shape[0], part.shape[1], dy.shape[1], _stream()),
+                                                           dy.shape[0], part.shape[1], dy.shape[1], part.stride(1),
+                                                           _tickets(dy.device).data_ptr(), _stream()),
                            "colsum_finish")
             else:
                 per_sample, total = colsum(dy, has_bias, total=btarget)
@@ -223,7 +329,10 @@ class _ConvFn(Function):
             if has_addvec:
                 grads[nsrc + nw + 1] = per_sample
         if has_res and need[1 + nsrc + nw + 2]:
-            grads[nsrc + nw + 2] = dy
+            if res_slot is not None:
+                res_slot.park(dy)
+            else:
+                grads[nsrc + nw + 2] = dy
         return (None, *grads)
 
 
@@ -240,7 +349,18 @@ def conv(srcs: Sequence[torch.Tensor], weights: Sequence[tuple], *, bias=None, s
         else:
             uniq.append(w)
             segs.append((len(uniq) - 1, int(cb), int(cc)))
-    meta = (int(stride), tuple(segs), len(srcs), len(uniq))
+    # gradient slots (see _Slot): a source this conv consumes first accumulates, a source / residual that already has
+    # an accumulating consumer parks
+    src_slots = []
+    for t in srcs:
+        joined = _slot_join(t)
+        if joined is not None:
+            src_slots.append(("park", joined))
+        else:
+            opened = _slot_open(t)
+            src_slots.append(("acc", opened) if opened is not None else (None, None))
+    res_slot = _slot_join(residual) if residual is not None else None
+    meta = (int(stride), tuple(segs), len(srcs), len(uniq), tuple(src_slots), res_slot)
     return _ConvFn.apply(meta, *srcs, *uniq, bias, addvec, residual)
 
 
@@ -251,8 +371,9 @@ class _GroupNormFn(Function):
     """GroupNorm over the virtual channel concat of one or two sources; the (materialised) result is one tensor."""
 
     @staticmethod
-    def forward(ctx, x0, x1, gamma, beta, scale_shift, groups, eps, silu):
+    def forward(ctx, x0, x1, gamma, beta, scale_shift, groups, eps, silu, slots):
         lib = _lib.lib()
+        ctx.slots = slots
         x0 = _nhwc(x0)
         x1 = None if x1 is None else _nhwc(x1)
         b, c0, h, w = x0.shape
@@ -306,33 +427,60 @@ class _GroupNormFn(Function):
         direct = tg is not None and tb is not None   # dgamma / dbeta land in the flat gradient, no AccumulateGrad
         dgb = None if direct else torch.empty((2, c), dtype=torch.float32, device=x0.device)
         dss = torch.empty((b, 2 * c), dtype=torch.float32, device=x0.device) if has_ss else None
-        # single source: also emit the column sums of dx (first stage); if x came straight out of a conv, that conv's
-        # backward turns them into its bias / embedding-add gradients without another pass over dx
-        nblk = int(lib.fm_groupnorm_bwd_blocks(b, h * w)) if not has_x1 else 0
+        # gradients the other consumers of x0 / x1 parked (`_Slot`): added by the apply pass while it writes dx
+        (role0, slot0), (role1, slot1) = ctx.slots
+        add0 = slot0.take(2) if role0 == "acc" else ([slot0.pop_one()] if role0 == "park" else [])
+        add1 = slot1.take(1) if role1 == "acc" else ([slot1.pop_one()] if role1 == "park" else [])
+        add0 = [_nhwc(t) for t in add0 if t is not None]
+        add1 = [_nhwc(t) for t in add1 if t is not None]
+        # also emit the column sums of dx (first stage); if x came straight out of a conv, that conv's backward turns
+        # them into its bias / embedding-add gradients without another pass over dx
+        nblk = int(lib.fm_groupnorm_bwd_blocks(b, h * w))
         colpart = torch.empty((b, nblk, c), dtype=torch.float32, device=x0.device) if nblk > 0 else None
         _lib.check(
             lib.fm_groupnorm_bwd_bf16(x0.data_ptr(), c0, _ptr(x1), c1, dout.data_ptr(), stats.data_ptr(),
                                       g32.data_ptr(), b32.data_ptr(), _ptr(ss), 0 if ss is None else ss.stride(0),
                                       int(silu), b, h * w, groups, ws.data_ptr(), dx0.data_ptr(), _ptr(dx1),
                                       tg.data_ptr() if direct else dgb.data_ptr(), _ptr(dss), _ptr(colpart),
-                                      tb.data_ptr() if direct else None, _stream()),
+                                      tb.data_ptr() if direct else None,
+                                      add0[0].data_ptr() if add0 else None, add0[1].data_ptr() if len(add0) > 1 else None,
+                                      add1[0].data_ptr() if add1 else None, _tickets(x0.device).data_ptr(), _stream()),
             "groupnorm_bwd",
         )
         if colpart is not None:
-            # valid only for this exact tensor state: autograd may accumulate another branch's gradient into dx0 in
+            # valid only for this exact tensor state: autograd may accumulate another branch's gradient into dx in
             # place, which bumps `_version` and invalidates the sums
-            dx0._fm_colsum = (colpart, dx0._version)
+            dx0._fm_colsum = (colpart[:, :, :c0], dx0._version)
+            if has_x1:
+                dx1._fm_colsum = (colpart[:, :, c0:], dx1._version)
+        if role0 == "park":
+            slot0.park(dx0)
+            dx0 = None
+        if has_x1 and role1 == "park":
+            slot1.park(dx1)
+            dx1 = None
         if direct:
             _grad_written(gamma)
             _grad_written(beta)
-            return dx0, dx1, None, None, dss, None, None, None
-        return dx0, dx1, dgb[0], dgb[1], dss, None, None, None
+            return dx0, dx1, None, None, dss, None, None, None, None
+        return dx0, dx1, dgb[0], dgb[1], dss, None, None, None, None
 
 
 def group_norm(x, gamma, beta, *, groups: int, eps: float, silu: bool, scale_shift=None) -> torch.Tensor:
     """`x`: a tensor, or a pair of tensors read as their channel concat (never materialised)."""
     x0, x1 = (x[0], x[1]) if isinstance(x, (tuple, list)) else (x, None)
-    return _GroupNormFn.apply(x0, x1, gamma, beta, scale_shift, int(groups), float(eps), bool(silu))
+    slots = []
+    for t in (x0, x1):
+        if t is None:
+            slots.append((None, None))
+            continue
+        joined = _slot_join(t)
+        if joined is not None:
+            slots.append(("park", joined))
+        else:
+            opened = _slot_open(t)
+            slots.append(("acc", opened) if opened is not None else (None, None))
+    return _GroupNormFn.apply(x0, x1, gamma, beta, scale_shift, int(groups), float(eps), bool(silu), tuple(slots))
 
 
 # --------------------------------------------------------------------------------------------------------------

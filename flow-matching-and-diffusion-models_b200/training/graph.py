@@ -35,16 +35,65 @@ def _gn(norm: nn.GroupNorm, x, *, silu: bool, scale_shift=None):
                         scale_shift=scale_shift)
 
 
+class BackwardCut:
+    """Splits the backward pass of one training forward into two stages so that the data-parallel gradient all-reduce
+    of the first stage's parameters runs while the second stage still computes (`training.step`): every tensor that
+    flows from the early part of the network (stage 2 of the backward: stem, time MLP, the first down blocks) into
+    the late part (stage 1: the remaining down blocks, mid block, up path, head) is replaced by a detached leaf;
+    `loss.backward()` then stops at the leaves, and `finish()` continues from their gradients.
+
+    A UNet's parameters sit almost entirely in its low-resolution levels while its backward time sits in the
+    high-resolution ones, so cutting after the high-resolution down blocks leaves ~95 % of the gradient bytes ready
+    with ~40 % of the backward still to run."""
+
+    def __init__(self):
+        self.outer, self.inner, self._by_id = [], [], {}
+
+    def cross(self, t: torch.Tensor) -> torch.Tensor:
+        leaf = self._by_id.get(id(t))
+        if leaf is None:
+            leaf = t.detach().requires_grad_(True)
+            leaf._fm_fresh_leaf = True                   # made in this forward: may carry a gradient slot
+            stats = getattr(t, "_fm_stats", None)        # GroupNorm partial statistics the producer conv left
+            if stats is not None:
+                leaf._fm_stats = stats
+            self._by_id[id(t)] = leaf
+            self.outer.append(t)
+            self.inner.append(leaf)
+        return leaf
+
+    def finish(self) -> None:
+        """Stage 2: backward of the early part from the gradients `loss.backward()` left on the leaves."""
+        outs = [o for o, l in zip(self.outer, self.inner) if l.grad is not None]
+        grads = [l.grad for l in self.inner if l.grad is not None]
+        self.outer, self.inner, self._by_id = [], [], {}
+        if outs:
+            torch.autograd.backward(outs, grads)
+
+
+def finish_backward(model) -> None:
+    """Run the second backward stage of `model`'s last training forward, if that forward was cut."""
+    cut = model.__dict__.pop("_fm_cut_state", None)
+    if cut is not None:
+        cut.finish()
+
+
+def _embedding_blocks(modules):
+    from ..nn.blocks.residual import ResBlockND
+
+    return [m for mod in modules for m in mod.modules() if isinstance(m, ResBlockND) and m.uses_embedding
+            and (m.use_scale_shift_norm or m.add_embedding_to_hidden)]
+
+
 class EmbProjections:
     """Every ResBlock's `emb_layers` projection of the time embedding in ONE launch (`residual.py:99-108` runs one
     Linear per block on the same input): the weights are concatenated per step, the result is split into per-block
-    column views, and the backward is one dX / dW / db GEMM over the concatenation."""
+    column views, and the backward is one dX / dW / db GEMM over the concatenation.  `blocks`: restrict to these
+    ResBlocks (one projection batch per backward stage, see `BackwardCut`)."""
 
-    def __init__(self, model, emb: torch.Tensor):
-        from ..nn.blocks.residual import ResBlockND
-
-        blocks = [m for m in model.modules() if isinstance(m, ResBlockND) and m.uses_embedding
-                  and (m.use_scale_shift_norm or m.add_embedding_to_hidden)]
+    def __init__(self, model, emb: torch.Tensor, blocks=None):
+        if blocks is None:
+            blocks = _embedding_blocks([model])
         self.slices = {}
         groups = {}
         for blk in blocks:
@@ -185,7 +234,12 @@ def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Ten
     feats = ops.timestep_embedding(t, model.model_channels, 10000.0, flip_sin_to_cos=False, freq_shift=0.0)
     emb = F.linear(feats, model.time_embed[0].weight, model.time_embed[0].bias)
     emb = F.linear(emb, model.time_embed[2].weight, model.time_embed[2].bias, silu_in=True)
-    emb = EmbProjections(model, emb)
+    cut_at = model.__dict__.get("_fm_backward_cut")
+    blocks_in = list(model.input_blocks)
+    if cut_at is not None and not 1 <= cut_at < len(blocks_in):
+        cut_at = None
+    raw_emb = emb
+    emb = EmbProjections(model, raw_emb, None if cut_at is None else _embedding_blocks(blocks_in[:cut_at]))
     stem = model.input_blocks[0][0].conv
     cin = x.shape[1] + (context.shape[1] if context is not None else 0)
     if cin != stem.in_channels:
@@ -195,7 +249,13 @@ def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Ten
         raise RuntimeError("fmdm_b200.training: the stem backward supports up to 4 input channels")
     h = F.conv_stem(x, context, stem.weight, stem.bias)
     hs = [h]
-    for block in list(model.input_blocks)[1:]:
+    for i, block in enumerate(blocks_in[1:], start=1):
+        if i == cut_at:
+            cut = model.__dict__["_fm_cut_state"] = BackwardCut()
+            hs = [cut.cross(t) for t in hs]
+            h = hs[-1]
+            emb = EmbProjections(model, cut.cross(raw_emb), _embedding_blocks(
+                blocks_in[cut_at:] + [model.middle_block] + list(model.output_blocks)))
         h = _sequential(block, h, emb)
         hs.append(h)
     h = _sequential(model.middle_block, h, emb)
@@ -220,6 +280,8 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
         plan = model.__dict__["_fm_pack_plan"] = PackPlan()
     plan.begin_step(x.device)
     F.ACTIVE_PLAN = plan
+    model.__dict__.pop("_fm_cut_state", None)
+    del F._OPEN_SLOTS[:]
     if isinstance(model, EfficientUNetND):
         return efficient_unet_forward(model, x, t, context)
     ops.require_cuda(x, "training.unet_forward")
@@ -228,8 +290,12 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
                                    freq_shift=float(model.freq_shift))
     te = model.time_embedding
     emb = F.linear(feats, te.linear_1.weight, te.linear_1.bias)
-    emb = F.linear(emb, te.linear_2.weight, te.linear_2.bias, silu_in=True)  # SiLU between the two layers
-    emb = EmbProjections(model, emb)
+    raw_emb = F.linear(emb, te.linear_2.weight, te.linear_2.bias, silu_in=True)  # SiLU between the two layers
+    down = list(model.down_blocks)
+    cut_at = model.__dict__.get("_fm_backward_cut")     # number of down blocks in the second backward stage
+    if cut_at is not None and not 1 <= cut_at < len(down):
+        cut_at = None
+    emb = EmbProjections(model, raw_emb, None if cut_at is None else _embedding_blocks(down[:cut_at]))
 
     scale, shift = (2.0, -1.0) if model.center_input_sample else (1.0, 0.0)
     cin = x.shape[1] + (context.shape[1] if context is not None else 0)
@@ -241,7 +307,13 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
     sample = F.conv_stem(x, context, model.conv_in.weight, model.conv_in.bias, in_scale=scale, in_shift=shift)
 
     skips = [sample]
-    for block in model.down_blocks:
+    for bi, block in enumerate(down):
+        if bi == cut_at:
+            cut = model.__dict__["_fm_cut_state"] = BackwardCut()
+            skips = [cut.cross(t) for t in skips]
+            sample = skips[-1]
+            late = down[cut_at:] + ([model.mid_block] if model.mid_block is not None else []) + list(model.up_blocks)
+            emb = EmbProjections(model, cut.cross(raw_emb), _embedding_blocks(late))
         for i, res in enumerate(block.resnets):
             sample = resblock(res, sample, emb)
             if block.attentions is not None:

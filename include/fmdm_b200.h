@@ -295,7 +295,11 @@ int fm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, float* workspac
  * [c] = sum_b out[b][c] (the bias gradient).  workspace: fm_colsum_workspace_elems floats. */
 int64_t fm_colsum_workspace_elems(int32_t B, int64_t HW, int32_t C);
 int fm_colsum_bf16(const void* dy, float* workspace, float* out, float* total, int32_t B, int64_t HW, int32_t C,
-                   fm_stream_t stream);
+                   int32_t* tickets, fm_stream_t stream);
+/* tickets: a caller-owned device buffer of fm_ticket_ints() int32, ZERO before its first use and used by one stream at
+ * a time; kernels that end with a "the last block finishes the job" step count their blocks in it and leave it zero
+ * again (the counters only decide which block runs the fixed-order fold, never the order of a sum). */
+int32_t fm_ticket_ints(void);
 /* out[b][2y][2x][c] = x[b][y][x][c], zero elsewhere: turns the dgrad of a stride-2 conv into a stride-1 conv */
 int fm_zero_insert2x_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, fm_stream_t stream);
 /* out[b][y][x][c] = sum of the 2x2 block of x [B][2H][2W][C]: backward of fm_upsample_nearest2x_bf16 */
@@ -303,20 +307,27 @@ int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W
 /* Backward of fm_groupnorm_apply_bf16 over the virtual channel concat of (x0 [C0], x1 [C1] or NULL/0), bf16
  * [B][HW][C_s]; dout bf16 [B][HW][C0+C1]; stats as the forward computed them.  dx0 / dx1 bf16 like x0 / x1;
  * dgamma_dbeta fp32 [2][C]; dscale_shift fp32 [B][2C] (NULL iff scale_shift is NULL).
- * workspace: fm_groupnorm_bwd_workspace_elems(B, HW, C0+C1) floats. */
+ * Two launches: the partial-sum pass (whose last block per sample folds the sums, forms the group totals and the
+ * coefficient table, and whose last block overall folds dgamma / dbeta over the batch) and the apply pass.
+ * add0_a, add0_b (or NULL): bf16 tensors shaped like x0 that are ADDED to dx0 - the gradients other consumers of x0
+ * (a residual connection, a skip connection) produced, so no separate accumulation pass runs; add1: same for dx1.
+ * dbeta (or NULL): when given, dgamma_dbeta receives only the [C] dgamma row and dbeta the [C] dbeta row (two separate
+ * destinations, e.g. the parameters' slices of a flat gradient buffer).
+ * dx_colsum_partials (or NULL): fp32 [B][fm_groupnorm_bwd_blocks(B, HW)][C0+C1] per-block column sums of (dx0 | dx1)
+ * incl. the added tensors, i.e. the first stage of the bias / time-embedding-add gradient of the conv that produced
+ * x; fold with fm_colsum_finish_f32 (ld = C0+C1).
+ * workspace: fm_groupnorm_bwd_workspace_elems(B, HW, C0+C1) floats; tickets: see fm_ticket_ints. */
 int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C);
 int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, const void* dout, const float* stats,
                           const float* gamma, const float* beta, const float* scale_shift, int64_t ss_stride,
                           int32_t silu, int32_t B, int64_t HW, int32_t groups, float* workspace, void* dx0, void* dx1,
                           float* dgamma_dbeta, float* dscale_shift, float* dx_colsum_partials, float* dbeta,
+                          const void* add0_a, const void* add0_b, const void* add1, int32_t* tickets,
                           fm_stream_t stream);
-/* dbeta (or NULL): when given, dgamma_dbeta receives only the [C] dgamma row and dbeta the [C] dbeta row (two separate
- * destinations, e.g. the parameters' slices of a flat gradient buffer) */
-/* dx_colsum_partials (or NULL): fp32 [B][fm_groupnorm_bwd_blocks(B, HW)][C] per-block column sums of dx, i.e. the
- * first stage of the bias / time-embedding-add gradient of the conv that produced x; fold with fm_colsum_finish_f32 */
 int32_t fm_groupnorm_bwd_blocks(int32_t B, int64_t HW);
+/* out[b][c] = sum_blk partials[(b*nblk + blk)*ld + c] (fp32 [B][C]); total (or NULL) [c] = sum_b out[b][c] */
 int fm_colsum_finish_f32(const float* partials, float* out, float* total, int32_t B, int32_t nblk, int32_t C,
-                         fm_stream_t stream);
+                         int32_t ld, int32_t* tickets, fm_stream_t stream);
 /* Backward of fm_attention_bf16 (self-attention, tq == tk == T; q/k/v share the strides qs_*, o/dout share os_*;
  * dq/dk/dv are written with the q strides).  Strides in elements. */
 int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,

@@ -110,3 +110,59 @@ def test_data_parallel_mean_equals_single_process_gradient_of_the_concatenated_b
     for got, p in zip(reduced, net.parameters()):
         want = p.grad if p.grad is not None else torch.zeros_like(p)
         assert torch.allclose(got * 0.5, want, rtol=1e-5, atol=1e-7)
+
+
+def _staged_worker(rank, world, port, bucket_bytes, ret):
+    """The CUDA-graph path's reduction schedule (`FlowMatchingTrainer._step`): backward stage 1 -> all-reduce of the
+    ranges whose gradients are complete -> backward stage 2 (`BackwardCut.finish`) -> all-reduce of the rest."""
+    from fmdm_b200.training.graph import BackwardCut
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = _model()
+    flat = FlatBuffers(net.parameters())
+    red = BucketedAllReduce(flat, bucket_bytes=bucket_bytes)
+    x, y = _data(rank)
+    outs, ranges = [], None
+    for cycle in range(2):
+        flat.grad.zero_()
+        cut = BackwardCut()
+        h = net[1](net[0](x))                              # early part: stage 2 of the backward
+        h2 = cut.cross(h)
+        assert cut.cross(h) is h2                          # one leaf per crossing tensor
+        loss = torch.nn.functional.mse_loss(net[4](net[3](net[2](h2))), y)
+        if ranges is None:
+            red.record(True)
+        loss.backward()                                    # stage 1: stops at the leaf
+        if ranges is None:
+            first = red.ranges_of(red.record(False))
+            ranges = (first, red.complement(first))
+        assert net[0].weight.grad.abs().sum() == 0         # nothing has reached the early layers yet
+        red.launch(ranges[0])
+        cut.finish()
+        red.launch(ranges[1])
+        red.wait()
+        outs.append([p.grad.clone() for p in net.parameters()])
+    ret[rank] = (outs, ranges)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_bytes", [64, 1 << 20])
+def test_two_stage_backward_reduction_equals_plain_sum(bucket_bytes):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_staged_worker, args=(2, _free_port(), bucket_bytes, ret), nprocs=2, join=True)
+    want = [a + b for a, b in zip(_local_grads(0), _local_grads(1))]
+    for rank in (0, 1):
+        outs, (first, rest) = ret[rank]
+        for cyc in outs:
+            for got, ref in zip(cyc, want):
+                assert torch.allclose(got, ref, rtol=1e-6, atol=1e-7)
+        # the two range sets tile the flat buffer exactly once; stage 1 holds the late layers (flat order is reversed)
+        spans = sorted(first + rest)
+        assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        late = 33 * 17 + 17 + 17 * 5 + 5
+        assert sum(e - b for b, e in first) >= late and sum(e - b for b, e in rest) >= 12 * 33 + 33 + 7
+        if bucket_bytes == 64:
+            assert max(e - b for b, e in first) <= 16

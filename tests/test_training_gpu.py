@@ -251,3 +251,71 @@ def test_fused_adamw_matches_torch():
         ref.step()
     for p, r in zip(ps, pr):
         assert torch.allclose(p, r, rtol=2e-6, atol=2e-7), (p - r).abs().max().item()
+
+
+@pytest.mark.parametrize("two_sources", [False, True])
+def test_gradient_slots_fold_residual_and_skip_gradients(F, two_sources):
+    """A ResBlock-shaped graph: x feeds a GroupNorm (first consumer) and, further down, the residual input of a conv
+    (and, with two sources, the 1x1 skip conv of a virtual concat).  With gradient slots the later consumers park their
+    contributions and the GroupNorm backward adds them inside its apply pass; the result must equal torch autograd on
+    the same graph, and equal the unfused path up to one bf16 rounding."""
+    torch.manual_seed(5)
+    dev = "cuda"
+    b, c, hw = 2, 128, 16
+    leaf = nhwc(torch.randn(b, c, hw, hw, device=dev)).requires_grad_(True)
+    leaf2 = nhwc(torch.randn(b, c, hw, hw, device=dev)).requires_grad_(True)
+    gamma = (torch.rand(2 * c if two_sources else c, device=dev) + 0.5).requires_grad_(True)
+    beta = (torch.randn(2 * c if two_sources else c, device=dev) * 0.2).requires_grad_(True)
+    w = (torch.randn(c, 2 * c if two_sources else c, 3, 3, device=dev) * 0.03).requires_grad_(True)
+    ws = (torch.randn(c, 2 * c, device=dev) * 0.05).requires_grad_(True)
+    gy = nhwc(torch.randn(b, c, hw, hw, device=dev))
+
+    def run(fuse):
+        old, F.FUSE_GRAD_ACCUMULATION = F.FUSE_GRAD_ACCUMULATION, fuse
+        try:
+            for t in (leaf, leaf2, gamma, beta, w, ws):
+                t.grad = None
+            x = F.upsample_nearest2x(leaf)          # activations (non-leaf): eligible for slots
+            x2 = F.upsample_nearest2x(leaf2)
+            if two_sources:
+                h = F.group_norm((x, x2), gamma, beta, groups=32, eps=1e-5, silu=True)
+                y = F.conv([h, x, x2], [(w, 0, 2 * c), (ws, 0, c), (ws, c, c)])
+            else:
+                h = F.group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=True)
+                y = F.conv([h], [(w, 0, c)], residual=x)
+            if fuse:
+                assert getattr(x, "_fm_slot").expected == 1
+            y.backward(F.upsample_nearest2x(gy).detach())
+            F.assert_slots_drained()
+            return y.detach().clone(), [t.grad.detach().clone() for t in (leaf, leaf2 if two_sources else leaf, gamma, w)]
+        finally:
+            F.FUSE_GRAD_ACCUMULATION = old
+
+    y1, g1 = run(True)
+    y0, g0 = run(False)
+    assert torch.equal(y1, y0)
+    for a, r in zip(g1, g0):
+        assert rel_l2(a, r) < 4e-3
+    # torch autograd on the same graph (fp32)
+    up = lambda t: TF.interpolate(t.detach().float(), scale_factor=2.0, mode="nearest")
+    l1, l2 = leaf.detach().float().requires_grad_(True), leaf2.detach().float().requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    wr, wsr = w.detach().clone().requires_grad_(True), ws.detach().clone().requires_grad_(True)
+    xr, x2r = TF.interpolate(l1, scale_factor=2.0), TF.interpolate(l2, scale_factor=2.0)
+    if two_sources:
+        cat = torch.cat([xr, x2r], 1)
+        hr = TF.silu(TF.group_norm(cat, 32, gr, br, 1e-5))
+        yr = TF.conv2d(hr, wr, padding=1) + TF.conv2d(cat, wsr[:, :, None, None])
+    else:
+        hr = TF.silu(TF.group_norm(xr, 32, gr, br, 1e-5))
+        yr = TF.conv2d(hr, wr, padding=1) + xr
+    yr.backward(up(gy))
+    assert rel_l2(g1[0], l1.grad) < 1.2e-2 and rel_l2(g1[2], gr.grad) < 1.2e-2 and rel_l2(g1[3], wr.grad) < 1.2e-2
+    if two_sources:
+        assert rel_l2(g1[1], l2.grad) < 1.2e-2
+    # a long-lived leaf consumed by several forward passes never carries a slot (each backward stands alone)
+    for _ in range(2):
+        hh = F.group_norm(leaf, gamma[:c].detach().requires_grad_(True), beta[:c].detach().requires_grad_(True),
+                          groups=32, eps=1e-5, silu=True)
+        assert getattr(leaf, "_fm_slot", None) is None
+        hh.backward(gy)

@@ -352,3 +352,91 @@ def test_diffusion_trainer_epsilon_target():
     losses = [float(tr.step(clean, ldct)) for _ in range(14)]
     assert tr._graph is not None and all(torch.isfinite(torch.tensor(losses)))
     assert sum(losses[-4:]) / 4 < sum(losses[:4]) / 4
+
+
+def _grads_of(cfg, hw, b, *, fuse=True, cut=None, seed=21):
+    """Parameter gradients of one flow-matching loss (seeded weights, inputs, noise, t) under the given switches."""
+    from fmdm_b200.training import flow_matching_loss
+    from fmdm_b200.training import functions as F
+    from fmdm_b200.training.graph import finish_backward
+
+    model, _ = build(cfg, seed=2)
+    clean, ldct, noise, t = batch(b, hw, seed)
+    old = F.FUSE_GRAD_ACCUMULATION
+    F.FUSE_GRAD_ACCUMULATION = fuse
+    try:
+        if cut is not None:
+            model.__dict__["_fm_backward_cut"] = cut
+        loss = flow_matching_loss(model, clean, ldct, noise=noise, t=t)
+        loss.backward()
+        stage1 = {k: (p.grad is not None and bool(p.grad.abs().sum() > 0)) for k, p in model.named_parameters()}
+        had_cut = "_fm_cut_state" in model.__dict__
+        finish_backward(model)
+        F.assert_slots_drained()
+    finally:
+        F.FUSE_GRAD_ACCUMULATION = old
+        model.__dict__.pop("_fm_backward_cut", None)
+    return float(loss), {k: p.grad.detach().clone() for k, p in model.named_parameters()}, stage1, had_cut
+
+
+@pytest.mark.parametrize("name,cfg,hw,b", [("small32", SMALL, 32, 3), ("ldct64", LDCT, 64, 2),
+                                           ("compvis32", COMPVIS, 32, 2), ("compvis_attn32", COMPVIS_ATTN, 32, 2)])
+def test_fused_gradient_accumulation_equals_autograd_accumulation(name, cfg, hw, b):
+    """Gradient slots (`training.functions._Slot`): the gradients of tensors with several consumers are summed inside
+    the GroupNorm-backward / dgrad-conv kernels instead of by autograd's ATen adds.  Same terms, summed in fp32 and
+    rounded once instead of after every add: the parameter gradients agree to bf16 rounding of a few activations."""
+    l0, g0, _, _ = _grads_of(cfg, hw, b, fuse=False)
+    l1, g1, _, _ = _grads_of(cfg, hw, b, fuse=True)
+    assert l0 == l1
+    tot = float(torch.cat([v.reshape(-1) for v in g0.values()]).norm())
+    for k in g0:
+        assert float((g0[k] - g1[k]).norm()) < 4e-3 * tot, (name, k)
+    a = torch.cat([v.reshape(-1) for v in g0.values()])
+    c = torch.cat([v.reshape(-1) for v in g1.values()])
+    assert rel_l2(c, a) < 6e-3, (name, rel_l2(c, a))
+
+
+@pytest.mark.parametrize("name,cfg,hw,b,cut", [("small32", SMALL, 32, 3, 1), ("ldct64", LDCT, 64, 2, 4),
+                                               ("ldct64_cut2", LDCT, 64, 1, 2), ("compvis32", COMPVIS, 32, 2, 7)])
+def test_two_stage_backward_equals_single_backward(name, cfg, hw, b, cut):
+    """`BackwardCut`: `loss.backward()` stops at the boundary (the early layers have no gradient yet, the late ones are
+    complete), `finish_backward` runs the rest; the result equals the uncut backward (the time-embedding projection
+    runs as two GEMM batches instead of one, so its inputs' gradients differ by fp32 summation order only)."""
+    l0, g0, _, had0 = _grads_of(cfg, hw, b, cut=None)
+    l1, g1, stage1, had1 = _grads_of(cfg, hw, b, cut=cut)
+    assert not had0 and had1
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)
+    early = [k for k, done in stage1.items() if not done]
+    late = [k for k, done in stage1.items() if done]
+    assert any(k.startswith(("conv_in", "input_blocks.0")) for k in early)
+    assert any(k.startswith(("time_embedding", "time_embed")) for k in early)
+    assert any(k.startswith(("conv_out", "out.")) for k in late) and len(late) > len(early)
+    tot = float(torch.cat([v.reshape(-1) for v in g0.values()]).norm())
+    for k in g0:
+        assert float((g0[k] - g1[k]).norm()) < 2e-3 * tot, (name, k)
+
+
+def test_trainer_with_backward_cut_replays_two_graphs():
+    """The graph-replayed step with a forced cut (world size 1): two graphs, all-reduce ranges that tile the flat
+    gradient buffer, and the same training trajectory as the single-graph step on the same seeded noise stream."""
+    from fmdm_b200.training import FlowMatchingTrainer
+
+    clean, ldct, _, _ = batch(8, 32, 9)
+    losses = {}
+    for cut in (None, 1):
+        model, _ = build(SMALL, seed=8)
+        tr = FlowMatchingTrainer(model, lr=3e-4, cuda_graph=True, graph_warmup=2, backward_cut=cut)
+        torch.manual_seed(123)
+        losses[cut] = [float(tr.step(clean, ldct)) for _ in range(8)]
+        if cut is None:
+            assert tr._graph2 is None
+        else:
+            assert tr._graph2 is not None
+            first, rest = tr._stage_ranges
+            spans = sorted(first + rest)
+            assert spans[0][0] == 0 and spans[-1][1] == tr.optimizer.flat.numel
+            assert all(x[1] == y[0] for x, y in zip(spans, spans[1:]))
+            assert sum(e - s for s, e in first) > sum(e - s for s, e in rest)   # most gradient bytes are ready early
+    for a, c in zip(losses[None], losses[1]):
+        assert abs(a - c) <= 2e-2 * abs(a), (losses[None], losses[1])
+    assert sum(losses[1][-3:]) < sum(losses[1][:3])

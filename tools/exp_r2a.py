@@ -332,8 +332,8 @@ def exp_attention_micro():
     torch.cuda.synchronize()
     q, k, v = [x.reshape(b, t, heads, hd).transpose(1, 2).float() for x in qkv.split(c, dim=-1)]
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, t, c)
-    print("attention hd8 T=1024 B=16 heads=64: %.4f ms/launch, poly_exp=%s, rel_l2 vs fp32 SDPA %.3e" % (
-        e0.elapsed_time(e1) / 200, os.environ.get("FMDM_ATTENTION_NO_POLY_EXP") is None, rel_l2(out, ref)), flush=True)
+    print("attention hd8 T=1024 B=16 heads=64: %.4f ms/launch, bf16p=%s, rel_l2 vs fp32 SDPA %.3e" % (
+        e0.elapsed_time(e1) / 200, os.environ.get("FMDM_ATTENTION_BF16P") is not None, rel_l2(out, ref)), flush=True)
 
 
 def exp_mnist_steps():
