@@ -89,6 +89,7 @@ class FlowMatchingTrainer:
             backward_cut = self._default_cut(model) if self.reducer.world > 1 else None
         self.backward_cut = backward_cut
         self._stage_ranges = None
+        self.reduce_mode = "single rank" if self.reducer.world == 1 else "after the graph replay"
 
     # ---------------------------------------------------------------------------------------------------------
     @staticmethod
@@ -182,6 +183,9 @@ class FlowMatchingTrainer:
             self._graph2 = graph2
             first = self.reducer.ranges_of(early)
             self._stage_ranges = (first, self.reducer.complement(first))
+            nb = [4 * sum(e - b for b, e in r) for r in self._stage_ranges]
+            self.reduce_mode = (f"two-stage backward: {nb[0]} gradient bytes all-reduced while backward stage 2 runs, "
+                                f"{nb[1]} bytes after it")
         F.assert_slots_drained()
 
     def step(self, clean: torch.Tensor, ldct: Optional[torch.Tensor] = None, *, noise=None, t=None) -> torch.Tensor:
