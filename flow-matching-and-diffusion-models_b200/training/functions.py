@@ -29,8 +29,54 @@ DIRECT_PARAM_GRADS = False
 GRAD_READY_HOOK = None
 
 
+def fused_param(params):
+    """ONE tensor over several parameters that lie back to back in memory, or None.
+
+    The trainers lay the flat parameter buffer out so that parameters which the step uses as one matrix - the
+    `emb_layers` projections of all ResBlocks of a backward stage, the to_q / to_k / to_v weights of an attention block
+    - are adjacent (`training.graph.flat_param_order`).  The concatenation is then a VIEW of the flat buffer (no
+    `torch.cat` per step) and its gradient a view of the flat gradient buffer, which the backward kernels write
+    directly (no per-parameter slice + AccumulateGrad).  Only under DIRECT_PARAM_GRADS (the trainers hold it over the
+    forward AND the backward): the view is detached from autograd, its gradient exists only as that direct write."""
+    if not DIRECT_PARAM_GRADS or not params:
+        return None
+    p0 = params[0]
+    inner = tuple(p0.shape[1:])
+    wp, gp, rows = p0.data_ptr(), None if p0.grad is None else p0.grad.data_ptr(), 0
+    for q in params:
+        g = q.grad
+        if (not isinstance(q, torch.nn.Parameter) or not q.requires_grad or q.dtype != torch.float32
+                or not q.is_contiguous() or tuple(q.shape[1:]) != inner or q.numel() % 4 or g is None
+                or g.dtype != torch.float32 or not g.is_contiguous()
+                or q.data_ptr() != wp or g.data_ptr() != gp):
+            return None
+        wp += 4 * q.numel()
+        gp += 4 * q.numel()
+        rows += q.shape[0]
+    shape = (rows,) + inner
+    strides = []
+    acc = 1
+    for d in reversed(shape):
+        strides.append(acc)
+        acc *= d
+    strides = tuple(reversed(strides))
+    w = torch.as_strided(p0.data, shape, strides)
+    w._fm_grad_view = torch.as_strided(p0.grad, shape, strides)
+    w._fm_params = tuple(params)
+    return w
+
+
+def _is_fused(t) -> bool:
+    return getattr(t, "_fm_grad_view", None) is not None
+
+
 def _grad_target(param, shape=None):
     """The `.grad` view of `param` to write into directly, or None (autograd accumulates the returned gradient)."""
+    if _is_fused(param):
+        if not DIRECT_PARAM_GRADS:
+            raise RuntimeError("fmdm_b200.training: a forward that ran under DIRECT_PARAM_GRADS (fused parameter "
+                               "views) must run its backward under it too")
+        return param._fm_grad_view
     if not DIRECT_PARAM_GRADS or not isinstance(param, torch.nn.Parameter) or not param.requires_grad:
         return None
     g = param.grad
@@ -43,7 +89,8 @@ def _grad_target(param, shape=None):
 
 def _grad_written(param) -> None:
     if GRAD_READY_HOOK is not None:
-        GRAD_READY_HOOK(param)
+        for q in getattr(param, "_fm_params", (param,)):
+            GRAD_READY_HOOK(q)
 
 
 _TICKETS = {}
@@ -288,7 +335,7 @@ class _ConvFn(Function):
                 grads[i] = dx
         dws, direct = {}, set()
         for i, (wi, cb, cc) in enumerate(segs):
-            if not need[1 + nsrc + wi]:
+            if not (need[1 + nsrc + wi] or _is_fused(ctx.params[wi])):
                 continue
             w = weights[wi]
             if wi not in dws:
@@ -307,10 +354,11 @@ class _ConvFn(Function):
                 _grad_written(ctx.params[wi])
             else:
                 grads[nsrc + wi] = dw
-        if (has_bias and need[1 + nsrc + nw]) or (has_addvec and need[1 + nsrc + nw + 1]):
+        need_bias = has_bias and (need[1 + nsrc + nw] or _is_fused(ctx.bias_param))
+        if need_bias or (has_addvec and need[1 + nsrc + nw + 1]):
             tagged = getattr(dy, "_fm_colsum", None)
             part = tagged[0] if tagged is not None and tagged[1] == dy._version else None
-            btarget = _grad_target(ctx.bias_param, (dy.shape[1],)) if has_bias and need[1 + nsrc + nw] else None
+            btarget = _grad_target(ctx.bias_param, (dy.shape[1],)) if need_bias else None
             if part is not None and tuple(part.shape[::2]) == (dy.shape[0], dy.shape[1]):
                 # dy is the dx of a GroupNorm backward that already summed its columns per row block
                 per_sample = torch.empty((dy.shape[0], dy.shape[1]), dtype=torch.float32, device=dy.device)

@@ -85,6 +85,66 @@ def _embedding_blocks(modules):
             and (m.use_scale_shift_norm or m.add_embedding_to_hidden)]
 
 
+def _cut_groups(model, cut_at):
+    """(early, late) module lists of a two-stage backward (`BackwardCut`); without a cut everything is "late"."""
+    if hasattr(model, "down_blocks"):
+        down = list(model.down_blocks)
+        rest = ([model.mid_block] if getattr(model, "mid_block", None) is not None else []) + list(model.up_blocks)
+        if cut_at is None or not 1 <= cut_at < len(down):
+            return [], down + rest
+        return down[:cut_at], down[cut_at:] + rest
+    blocks_in = list(model.input_blocks)
+    rest = [model.middle_block] + list(model.output_blocks)
+    if cut_at is None or not 1 <= cut_at < len(blocks_in):
+        return [], blocks_in + rest
+    return blocks_in[:cut_at], blocks_in[cut_at:] + rest
+
+
+def flat_param_order(model, cut_at=None):
+    """Layout of the trainers' flat parameter / gradient buffers: reverse registration order (gradients complete
+    roughly front to back during the backward), except that parameters the step uses as ONE matrix are made adjacent
+    so that `functions.fused_param` can view them in place: the `emb_layers` weights (then biases) of all ResBlocks of
+    a backward stage in block order - the late stage's at the front of the buffer, the early stage's at the end - and
+    the to_q / to_k / to_v weights (then biases) of every attention block."""
+    from ..nn.blocks.attention import DiffusersAttentionND
+
+    params = [p for p in model.parameters() if p.requires_grad]
+    early, late = _cut_groups(model, cut_at)
+    front, back, taken = [], [], set()
+
+    def emb_group(mods, dest):
+        groups = {}
+        for blk in _embedding_blocks(mods):
+            groups.setdefault(bool(blk.emb_activation_before_proj), []).append(blk)
+        for blks in groups.values():
+            if any(b.emb_layers.bias is None for b in blks):
+                continue
+            for plist in ([b.emb_layers.weight for b in blks], [b.emb_layers.bias for b in blks]):
+                if all(q.requires_grad and id(q) not in taken for q in plist):
+                    dest.extend(plist)
+                    taken.update(id(q) for q in plist)
+
+    emb_group(late, front)
+    emb_group(early, back)
+    trios = {}
+    for m in model.modules():
+        if isinstance(m, DiffusersAttentionND) and getattr(m, "context_dim", None) is None:
+            for plist in ([m.to_q.weight, m.to_k.weight, m.to_v.weight], [m.to_q.bias, m.to_k.bias, m.to_v.bias]):
+                if all(q is not None and q.requires_grad and id(q) not in taken for q in plist):
+                    for q in plist:
+                        trios[id(q)] = plist
+                    taken.update(id(q) for q in plist)
+    middle, emitted = [], set()
+    for q in reversed(params):
+        if id(q) in trios:
+            if id(q) not in emitted:
+                middle.extend(trios[id(q)])
+                emitted.update(id(t) for t in trios[id(q)])
+        elif id(q) not in taken:
+            middle.append(q)
+    return front + middle + back
+
+
 class EmbProjections:
     """Every ResBlock's `emb_layers` projection of the time embedding in ONE launch (`residual.py:99-108` runs one
     Linear per block on the same input): the weights are concatenated per step, the result is split into per-block
@@ -100,6 +160,18 @@ class EmbProjections:
             groups.setdefault(bool(blk.emb_activation_before_proj), []).append(blk)
         for silu_in, blks in groups.items():
             sizes = [(b.emb_layers.weight.shape[0] + 3) // 4 * 4 for b in blks]  # 16-byte aligned column slices
+            # under a trainer the projection weights of a stage are adjacent in the flat parameter buffer
+            # (`flat_param_order`): the concatenation is a view, its gradient a view of the flat gradient
+            wf = bf = None
+            if emb.shape[0] <= 32 and all(n == b.emb_layers.weight.shape[0] for b, n in zip(blks, sizes)) \
+                    and all(b.emb_layers.bias is not None for b in blks):
+                wf = F.fused_param([b.emb_layers.weight for b in blks])
+                bf = F.fused_param([b.emb_layers.bias for b in blks]) if wf is not None else None
+            if wf is not None and bf is not None:
+                e_all = F.linear(emb, wf, bf, silu_in=silu_in)
+                for b, e in zip(blks, F.split_cols(e_all, sizes)):
+                    self.slices[id(b)] = e
+                continue
             ws, bs = [], []
             for b, n in zip(blks, sizes):
                 w, bias = b.emb_layers.weight, b.emb_layers.bias
@@ -167,8 +239,11 @@ def attention(att, x: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("fmdm_b200.training: unsupported attention variant")
     gn = att.group_norm
     n = _gn(gn, x, silu=False)
-    w = torch.cat([att.to_q.weight, att.to_k.weight, att.to_v.weight], 0)
-    bias = torch.cat([att.to_q.bias, att.to_k.bias, att.to_v.bias], 0)
+    w = F.fused_param([att.to_q.weight, att.to_k.weight, att.to_v.weight])
+    bias = F.fused_param([att.to_q.bias, att.to_k.bias, att.to_v.bias]) if w is not None else None
+    if w is None or bias is None:
+        w = torch.cat([att.to_q.weight, att.to_k.weight, att.to_v.weight], 0)
+        bias = torch.cat([att.to_q.bias, att.to_k.bias, att.to_v.bias], 0)
     qkv = F.conv([n], [(w, 0, c)], bias=bias)
     a = F.attention_qkv(qkv, att.heads)
     return F.conv([a], [(att.to_out[0].weight, 0, c)], bias=att.to_out[0].bias, residual=x)
@@ -239,7 +314,8 @@ def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Ten
     if cut_at is not None and not 1 <= cut_at < len(blocks_in):
         cut_at = None
     raw_emb = emb
-    emb = EmbProjections(model, raw_emb, None if cut_at is None else _embedding_blocks(blocks_in[:cut_at]))
+    early_mods, late_mods = _cut_groups(model, cut_at)   # the same grouping `flat_param_order` lays the weights out by
+    emb = EmbProjections(model, raw_emb, _embedding_blocks(late_mods if cut_at is None else early_mods))
     stem = model.input_blocks[0][0].conv
     cin = x.shape[1] + (context.shape[1] if context is not None else 0)
     if cin != stem.in_channels:
@@ -254,8 +330,7 @@ def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Ten
             cut = model.__dict__["_fm_cut_state"] = BackwardCut()
             hs = [cut.cross(t) for t in hs]
             h = hs[-1]
-            emb = EmbProjections(model, cut.cross(raw_emb), _embedding_blocks(
-                blocks_in[cut_at:] + [model.middle_block] + list(model.output_blocks)))
+            emb = EmbProjections(model, cut.cross(raw_emb), _embedding_blocks(late_mods))
         h = _sequential(block, h, emb)
         hs.append(h)
     h = _sequential(model.middle_block, h, emb)
@@ -295,7 +370,8 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
     cut_at = model.__dict__.get("_fm_backward_cut")     # number of down blocks in the second backward stage
     if cut_at is not None and not 1 <= cut_at < len(down):
         cut_at = None
-    emb = EmbProjections(model, raw_emb, None if cut_at is None else _embedding_blocks(down[:cut_at]))
+    early_mods, late_mods = _cut_groups(model, cut_at)   # the same grouping `flat_param_order` lays the weights out by
+    emb = EmbProjections(model, raw_emb, _embedding_blocks(late_mods if cut_at is None else early_mods))
 
     scale, shift = (2.0, -1.0) if model.center_input_sample else (1.0, 0.0)
     cin = x.shape[1] + (context.shape[1] if context is not None else 0)
@@ -312,8 +388,7 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
             cut = model.__dict__["_fm_cut_state"] = BackwardCut()
             skips = [cut.cross(t) for t in skips]
             sample = skips[-1]
-            late = down[cut_at:] + ([model.mid_block] if model.mid_block is not None else []) + list(model.up_blocks)
-            emb = EmbProjections(model, cut.cross(raw_emb), _embedding_blocks(late))
+            emb = EmbProjections(model, cut.cross(raw_emb), _embedding_blocks(late_mods))
         for i, res in enumerate(block.resnets):
             sample = resblock(res, sample, emb)
             if block.attentions is not None:

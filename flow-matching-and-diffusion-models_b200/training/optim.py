@@ -23,7 +23,7 @@ class FlatBuffers:
     The flat order is the REVERSE of the given order: backward produces gradients roughly last-layer-first, so
     buckets of consecutive flat ranges complete in order (see `training.ddp.BucketedAllReduce`)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], order=None):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatBuffers: no trainable parameters")
@@ -31,7 +31,12 @@ class FlatBuffers:
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("FlatBuffers: parameters must be fp32 on one device")
-        order = list(reversed(self.params))
+        if order is None:
+            order = list(reversed(self.params))
+        else:   # a caller-chosen layout (`training.graph.flat_param_order`): must be a permutation of the parameters
+            order = [p for p in order if p.requires_grad]
+            if len(order) != len(self.params) or {id(p) for p in order} != {id(p) for p in self.params}:
+                raise ValueError("FlatBuffers: `order` must list every trainable parameter exactly once")
         self.offsets = {}
         off = 0
         for p in order:
@@ -63,7 +68,8 @@ class FlatBuffers:
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 flat_order=None):
         params = list(params)
         if any(isinstance(p, dict) for p in params):
             raise ValueError("FusedAdamW: a single parameter group (flow_matching_lib.py:74 passes model.parameters())")
@@ -71,7 +77,7 @@ class FusedAdamW(torch.optim.Optimizer):
             raise RuntimeError("fmdm_b200.training.FusedAdamW: parameters must live on a CUDA device (the optimiser is "
                                "one sm_100a kernel; there is no CPU implementation)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self.flat = FlatBuffers(self.param_groups[0]["params"])
+        self.flat = FlatBuffers(self.param_groups[0]["params"], order=flat_order)
         dev = self.flat.data.device
         self.exp_avg = torch.zeros_like(self.flat.data)
         self.exp_avg_sq = torch.zeros_like(self.flat.data)

@@ -22,6 +22,8 @@ BF16 = torch.bfloat16
 
 def _stable_source(w: torch.Tensor) -> bool:
     """fp32 contiguous storage of a Parameter (itself or a view of one): its address survives optimiser steps."""
+    if getattr(w, "_fm_params", None) is not None:      # `functions.fused_param`: a view over adjacent flat-buffer slices
+        return w.dtype == torch.float32 and w.is_contiguous()
     base = w._base if w._base is not None else w
     return (isinstance(base, torch.nn.Parameter) and w.dtype == torch.float32 and w.is_contiguous())
 
@@ -74,8 +76,9 @@ class PackPlan:
         return pw
 
     def _track(self, w: torch.Tensor) -> None:
-        base = w._base if w._base is not None else w
-        self.sources[id(base)] = (weakref.ref(base), base.data_ptr())
+        fused = getattr(w, "_fm_params", None)
+        for base in (fused if fused is not None else (w._base if w._base is not None else w,)):
+            self.sources[id(base)] = (weakref.ref(base), base.data_ptr())
 
     def _sources_moved(self) -> bool:
         for ref, ptr in self.sources.values():

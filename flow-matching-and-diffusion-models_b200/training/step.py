@@ -60,8 +60,20 @@ class FlowMatchingTrainer:
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  grad_accum: int = 1, num_train_timesteps: int = 1000, bucket_bytes: int = 64 << 20, group=None,
                  cuda_graph: bool = True, graph_warmup: int = 2, backward_cut="auto"):
+        import torch.distributed as dist
+
+        from .graph import flat_param_order, supported
+
         self.model = model
-        self.optimizer = FusedAdamW(model.parameters(), lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # two-stage backward (`training.graph.BackwardCut`): "auto" = cut when gradients are all-reduced, so the
+        # reduction of the late layers' gradients overlaps the early layers' backward; an int forces the cut position
+        if backward_cut == "auto":
+            backward_cut = self._default_cut(model) if world > 1 else None
+        self.backward_cut = backward_cut
+        order = flat_param_order(model, backward_cut) if supported(model) else None
+        self.optimizer = FusedAdamW(model.parameters(), lr=lr, weight_decay=weight_decay, betas=betas, eps=eps,
+                                    flat_order=order)
         self.reducer = BucketedAllReduce(self.optimizer.flat, bucket_bytes=bucket_bytes, group=group)
         if self.reducer.world > 1:
             # what torch DDP does at construction: every replica starts from rank 0's parameters and buffers (ranks
@@ -83,11 +95,6 @@ class FlowMatchingTrainer:
         self._graph_key = None
         self._eager_steps = 0
         self._static = None
-        # two-stage backward (`training.graph.BackwardCut`): "auto" = cut when gradients are all-reduced, so the
-        # reduction of the late layers' gradients overlaps the early layers' backward; an int forces the cut position
-        if backward_cut == "auto":
-            backward_cut = self._default_cut(model) if self.reducer.world > 1 else None
-        self.backward_cut = backward_cut
         self._stage_ranges = None
         self.reduce_mode = "single rank" if self.reducer.world == 1 else "after the graph replay"
 
@@ -147,7 +154,8 @@ class FlowMatchingTrainer:
         for i, (c, l, n, tt) in enumerate(zip(cc, lc, nc, tc)):
             if i == len(cc) - 1:
                 self.reducer.arm()
-            loss = self._loss(c, l, n, tt)
+            with self._direct_grads():      # held over the forward too: `functions.fused_param` views
+                loss = self._loss(c, l, n, tt)
             self._backward(loss / self.grad_accum)
             w = loss.detach() * (c.size(0) / bs)
             total = w if total is None else total + w
@@ -169,8 +177,8 @@ class FlowMatchingTrainer:
         self.reducer.record(True)
         with torch.cuda.graph(graph):
             self.optimizer.zero_grad()
-            loss = self._loss(sc, sl, None, None)
             with self._direct_grads():
+                loss = self._loss(sc, sl, None, None)
                 loss.backward()
             self._static_loss = loss.detach()
         early = self.reducer.record(False)

@@ -66,3 +66,55 @@ def test_fused_adamw_refuses_cpu_parameters():
     assert [p.data_ptr() for p in net.parameters()] == before         # parameters were not re-seated
     with pytest.raises(ValueError):
         FusedAdamW([{"params": list(net.parameters())}])
+
+
+def test_flat_param_order_makes_fused_views_possible():
+    """`flat_param_order` puts the per-stage `emb_layers` weights and each attention block's q/k/v weights back to back
+    in the flat buffers; `fused_param` then views them (and their gradients) as one matrix, and refuses anything that
+    is not adjacent, not direct-gradient mode, or not a parameter."""
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+    from fmdm_b200.nn.blocks.attention import DiffusersAttentionND
+    from fmdm_b200.training import functions as F
+    from fmdm_b200.training.graph import _cut_groups, _embedding_blocks, flat_param_order
+    from fmdm_b200.training.optim import FlatBuffers
+
+    cfg = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layers_per_block": 1,
+           "block_out_channels": [32, 64, 64], "down_block_types": ["DownBlock2D", "AttnDownBlock2D", "DownBlock2D"],
+           "up_block_types": ["UpBlock2D", "AttnUpBlock2D", "UpBlock2D"]}
+    for cut in (None, 1):
+        torch.manual_seed(0)
+        model = DiffusionUNetFactory().build(cfg, "concatenate", 1)
+        before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        order = flat_param_order(model, cut)
+        assert len(order) == len(list(model.parameters())) and len({id(p) for p in order}) == len(order)
+        flat = FlatBuffers(model.parameters(), order=order)
+        assert all(torch.equal(v, before[k]) for k, v in model.state_dict().items())      # re-seating keeps the values
+        early, late = _cut_groups(model, cut)
+        old = F.DIRECT_PARAM_GRADS
+        try:
+            F.DIRECT_PARAM_GRADS = False
+            assert F.fused_param([b.emb_layers.weight for b in _embedding_blocks(late)]) is None
+            F.DIRECT_PARAM_GRADS = True
+            for mods in (early, late):
+                blks = _embedding_blocks(mods)
+                if not blks:
+                    continue
+                for plist in ([b.emb_layers.weight for b in blks], [b.emb_layers.bias for b in blks]):
+                    w = F.fused_param(plist)
+                    assert w is not None and w.shape[0] == sum(p.shape[0] for p in plist)
+                    assert torch.equal(w, torch.cat([p.detach() for p in plist], 0))
+                    w._fm_grad_view.fill_(3.0)
+                    assert all(bool((p.grad == 3.0).all()) for p in plist)
+                    assert w._fm_params == tuple(plist)
+            att = next(m for m in model.modules() if isinstance(m, DiffusersAttentionND))
+            qkv = F.fused_param([att.to_q.weight, att.to_k.weight, att.to_v.weight])
+            assert qkv is not None and torch.equal(qkv[att.to_q.weight.shape[0]:2 * att.to_q.weight.shape[0]],
+                                                   att.to_k.weight.detach())
+            assert F.fused_param([att.to_k.weight, att.to_q.weight]) is None          # not adjacent in this order
+            assert F.fused_param([att.to_q.weight.detach()]) is None                  # not a parameter
+            if cut is not None:    # early and late stages are separate runs of the buffer
+                assert F.fused_param([b.emb_layers.weight for b in _embedding_blocks(early + late)]) is None
+        finally:
+            F.DIRECT_PARAM_GRADS = old
+        with pytest.raises(ValueError):
+            FlatBuffers(model.parameters(), order=order[:-1])
