@@ -1391,7 +1391,8 @@ extern "C" int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H
 }
 
 static int gn_bwd_blocks(int64_t HW, int B) {
-  int nblk = (int)((8LL * sm_count() + B - 1) / B);  // ~8 CTAs per SM across the batch
+  static const int per_sm = getenv("FMDM_GN_BWD_CTAS_PER_SM") ? atoi(getenv("FMDM_GN_BWD_CTAS_PER_SM")) : 8;
+  int nblk = (int)(((int64_t)per_sm * sm_count() + B - 1) / B);  // CTAs per SM across the batch (A/B: env)
   if (nblk > HW / 16) nblk = (int)(HW / 16);
   if (nblk < 1) nblk = 1;
   return nblk;

@@ -270,6 +270,28 @@ def stem_pack(weight_oihw: torch.Tensor) -> PackedConvWeight:
     return pack_conv_weight([(w2, 0, kp)])
 
 
+def stem_im2col(x0, x1, *, in_scale=1.0, in_shift=0.0, kp: Optional[int] = None) -> torch.Tensor:
+    """The 3x3 neighbourhoods of fp32 NCHW (x0 [, x1]) as a bf16 NHWC tensor [B][Kp][H][W] (logical NCHW), column
+    ci*9 + kh*3 + kw = scale * x[ci][y+kh-1][x+kw-1] + shift, zero beyond 9*Cin (`fm_stem_im2col_bf16`)."""
+    require_cuda(x0, "stem_im2col")
+    x0 = x0.to(torch.float32).contiguous()
+    b, c0, h, w = x0.shape
+    c1 = 0
+    if x1 is not None:
+        x1 = x1.to(torch.float32).contiguous()
+        c1 = x1.shape[1]
+    if kp is None:
+        kp = (9 * (c0 + c1) + 7) // 8 * 8
+    if kp > 72:
+        raise RuntimeError(f"fmdm_b200.stem_im2col: {c0 + c1} input channels (at most 8)")
+    cols = empty_nhwc(b, kp, h, w, x0.device)
+    e0 = _prof_begin()
+    _lib.check(_lib.lib().fm_stem_im2col_bf16(x0.data_ptr(), c0, _ptr(x1), c1, float(in_scale), float(in_shift),
+                                              cols.data_ptr(), b, h, w, kp, _stream()), "stem_im2col")
+    _prof_end("conv_stem_im2col", 2.0 * b * h * w * kp, e0)
+    return cols
+
+
 def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0, want_stats: bool = True,
               packed: Optional[PackedConvWeight] = None) -> torch.Tensor:
     """fp32 NCHW (x0 [, x1]) -> bf16 NHWC, 3x3 s1 p1; fuses the conditioning concat and the 2x-1 centering.

@@ -93,6 +93,12 @@ def _grad_written(param) -> None:
             GRAD_READY_HOOK(q)
 
 
+# The Cin <= 8 stem's weight gradient and the Cout = 1 head's data / weight gradients as tensor-core GEMMs over an im2col
+# matrix (the forward stem's own trick).  FMDM_TRAIN_SMALL_CUDA=1 selects the first-generation CUDA-core kernels (A/B).
+import os as _os
+
+SMALL_CONVS_ON_TENSOR_CORES = _os.environ.get("FMDM_TRAIN_SMALL_CUDA") is None
+
 _TICKETS = {}
 
 
@@ -746,13 +752,21 @@ class _StemFn(Function):
         b, c0, h, w = x0.shape
         c1 = x1.shape[1] if x1 is not None else 0
         cout = wshape[0]
-        ws = _ws(lib.fm_conv_stem_wgrad_workspace_elems(c0 + c1, cout), dy.device)
         wp, bp = ctx.wb
         tw = _grad_target(wp, wshape)
         tb = _grad_target(bp, (cout,)) if has_bias else None
         dw = tw if tw is not None else torch.empty(wshape, dtype=torch.float32, device=dy.device)
-        _lib.check(lib.fm_conv_stem_wgrad_f32(x0.data_ptr(), c0, _ptr(x1), c1, in_scale, in_shift, dy.data_ptr(),
-                                              ws.data_ptr(), dw.data_ptr(), b, h, w, cout, _stream()), "stem_wgrad")
+        if SMALL_CONVS_ON_TENSOR_CORES and 9 * (c0 + c1) <= 72:
+            # dW[co][ci*9 + tap] = sum_p dY[p][co] * im2col(x)[p][ci*9 + tap]: the 1x1 weight-gradient GEMM over the
+            # stem's im2col matrix (tcgen05), instead of a CUDA-core kernel that re-reads x through shared memory
+            cols = ops.stem_im2col(x0, x1, in_scale=in_scale, in_shift=in_shift)
+            dw2 = torch.empty((cout, cols.shape[1]), dtype=torch.float32, device=dy.device)
+            conv_wgrad(dy, cols, dw2, ksize=1, stride=1, c_begin=0)
+            dw.view(cout, -1).copy_(dw2[:, :9 * (c0 + c1)])
+        else:
+            ws = _ws(lib.fm_conv_stem_wgrad_workspace_elems(c0 + c1, cout), dy.device)
+            _lib.check(lib.fm_conv_stem_wgrad_f32(x0.data_ptr(), c0, _ptr(x1), c1, in_scale, in_shift, dy.data_ptr(),
+                                                  ws.data_ptr(), dw.data_ptr(), b, h, w, cout, _stream()), "stem_wgrad")
         db = colsum(dy, True, total=tb)[1] if has_bias else None
         if tw is not None:
             _grad_written(wp)
@@ -792,13 +806,29 @@ class _HeadFn(Function):
         a, w32 = ctx.saved_tensors
         dy = dy.float().contiguous()
         b, cin, h, w = a.shape
-        ws = _ws(lib.fm_conv_head_bwd_workspace_elems(cin), a.device)
-        da = ops.empty_nhwc(b, cin, h, w, a.device) if ctx.needs_input_grad[0] else None
         wp, bp = ctx.wb
         tw = _grad_target(wp, w32.shape)
         dw = tw if tw is not None else torch.empty_like(w32)
-        _lib.check(lib.fm_conv_head_bwd_f32(a.data_ptr(), dy.data_ptr(), w32.data_ptr(), ws.data_ptr(), _ptr(da),
-                                            dw.data_ptr(), b, h, w, cin, _stream()), "head_bwd")
+        want_da = ctx.needs_input_grad[0]
+        if SMALL_CONVS_ON_TENSOR_CORES:
+            # both gradients are GEMMs over the 3x3 neighbourhoods of dY (one im2col, [p][16] bf16, column k = the tap):
+            #   dA[p][c]  = sum_k cols[p][k] * w[c][8 - k]            -> the 1x1 implicit GEMM (forward conv kernel)
+            #   dW[c][k]  = sum_q a[q][c] * cols[q][8 - k]            -> the 1x1 weight-gradient GEMM, columns flipped
+            cols = ops.stem_im2col(dy, None)
+            kp = cols.shape[1]
+            da = None
+            if want_da:
+                wd = torch.zeros((cin, kp), dtype=torch.float32, device=a.device)
+                wd[:, :9] = w32.reshape(cin, 9).flip(1)
+                da = ops.conv2d([cols], ops.pack_conv_weight([(wd, 0, kp)]))
+            dw2 = torch.empty((cin, kp), dtype=torch.float32, device=a.device)
+            conv_wgrad(a, cols, dw2, ksize=1, stride=1, c_begin=0)
+            dw.view(cin, 9).copy_(dw2[:, :9].flip(1))
+        else:
+            ws = _ws(lib.fm_conv_head_bwd_workspace_elems(cin), a.device)
+            da = ops.empty_nhwc(b, cin, h, w, a.device) if want_da else None
+            _lib.check(lib.fm_conv_head_bwd_f32(a.data_ptr(), dy.data_ptr(), w32.data_ptr(), ws.data_ptr(), _ptr(da),
+                                                dw.data_ptr(), b, h, w, cin, _stream()), "head_bwd")
         db = sum_f32(dy) if ctx.has_bias else None
         if tw is not None:
             _grad_written(wp)

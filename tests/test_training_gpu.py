@@ -194,7 +194,12 @@ def test_stem_and_head_backward(F):
     wr, br = w.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
     yr = TF.conv2d(2 * torch.cat([x0, x1], 1) - 1, wr, br, padding=1)
     yr.backward(gy.float())
-    assert rel_l2(y, yr) < 1e-2 and rel_l2(w.grad, wr.grad) < 1e-3 and rel_l2(bias.grad, br.grad) < 1e-3
+    # the weight gradient is the tensor-core GEMM dY^T x im2col(x) with x rounded to bf16, as the conv inputs are under
+    # bf16 autocast (measured 1.6e-3); against the bf16-rounded input it is tight
+    assert rel_l2(y, yr) < 1e-2 and rel_l2(w.grad, wr.grad) < 4e-3 and rel_l2(bias.grad, br.grad) < 1e-3
+    wq = w.detach().clone().requires_grad_(True)
+    TF.conv2d((2 * torch.cat([x0, x1], 1) - 1).to(torch.bfloat16).float(), wq, None, padding=1).backward(gy.float())
+    assert rel_l2(w.grad, wq.grad) < 2e-4
     # head: bf16 NHWC -> fp32 NCHW, one output channel
     a = nhwc(torch.randn(b, 128, hw, hw, device=dev)).requires_grad_(True)
     wh = (torch.randn(1, 128, 3, 3, device=dev) * 0.1).requires_grad_(True)
@@ -207,7 +212,11 @@ def test_stem_and_head_backward(F):
     yr = TF.conv2d(ar, whr, bhr, padding=1)
     yr.backward(g)
     assert rel_l2(y, yr) < 1e-2
-    assert rel_l2(a.grad, ar.grad) < 1e-2 and rel_l2(wh.grad, whr.grad) < 1e-3 and rel_l2(bh.grad, bhr.grad) < 1e-4
+    # dY enters both gradient GEMMs rounded to bf16 (measured: weight gradient 1.6e-3)
+    assert rel_l2(a.grad, ar.grad) < 1e-2 and rel_l2(wh.grad, whr.grad) < 4e-3 and rel_l2(bh.grad, bhr.grad) < 1e-4
+    whq = wh.detach().clone().requires_grad_(True)
+    TF.conv2d(a.detach().float(), whq, None, padding=1).backward(g.to(torch.bfloat16).float())
+    assert rel_l2(wh.grad, whq.grad) < 2e-4
 
 
 def test_upsample_backward_and_mse(F):
