@@ -131,20 +131,6 @@ constexpr int kAtt8Threads = kAtt8Warps * 32;
 constexpr int kAtt8KeyChunk = 1024;            // keys staged per pass
 constexpr int kAtt8VtStride = kAtt8KeyChunk + 8;  // +8 bf16 (16 B) padding: conflict-free transposed reads
 
-// 2^x on the special-function unit without exp2f()'s range fix-ups (inputs are <= 0 after the running-max shift; -inf -> 0)
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ void mma_m16n8k8_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(b0));
-}
-
 __device__ __forceinline__ void mma_m16n8k16_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                  uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -304,14 +290,6 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
 constexpr int kAttMWarps = 8;
 constexpr int kAttMThreads = kAttMWarps * 32;
 constexpr int kAttMKeyChunk = 128;  // keys staged per pass
-
-__device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                                  uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 
 template <int HD>
 __global__ void __launch_bounds__(kAttMThreads) attention_mma_kernel(

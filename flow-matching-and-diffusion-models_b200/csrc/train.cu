@@ -788,6 +788,203 @@ __device__ __forceinline__ void att_stage8(__nv_bfloat16* dst, const __nv_bfloat
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
 }
 
+// ---- head_dim 8 on the tensor cores (mma.sync; K = 8 is half a tcgen05 K step, as in the forward kernel) ----------
+// One CTA per (sample, head), 8 warps.  Q, K, V, dO are staged once as bf16 rows (operands of the S / dP products) and
+// K, Q, dO also transposed (operands of the dQ / dK / dV products).
+//   phase A, warp = 16 query rows: online (max, sum) of S = Q K^T over all keys and delta = rowsum(dO * O); then, per 16
+//            keys, P = 2^(S c - lse), dP = dO V^T, dS = P (dP - delta) scale, dQ += dS K.  lse / delta are parked in
+//            shared memory for phase B.
+//   phase B, warp = 16 key rows: per 16 queries, S^T = K Q^T, P^T, dP^T = V dO^T, dS^T; dV += P^T dO, dK += dS^T Q.
+// The fragments of S / S^T are re-used in place as the A operands of the second products (same lane layout), so no
+// tile passes through shared memory; every sum has a fixed order (no atomics).
+constexpr int kAttB8Pad = 8;
+__global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+    const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dq,
+    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int heads, int T, int Tp, int64_t qs_b,
+    int64_t qs_h, int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);  // [Tp][8]
+  __nv_bfloat16* sK = sQ + (size_t)Tp * 8;
+  __nv_bfloat16* sV = sK + (size_t)Tp * 8;
+  __nv_bfloat16* sD = sV + (size_t)Tp * 8;                          // dO
+  const int ts = Tp + kAttB8Pad;                                    // transposed row stride
+  __nv_bfloat16* sKt = sD + (size_t)Tp * 8;                         // [8][ts]
+  __nv_bfloat16* sQt = sKt + (size_t)8 * ts;
+  __nv_bfloat16* sDt = sQt + (size_t)8 * ts;
+  float* s_lse = reinterpret_cast<float*>(sDt + (size_t)8 * ts);    // [Tp]
+  float* s_del = s_lse + Tp;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t qoff = b * qs_b + h * qs_h, ooff = b * os_b + h * os_h;
+  const float c = scale * 1.4426950408889634f;
+
+  for (int r = threadIdx.x; r < Tp; r += blockDim.x) {
+    uint4 vq = make_uint4(0, 0, 0, 0), vk = vq, vv = vq, vd = vq;
+    if (r < T) {
+      vq = *reinterpret_cast<const uint4*>(q + qoff + (int64_t)r * qs_t);
+      vk = *reinterpret_cast<const uint4*>(k + qoff + (int64_t)r * qs_t);
+      vv = *reinterpret_cast<const uint4*>(v + qoff + (int64_t)r * qs_t);
+      vd = *reinterpret_cast<const uint4*>(dout + ooff + (int64_t)r * os_t);
+    }
+    *reinterpret_cast<uint4*>(sQ + r * 8) = vq;
+    *reinterpret_cast<uint4*>(sK + r * 8) = vk;
+    *reinterpret_cast<uint4*>(sV + r * 8) = vv;
+    *reinterpret_cast<uint4*>(sD + r * 8) = vd;
+    const __nv_bfloat16* eq = reinterpret_cast<const __nv_bfloat16*>(&vq);
+    const __nv_bfloat16* ek = reinterpret_cast<const __nv_bfloat16*>(&vk);
+    const __nv_bfloat16* ed = reinterpret_cast<const __nv_bfloat16*>(&vd);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      sQt[d * ts + r] = eq[d];
+      sKt[d * ts + r] = ek[d];
+      sDt[d * ts + r] = ed[d];
+    }
+  }
+  __syncthreads();
+
+  // ================= phase A: dQ, lse, delta =================
+  for (int q0 = warp * 16; q0 < Tp; q0 += 8 * 16) {
+    const uint32_t qa0 = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g) * 8 + 2 * t);
+    const uint32_t qa1 = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g + 8) * 8 + 2 * t);
+    const uint32_t da0 = *reinterpret_cast<const uint32_t*>(sD + (q0 + g) * 8 + 2 * t);
+    const uint32_t da1 = *reinterpret_cast<const uint32_t*>(sD + (q0 + g + 8) * 8 + 2 * t);
+    // delta = sum_d dO * O (O from global memory: it is read exactly once)
+    float del0 = 0.f, del1 = 0.f;
+    {
+      const int r0 = q0 + g, r1 = q0 + g + 8;
+      const float2 d0 = bf16x2_as_f32x2(da0), d1 = bf16x2_as_f32x2(da1);
+      if (r0 < T) {
+        const float2 o0 = bf16x2_as_f32x2(*reinterpret_cast<const uint32_t*>(o + ooff + (int64_t)r0 * os_t + 2 * t));
+        del0 = fmaf(d0.x, o0.x, d0.y * o0.y);
+      }
+      if (r1 < T) {
+        const float2 o1 = bf16x2_as_f32x2(*reinterpret_cast<const uint32_t*>(o + ooff + (int64_t)r1 * os_t + 2 * t));
+        del1 = fmaf(d1.x, o1.x, d1.y * o1.y);
+      }
+      del0 += __shfl_xor_sync(0xffffffffu, del0, 1);
+      del0 += __shfl_xor_sync(0xffffffffu, del0, 2);
+      del1 += __shfl_xor_sync(0xffffffffu, del1, 1);
+      del1 += __shfl_xor_sync(0xffffffffu, del1, 2);
+    }
+    // pass 1: online row max / sum (log2 domain), 64 keys at a time
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int kb0 = 0; kb0 < Tp; kb0 += 64) {
+      float sc[8][4];
+      const int nblk = (Tp - kb0) >= 64 ? 8 : (Tp - kb0) / 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY;
+        if (j < nblk) {
+          sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+          mma_m16n8k8_bf16(sc[j], qa0, qa1, *reinterpret_cast<const uint32_t*>(sK + (kb0 + j * 8 + g) * 8 + 2 * t));
+          const int key = kb0 + j * 8 + 2 * t;
+          if (key >= T) sc[j][0] = sc[j][2] = -INFINITY;
+          if (key + 1 >= T) sc[j][1] = sc[j][3] = -INFINITY;
+        }
+      }
+      float mx0 = sc[0][0], mx1 = sc[0][2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0 * c), mn1 = fmaxf(m1, mx1 * c);
+      l0 *= ex2_approx(m0 - mn0);
+      l1 *= ex2_approx(m1 - mn1);
+      m0 = mn0, m1 = mn1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        l0 += ex2_approx(fmaf(sc[j][0], c, -mn0)) + ex2_approx(fmaf(sc[j][1], c, -mn0));
+        l1 += ex2_approx(fmaf(sc[j][2], c, -mn1)) + ex2_approx(fmaf(sc[j][3], c, -mn1));
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float lse0 = m0 + __log2f(l0), lse1 = m1 + __log2f(l1);
+    if (t == 0) {  // rows past T: +inf, so phase B's 2^(s c - lse) is exactly 0 for them
+      s_lse[q0 + g] = (q0 + g < T) ? lse0 : INFINITY;
+      s_lse[q0 + g + 8] = (q0 + g + 8 < T) ? lse1 : INFINITY;
+      s_del[q0 + g] = del0;
+      s_del[q0 + g + 8] = del1;
+    }
+    // pass 2: dQ
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kb = 0; kb < Tp; kb += 16) {
+      uint32_t af[4];
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        const int kk = kb + hb * 8;
+        float sv[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_m16n8k8_bf16(sv, qa0, qa1, *reinterpret_cast<const uint32_t*>(sK + (kk + g) * 8 + 2 * t));
+        mma_m16n8k8_bf16(dp, da0, da1, *reinterpret_cast<const uint32_t*>(sV + (kk + g) * 8 + 2 * t));
+        const int key = kk + 2 * t;
+        const float p0 = key < T ? ex2_approx(fmaf(sv[0], c, -lse0)) : 0.f;
+        const float p1 = key + 1 < T ? ex2_approx(fmaf(sv[1], c, -lse0)) : 0.f;
+        const float p2 = key < T ? ex2_approx(fmaf(sv[2], c, -lse1)) : 0.f;
+        const float p3 = key + 1 < T ? ex2_approx(fmaf(sv[3], c, -lse1)) : 0.f;
+        af[hb * 2 + 0] = pack_bf16x2(p0 * (dp[0] - del0) * scale, p1 * (dp[1] - del0) * scale);
+        af[hb * 2 + 1] = pack_bf16x2(p2 * (dp[2] - del1) * scale, p3 * (dp[3] - del1) * scale);
+      }
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sKt + g * ts + kb + 2 * t);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sKt + g * ts + kb + 8 + 2 * t);
+      mma_m16n8k16_bf16(acc, af[0], af[1], af[2], af[3], b0, b1);
+    }
+    if (q0 + g < T)
+      *reinterpret_cast<uint32_t*>(dq + qoff + (int64_t)(q0 + g) * qs_t + 2 * t) = pack_bf16x2(acc[0], acc[1]);
+    if (q0 + g + 8 < T)
+      *reinterpret_cast<uint32_t*>(dq + qoff + (int64_t)(q0 + g + 8) * qs_t + 2 * t) = pack_bf16x2(acc[2], acc[3]);
+  }
+  __syncthreads();
+
+  // ================= phase B: dK, dV =================
+  for (int k0 = warp * 16; k0 < Tp; k0 += 8 * 16) {
+    const uint32_t ka0 = *reinterpret_cast<const uint32_t*>(sK + (k0 + g) * 8 + 2 * t);
+    const uint32_t ka1 = *reinterpret_cast<const uint32_t*>(sK + (k0 + g + 8) * 8 + 2 * t);
+    const uint32_t va0 = *reinterpret_cast<const uint32_t*>(sV + (k0 + g) * 8 + 2 * t);
+    const uint32_t va1 = *reinterpret_cast<const uint32_t*>(sV + (k0 + g + 8) * 8 + 2 * t);
+    float ak[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int qb = 0; qb < Tp; qb += 16) {
+      uint32_t pf[4], sf[4];
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        const int qq = qb + hb * 8;
+        float st[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_m16n8k8_bf16(st, ka0, ka1, *reinterpret_cast<const uint32_t*>(sQ + (qq + g) * 8 + 2 * t));
+        mma_m16n8k8_bf16(dp, va0, va1, *reinterpret_cast<const uint32_t*>(sD + (qq + g) * 8 + 2 * t));
+        const float2 ls = *reinterpret_cast<const float2*>(s_lse + qq + 2 * t);   // columns = queries qq+2t, qq+2t+1
+        const float2 dl = *reinterpret_cast<const float2*>(s_del + qq + 2 * t);
+        const float p0 = ex2_approx(fmaf(st[0], c, -ls.x)), p1 = ex2_approx(fmaf(st[1], c, -ls.y));
+        const float p2 = ex2_approx(fmaf(st[2], c, -ls.x)), p3 = ex2_approx(fmaf(st[3], c, -ls.y));
+        pf[hb * 2 + 0] = pack_bf16x2(p0, p1);
+        pf[hb * 2 + 1] = pack_bf16x2(p2, p3);
+        sf[hb * 2 + 0] = pack_bf16x2(p0 * (dp[0] - dl.x) * scale, p1 * (dp[1] - dl.y) * scale);
+        sf[hb * 2 + 1] = pack_bf16x2(p2 * (dp[2] - dl.x) * scale, p3 * (dp[3] - dl.y) * scale);
+      }
+      const uint32_t d0 = *reinterpret_cast<const uint32_t*>(sDt + g * ts + qb + 2 * t);
+      const uint32_t d1 = *reinterpret_cast<const uint32_t*>(sDt + g * ts + qb + 8 + 2 * t);
+      mma_m16n8k16_bf16(av, pf[0], pf[1], pf[2], pf[3], d0, d1);
+      const uint32_t q0b = *reinterpret_cast<const uint32_t*>(sQt + g * ts + qb + 2 * t);
+      const uint32_t q1b = *reinterpret_cast<const uint32_t*>(sQt + g * ts + qb + 8 + 2 * t);
+      mma_m16n8k16_bf16(ak, sf[0], sf[1], sf[2], sf[3], q0b, q1b);
+    }
+    if (k0 + g < T) {
+      *reinterpret_cast<uint32_t*>(dk + qoff + (int64_t)(k0 + g) * qs_t + 2 * t) = pack_bf16x2(ak[0], ak[1]);
+      *reinterpret_cast<uint32_t*>(dv + qoff + (int64_t)(k0 + g) * qs_t + 2 * t) = pack_bf16x2(av[0], av[1]);
+    }
+    if (k0 + g + 8 < T) {
+      *reinterpret_cast<uint32_t*>(dk + qoff + (int64_t)(k0 + g + 8) * qs_t + 2 * t) = pack_bf16x2(ak[2], ak[3]);
+      *reinterpret_cast<uint32_t*>(dv + qoff + (int64_t)(k0 + g + 8) * qs_t + 2 * t) = pack_bf16x2(av[2], av[3]);
+    }
+  }
+}
+
 template <int HD, typename ST>
 __global__ void __launch_bounds__(256) attention_bwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
@@ -1479,6 +1676,27 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
                  (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq |
                    (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
              "attention_bwd: rows must be 16-byte aligned (strides multiples of 8 elements)");
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool scalar8 = getenv("FMDM_ATTENTION_BWD_SCALAR") != nullptr;  // A/B: the CUDA-core kernel at head_dim 8
+  if (head_dim == 8 && !scalar8) {
+    const int Tp = (T + 15) & ~15;
+    const size_t need = (size_t)Tp * 8 * 2 * 4 + (size_t)3 * 8 * (Tp + kAttB8Pad) * 2 + (size_t)2 * Tp * 4;
+    if (need <= 200 * 1024) {
+      static size_t attr8 = 48 * 1024;
+      if (need > attr8) {
+        if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_hd8_mma_kernel,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need),
+                               "attention_bwd_hd8 attr")) return e;
+        attr8 = need;
+      }
+      attention_bwd_hd8_mma_kernel<<<B * heads, 256, need, st>>>(
+          (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,
+          (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, T, Tp, qs_b,
+          qs_h, qs_t, os_b, os_h, os_t, scale);
+      FM_LAUNCH_CHECK("attention_bwd_hd8_mma_kernel");
+      return 0;
+    }
+  }
   // fp32 staging (no unpacking in the T^2 loops) when the four tiles fit in 96 KB, else bf16 staging
   const size_t tiles = (size_t)4 * T * head_dim;
   const bool f32 = tiles * 4 + (size_t)2 * T * 4 <= 96 * 1024;
@@ -1487,7 +1705,6 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
     set_error("attention_bwd: T=%d head_dim=%d exceeds the shared-memory staging budget", T, head_dim);
     return FM_ERR_UNSUPPORTED;
   }
-  cudaStream_t st = (cudaStream_t)stream;
 #define FM_ATT_BWD_ST(HD, ST)                                                                                       \
   {                                                                                                                 \
     static size_t attr_smem = 0;                                                                                    \

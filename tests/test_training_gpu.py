@@ -145,7 +145,8 @@ def test_group_norm_backward_two_sources(F):
         assert rel_l2(got, ref) < 1e-2
 
 
-@pytest.mark.parametrize("c,heads,hw,b", [(512, 64, 16, 2), (512, 64, 8, 3), (128, 8, 16, 2), (256, 4, 8, 2)])
+@pytest.mark.parametrize("c,heads,hw,b", [(512, 64, 16, 2), (512, 64, 8, 3), (128, 8, 16, 2), (256, 4, 8, 2), (64, 8, 5, 2),
+                                          (64, 8, 32, 1)])
 def test_attention_backward(F, c, heads, hw, b):
     torch.manual_seed(3)
     dev = "cuda"
