@@ -590,8 +590,15 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_partial_kernel(const uint4* __r
     for (int item = threadIdx.x; item < ng * n4; item += blockDim.x) {
       const int grp = item / n4, col = item - grp * n4;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int k = grp; k < nblk; k += ng) {
+      int k = grp;
+      for (; k + 7 * ng < nblk; k += 8 * ng) {  // eight independent L2 loads in flight, added in row order
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src0 + (int64_t)(k + u * ng) * n4 + col);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc.x += v[u].x, acc.y += v[u].y, acc.z += v[u].z, acc.w += v[u].w;
+      }
+      for (; k < nblk; k += ng) {
         const float4 v = __ldcg(src0 + (int64_t)k * n4 + col);
         acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
       }
@@ -650,7 +657,15 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_partial_kernel(const uint4* __r
   __threadfence();
   for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
     float acc = 0.f;
-    for (int s = 0; s < tl.B; ++s) acc += __ldcg(tl.dgb_part + (int64_t)s * 2 * C + idx);
+    int s = 0;
+    for (; s + 8 <= tl.B; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(tl.dgb_part + (int64_t)(s + u) * 2 * C + idx);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; s < tl.B; ++s) acc += __ldcg(tl.dgb_part + (int64_t)s * 2 * C + idx);
     if (tl.dbeta != nullptr && idx >= C) tl.dbeta[idx - C] = acc;
     else tl.dgamma[idx] = acc;
   }

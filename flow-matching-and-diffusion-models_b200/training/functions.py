@@ -7,6 +7,7 @@ Activations are bf16 channels_last, parameters fp32 (bf16-autocast semantics: fp
 inputs, fp32 accumulation; `flow_matching_lib.py:158-164`)."""
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Optional, Sequence
 
@@ -100,16 +101,66 @@ import os as _os
 SMALL_CONVS_ON_TENSOR_CORES = _os.environ.get("FMDM_TRAIN_SMALL_CUDA") is None
 
 _TICKETS = {}
+_IN_SIDE = False
 
 
 def _tickets(device) -> torch.Tensor:
-    """The per-device ticket buffer of the "last block finishes the job" kernels (`fm_ticket_ints`): allocated and
-    zeroed once (outside any CUDA-graph capture the first eager step reaches it), left zero by every kernel."""
-    key = (device.type, device.index)
+    """The per-device (and per-stream: main / side) ticket buffer of the "last block finishes the job" kernels
+    (`fm_ticket_ints`): zeroed once, left zero by every kernel, used by one stream at a time.  The trainers create
+    both up front (`ensure_tickets`) so that none is first allocated inside a CUDA-graph capture."""
+    key = (device.type, device.index, _IN_SIDE)
     t = _TICKETS.get(key)
     if t is None:
         t = _TICKETS[key] = torch.zeros(int(_lib.lib().fm_ticket_ints()), dtype=torch.int32, device=device)
     return t
+
+
+def ensure_tickets(device) -> None:
+    global _IN_SIDE
+    was = _IN_SIDE
+    try:
+        for _IN_SIDE in (False, True):
+            _tickets(device)
+    finally:
+        _IN_SIDE = was
+
+
+# Side stream for work nothing downstream waits on (parameter gradients of small layers, see _ConvFn.backward).  The
+# trainers switch it on while they run / capture a step and join it (`join_side_streams`) before anything reads the
+# flat gradient buffer.  Tensors handed to the side stream are `record_stream`ed, so the caching allocator does not
+# give their memory to a later main-stream allocation while the side branch still reads it.
+SIDE_STREAMS = False
+SIDE_STREAM_MAX_ELEMS = 1 << 22     # per tensor: 8 MB of bf16 - the levels at <= 1/8 resolution of LDCT-256 at B = 16
+_SIDE = {}
+_SIDE_USED = set()
+
+
+@contextlib.contextmanager
+def _side_branch(tensors):
+    global _IN_SIDE
+    dev = tensors[0].device
+    key = (dev.type, dev.index)
+    side = _SIDE.get(key)
+    if side is None:
+        side = _SIDE[key] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    was, _IN_SIDE = _IN_SIDE, True
+    try:
+        with torch.cuda.stream(side):
+            yield
+    finally:
+        _IN_SIDE = was
+    for t in tensors:
+        t.record_stream(side)
+    _SIDE_USED.add(key)
+
+
+def join_side_streams() -> None:
+    """The current stream waits for every side branch opened since the last join."""
+    for key in list(_SIDE_USED):
+        dev = torch.device(key[0], key[1])
+        torch.cuda.current_stream(dev).wait_stream(_SIDE[key])
+    _SIDE_USED.clear()
 
 
 # Gradient slots.  A tensor with several consumers (a ResBlock input feeds its GroupNorm AND its residual / skip
@@ -339,7 +390,7 @@ class _ConvFn(Function):
                 slot.park(dx)
             else:
                 grads[i] = dx
-        dws, direct = {}, set()
+        dws, direct, jobs = {}, set(), []
         for i, (wi, cb, cc) in enumerate(segs):
             if not (need[1 + nsrc + wi] or _is_fused(ctx.params[wi])):
                 continue
@@ -353,19 +404,18 @@ class _ConvFn(Function):
                     covered = sum(c for j, _, c in segs if j == wi)
                     dws[wi] = (torch.empty if covered == w.shape[1] else torch.zeros)(
                         w.shape, dtype=torch.float32, device=w.device)
-            ks = 1 if w.dim() == 2 else int(w.shape[-1])
-            conv_wgrad(dy, srcs[i], dws[wi], ksize=ks, stride=stride, c_begin=cb)
-        for wi, dw in dws.items():
-            if wi in direct:
-                _grad_written(ctx.params[wi])
-            else:
-                grads[nsrc + wi] = dw
+            jobs.append((i, wi, cb, 1 if w.dim() == 2 else int(w.shape[-1])))
         need_bias = has_bias and (need[1 + nsrc + nw] or _is_fused(ctx.bias_param))
-        if need_bias or (has_addvec and need[1 + nsrc + nw + 1]):
-            tagged = getattr(dy, "_fm_colsum", None)
-            part = tagged[0] if tagged is not None and tagged[1] == dy._version else None
-            btarget = _grad_target(ctx.bias_param, (dy.shape[1],)) if need_bias else None
-            if part is not None and tuple(part.shape[::2]) == (dy.shape[0], dy.shape[1]):
+        need_addvec = has_addvec and need[1 + nsrc + nw + 1]
+        btarget = _grad_target(ctx.bias_param, (dy.shape[1],)) if need_bias else None
+        tagged = getattr(dy, "_fm_colsum", None)
+        part = tagged[0] if tagged is not None and tagged[1] == dy._version else None
+        if part is not None and tuple(part.shape[::2]) != (dy.shape[0], dy.shape[1]):
+            part = None
+
+        def bias_grads():
+            """(per-sample column sums, their total): from the GroupNorm backward's partials if dy carries them."""
+            if part is not None:
                 # dy is the dx of a GroupNorm backward that already summed its columns per row block
                 per_sample = torch.empty((dy.shape[0], dy.shape[1]), dtype=torch.float32, device=dy.device)
                 total = btarget if btarget is not None else (
@@ -374,8 +424,33 @@ class _ConvFn(Function):
                                                            dy.shape[0], part.shape[1], dy.shape[1], part.stride(1),
                                                            _tickets(dy.device).data_ptr(), _stream()),
                            "colsum_finish")
+                return per_sample, total
+            return colsum(dy, has_bias, total=btarget)
+
+        # Nothing downstream waits for a parameter gradient, so on small tensors - where the data-gradient chain is a
+        # string of latency-bound launches that leave most SMs idle - the weight-gradient GEMMs, their split-K folds
+        # and the bias column sums run on a side stream beside that chain (a parallel branch of the step graph).
+        # (not when dy itself is handed back to autograd as the residual's gradient: the engine may accumulate into it)
+        on_side = (SIDE_STREAMS and dy.is_cuda and jobs and len(direct) == len(dws)
+                   and not (has_res and need[1 + nsrc + nw + 2] and res_slot is None)
+                   and dy.numel() <= SIDE_STREAM_MAX_ELEMS and all(srcs[i].numel() <= SIDE_STREAM_MAX_ELEMS
+                                                                   for i, _, _, _ in jobs))
+        bias_on_side = on_side and need_bias and btarget is not None and not need_addvec
+        with _side_branch([dy] + [srcs[i] for i, _, _, _ in jobs] + ([part] if part is not None and bias_on_side else
+                                                                     [])) if on_side else contextlib.nullcontext():
+            for i, wi, cb, ks in jobs:
+                conv_wgrad(dy, srcs[i], dws[wi], ksize=ks, stride=stride, c_begin=cb)
+            if bias_on_side:
+                bias_grads()
+        for wi, dw in dws.items():
+            if wi in direct:
+                _grad_written(ctx.params[wi])
             else:
-                per_sample, total = colsum(dy, has_bias, total=btarget)
+                grads[nsrc + wi] = dw
+        if bias_on_side:
+            _grad_written(ctx.bias_param)
+        elif need_bias or need_addvec:
+            per_sample, total = bias_grads()
             if btarget is not None:
                 _grad_written(ctx.bias_param)
             elif has_bias:

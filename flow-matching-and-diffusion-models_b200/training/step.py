@@ -59,12 +59,13 @@ class FlowMatchingTrainer:
 
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  grad_accum: int = 1, num_train_timesteps: int = 1000, bucket_bytes: int = 64 << 20, group=None,
-                 cuda_graph: bool = True, graph_warmup: int = 2, backward_cut="auto"):
+                 cuda_graph: bool = True, graph_warmup: int = 2, backward_cut="auto", side_streams: bool = True):
         import torch.distributed as dist
 
         from .graph import flat_param_order, supported
 
         self.model = model
+        self.side_streams = bool(side_streams)
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         # two-stage backward (`training.graph.BackwardCut`): "auto" = cut when gradients are all-reduced, so the
         # reduction of the late layers' gradients overlaps the early layers' backward; an int forces the cut position
@@ -85,6 +86,7 @@ class FlowMatchingTrainer:
             for buf in model.buffers():
                 dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             torch._C._increment_version(self.optimizer.flat.params)
+        F.ensure_tickets(self.optimizer.flat.data.device)
         self.optimizer.grad_scale = 1.0 / self.reducer.world
         self.grad_accum = max(1, int(grad_accum))
         self.num_train_timesteps = int(num_train_timesteps)
@@ -132,12 +134,17 @@ class FlowMatchingTrainer:
 
         class _Ctx:
             def __enter__(self):
-                self.saved = (F.DIRECT_PARAM_GRADS, F.GRAD_READY_HOOK)
+                self.saved = (F.DIRECT_PARAM_GRADS, F.GRAD_READY_HOOK, F.SIDE_STREAMS)
                 F.DIRECT_PARAM_GRADS = trainer.grad_accum == 1
                 F.GRAD_READY_HOOK = trainer.reducer._on_grad if trainer.grad_accum == 1 else None
+                # parameter-gradient work of small layers on a side stream: only where no bucket all-reduce is launched
+                # from the gradient-ready hooks in the middle of the backward (they would have to wait for it)
+                F.SIDE_STREAMS = (trainer.side_streams and F.DIRECT_PARAM_GRADS
+                                  and not (trainer.reducer._armed and trainer.reducer.world > 1))
 
             def __exit__(self, *exc):
-                F.DIRECT_PARAM_GRADS, F.GRAD_READY_HOOK = self.saved
+                F.join_side_streams()
+                F.DIRECT_PARAM_GRADS, F.GRAD_READY_HOOK, F.SIDE_STREAMS = self.saved
                 return False
 
         return _Ctx()

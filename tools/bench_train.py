@@ -111,7 +111,15 @@ def main():
         for p in model.parameters():
             dist.broadcast(p.data, 0)
     model_name = type(model).__name__
-    tr = FlowMatchingTrainer(model, lr=1e-4, cuda_graph=not os.environ.get("NO_GRAPH"))
+    kw = {}
+    if os.environ.get("BACKWARD_CUT"):       # diagnostics: "none" = reduce after the replay (round-1 schedule), or an int
+        kw["backward_cut"] = None if os.environ["BACKWARD_CUT"] == "none" else int(os.environ["BACKWARD_CUT"])
+    if os.environ.get("NO_SIDE_STREAMS"):
+        kw["side_streams"] = False
+    tr = FlowMatchingTrainer(model, lr=1e-4, cuda_graph=not os.environ.get("NO_GRAPH"), **kw)
+    if os.environ.get("SKIP_ALLREDUCE"):     # diagnostics: the multi-rank step without its collective (rank spread only)
+        tr.reducer.launch = lambda ranges: None
+        tr.reducer.reduce_all = lambda: None
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     clean = torch.rand(B, 1, hw, hw, device=dev, generator=g)
     ldct = torch.rand(B, 1, hw, hw, device=dev, generator=g)
@@ -168,7 +176,11 @@ def main():
                           "warmup": warmup, "dtype": "bf16", "data": "synthetic",
                           "config": {"workload": f"LDCT {hw}x{hw} flow-matching training step, batch {B}/GPU",
                                      "model": model_name,
-                                     "optimizer": "AdamW (flat, fused)", "cuda_graph": not os.environ.get("NO_GRAPH"), "loss_first": ls[0], "loss_last": ls[-1]},
+                                     "optimizer": "AdamW (flat, fused)", "cuda_graph": not os.environ.get("NO_GRAPH"), "loss_first": ls[0], "loss_last": ls[-1],
+                                     "grad_reduce": getattr(tr, "reduce_mode", None),
+                                     "diagnostic_env": {k: os.environ[k] for k in ("BACKWARD_CUT", "NO_SIDE_STREAMS",
+                                                                                  "SKIP_ALLREDUCE", "NCCL_MAX_CTAS")
+                                                        if k in os.environ}},
                           "host_enqueue_ms_per_step": round(enqueue_ms, 2),
                           "e2e": {"value": round(B * world / (e2e_ms.item() / 1e3), 2), "unit": "samples/s",
                                   "h2d_bytes_per_step": int(clean.numel() + ldct.numel()) * 4, "d2h_bytes_per_step": 4},
