@@ -130,7 +130,9 @@ def ensure_tickets(device) -> None:
 # flat gradient buffer.  Tensors handed to the side stream are `record_stream`ed, so the caching allocator does not
 # give their memory to a later main-stream allocation while the side branch still reads it.
 SIDE_STREAMS = False
-SIDE_STREAM_MAX_ELEMS = 1 << 22     # per tensor: 8 MB of bf16 - the levels at <= 1/8 resolution of LDCT-256 at B = 16
+# per tensor: 32 Mi elements = 64 MB of bf16 - everything below the full-resolution level of LDCT-256 at B = 16 (measured
+# at that config: 4 Mi no gain, 32 Mi -0.7 ms per step, 256 Mi -0.6 ms; the largest layers saturate the GPU on their own)
+SIDE_STREAM_MAX_ELEMS = int(_os.environ.get("FMDM_SIDE_MAX_ELEMS", 1 << 25))
 _SIDE = {}
 _SIDE_USED = set()
 

@@ -59,13 +59,26 @@ class FlowMatchingTrainer:
 
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  grad_accum: int = 1, num_train_timesteps: int = 1000, bucket_bytes: int = 64 << 20, group=None,
-                 cuda_graph: bool = True, graph_warmup: int = 2, backward_cut="auto", side_streams: bool = True):
+                 cuda_graph: bool = True, graph_warmup: int = 2, backward_cut="auto", side_streams: bool = True,
+                 allreduce_max_ctas: Optional[int] = None):
         import torch.distributed as dist
 
         from .graph import flat_param_order, supported
 
+        import os
+
         self.model = model
         self.side_streams = bool(side_streams)
+        # a communicator of its own for the gradient all-reduce, capped at a few CTAs: the collective runs beside the
+        # second backward stage, where every SM it occupies is taken from the convs (NCCL's default sizes for speed)
+        if allreduce_max_ctas is None and os.environ.get("FMDM_ALLREDUCE_MAX_CTAS"):
+            allreduce_max_ctas = int(os.environ["FMDM_ALLREDUCE_MAX_CTAS"])
+        if (allreduce_max_ctas and group is None and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1 and dist.get_backend() == "nccl"):
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(allreduce_max_ctas)
+            opts.config.min_ctas = 1
+            group = dist.new_group(backend="nccl", pg_options=opts)
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         # two-stage backward (`training.graph.BackwardCut`): "auto" = cut when gradients are all-reduced, so the
         # reduction of the late layers' gradients overlaps the early layers' backward; an int forces the cut position
