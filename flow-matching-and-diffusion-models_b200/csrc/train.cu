@@ -645,31 +645,9 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_partial_kernel(const uint4* __r
     *reinterpret_cast<float4*>(tl.tab + ((int64_t)b * C + c) * kGnTab) =
         make_float4(a, bb, fmaf(m2, mean * rstd, -m1), -m2 * rstd);
   }
-  // ---- ticket: last sample of the launch folds the parameter gradients over the batch -----------------------------
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    tl.tickets[b] = 0;
-    s_last = atomicAdd(tl.tickets + kTicketGlobal, 1) == tl.B - 1;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
-    float acc = 0.f;
-    int s = 0;
-    for (; s + 8 <= tl.B; s += 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcg(tl.dgb_part + (int64_t)(s + u) * 2 * C + idx);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc += v[u];
-    }
-    for (; s < tl.B; ++s) acc += __ldcg(tl.dgb_part + (int64_t)s * 2 * C + idx);
-    if (tl.dbeta != nullptr && idx >= C) tl.dbeta[idx - C] = acc;
-    else tl.dgamma[idx] = acc;
-  }
-  if (threadIdx.x == 0) tl.tickets[kTicketGlobal] = 0;
+  if (threadIdx.x == 0) tl.tickets[b] = 0;  // leave the ticket buffer zero
+  // (dgamma / dbeta = the per-sample rows folded over the batch: done by one block of the apply pass, which the kernel
+  // boundary orders after every sample's finalize - a second ticket here cost ~4 us of fences per launch)
 }
 
 // pass 2: dx = a*dn + P + Q*x (+ the gradients other consumers of x left: add_a / add_b for source 0, add_1 for source 1)
@@ -681,7 +659,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const uint4* __res
                                                             int rows_per_blk, int silu, float* __restrict__ colpart,
                                                             const uint4* __restrict__ add_a,
                                                             const uint4* __restrict__ add_b,
-                                                            const uint4* __restrict__ add_1) {
+                                                            const uint4* __restrict__ add_1,
+                                                            const float* __restrict__ dgb_part,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int B) {
   // colpart (optional): per-block column sums of dx, [B][nblk][C] -- the bias / time-embedding-add gradient of the conv
   // that produced x, so that conv's backward needs no column-sum pass over dx
   extern __shared__ float cred[];  // [lanes][C8*8], only when colpart != NULL
@@ -753,16 +734,34 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const uint4* __res
 #pragma unroll
     for (int k = 0; k < 4; ++k) cs[2 * k] = cs2[k].x, cs[2 * k + 1] = cs2[k].y;
   }
-  if (colpart == nullptr) return;
-  if (lane < lanes) {
+  if (colpart != nullptr) {
+    if (lane < lanes) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cred[(lane * C8 + c8) * 8 + k] = cs[k];
+      for (int k = 0; k < 8; ++k) cred[(lane * C8 + c8) * 8 + k] = cs[k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < C; idx += blockDim.x) {
+      float acc = 0.f;
+      for (int l = 0; l < lanes; ++l) acc += cred[l * C + idx];
+      colpart[((int64_t)b * nblk + blk) * C + idx] = acc;
+    }
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < C; idx += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += cred[l * C + idx];
-    colpart[((int64_t)b * nblk + blk) * C + idx] = acc;
+  // one block also folds the per-sample (dgamma, dbeta) rows the partial pass left, in sample order
+  if (blk == nblk - 1 && b == (int)gridDim.y - 1) {
+    for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+      float acc = 0.f;
+      int sm = 0;
+      for (; sm + 8 <= B; sm += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(dgb_part + (int64_t)(sm + u) * 2 * C + idx);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      for (; sm < B; ++sm) acc += __ldg(dgb_part + (int64_t)sm * 2 * C + idx);
+      if (dbeta != nullptr && idx >= C) dbeta[idx - C] = acc;
+      else dgamma[idx] = acc;
+    }
   }
 }
 
@@ -1676,7 +1675,7 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
       reinterpret_cast<const uint4*>(dout), tab, reinterpret_cast<uint4*>(dx0), reinterpret_cast<uint4*>(dx1), HW, C8,
       lanes, rows, silu, dx_colsum_partials, reinterpret_cast<const uint4*>(add0_a),
-      reinterpret_cast<const uint4*>(add0_b), reinterpret_cast<const uint4*>(add1));
+      reinterpret_cast<const uint4*>(add0_b), reinterpret_cast<const uint4*>(add1), dgb, dgamma_dbeta, dbeta, B);
   FM_LAUNCH_CHECK("gn_bwd_apply_kernel");
   return 0;
 }

@@ -307,8 +307,9 @@ int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H, int32_t W
 /* Backward of fm_groupnorm_apply_bf16 over the virtual channel concat of (x0 [C0], x1 [C1] or NULL/0), bf16
  * [B][HW][C_s]; dout bf16 [B][HW][C0+C1]; stats as the forward computed them.  dx0 / dx1 bf16 like x0 / x1;
  * dgamma_dbeta fp32 [2][C]; dscale_shift fp32 [B][2C] (NULL iff scale_shift is NULL).
- * Two launches: the partial-sum pass (whose last block per sample folds the sums, forms the group totals and the
- * coefficient table, and whose last block overall folds dgamma / dbeta over the batch) and the apply pass.
+ * Two launches: the partial-sum pass (whose last block per sample folds the sums, forms the group totals, the
+ * coefficient table and the per-sample parameter gradients) and the apply pass (one block of which folds dgamma /
+ * dbeta over the batch).
  * add0_a, add0_b (or NULL): bf16 tensors shaped like x0 that are ADDED to dx0 - the gradients other consumers of x0
  * (a residual connection, a skip connection) produced, so no separate accumulation pass runs; add1: same for dx1.
  * dbeta (or NULL): when given, dgamma_dbeta receives only the [C] dgamma row and dbeta the [C] dbeta row (two separate

@@ -1,0 +1,31 @@
+"""Key metrics of every kernel in an .ncu-rep (`ncu --set full`): python tools/ncu_brief.py REPORT.ncu-rep > summary.txt"""
+import csv
+import io
+import subprocess
+import sys
+
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fma.sum",
+        "sm__inst_executed_pipe_alu.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "lts__t_bytes.sum", "sm__cycles_elapsed.avg.per_second"]
+
+
+def main():
+    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        print(name.split("(")[0])
+        for w in WANT:
+            if w in hdr and r[hdr.index(w)] not in ("", None):
+                print(f"    {w:66s} {r[hdr.index(w)]:>16s} {units[hdr.index(w)]}")
+        print()
+
+
+main()
