@@ -627,6 +627,21 @@ static int plan_conv(const fm_conv_params* p, ConvPlan* pl) {
   if (pl->rolling && pl->block_n == 256) pl->block_n = 128;
   // CTA pairs (cta_group::2): the 128/256-wide tiles when there are at least two M tiles; always for rolling rows
   const int m_tiles = pl->tiles_w * pl->tiles_h * pl->tiles_n;
+  // Small problems (the 16x16 / 8x8 levels: a few dozen M tiles): 256-column tiles leave most SM pairs without a work
+  // unit, so take the N tile that minimises (waves of work units) x (tile cost ~ columns + a fixed 64-column
+  // equivalent of per-tile overhead).  Large problems keep 256 (many waves: fewer, fatter tiles win).
+  if (!pl->rolling && pl->block_n == 256 && getenv("FMDM_CONV_NO_SMALL_N") == nullptr) {
+    long best_cost = -1;
+    int best_bn = 256;
+    for (int bn = 256; bn >= 64; bn >>= 1) {
+      const bool pr = bn >= 128 && m_tiles >= 2;
+      const long units = (long)((m_tiles + (pr ? 1 : 0)) / (pr ? 2 : 1)) * ((p->Cout + bn - 1) / bn);
+      const long slots = pr ? sm_count() / 2 : sm_count();
+      const long cost = ((units + slots - 1) / slots) * (bn + 64);
+      if (best_cost < 0 || cost < best_cost) best_cost = cost, best_bn = bn;
+    }
+    pl->block_n = best_bn;
+  }
   pl->pair = (pl->block_n >= 128) && (m_tiles >= 2);
   {
     const char* pe = getenv("FMDM_CONV_PAIR");  // 0 disables, 1 (default) enables
