@@ -16,7 +16,7 @@ def main():
         rows.append((re.sub(r"\(.*", "", r["Kernel Name"]), float(r["Metric Value"].replace(",", "")) / 1e3))
     idx = [i for i, r in enumerate(rows) if "adamw" in r[0]]
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    step = rows[idx[k] + 1:idx[k + 1] + 1]
+    step = rows[idx[k] + 1:idx[k + 1] + 1] if len(idx) > k + 1 else rows   # a list already trimmed to one step
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, t in step:
         agg[n][0] += 1
