@@ -815,50 +815,58 @@ constexpr int kAttB8Pad = 8;
 __global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dq,
-    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int heads, int T, int Tp, int64_t qs_b,
-    int64_t qs_h, int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale) {
+    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int heads, int Tq, int Tqp, int Tk, int Tkp,
+    int64_t qs_b, int64_t qs_h, int64_t qs_t, int64_t ks_b, int64_t ks_h, int64_t ks_t, int64_t os_b, int64_t os_h,
+    int64_t os_t, float scale) {
   extern __shared__ __align__(16) uint8_t smem_att[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);  // [Tp][8]
-  __nv_bfloat16* sK = sQ + (size_t)Tp * 8;
-  __nv_bfloat16* sV = sK + (size_t)Tp * 8;
-  __nv_bfloat16* sD = sV + (size_t)Tp * 8;                          // dO
-  const int ts = Tp + kAttB8Pad;                                    // transposed row stride
-  __nv_bfloat16* sKt = sD + (size_t)Tp * 8;                         // [8][ts]
-  __nv_bfloat16* sQt = sKt + (size_t)8 * ts;
-  __nv_bfloat16* sDt = sQt + (size_t)8 * ts;
-  float* s_lse = reinterpret_cast<float*>(sDt + (size_t)8 * ts);    // [Tp]
-  float* s_del = s_lse + Tp;
+  // queries (Tq rows: Q, dO, lse, delta) and keys (Tk rows: K, V) have their own lengths: cross-attention has Tq != Tk
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);  // [Tqp][8]
+  __nv_bfloat16* sD = sQ + (size_t)Tqp * 8;                         // dO [Tqp][8]
+  __nv_bfloat16* sK = sD + (size_t)Tqp * 8;                         // [Tkp][8]
+  __nv_bfloat16* sV = sK + (size_t)Tkp * 8;
+  const int tsq = Tqp + kAttB8Pad, tsk = Tkp + kAttB8Pad;           // transposed row strides
+  __nv_bfloat16* sKt = sV + (size_t)Tkp * 8;                        // [8][tsk]
+  __nv_bfloat16* sQt = sKt + (size_t)8 * tsk;                       // [8][tsq]
+  __nv_bfloat16* sDt = sQt + (size_t)8 * tsq;
+  float* s_lse = reinterpret_cast<float*>(sDt + (size_t)8 * tsq);   // [Tqp]
+  float* s_del = s_lse + Tqp;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int64_t qoff = b * qs_b + h * qs_h, ooff = b * os_b + h * os_h;
+  const int64_t qoff = b * qs_b + h * qs_h, koff = b * ks_b + h * ks_h, ooff = b * os_b + h * os_h;
   const float c = scale * 1.4426950408889634f;
 
-  for (int r = threadIdx.x; r < Tp; r += blockDim.x) {
-    uint4 vq = make_uint4(0, 0, 0, 0), vk = vq, vv = vq, vd = vq;
-    if (r < T) {
+  for (int r = threadIdx.x; r < Tqp; r += blockDim.x) {
+    uint4 vq = make_uint4(0, 0, 0, 0), vd = vq;
+    if (r < Tq) {
       vq = *reinterpret_cast<const uint4*>(q + qoff + (int64_t)r * qs_t);
-      vk = *reinterpret_cast<const uint4*>(k + qoff + (int64_t)r * qs_t);
-      vv = *reinterpret_cast<const uint4*>(v + qoff + (int64_t)r * qs_t);
       vd = *reinterpret_cast<const uint4*>(dout + ooff + (int64_t)r * os_t);
     }
     *reinterpret_cast<uint4*>(sQ + r * 8) = vq;
-    *reinterpret_cast<uint4*>(sK + r * 8) = vk;
-    *reinterpret_cast<uint4*>(sV + r * 8) = vv;
     *reinterpret_cast<uint4*>(sD + r * 8) = vd;
     const __nv_bfloat16* eq = reinterpret_cast<const __nv_bfloat16*>(&vq);
-    const __nv_bfloat16* ek = reinterpret_cast<const __nv_bfloat16*>(&vk);
     const __nv_bfloat16* ed = reinterpret_cast<const __nv_bfloat16*>(&vd);
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
-      sQt[d * ts + r] = eq[d];
-      sKt[d * ts + r] = ek[d];
-      sDt[d * ts + r] = ed[d];
+      sQt[d * tsq + r] = eq[d];
+      sDt[d * tsq + r] = ed[d];
     }
+  }
+  for (int r = threadIdx.x; r < Tkp; r += blockDim.x) {
+    uint4 vk = make_uint4(0, 0, 0, 0), vv = vk;
+    if (r < Tk) {
+      vk = *reinterpret_cast<const uint4*>(k + koff + (int64_t)r * ks_t);
+      vv = *reinterpret_cast<const uint4*>(v + koff + (int64_t)r * ks_t);
+    }
+    *reinterpret_cast<uint4*>(sK + r * 8) = vk;
+    *reinterpret_cast<uint4*>(sV + r * 8) = vv;
+    const __nv_bfloat16* ek = reinterpret_cast<const __nv_bfloat16*>(&vk);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) sKt[d * tsk + r] = ek[d];
   }
   __syncthreads();
 
   // ================= phase A: dQ, lse, delta =================
-  for (int q0 = warp * 16; q0 < Tp; q0 += 8 * 16) {
+  for (int q0 = warp * 16; q0 < Tqp; q0 += 8 * 16) {
     const uint32_t qa0 = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g) * 8 + 2 * t);
     const uint32_t qa1 = *reinterpret_cast<const uint32_t*>(sQ + (q0 + g + 8) * 8 + 2 * t);
     const uint32_t da0 = *reinterpret_cast<const uint32_t*>(sD + (q0 + g) * 8 + 2 * t);
@@ -868,11 +876,11 @@ __global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
     {
       const int r0 = q0 + g, r1 = q0 + g + 8;
       const float2 d0 = bf16x2_as_f32x2(da0), d1 = bf16x2_as_f32x2(da1);
-      if (r0 < T) {
+      if (r0 < Tq) {
         const float2 o0 = bf16x2_as_f32x2(*reinterpret_cast<const uint32_t*>(o + ooff + (int64_t)r0 * os_t + 2 * t));
         del0 = fmaf(d0.x, o0.x, d0.y * o0.y);
       }
-      if (r1 < T) {
+      if (r1 < Tq) {
         const float2 o1 = bf16x2_as_f32x2(*reinterpret_cast<const uint32_t*>(o + ooff + (int64_t)r1 * os_t + 2 * t));
         del1 = fmaf(d1.x, o1.x, d1.y * o1.y);
       }
@@ -883,9 +891,9 @@ __global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
     }
     // pass 1: online row max / sum (log2 domain), 64 keys at a time
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int kb0 = 0; kb0 < Tp; kb0 += 64) {
+    for (int kb0 = 0; kb0 < Tkp; kb0 += 64) {
       float sc[8][4];
-      const int nblk = (Tp - kb0) >= 64 ? 8 : (Tp - kb0) / 8;
+      const int nblk = (Tkp - kb0) >= 64 ? 8 : (Tkp - kb0) / 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY;
@@ -893,8 +901,8 @@ __global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
           sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
           mma_m16n8k8_bf16(sc[j], qa0, qa1, *reinterpret_cast<const uint32_t*>(sK + (kb0 + j * 8 + g) * 8 + 2 * t));
           const int key = kb0 + j * 8 + 2 * t;
-          if (key >= T) sc[j][0] = sc[j][2] = -INFINITY;
-          if (key + 1 >= T) sc[j][1] = sc[j][3] = -INFINITY;
+          if (key >= Tk) sc[j][0] = sc[j][2] = -INFINITY;
+          if (key + 1 >= Tk) sc[j][1] = sc[j][3] = -INFINITY;
         }
       }
       float mx0 = sc[0][0], mx1 = sc[0][2];
@@ -923,14 +931,14 @@ __global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float lse0 = m0 + __log2f(l0), lse1 = m1 + __log2f(l1);
     if (t == 0) {  // rows past T: +inf, so phase B's 2^(s c - lse) is exactly 0 for them
-      s_lse[q0 + g] = (q0 + g < T) ? lse0 : INFINITY;
-      s_lse[q0 + g + 8] = (q0 + g + 8 < T) ? lse1 : INFINITY;
+      s_lse[q0 + g] = (q0 + g < Tq) ? lse0 : INFINITY;
+      s_lse[q0 + g + 8] = (q0 + g + 8 < Tq) ? lse1 : INFINITY;
       s_del[q0 + g] = del0;
       s_del[q0 + g + 8] = del1;
     }
     // pass 2: dQ
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int kb = 0; kb < Tp; kb += 16) {
+    for (int kb = 0; kb < Tkp; kb += 16) {
       uint32_t af[4];
 #pragma unroll
       for (int hb = 0; hb < 2; ++hb) {
@@ -939,32 +947,32 @@ __global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
         mma_m16n8k8_bf16(sv, qa0, qa1, *reinterpret_cast<const uint32_t*>(sK + (kk + g) * 8 + 2 * t));
         mma_m16n8k8_bf16(dp, da0, da1, *reinterpret_cast<const uint32_t*>(sV + (kk + g) * 8 + 2 * t));
         const int key = kk + 2 * t;
-        const float p0 = key < T ? ex2_approx(fmaf(sv[0], c, -lse0)) : 0.f;
-        const float p1 = key + 1 < T ? ex2_approx(fmaf(sv[1], c, -lse0)) : 0.f;
-        const float p2 = key < T ? ex2_approx(fmaf(sv[2], c, -lse1)) : 0.f;
-        const float p3 = key + 1 < T ? ex2_approx(fmaf(sv[3], c, -lse1)) : 0.f;
+        const float p0 = key < Tk ? ex2_approx(fmaf(sv[0], c, -lse0)) : 0.f;
+        const float p1 = key + 1 < Tk ? ex2_approx(fmaf(sv[1], c, -lse0)) : 0.f;
+        const float p2 = key < Tk ? ex2_approx(fmaf(sv[2], c, -lse1)) : 0.f;
+        const float p3 = key + 1 < Tk ? ex2_approx(fmaf(sv[3], c, -lse1)) : 0.f;
         af[hb * 2 + 0] = pack_bf16x2(p0 * (dp[0] - del0) * scale, p1 * (dp[1] - del0) * scale);
         af[hb * 2 + 1] = pack_bf16x2(p2 * (dp[2] - del1) * scale, p3 * (dp[3] - del1) * scale);
       }
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sKt + g * ts + kb + 2 * t);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sKt + g * ts + kb + 8 + 2 * t);
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sKt + g * tsk + kb + 2 * t);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sKt + g * tsk + kb + 8 + 2 * t);
       mma_m16n8k16_bf16(acc, af[0], af[1], af[2], af[3], b0, b1);
     }
-    if (q0 + g < T)
+    if (q0 + g < Tq)
       *reinterpret_cast<uint32_t*>(dq + qoff + (int64_t)(q0 + g) * qs_t + 2 * t) = pack_bf16x2(acc[0], acc[1]);
-    if (q0 + g + 8 < T)
+    if (q0 + g + 8 < Tq)
       *reinterpret_cast<uint32_t*>(dq + qoff + (int64_t)(q0 + g + 8) * qs_t + 2 * t) = pack_bf16x2(acc[2], acc[3]);
   }
   __syncthreads();
 
   // ================= phase B: dK, dV =================
-  for (int k0 = warp * 16; k0 < Tp; k0 += 8 * 16) {
+  for (int k0 = warp * 16; k0 < Tkp; k0 += 8 * 16) {
     const uint32_t ka0 = *reinterpret_cast<const uint32_t*>(sK + (k0 + g) * 8 + 2 * t);
     const uint32_t ka1 = *reinterpret_cast<const uint32_t*>(sK + (k0 + g + 8) * 8 + 2 * t);
     const uint32_t va0 = *reinterpret_cast<const uint32_t*>(sV + (k0 + g) * 8 + 2 * t);
     const uint32_t va1 = *reinterpret_cast<const uint32_t*>(sV + (k0 + g + 8) * 8 + 2 * t);
     float ak[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int qb = 0; qb < Tp; qb += 16) {
+    for (int qb = 0; qb < Tqp; qb += 16) {
       uint32_t pf[4], sf[4];
 #pragma unroll
       for (int hb = 0; hb < 2; ++hb) {
@@ -981,20 +989,20 @@ __global__ void __launch_bounds__(256) attention_bwd_hd8_mma_kernel(
         sf[hb * 2 + 0] = pack_bf16x2(p0 * (dp[0] - dl.x) * scale, p1 * (dp[1] - dl.y) * scale);
         sf[hb * 2 + 1] = pack_bf16x2(p2 * (dp[2] - dl.x) * scale, p3 * (dp[3] - dl.y) * scale);
       }
-      const uint32_t d0 = *reinterpret_cast<const uint32_t*>(sDt + g * ts + qb + 2 * t);
-      const uint32_t d1 = *reinterpret_cast<const uint32_t*>(sDt + g * ts + qb + 8 + 2 * t);
+      const uint32_t d0 = *reinterpret_cast<const uint32_t*>(sDt + g * tsq + qb + 2 * t);
+      const uint32_t d1 = *reinterpret_cast<const uint32_t*>(sDt + g * tsq + qb + 8 + 2 * t);
       mma_m16n8k16_bf16(av, pf[0], pf[1], pf[2], pf[3], d0, d1);
-      const uint32_t q0b = *reinterpret_cast<const uint32_t*>(sQt + g * ts + qb + 2 * t);
-      const uint32_t q1b = *reinterpret_cast<const uint32_t*>(sQt + g * ts + qb + 8 + 2 * t);
+      const uint32_t q0b = *reinterpret_cast<const uint32_t*>(sQt + g * tsq + qb + 2 * t);
+      const uint32_t q1b = *reinterpret_cast<const uint32_t*>(sQt + g * tsq + qb + 8 + 2 * t);
       mma_m16n8k16_bf16(ak, sf[0], sf[1], sf[2], sf[3], q0b, q1b);
     }
-    if (k0 + g < T) {
-      *reinterpret_cast<uint32_t*>(dk + qoff + (int64_t)(k0 + g) * qs_t + 2 * t) = pack_bf16x2(ak[0], ak[1]);
-      *reinterpret_cast<uint32_t*>(dv + qoff + (int64_t)(k0 + g) * qs_t + 2 * t) = pack_bf16x2(av[0], av[1]);
+    if (k0 + g < Tk) {
+      *reinterpret_cast<uint32_t*>(dk + koff + (int64_t)(k0 + g) * ks_t + 2 * t) = pack_bf16x2(ak[0], ak[1]);
+      *reinterpret_cast<uint32_t*>(dv + koff + (int64_t)(k0 + g) * ks_t + 2 * t) = pack_bf16x2(av[0], av[1]);
     }
-    if (k0 + g + 8 < T) {
-      *reinterpret_cast<uint32_t*>(dk + qoff + (int64_t)(k0 + g + 8) * qs_t + 2 * t) = pack_bf16x2(ak[2], ak[3]);
-      *reinterpret_cast<uint32_t*>(dv + qoff + (int64_t)(k0 + g + 8) * qs_t + 2 * t) = pack_bf16x2(av[2], av[3]);
+    if (k0 + g + 8 < Tk) {
+      *reinterpret_cast<uint32_t*>(dk + koff + (int64_t)(k0 + g + 8) * ks_t + 2 * t) = pack_bf16x2(ak[2], ak[3]);
+      *reinterpret_cast<uint32_t*>(dv + koff + (int64_t)(k0 + g + 8) * ks_t + 2 * t) = pack_bf16x2(av[2], av[3]);
     }
   }
 }
@@ -1625,6 +1633,175 @@ extern "C" int fm_colsum_finish_f32(const float* partials, float* out, float* to
 
 extern "C" int32_t fm_ticket_ints(void) { return kTicketInts; }
 
+// =============================================================================================================
+// Backward of the cross-attention context path (fm_context_kv_bf16, token-major): kv[b][t][o] = bias[o] + sum_c W[o][c] n,
+// n = (ctx[b][c][t] - mean) rstd gamma[c] + beta[c].  Tiny (Cc <= 16): two CUDA-core kernels with fixed-order folds.
+//   dW[o][c] = sum_{b,t} dkv n,  dbias[o] = sum dkv          (thread = output feature, block = 64 tokens of a sample)
+//   dgamma[c] = sum_{b,t} (sum_o dkv W[o][c]) xhat,  dbeta[c] = sum (sum_o dkv W[o][c])       (thread = token)
+// =============================================================================================================
+constexpr int kCtxBwdMaxC = 16;
+constexpr int kCtxBwdTok = 64;
+
+__global__ void __launch_bounds__(256) context_kv_bwd_w_kernel(const float* __restrict__ ctx,
+                                                                const float* __restrict__ stats,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                const __nv_bfloat16* __restrict__ dkv,
+                                                                float* __restrict__ part, int Cc, int Tc, int O,
+                                                                int groups, int chunks_per_sample) {
+  __shared__ float sn[kCtxBwdMaxC][kCtxBwdTok];
+  const int chunk = blockIdx.x, b = chunk / chunks_per_sample, t0 = (chunk % chunks_per_sample) * kCtxBwdTok;
+  const int cpg = Cc / groups;
+  for (int i = threadIdx.x; i < Cc * kCtxBwdTok; i += blockDim.x) {
+    const int c = i / kCtxBwdTok, tt = i - c * kCtxBwdTok;
+    float v = 0.f;
+    if (t0 + tt < Tc) {
+      const int g = c / cpg;
+      const float mean = stats[((int64_t)b * groups + g) * 2 + 0], rstd = stats[((int64_t)b * groups + g) * 2 + 1];
+      v = fmaf((ctx[((int64_t)b * Cc + c) * Tc + t0 + tt] - mean) * rstd, gamma[c], beta[c]);
+    }
+    sn[c][tt] = v;
+  }
+  __syncthreads();
+  const int ntok = min(kCtxBwdTok, Tc - t0);
+  // part[chunk][o][Cc + 1]: the weight-gradient row of feature o, then its bias gradient
+  for (int o = threadIdx.x; o < O; o += blockDim.x) {
+    float acc[kCtxBwdMaxC + 1];
+#pragma unroll
+    for (int c = 0; c <= kCtxBwdMaxC; ++c) acc[c] = 0.f;
+    for (int tt = 0; tt < ntok; ++tt) {
+      const float d = __bfloat162float(dkv[((int64_t)b * Tc + t0 + tt) * O + o]);
+#pragma unroll
+      for (int c = 0; c < kCtxBwdMaxC; ++c)
+        if (c < Cc) acc[c] = fmaf(d, sn[c][tt], acc[c]);
+      acc[kCtxBwdMaxC] += d;
+    }
+    float* dst = part + ((int64_t)chunk * O + o) * (Cc + 1);
+#pragma unroll
+    for (int c = 0; c < kCtxBwdMaxC; ++c)
+      if (c < Cc) dst[c] = acc[c];
+    dst[Cc] = acc[kCtxBwdMaxC];
+  }
+}
+
+// dwb[o][Cc + 1] -> dW [O][Cc], dbias [O]
+__global__ void context_kv_bwd_split_kernel(const float* __restrict__ dwb, float* __restrict__ dW,
+                                            float* __restrict__ dbias, int O, int Cc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * (Cc + 1)) return;
+  const int o = i / (Cc + 1), c = i - o * (Cc + 1);
+  if (c < Cc) dW[o * Cc + c] = dwb[i];
+  else if (dbias != nullptr) dbias[o] = dwb[i];
+}
+
+__global__ void __launch_bounds__(128) context_kv_bwd_norm_kernel(const float* __restrict__ ctx,
+                                                                   const float* __restrict__ stats,
+                                                                   const float* __restrict__ W,
+                                                                   const __nv_bfloat16* __restrict__ dkv,
+                                                                   float* __restrict__ part, int Cc, int Tc, int O,
+                                                                   int groups, int64_t tokens) {
+  extern __shared__ float sW[];                 // [O][Cc]
+  __shared__ float red[4][2 * kCtxBwdMaxC];
+  for (int i = threadIdx.x; i < O * Cc; i += blockDim.x) sW[i] = W[i];
+  __syncthreads();
+  const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float dn[kCtxBwdMaxC], dg[kCtxBwdMaxC];
+#pragma unroll
+  for (int c = 0; c < kCtxBwdMaxC; ++c) dn[c] = dg[c] = 0.f;
+  if (tok < tokens) {
+    const int b = (int)(tok / Tc), t = (int)(tok - (int64_t)b * Tc);
+    const __nv_bfloat16* row = dkv + tok * O;
+    for (int o = 0; o < O; ++o) {
+      const float d = __bfloat162float(row[o]);
+#pragma unroll
+      for (int c = 0; c < kCtxBwdMaxC; ++c)
+        if (c < Cc) dn[c] = fmaf(d, sW[o * Cc + c], dn[c]);
+    }
+    const int cpg = Cc / groups;
+#pragma unroll
+    for (int c = 0; c < kCtxBwdMaxC; ++c) {
+      if (c < Cc) {
+        const int g = c / cpg;
+        const float mean = stats[((int64_t)b * groups + g) * 2 + 0], rstd = stats[((int64_t)b * groups + g) * 2 + 1];
+        dg[c] = dn[c] * (ctx[((int64_t)b * Cc + c) * Tc + t] - mean) * rstd;
+      }
+    }
+  }
+  // fixed-order fold over the block's tokens: lanes by shuffle, the four warps through shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < kCtxBwdMaxC; ++c) {
+    const float a = warp_sum(dg[c]), bsum = warp_sum(dn[c]);
+    if (lane == 0) {
+      red[warp][c] = a;
+      red[warp][kCtxBwdMaxC + c] = bsum;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kCtxBwdMaxC) {
+    const float v = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    part[(int64_t)blockIdx.x * 2 * kCtxBwdMaxC + threadIdx.x] = v;   // [block][dgamma(16) | dbeta(16)]
+  }
+}
+
+__global__ void context_kv_bwd_gb_kernel(const float* __restrict__ folded, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta, int Cc) {
+  const int c = threadIdx.x;
+  if (c < Cc) {
+    dgamma[c] = folded[c];
+    dbeta[c] = folded[kCtxBwdMaxC + c];
+  }
+}
+
+extern "C" int64_t fm_context_kv_bwd_workspace_elems(int32_t B, int32_t Cc, int32_t Tc, int32_t O) {
+  const int64_t chunks = (int64_t)B * ((Tc + kCtxBwdTok - 1) / kCtxBwdTok);
+  const int64_t nb = ((int64_t)B * Tc + 127) / 128;
+  return chunks * O * (Cc + 1) + (int64_t)O * (Cc + 1) + nb * 2 * kCtxBwdMaxC + 2 * kCtxBwdMaxC;
+}
+
+extern "C" int fm_context_kv_bwd_f32(const float* ctx, const float* stats, const float* gamma, const float* beta,
+                                     const float* W, const void* dkv, float* workspace, float* dW, float* dbias,
+                                     float* dgamma, float* dbeta, int32_t B, int32_t Cc, int32_t Tc, int32_t O,
+                                     int32_t groups, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(ctx && stats && gamma && beta && W && dkv && workspace && dW && dgamma && dbeta,
+             "context_kv_bwd: null pointer");
+  FM_REQUIRE(Cc >= 1 && Cc <= kCtxBwdMaxC && groups > 0 && Cc % groups == 0 && B > 0 && Tc > 0 && O > 0,
+             "context_kv_bwd: bad shape (context_dim <= 16)");
+  FM_REQUIRE((size_t)O * Cc * sizeof(float) <= 160 * 1024, "context_kv_bwd: O * Cc too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cps = (Tc + kCtxBwdTok - 1) / kCtxBwdTok;
+  const int chunks = B * cps;
+  float* part = workspace;
+  float* dwb = part + (int64_t)chunks * O * (Cc + 1);
+  const int64_t tokens = (int64_t)B * Tc;
+  const int nb = (int)((tokens + 127) / 128);
+  float* npart = dwb + (int64_t)O * (Cc + 1);
+  float* nfold = npart + (int64_t)nb * 2 * kCtxBwdMaxC;
+  context_kv_bwd_w_kernel<<<chunks, 256, 0, st>>>(ctx, stats, gamma, beta, reinterpret_cast<const __nv_bfloat16*>(dkv),
+                                                  part, Cc, Tc, O, groups, cps);
+  FM_LAUNCH_CHECK("context_kv_bwd_w_kernel");
+  if (int e = launch_reduce(part, dwb, 1, chunks, (int64_t)O * (Cc + 1), st)) return e;
+  context_kv_bwd_split_kernel<<<(O * (Cc + 1) + 255) / 256, 256, 0, st>>>(dwb, dW, dbias, O, Cc);
+  FM_LAUNCH_CHECK("context_kv_bwd_split_kernel");
+  const size_t smem = (size_t)O * Cc * sizeof(float);
+  static size_t attr = 48 * 1024;
+  if (smem > attr) {
+    if (int e = check_cuda(cudaFuncSetAttribute(context_kv_bwd_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem), "context_kv_bwd attr")) return e;
+    attr = smem;
+  }
+  context_kv_bwd_norm_kernel<<<nb, 128, smem, st>>>(ctx, stats, W, reinterpret_cast<const __nv_bfloat16*>(dkv), npart,
+                                                    Cc, Tc, O, groups, tokens);
+  FM_LAUNCH_CHECK("context_kv_bwd_norm_kernel");
+  if (int e = launch_reduce(npart, nfold, 1, nb, 2 * kCtxBwdMaxC, st)) return e;
+  context_kv_bwd_gb_kernel<<<1, 32, 0, st>>>(nfold, dgamma, dbeta, Cc);
+  FM_LAUNCH_CHECK("context_kv_bwd_gb_kernel");
+  return 0;
+}
+
+
+
 extern "C" int64_t fm_groupnorm_bwd_workspace_elems(int32_t B, int64_t HW, int32_t C) {
   if (ensure_device()) return 0;
   /* table [B][C][4] + partials [B][nblk][2][C] + dgb_part [B][2][C] */
@@ -1680,6 +1857,41 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
   return 0;
 }
 
+/* head_dim 8, queries and keys of different length / layout (cross-attention): q, dq use the q strides; k, v, dk, dv the
+ * kv strides; o, dout the o strides.  FM_ERR_UNSUPPORTED if the staged tiles exceed shared memory. */
+extern "C" int fm_attention_bwd_cross_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                                           void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t Tq,
+                                           int32_t Tk, int32_t head_dim, int64_t qs_b, int64_t qs_h, int64_t qs_t,
+                                           int64_t ks_b, int64_t ks_h, int64_t ks_t, int64_t os_b, int64_t os_h,
+                                           int64_t os_t, float scale, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(q && k && v && o && dout && dq && dk && dv && Tq > 0 && Tk > 0, "attention_bwd_cross: bad argument");
+  FM_REQUIRE(head_dim == 8, "attention_bwd_cross: head_dim %d unsupported (8)", head_dim);
+  FM_REQUIRE(((qs_b | qs_h | qs_t | ks_b | ks_h | ks_t | os_b | os_h | os_t) % 8) == 0 &&
+                 (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq |
+                   (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+             "attention_bwd_cross: rows must be 16-byte aligned (strides multiples of 8 elements)");
+  const int Tqp = (Tq + 15) & ~15, Tkp = (Tk + 15) & ~15;
+  const size_t need = (size_t)(Tqp + Tkp) * 8 * 2 * 2 + (size_t)8 * (Tkp + kAttB8Pad) * 2 +
+                      (size_t)2 * 8 * (Tqp + kAttB8Pad) * 2 + (size_t)2 * Tqp * 4;
+  if (need > 200 * 1024) {
+    set_error("attention_bwd_cross: Tq=%d Tk=%d exceed the shared-memory staging budget", Tq, Tk);
+    return FM_ERR_UNSUPPORTED;
+  }
+  static size_t attr8 = 48 * 1024;
+  if (need > attr8) {
+    if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_hd8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)need), "attention_bwd_hd8 attr")) return e;
+    attr8 = need;
+  }
+  attention_bwd_hd8_mma_kernel<<<B * heads, 256, need, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,
+      (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, Tq, Tqp, Tk, Tkp,
+      qs_b, qs_h, qs_t, ks_b, ks_h, ks_t, os_b, os_h, os_t, scale);
+  FM_LAUNCH_CHECK("attention_bwd_hd8_mma_kernel");
+  return 0;
+}
+
 extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout,
                                      void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t T,
                                      int32_t head_dim, int64_t qs_b, int64_t qs_h, int64_t qs_t, int64_t os_b,
@@ -1693,23 +1905,9 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
   cudaStream_t st = (cudaStream_t)stream;
   static const bool scalar8 = getenv("FMDM_ATTENTION_BWD_SCALAR") != nullptr;  // A/B: the CUDA-core kernel at head_dim 8
   if (head_dim == 8 && !scalar8) {
-    const int Tp = (T + 15) & ~15;
-    const size_t need = (size_t)Tp * 8 * 2 * 4 + (size_t)3 * 8 * (Tp + kAttB8Pad) * 2 + (size_t)2 * Tp * 4;
-    if (need <= 200 * 1024) {
-      static size_t attr8 = 48 * 1024;
-      if (need > attr8) {
-        if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_hd8_mma_kernel,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need),
-                               "attention_bwd_hd8 attr")) return e;
-        attr8 = need;
-      }
-      attention_bwd_hd8_mma_kernel<<<B * heads, 256, need, st>>>(
-          (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,
-          (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, T, Tp, qs_b,
-          qs_h, qs_t, os_b, os_h, os_t, scale);
-      FM_LAUNCH_CHECK("attention_bwd_hd8_mma_kernel");
-      return 0;
-    }
+    const int rc = fm_attention_bwd_cross_bf16(q, k, v, o, dout, dq, dk, dv, B, heads, T, T, 8, qs_b, qs_h, qs_t, qs_b,
+                                               qs_h, qs_t, os_b, os_h, os_t, scale, stream);
+    if (rc != FM_ERR_UNSUPPORTED) return rc;
   }
   // fp32 staging (no unpacking in the T^2 loops) when the four tiles fit in 96 KB, else bf16 staging
   const size_t tiles = (size_t)4 * T * head_dim;

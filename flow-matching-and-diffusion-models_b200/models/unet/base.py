@@ -89,7 +89,7 @@ class BaseUNetND(nn.Module, ABC):
             # training step (`flow_matching_lib.py:158-169`): same modules and parameters, differentiable kernels
             from ...training import graph
 
-            return self._postprocess_output(graph.unet_forward(self, x, t, context))
+            return self._postprocess_output(graph.unet_forward(self, x, t, context, context_ca))
         if t_table is not None:
             # the sampling loop feeds one timestep to the whole batch (`pipelines/utils.py:206-209` expands a scalar):
             # the time embedding and every projection of it are computed for ONE row and broadcast (stride 0)

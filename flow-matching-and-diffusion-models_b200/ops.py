@@ -556,7 +556,7 @@ def linear_attention(q, k, v, out, *, batch, heads, tq, tk, head_dim, q_strides,
 
 
 def context_kv(ctx: torch.Tensor, gamma, beta, weight, bias, *, groups: int, eps: float,
-               channel_major: bool) -> torch.Tensor:
+               channel_major: bool, return_stats: bool = False):
     """GroupNorm over the context tokens + key/value projection: ctx fp32 [B][Cc][Tc] -> bf16 [B][Tc][O]
     (or [B][O][Tc] when channel_major); weight fp32 [O][Cc]."""
     lib = _lib.lib()
@@ -573,7 +573,7 @@ def context_kv(ctx: torch.Tensor, gamma, beta, weight, bias, *, groups: int, eps
                                int(bool(channel_major)), _stream()),
         "context_kv",
     )
-    return out
+    return (out, ws) if return_stats else out
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -657,6 +657,96 @@ def attention_qkv(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     return _AttentionFn.apply(qkv, int(heads))
 
 
+class _CrossAttentionFn(Function):
+    """Cross-attention of `DiffusersAttentionND(context_dim)` (`attention.py:232-274`): q NHWC [b][T][C] from the image
+    tokens, kv [b][Tc][2C] (K | V, head h at h*hd) from the context path; head_dim 8."""
+
+    @staticmethod
+    def forward(ctx, q, kv, heads):
+        q = _nhwc(q)
+        b, c, hh, ww = q.shape
+        t, hd, tc = hh * ww, c // heads, kv.shape[1]
+        assert kv.dtype == BF16 and kv.is_contiguous() and kv.shape[2] == 2 * c
+        att = ops.empty_nhwc(b, c, hh, ww, q.device)
+        kvf = kv.view(-1)
+        ops.attention(q.permute(0, 2, 3, 1).reshape(-1), kvf, kvf[c:], att.permute(0, 2, 3, 1).reshape(-1), batch=b,
+                      heads=heads, tq=t, tk=tc, head_dim=hd, q_strides=(t * c, hd, c),
+                      kv_strides=(tc * 2 * c, hd, 2 * c), o_strides=(t * c, hd, c))
+        ctx.heads = heads
+        ctx.save_for_backward(q, kv, att)
+        return att
+
+    @staticmethod
+    def backward(ctx, datt):
+        q, kv, att = ctx.saved_tensors
+        heads = ctx.heads
+        datt = _nhwc(datt)
+        b, c, hh, ww = q.shape
+        t, hd, tc = hh * ww, c // heads, kv.shape[1]
+        dq = ops.empty_nhwc(b, c, hh, ww, q.device)
+        dkv = torch.empty_like(kv)
+        k0, d0 = kv.data_ptr(), dkv.data_ptr()
+        _lib.check(
+            _lib.lib().fm_attention_bwd_cross_bf16(q.data_ptr(), k0, k0 + 2 * c, att.data_ptr(), datt.data_ptr(),
+                                                   dq.data_ptr(), d0, d0 + 2 * c, b, heads, t, tc, hd, t * c, hd, c,
+                                                   tc * 2 * c, hd, 2 * c, t * c, hd, c, 1.0 / math.sqrt(hd), _stream()),
+            "attention_bwd_cross",
+        )
+        return dq, dkv, None
+
+
+def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int) -> torch.Tensor:
+    return _CrossAttentionFn.apply(q, kv, int(heads))
+
+
+class _ContextKVFn(Function):
+    """The cross-attention context path (`fm_context_kv_bf16`, token-major): GroupNorm over the context tokens + the
+    key | value projection; gradients to the projection and to the context GroupNorm's affine (the context is data)."""
+
+    @staticmethod
+    def forward(ctx, tokens, gamma, beta, weight, bias, groups, eps):
+        tokens = tokens.detach().float().contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        w32 = weight.detach().float().contiguous()
+        bias32 = None if bias is None else bias.detach().float().contiguous()
+        kv, stats = ops.context_kv(tokens, g32, b32, w32, bias32, groups=groups, eps=eps, channel_major=False,
+                                   return_stats=True)
+        ctx.groups = int(groups)
+        ctx.params = (gamma, beta, weight, bias)
+        ctx.save_for_backward(tokens, stats, g32, b32, w32)
+        return kv
+
+    @staticmethod
+    def backward(ctx, dkv):
+        lib = _lib.lib()
+        tokens, stats, g32, b32, w32 = ctx.saved_tensors
+        gamma, beta, weight, bias = ctx.params
+        dkv = dkv.to(BF16).contiguous()
+        b, cc, tc = tokens.shape
+        o = w32.shape[0]
+        ws = _ws(lib.fm_context_kv_bwd_workspace_elems(b, cc, tc, o), tokens.device)
+        tw, tb = _grad_target(weight, w32.shape), (_grad_target(bias, (o,)) if bias is not None else None)
+        tg, tbe = _grad_target(gamma, (cc,)), _grad_target(beta, (cc,))
+        dw = tw if tw is not None else torch.empty_like(w32)
+        db = tb if tb is not None else (torch.empty((o,), dtype=torch.float32, device=tokens.device)
+                                        if bias is not None else None)
+        dg = tg if tg is not None else torch.empty((cc,), dtype=torch.float32, device=tokens.device)
+        dbe = tbe if tbe is not None else torch.empty((cc,), dtype=torch.float32, device=tokens.device)
+        _lib.check(lib.fm_context_kv_bwd_f32(tokens.data_ptr(), stats.data_ptr(), g32.data_ptr(), b32.data_ptr(),
+                                             w32.data_ptr(), dkv.data_ptr(), ws.data_ptr(), dw.data_ptr(), _ptr(db),
+                                             dg.data_ptr(), dbe.data_ptr(), b, cc, tc, o, ctx.groups, _stream()),
+                   "context_kv_bwd")
+        for param, target in ((weight, tw), (bias, tb), (gamma, tg), (beta, tbe)):
+            if target is not None:
+                _grad_written(param)
+        return (None, None if tg is not None else dg, None if tbe is not None else dbe, None if tw is not None else dw,
+                None if (tb is not None or bias is None) else db, None, None)
+
+
+def context_kv(tokens, gamma, beta, weight, bias, *, groups: int, eps: float) -> torch.Tensor:
+    return _ContextKVFn.apply(tokens, gamma, beta, weight, bias, int(groups), float(eps))
+
+
 class _AttentionRawFn(Function):
     """SpatialSelfAttention's raw-reshape head split (`attention.py:111-115`): the channel-major (b, 3*inner, T) qkv
     buffer re-read as (b, heads, T, 3*dh); returns (b, heads, T, dh) contiguous."""

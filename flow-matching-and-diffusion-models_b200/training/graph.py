@@ -23,7 +23,16 @@ def supported(model) -> bool:
     from ..models.unet.unet_diffusers_nd import UNetDiffusersND
 
     if isinstance(model, UNetDiffusersND):
-        return model.spatial_dims == 2 and model.cross_attention_dim is None
+        if model.spatial_dims != 2:
+            return False
+        if model.cross_attention_dim is None:
+            return True
+        # conditioning: "attention" (`flow_matching_lib.py:159-164`): cross-attention trains at head_dim 8 with a
+        # context of <= 16 channels (the LDCT latents have 4)
+        from ..nn.blocks.attention import CONTEXT_DIM_MAX, DiffusersAttentionND
+
+        cross = [m for m in model.modules() if isinstance(m, DiffusersAttentionND) and m.context_dim is not None]
+        return all(m.head_dim == 8 and m.context_dim <= CONTEXT_DIM_MAX and m.dropout == 0 for m in cross)
     if isinstance(model, EfficientUNetND):
         return (model.spatial_dims == 2 and not model.cross_attention_resolutions
                 and not model.cross_attention_in_middle and model.dropout == 0)
@@ -128,8 +137,11 @@ def flat_param_order(model, cut_at=None):
     emb_group(early, back)
     trios = {}
     for m in model.modules():
-        if isinstance(m, DiffusersAttentionND) and getattr(m, "context_dim", None) is None:
-            for plist in ([m.to_q.weight, m.to_k.weight, m.to_v.weight], [m.to_q.bias, m.to_k.bias, m.to_v.bias]):
+        if isinstance(m, DiffusersAttentionND):
+            cross = getattr(m, "context_dim", None) is not None   # cross-attention: only K | V are one matrix
+            wts = [m.to_k.weight, m.to_v.weight] if cross else [m.to_q.weight, m.to_k.weight, m.to_v.weight]
+            bss = [m.to_k.bias, m.to_v.bias] if cross else [m.to_q.bias, m.to_k.bias, m.to_v.bias]
+            for plist in (wts, bss):
                 if all(q is not None and q.requires_grad and id(q) not in taken for q in plist):
                     for q in plist:
                         trios[id(q)] = plist
@@ -231,11 +243,36 @@ def resblock(blk, x: torch.Tensor, emb) -> torch.Tensor:
     return F.conv([h] + xs, segs, bias=bias)
 
 
-def attention(att, x: torch.Tensor) -> torch.Tensor:
-    """`attention.py:220-274` (self-attention)."""
+def cross_attention(att, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+    """`attention.py:232-274` with `context_dim`: q from the image tokens, k / v from the normalised context."""
+    from ..nn.blocks.attention import CONTEXT_DIM_MAX, context_tokens
+
     b, c, hh, ww = x.shape
-    if att.context_dim is not None or att.head_dim not in (8, 16, 32, 64) or att.dropout > 0:
-        out_of_scope("training DiffusersAttentionND (cross-attention / dropout / head_dim)")
+    if context is None:
+        raise ValueError("DiffusersAttentionND cross-attention requires a non-empty context tensor.")
+    if att.head_dim != 8 or att.context_dim > CONTEXT_DIM_MAX or att.dropout > 0:
+        out_of_scope("training DiffusersAttentionND cross-attention (head_dim != 8 / context_dim > 16 / dropout)")
+    n = _gn(att.group_norm, x, silu=False)
+    q = F.conv([n], [(att.to_q.weight, 0, c)], bias=att.to_q.bias)
+    wkv = F.fused_param([att.to_k.weight, att.to_v.weight])
+    bkv = F.fused_param([att.to_k.bias, att.to_v.bias]) if wkv is not None else None
+    if wkv is None or bkv is None:
+        wkv = torch.cat([att.to_k.weight, att.to_v.weight], 0)
+        bkv = torch.cat([att.to_k.bias, att.to_v.bias], 0)
+    cn = att.context_norm
+    kv = F.context_kv(context_tokens(context, att.context_dim), cn.weight, cn.bias, wkv, bkv, groups=cn.num_groups,
+                      eps=cn.eps)
+    a = F.cross_attention(q, kv, att.heads)
+    return F.conv([a], [(att.to_out[0].weight, 0, c)], bias=att.to_out[0].bias, residual=x)
+
+
+def attention(att, x: torch.Tensor, context=None) -> torch.Tensor:
+    """`attention.py:220-274` (self-attention; with `context_dim`: cross-attention over `context`)."""
+    b, c, hh, ww = x.shape
+    if att.context_dim is not None:
+        return cross_attention(att, x, context)
+    if att.head_dim not in (8, 16, 32, 64) or att.dropout > 0:
+        out_of_scope("training DiffusersAttentionND (dropout / head_dim)")
         raise RuntimeError("fmdm_b200.training: unsupported attention variant")
     gn = att.group_norm
     n = _gn(gn, x, silu=False)
@@ -341,7 +378,7 @@ def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Ten
     return F.conv_head(h, head.weight, head.bias)
 
 
-def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
+def unet_forward(model, x: torch.Tensor, t, context=None, context_ca=None) -> torch.Tensor:
     """`UNetDiffusersND.forward` / `EfficientUNetND.forward` with autograd: returns the fp32 NCHW prediction."""
     from ..models.unet.unet import EfficientUNetND
     from .packplan import PackPlan
@@ -392,7 +429,7 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
         for i, res in enumerate(block.resnets):
             sample = resblock(res, sample, emb)
             if block.attentions is not None:
-                sample = attention(block.attentions[i], sample)
+                sample = attention(block.attentions[i], sample, context_ca)
             skips.append(sample)
         if block.downsamplers is not None:
             for d in block.downsamplers:
@@ -402,14 +439,14 @@ def unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
     if mid is not None:
         sample = resblock(mid.resnets[0], sample, emb)
         if mid.attentions is not None:
-            sample = attention(mid.attentions[0], sample)
+            sample = attention(mid.attentions[0], sample, context_ca)
         sample = resblock(mid.resnets[1], sample, emb)
     for block in model.up_blocks:
         for i, res in enumerate(block.resnets):
             skip = skips.pop()
             sample = resblock(res, (sample, skip), emb)  # `legacy_unet.py:150`, concat kept virtual
             if block.attentions is not None:
-                sample = attention(block.attentions[i], sample)
+                sample = attention(block.attentions[i], sample, context_ca)
         if block.upsamplers is not None:
             for u in block.upsamplers:
                 sample = upsample(u, sample)

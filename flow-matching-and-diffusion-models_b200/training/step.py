@@ -15,8 +15,21 @@ from .ddp import BucketedAllReduce
 from .optim import FusedAdamW
 
 
+def _forward(model, x, timesteps, ldct, conditioning: str, latent_norm):
+    """`flow_matching_lib.py:154-164` / `diffusion_lib.py:159-170`: "concatenate" hands the conditioning image to the
+    stem (virtual concat); "attention" normalises the conditioning latents and hands them to the cross-attention blocks."""
+    if ldct is None:
+        return model(x, timesteps)
+    if str(conditioning).lower() == "attention":
+        from ..pipelines.utils import normalize_latent_conditioning
+
+        return model(x, timesteps, context_ca=normalize_latent_conditioning(ldct, latent_norm))
+    return model(x, timesteps, context=ldct)
+
+
 def flow_matching_loss(model, clean: torch.Tensor, ldct: Optional[torch.Tensor], *, noise=None, t=None,
-                       num_train_timesteps: int = 1000) -> torch.Tensor:
+                       num_train_timesteps: int = 1000, conditioning: str = "concatenate",
+                       latent_norm: Optional[str] = None) -> torch.Tensor:
     """`flow_matching_lib.py:150-164`: x_t = (1-t) clean + t noise, target = noise - clean, loss = MSE(model(x_t), target).
 
     `noise` / `t` may be passed in (tests, seeded benchmarks); otherwise they are drawn as the reference draws them."""
@@ -27,12 +40,13 @@ def flow_matching_loss(model, clean: torch.Tensor, ldct: Optional[torch.Tensor],
     timesteps = (t * (num_train_timesteps - 1)).long()
     x_t = ops.sched_add_noise(clean.float().contiguous(), noise.float().contiguous(), (1.0 - t).float().contiguous(),
                               t.float().contiguous())
-    pred = model(x_t, timesteps, context=ldct) if ldct is not None else model(x_t, timesteps)
+    pred = _forward(model, x_t, timesteps, ldct, conditioning, latent_norm)
     return F.mse_loss(pred, noise, clean)
 
 
 def diffusion_loss(model, clean: torch.Tensor, ldct: Optional[torch.Tensor], sqrt_ac: torch.Tensor,
-                   sqrt_1m_ac: torch.Tensor, *, noise=None, timesteps=None) -> torch.Tensor:
+                   sqrt_1m_ac: torch.Tensor, *, noise=None, timesteps=None, conditioning: str = "concatenate",
+                   latent_norm: Optional[str] = None) -> torch.Tensor:
     """`diffusion_lib.py:153-171`: timesteps ~ U{0..T-1}, noisy = scheduler.add_noise(clean, noise, timesteps)
     (= sqrt(abar_t) clean + sqrt(1-abar_t) noise), loss = MSE(model(noisy, timesteps), noise).
 
@@ -44,7 +58,7 @@ def diffusion_loss(model, clean: torch.Tensor, ldct: Optional[torch.Tensor], sqr
         timesteps = torch.randint(0, sqrt_ac.numel(), (clean.size(0),), device=clean.device).long()
     noisy = ops.sched_add_noise(clean.float().contiguous(), noise.float().contiguous(),
                                 sqrt_ac[timesteps].contiguous(), sqrt_1m_ac[timesteps].contiguous())
-    pred = model(noisy, timesteps, context=ldct) if ldct is not None else model(noisy, timesteps)
+    pred = _forward(model, noisy, timesteps, ldct, conditioning, latent_norm)
     return F.mse_loss(pred, noise)
 
 
@@ -60,7 +74,8 @@ class FlowMatchingTrainer:
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  grad_accum: int = 1, num_train_timesteps: int = 1000, bucket_bytes: int = 64 << 20, group=None,
                  cuda_graph: bool = True, graph_warmup: int = 2, backward_cut="auto", side_streams: bool = True,
-                 allreduce_max_ctas: Optional[int] = None):
+                 allreduce_max_ctas: Optional[int] = None, conditioning: str = "concatenate",
+                 latent_norm: Optional[str] = None):
         import torch.distributed as dist
 
         from .graph import flat_param_order, supported
@@ -68,6 +83,7 @@ class FlowMatchingTrainer:
         import os
 
         self.model = model
+        self.conditioning, self.latent_norm = str(conditioning), latent_norm    # `training.conditioning` / `.latent_norm`
         self.side_streams = bool(side_streams)
         # a communicator of its own for the gradient all-reduce, capped at a few CTAs: the collective runs beside the
         # second backward stage, where every SM it occupies is taken from the convs (NCCL's default sizes for speed)
@@ -138,7 +154,8 @@ class FlowMatchingTrainer:
 
     def _loss(self, clean, ldct, noise, t) -> torch.Tensor:
         return flow_matching_loss(self.model, clean, ldct, noise=noise, t=t,
-                                  num_train_timesteps=self.num_train_timesteps)
+                                  num_train_timesteps=self.num_train_timesteps, conditioning=self.conditioning,
+                                  latent_norm=self.latent_norm)
 
     def _direct_grads(self):
         """Backward kernels write parameter gradients straight into the flat buffer (`functions.DIRECT_PARAM_GRADS`):
@@ -274,4 +291,5 @@ class DiffusionTrainer(FlowMatchingTrainer):
         self.sqrt_1m_ac = ((1 - ac) ** 0.5).to(dev).contiguous()
 
     def _loss(self, clean, ldct, noise, t) -> torch.Tensor:
-        return diffusion_loss(self.model, clean, ldct, self.sqrt_ac, self.sqrt_1m_ac, noise=noise, timesteps=t)
+        return diffusion_loss(self.model, clean, ldct, self.sqrt_ac, self.sqrt_1m_ac, noise=noise, timesteps=t,
+                              conditioning=self.conditioning, latent_norm=self.latent_norm)

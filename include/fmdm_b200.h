@@ -335,6 +335,19 @@ int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const voi
                           void* dk, void* dv, int32_t B, int32_t heads, int32_t T, int32_t head_dim, int64_t qs_b,
                           int64_t qs_h, int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale,
                           fm_stream_t stream);
+/* head_dim 8 with queries and keys of different length / layout (cross-attention, attention.py:232-274 with
+ * context_dim): q, dq use the q strides; k, v, dk, dv the kv strides; o, dout the o strides (elements). */
+int fm_attention_bwd_cross_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,
+                                void* dk, void* dv, int32_t B, int32_t heads, int32_t Tq, int32_t Tk, int32_t head_dim,
+                                int64_t qs_b, int64_t qs_h, int64_t qs_t, int64_t ks_b, int64_t ks_h, int64_t ks_t,
+                                int64_t os_b, int64_t os_h, int64_t os_t, float scale, fm_stream_t stream);
+/* Backward of fm_context_kv_bf16 (token-major output): dkv bf16 [B][Tc][O]; stats = the (mean, rstd) pairs the forward
+ * wrote; dW fp32 [O][Cc], dbias fp32 [O] (or NULL), dgamma / dbeta fp32 [Cc] of the context GroupNorm.
+ * workspace: fm_context_kv_bwd_workspace_elems floats. */
+int64_t fm_context_kv_bwd_workspace_elems(int32_t B, int32_t Cc, int32_t Tc, int32_t O);
+int fm_context_kv_bwd_f32(const float* ctx, const float* stats, const float* gamma, const float* beta, const float* W,
+                          const void* dkv, float* workspace, float* dW, float* dbias, float* dgamma, float* dbeta,
+                          int32_t B, int32_t Cc, int32_t Tc, int32_t O, int32_t groups, fm_stream_t stream);
 /* Backward of fm_linear_f32 (y = f(x) W^T + b, f = SiLU if silu_in) for B <= 32 rows: dx fp32 [B][I] (or NULL), dw fp32
  * [O][I], db fp32 [O] (or NULL).  workspace: fm_linear_bwd_workspace_elems floats (needed for dx only). */
 int64_t fm_linear_bwd_workspace_elems(int32_t B, int32_t I, int32_t O);

@@ -329,3 +329,50 @@ def test_gradient_slots_fold_residual_and_skip_gradients(F, two_sources):
                           groups=32, eps=1e-5, silu=True)
         assert getattr(leaf, "_fm_slot", None) is None
         hh.backward(gy)
+
+
+@pytest.mark.parametrize("c,heads,hw,tc,b", [(128, 16, 8, 25, 2), (64, 8, 16, 256, 2), (512, 64, 16, 64, 1)])
+def test_cross_attention_backward(F, c, heads, hw, tc, b):
+    """Cross-attention (Tq != Tk, head_dim 8; `attention.py:232-274` with context_dim): forward and the gradients of q
+    and of the K | V buffer against torch SDPA."""
+    torch.manual_seed(8)
+    dev = "cuda"
+    q = nhwc(torch.randn(b, c, hw, hw, device=dev)).requires_grad_(True)
+    kv = torch.randn(b, tc, 2 * c, device=dev).to(torch.bfloat16).requires_grad_(True)
+    gy = nhwc(torch.randn(b, c, hw, hw, device=dev))
+    y = F.cross_attention(q, kv, heads)
+    y.backward(gy)
+    t, hd = hw * hw, c // heads
+    qr = q.detach().float().requires_grad_(True)
+    kvr = kv.detach().float().requires_grad_(True)
+    qh = qr.permute(0, 2, 3, 1).reshape(b, t, heads, hd).transpose(1, 2)
+    kh = kvr[:, :, :c].reshape(b, tc, heads, hd).transpose(1, 2)
+    vh = kvr[:, :, c:].reshape(b, tc, heads, hd).transpose(1, 2)
+    o = TF.scaled_dot_product_attention(qh, kh, vh)
+    yr = o.transpose(1, 2).reshape(b, hw, hw, c).permute(0, 3, 1, 2)
+    yr.backward(gy.float())
+    assert rel_l2(y, yr) < 1e-2
+    assert rel_l2(q.grad, qr.grad) < 2e-2 and rel_l2(kv.grad, kvr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("cc,groups,tc,o,b", [(4, 4, 64, 256, 2), (8, 8, 50, 128, 3), (16, 16, 256, 1024, 2)])
+def test_context_kv_backward(F, cc, groups, tc, o, b):
+    """The cross-attention context path (GroupNorm over the context tokens + K | V projection): gradients of the
+    projection and of the context GroupNorm's affine against torch autograd (the context itself is data)."""
+    torch.manual_seed(9)
+    dev = "cuda"
+    tokens = torch.randn(b, cc, tc, device=dev) * 1.5 + 0.2
+    gamma = (torch.rand(cc, device=dev) + 0.5).requires_grad_(True)
+    beta = (torch.randn(cc, device=dev) * 0.3).requires_grad_(True)
+    w = (torch.randn(o, cc, device=dev) * 0.3).requires_grad_(True)
+    bias = torch.randn(o, device=dev, requires_grad=True)
+    gy = torch.randn(b, tc, o, device=dev).to(torch.bfloat16)
+    kv = F.context_kv(tokens, gamma, beta, w, bias, groups=groups, eps=1e-5)
+    kv.backward(gy)
+    gr, br, wr, bir = [z.detach().clone().requires_grad_(True) for z in (gamma, beta, w, bias)]
+    n = TF.group_norm(tokens, groups, gr, br, 1e-5)                         # (b, cc, tc)
+    ref = torch.einsum("oc,bct->bto", wr, n) + bir
+    ref.backward(gy.float())
+    assert rel_l2(kv, ref) < 1e-2
+    for got, want in ((w.grad, wr.grad), (bias.grad, bir.grad), (gamma.grad, gr.grad), (beta.grad, br.grad)):
+        assert rel_l2(got, want) < 1e-4

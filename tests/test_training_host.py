@@ -19,7 +19,12 @@ def test_which_variants_have_a_training_path():
     assert graph.supported(f.build({"in_channels": 1, "out_channels": 1, "num_res_blocks": 1, "channel_mult": [1, 2],
                                     "model_channels": 32, "attention_resolutions": []}, "concatenate", 1))
     ca = dict(SMALL, cross_attention_dim=4, down_block_types=["DownBlock2D", "CrossAttnDownBlock2D"])
-    assert not graph.supported(f.build(ca, "attention", 1))          # cross-attention: inference only
+    assert graph.supported(f.build(ca, "attention", 1))              # cross-attention trains at head_dim 8
+    assert not graph.supported(f.build(dict(ca, attention_head_dim=16), "attention", 1))
+    ce = {"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1, "num_res_blocks": 1, "channel_mult": [1, 2],
+          "model_channels": 64, "attention_resolutions": [2], "cross_attention_resolutions": [2],
+          "cross_attention_in_middle": True, "cross_attention_dim": 4}
+    assert not graph.supported(f.build(ce, "attention", 1))          # CompVis cross- / linear attention: inference only
     assert not graph.supported(torch.nn.Linear(2, 2))
 
 

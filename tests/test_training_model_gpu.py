@@ -440,3 +440,69 @@ def test_trainer_with_backward_cut_replays_two_graphs():
     for a, c in zip(losses[None], losses[1]):
         assert abs(a - c) <= 2e-2 * abs(a), (losses[None], losses[1])
     assert sum(losses[1][-3:]) < sum(losses[1][:3])
+
+
+CA_DIFFUSERS = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1, "layers_per_block": 1,
+                "block_out_channels": [64, 128], "cross_attention_dim": 4,
+                "down_block_types": ["DownBlock2D", "CrossAttnDownBlock2D"], "mid_block_type": "UNetMidBlock2DCrossAttn",
+                "up_block_types": ["CrossAttnUpBlock2D", "UpBlock2D"]}
+
+
+@pytest.mark.parametrize("latent_norm", [None, "standardize"])
+def test_attention_conditioned_training_gradients_match_oracle(latent_norm):
+    """`conditioning: "attention"` (`flow_matching_lib.py:159-164`): the conditioning latents reach the denoiser as the
+    cross-attention context; loss and every parameter gradient against torch fp32 autograd through the oracle."""
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+    from fmdm_b200.pipelines.utils import normalize_latent_conditioning
+    from fmdm_b200.training import flow_matching_loss
+
+    model = DiffusionUNetFactory().build(CA_DIFFUSERS, "attention", 1)
+    sd = OD.reinit_state_dict(model.state_dict(), 5)
+    model.load_state_dict(sd)
+    model = model.to(DEV).train()
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(17)
+    b, hw = 3, 32
+    clean = torch.rand(b, 1, hw, hw, generator=g).to(DEV)
+    latents = torch.randn(b, 4, 8, 8, generator=g).to(DEV)
+    noise = torch.randn(b, 1, hw, hw, generator=g).to(DEV)
+    t = torch.rand(b, generator=g).to(DEV)
+    loss = flow_matching_loss(model, clean, latents, noise=noise, t=t, conditioning="attention", latent_norm=latent_norm)
+    loss.backward()
+    params = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    tt = t[:, None, None, None]
+    x_t = (1.0 - tt) * clean + tt * noise
+    pred = OD.denoiser_forward(params, CA_DIFFUSERS, x_t, (t * 999).long(), conditioning="attention", channels=1,
+                               context_ca=normalize_latent_conditioning(latents, latent_norm))
+    ref_loss = TF.mse_loss(pred, noise - clean)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())
+    total = float(torch.cat([p.grad.reshape(-1) for p in params.values() if p.grad is not None]).norm())
+    ga, gb = [], []
+    for k, p in model.named_parameters():
+        r = params[k].grad
+        assert p.grad is not None and r is not None, k
+        assert float((p.grad.float() - r).norm()) / total < 1e-2, (k, float((p.grad.float() - r).norm()) / total)
+        if float(r.norm()) >= 1e-4 * total:
+            assert rel_l2(p.grad, r) < 3.5e-2, (k, rel_l2(p.grad, r))
+        ga.append(p.grad.float().reshape(-1))
+        gb.append(r.reshape(-1))
+    assert rel_l2(torch.cat(ga), torch.cat(gb)) < 2e-2
+    assert any("to_k" in k or "context_norm" in k for k, _ in model.named_parameters())
+
+
+def test_attention_conditioned_trainer_steps():
+    """FlowMatchingTrainer(conditioning="attention"): graph-replayed steps on a fixed batch reduce the loss."""
+    from fmdm_b200.models.generators import DiffusionUNetFactory
+    from fmdm_b200.training import FlowMatchingTrainer
+
+    model = DiffusionUNetFactory().build(CA_DIFFUSERS, "attention", 1)
+    model.load_state_dict(OD.reinit_state_dict(model.state_dict(), 6))
+    model = model.to(DEV).train()
+    tr = FlowMatchingTrainer(model, lr=3e-4, conditioning="attention", latent_norm="standardize", backward_cut=1)
+    g = torch.Generator().manual_seed(3)
+    clean = torch.rand(8, 1, 32, 32, generator=g).to(DEV)
+    latents = torch.randn(8, 4, 8, 8, generator=g).to(DEV)
+    losses = [float(tr.step(clean, latents)) for _ in range(12)]
+    assert tr._graph is not None and tr._graph2 is not None
+    assert all(torch.isfinite(torch.tensor(losses))) and sum(losses[-3:]) < sum(losses[:3])
