@@ -139,6 +139,8 @@ SIGNATURES = {
     "fm_colsum_finish_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fm_attention_bwd_cross_bf16": (
         C.c_int, [_vp] * 8 + [_i32, _i32, _i32, _i32, _i32] + [_i64] * 9 + [_f32, _vp]),
+    "fm_linear_attention_bwd_bf16": (
+        C.c_int, [_vp] * 7 + [_i32, _i32, _i32, _i32, _i32] + [_i64] * 9 + [_f32, _vp]),
     "fm_context_kv_bwd_workspace_elems": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "fm_context_kv_bwd_f32": (C.c_int, [_vp] * 11 + [_i32, _i32, _i32, _i32, _i32, _vp]),
     "fm_attention_bwd_bf16": (

@@ -1011,28 +1011,33 @@ template <int HD, typename ST>
 __global__ void __launch_bounds__(256) attention_bwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dq,
-    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int heads, int T, int64_t qs_b, int64_t qs_h,
-    int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale) {
+    __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int heads, int Tq, int Tk, int64_t qs_b,
+    int64_t qs_h, int64_t qs_t, int64_t ks_b, int64_t ks_h, int64_t ks_t, int64_t os_b, int64_t os_h, int64_t os_t,
+    float scale) {
+  // Tq query rows (q, dq, o, dout) and Tk key rows (k, v, dk, dv): equal for self-attention
   extern __shared__ __align__(16) uint8_t smem_att[];
   ST* sq = reinterpret_cast<ST*>(smem_att);
-  ST* sk = sq + (size_t)T * HD;
-  ST* sv = sk + (size_t)T * HD;
-  ST* sdo = sv + (size_t)T * HD;
-  float* lse = reinterpret_cast<float*>(sdo + (size_t)T * HD);
-  float* dsum = lse + T;
+  ST* sdo = sq + (size_t)Tq * HD;
+  ST* sk = sdo + (size_t)Tq * HD;
+  ST* sv = sk + (size_t)Tk * HD;
+  float* lse = reinterpret_cast<float*>(sv + (size_t)Tk * HD);
+  float* dsum = lse + Tq;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int64_t qoff = b * qs_b + h * qs_h, ooff = b * os_b + h * os_h;
+  const int64_t qoff = b * qs_b + h * qs_h, koff = b * ks_b + h * ks_h, ooff = b * os_b + h * os_h;
   // rows of HD contiguous bf16 (16-byte aligned by the caller's strides)
-  for (int idx = threadIdx.x; idx < T * (HD / 8); idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < Tq * (HD / 8); idx += blockDim.x) {
     const int t = idx / (HD / 8), c = idx - t * (HD / 8);
     att_stage8(sq + idx * 8, q + qoff + t * qs_t + c * 8);
-    att_stage8(sk + idx * 8, k + qoff + t * qs_t + c * 8);
-    att_stage8(sv + idx * 8, v + qoff + t * qs_t + c * 8);
     att_stage8(sdo + idx * 8, dout + ooff + t * os_t + c * 8);
+  }
+  for (int idx = threadIdx.x; idx < Tk * (HD / 8); idx += blockDim.x) {
+    const int t = idx / (HD / 8), c = idx - t * (HD / 8);
+    att_stage8(sk + idx * 8, k + koff + t * ks_t + c * 8);
+    att_stage8(sv + idx * 8, v + koff + t * ks_t + c * 8);
   }
   __syncthreads();
   // phase 1+2: per query row i: log-sum-exp, D_i = dO_i . O_i, then dQ_i
-  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+  for (int i = threadIdx.x; i < Tq; i += blockDim.x) {
     float qi[HD], doi[HD], tmp[HD];
     att_row<HD>(sq + i * HD, qi);
     att_row<HD>(sdo + i * HD, doi);
@@ -1051,7 +1056,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
 #pragma unroll
     for (int d = 0; d < HD; ++d) qi[d] *= scale;
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < T; ++j) {
+    for (int j = 0; j < Tk; ++j) {
       att_row<HD>(sk + j * HD, tmp);
       float s = 0.f;
 #pragma unroll
@@ -1066,7 +1071,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
     float acc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-    for (int j = 0; j < T; ++j) {
+    for (int j = 0; j < Tk; ++j) {
       float kj[HD];
       att_row<HD>(sk + j * HD, kj);
       att_row<HD>(sv + j * HD, tmp);
@@ -1088,7 +1093,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
   }
   __syncthreads();
   // phase 3: per key row j: dK_j, dV_j
-  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
     float kj[HD], vj[HD], ak[HD], av[HD];
     att_row<HD>(sk + j * HD, kj);
     att_row<HD>(sv + j * HD, vj);
@@ -1098,7 +1103,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
       ak[d] = 0.f;
       av[d] = 0.f;
     }
-    for (int i = 0; i < T; ++i) {
+    for (int i = 0; i < Tq; ++i) {
       float qi[HD], doi[HD];
       att_row<HD>(sq + i * HD, qi);
       att_row<HD>(sdo + i * HD, doi);
@@ -1118,10 +1123,10 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
     }
 #pragma unroll
     for (int c = 0; c < HD / 8; ++c) {
-      *reinterpret_cast<uint4*>(dk + qoff + j * qs_t + c * 8) =
+      *reinterpret_cast<uint4*>(dk + koff + j * ks_t + c * 8) =
           make_uint4(pack_bf16x2(ak[c * 8], ak[c * 8 + 1]), pack_bf16x2(ak[c * 8 + 2], ak[c * 8 + 3]),
                      pack_bf16x2(ak[c * 8 + 4], ak[c * 8 + 5]), pack_bf16x2(ak[c * 8 + 6], ak[c * 8 + 7]));
-      *reinterpret_cast<uint4*>(dv + qoff + j * qs_t + c * 8) =
+      *reinterpret_cast<uint4*>(dv + koff + j * ks_t + c * 8) =
           make_uint4(pack_bf16x2(av[c * 8], av[c * 8 + 1]), pack_bf16x2(av[c * 8 + 2], av[c * 8 + 3]),
                      pack_bf16x2(av[c * 8 + 4], av[c * 8 + 5]), pack_bf16x2(av[c * 8 + 6], av[c * 8 + 7]));
     }
@@ -1857,64 +1862,19 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
   return 0;
 }
 
-/* head_dim 8, queries and keys of different length / layout (cross-attention): q, dq use the q strides; k, v, dk, dv the
- * kv strides; o, dout the o strides.  FM_ERR_UNSUPPORTED if the staged tiles exceed shared memory. */
-extern "C" int fm_attention_bwd_cross_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout,
-                                           void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t Tq,
-                                           int32_t Tk, int32_t head_dim, int64_t qs_b, int64_t qs_h, int64_t qs_t,
-                                           int64_t ks_b, int64_t ks_h, int64_t ks_t, int64_t os_b, int64_t os_h,
-                                           int64_t os_t, float scale, fm_stream_t stream) {
-  if (int e = ensure_device()) return e;
-  FM_REQUIRE(q && k && v && o && dout && dq && dk && dv && Tq > 0 && Tk > 0, "attention_bwd_cross: bad argument");
-  FM_REQUIRE(head_dim == 8, "attention_bwd_cross: head_dim %d unsupported (8)", head_dim);
-  FM_REQUIRE(((qs_b | qs_h | qs_t | ks_b | ks_h | ks_t | os_b | os_h | os_t) % 8) == 0 &&
-                 (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq |
-                   (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
-             "attention_bwd_cross: rows must be 16-byte aligned (strides multiples of 8 elements)");
-  const int Tqp = (Tq + 15) & ~15, Tkp = (Tk + 15) & ~15;
-  const size_t need = (size_t)(Tqp + Tkp) * 8 * 2 * 2 + (size_t)8 * (Tkp + kAttB8Pad) * 2 +
-                      (size_t)2 * 8 * (Tqp + kAttB8Pad) * 2 + (size_t)2 * Tqp * 4;
-  if (need > 200 * 1024) {
-    set_error("attention_bwd_cross: Tq=%d Tk=%d exceed the shared-memory staging budget", Tq, Tk);
-    return FM_ERR_UNSUPPORTED;
-  }
-  static size_t attr8 = 48 * 1024;
-  if (need > attr8) {
-    if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_hd8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)need), "attention_bwd_hd8 attr")) return e;
-    attr8 = need;
-  }
-  attention_bwd_hd8_mma_kernel<<<B * heads, 256, need, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,
-      (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, Tq, Tqp, Tk, Tkp,
-      qs_b, qs_h, qs_t, ks_b, ks_h, ks_t, os_b, os_h, os_t, scale);
-  FM_LAUNCH_CHECK("attention_bwd_hd8_mma_kernel");
-  return 0;
-}
-
-extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout,
-                                     void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t T,
-                                     int32_t head_dim, int64_t qs_b, int64_t qs_h, int64_t qs_t, int64_t os_b,
-                                     int64_t os_h, int64_t os_t, float scale, fm_stream_t stream) {
-  if (int e = ensure_device()) return e;
-  FM_REQUIRE(q && k && v && o && dout && dq && dk && dv, "attention_bwd: null pointer");
-  FM_REQUIRE(((qs_b | qs_h | qs_t | os_b | os_h | os_t) % 8) == 0 &&
-                 (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq |
-                   (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
-             "attention_bwd: rows must be 16-byte aligned (strides multiples of 8 elements)");
-  cudaStream_t st = (cudaStream_t)stream;
-  static const bool scalar8 = getenv("FMDM_ATTENTION_BWD_SCALAR") != nullptr;  // A/B: the CUDA-core kernel at head_dim 8
-  if (head_dim == 8 && !scalar8) {
-    const int rc = fm_attention_bwd_cross_bf16(q, k, v, o, dout, dq, dk, dv, B, heads, T, T, 8, qs_b, qs_h, qs_t, qs_b,
-                                               qs_h, qs_t, os_b, os_h, os_t, scale, stream);
-    if (rc != FM_ERR_UNSUPPORTED) return rc;
-  }
+/* Attention backward with queries and keys of their own length / layout (cross-attention; self-attention is the
+ * special case fm_attention_bwd_bf16 forwards here): q, dq use the q strides; k, v, dk, dv the kv strides; o, dout the
+ * o strides.  head_dim 8: the mma.sync kernel; 16 / 32 / 64: the CUDA-core kernel. */
+static int attention_bwd_scalar(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,
+                                void* dk, void* dv, int B, int heads, int Tq, int Tk, int head_dim, int64_t qs_b,
+                                int64_t qs_h, int64_t qs_t, int64_t ks_b, int64_t ks_h, int64_t ks_t, int64_t os_b,
+                                int64_t os_h, int64_t os_t, float scale, cudaStream_t st) {
   // fp32 staging (no unpacking in the T^2 loops) when the four tiles fit in 96 KB, else bf16 staging
-  const size_t tiles = (size_t)4 * T * head_dim;
-  const bool f32 = tiles * 4 + (size_t)2 * T * 4 <= 96 * 1024;
-  const size_t smem = tiles * (f32 ? 4 : 2) + (size_t)2 * T * 4;
+  const size_t tiles = (size_t)2 * (Tq + Tk) * head_dim;
+  const bool f32 = tiles * 4 + (size_t)2 * Tq * 4 <= 96 * 1024;
+  const size_t smem = tiles * (f32 ? 4 : 2) + (size_t)2 * Tq * 4;
   if (smem > 200 * 1024) {
-    set_error("attention_bwd: T=%d head_dim=%d exceeds the shared-memory staging budget", T, head_dim);
+    set_error("attention_bwd: Tq=%d Tk=%d head_dim=%d exceed the shared-memory staging budget", Tq, Tk, head_dim);
     return FM_ERR_UNSUPPORTED;
   }
 #define FM_ATT_BWD_ST(HD, ST)                                                                                       \
@@ -1928,8 +1888,8 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
     }                                                                                                               \
     attention_bwd_kernel<HD, ST><<<B * heads, 256, smem, st>>>(                                                     \
         (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,         \
-        (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, T, qs_b, qs_h, \
-        qs_t, os_b, os_h, os_t, scale);                                                                             \
+        (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, Tq, Tk, qs_b, \
+        qs_h, qs_t, ks_b, ks_h, ks_t, os_b, os_h, os_t, scale);                                                     \
   }
 #define FM_ATT_BWD(HD)                                  \
   case HD:                                              \
@@ -1949,6 +1909,297 @@ extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v
 #undef FM_ATT_BWD
   FM_LAUNCH_CHECK("attention_bwd_kernel");
   return 0;
+}
+
+extern "C" int fm_attention_bwd_cross_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                                           void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t Tq,
+                                           int32_t Tk, int32_t head_dim, int64_t qs_b, int64_t qs_h, int64_t qs_t,
+                                           int64_t ks_b, int64_t ks_h, int64_t ks_t, int64_t os_b, int64_t os_h,
+                                           int64_t os_t, float scale, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(q && k && v && o && dout && dq && dk && dv && Tq > 0 && Tk > 0, "attention_bwd: bad argument");
+  FM_REQUIRE(((qs_b | qs_h | qs_t | ks_b | ks_h | ks_t | os_b | os_h | os_t) % 8) == 0 &&
+                 (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq |
+                   (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+             "attention_bwd: rows must be 16-byte aligned (strides multiples of 8 elements)");
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool scalar8 = getenv("FMDM_ATTENTION_BWD_SCALAR") != nullptr;  // A/B: the CUDA-core kernel at head_dim 8
+  if (head_dim == 8 && !scalar8) {
+    const int Tqp = (Tq + 15) & ~15, Tkp = (Tk + 15) & ~15;
+    const size_t need = (size_t)(Tqp + Tkp) * 8 * 2 * 2 + (size_t)8 * (Tkp + kAttB8Pad) * 2 +
+                        (size_t)2 * 8 * (Tqp + kAttB8Pad) * 2 + (size_t)2 * Tqp * 4;
+    if (need <= 200 * 1024) {
+      static size_t attr8 = 48 * 1024;
+      if (need > attr8) {
+        if (int e = check_cuda(cudaFuncSetAttribute(attention_bwd_hd8_mma_kernel,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need),
+                               "attention_bwd_hd8 attr")) return e;
+        attr8 = need;
+      }
+      attention_bwd_hd8_mma_kernel<<<B * heads, 256, need, st>>>(
+          (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)o,
+          (const __nv_bfloat16*)dout, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, Tq, Tqp, Tk, Tkp,
+          qs_b, qs_h, qs_t, ks_b, ks_h, ks_t, os_b, os_h, os_t, scale);
+      FM_LAUNCH_CHECK("attention_bwd_hd8_mma_kernel");
+      return 0;
+    }
+  }
+  return attention_bwd_scalar(q, k, v, o, dout, dq, dk, dv, B, heads, Tq, Tk, head_dim, qs_b, qs_h, qs_t, ks_b, ks_h,
+                              ks_t, os_b, os_h, os_t, scale, st);
+}
+
+// =============================================================================================================
+// Linear attention backward (`attention.py:53-70` LinearQKVAttention; forward: fm_linear_attention_bf16):
+//   ks = softmax_tokens(k), qs = softmax_features(q), ctx = ks^T v / (sum_n ks + eps), out = qs ctx.
+//   dctx = qs^T dout;  dqs = dout ctx^T;  dA = dctx / den;  dks = v dA^T;  dv = ks dA;
+//   dq = qs * (dqs - rowsum(qs * dqs));  dk = ks * (dks - colsum(ks * dks))
+// (the denominator's own gradient is a per-column constant added to dks, which the column softmax's backward cancels
+// exactly because sum_n ks = 1).  O(T d^2) fp32 CUDA-core math, one CTA per (sample, head), d x d matrices in shared
+// memory, every sum in a fixed order.
+// =============================================================================================================
+template <int HD>
+__global__ void __launch_bounds__(256) linear_attention_bwd_kernel(
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+    const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dq, __nv_bfloat16* __restrict__ dk,
+    __nv_bfloat16* __restrict__ dv, int heads, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st,
+    int64_t kv_sb, int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float eps) {
+  constexpr int kLanes = 256 / HD;   // token lanes per feature column
+  constexpr int kChunk = HD == 64 ? 16 : 32;   // tokens staged per step (static shared memory stays under 48 KB)
+  constexpr int kPairs = HD * HD / 256 > 0 ? HD * HD / 256 : 1;
+  __shared__ float ctx[HD][HD + 1], dA[HD][HD + 1];
+  __shared__ float red[256];
+  __shared__ float cmax[HD], csum[HD], cden[HD], cS[HD];
+  __shared__ float sa[kChunk][HD + 1], sb[kChunk][HD + 1], sc[kChunk][HD + 1];
+  __shared__ float rstat[kChunk];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const __nv_bfloat16* kb = k + b * kv_sb + h * kv_sh;
+  const __nv_bfloat16* vb = v + b * kv_sb + h * kv_sh;
+  const __nv_bfloat16* qb = q + b * q_sb + h * q_sh;
+  const __nv_bfloat16* gb = dout + b * o_sb + h * o_sh;
+  __nv_bfloat16* dqb = dq + b * q_sb + h * q_sh;
+  __nv_bfloat16* dkb = dk + b * kv_sb + h * kv_sh;
+  __nv_bfloat16* dvb = dv + b * kv_sb + h * kv_sh;
+  const int d = threadIdx.x % HD, lane = threadIdx.x / HD;
+
+  // ---- column softmax statistics of k ----
+  float m = -INFINITY;
+  for (int n = lane; n < Tk; n += kLanes) m = fmaxf(m, __bfloat162float(kb[n * kv_st + d]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < kLanes; ++l) m = fmaxf(m, red[l * HD + d]);
+    cmax[d] = m;
+  }
+  __syncthreads();
+  float s = 0.f;
+  const float cm = cmax[d];
+  for (int n = lane; n < Tk; n += kLanes) s += __expf(__bfloat162float(kb[n * kv_st + d]) - cm);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < kLanes; ++l) s += red[l * HD + d];
+    csum[d] = s;
+  }
+  __syncthreads();
+
+  // ---- forward context: ctx[d][e] = sum_n ks[n][d] v[n][e] / (sum_n ks[n][d] + eps) ----
+  float acc[kPairs];
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) acc[j] = 0.f;
+  float den = 0.f;
+  for (int n0 = 0; n0 < Tk; n0 += kChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk * HD; i += 256) {
+      const int nn = i / HD, dd = i - nn * HD;
+      float kv_ = 0.f, vv = 0.f;
+      if (n0 + nn < Tk) {
+        kv_ = __expf(__bfloat162float(kb[(n0 + nn) * kv_st + dd]) - cmax[dd]) / csum[dd];
+        vv = __bfloat162float(vb[(n0 + nn) * kv_st + dd]);
+      }
+      sa[nn][dd] = kv_;
+      sb[nn][dd] = vv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) {
+      const int p = threadIdx.x + 256 * j;
+      if (p < HD * HD) {
+        const int dd = p / HD, ee = p - dd * HD;
+        float a = acc[j];
+#pragma unroll 8
+        for (int nn = 0; nn < kChunk; ++nn) a = fmaf(sa[nn][dd], sb[nn][ee], a);
+        acc[j] = a;
+      }
+    }
+    if (threadIdx.x < HD)
+      for (int nn = 0; nn < kChunk; ++nn) den += sa[nn][threadIdx.x];
+  }
+  if (threadIdx.x < HD) cden[threadIdx.x] = den + eps;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) {
+    const int p = threadIdx.x + 256 * j;
+    if (p < HD * HD) {
+      const int dd = p / HD, ee = p - dd * HD;
+      ctx[dd][ee] = acc[j] / cden[dd];
+      acc[j] = 0.f;  // re-used for dctx
+    }
+  }
+  __syncthreads();
+
+  // ---- queries: dctx += qs^T dout;  dq = qs * (dout ctx^T - rowsum) ----
+  for (int n0 = 0; n0 < Tq; n0 += kChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk * HD; i += 256) {
+      const int nn = i / HD, dd = i - nn * HD;
+      const bool in = n0 + nn < Tq;
+      sa[nn][dd] = in ? __bfloat162float(qb[(n0 + nn) * q_st + dd]) : 0.f;   // raw q, normalised below
+      sb[nn][dd] = in ? __bfloat162float(gb[(n0 + nn) * o_st + dd]) : 0.f;   // dout
+    }
+    __syncthreads();
+    if (threadIdx.x < kChunk) {  // row softmax of q over the HD features (fixed order)
+      const int nn = threadIdx.x;
+      float mx = -INFINITY, sm = 0.f;
+      for (int dd = 0; dd < HD; ++dd) mx = fmaxf(mx, sa[nn][dd]);
+      for (int dd = 0; dd < HD; ++dd) sm += __expf(sa[nn][dd] - mx);
+      const float inv = (n0 + nn < Tq) ? 1.f / sm : 0.f;
+      for (int dd = 0; dd < HD; ++dd) sa[nn][dd] = __expf(sa[nn][dd] - mx) * inv;   // qs (zero rows past Tq)
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPairs; ++j) {
+      const int p = threadIdx.x + 256 * j;
+      if (p < HD * HD) {
+        const int dd = p / HD, ee = p - dd * HD;
+        float a = acc[j];
+#pragma unroll 8
+        for (int nn = 0; nn < kChunk; ++nn) a = fmaf(sa[nn][dd], sb[nn][ee], a);
+        acc[j] = a;
+      }
+    }
+    // dqs[nn][d] = sum_e dout[nn][e] ctx[d][e]
+    for (int nn = lane; nn < kChunk; nn += kLanes) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int ee = 0; ee < HD; ++ee) a = fmaf(sb[nn][ee], ctx[d][ee], a);
+      sc[nn][d] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < kChunk) {
+      const int nn = threadIdx.x;
+      float dot = 0.f;
+      for (int dd = 0; dd < HD; ++dd) dot = fmaf(sa[nn][dd], sc[nn][dd], dot);
+      rstat[nn] = dot;
+    }
+    __syncthreads();
+    for (int nn = lane; nn < kChunk; nn += kLanes)
+      if (n0 + nn < Tq) dqb[(n0 + nn) * q_st + d] = __float2bfloat16_rn(sa[nn][d] * (sc[nn][d] - rstat[nn]));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) {
+    const int p = threadIdx.x + 256 * j;
+    if (p < HD * HD) {
+      const int dd = p / HD, ee = p - dd * HD;
+      dA[dd][ee] = acc[j] / cden[dd];
+    }
+  }
+  __syncthreads();
+
+  // ---- keys, pass a: S[d] = sum_n ks[n][d] dks[n][d],  dks[n][d] = sum_e v[n][e] dA[d][e];  dv = ks dA ----
+  float sp = 0.f;
+  for (int n0 = 0; n0 < Tk; n0 += kChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk * HD; i += 256) {
+      const int nn = i / HD, dd = i - nn * HD;
+      float kv_ = 0.f, vv = 0.f;
+      if (n0 + nn < Tk) {
+        kv_ = __expf(__bfloat162float(kb[(n0 + nn) * kv_st + dd]) - cmax[dd]) / csum[dd];
+        vv = __bfloat162float(vb[(n0 + nn) * kv_st + dd]);
+      }
+      sa[nn][dd] = kv_;
+      sb[nn][dd] = vv;
+    }
+    __syncthreads();
+    for (int nn = lane; nn < kChunk; nn += kLanes) {
+      float a = 0.f, dvv = 0.f;
+#pragma unroll 8
+      for (int ee = 0; ee < HD; ++ee) {
+        a = fmaf(sb[nn][ee], dA[d][ee], a);       // dks[nn][d]
+        dvv = fmaf(sa[nn][ee], dA[ee][d], dvv);   // dv[nn][d] = sum_e ks[nn][e] dA[e][d]
+      }
+      sc[nn][d] = a;
+      sp = fmaf(sa[nn][d], a, sp);
+      if (n0 + nn < Tk) dvb[(n0 + nn) * kv_st + d] = __float2bfloat16_rn(dvv);
+    }
+  }
+  red[threadIdx.x] = sp;
+  __syncthreads();
+  if (lane == 0) {
+    float t = 0.f;
+    for (int l = 0; l < kLanes; ++l) t += red[l * HD + d];
+    cS[d] = t;
+  }
+  __syncthreads();
+  // ---- keys, pass b: dk = ks * (dks - S) ----
+  for (int n0 = 0; n0 < Tk; n0 += kChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk * HD; i += 256) {
+      const int nn = i / HD, dd = i - nn * HD;
+      float kv_ = 0.f, vv = 0.f;
+      if (n0 + nn < Tk) {
+        kv_ = __expf(__bfloat162float(kb[(n0 + nn) * kv_st + dd]) - cmax[dd]) / csum[dd];
+        vv = __bfloat162float(vb[(n0 + nn) * kv_st + dd]);
+      }
+      sa[nn][dd] = kv_;
+      sb[nn][dd] = vv;
+    }
+    __syncthreads();
+    for (int nn = lane; nn < kChunk; nn += kLanes) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int ee = 0; ee < HD; ++ee) a = fmaf(sb[nn][ee], dA[d][ee], a);
+      if (n0 + nn < Tk) dkb[(n0 + nn) * kv_st + d] = __float2bfloat16_rn(sa[nn][d] * (a - cS[d]));
+    }
+  }
+}
+
+extern "C" int fm_linear_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* dout, void* dq,
+                                            void* dk, void* dv, int32_t B, int32_t heads, int32_t Tq, int32_t Tk,
+                                            int32_t head_dim, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
+                                            int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st,
+                                            float eps, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(q && k && v && dout && dq && dk && dv && B > 0 && heads > 0 && Tq > 0 && Tk > 0,
+             "linear_attention_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+#define FM_LINB(HD)                                                                                                  \
+  case HD:                                                                                                          \
+    linear_attention_bwd_kernel<HD><<<B * heads, 256, 0, st>>>(                                                     \
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)dout,      \
+        (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, heads, Tq, Tk, q_sb, q_sh, q_st, kv_sb, kv_sh,  \
+        kv_st, o_sb, o_sh, o_st, eps);                                                                              \
+    break;
+  switch (head_dim) {
+    FM_LINB(8)
+    FM_LINB(16)
+    FM_LINB(32)
+    FM_LINB(64)
+    default:
+      set_error("linear_attention_bwd: head_dim=%d unsupported (8, 16, 32, 64)", head_dim);
+      return FM_ERR_UNSUPPORTED;
+  }
+#undef FM_LINB
+  FM_LAUNCH_CHECK("linear_attention_bwd_kernel");
+  return 0;
+}
+
+extern "C" int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                                     void* dq, void* dk, void* dv, int32_t B, int32_t heads, int32_t T,
+                                     int32_t head_dim, int64_t qs_b, int64_t qs_h, int64_t qs_t, int64_t os_b,
+                                     int64_t os_h, int64_t os_t, float scale, fm_stream_t stream) {
+  return fm_attention_bwd_cross_bf16(q, k, v, o, dout, dq, dk, dv, B, heads, T, T, head_dim, qs_b, qs_h, qs_t, qs_b,
+                                     qs_h, qs_t, os_b, os_h, os_t, scale, stream);
 }
 
 extern "C" int fm_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, fm_stream_t stream) {

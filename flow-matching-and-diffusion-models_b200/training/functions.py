@@ -747,45 +747,105 @@ def context_kv(tokens, gamma, beta, weight, bias, *, groups: int, eps: float) ->
     return _ContextKVFn.apply(tokens, gamma, beta, weight, bias, int(groups), float(eps))
 
 
+LINEAR_ATTENTION_EPS = 1e-6   # LinearQKVAttention's default (`attention.py:58`)
+
+
 class _AttentionRawFn(Function):
     """SpatialSelfAttention's raw-reshape head split (`attention.py:111-115`): the channel-major (b, 3*inner, T) qkv
-    buffer re-read as (b, heads, T, 3*dh); returns (b, heads, T, dh) contiguous."""
+    buffer re-read as (b, heads, T, 3*dh); returns (b, heads, T, dh) contiguous.  `linear`: LinearQKVAttention."""
 
     @staticmethod
-    def forward(ctx, qkv_cm, heads, dh):
+    def forward(ctx, qkv_cm, heads, dh, linear):
         assert qkv_cm.dtype == BF16 and qkv_cm.is_contiguous() and qkv_cm.dim() == 3
         b, c3, t = qkv_cm.shape
         inner = heads * dh
         assert c3 == 3 * inner
         att = torch.empty((b, heads, t, dh), dtype=BF16, device=qkv_cm.device)
         flat = qkv_cm.view(-1)
-        ops.attention(flat, flat[dh:], flat[2 * dh:], att, batch=b, heads=heads, tq=t, tk=t, head_dim=dh,
-                      q_strides=(3 * inner * t, t * 3 * dh, 3 * dh), kv_strides=(3 * inner * t, t * 3 * dh, 3 * dh),
-                      o_strides=(heads * t * dh, t * dh, dh))
-        ctx.cfg = (heads, dh)
+        kw = dict(batch=b, heads=heads, tq=t, tk=t, head_dim=dh, q_strides=(3 * inner * t, t * 3 * dh, 3 * dh),
+                  kv_strides=(3 * inner * t, t * 3 * dh, 3 * dh), o_strides=(heads * t * dh, t * dh, dh))
+        if linear:
+            ops.linear_attention(flat, flat[dh:], flat[2 * dh:], att, eps=LINEAR_ATTENTION_EPS, **kw)
+        else:
+            ops.attention(flat, flat[dh:], flat[2 * dh:], att, **kw)
+        ctx.cfg = (heads, dh, bool(linear))
         ctx.save_for_backward(qkv_cm, att)
         return att
 
     @staticmethod
     def backward(ctx, datt):
         qkv_cm, att = ctx.saved_tensors
-        heads, dh = ctx.cfg
+        heads, dh, linear = ctx.cfg
         b, c3, t = qkv_cm.shape
         inner = heads * dh
         datt = datt.to(BF16).contiguous()
         dqkv = torch.empty_like(qkv_cm)
         q, dq = qkv_cm.data_ptr(), dqkv.data_ptr()
-        _lib.check(
-            _lib.lib().fm_attention_bwd_bf16(q, q + 2 * dh, q + 4 * dh, att.data_ptr(), datt.data_ptr(), dq, dq + 2 * dh,
-                                             dq + 4 * dh, b, heads, t, dh, 3 * inner * t, t * 3 * dh, 3 * dh,
-                                             heads * t * dh, t * dh, dh, 1.0 / math.sqrt(dh), _stream()),
-            "attention_bwd",
-        )
-        return dqkv, None, None
+        qs, os_ = (3 * inner * t, t * 3 * dh, 3 * dh), (heads * t * dh, t * dh, dh)
+        if linear:
+            _lib.check(
+                _lib.lib().fm_linear_attention_bwd_bf16(q, q + 2 * dh, q + 4 * dh, datt.data_ptr(), dq, dq + 2 * dh,
+                                                        dq + 4 * dh, b, heads, t, t, dh, *qs, *qs, *os_,
+                                                        LINEAR_ATTENTION_EPS, _stream()), "linear_attention_bwd")
+        else:
+            _lib.check(
+                _lib.lib().fm_attention_bwd_bf16(q, q + 2 * dh, q + 4 * dh, att.data_ptr(), datt.data_ptr(), dq,
+                                                 dq + 2 * dh, dq + 4 * dh, b, heads, t, dh, *qs, *os_,
+                                                 1.0 / math.sqrt(dh), _stream()), "attention_bwd")
+        return dqkv, None, None, None
 
 
-def attention_raw(qkv_cm: torch.Tensor, heads: int, dim_head: int) -> torch.Tensor:
-    return _AttentionRawFn.apply(qkv_cm, int(heads), int(dim_head))
+def attention_raw(qkv_cm: torch.Tensor, heads: int, dim_head: int, linear: bool = False) -> torch.Tensor:
+    return _AttentionRawFn.apply(qkv_cm, int(heads), int(dim_head), bool(linear))
+
+
+class _CrossAttentionRawFn(Function):
+    """SpatialCrossAttention's raw-reshape head split (`attention.py:176-186`): q_cm (b, inner, T) re-read as
+    (b, heads, T, dh), kv_cm (b, 2*inner, Tc) as (b, heads, Tc, 2*dh) = K | V; returns (b, heads, T, dh)."""
+
+    @staticmethod
+    def forward(ctx, q_cm, kv_cm, heads, dh, linear):
+        assert q_cm.dtype == BF16 and q_cm.is_contiguous() and kv_cm.dtype == BF16 and kv_cm.is_contiguous()
+        b, inner, t = q_cm.shape
+        tc = kv_cm.shape[-1]
+        assert inner == heads * dh and kv_cm.shape[1] == 2 * inner
+        att = torch.empty((b, heads, t, dh), dtype=BF16, device=q_cm.device)
+        kvf = kv_cm.view(-1)
+        kw = dict(batch=b, heads=heads, tq=t, tk=tc, head_dim=dh, q_strides=(inner * t, t * dh, dh),
+                  kv_strides=(2 * inner * tc, tc * 2 * dh, 2 * dh), o_strides=(heads * t * dh, t * dh, dh))
+        if linear:
+            ops.linear_attention(q_cm.view(-1), kvf, kvf[dh:], att, eps=LINEAR_ATTENTION_EPS, **kw)
+        else:
+            ops.attention(q_cm.view(-1), kvf, kvf[dh:], att, **kw)
+        ctx.cfg = (heads, dh, bool(linear))
+        ctx.save_for_backward(q_cm, kv_cm, att)
+        return att
+
+    @staticmethod
+    def backward(ctx, datt):
+        q_cm, kv_cm, att = ctx.saved_tensors
+        heads, dh, linear = ctx.cfg
+        b, inner, t = q_cm.shape
+        tc = kv_cm.shape[-1]
+        datt = datt.to(BF16).contiguous()
+        dq, dkv = torch.empty_like(q_cm), torch.empty_like(kv_cm)
+        k0, d0 = kv_cm.data_ptr(), dkv.data_ptr()
+        qs, ks, os_ = (inner * t, t * dh, dh), (2 * inner * tc, tc * 2 * dh, 2 * dh), (heads * t * dh, t * dh, dh)
+        if linear:
+            _lib.check(
+                _lib.lib().fm_linear_attention_bwd_bf16(q_cm.data_ptr(), k0, k0 + 2 * dh, datt.data_ptr(), dq.data_ptr(),
+                                                        d0, d0 + 2 * dh, b, heads, t, tc, dh, *qs, *ks, *os_,
+                                                        LINEAR_ATTENTION_EPS, _stream()), "linear_attention_bwd")
+        else:
+            _lib.check(
+                _lib.lib().fm_attention_bwd_cross_bf16(q_cm.data_ptr(), k0, k0 + 2 * dh, att.data_ptr(), datt.data_ptr(),
+                                                       dq.data_ptr(), d0, d0 + 2 * dh, b, heads, t, tc, dh, *qs, *ks,
+                                                       *os_, 1.0 / math.sqrt(dh), _stream()), "attention_bwd_cross")
+        return dq, dkv, None, None, None
+
+
+def cross_attention_raw(q_cm, kv_cm, heads: int, dim_head: int, linear: bool = False) -> torch.Tensor:
+    return _CrossAttentionRawFn.apply(q_cm, kv_cm, int(heads), int(dim_head), bool(linear))
 
 
 class _TransposeFn(Function):

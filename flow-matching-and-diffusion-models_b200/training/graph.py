@@ -34,8 +34,16 @@ def supported(model) -> bool:
         cross = [m for m in model.modules() if isinstance(m, DiffusersAttentionND) and m.context_dim is not None]
         return all(m.head_dim == 8 and m.context_dim <= CONTEXT_DIM_MAX and m.dropout == 0 for m in cross)
     if isinstance(model, EfficientUNetND):
-        return (model.spatial_dims == 2 and not model.cross_attention_resolutions
-                and not model.cross_attention_in_middle and model.dropout == 0)
+        from ..nn.blocks.attention import CONTEXT_DIM_MAX, SpatialCrossAttention, SpatialSelfAttention
+
+        if model.spatial_dims != 2 or model.dropout != 0:
+            return False
+        for m in model.modules():   # softmax or linear attention, self or over a context of <= 16 channels
+            if isinstance(m, (SpatialSelfAttention, SpatialCrossAttention)) and m.dim_head not in (8, 16, 32, 64):
+                return False
+            if isinstance(m, SpatialCrossAttention) and m.context_dim > CONTEXT_DIM_MAX:
+                return False
+        return True
     return False
 
 
@@ -289,14 +297,38 @@ def attention(att, x: torch.Tensor, context=None) -> torch.Tensor:
 def spatial_self_attention(att, x: torch.Tensor) -> torch.Tensor:
     """`attention.py:82-117` (CompVis block: GN -> Conv1d qkv -> raw-reshape head split -> SDPA -> Conv1d -> + x)."""
     b, c, hh, ww = x.shape
-    if att.use_linear or att.dim_head not in (8, 16, 32, 64):
-        out_of_scope("training SpatialSelfAttention (linear attention / dim_head)")
+    if att.dim_head not in (8, 16, 32, 64):
+        out_of_scope("training SpatialSelfAttention (dim_head)")
         raise RuntimeError("fmdm_b200.training: unsupported SpatialSelfAttention variant")
     t, inner = hh * ww, att.inner_dim
     n = _gn(att.norm, x, silu=False)
     qkv = F.conv([n], [(att.qkv.weight.squeeze(-1), 0, c)], bias=att.qkv.bias)          # NHWC == [b][T][3*inner]
     qkv_cm = F.transpose(qkv.permute(0, 2, 3, 1).reshape(b, t, 3 * inner))              # [b][3*inner][T]
-    a = F.attention_raw(qkv_cm, att.heads, att.dim_head)                                 # [b][heads][T][dh]
+    a = F.attention_raw(qkv_cm, att.heads, att.dim_head, linear=att.use_linear)          # [b][heads][T][dh]
+    h_tc = F.transpose(a.view(b, inner, t))                                              # raw reshape, [b][T][inner]
+    h = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
+    return F.conv([h], [(att.proj_out.weight.squeeze(-1), 0, inner)], bias=att.proj_out.bias, residual=x)
+
+
+def spatial_cross_attention(att, x: torch.Tensor, context) -> torch.Tensor:
+    """`attention.py:120-189` (CompVis cross-attention: GN -> Conv1d q -> raw reshape; context GN -> Conv1d kv -> raw
+    reshape -> softmax or linear attention with Tq != Tk -> raw reshape back -> Conv1d -> + x)."""
+    from ..nn.blocks.attention import CONTEXT_DIM_MAX, context_tokens
+
+    if context is None:
+        raise ValueError("SpatialCrossAttention requires a non-empty context tensor.")
+    b, c, hh, ww = x.shape
+    if att.dim_head not in (8, 16, 32, 64) or att.context_dim > CONTEXT_DIM_MAX:
+        out_of_scope("training SpatialCrossAttention (dim_head / context_dim > 16)")
+    t, inner = hh * ww, att.inner_dim
+    n = _gn(att.norm, x, silu=False)
+    q = F.conv([n], [(att.q_proj.weight.squeeze(-1), 0, c)], bias=att.q_proj.bias)       # NHWC == [b][T][inner]
+    q_cm = F.transpose(q.permute(0, 2, 3, 1).reshape(b, t, inner))                       # [b][inner][T]
+    cn = att.context_norm
+    kv = F.context_kv(context_tokens(context, att.context_dim), cn.weight, cn.bias, att.kv_proj.weight.squeeze(-1),
+                      att.kv_proj.bias, groups=cn.num_groups, eps=cn.eps)                # [b][Tc][2*inner]
+    kv_cm = F.transpose(kv)                                                              # [b][2*inner][Tc]
+    a = F.cross_attention_raw(q_cm, kv_cm, att.heads, att.dim_head, linear=att.use_linear)
     h_tc = F.transpose(a.view(b, inner, t))                                              # raw reshape, [b][T][inner]
     h = h_tc.view(b, hh, ww, inner).permute(0, 3, 1, 2)
     return F.conv([h], [(att.proj_out.weight.squeeze(-1), 0, inner)], bias=att.proj_out.bias, residual=x)
@@ -318,9 +350,9 @@ def upsample(up, x):
     return F.conv([y], [(conv.weight, 0, up.channels)], bias=conv.bias)
 
 
-def _sequential(seq, x, emb):
+def _sequential(seq, x, emb, context_ca=None):
     """`TimestepEmbedSequential.forward` (`unet.py:18-39`) over differentiable ops."""
-    from ..nn.blocks.attention import SpatialSelfAttention
+    from ..nn.blocks.attention import SpatialCrossAttention, SpatialSelfAttention
     from ..nn.blocks.residual import ResBlockND
     from ..nn.ops.upsampling import DownsampleND, UpsampleND
 
@@ -329,6 +361,8 @@ def _sequential(seq, x, emb):
             x = resblock(layer, x, emb)
         elif isinstance(layer, SpatialSelfAttention):
             x = spatial_self_attention(layer, x)
+        elif isinstance(layer, SpatialCrossAttention):
+            x = spatial_cross_attention(layer, x, context_ca)
         elif isinstance(layer, DownsampleND):
             x = downsample(layer, x)
         elif isinstance(layer, UpsampleND):
@@ -339,7 +373,7 @@ def _sequential(seq, x, emb):
     return x
 
 
-def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Tensor:
+def efficient_unet_forward(model, x: torch.Tensor, t, context=None, context_ca=None) -> torch.Tensor:
     """`EfficientUNetND.forward` (`unet.py:295-326`) with autograd."""
     ops.require_cuda(x, "training.efficient_unet_forward")
     t = model._normalize_timesteps(t, x)
@@ -368,11 +402,11 @@ def efficient_unet_forward(model, x: torch.Tensor, t, context=None) -> torch.Ten
             hs = [cut.cross(t) for t in hs]
             h = hs[-1]
             emb = EmbProjections(model, cut.cross(raw_emb), _embedding_blocks(late_mods))
-        h = _sequential(block, h, emb)
+        h = _sequential(block, h, emb, context_ca)
         hs.append(h)
-    h = _sequential(model.middle_block, h, emb)
+    h = _sequential(model.middle_block, h, emb, context_ca)
     for block in model.output_blocks:
-        h = _sequential(block, (h, hs.pop()), emb)   # `unet.py:321-322`, concat kept virtual
+        h = _sequential(block, (h, hs.pop()), emb, context_ca)   # `unet.py:321-322`, concat kept virtual
     h = _gn(model.out[0], h, silu=True)
     head = model.out[2].conv
     return F.conv_head(h, head.weight, head.bias)
@@ -395,7 +429,7 @@ def unet_forward(model, x: torch.Tensor, t, context=None, context_ca=None) -> to
     model.__dict__.pop("_fm_cut_state", None)
     del F._OPEN_SLOTS[:]
     if isinstance(model, EfficientUNetND):
-        return efficient_unet_forward(model, x, t, context)
+        return efficient_unet_forward(model, x, t, context, context_ca)
     ops.require_cuda(x, "training.unet_forward")
     t = model._normalize_timesteps(t, x)
     feats = ops.timestep_embedding(t, model.time_proj_dim, 10000.0, flip_sin_to_cos=model.flip_sin_to_cos,

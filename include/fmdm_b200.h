@@ -335,12 +335,19 @@ int fm_attention_bwd_bf16(const void* q, const void* k, const void* v, const voi
                           void* dk, void* dv, int32_t B, int32_t heads, int32_t T, int32_t head_dim, int64_t qs_b,
                           int64_t qs_h, int64_t qs_t, int64_t os_b, int64_t os_h, int64_t os_t, float scale,
                           fm_stream_t stream);
-/* head_dim 8 with queries and keys of different length / layout (cross-attention, attention.py:232-274 with
- * context_dim): q, dq use the q strides; k, v, dk, dv the kv strides; o, dout the o strides (elements). */
+/* Attention backward with queries and keys of their own length / layout (cross-attention: attention.py:149-189,
+ * 232-274; fm_attention_bwd_bf16 is the Tq == Tk case): q, dq use the q strides; k, v, dk, dv the kv strides; o, dout
+ * the o strides (elements).  head_dim 8 runs on mma.sync, 16 / 32 / 64 on the CUDA cores. */
 int fm_attention_bwd_cross_bf16(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq,
                                 void* dk, void* dv, int32_t B, int32_t heads, int32_t Tq, int32_t Tk, int32_t head_dim,
                                 int64_t qs_b, int64_t qs_h, int64_t qs_t, int64_t ks_b, int64_t ks_h, int64_t ks_t,
                                 int64_t os_b, int64_t os_h, int64_t os_t, float scale, fm_stream_t stream);
+/* Backward of fm_linear_attention_bf16 (attention.py:53-70): same strided bf16 operands; dq with the q strides, dk / dv
+ * with the kv strides, dout with the o strides. */
+int fm_linear_attention_bwd_bf16(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk,
+                                 void* dv, int32_t B, int32_t heads, int32_t Tq, int32_t Tk, int32_t head_dim,
+                                 int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb, int64_t kv_sh, int64_t kv_st,
+                                 int64_t o_sb, int64_t o_sh, int64_t o_st, float eps, fm_stream_t stream);
 /* Backward of fm_context_kv_bf16 (token-major output): dkv bf16 [B][Tc][O]; stats = the (mean, rstd) pairs the forward
  * wrote; dW fp32 [O][Cc], dbias fp32 [O] (or NULL), dgamma / dbeta fp32 [Cc] of the context GroupNorm.
  * workspace: fm_context_kv_bwd_workspace_elems floats. */

