@@ -91,6 +91,9 @@ SIGNATURES = {
         C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "fm_stem_im2col_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "fm_conv_stem_stats_rows": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "fm_conv_stem_tc_f32_bf16": (
+        C.c_int, [_vp, _i32, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "fm_conv_stem_tc_stats_rows": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),
     "fm_conv_head_bf16_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "fm_groupnorm_workspace_elems": (C.c_int64, [_i32, _i64, _i32, _i32]),
     "fm_groupnorm_stats_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp]),

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     __nv_bfloat16* __restrict__ out, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
     int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float scale_log2e) {
+  pdl_enter();
   __shared__ __align__(16) __nv_bfloat16 sK[kAtt8KeyChunk * 8];      // [key][8]
   __shared__ __align__(16) __nv_bfloat16 sVt[8 * kAtt8VtStride];     // [dim][key]
   const int b = blockIdx.z, h = blockIdx.y;
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(kAttMThreads) attention_mma_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     __nv_bfloat16* __restrict__ out, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
     int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float scale_log2e) {
+  pdl_enter();
   constexpr int kKS = HD + 8;                  // K row stride (elements): +16 B => the 8 keys of a fragment hit 8 bank groups
   constexpr int kVS = kAttMKeyChunk + 8;       // V^T row stride
   constexpr int kSteps = HD / 16;              // k-steps of Q K^T
@@ -428,7 +430,7 @@ static int launch_attention_mma(const void* q, const void* k, const void* v, voi
                                 int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb, int64_t kv_sh,
                                 int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float scale, cudaStream_t st) {
   dim3 grid((Tq + kAttMWarps * 16 - 1) / (kAttMWarps * 16), heads, B);
-  attention_mma_kernel<HD><<<grid, kAttMThreads, 0, st>>>(
+  launch_pdl(attention_mma_kernel<HD>, dim3(grid), dim3(kAttMThreads), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
       reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Tq, Tk, q_sb, q_sh, q_st,
       kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale * 1.4426950408889634f);
@@ -564,6 +566,7 @@ __global__ void __launch_bounds__(256) linear_attention_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     __nv_bfloat16* __restrict__ out, int heads, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
     int64_t kv_sh, int64_t kv_st, int64_t o_sb, int64_t o_sh, int64_t o_st, float eps) {
+  pdl_enter();
   constexpr int kLanes = 256 / HD;   // token lanes per feature column
   constexpr int kChunk = 32;         // tokens staged per step of the context accumulation
   constexpr int kPairs = HD * HD / 256 > 0 ? HD * HD / 256 : 1;
@@ -696,7 +699,7 @@ extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, vo
       // FMDM_ATTENTION_BF16P=1: the first-generation inner loop (scalar fp32 exponentials, bf16 probabilities), A/B only
       static const bool bf16p = getenv("FMDM_ATTENTION_BF16P") != nullptr;
       auto kern = bf16p ? attention_hd8_mma_kernel<false> : attention_hd8_mma_kernel<true>;
-      kern<<<grid, kAtt8Threads, 0, st>>>(
+      launch_pdl(kern, grid, dim3(kAtt8Threads), 0, st,
           reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
           reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Tq, Tk, q_sb, q_sh, q_st,
           kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, scale * 1.4426950408889634f);
@@ -747,7 +750,7 @@ extern "C" int fm_linear_attention_bf16(const void* q, const void* k, const void
   cudaStream_t st = (cudaStream_t)stream;
 #define FM_LIN(HD)                                                                                                  \
   case HD:                                                                                                          \
-    linear_attention_kernel<HD><<<B * heads, 256, 0, st>>>(                                                         \
+    launch_pdl(linear_attention_kernel<HD>, dim3(B * heads), dim3(256), 0, st,                                                          \
         reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),                       \
         reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), heads, Tq, Tk, q_sb, q_sh, \
         q_st, kv_sb, kv_sh, kv_st, o_sb, o_sh, o_st, eps);                                                          \

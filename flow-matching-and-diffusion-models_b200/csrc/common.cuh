@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/fmdm_b200.h"
 
@@ -36,6 +37,43 @@ int wgrad_tc_max_splits(int B, int Ho, int Wo, int Cin, int Cout, int ksize);
     cudaError_t e__ = cudaGetLastError();                      \
     if (e__ != cudaSuccess) return fm::check_cuda(e__, what);  \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Kernel boundaries of the replayed graphs (~340 per Euler step, ~1000 per training step) cost a drain + launch +
+// prologue each.  A kernel launched through launch_pdl() may become resident while its predecessor in the stream is
+// still running: it does its private set-up (barrier init, TMEM allocation, tensor-map prefetch, index arithmetic),
+// then pdl_wait() blocks until the predecessor grid has COMPLETED and its memory is visible.  Rules every such kernel
+// follows: (1) pdl_wait() precedes the first global-memory access of every thread, reads and writes alike (the kernel
+// before may still be reading what this one overwrites), and is executed by every CTA; (2) pdl_trigger() early, so the
+// successor can start its own set-up.  A kernel launched without the attribute (plain <<<>>>) serialises as always and
+// the two instructions are no-ops in it, so converted and unconverted kernels mix freely.  The attribute is OPT-IN
+// (FMDM_PDL=1): same-box A/B on the B200 showed the 50-step LDCT-512 loop 1.7 % slower with it (9.95 vs 10.12
+// samples/s; kernels of 0.2-1.7 ms leave nothing to hide and the early-resident CTAs cost power under the 1 kW cap)
+// and the training step unchanged (37.4 vs 37.2 ms), so the default launch is the plain one.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- small device helpers -----------------------------------------------------------------------------------
 // SiLU with ONE special-function op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32, rel. error ~2^-11, below

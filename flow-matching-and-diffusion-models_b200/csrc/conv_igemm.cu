@@ -159,6 +159,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // PDL: everything above is private set-up; from here on global memory of the preceding kernels is touched
+  pdl_trigger();
+  pdl_wait();
 
   // ---- static tile schedule: work unit = (M tile [pair], N tile), N fastest so neighbours share the A rows in L2
   const int units_m = p.m_tiles / (CG * MT);
@@ -550,13 +553,15 @@ static int launch_conv_persistent(const ConvKernelParams& kp, cudaStream_t st) {
   cfg.blockDim = dim3(kPConvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<BLOCK_N, MODE, CG, MT>, kp);
   count_launch();
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_igemm_persistent)");

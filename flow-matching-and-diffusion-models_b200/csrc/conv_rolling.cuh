@@ -132,6 +132,9 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // PDL: everything above is private set-up; from here on global memory of the preceding kernels is touched
+  pdl_trigger();
+  pdl_wait();
 
   // ---- static schedule: unit = (strip pair, N tile), N fastest --------------------------------------------------
   const int total_units = sch.pairs * p.n_tiles;
@@ -536,13 +539,15 @@ static int launch_conv_rolling(const ConvKernelParams& kp, const RollSched& sch,
   cfg.blockDim = dim3(kPConvThreads + XF * kXfThreads + 32);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_rolling_kernel<BLOCK_N, XF, OB>, kp, sch);
   count_launch();
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_rolling)");

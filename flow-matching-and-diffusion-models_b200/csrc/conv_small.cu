@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const float* __
                                                                 const float* __restrict__ bias,
                                                                 uint4* __restrict__ out, int H, int W, int Cout,
                                                                 float* __restrict__ stats) {
+  pdl_enter();
   extern __shared__ float sw[];  // [Cin*9][Cout] + bias[Cout] (+ statistics scratch, reusing the weights at the end)
   const int Cin = C0 + C1;
   const int K = Cin * 9;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
                                                          const float* __restrict__ x1, int C1, float in_scale,
                                                          float in_shift, uint4* __restrict__ out, int H, int W,
                                                          int64_t total) {
+  pdl_enter();
   const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= total) return;
   const int HW = H * W;
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(kHd2Threads, 2) conv_head_dot_kernel(const uin
                                                                       float* __restrict__ out, int H, int W,
                                                                       const float* __restrict__ norm_ab,
                                                                       int norm_act) {
+  pdl_enter();
   constexpr int C = LPP * 8;
   constexpr int PPW = 32 / LPP;  // pixels per warp iteration
   __shared__ float P[kHd2Pix * 9];
@@ -399,9 +402,384 @@ __global__ void __launch_bounds__(kHd2Threads, 2) conv_head_dot_kernel(const uin
   }
 }
 
+// Head, Cout = 1, fused output norm, Cin in {64, 128}: "dot-then-gather" with phase 1 on the tensor cores.  The nine
+// per-tap dot products of a pixel are one row of a [pixels x Cin] x [Cin x 9] GEMM: a warp takes 16 halo pixels at a
+// time, every lane loads 16-byte channel runs of rows g and g+8 straight from global memory (a quad covers 64
+// contiguous bytes of a pixel), passes them through act(a*x+b) in packed arithmetic and uses the four words of a load
+// AS the A fragments of two m16n8k16 steps - the K axis is permuted (k = 2q+j <-> channel 8q+4s+j) identically in the
+// weight fragments, so no shuffle or shared-memory pass touches the activations.  Activations and weights are fp16
+// (11 significant bits; the weights are scaled by a power of two taken from their largest magnitude so that none
+// under- or overflows, undone exactly in phase 2), accumulation fp32.  Taps 0-7 are the first n-tile, tap 8 column 0
+// of a second.  Partials go to shared memory tap-major (conflict-free both ways); phase 2 as in the dot kernel.
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// two bf16 channels -> act(a*x+b) as packed halves (a, b pre-halved when kSilu: SiLU(2h) = h + h*tanh(h))
+template <bool kSilu>
+__device__ __forceinline__ uint32_t xf_word_f16(uint32_t w, float2 a, float2 b) {
+  const float2 h = ffma2(bf16x2_as_f32x2(w), a, b);
+  const uint32_t hu = pack_f16x2_sat(h.x, h.y);
+  if (!kSilu) return hu;
+  uint32_t tu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+  const __half2 hh = *reinterpret_cast<const __half2*>(&hu);
+  const __half2 o = __hfma2(hh, *reinterpret_cast<const __half2*>(&tu), hh);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+
+constexpr int kHmTW = 64, kHmThreads = 256;
+
+template <int C, int TH, bool kSilu>
+__global__ void __launch_bounds__(kHmThreads, 2) conv_head_mma_kernel(const uint4* __restrict__ x,
+                                                                     const float* __restrict__ w_oihw,
+                                                                     const float* __restrict__ bias,
+                                                                     float* __restrict__ out, int H, int W,
+                                                                     const float* __restrict__ norm_ab) {
+  pdl_enter();
+  constexpr int NBLK = C / 32;           // 32-channel blocks: one 16-byte load per lane and row
+  constexpr int LPP = C / 8;             // uint4 per pixel
+  constexpr int kWP = kHmTW + 2;
+  constexpr int kPix = (TH + 2) * kWP;   // halo pixels; kPix % 16 == 4 makes the tap-major stores conflict-free
+  constexpr int kGroups = (kPix + 15) / 16;
+  static_assert(kPix % 16 == 4, "partial-sum pitch");
+  extern __shared__ __align__(16) uint8_t hm_smem[];
+  float* P = reinterpret_cast<float*>(hm_smem);              // [9][kPix]
+  float* sab = P + 9 * kPix;                                 // [2][C]: a, b (pre-halved for SiLU)
+  uint32_t* smax = reinterpret_cast<uint32_t*>(sab + 2 * C); // [8]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int w0 = blockIdx.x * kHmTW, h0 = blockIdx.y * TH, n = blockIdx.z;
+
+  uint32_t m = 0;
+  for (int i = threadIdx.x; i < 9 * C; i += kHmThreads) m = max(m, __float_as_uint(__ldg(w_oihw + i)) & 0x7fffffffu);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if (lane == 0) smax[warp] = m;
+  {
+    const float k = kSilu ? 0.5f : 1.0f;
+    for (int i = threadIdx.x; i < 2 * C; i += kHmThreads) sab[i] = k * __ldg(norm_ab + (size_t)n * 2 * C + i);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kHmThreads / 32; ++i) m = max(m, smax[i]);
+  // S = 2^(14 - floor(log2 max|w|)): the largest weight lands in [2^14, 2^15), below fp16's 65504
+  int se = 268 - (int)(m >> 23);
+  se = se < 1 ? 1 : (se > 253 ? 253 : se);
+  const float S = __uint_as_float((uint32_t)se << 23), invS = __uint_as_float((uint32_t)(254 - se) << 23);
+
+  // weight fragments: (blk, s) covers channels blk*32 + 8q + 4s + {0..3} in this lane; column n = g is tap g
+  uint32_t bf[NBLK][2][2], bf8[NBLK][2][2];
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float* wc = w_oihw + (blk * 32 + q * 8 + 4 * s) * 9;
+      bf[blk][s][0] = pack_f16x2_sat(S * __ldg(wc + g), S * __ldg(wc + 9 + g));
+      bf[blk][s][1] = pack_f16x2_sat(S * __ldg(wc + 18 + g), S * __ldg(wc + 27 + g));
+      bf8[blk][s][0] = g == 0 ? pack_f16x2_sat(S * __ldg(wc + 8), S * __ldg(wc + 9 + 8)) : 0u;
+      bf8[blk][s][1] = g == 0 ? pack_f16x2_sat(S * __ldg(wc + 18 + 8), S * __ldg(wc + 27 + 8)) : 0u;
+    }
+
+  for (int grp = warp; grp < kGroups; grp += kHmThreads / 32) {
+    const int pi0 = grp * 16 + g, pi1 = pi0 + 8;
+    const int ph0 = pi0 / kWP, pw0 = pi0 - ph0 * kWP, ph1 = pi1 / kWP, pw1 = pi1 - ph1 * kWP;
+    const int ih0 = h0 + ph0 - 1, iw0 = w0 + pw0 - 1, ih1 = h0 + ph1 - 1, iw1 = w0 + pw1 - 1;
+    const bool in0 = pi0 < kPix && (unsigned)ih0 < (unsigned)H && (unsigned)iw0 < (unsigned)W;
+    const bool in1 = pi1 < kPix && (unsigned)ih1 < (unsigned)H && (unsigned)iw1 < (unsigned)W;
+    const uint4* r0 = x + (((size_t)n * H + (in0 ? ih0 : 0)) * W + (in0 ? iw0 : 0)) * LPP + q;
+    const uint4* r1 = x + (((size_t)n * H + (in1 ? ih1 : 0)) * W + (in1 ? iw1 : 0)) * LPP + q;
+    uint4 v0[NBLK], v1[NBLK];
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk) {
+      v0[blk] = in0 ? __ldg(r0 + blk * 4) : make_uint4(0, 0, 0, 0);
+      v1[blk] = in1 ? __ldg(r1 + blk * 4) : make_uint4(0, 0, 0, 0);
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc8[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk) {
+      const float4 al = *reinterpret_cast<const float4*>(sab + blk * 32 + q * 8);
+      const float4 ah = *reinterpret_cast<const float4*>(sab + blk * 32 + q * 8 + 4);
+      const float4 bl = *reinterpret_cast<const float4*>(sab + C + blk * 32 + q * 8);
+      const float4 bh = *reinterpret_cast<const float4*>(sab + C + blk * 32 + q * 8 + 4);
+      const float2 a01 = make_float2(al.x, al.y), a23 = make_float2(al.z, al.w), a45 = make_float2(ah.x, ah.y),
+                   a67 = make_float2(ah.z, ah.w);
+      const float2 b01 = make_float2(bl.x, bl.y), b23 = make_float2(bl.z, bl.w), b45 = make_float2(bh.x, bh.y),
+                   b67 = make_float2(bh.z, bh.w);
+      const uint32_t x00 = xf_word_f16<kSilu>(v0[blk].x, a01, b01), x01 = xf_word_f16<kSilu>(v0[blk].y, a23, b23);
+      const uint32_t x02 = xf_word_f16<kSilu>(v0[blk].z, a45, b45), x03 = xf_word_f16<kSilu>(v0[blk].w, a67, b67);
+      const uint32_t x10 = xf_word_f16<kSilu>(v1[blk].x, a01, b01), x11 = xf_word_f16<kSilu>(v1[blk].y, a23, b23);
+      const uint32_t x12 = xf_word_f16<kSilu>(v1[blk].z, a45, b45), x13 = xf_word_f16<kSilu>(v1[blk].w, a67, b67);
+      mma_m16n8k16_f16(acc, x00, x10, x01, x11, bf[blk][0][0], bf[blk][0][1]);
+      mma_m16n8k16_f16(acc8, x00, x10, x01, x11, bf8[blk][0][0], bf8[blk][0][1]);
+      mma_m16n8k16_f16(acc, x02, x12, x03, x13, bf[blk][1][0], bf[blk][1][1]);
+      mma_m16n8k16_f16(acc8, x02, x12, x03, x13, bf8[blk][1][0], bf8[blk][1][1]);
+    }
+    // zero padding applies AFTER the activation: an out-of-image pixel contributes nothing
+    if (pi0 < kPix) {
+      P[(2 * q) * kPix + pi0] = in0 ? acc[0] : 0.f;
+      P[(2 * q + 1) * kPix + pi0] = in0 ? acc[1] : 0.f;
+      if (q == 0) P[8 * kPix + pi0] = in0 ? acc8[0] : 0.f;
+    }
+    if (pi1 < kPix) {
+      P[(2 * q) * kPix + pi1] = in1 ? acc[2] : 0.f;
+      P[(2 * q + 1) * kPix + pi1] = in1 ? acc[3] : 0.f;
+      if (q == 0) P[8 * kPix + pi1] = in1 ? acc8[2] : 0.f;
+    }
+  }
+  __syncthreads();
+  const float bv = bias ? __ldg(bias) : 0.f;
+  for (int o = threadIdx.x; o < TH * kHmTW; o += kHmThreads) {
+    const int ty = o / kHmTW, tx = o - ty * kHmTW;
+    const int oh = h0 + ty, ow = w0 + tx;
+    if (oh >= H || ow >= W) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) acc += P[(kh * 3 + kw) * kPix + (ty + kh) * kWP + tx + kw];
+    out[((size_t)n * H + oh) * W + ow] = fmaf(acc, invS, bv);
+  }
+}
+
+template <int C, int TH, bool kSilu>
+static int launch_head_mma(const void* x, const float* w, const float* bias, float* out, int B, int H, int W,
+                           const float* norm_ab, cudaStream_t st) {
+  constexpr int kPix = (TH + 2) * (kHmTW + 2);
+  constexpr int smem = (9 * kPix + 2 * C + 8) * 4;
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_head_mma_kernel<C, TH, kSilu>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_head_mma)");
+    attr_set = true;
+  }
+  dim3 grid((W + kHmTW - 1) / kHmTW, (H + TH - 1) / TH, B);
+  launch_pdl(conv_head_mma_kernel<C, TH, kSilu>, dim3(grid), dim3(kHmThreads), smem, st, reinterpret_cast<const uint4*>(x), w, bias, out,
+                                                                    H, W, norm_ab);
+  FM_LAUNCH_CHECK("conv_head_mma_kernel");
+  return 0;
+}
+
+// Stem on the tensor cores without the im2col round trip: conv_in as a [pixels x K] x [K x Cout] GEMM on `mma.sync`,
+// K = 9*Cin (+2) <= 32.  A CTA walks 8 x 64-pixel tiles of one image (static stride over the image's tiles), stages
+// the fp32 halo tile (centred, zero outside the image) in shared memory and every lane gathers ITS k-columns of two
+// pixels straight into m16n8k16 A fragments (bf16, the rounding the im2col path applied).  The bias rides in the GEMM
+// as two extra k-columns (hi + lo bf16 halves against a constant 1), so the accumulators are the finished fp32
+// outputs: they feed the GroupNorm channel-quad partial sums (one row per CTA, fixed order) and are staged per warp in
+// shared memory so that the store is 16 bytes per lane, 256 contiguous bytes per pixel.  Store-bandwidth bound.
+constexpr int kSmTH = 8, kSmTW = 64, kSmThreads = 256;
+constexpr int kSmWP = kSmTW + 2, kSmPlane = (kSmTH + 2) * kSmWP;
+
+template <int NT, int KS>  // NT n-tiles of 8 output channels, KS k-steps of 16
+__global__ void __launch_bounds__(kSmThreads, 2) conv_stem_mma_kernel(const float* __restrict__ x0, int C0,
+                                                                     const float* __restrict__ x1, int C1,
+                                                                     float in_scale, float in_shift,
+                                                                     const float* __restrict__ w_oihw,
+                                                                     const float* __restrict__ bias,
+                                                                     uint4* __restrict__ out, int H, int W,
+                                                                     float* __restrict__ gn_stats) {
+  pdl_enter();
+  constexpr int COUT = NT * 8, C8 = COUT / 8;
+  constexpr int kPitch = COUT / 2 + 4;  // 32-bit words per staged output pixel (+4: conflict-free fragment stores)
+  extern __shared__ __align__(16) uint8_t sm_smem[];
+  const int Cin = C0 + C1, K9 = 9 * Cin;
+  uint2* sB = reinterpret_cast<uint2*>(sm_smem);                       // [KS][NT][32] weight fragments
+  float* sx = reinterpret_cast<float*>(sB + KS * NT * 32);             // [Cin][kSmPlane], then {0, 1, 0, 0}
+  uint32_t* so = reinterpret_cast<uint32_t*>(sx + Cin * kSmPlane + 4); // [8 warps][16][kPitch]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int n = blockIdx.y;
+  const size_t HW = (size_t)H * W;
+
+  auto wk = [&](int co, int k) -> float {
+    if (k < K9) return __ldg(w_oihw + (size_t)co * K9 + k);
+    if (bias == nullptr || k >= K9 + 2) return 0.f;
+    const float b = __ldg(bias + co);
+    const float hi = __bfloat162float(__float2bfloat16_rn(b));
+    return k == K9 ? hi : b - hi;
+  };
+  for (int e = threadIdx.x; e < KS * NT * 32; e += kSmThreads) {
+    const int l = e & 31, nt = (e >> 5) % NT, s = e / (NT * 32);
+    const int co = nt * 8 + (l >> 2), k0 = 16 * s + 2 * (l & 3);
+    sB[e] = make_uint2(pack_bf16x2(wk(co, k0), wk(co, k0 + 1)), pack_bf16x2(wk(co, k0 + 8), wk(co, k0 + 9)));
+  }
+  if (threadIdx.x < 4) sx[Cin * kSmPlane + threadIdx.x] = threadIdx.x == 1 ? 1.f : 0.f;
+  // this lane's k-columns: address = pixel * kmul + koff (taps move with the pixel, the constants do not)
+  int koff[4 * KS], kmul[4 * KS];
+#pragma unroll
+  for (int j = 0; j < 4 * KS; ++j) {
+    const int k = 16 * (j >> 2) + 2 * q + (j & 1) + ((j >> 1) & 1) * 8;
+    const int ci = k / 9, tap = k - ci * 9;
+    kmul[j] = k < K9 ? 1 : 0;
+    koff[j] = k < K9 ? ci * kSmPlane + (tap / 3) * kSmWP + tap % 3 : Cin * kSmPlane + (k < K9 + 2 ? 1 : 0);
+  }
+  float st_s[NT], st_q[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) st_s[i] = st_q[i] = 0.f;
+
+  const int tiles_w = (W + kSmTW - 1) / kSmTW, tiles = tiles_w * ((H + kSmTH - 1) / kSmTH);
+  uint32_t* sow = so + warp * 16 * kPitch;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int th = t / tiles_w, w0 = (t - th * tiles_w) * kSmTW, h0 = th * kSmTH;
+    __syncthreads();  // the previous tile's gathers are done (first pass: the fragment table is complete)
+    for (int i = threadIdx.x; i < Cin * kSmPlane; i += kSmThreads) {
+      const int ci = i / kSmPlane, p = i - ci * kSmPlane, r = p / kSmWP, c = p - r * kSmWP;
+      const int ih = h0 + r - 1, iw = w0 + c - 1;
+      float v = 0.f;  // zero padding applies AFTER the optional 2x-1 centering
+      if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+        const float* src = ci < C0 ? x0 + ((size_t)n * C0 + ci) * HW : x1 + ((size_t)n * C1 + (ci - C0)) * HW;
+        v = fmaf(__ldg(src + (size_t)ih * W + iw), in_scale, in_shift);
+      }
+      sx[i] = v;
+    }
+    __syncthreads();
+    const int oh = h0 + warp;
+    if (oh >= H) continue;  // warp-uniform; the block barriers above are reached by every warp on the next pass
+#pragma unroll 1
+    for (int grp = 0; grp < kSmTW / 16; ++grp) {
+      const int col = grp * 16 + g;
+      const bool v0 = w0 + col < W, v1 = w0 + col + 8 < W;
+      if (w0 + grp * 16 >= W) break;
+      const int p0 = warp * kSmWP + col, p1 = p0 + 8;
+      const uint32_t m0 = v0 ? 0xffffffffu : 0u, m1 = v1 ? 0xffffffffu : 0u;
+      uint32_t a[KS][4];
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const int j = 4 * s;
+        a[s][0] = pack_bf16x2(sx[p0 * kmul[j] + koff[j]], sx[p0 * kmul[j + 1] + koff[j + 1]]) & m0;
+        a[s][1] = pack_bf16x2(sx[p1 * kmul[j] + koff[j]], sx[p1 * kmul[j + 1] + koff[j + 1]]) & m1;
+        a[s][2] = pack_bf16x2(sx[p0 * kmul[j + 2] + koff[j + 2]], sx[p0 * kmul[j + 3] + koff[j + 3]]) & m0;
+        a[s][3] = pack_bf16x2(sx[p1 * kmul[j + 2] + koff[j + 2]], sx[p1 * kmul[j + 3] + koff[j + 3]]) & m1;
+      }
+#pragma unroll
+      for (int half = 0; half < NT / 8; ++half) {
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+          for (int s = 0; s < KS; ++s) {
+            const uint2 b = sB[(s * NT + half * 8 + i) * 32 + lane];
+            mma_m16n8k16_bf16(acc[i], a[s][0], a[s][1], a[s][2], a[s][3], b.x, b.y);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int nt = half * 8 + i;
+          const float2 s2 = fadd2(make_float2(acc[i][0], acc[i][1]), make_float2(acc[i][2], acc[i][3]));
+          const float2 q2 = ffma2(make_float2(acc[i][2], acc[i][3]), make_float2(acc[i][2], acc[i][3]),
+                                  fmul2(make_float2(acc[i][0], acc[i][1]), make_float2(acc[i][0], acc[i][1])));
+          st_s[nt] += s2.x + s2.y;
+          st_q[nt] += q2.x + q2.y;
+          sow[g * kPitch + nt * 4 + q] = pack_bf16x2(acc[i][0], acc[i][1]);
+          sow[(g + 8) * kPitch + nt * 4 + q] = pack_bf16x2(acc[i][2], acc[i][3]);
+        }
+      }
+      __syncwarp();
+      uint4* dst = out + (((size_t)n * H + oh) * W + w0 + grp * 16) * C8;
+#pragma unroll
+      for (int i = 0; i < 16 * C8 / 32; ++i) {
+        const int idx = i * 32 + lane, px = idx / C8, ch = idx - px * C8;
+        const uint4 v = *reinterpret_cast<const uint4*>(sow + px * kPitch + ch * 4);
+        if (w0 + grp * 16 + px < W) dst[(size_t)px * C8 + ch] = v;
+      }
+      __syncwarp();
+    }
+  }
+  if (gn_stats == nullptr) return;
+  // channel-quad partial sums of this CTA: lanes that differ in g or in the low bit of q hold the same quad
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+#pragma unroll
+    for (int o = 1; o <= 16; o = o == 1 ? 4 : o << 1) {
+      st_s[i] += __shfl_xor_sync(0xffffffffu, st_s[i], o);
+      st_q[i] += __shfl_xor_sync(0xffffffffu, st_q[i], o);
+    }
+  }
+  __syncthreads();  // every warp is past its last use of the staging buffers
+  float* red = reinterpret_cast<float*>(so);  // [8 warps][NT*2 quads][2]
+  if (g == 0 && (q & 1) == 0) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      red[(warp * NT * 2 + i * 2 + (q >> 1)) * 2 + 0] = st_s[i];
+      red[(warp * NT * 2 + i * 2 + (q >> 1)) * 2 + 1] = st_q[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NT * 4) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kSmThreads / 32; ++w) acc += red[w * NT * 4 + threadIdx.x];
+    gn_stats[((size_t)n * gridDim.x + blockIdx.x) * NT * 4 + threadIdx.x] = acc;
+  }
+}
+
+static int stem_mma_blocks_per_image(int B, int H, int W) {
+  const int tiles = ((W + kSmTW - 1) / kSmTW) * ((H + kSmTH - 1) / kSmTH);
+  int bpi = (2 * sm_count()) / B;  // two resident CTAs per SM, one wave
+  if (bpi < 1) bpi = 1;
+  return bpi < tiles ? bpi : tiles;
+}
+
+static bool stem_mma_supported(int Cin, int Cout) { return (Cout == 64 || Cout == 128) && 9 * Cin + 2 <= 32; }
+
+template <int NT, int KS>
+static int launch_stem_mma(const float* x0, int C0, const float* x1, int C1, float in_scale, float in_shift,
+                           const float* w, const float* bias, void* out, int B, int H, int W, float* gn_stats,
+                           cudaStream_t st) {
+  const int smem = KS * NT * 32 * 8 + ((C0 + C1) * kSmPlane + 4) * 4 + (kSmThreads / 32) * 16 * (NT * 4 + 4) * 4;
+  static int attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_stem_mma_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_stem_mma)");
+    attr = smem;
+  }
+  launch_pdl(conv_stem_mma_kernel<NT, KS>, dim3(stem_mma_blocks_per_image(B, H, W), B), dim3(kSmThreads), smem, st, 
+      x0, C0, x1, C1, in_scale, in_shift, w, bias, reinterpret_cast<uint4*>(out), H, W, gn_stats);
+  FM_LAUNCH_CHECK("conv_stem_mma_kernel");
+  return 0;
+}
+
 }  // namespace fm
 
 using namespace fm;
+
+extern "C" int fm_conv_stem_tc_stats_rows(int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || !stem_mma_supported(Cin, Cout)) return 0;
+  return stem_mma_blocks_per_image(B, H, W);
+}
+
+extern "C" int fm_conv_stem_tc_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale,
+                                        float in_shift, const float* weight_oihw, const float* bias, void* out,
+                                        int32_t B, int32_t H, int32_t W, int32_t Cout, float* gn_stats,
+                                        fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  FM_REQUIRE(x0 && C0 > 0 && (x1 != nullptr) == (C1 > 0), "conv_stem_tc: inconsistent sources");
+  FM_REQUIRE(weight_oihw && out && B > 0 && B <= 65535 && H > 0 && W > 0, "conv_stem_tc: bad argument");
+  FM_REQUIRE((int64_t)H * W < (1ll << 31), "conv_stem_tc: image too large for 32-bit indexing");
+  if (!stem_mma_supported(C0 + C1, Cout)) {
+    set_error("conv_stem_tc: Cin=%d, Cout=%d not covered (Cout 64|128, 9*Cin+2 <= 32)", C0 + C1, Cout);
+    return FM_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool one = 9 * (C0 + C1) + 2 <= 16;
+#define FM_STEM_MMA(NT, KS) \
+  launch_stem_mma<NT, KS>(x0, C0, x1, C1, in_scale, in_shift, weight_oihw, bias, out, B, H, W, gn_stats, st)
+  if (Cout == 64) return one ? FM_STEM_MMA(8, 1) : FM_STEM_MMA(8, 2);
+  return one ? FM_STEM_MMA(16, 1) : FM_STEM_MMA(16, 2);
+#undef FM_STEM_MMA
+}
 
 static int stem_blocks_per_image(int B, int H, int W, int Cout) {
   const int gpb = kStemThreads / (Cout / 8);
@@ -438,7 +816,7 @@ extern "C" int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x
     attr = smem;
   }
   const int bpi = stem_blocks_per_image(B, H, W, Cout);
-  conv_stem_kernel<<<dim3(bpi, B), kStemThreads, smem, (cudaStream_t)stream>>>(
+  launch_pdl(conv_stem_kernel, dim3(bpi, B), dim3(kStemThreads), smem, (cudaStream_t)stream, 
       x0, C0, x1, C1, in_scale, in_shift, weight_oihw, bias, reinterpret_cast<uint4*>(out), H, W, Cout, gn_stats);
   FM_LAUNCH_CHECK("conv_stem_kernel");
   return 0;
@@ -458,7 +836,7 @@ extern "C" int fm_stem_im2col_bf16(const float* x0, int32_t C0, const float* x1,
   cudaStream_t st = (cudaStream_t)stream;
   uint4* o = reinterpret_cast<uint4*>(out);
 #define FM_IM2COL_CASE(K)                                                                                            \
-  case K: stem_im2col_kernel<K><<<blocks, 256, 0, st>>>(x0, C0, x1, C1, in_scale, in_shift, o, H, W, total); break;
+  case K: launch_pdl(stem_im2col_kernel<K>, dim3(blocks), dim3(256), 0, st, x0, C0, x1, C1, in_scale, in_shift, o, H, W, total); break;
   switch (Kp) {
     FM_IM2COL_CASE(16) FM_IM2COL_CASE(24) FM_IM2COL_CASE(32) FM_IM2COL_CASE(40) FM_IM2COL_CASE(48) FM_IM2COL_CASE(56)
     FM_IM2COL_CASE(64) FM_IM2COL_CASE(72)
@@ -477,13 +855,26 @@ extern "C" int fm_conv_head_bf16_f32(const void* x, const float* weight_oihw, co
   FM_REQUIRE(Cin > 0 && Cin % 8 == 0, "conv_head: Cin=%d must be a multiple of 8", Cin);
   FM_REQUIRE(Cout >= 1 && Cout <= 4, "conv_head: Cout=%d must be in 1..4", Cout);
   FM_REQUIRE(B <= 65535, "conv_head: batch too large for the grid");
+  if (Cout == 1 && (Cin == 64 || Cin == 128) && norm_ab != nullptr && getenv("FMDM_HEAD_TILE") == nullptr &&
+      getenv("FMDM_HEAD_DOT") == nullptr) {
+    FM_REQUIRE(((uintptr_t)norm_ab & 15) == 0, "conv_head: norm_ab must be 16B aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tall = H >= 128;
+#define FM_HEAD_MMA(CC)                                                                                              \
+  (tall ? (norm_act ? launch_head_mma<CC, 32, true>(x, weight_oihw, bias, out, B, H, W, norm_ab, st)                  \
+                    : launch_head_mma<CC, 32, false>(x, weight_oihw, bias, out, B, H, W, norm_ab, st))                \
+        : (norm_act ? launch_head_mma<CC, 16, true>(x, weight_oihw, bias, out, B, H, W, norm_ab, st)                  \
+                    : launch_head_mma<CC, 16, false>(x, weight_oihw, bias, out, B, H, W, norm_ab, st)))
+    return Cin == 64 ? FM_HEAD_MMA(64) : FM_HEAD_MMA(128);
+#undef FM_HEAD_MMA
+  }
   if (Cout == 1 && (Cin == 64 || Cin == 128) && getenv("FMDM_HEAD_TILE") == nullptr) {
     dim3 grid2((W + kHd2TW - 1) / kHd2TW, (H + kHd2TH - 1) / kHd2TH, B);
     if (Cin == 64)
-      conv_head_dot_kernel<8><<<grid2, kHd2Threads, 0, (cudaStream_t)stream>>>(
+      launch_pdl(conv_head_dot_kernel<8>, dim3(grid2), dim3(kHd2Threads), 0, (cudaStream_t)stream, 
           reinterpret_cast<const uint4*>(x), weight_oihw, bias, out, H, W, norm_ab, norm_act);
     else
-      conv_head_dot_kernel<16><<<grid2, kHd2Threads, 0, (cudaStream_t)stream>>>(
+      launch_pdl(conv_head_dot_kernel<16>, dim3(grid2), dim3(kHd2Threads), 0, (cudaStream_t)stream, 
           reinterpret_cast<const uint4*>(x), weight_oihw, bias, out, H, W, norm_ab, norm_act);
     FM_LAUNCH_CHECK("conv_head_dot_kernel");
     return 0;

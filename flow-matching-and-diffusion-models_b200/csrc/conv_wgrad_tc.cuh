@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(wgtc::kThreads, 1) conv_wgrad_tc_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kStages * kStage + 16 * kStages + 8);
+  pdl_trigger();  // PDL: barrier init and TMEM allocation above overlap the predecessor's tail
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -208,7 +210,7 @@ int wgrad_tc_launch(const void* dy, const void* x, float* workspace, int64_t wor
       if (int e = check_cuda(cudaFuncSetAttribute(conv_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "wgrad_tc attr")) return e;
       attr = true;
     }
-    conv_wgrad_tc_kernel<3><<<grid, wgtc::kThreads, smem, st>>>(p);
+    launch_pdl(conv_wgrad_tc_kernel<3>, grid, dim3(wgtc::kThreads), smem, st, p);
   } else {
     constexpr int smem = wgtc::stages(1) * wgtc::stage_bytes(1) + 1024 + 256;
     static bool attr = false;
@@ -216,7 +218,7 @@ int wgrad_tc_launch(const void* dy, const void* x, float* workspace, int64_t wor
       if (int e = check_cuda(cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "wgrad_tc attr")) return e;
       attr = true;
     }
-    conv_wgrad_tc_kernel<1><<<grid, wgtc::kThreads, smem, st>>>(p);
+    launch_pdl(conv_wgrad_tc_kernel<1>, grid, dim3(wgtc::kThreads), smem, st, p);
   }
   FM_LAUNCH_CHECK("conv_wgrad_tc_kernel");
   *splits_out = splits;

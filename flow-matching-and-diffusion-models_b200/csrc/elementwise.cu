@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) sched_flowmatch_kernel(float* __restrict_
                                                              const float* __restrict__ coef,
                                                              const int32_t* __restrict__ step_dev, int step_host,
                                                              int64_t n) {
+  pdl_enter();
   const float dt = coef[pick_step(step_dev, step_host) * FM_FLOWMATCH_NCOEF];
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) sched_ddpm_kernel(float* __restrict__ xo,
                                                         const float* __restrict__ coef,
                                                         const int32_t* __restrict__ step_dev, int step_host,
                                                         int clip, float cr, int64_t n) {
+  pdl_enter();
   const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_DDPM_NCOEF;
   const float sb = c[0], sa = c[1], c0 = c[2], c1 = c[3], sg = c[4];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) sched_ddim_kernel(float* __restrict__ xo,
                                                         const float* __restrict__ coef,
                                                         const int32_t* __restrict__ step_dev, int step_host,
                                                         int clip, float cr, int64_t n) {
+  pdl_enter();
   const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_DDIM_NCOEF;
   const float sb = c[0], sa = c[1], sp = c[2], dc = c[3];
   const int64_t n4 = n >> 2;
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(256) sched_dpmpp_kernel(float* __restrict__ xo
                                                          const float* __restrict__ coef,
                                                          const int32_t* __restrict__ step_dev, int step_host,
                                                          int64_t n) {
+  pdl_enter();
   const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_DPMPP_NCOEF;
   const float ss = c[0], as = c[1], c1 = c[2], c2 = c[3], c3 = c[4], ir = c[5];
   const bool second = c[6] != 0.0f, raw = c[7] != 0.0f;
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(256) sched_unipc_kernel(float* __restrict__ xo
                                                          const float* __restrict__ coef,
                                                          const int32_t* __restrict__ step_dev, int step_host,
                                                          int64_t n) {
+  pdl_enter();
   const float* c = coef + (size_t)pick_step(step_dev, step_host) * FM_UNIPC_NCOEF;
   UniPCCoef k;
   k.sg = c[0]; k.al = c[1]; k.corr = c[2] != 0.0f; k.ca = c[3]; k.cb = c[4]; k.cc = c[5]; k.corr2 = c[6] != 0.0f;
@@ -187,10 +192,14 @@ __global__ void __launch_bounds__(256) add_noise_kernel(float* __restrict__ xo, 
   }
 }
 
-__global__ void counter_add_kernel(int32_t* ctr, int32_t delta) { *ctr += delta; }
+__global__ void counter_add_kernel(int32_t* ctr, int32_t delta) {
+  pdl_enter();
+  *ctr += delta;
+}
 
 __global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ y, const float* __restrict__ x, float lo,
                                                    float hi, int64_t n) {
+  pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = fminf(fmaxf(x[i], lo), hi);
@@ -200,6 +209,7 @@ __global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ y, const
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ t_table,
                                           const int32_t* __restrict__ step_dev, float* __restrict__ out, int B,
                                           int dim, float neg_log_period, int flip, float denom) {
+  pdl_enter();
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * dim) return;
@@ -221,6 +231,7 @@ __global__ void __launch_bounds__(128) linear_f32_kernel(const float* __restrict
                                                         const float* __restrict__ bias,
                                                         const float* __restrict__ bias2, float* __restrict__ y,
                                                         int B, int I, int O, int silu_in, int silu_out, int rows) {
+  pdl_enter();
   extern __shared__ float sx[];  // [rows][I]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.x * 4 + warp;
@@ -299,40 +310,54 @@ __global__ void weight_prepack_dgrad_kernel(__nv_bfloat16* __restrict__ dst, con
 
 // Batched form of the two pack kernels above: every conv weight of a training step (forward matrices and data-gradient
 // matrices) re-packed from the fp32 master parameters in ONE launch.  Blocks are pre-assigned to (entry, offset) pairs
-// on the host; an entry is one K segment of one packed matrix.
-constexpr int kPackPerBlock = 256 * 16;
+// on the host; an entry is one K segment of one packed matrix and the offset counts (matrix row, channel) PAIRS: a
+// thread owns one pair and walks its ksize^2 taps, which lie contiguously in the OIHW source - the nine loads of a lane
+// hit the same one or two sectors (a thread per destination element fetched every source sector nine times).
+constexpr int kPackPerBlock = 256 * 4;
+template <int TAPS>
+__device__ __forceinline__ void pack_pair(const fm_pack_entry& e, uint32_t j) {
+  const float* __restrict__ src = reinterpret_cast<const float*>(e.src);
+  __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
+  const uint32_t cin_total = (uint32_t)e.Cin_total, c_begin = (uint32_t)e.c_begin;
+  if (e.mode == 0) {  // forward: dst[co][koff + tap * Cseg + c] = w[co][c_begin + c][tap]
+    const uint32_t cseg = (uint32_t)e.Cseg, co = j / cseg, c = j - co * cseg;
+    const float* sp = src + ((size_t)co * cin_total + c_begin + c) * TAPS;
+    __nv_bfloat16* dp = dst + (int64_t)co * e.dst_row_stride + e.koff + c;
+    float v[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) v[t] = sp[t];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) dp[(size_t)t * cseg] = __float2bfloat16_rn(v[t]);
+  } else {            // dgrad: dst[ci][tap' * Cout + co] = w[co][c_begin + ci][taps - 1 - tap']
+    const uint32_t cout = (uint32_t)e.Cout, ci = j / cout, co = j - ci * cout;
+    const float* sp = src + ((size_t)co * cin_total + c_begin + ci) * TAPS;
+    __nv_bfloat16* dp = dst + (size_t)ci * TAPS * cout + co;
+    float v[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) v[t] = sp[t];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) dp[(size_t)t * cout] = __float2bfloat16_rn(v[TAPS - 1 - t]);
+  }
+}
+
 __global__ void __launch_bounds__(256) weight_prepack_batch_kernel(const fm_pack_entry* __restrict__ entries,
                                                                    const int32_t* __restrict__ block_entry,
                                                                    const int64_t* __restrict__ block_offset) {
   const fm_pack_entry e = entries[block_entry[blockIdx.x]];
-  const int64_t base = block_offset[blockIdx.x];
-  const int taps = e.ksize * e.ksize;
-  const int64_t total = (int64_t)e.Cout * taps * e.Cseg;
-  const float* __restrict__ src = reinterpret_cast<const float*>(e.src);
-  __nv_bfloat16* __restrict__ dst = reinterpret_cast<__nv_bfloat16*>(e.dst);
   // 32-bit index arithmetic (a conv weight has < 2^31 elements; 64-bit divisions were ~90 % of this kernel's time)
-  const uint32_t total32 = (uint32_t)total, cseg = (uint32_t)e.Cseg, utaps = (uint32_t)taps, cout = (uint32_t)e.Cout;
-  const uint32_t cin_total = (uint32_t)e.Cin_total, c_begin = (uint32_t)e.c_begin;
-#pragma unroll 4
-  for (int k = 0; k < 16; ++k) {
-    const uint32_t i = (uint32_t)base + k * 256 + threadIdx.x;
-    if (i >= total32) break;
-    if (e.mode == 0) {  // forward: dst[co][koff + tap * Cseg + c] = w[co][c_begin + c][tap]
-      const uint32_t q = i / cseg, c = i - q * cseg;
-      const uint32_t co = q / utaps, tap = q - co * utaps;
-      dst[(int64_t)co * e.dst_row_stride + e.koff + tap * cseg + c] =
-          __float2bfloat16_rn(src[((size_t)co * cin_total + c_begin + c) * utaps + tap]);
-    } else {            // dgrad: dst[ci][tap' * Cout + co] = w[co][c_begin + ci][taps - 1 - tap']
-      const uint32_t q = i / cout, co = i - q * cout;
-      const uint32_t ci = q / utaps, tap = q - ci * utaps;
-      dst[i] = __float2bfloat16_rn(src[((size_t)co * cin_total + c_begin + ci) * utaps + (utaps - 1 - tap)]);
-    }
+  const uint32_t base = (uint32_t)block_offset[blockIdx.x], pairs = (uint32_t)e.Cout * (uint32_t)e.Cseg;
+#pragma unroll
+  for (int k = 0; k < kPackPerBlock / 256; ++k) {
+    const uint32_t j = base + k * 256 + threadIdx.x;
+    if (j >= pairs) break;
+    if (e.ksize == 3) pack_pair<9>(e, j); else pack_pair<1>(e, j);
   }
 }
 
 // ---- nearest 2x upsample, NHWC bf16, 16 B per thread -----------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B,
                                                         int H, int W, int C8) {
+  pdl_enter();
   const int64_t total = (int64_t)B * (2 * H) * (2 * W) * C8;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -348,6 +373,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
 // ---- [B][R][C] -> [B][C][R] bf16 ------------------------------------------------------------------------------
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int R,
                                       int C) {
+  pdl_enter();
   __shared__ __nv_bfloat16 tile[32][33];
   const int b = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -383,7 +409,7 @@ extern "C" int fm_sched_flowmatch_f32(float* x_out, const float* x, const float*
   FM_REQUIRE((((uintptr_t)x_out | (uintptr_t)x | (uintptr_t)v) & 15) == 0, "flowmatch: pointers must be 16B aligned");
   FM_REQUIRE(step_dev != nullptr || step_host >= 0, "flowmatch: negative step");
   if (n == 0) return 0;
-  sched_flowmatch_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, x, v, coef, step_dev,
+  launch_pdl(sched_flowmatch_kernel, dim3(ew_blocks(n / 4 + 1)), dim3(256), 0, (cudaStream_t)stream, x_out, x, v, coef, step_dev,
                                                                                  step_host, n);
   FM_LAUNCH_CHECK("sched_flowmatch_kernel");
   return 0;
@@ -397,7 +423,7 @@ extern "C" int fm_sched_ddim_f32(float* x_out, const float* x, const float* eps,
   FM_REQUIRE((((uintptr_t)x_out | (uintptr_t)x | (uintptr_t)eps) & 15) == 0, "ddim: pointers must be 16B aligned");
   FM_REQUIRE(step_dev != nullptr || step_host >= 0, "ddim: negative step");
   if (n == 0) return 0;
-  sched_ddim_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, x, eps, coef, step_dev, step_host,
+  launch_pdl(sched_ddim_kernel, dim3(ew_blocks(n / 4 + 1)), dim3(256), 0, (cudaStream_t)stream, x_out, x, eps, coef, step_dev, step_host,
                                                                             clip, clip_range, n);
   FM_LAUNCH_CHECK("sched_ddim_kernel");
   return 0;
@@ -410,7 +436,7 @@ extern "C" int fm_sched_ddpm_f32(float* x_out, const float* x, const float* eps,
   FM_REQUIRE(x_out && x && eps && noise && coef && n >= 0, "ddpm: null pointer or negative n");
   FM_REQUIRE(step_dev != nullptr || step_host >= 0, "ddpm: negative step");
   if (n == 0) return 0;
-  sched_ddpm_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x_out, x, eps, noise, coef, step_dev, step_host,
+  launch_pdl(sched_ddpm_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x_out, x, eps, noise, coef, step_dev, step_host,
                                                                     clip, clip_range, n);
   FM_LAUNCH_CHECK("sched_ddpm_kernel");
   return 0;
@@ -425,7 +451,7 @@ extern "C" int fm_sched_dpmpp2m_f32(float* x_out, float* m_cur, const float* x, 
              "dpmpp2m: pointers must be 16B aligned");
   FM_REQUIRE(step_dev != nullptr || step_host >= 0, "dpmpp2m: negative step");
   if (n == 0) return 0;
-  sched_dpmpp_kernel<<<ew_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(x_out, m_cur, x, eps, m_prev, coef,
+  launch_pdl(sched_dpmpp_kernel, dim3(ew_blocks(n / 4 + 1)), dim3(256), 0, (cudaStream_t)stream, x_out, m_cur, x, eps, m_prev, coef,
                                                                              step_dev, step_host, n);
   FM_LAUNCH_CHECK("sched_dpmpp_kernel");
   return 0;
@@ -438,7 +464,7 @@ extern "C" int fm_sched_unipc_f32(float* x_out, float* last, float* m1, float* m
   FM_REQUIRE(x_out && last && m1 && m2 && x && eps && coef && n >= 0, "unipc: null pointer or negative n");
   FM_REQUIRE(step_dev != nullptr || step_host >= 0, "unipc: negative step");
   if (n == 0) return 0;
-  sched_unipc_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x_out, last, m1, m2, x, eps, coef, step_dev,
+  launch_pdl(sched_unipc_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x_out, last, m1, m2, x, eps, coef, step_dev,
                                                                      step_host, n);
   FM_LAUNCH_CHECK("sched_unipc_kernel");
   return 0;
@@ -458,7 +484,7 @@ extern "C" int fm_sched_add_noise_f32(float* x_out, const float* x0, const float
 extern "C" int fm_counter_add(int32_t* ctr, int32_t delta, fm_stream_t stream) {
   if (int e = ensure_device()) return e;
   FM_REQUIRE(ctr != nullptr, "counter_add: null counter");
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctr, delta);
+  launch_pdl(counter_add_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, ctr, delta);
   FM_LAUNCH_CHECK("counter_add_kernel");
   return 0;
 }
@@ -467,7 +493,7 @@ extern "C" int fm_clamp_f32(float* y, const float* x, float lo, float hi, int64_
   if (int e = ensure_device()) return e;
   FM_REQUIRE(y && x && n >= 0, "clamp: bad argument");
   if (n == 0) return 0;
-  clamp_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(y, x, lo, hi, n);
+  launch_pdl(clamp_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, y, x, lo, hi, n);
   FM_LAUNCH_CHECK("clamp_kernel");
   return 0;
 }
@@ -484,7 +510,7 @@ extern "C" int fm_timestep_embedding_f32(const float* t, const float* t_table, c
   if (denom < 1.0f) denom = 1.0f;
   const float nlp = (float)(-log((double)max_period));
   const int total = B * dim;
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, t_table, step_dev, out, B, dim,
+  launch_pdl(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, (cudaStream_t)stream, t, t_table, step_dev, out, B, dim,
                                                                                    nlp, flip_sin_to_cos, denom);
   FM_LAUNCH_CHECK("timestep_embedding_kernel");
   return 0;
@@ -507,7 +533,7 @@ extern "C" int fm_linear_f32(const float* x, const float* W, const float* bias, 
                                                 kLinSmemMax), "linear attr")) return e;
     attr = true;
   }
-  linear_f32_kernel<<<(O + 3) / 4, 128, smem, (cudaStream_t)stream>>>(x, W, bias, bias2, y, B, I, O, silu_in,
+  launch_pdl(linear_f32_kernel, dim3((O + 3) / 4), dim3(128), smem, (cudaStream_t)stream, x, W, bias, bias2, y, B, I, O, silu_in,
                                                                       silu_out, rows);
   FM_LAUNCH_CHECK("linear_f32_kernel");
   return 0;
@@ -572,7 +598,7 @@ extern "C" int fm_upsample_nearest2x_bf16(const void* x, void* out, int32_t B, i
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample: bad shape (C %% 8 != 0?)");
   const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x),
+  launch_pdl(upsample2x_kernel, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(x),
                                                                         reinterpret_cast<uint4*>(out), B, H, W, C / 8);
   FM_LAUNCH_CHECK("upsample2x_kernel");
   return 0;
@@ -582,7 +608,7 @@ extern "C" int fm_transpose_bf16(const void* x, void* out, int32_t B, int32_t R,
   if (int e = ensure_device()) return e;
   FM_REQUIRE(x && out && B > 0 && R > 0 && C > 0, "transpose: bad shape");
   dim3 grid((C + 31) / 32, (R + 31) / 32, B), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_pdl(transpose_bf16_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                                  reinterpret_cast<__nv_bfloat16*>(out), R, C);
   FM_LAUNCH_CHECK("transpose_bf16_kernel");
   return 0;

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __res
                                                              const uint4* __restrict__ x1, int c81, int64_t HW,
                                                              int groups, float* __restrict__ partial,
                                                              int64_t pix_per_block) {
+  pdl_enter();
   extern __shared__ float sm[];  // [ppi][C][2]
   const int tpp = c80 + c81;     // 8-channel chunks per pixel
   const int C = tpp * 8;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const uint4* __res
 // stats[n][g] = (mean, rstd) from the per-block partial sums, accumulated in fp64 in a fixed order
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, int groups, double inv_cnt, float eps,
                                    float* __restrict__ stats) {
+  pdl_enter();
   const int n = blockIdx.x;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double s = 0.0, q = 0.0;
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(128) gn_finalize_partials_kernel(const float* 
                                                                   const float* __restrict__ beta,
                                                                   const float* __restrict__ scale_shift,
                                                                   int64_t ss_stride, float* __restrict__ ab) {
+  pdl_enter();
   __shared__ double ss[128], sq[128];
   __shared__ float s_mean, s_rstd;
   const int g = blockIdx.x, n = blockIdx.y;
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(256) gn_affine_kernel(const float* __restrict_
                                                        const float* __restrict__ beta,
                                                        const float* __restrict__ scale_shift, int64_t ss_stride,
                                                        int C, int groups, float* __restrict__ ab) {
+  pdl_enter();
   const int n = blockIdx.x;
   const int cg = C / groups;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -182,6 +186,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
                                                              const float* __restrict__ scale_shift,
                                                              int64_t ss_stride, int silu, uint4* __restrict__ out,
                                                              int64_t pix_per_block) {
+  pdl_enter();
   extern __shared__ float sm[];  // a[C], b[C]
   const int tpp = c80 + c81;
   const int C = tpp * 8;
@@ -291,12 +296,12 @@ extern "C" int fm_groupnorm_stats_bf16(const void* x0, int32_t C0, const void* x
   const int gx = gn_grid(B, HW, tpp, &ppb);
   const int ppi = kGnThreads / tpp;
   const size_t smem = (size_t)ppi * (C0 + C1) * 2 * sizeof(float);
-  gn_stats_kernel<<<dim3(gx, B), kGnThreads, smem, (cudaStream_t)stream>>>(
+  launch_pdl(gn_stats_kernel, dim3(gx, B), dim3(kGnThreads), smem, (cudaStream_t)stream, 
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, workspace,
       ppb);
   FM_LAUNCH_CHECK("gn_stats_kernel");
   const double inv_cnt = 1.0 / ((double)HW * (double)((C0 + C1) / groups));
-  gn_finalize_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(workspace, gx, groups, inv_cnt, eps, stats);
+  launch_pdl(gn_finalize_kernel, dim3(B), dim3(64), 0, (cudaStream_t)stream, workspace, gx, groups, inv_cnt, eps, stats);
   FM_LAUNCH_CHECK("gn_finalize_kernel");
   return 0;
 }
@@ -313,7 +318,7 @@ extern "C" int fm_groupnorm_finalize_partials(const float* p0, int32_t rows0, in
              "gn_finalize_partials: channels per group (%d/%d) must be a multiple of 4", C, groups);
   FM_REQUIRE(B > 0 && B <= 65535 && HW > 0 && stats != nullptr, "gn_finalize_partials: bad argument");
   const double inv_cnt = 1.0 / ((double)HW * (double)(C / groups));
-  gn_finalize_partials_kernel<<<dim3(groups, B), 128, 0, (cudaStream_t)stream>>>(
+  launch_pdl(gn_finalize_partials_kernel, dim3(groups, B), dim3(128), 0, (cudaStream_t)stream, 
       p0, rows0, C0 / 4, p1, rows1, C1 / 4, groups, inv_cnt, eps, stats, nullptr, nullptr, nullptr, 0, nullptr);
   FM_LAUNCH_CHECK("gn_finalize_partials_kernel");
   return 0;
@@ -333,7 +338,7 @@ extern "C" int fm_groupnorm_finalize_partials_affine(const float* p0, int32_t ro
              "gn_finalize_partials_affine: channels per group (%d/%d) must be a multiple of 4", C, groups);
   FM_REQUIRE(B > 0 && B <= 65535 && HW > 0 && gamma && beta && ab, "gn_finalize_partials_affine: bad argument");
   const double inv_cnt = 1.0 / ((double)HW * (double)(C / groups));
-  gn_finalize_partials_kernel<<<dim3(groups, B), 128, 0, (cudaStream_t)stream>>>(
+  launch_pdl(gn_finalize_partials_kernel, dim3(groups, B), dim3(128), 0, (cudaStream_t)stream, 
       p0, rows0, C0 / 4, p1, rows1, C1 / 4, groups, inv_cnt, eps, stats, gamma, beta, scale_shift, ss_stride, ab);
   FM_LAUNCH_CHECK("gn_finalize_partials_kernel");
   return 0;
@@ -346,7 +351,7 @@ extern "C" int fm_groupnorm_affine_f32(const float* stats, const float* gamma, c
   FM_REQUIRE(stats && gamma && beta && ab, "groupnorm_affine: null pointer");
   FM_REQUIRE(B > 0 && C > 0 && groups > 0 && C % groups == 0, "groupnorm_affine: bad shape B=%d C=%d groups=%d", B, C,
              groups);
-  gn_affine_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(stats, gamma, beta, scale_shift, ss_stride, C, groups, ab);
+  launch_pdl(gn_affine_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, stats, gamma, beta, scale_shift, ss_stride, C, groups, ab);
   FM_LAUNCH_CHECK("gn_affine_kernel");
   return 0;
 }
@@ -363,7 +368,7 @@ extern "C" int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x
   int64_t ppb;
   const int gx = gn_grid(B, HW, tpp, &ppb);
   const size_t smem = (size_t)(C0 + C1) * 2 * sizeof(float);
-  gn_apply_kernel<<<dim3(gx, B), kGnThreads, smem, (cudaStream_t)stream>>>(
+  launch_pdl(gn_apply_kernel, dim3(gx, B), dim3(kGnThreads), smem, (cudaStream_t)stream, 
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, stats,
       gamma, beta, scale_shift, ss_stride, silu, reinterpret_cast<uint4*>(out), ppb);
   FM_LAUNCH_CHECK("gn_apply_kernel");

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -55,6 +56,15 @@ int ensure_device() {
 }
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FMDM_PDL");
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral-to-negative on the power-capped loops
+  }
+  return on == 1;
+}
 
 }  // namespace fm
 

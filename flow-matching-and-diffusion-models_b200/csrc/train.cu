@@ -33,6 +33,7 @@ constexpr int kTicketInts = 4096;
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                int parts, int64_t inner, float* __restrict__ out2,
                                                                int64_t split) {
+  pdl_enter();
   __shared__ float sh[8][33];
   const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
   const int64_t o = blockIdx.y;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 static int launch_reduce(const float* in, float* out, int64_t outer, int parts, int64_t inner, cudaStream_t st,
                          float* out2 = nullptr, int64_t split = 0) {
   if (outer * inner == 0) return 0;
-  reduce_partials_kernel<<<dim3((unsigned)((inner + 31) / 32), (unsigned)outer), dim3(32, 8), 0, st>>>(
+  launch_pdl(reduce_partials_kernel, dim3((unsigned)((inner + 31) / 32), (unsigned)outer), dim3(32, 8), 0, st, 
       in, out, parts, inner, out2, split);
   FM_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
@@ -248,6 +249,7 @@ constexpr int kWrCi = 64;
 __global__ void __launch_bounds__(192) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
                                                             int splits, int taps, int Cout, int Cin, int cin_total,
                                                             int c_begin) {
+  pdl_enter();
   __shared__ float tile[kWrCi * 9];
   const int co = blockIdx.y, ci0 = blockIdx.x * kWrCi;
   const int nci = Cin - ci0 < kWrCi ? Cin - ci0 : kWrCi;
@@ -257,7 +259,15 @@ __global__ void __launch_bounds__(192) wgrad_reduce_kernel(const float* __restri
     if (i >= nci) continue;
     const float* src = part + ((int64_t)tap * Cout + co) * Cin + ci0 + i;
     float acc = 0.f;
-    for (int sp = 0; sp < splits; ++sp) acc += src[(int64_t)sp * per];
+    int sp = 0;
+    for (; sp + 8 <= splits; sp += 8) {  // eight independent loads in flight, summed in the same fixed order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(src + (int64_t)(sp + u) * per);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; sp < splits; ++sp) acc += __ldcs(src + (int64_t)sp * per);
     tile[i * taps + tap] = acc;
   }
   __syncthreads();
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(192) wgrad_reduce_kernel(const float* __restri
 
 static void launch_wgrad_reduce(const float* part, float* dw, int splits, int taps, int Cout, int Cin, int cin_total,
                                 int c_begin, cudaStream_t st) {
-  wgrad_reduce_kernel<<<dim3((Cin + kWrCi - 1) / kWrCi, Cout), 192, 0, st>>>(part, dw, splits, taps, Cout, Cin,
+  launch_pdl(wgrad_reduce_kernel, dim3((Cin + kWrCi - 1) / kWrCi, Cout), dim3(192), 0, st, part, dw, splits, taps, Cout, Cin,
                                                                              cin_total, c_begin);
 }
 
@@ -292,6 +302,7 @@ static int wgrad_plan(int B, int Ho, int Wo, int Cin, int Cout, int ksize, int* 
 // thread = (8-channel group, row lane) as in the GroupNorm passes: 16-byte loads, four in flight per thread
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const uint4* __restrict__ dy, float* __restrict__ part,
                                                               int64_t HW, int C8, int lanes, int rows_per_blk) {
+  pdl_enter();
   extern __shared__ float cred[];  // [lanes][C]
   const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
@@ -336,6 +347,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const uint4* __rest
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, float* out,
                                                             float* __restrict__ total, int B, int nblk, int C, int ld,
                                                             int* tickets) {
+  pdl_enter();
   __shared__ float sh[8][33];
   __shared__ int s_last;
   const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
@@ -369,6 +381,7 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 // =============================================================================================================
 __global__ void __launch_bounds__(256) zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                              int B, int H, int W, int C8) {
+  pdl_enter();
   const int64_t total = (int64_t)B * 2 * H * 2 * W * C8;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -385,7 +398,8 @@ __global__ void __launch_bounds__(256) zero_insert2x_kernel(const uint4* __restr
 }
 
 __global__ void __launch_bounds__(256) sumpool2x2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
-                                                          int B, int H, int W, int C8) {  // H, W: output size
+                                                          int B, int H, int W, int C8) {
+  pdl_enter();  // H, W: output size
   const int64_t total = (int64_t)B * H * W * C8;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -491,6 +505,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_partial_kernel(const uint4* __r
                                                               const uint4* __restrict__ x1, const uint4* __restrict__ da,
                                                               float* part, int64_t HW, int C8, int lanes,
                                                               int rows_per_blk, int silu, GnBwdTail tl) {
+  pdl_enter();
   extern __shared__ float red[];  // [lanes][C8*16], reused by the tail as [4][C]
   __shared__ int s_last;
   const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
@@ -663,6 +678,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const uint4* __res
                                                             const float* __restrict__ dgb_part,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             int B) {
+  pdl_enter();
   // colpart (optional): per-block column sums of dx, [B][nblk][C] -- the bias / time-embedding-add gradient of the conv
   // that produced x, so that conv's backward needs no column-sum pass over dx
   extern __shared__ float cred[];  // [lanes][C8*8], only when colpart != NULL
@@ -1566,7 +1582,7 @@ static int launch_colsum_final(const float* part, float* out, float* total, int 
                                cudaStream_t st) {
   FM_REQUIRE(total == nullptr || tickets != nullptr, "colsum: the batch total needs the ticket buffer");
   FM_REQUIRE((C + 31) / 32 <= kTicketInts - kTicketCols, "colsum: too many channels");
-  colsum_final_kernel<<<dim3((C + 31) / 32, B), dim3(32, 8), 0, st>>>(part, out, total, B, nblk, C, ld, tickets);
+  launch_pdl(colsum_final_kernel, dim3((C + 31) / 32, B), dim3(32, 8), 0, st, part, out, total, B, nblk, C, ld, tickets);
   FM_LAUNCH_CHECK("colsum_final_kernel");
   return 0;
 }
@@ -1583,7 +1599,7 @@ extern "C" int fm_colsum_bf16(const void* dy, float* workspace, float* out, floa
   const int C8 = C / 8;
   const int lanes = C8 >= 256 ? 1 : 256 / C8;
   const int threads = ((C8 * lanes + 31) / 32) * 32;
-  colsum_partial_kernel<<<dim3(nblk, B), threads, (size_t)lanes * C * sizeof(float), st>>>(
+  launch_pdl(colsum_partial_kernel, dim3(nblk, B), dim3(threads), (size_t)lanes * C * sizeof(float), st, 
       reinterpret_cast<const uint4*>(dy), workspace, HW, C8, lanes, rows);
   FM_LAUNCH_CHECK("colsum_partial_kernel");
   return launch_colsum_final(workspace, out, total, B, nblk, C, C, tickets, st);
@@ -1595,7 +1611,7 @@ extern "C" int fm_zero_insert2x_bf16(const void* x, void* out, int32_t B, int32_
   FM_REQUIRE(x && out && C % 8 == 0, "zero_insert2x: null pointer or C not a multiple of 8");
   const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
   if (total == 0) return 0;
-  zero_insert2x_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x),
+  launch_pdl(zero_insert2x_kernel, dim3(ew_grid(total)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(x),
                                                                        reinterpret_cast<uint4*>(out), B, H, W, C / 8);
   FM_LAUNCH_CHECK("zero_insert2x_kernel");
   return 0;
@@ -1608,7 +1624,7 @@ extern "C" int fm_sumpool2x2_bf16(const void* x, void* out, int32_t B, int32_t H
   FM_REQUIRE(x && out && C % 8 == 0, "sumpool2x2: null pointer or C not a multiple of 8");
   const int64_t total = (int64_t)B * H * W * (C / 8);
   if (total == 0) return 0;
-  sumpool2x2_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x),
+  launch_pdl(sumpool2x2_kernel, dim3(ew_grid(total)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(x),
                                                                     reinterpret_cast<uint4*>(out), B, H, W, C / 8);
   FM_LAUNCH_CHECK("sumpool2x2_kernel");
   return 0;
@@ -1848,12 +1864,12 @@ extern "C" int fm_groupnorm_bwd_bf16(const void* x0, int32_t C0, const void* x1,
   tl.tickets = tickets, tl.B = B;
   size_t smem1 = (size_t)lanes * C8 * 16 * sizeof(float);
   if (smem1 < (size_t)4 * C * sizeof(float)) smem1 = (size_t)4 * C * sizeof(float);
-  gn_bwd_partial_kernel<<<dim3(nblk, B), sthreads, smem1, st>>>(
+  launch_pdl(gn_bwd_partial_kernel, dim3(nblk, B), dim3(sthreads), smem1, st, 
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
       reinterpret_cast<const uint4*>(dout), part, HW, C8, lanes, rows, silu, tl);
   FM_LAUNCH_CHECK("gn_bwd_partial_kernel");
   auto apply = (add0_a || add1) ? gn_bwd_apply_kernel<true> : gn_bwd_apply_kernel<false>;
-  apply<<<dim3(nblk, B), sthreads, dx_colsum_partials ? (size_t)lanes * C * sizeof(float) : 0, st>>>(
+  launch_pdl(apply, dim3(nblk, B), dim3(sthreads), dx_colsum_partials ? (size_t)lanes * C * sizeof(float) : 0, st,
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1),
       reinterpret_cast<const uint4*>(dout), tab, reinterpret_cast<uint4*>(dx0), reinterpret_cast<uint4*>(dx1), HW, C8,
       lanes, rows, silu, dx_colsum_partials, reinterpret_cast<const uint4*>(add0_a),

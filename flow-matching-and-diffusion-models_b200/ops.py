@@ -293,13 +293,15 @@ def stem_im2col(x0, x1, *, in_scale=1.0, in_shift=0.0, kp: Optional[int] = None)
 
 
 def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0, want_stats: bool = True,
-              packed: Optional[PackedConvWeight] = None) -> torch.Tensor:
+              packed: Optional[PackedConvWeight] = None, tensor_cores: bool = False) -> torch.Tensor:
     """fp32 NCHW (x0 [, x1]) -> bf16 NHWC, 3x3 s1 p1; fuses the conditioning concat and the 2x-1 centering.
 
     want_stats: also emit the GroupNorm partial statistics of the output (`out._fm_stats`, as `conv2d` does).
-    packed (`stem_pack(weight)`): on large inputs the conv runs on the tensor cores - `fm_stem_im2col_bf16` writes the
-    3x3 neighbourhoods as a [B][H][W][Kp] bf16 tensor and the 1x1 implicit GEMM contracts it (store-bandwidth bound
-    instead of fp32-FMA bound); small inputs keep the fp32 CUDA-core kernel."""
+    packed (`stem_pack(weight)`): on large inputs the conv runs on the tensor cores (bf16-rounded inputs and weights):
+    `fm_conv_stem_tc_f32_bf16` in one launch for Cout 64 / 128 and Cin <= 3, otherwise `fm_stem_im2col_bf16` writes the
+    3x3 neighbourhoods as a [B][H][W][Kp] bf16 tensor and the 1x1 implicit GEMM contracts it; store-bandwidth bound
+    instead of fp32-FMA bound.  Small inputs (and packed=None) keep the fp32 CUDA-core kernel.
+    tensor_cores=True allows the one-launch kernel without a packed matrix (the training forward)."""
     lib = _lib.lib()
     require_cuda(x0, "conv_stem")
     x0 = x0.to(torch.float32).contiguous()
@@ -309,6 +311,26 @@ def conv_stem(x0, x1, weight_oihw, bias, *, in_scale=1.0, in_shift=0.0, want_sta
         x1 = x1.to(torch.float32).contiguous()
         c1 = x1.shape[1]
     cout = weight_oihw.shape[0]
+    tc_rows = 0
+    if (packed is not None or tensor_cores) and b * h * w >= STEM_TENSOR_MIN_PIXELS:
+        tc_rows = int(lib.fm_conv_stem_tc_stats_rows(b, h, w, c0 + c1, cout))
+    if tc_rows > 0:  # one launch: mma.sync fragments gathered from a shared-memory halo tile
+        out = empty_nhwc(b, cout, h, w, x0.device)
+        stats_ws = None
+        if want_stats:
+            stats_ws = torch.empty((b * tc_rows, cout // 4, 2), dtype=torch.float32, device=x0.device)
+        e0 = _prof_begin()
+        _lib.check(
+            lib.fm_conv_stem_tc_f32_bf16(
+                x0.data_ptr(), c0, _ptr(x1), c1, float(in_scale), float(in_shift), weight_oihw.data_ptr(), _ptr(bias),
+                out.data_ptr(), b, h, w, cout, _ptr(stats_ws), _stream(),
+            ),
+            "conv_stem_tc",
+        )
+        _prof_end("conv_stem", 2.0 * b * h * w * (c0 + c1) * 9 * cout, e0)
+        if stats_ws is not None:
+            out._fm_stats = (stats_ws, tc_rows)
+        return out
     if packed is not None and b * h * w >= STEM_TENSOR_MIN_PIXELS and 9 * (c0 + c1) <= 72:
         kp = packed.seg_channels[0]
         cols = empty_nhwc(b, kp, h, w, x0.device)

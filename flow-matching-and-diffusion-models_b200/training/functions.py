@@ -963,7 +963,8 @@ class _StemFn(Function):
         x1 = None if x1 is None else x1.detach().float().contiguous()
         w32 = weight.detach().float().contiguous()
         out = ops.conv_stem(x0, x1, w32, None if bias is None else bias.detach().float().contiguous(),
-                            in_scale=in_scale, in_shift=in_shift, want_stats=True)
+                            in_scale=in_scale, in_shift=in_shift, want_stats=True,
+                            tensor_cores=SMALL_CONVS_ON_TENSOR_CORES)
         ctx.cfg = (float(in_scale), float(in_shift), x1 is not None, bias is not None, tuple(weight.shape))
         ctx.wb = (weight, bias)
         ctx.save_for_backward(x0, *([x1] if x1 is not None else []))

@@ -110,8 +110,8 @@ class PackPlan:
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
         blk_e, blk_o = [], []
         for i, e in enumerate(self.entries):
-            total = e.Cout * e.ksize * e.ksize * e.Cseg
-            for off in range(0, total, per_block):
+            pairs = e.Cout * e.Cseg  # a thread packs the ksize^2 taps of one (matrix row, channel) pair
+            for off in range(0, pairs, per_block):
                 blk_e.append(i)
                 blk_o.append(off)
         self._tables = (raw, torch.tensor(blk_e, dtype=torch.int32, device=device),

@@ -128,6 +128,16 @@ int fm_conv_stem_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t 
                           int32_t W, int32_t Cout, float* gn_stats, fm_stream_t stream);
 /* rows of statistics partials per image the stem kernel writes for this problem size (0 = unsupported) */
 int fm_conv_stem_stats_rows(int32_t B, int32_t H, int32_t W, int32_t Cout);
+/* Stem on the tensor cores in ONE launch (Cout 64 | 128, 9*Cin + 2 <= 32, i.e. Cin <= 3): same arguments and result
+ * layout as fm_conv_stem_f32_bf16, inputs and weights rounded to bf16 (fp32 accumulation, bias exact to 2^-17 as two
+ * bf16 k-columns), `mma.sync` fragments gathered from a shared-memory halo tile, no im2col tensor.  gn_stats (or NULL):
+ * fp32 [B * fm_conv_stem_tc_stats_rows(...)][Cout/4][2].  FM_ERR_UNSUPPORTED outside the covered shapes.  Replaces
+ * conv_in of src/models/unet/unet_diffusers_nd.py:148-158,173 on large inputs. */
+int fm_conv_stem_tc_f32_bf16(const float* x0, int32_t C0, const float* x1, int32_t C1, float in_scale, float in_shift,
+                             const float* weight_oihw, const float* bias, void* out_nhwc_bf16, int32_t B, int32_t H,
+                             int32_t W, int32_t Cout, float* gn_stats, fm_stream_t stream);
+/* rows of statistics partials per image fm_conv_stem_tc_f32_bf16 writes (0 = shape not covered by that kernel) */
+int fm_conv_stem_tc_stats_rows(int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
 /* Stem on the tensor cores, step 1 (large inputs): the 3x3 neighbourhoods of the fp32 NCHW inputs (same x0 / x1 /
  * in_scale / in_shift meaning as fm_conv_stem_f32_bf16) as a bf16 NHWC tensor out[B][H][W][Kp], column ci*9 + kh*3 + kw
  * (zero beyond 9*Cin; Kp a multiple of 8, <= 72).  Step 2 is fm_conv2d_igemm_bf16 as a 1x1 conv over it with the
@@ -271,8 +281,9 @@ int fm_weight_prepack_dgrad_bf16(void* dst, const float* src_oihw, int32_t Cout,
                                  int32_t Cseg, int32_t ksize, fm_stream_t stream);
 /* One launch for every weight pack of a training step.  An entry is one K segment of one packed matrix: mode 0 =
  * fm_weight_prepack_bf16 arguments, mode 1 = fm_weight_prepack_dgrad_bf16 arguments (dst_row_stride / koff unused).
- * The host pre-assigns blocks: block b packs elements [block_offset[b], block_offset[b] +
- * fm_weight_prepack_batch_block_elems()) of entry block_entry[b] (element count = Cout * ksize^2 * Cseg). */
+ * The host pre-assigns blocks: block b packs the (matrix row, channel) pairs [block_offset[b], block_offset[b] +
+ * fm_weight_prepack_batch_block_elems()) of entry block_entry[b] (pair count = Cout * Cseg; a pair = its ksize^2
+ * taps, contiguous in the OIHW source). */
 typedef struct fm_pack_entry {
   const void* src;          /* fp32 OIHW (or [O][I]) master weight */
   void* dst;                /* bf16 packed matrix base */

@@ -395,6 +395,32 @@ def test_conv_head_dot_kernel(cin, H, W, norm):
     assert _rel_l2(out, ref) < (2e-3 if norm else 1e-4)
 
 
+@pytest.mark.parametrize("cin,H,W,silu,wscale", [(128, 130, 70, True, 1 / 20), (64, 200, 129, True, 1 / 20),
+                                                 (128, 128, 64, False, 1 / 20), (128, 33, 200, True, 3e-7),
+                                                 (64, 17, 130, False, 4e3), (128, 160, 66, True, 0.0)])
+def test_conv_head_tensor_core_kernel(cin, H, W, silu, wscale):
+    """Cout = 1 head with the fused output norm: phase 1 on `mma.sync` (fp16 operands, power-of-two weight scaling).
+    Both tile heights, ragged tiles, with / without SiLU, weights far outside fp16's range, and an all-zero conv_out
+    (the reference zero-initialises it)."""
+    g = torch.Generator().manual_seed(71)
+    B = 2
+    x = _bf16r(torch.randn(B, cin, H, W, generator=g) * 1.3 + 0.2).to(DEV)
+    wh = (torch.randn(1, cin, 3, 3, generator=g) * wscale).to(DEV)
+    bh = (torch.randn(1, generator=g) * max(wscale, 1e-9) * 20).to(DEV)
+    ab = torch.empty(B, 2, cin)
+    ab[:, 0] = torch.rand(B, cin, generator=g) + 0.5
+    ab[:, 1] = torch.randn(B, cin, generator=g) * 0.5
+    ab = ab.to(DEV)
+    y = x * ab[:, 0, :, None, None] + ab[:, 1, :, None, None]
+    ref = F.conv2d(F.silu(y) if silu else y, wh, bh, padding=1)
+    out = ops.conv_head(_nhwc(x), wh, bh, norm=ops.NormTable(ab, silu))
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    if wscale == 0.0:
+        assert torch.equal(out, ref)
+    else:
+        assert _rel_l2(out, ref) < 2e-3
+
+
 def test_stem_fused_groupnorm_statistics():
     """GroupNorm table from the stem kernel's partial statistics == table from a statistics pass over its output."""
     g = torch.Generator().manual_seed(12)
@@ -414,9 +440,11 @@ def test_stem_fused_groupnorm_statistics():
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout", [(1, 512, 512, 2, 128), (6, 256, 200, 1, 128), (2, 300, 444, 4, 64),
-                                             (1, 512, 520, 8, 256)])
+                                             (1, 512, 520, 8, 256), (3, 300, 444, 3, 64), (2, 515, 300, 2, 64),
+                                             (17, 128, 136, 2, 128)])
 def test_stem_tensor_core_path(B, H, W, cin, cout):
-    """conv_in on large inputs = `fm_stem_im2col_bf16` + the 1x1 implicit GEMM: against F.conv2d on the bf16-rounded
+    """conv_in on large inputs: ONE `mma.sync` launch (`fm_conv_stem_tc_f32_bf16`: Cout 64 / 128, Cin <= 3) or
+    `fm_stem_im2col_bf16` + the 1x1 implicit GEMM: against F.conv2d on the bf16-rounded
     operands (tight) and on the fp32 operands (bf16 rounding of inputs and weights only), with the 2x-1 centering, the
     fused conditioning concat and the GroupNorm partial statistics of the output."""
     g = torch.Generator().manual_seed(17)
@@ -431,7 +459,8 @@ def test_stem_tensor_core_path(B, H, W, cin, cout):
     for scale, shift in ((1.0, 0.0), (2.0, -1.0)):
         n0 = ops.launch_count()
         y = ops.conv_stem(x0, x1, w, b, in_scale=scale, in_shift=shift, packed=packed)
-        assert ops.launch_count() - n0 == 2                      # im2col + one GEMM launch
+        one_launch = cin <= 3 and cout in (64, 128)
+        assert ops.launch_count() - n0 == (1 if one_launch else 2)   # else: im2col + one GEMM launch
         ref32 = F.conv2d(full * scale + shift, w, b, padding=1)
         ref16 = F.conv2d(_bf16r(full * scale + shift), _bf16r(w), b, padding=1)
         assert y.shape == ref32.shape and y.dtype == torch.bfloat16

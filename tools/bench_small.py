@@ -37,6 +37,8 @@ def main():
     b = torch.randn(128, device=dev)
     res["stem_ms"] = timeit(lambda: ops.conv_stem(x0, x1, w, b), flush)
     res["stem_nostats_ms"] = timeit(lambda: ops.conv_stem(x0, x1, w, b, want_stats=False), flush)
+    res["stem_tc_ms"] = timeit(lambda: ops.conv_stem(x0, x1, w, b, tensor_cores=True), flush)
+    res["stem_tc_nostats_ms"] = timeit(lambda: ops.conv_stem(x0, x1, w, b, want_stats=False, tensor_cores=True), flush)
     y = ops.conv_stem(x0, x1, w, b)
     gamma = torch.randn(128, device=dev)
     beta = torch.randn(128, device=dev)
