@@ -147,10 +147,32 @@ __device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
   return y;
 }
 
+// 2^x for a pair of scores WITHOUT the special-function unit (the FlashAttention-4 trick): x <= 0 is clamped at -30
+// (2^-30 is zero in fp16; also maps the -inf of masked keys to zero), split as n + f with the 1.5*2^23 magic-number
+// rounding (n integer, |f| <= 0.5), 2^f by a minimax cubic (relative error 7.5e-5, fp16 keeps 4.9e-4) on packed fp32
+// FMAs, and 2^n applied by adding n to the exponent field.  The hd-8 loop does one MUFU per score and the MUFU pipe
+// (16 / clk / SM) is its ceiling; moving a share of the exponentials to the FMA pipe trades MUFU cycles for issue slots.
+__device__ __forceinline__ uint32_t ex2_poly_f16x2(float lo, float hi) {
+  const float2 x = make_float2(fmaxf(lo, -30.f), fmaxf(hi, -30.f));
+  const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = fadd2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 p = ffma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  p = ffma2(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = ffma2(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  const float rl = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+  const float rh = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+  uint32_t y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(rh), "f"(rl));
+  return y;
+}
+
 // F16P = true: probabilities as packed halves (11 significant bits instead of bf16's 8).  Per 16 keys and thread: no
 // row-sum adds (the row sums come from one extra MMA against a ones matrix, which also folds the four lanes of a
 // row) and P V as ONE m16n8k16 (V staged as fp16).  The loop is issue-bound, so the instruction count is what matters.
-template <bool F16P>
+// POLY (F16P only): how many of the four probability pairs per 16 keys take the FMA-pipe exponential (0, 1 or 2).
+constexpr int kAtt8PolyDefault = 0;
+template <bool F16P, int POLY>
 __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     __nv_bfloat16* __restrict__ out, int Tq, int Tk, int64_t q_sb, int64_t q_sh, int64_t q_st, int64_t kv_sb,
@@ -238,8 +260,10 @@ __global__ void __launch_bounds__(kAtt8Threads) attention_hd8_mma_kernel(
           const float2 e2 = ffma2(make_float2(s[j + 1][0], s[j + 1][1]), sc, n0);
           const float2 e3 = ffma2(make_float2(s[j + 1][2], s[j + 1][3]), sc, n1);
           // A fragment of m16n8k16: (row g, keys 2t..), (row g+8, keys 2t..), (row g, keys 8+2t..), (row g+8, keys 8+2t..)
-          const uint32_t pa0 = ex2_f16x2(e0.x, e0.y), pa1 = ex2_f16x2(e1.x, e1.y);
-          const uint32_t pa2 = ex2_f16x2(e2.x, e2.y), pa3 = ex2_f16x2(e3.x, e3.y);
+          const uint32_t pa0 = ex2_f16x2(e0.x, e0.y);
+          const uint32_t pa1 = POLY >= 2 ? ex2_poly_f16x2(e1.x, e1.y) : ex2_f16x2(e1.x, e1.y);
+          const uint32_t pa2 = ex2_f16x2(e2.x, e2.y);
+          const uint32_t pa3 = POLY >= 1 ? ex2_poly_f16x2(e3.x, e3.y) : ex2_f16x2(e3.x, e3.y);
           const __half* vt = reinterpret_cast<const __half*>(sVt) + g * kAtt8VtStride + kb0 + j * 8 + 2 * t;
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vt), b1 = *reinterpret_cast<const uint32_t*>(vt + 8);
           mma_m16n8k16_f16(o, pa0, pa1, pa2, pa3, b0, b1);
@@ -698,7 +722,11 @@ extern "C" int fm_attention_bf16(const void* q, const void* k, const void* v, vo
       dim3 grid((Tq + kAtt8Warps * 16 - 1) / (kAtt8Warps * 16), heads, B);
       // FMDM_ATTENTION_BF16P=1: the first-generation inner loop (scalar fp32 exponentials, bf16 probabilities), A/B only
       static const bool bf16p = getenv("FMDM_ATTENTION_BF16P") != nullptr;
-      auto kern = bf16p ? attention_hd8_mma_kernel<false> : attention_hd8_mma_kernel<true>;
+      // FMDM_ATTENTION_POLY=0|1|2: share of the exponentials on the FMA pipe (0, 1/4, 1/2); A/B switch
+      static const int poly = getenv("FMDM_ATTENTION_POLY") ? atoi(getenv("FMDM_ATTENTION_POLY")) : kAtt8PolyDefault;
+      auto kern = bf16p ? attention_hd8_mma_kernel<false, 0>
+                        : (poly >= 2 ? attention_hd8_mma_kernel<true, 2>
+                                     : (poly == 1 ? attention_hd8_mma_kernel<true, 1> : attention_hd8_mma_kernel<true, 0>));
       launch_pdl(kern, grid, dim3(kAtt8Threads), 0, st,
           reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
           reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), Tq, Tk, q_sb, q_sh, q_st,

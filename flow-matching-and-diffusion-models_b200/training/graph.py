@@ -219,8 +219,8 @@ def resblock(blk, x: torch.Tensor, emb) -> torch.Tensor:
         raise RuntimeError("fmdm_b200.training: unsupported ResBlockND variant")
     c, oc = blk.channels, blk.out_channels
     xs = list(x) if isinstance(x, (tuple, list)) else [x]   # (hidden, skip): the decoder concat stays virtual
-    if len(xs) == 2 and any((t.shape[1] * blk.norm1.num_groups) % c for t in xs):
-        xs = [torch.cat(xs, 1)]                               # a group would straddle the two sources
+    if len(xs) == 2 and any(t.shape[1] % 8 for t in xs):
+        xs = [torch.cat(xs, 1)]                               # the two-source kernels take 8-channel granules
     h = _gn(blk.norm1, xs if len(xs) == 2 else xs[0], silu=True)
     addvec = scale_shift = None
     if blk.uses_embedding:
