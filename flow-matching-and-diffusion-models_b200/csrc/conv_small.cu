@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(kHmThreads, 2) conv_head_mma_kernel(const uint
   float* P = reinterpret_cast<float*>(hm_smem);              // [9][kPix]
   float* sab = P + 9 * kPix;                                 // [2][C]: a, b (pre-halved for SiLU)
   uint32_t* smax = reinterpret_cast<uint32_t*>(sab + 2 * C); // [8]
+  uint4* sbf = reinterpret_cast<uint4*>(smax + 8);           // [NBLK][2 n-tiles][32 lanes] weight fragments
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int w0 = blockIdx.x * kHmTW, h0 = blockIdx.y * TH, n = blockIdx.z;
@@ -477,33 +478,50 @@ __global__ void __launch_bounds__(kHmThreads, 2) conv_head_mma_kernel(const uint
   se = se < 1 ? 1 : (se > 253 ? 253 : se);
   const float S = __uint_as_float((uint32_t)se << 23), invS = __uint_as_float((uint32_t)(254 - se) << 23);
 
-  // weight fragments: (blk, s) covers channels blk*32 + 8q + 4s + {0..3} in this lane; column n = g is tap g
-  uint32_t bf[NBLK][2][2], bf8[NBLK][2][2];
+  // weight fragments: (blk, s) covers channels blk*32 + 8q + 4s + {0..3} in this lane; column n = g is tap g.  They
+  // live in shared memory (one 16-byte read per lane, block and n-tile: conflict-free) so that the registers hold the
+  // NEXT group's sixteen 16-byte loads while the current group is transformed and multiplied.
 #pragma unroll
-  for (int blk = 0; blk < NBLK; ++blk)
+  for (int blk = 0; blk < NBLK; ++blk) {
+    uint32_t f[4], f8[4];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const float* wc = w_oihw + (blk * 32 + q * 8 + 4 * s) * 9;
-      bf[blk][s][0] = pack_f16x2_sat(S * __ldg(wc + g), S * __ldg(wc + 9 + g));
-      bf[blk][s][1] = pack_f16x2_sat(S * __ldg(wc + 18 + g), S * __ldg(wc + 27 + g));
-      bf8[blk][s][0] = g == 0 ? pack_f16x2_sat(S * __ldg(wc + 8), S * __ldg(wc + 9 + 8)) : 0u;
-      bf8[blk][s][1] = g == 0 ? pack_f16x2_sat(S * __ldg(wc + 18 + 8), S * __ldg(wc + 27 + 8)) : 0u;
+      f[2 * s + 0] = pack_f16x2_sat(S * __ldg(wc + g), S * __ldg(wc + 9 + g));
+      f[2 * s + 1] = pack_f16x2_sat(S * __ldg(wc + 18 + g), S * __ldg(wc + 27 + g));
+      f8[2 * s + 0] = g == 0 ? pack_f16x2_sat(S * __ldg(wc + 8), S * __ldg(wc + 9 + 8)) : 0u;
+      f8[2 * s + 1] = g == 0 ? pack_f16x2_sat(S * __ldg(wc + 18 + 8), S * __ldg(wc + 27 + 8)) : 0u;
     }
+    if (warp == 0) {
+      sbf[(blk * 2 + 0) * 32 + lane] = make_uint4(f[0], f[1], f[2], f[3]);
+      sbf[(blk * 2 + 1) * 32 + lane] = make_uint4(f8[0], f8[1], f8[2], f8[3]);
+    }
+  }
+  __syncthreads();
 
-  for (int grp = warp; grp < kGroups; grp += kHmThreads / 32) {
+  auto load_group = [&](int grp, uint4 (&v0)[NBLK], uint4 (&v1)[NBLK], bool& in0, bool& in1) {
     const int pi0 = grp * 16 + g, pi1 = pi0 + 8;
     const int ph0 = pi0 / kWP, pw0 = pi0 - ph0 * kWP, ph1 = pi1 / kWP, pw1 = pi1 - ph1 * kWP;
     const int ih0 = h0 + ph0 - 1, iw0 = w0 + pw0 - 1, ih1 = h0 + ph1 - 1, iw1 = w0 + pw1 - 1;
-    const bool in0 = pi0 < kPix && (unsigned)ih0 < (unsigned)H && (unsigned)iw0 < (unsigned)W;
-    const bool in1 = pi1 < kPix && (unsigned)ih1 < (unsigned)H && (unsigned)iw1 < (unsigned)W;
+    in0 = pi0 < kPix && (unsigned)ih0 < (unsigned)H && (unsigned)iw0 < (unsigned)W;
+    in1 = pi1 < kPix && (unsigned)ih1 < (unsigned)H && (unsigned)iw1 < (unsigned)W;
     const uint4* r0 = x + (((size_t)n * H + (in0 ? ih0 : 0)) * W + (in0 ? iw0 : 0)) * LPP + q;
     const uint4* r1 = x + (((size_t)n * H + (in1 ? ih1 : 0)) * W + (in1 ? iw1 : 0)) * LPP + q;
-    uint4 v0[NBLK], v1[NBLK];
 #pragma unroll
     for (int blk = 0; blk < NBLK; ++blk) {
       v0[blk] = in0 ? __ldg(r0 + blk * 4) : make_uint4(0, 0, 0, 0);
       v1[blk] = in1 ? __ldg(r1 + blk * 4) : make_uint4(0, 0, 0, 0);
     }
+  };
+
+  uint4 v0[NBLK], v1[NBLK];
+  bool in0 = false, in1 = false;
+  if (warp < kGroups) load_group(warp, v0, v1, in0, in1);
+  for (int grp = warp; grp < kGroups; grp += kHmThreads / 32) {
+    uint4 nv0[NBLK], nv1[NBLK];
+    bool nin0 = false, nin1 = false;
+    if (grp + kHmThreads / 32 < kGroups) load_group(grp + kHmThreads / 32, nv0, nv1, nin0, nin1);
+    const int pi0 = grp * 16 + g, pi1 = pi0 + 8;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc8[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int blk = 0; blk < NBLK; ++blk) {
@@ -519,10 +537,11 @@ __global__ void __launch_bounds__(kHmThreads, 2) conv_head_mma_kernel(const uint
       const uint32_t x02 = xf_word_f16<kSilu>(v0[blk].z, a45, b45), x03 = xf_word_f16<kSilu>(v0[blk].w, a67, b67);
       const uint32_t x10 = xf_word_f16<kSilu>(v1[blk].x, a01, b01), x11 = xf_word_f16<kSilu>(v1[blk].y, a23, b23);
       const uint32_t x12 = xf_word_f16<kSilu>(v1[blk].z, a45, b45), x13 = xf_word_f16<kSilu>(v1[blk].w, a67, b67);
-      mma_m16n8k16_f16(acc, x00, x10, x01, x11, bf[blk][0][0], bf[blk][0][1]);
-      mma_m16n8k16_f16(acc8, x00, x10, x01, x11, bf8[blk][0][0], bf8[blk][0][1]);
-      mma_m16n8k16_f16(acc, x02, x12, x03, x13, bf[blk][1][0], bf[blk][1][1]);
-      mma_m16n8k16_f16(acc8, x02, x12, x03, x13, bf8[blk][1][0], bf8[blk][1][1]);
+      const uint4 bf = sbf[(blk * 2 + 0) * 32 + lane], bf8 = sbf[(blk * 2 + 1) * 32 + lane];
+      mma_m16n8k16_f16(acc, x00, x10, x01, x11, bf.x, bf.y);
+      mma_m16n8k16_f16(acc8, x00, x10, x01, x11, bf8.x, bf8.y);
+      mma_m16n8k16_f16(acc, x02, x12, x03, x13, bf.z, bf.w);
+      mma_m16n8k16_f16(acc8, x02, x12, x03, x13, bf8.z, bf8.w);
     }
     // zero padding applies AFTER the activation: an out-of-image pixel contributes nothing
     if (pi0 < kPix) {
@@ -535,6 +554,9 @@ __global__ void __launch_bounds__(kHmThreads, 2) conv_head_mma_kernel(const uint
       P[(2 * q + 1) * kPix + pi1] = in1 ? acc[3] : 0.f;
       if (q == 0) P[8 * kPix + pi1] = in1 ? acc8[2] : 0.f;
     }
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk) { v0[blk] = nv0[blk]; v1[blk] = nv1[blk]; }
+    in0 = nin0, in1 = nin1;
   }
   __syncthreads();
   const float bv = bias ? __ldg(bias) : 0.f;
@@ -555,7 +577,7 @@ template <int C, int TH, bool kSilu>
 static int launch_head_mma(const void* x, const float* w, const float* bias, float* out, int B, int H, int W,
                            const float* norm_ab, cudaStream_t st) {
   constexpr int kPix = (TH + 2) * (kHmTW + 2);
-  constexpr int smem = (9 * kPix + 2 * C + 8) * 4;
+  constexpr int smem = (9 * kPix + 2 * C + 8) * 4 + (C / 32) * 2 * 32 * 16;
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_head_mma_kernel<C, TH, kSilu>,

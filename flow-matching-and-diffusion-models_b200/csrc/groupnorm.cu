@@ -190,7 +190,11 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
   extern __shared__ float sm[];  // a[C], b[C]
   const int tpp = c80 + c81;
   const int C = tpp * 8;
-  const int n = blockIdx.y;
+  // Block order: the producer conv wrote the tensor row chunk by row chunk over all images, so its LAST rows are what
+  // the L2 still holds - walk the pixel ranges from the end, images innermost, and read them before this kernel's own
+  // stream evicts them (the consumer conv then starts at the rows written last here)
+  const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+  const int n = lin % (int)gridDim.y, bx = (int)gridDim.x - 1 - lin / (int)gridDim.y;
   float* sa = sm;
   float* sb = sm + C;
   const int cg = C / groups;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = sa[chunk * 8 + j]; b[j] = sb[chunk * 8 + j]; }
-  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_begin = (int64_t)bx * pix_per_block;
   int64_t p_end = p_begin + pix_per_block;
   if (p_end > HW) p_end = HW;
   const int64_t base = (int64_t)n * HW;

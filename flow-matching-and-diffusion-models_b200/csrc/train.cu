@@ -508,7 +508,11 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_partial_kernel(const uint4* __r
   pdl_enter();
   extern __shared__ float red[];  // [lanes][C8*16], reused by the tail as [4][C]
   __shared__ int s_last;
-  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  // Block order: dOut was just written by the data-gradient conv row chunk by row chunk over all images, so its last
+  // rows are what the L2 still holds: walk the row blocks from the end, images innermost (the apply pass then walks
+  // them from the start and finds the rows this pass read last)
+  const int nblk = gridDim.x, lin = blockIdx.y * nblk + blockIdx.x;
+  const int b = lin % (int)gridDim.y, blk = nblk - 1 - lin / (int)gridDim.y;
   const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
   const int C = C8 * 8;
   const int cpg = C / tl.groups;
@@ -682,7 +686,9 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const uint4* __res
   // colpart (optional): per-block column sums of dx, [B][nblk][C] -- the bias / time-embedding-add gradient of the conv
   // that produced x, so that conv's backward needs no column-sum pass over dx
   extern __shared__ float cred[];  // [lanes][C8*8], only when colpart != NULL
-  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  // row blocks from the start, images innermost: the rows the partial pass read last are still in the L2
+  const int nblk = gridDim.x, lin = blockIdx.y * nblk + blockIdx.x;
+  const int b = lin % (int)gridDim.y, blk = lin / (int)gridDim.y;
   const int c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
   const int C = C8 * 8;
   float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};

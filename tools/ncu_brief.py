@@ -12,7 +12,14 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fma.sum",
         "sm__inst_executed_pipe_alu.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-        "lts__t_bytes.sum", "sm__cycles_elapsed.avg.per_second"]
+        "lts__t_bytes.sum", "sm__cycles_elapsed.avg.per_second",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 
 
 def main():
