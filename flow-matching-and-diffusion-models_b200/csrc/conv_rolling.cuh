@@ -77,7 +77,6 @@ struct RollSched {
   int chunks;   // row chunks per image
   int combos;   // (image, w-tile) combinations, padded to even so the two strips of a pair share their row chunk
   int pairs;    // strip pairs = chunks * combos / 2
-  int rev;      // 1: walk the units from the last to the first ("serpentine" over consecutive launches, see launch)
 };
 
 template <int BLOCK_N, int XF, int OB>
@@ -143,7 +142,6 @@ conv_rolling_kernel(const __grid_constant__ ConvKernelParams p, const RollSched 
   const int unit_stride = (int)gridDim.x >> 1;
   // this CTA's strip of a unit: 128 pixels starting at w0 of rows [h_begin, h_end) of image n
   auto strip_coords = [&](int unit, int& tw, int& w0, int& n, int& h_begin, int& h_end, int& ncol0) {
-    if (sch.rev) unit = total_units - 1 - unit;
     const int ps = unit / p.n_tiles;
     ncol0 = (unit - ps * p.n_tiles) * BLOCK_N;
     const int sid = ps * 2 + (int)cta_rank;
@@ -516,13 +514,11 @@ static RollSched roll_schedule(int B, int Ho, int tiles_w, int n_tiles, int sm_p
     const double cost = (double)rounds * (R + 0.25 * 2.0);
     if (cost < best_cost * 0.96) {
       best_cost = cost;
-      best = RollSched{R, chunks, combos, pairs, 0};
+      best = RollSched{R, chunks, combos, pairs};
     }
   }
   return best;
 }
-
-static int g_roll_flip = 0;  // direction of the next rolling-row launch (all template variants share it)
 
 template <int BLOCK_N, int XF, int OB>
 static int launch_conv_rolling(const ConvKernelParams& kp, const RollSched& sch, cudaStream_t st) {
@@ -537,13 +533,6 @@ static int launch_conv_rolling(const ConvKernelParams& kp, const RollSched& sch,
   const int units = sch.pairs * kp.n_tiles;
   int ctas = (sm_count() / 2) * 2;
   if (ctas > units * 2) ctas = units * 2;
-  // Serpentine: a conv writes its output strip by strip and the next conv of the chain reads that tensor, so the rows
-  // written LAST are the ones the 126 MB L2 still holds.  Consecutive launches walk their units in opposite directions:
-  // each starts where its producer stopped (a tenth of a 1.07 GB level-0 tensor is served from L2 instead of HBM,
-  // which under the 1 kW cap is also energy).  The result does not depend on the order.  FMDM_CONV_SERPENTINE=0: off.
-  static const bool serpentine = !(getenv("FMDM_CONV_SERPENTINE") && getenv("FMDM_CONV_SERPENTINE")[0] == '0');
-  RollSched sched = sch;
-  if (serpentine) sched.rev = (g_roll_flip ^= 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ctas);
@@ -559,7 +548,7 @@ static int launch_conv_rolling(const ConvKernelParams& kp, const RollSched& sch,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_rolling_kernel<BLOCK_N, XF, OB>, kp, sched);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_rolling_kernel<BLOCK_N, XF, OB>, kp, sch);
   count_launch();
   if (e != cudaSuccess) return check_cuda(e, "cudaLaunchKernelEx(conv_rolling)");
   return 0;
