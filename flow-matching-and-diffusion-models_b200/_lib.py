@@ -75,6 +75,7 @@ SIGNATURES = {
     "fm_version": (C.c_int, []),
     "fm_last_error": (C.c_char_p, []),
     "fm_launch_count": (C.c_longlong, []),
+    "fm_set_pdl": (C.c_int, [C.c_int]),
     "fm_conv2d_igemm_bf16": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "fm_conv_kernel_kind": (C.c_int, [C.POINTER(ConvParams)]),
     "fm_conv_operand_norm_supported": (C.c_int, [_i32, _i32, _i32, _i32]),

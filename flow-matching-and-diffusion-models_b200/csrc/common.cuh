@@ -46,10 +46,12 @@ int wgrad_tc_max_splits(int B, int Ho, int Wo, int Cin, int Cout, int ksize);
 // follows: (1) pdl_wait() precedes the first global-memory access of every thread, reads and writes alike (the kernel
 // before may still be reading what this one overwrites), and is executed by every CTA; (2) pdl_trigger() early, so the
 // successor can start its own set-up.  A kernel launched without the attribute (plain <<<>>>) serialises as always and
-// the two instructions are no-ops in it, so converted and unconverted kernels mix freely.  The attribute is OPT-IN
-// (FMDM_PDL=1): same-box A/B on the B200 showed the 50-step LDCT-512 loop 1.7 % slower with it (9.95 vs 10.12
-// samples/s; kernels of 0.2-1.7 ms leave nothing to hide and the early-resident CTAs cost power under the 1 kW cap)
-// and the training step unchanged (37.4 vs 37.2 ms), so the default launch is the plain one.
+// the two instructions are no-ops in it, so converted and unconverted kernels mix freely.  The attribute is set only
+// where it pays: same-box A/B on the B200 showed the 50-step LDCT-512 loop 1.7 % slower with it (9.95 vs 10.12
+// samples/s; kernels of 0.2-1.7 ms leave nothing to hide and the early-resident CTAs cost power under the 1 kW cap), the
+// training step unchanged (37.4 vs 37.2 ms), but MNIST-sized problems (157 kernels of 3-30 us per Euler step) 6 %
+// faster (925 vs 870 samples/s) - the sampling loop switches it on (fm_set_pdl) while it captures the graph of a small
+// problem.  FMDM_PDL=1 / 0 forces it on / off everywhere.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() {
@@ -57,10 +59,11 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_wait();
 }
 bool pdl_enabled();
+int set_pdl(int on);  // returns the previous setting (fm_set_pdl)
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              Args&&... args) {
+inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -71,10 +74,14 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = on ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  return launch_pdl_if(pdl_enabled(), kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
 // ---- small device helpers -----------------------------------------------------------------------------------
 // SiLU with ONE special-function op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32, rel. error ~2^-11, below
 // the bf16 rounding of the stored result).  The exp+rcp form needs two MUFU ops and makes K2 MUFU-bound.

@@ -57,17 +57,31 @@ int ensure_device() {
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
+// -1: FMDM_PDL unset (off unless a caller switches it on for a capture, fm_set_pdl), 0 / 1: forced by the environment
+static int pdl_env() {
+  static int env = -2;
+  if (env == -2) {
     const char* e = getenv("FMDM_PDL");
-    on = (e != nullptr && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral-to-negative on the power-capped loops
+    env = e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
   }
-  return on == 1;
+  return env;
+}
+static int g_pdl = 0;
+
+bool pdl_enabled() {
+  const int env = pdl_env();
+  return env >= 0 ? env == 1 : g_pdl == 1;
+}
+
+int set_pdl(int on) {
+  const int was = g_pdl;
+  g_pdl = on ? 1 : 0;
+  return was;
 }
 
 }  // namespace fm
 
 extern "C" int fm_version(void) { return 100; }
+extern "C" int fm_set_pdl(int on) { return fm::set_pdl(on); }
 extern "C" const char* fm_last_error(void) { return fm::g_err; }
 extern "C" long long fm_launch_count(void) { return fm::g_launches.load(std::memory_order_relaxed); }

@@ -17,6 +17,22 @@ from . import _lib
 BF16 = torch.bfloat16
 
 
+class pdl:
+    """`with ops.pdl(True): ...` - launches inside carry the programmatic-dependent-launch attribute (`fm_set_pdl`);
+    a CUDA graph captured inside keeps the programmatic edges for all its replays."""
+
+    def __init__(self, on: bool):
+        self.on, self._was = bool(on), 0
+
+    def __enter__(self):
+        self._was = int(_lib.lib().fm_set_pdl(int(self.on)))
+        return self
+
+    def __exit__(self, *exc):
+        _lib.lib().fm_set_pdl(self._was)
+        return False
+
+
 def _stream() -> int:
     """Raw handle of torch's current stream on the CURRENT device.  Every entry point checks (`require_cuda`) that its
     tensors live on that device: the C-ABI launches on the current device, so a tensor of another GPU would otherwise

@@ -37,6 +37,12 @@ int fm_version(void);
 const char* fm_last_error(void);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 long long fm_launch_count(void);
+/* Programmatic dependent launch (PDL) for the launches that follow: a kernel may become resident while its predecessor
+ * in the stream still runs and waits (griddepcontrol.wait) before its first global access.  Pays on graphs of many
+ * microsecond kernels (MNIST-sized problems: +6 %), costs on the large ones, so it is off unless the caller switches it
+ * on - the sampling loop does while it captures the graph of a small problem.  Returns the previous setting; the
+ * environment variable FMDM_PDL=0 / 1 overrides it.  Process-wide, not thread-safe (one process per GPU). */
+int fm_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K1: conv2d as implicit GEMM on tcgen05/TMEM, TMA-fed, bf16 in / fp32 accumulate / bf16 out.
