@@ -102,6 +102,11 @@ SIGNATURES = {
         C.c_int,
         [_vp, _i32, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
     ),
+    "fm_groupnorm_apply_partials_supported": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),
+    "fm_groupnorm_apply_partials_bf16": (
+        C.c_int,
+        [_vp, _i32, _vp, _i32, _i32, _i64, _i32, _vp, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
+    ),
     "fm_memset_f32": (C.c_int, [_vp, _i64, _vp]),
     "fm_upsample_nearest2x_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "fm_transpose_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),

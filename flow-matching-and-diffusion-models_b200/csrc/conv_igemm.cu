@@ -50,6 +50,8 @@ struct alignas(64) ConvKernelParams {
   float* gn_partial;                // [m_tiles*4][Cout/4][2] quad statistics, or null
   int log_wt, log_ht;               // Wt, Ht are powers of two
   int num_k_blocks;
+  int dup_koff;                     // per-tile kernel, split-bf16 weights: K offset of the residual (lo) half of the
+                                    // matrix - every A tile is multiplied by its hi AND lo weight tile (0: plain)
   int m_tiles, n_tiles;             // persistent kernel: real tile counts (M tiles padded to even for CTA pairs)
   // fused operand transform (XF kernels): per segment a*x+b table rows [B][.] and activation, or null
   const float* seg_na[FM_CONV_MAX_SEG];
@@ -221,13 +223,16 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
               // weight tiles of this A step: MODE 1 -> the three kw taps of row kh = as; MODE 0 -> tap = as
               int kcol = p.seg_koff[s] + ((MODE == 1) ? as * 3 : as) * C + cb * kBlockK;
               for (int bs = 0; bs < bsteps; ++bs, kcol += C) {
-                mbar_wait(b_empty(rb.idx), rb.phase ^ 1u);
-                if (arm) mbar_expect_tx(b_full(rb.idx), CG * Cfg::kBBytes);
-                if (CG == 2)
-                  tma_load_2d_pair(&p.wgt, b_full_dst0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kcol, bcol);
-                else
-                  tma_load_2d(&p.wgt, b_full_dst0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kcol, bcol);
-                rb.advance(Cfg::kBStages);
+                // [lo,] hi tile: the small residual products enter the accumulator before the large ones of the step
+                for (int kc = kcol + p.dup_koff; kc >= kcol; kc -= (p.dup_koff ? p.dup_koff : 1)) {
+                  mbar_wait(b_empty(rb.idx), rb.phase ^ 1u);
+                  if (arm) mbar_expect_tx(b_full(rb.idx), CG * Cfg::kBBytes);
+                  if (CG == 2)
+                    tma_load_2d_pair(&p.wgt, b_full_dst0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kc, bcol);
+                  else
+                    tma_load_2d(&p.wgt, b_full_dst0 + 8u * rb.idx, smem_b0 + rb.idx * Cfg::kBBytes, kc, bcol);
+                  rb.advance(Cfg::kBStages);
+                }
               }
             }
             // next A step: MODE 1 walks kh (dh), MODE 0 walks the nine taps row-major
@@ -263,7 +268,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ ConvKernelParams p) {
           for (int ac = 0; ac < asteps * cblocks; ++ac) {
             mbar_wait(a_full(ra.idx), ra.phase);
             uint32_t a_lo = a_lo0 + ra.idx * (uint32_t)(Cfg::kASlot >> 4) + a_row0;
-            for (int bs = 0; bs < bsteps; ++bs, a_lo += (uint32_t)(kARowBytes >> 4)) {
+            const int ndup = p.dup_koff ? 2 : 1;  // split-bf16 weights: the hi and the lo tile against the same A tile
+            for (int bd = 0; bd < bsteps * ndup; ++bd, a_lo += (bd % ndup == 0) ? (uint32_t)(kARowBytes >> 4) : 0u) {
               mbar_wait(b_full(rb.idx), rb.phase);
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + rb.idx * (uint32_t)(Cfg::kBBytes >> 4);
@@ -734,6 +740,22 @@ extern "C" int fm_conv2d_igemm_bf16(const fm_conv_params* p, fm_stream_t stream)
       return e;
   }
   kp.num_k_blocks = nk;
+  // Split-bf16 weights arrive as every source twice (hi segments, then the residual segments over the same tensors).
+  // The per-tile kernel multiplies each A tile by both weight tiles instead of fetching it twice: half the operand
+  // traffic of the narrow, launch-bound denoisers this mode exists for.
+  kp.dup_koff = 0;
+  if (!pl.rolling && p->nseg >= 2 && p->nseg % 2 == 0 && getenv("FMDM_CONV_NO_DUP") == nullptr) {
+    const int h = p->nseg / 2;
+    bool dup = true;
+    for (int s = 0; s < h; ++s) {
+      const fm_conv_seg &a = p->seg[s], &b = p->seg[s + h];
+      dup = dup && a.src == b.src && a.C == b.C && a.ksize == b.ksize && a.norm_a == nullptr && b.norm_a == nullptr;
+    }
+    if (dup) {
+      kp.nseg = h;
+      kp.dup_koff = ktot / 2;
+    }
+  }
   const int block_n = pl.block_n;
   if (int e = encode_wgt_map(&kp.wgt, p->weight, ktot, p->Cout, pl.pair ? block_n / 2 : block_n)) return e;
   kp.n_out = 1;

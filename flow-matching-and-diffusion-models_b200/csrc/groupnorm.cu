@@ -4,6 +4,8 @@
 // Two sources are read as a virtual channel concat (the up-path torch.cat of legacy_unet.py:150 never exists in
 // memory); the apply kernel writes the concatenated, normalised, activated tensor the consumer conv reads.
 // Reference ops replaced: nn.GroupNorm + nn.SiLU (src/nn/blocks/residual.py:95-96,113-116).
+#include <cstring>
+
 #include "common.cuh"
 
 namespace fm {
@@ -178,6 +180,16 @@ __global__ void __launch_bounds__(256) gn_affine_kernel(const float* __restrict_
   }
 }
 
+// channel-quad partial sums of the producer convs (fm_conv_params.gn_stats format), folded inside gn_apply_kernel
+constexpr int kGnMaxFusedGroups = 64;
+struct GnPartials {
+  const float* p0;
+  const float* p1;
+  int rows0, nq0, rows1, nq1;
+  double inv_cnt;
+  float eps;
+};
+
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __restrict__ x0, int c80,
                                                              const uint4* __restrict__ x1, int c81, int64_t HW,
                                                              int groups, const float* __restrict__ stats,
@@ -185,9 +197,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
                                                              const float* __restrict__ beta,
                                                              const float* __restrict__ scale_shift,
                                                              int64_t ss_stride, int silu, uint4* __restrict__ out,
-                                                             int64_t pix_per_block) {
+                                                             int64_t pix_per_block, GnPartials pt) {
   pdl_enter();
   extern __shared__ float sm[];  // a[C], b[C]
+  __shared__ float s_mr[2 * kGnMaxFusedGroups];  // (mean, rstd) per group when folded here from the conv partials
   const int tpp = c80 + c81;
   const int C = tpp * 8;
   // Block order: the producer conv wrote the tensor row chunk by row chunk over all images, so its LAST rows are what
@@ -198,10 +211,36 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const uint4* __res
   float* sa = sm;
   float* sb = sm + C;
   const int cg = C / groups;
+  if (pt.p0 != nullptr) {
+    // Small partial tables (a few KB per sample): every block folds its sample's channel-quad partials itself, in fp64
+    // and a fixed order, instead of reading statistics a finalize launch wrote - one kernel node less per GroupNorm
+    // where a kernel node is what a GroupNorm costs (MNIST-sized problems, the 16x16 level).
+    const int qpg = (pt.nq0 + pt.nq1) / groups;
+    for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+      double s = 0.0, q = 0.0;
+      for (int k = 0; k < qpg; ++k) {
+        const int qi = g * qpg + k;
+        const bool first = qi < pt.nq0;
+        const int rows = first ? pt.rows0 : pt.rows1, nq = first ? pt.nq0 : pt.nq1, ql = first ? qi : qi - pt.nq0;
+        const float* src = (first ? pt.p0 : pt.p1) + ((size_t)n * rows * nq + ql) * 2;
+        for (int r = 0; r < rows; ++r) {
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(src + (size_t)r * nq * 2));
+          s += (double)v.x;
+          q += (double)v.y;
+        }
+      }
+      const double mean = s * pt.inv_cnt;
+      double var = q * pt.inv_cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mr[2 * g] = (float)mean;
+      s_mr[2 * g + 1] = (float)(1.0 / sqrt(var + (double)pt.eps));
+    }
+    __syncthreads();
+  }
   for (int c = threadIdx.x; c < C; c += kGnThreads) {
     const int g = c / cg;
-    const float mean = stats[((size_t)n * groups + g) * 2 + 0];
-    const float rstd = stats[((size_t)n * groups + g) * 2 + 1];
+    const float mean = pt.p0 != nullptr ? s_mr[2 * g] : stats[((size_t)n * groups + g) * 2 + 0];
+    const float rstd = pt.p0 != nullptr ? s_mr[2 * g + 1] : stats[((size_t)n * groups + g) * 2 + 1];
     float a = rstd * gamma[c];
     float b = beta[c] - mean * a;
     if (scale_shift != nullptr) {
@@ -372,9 +411,50 @@ extern "C" int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x
   int64_t ppb;
   const int gx = gn_grid(B, HW, tpp, &ppb);
   const size_t smem = (size_t)(C0 + C1) * 2 * sizeof(float);
+  GnPartials none;
+  memset(&none, 0, sizeof(none));
   launch_pdl(gn_apply_kernel, dim3(gx, B), dim3(kGnThreads), smem, (cudaStream_t)stream, 
       reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups, stats,
-      gamma, beta, scale_shift, ss_stride, silu, reinterpret_cast<uint4*>(out), ppb);
+      gamma, beta, scale_shift, ss_stride, silu, reinterpret_cast<uint4*>(out), ppb, none);
+  FM_LAUNCH_CHECK("gn_apply_kernel");
+  return 0;
+}
+
+extern "C" int fm_groupnorm_apply_partials_supported(int32_t rows0, int32_t C0, int32_t rows1, int32_t C1,
+                                                     int32_t groups) {
+  const int C = C0 + C1;
+  if (rows0 <= 0 || C0 <= 0 || C0 % 8 || C1 % 8 || (C1 > 0 && rows1 <= 0) || groups <= 0 || groups > kGnMaxFusedGroups ||
+      C % groups || (C / groups) % 4)
+    return 0;
+  // every block folds the whole per-sample table: worth it only while that is a few KB
+  return ((int64_t)rows0 * C0 + (int64_t)rows1 * C1) * 2 <= 16 * 1024 ? 1 : 0;
+}
+
+extern "C" int fm_groupnorm_apply_partials_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B,
+                                                int64_t HW, int32_t groups, const float* p0, int32_t rows0,
+                                                const float* p1, int32_t rows1, float eps, const float* gamma,
+                                                const float* beta, const float* scale_shift, int64_t ss_stride,
+                                                int32_t silu, void* out, fm_stream_t stream) {
+  if (int e = ensure_device()) return e;
+  if (int e = gn_check(x0, C0, x1, C1, B, HW, groups)) return e;
+  FM_REQUIRE(p0 && gamma && beta && out && (p1 != nullptr) == (C1 > 0), "groupnorm_apply_partials: null pointer");
+  FM_REQUIRE(((uintptr_t)out & 15) == 0, "groupnorm_apply_partials: out must be 16B aligned");
+  if (!fm_groupnorm_apply_partials_supported(rows0, C0, rows1, C1, groups)) {
+    set_error("groupnorm_apply_partials: table too large or groups not made of channel quads "
+              "(fm_groupnorm_apply_partials_supported)");
+    return FM_ERR_UNSUPPORTED;
+  }
+  const int tpp = (C0 + C1) / 8;
+  int64_t ppb;
+  const int gx = gn_grid(B, HW, tpp, &ppb);
+  const size_t smem = (size_t)(C0 + C1) * 2 * sizeof(float);
+  GnPartials pt;
+  pt.p0 = p0, pt.p1 = p1, pt.rows0 = rows0, pt.nq0 = C0 / 4, pt.rows1 = rows1, pt.nq1 = C1 / 4;
+  pt.inv_cnt = 1.0 / ((double)HW * (double)((C0 + C1) / groups));
+  pt.eps = eps;
+  launch_pdl(gn_apply_kernel, dim3(gx, B), dim3(kGnThreads), smem, (cudaStream_t)stream,
+             reinterpret_cast<const uint4*>(x0), C0 / 8, reinterpret_cast<const uint4*>(x1), C1 / 8, HW, groups,
+             (const float*)nullptr, gamma, beta, scale_shift, ss_stride, silu, reinterpret_cast<uint4*>(out), ppb, pt);
   FM_LAUNCH_CHECK("gn_apply_kernel");
   return 0;
 }

@@ -495,10 +495,28 @@ def group_norm(
     b, c0, h, w = x0.shape
     c1 = x1.shape[1] if x1 is not None else 0
     ctot = c0 + c1
-    stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x0.device)
     st = _stream()
     e0 = _prof_begin()
     fused = [getattr(s, "_fm_stats", None) for s in srcs]
+    if scale_shift is not None and (scale_shift.dtype != torch.float32 or scale_shift.shape != (b, 2 * ctot)
+                                    or scale_shift.stride(1) != 1):
+        raise ValueError("group_norm: scale_shift must be fp32 [B][2C] with unit inner stride")
+    if all(f is not None for f in fused):
+        p1 = fused[1] if len(fused) == 2 else (None, 0)
+        if lib.fm_groupnorm_apply_partials_supported(fused[0][1], c0, p1[1], c1, groups):
+            # small partial tables: the apply kernel folds them itself - one kernel for the whole GroupNorm (+SiLU)
+            out = empty_nhwc(b, ctot, h, w, x0.device)
+            _lib.check(
+                lib.fm_groupnorm_apply_partials_bf16(
+                    x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, fused[0][0].data_ptr(), fused[0][1],
+                    _ptr(p1[0]), p1[1], float(eps), gamma.data_ptr(), beta.data_ptr(), _ptr(scale_shift),
+                    0 if scale_shift is None else scale_shift.stride(0), int(silu), out.data_ptr(), st,
+                ),
+                "groupnorm_apply_partials",
+            )
+            _prof_end("groupnorm", 4.0 * b * ctot * h * w, e0)
+            return out
+    stats = torch.empty((b, groups, 2), dtype=torch.float32, device=x0.device)
     if all(f is not None for f in fused) and (ctot // groups) % 4 == 0:
         # statistics were produced by the convs that wrote the sources: fold their partial sums, no extra read pass
         p1 = fused[1] if len(fused) == 2 else (None, 0)
@@ -518,9 +536,6 @@ def group_norm(
             "groupnorm_stats",
         )
     out = empty_nhwc(b, ctot, h, w, x0.device)
-    if scale_shift is not None and (scale_shift.dtype != torch.float32 or scale_shift.shape != (b, 2 * ctot)
-                                    or scale_shift.stride(1) != 1):
-        raise ValueError("group_norm: scale_shift must be fp32 [B][2C] with unit inner stride")
     _lib.check(
         lib.fm_groupnorm_apply_bf16(
             x0.data_ptr(), c0, _ptr(x1), c1, b, h * w, groups, stats.data_ptr(), gamma.data_ptr(),

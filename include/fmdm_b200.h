@@ -190,6 +190,16 @@ int fm_groupnorm_finalize_partials_affine(const float* p0, int32_t rows0, int32_
 int fm_groupnorm_apply_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
                             int32_t groups, const float* stats, const float* gamma, const float* beta,
                             const float* scale_shift, int64_t ss_stride, int32_t silu, void* out, fm_stream_t stream);
+/* The same apply with the statistics folded inside the kernel from the producer convs' channel-quad partials (p0 / p1,
+ * rows per image rows0 / rows1: the fm_conv_params.gn_stats format) - no finalize launch, no statistics tensor.  Only
+ * while the per-sample table is a few KB and the groups are made of whole quads
+ * (fm_groupnorm_apply_partials_supported != 0): the one-kernel form of nn.GroupNorm (+SiLU) for the small problems
+ * whose cost is the number of kernel nodes (src/nn/blocks/residual.py:95-96,113-116 on 14x14 / 7x7 feature maps). */
+int fm_groupnorm_apply_partials_supported(int32_t rows0, int32_t C0, int32_t rows1, int32_t C1, int32_t groups);
+int fm_groupnorm_apply_partials_bf16(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int64_t HW,
+                                     int32_t groups, const float* p0, int32_t rows0, const float* p1, int32_t rows1,
+                                     float eps, const float* gamma, const float* beta, const float* scale_shift,
+                                     int64_t ss_stride, int32_t silu, void* out, fm_stream_t stream);
 int fm_memset_f32(float* p, int64_t n, fm_stream_t stream);
 
 /* nearest-neighbour 2x upsample on NHWC bf16 (F.interpolate, src/nn/ops/upsampling.py:27) */

@@ -106,6 +106,39 @@ def test_conv2d_igemm_two_m_tiles_per_cta(case, monkeypatch):
     assert float((out - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 0.05
 
 
+@pytest.mark.parametrize("case", [
+    (3, 28, 28, [64], 64, [3], 1), (2, 14, 14, [128], 128, [3], 1), (3, 7, 7, [128, 64], 128, [3, 1], 1),
+    (2, 28, 28, [64], 128, [3], 2), (1, 16, 16, [32], 72, [1], 1), (2, 40, 36, [64, 64], 64, [3, 3], 1),
+], ids=lambda c: "B{}_{}x{}_cin{}_cout{}_k{}_s{}".format(c[0], c[1], c[2], "+".join(map(str, c[3])), c[4],
+                                                        "".join(map(str, c[5])), c[6]))
+def test_conv2d_split_weights_share_the_a_tile(case, monkeypatch):
+    """Split-bf16 weights (w_hi + w_lo along K) on the per-tile kernel: each A tile is multiplied by its hi and its lo
+    weight tile (`dup_koff`) instead of being fetched once per half.  Equal to the two-pass form (FMDM_CONV_NO_DUP=1)
+    up to the order of the fp32 accumulation, and much closer to the fp32-weight reference than plain bf16 weights."""
+    B, H, W, cins, cout, ks, stride = case
+    g = torch.Generator(device="cpu").manual_seed(9)
+    xs = [_bf16r(torch.randn(B, c, H, W, generator=g)).to(DEV) for c in cins]
+    ws = [(torch.randn(cout, c, k, k, generator=g) / math.sqrt(c * k * k)).to(DEV) for c, k in zip(cins, ks)]
+    bvec = torch.randn(cout, generator=g).to(DEV)
+    ref = bvec.view(1, -1, 1, 1)
+    for x, w, k in zip(xs, ws, ks):
+        ref = ref + F.conv2d(x, w, None, stride=stride, padding=k // 2)
+    srcs = [_nhwc(x) for x in xs]
+    parts = [(w, 0, c) for w, c in zip(ws, cins)]
+    split = ops.pack_conv_weight(parts, split=True)
+    plain = ops.pack_conv_weight(parts)
+    assert split.split
+    out = ops.conv2d(srcs, split, stride=stride, bias=bvec).float()
+    monkeypatch.setenv("FMDM_CONV_NO_DUP", "1")
+    two_pass = ops.conv2d(srcs, split, stride=stride, bias=bvec).float()
+    monkeypatch.delenv("FMDM_CONV_NO_DUP")
+    out_plain = ops.conv2d(srcs, plain, stride=stride, bias=bvec).float()
+    assert _rel_l2(out, two_pass) < 2e-3                      # both carry the bf16 rounding of the OUTPUT only
+    assert _rel_l2(out, ref) < 3e-3                           # output rounding (2^-9) dominates
+    # against the un-rounded output the weight error is gone: compare in fp32 through the rounding of the reference
+    assert _rel_l2(out, _bf16r(ref)) < 0.7 * _rel_l2(out_plain, _bf16r(ref)) + 2e-4
+
+
 ROLLING_CASES = [c for c in CONV_CASES if c[6] == 1 and c[2] > 64 and c[5][0] == 3] + [
     (2, 37, 128, [64], 64, [3], 1, True, True, True),
     (3, 70, 200, [128, 64], 128, [3, 3], 1, True, True, False),
