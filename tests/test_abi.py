@@ -82,3 +82,21 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setenv("FMDM_B200_LIB", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="not built"):
         _lib.lib()
+
+
+def test_pdl_switch_is_scoped(monkeypatch):
+    """`ops.pdl` sets the programmatic-dependent-launch mode for the launches inside and restores what was there
+    (host-side state only: works without a GPU); nested scopes unwind in order."""
+    from fmdm_b200 import _lib, ops
+
+    handle = _lib.lib()
+    start = handle.fm_set_pdl(0)
+    try:
+        with ops.pdl(True):
+            assert handle.fm_set_pdl(1) == 1          # on inside the scope (the call returns the previous setting)
+            with ops.pdl(False):
+                assert handle.fm_set_pdl(0) == 0
+            assert handle.fm_set_pdl(1) == 1          # the inner scope restored "on"
+        assert handle.fm_set_pdl(0) == 0              # the outer scope restored "off"
+    finally:
+        handle.fm_set_pdl(start)
