@@ -449,7 +449,9 @@ def test_cross_attention_conditioning_parity(name, cfg):
                       weights_only=False)
     with torch.no_grad():
         out = model(gold["x"].to(DEV), gold["t"].to(DEV), context_ca=gold["context_ca"].to(DEV))
-    assert rel_l2(out.cpu(), gold["out"]) < TOL_STEP  # measured 0.56 / 0.97 / 0.90e-2 (split-bf16 weights, <= 128 ch)
+    # measured 0.544 / 0.953 / 0.909e-2 (split-bf16 weights, <= 128 channels; 0.518 / 0.917 / 0.882e-2 when every A tile
+    # is fetched once per weight half, FMDM_CONV_NO_DUP=1 - the shared-A form costs ~4 % of the error budget)
+    assert rel_l2(out.cpu(), gold["out"]) < TOL_STEP
 
 
 def test_context_kv_kernel():
